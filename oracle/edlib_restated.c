@@ -1,0 +1,152 @@
+/*
+ * oracle/edlib_restated.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the one third-party primitive on specimux's hot path:
+ * edlib.align(query, target, mode, task='locations', k, additionalEqualities)
+ * as specimux calls it from src/specimux/alignment.py:42 (HW / SHW) and
+ * src/specimux/orchestration.py:552 (NW, task="distance").
+ *
+ * edlib itself (Martinsos/edlib, pinned only as `edlib>=1.1.2` in the
+ * reference's pyproject.toml:28; latest line 1.3.9) is NOT vendored in
+ * /root/reference and is not installable here (no network).  This file restates
+ * its *published* semantics with a plain O(m*n) Levenshtein DP -- deliberately
+ * not a bit-vector algorithm, so it shares no structure (and no bugs) with the
+ * CUDA Myers kernels it checks:
+ *
+ *   E(a,b)   := a == b, or (a,b) / (b,a) listed in additionalEqualities
+ *               (symmetric, NOT transitive, case-sensitive)
+ *   D[i][0]  = i ;  D[0][j] = 0 (HW) | j (SHW, NW)
+ *   D[i][j]  = min(D[i-1][j-1] + !E(q[i-1],t[j-1]), D[i-1][j] + 1, D[i][j-1] + 1)
+ *   HW/SHW   : best = min_j D[m][j] over j = 1..n  (plus j = 0, i.e. end -1, only
+ *              when m is not a multiple of 64: edlib reads the last row through
+ *              W = 64 - m%64 wildcard padding rows, which exposes column 0)
+ *              best > k (k >= 0)  ->  editDistance -1, no locations
+ *              ends = ascending [ j-1 : D[m][j] == best ]
+ *              SHW starts = 0 ; HW start(e) = e - (LAST best end of the reverse SHW
+ *              pass rev(q) vs rev(t[0..e]) with k = best), i.e. the longest
+ *              alignment ending at e ; start(-1) = 0
+ *   NW       : editDistance = D[m][n] ; one location (0, n-1)
+ *   m == 0 or n == 0 : HW/SHW editDistance = m, one end location -1, no start
+ *                      (caller clamps by k: alignment.py:44-46) ;
+ *                      NW editDistance = max(m, n)
+ *
+ * Parity status: pinned through the reference's own integration fixture (all
+ * distances + primer end positions of 40 reads; see tests/golden/).  HW *start*
+ * tie-break, SHW end lists and NW distances are "oracle-derived" (unpinned by
+ * any reference test).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MODE_NW 0
+#define ORC_MODE_SHW 1
+#define ORC_MODE_HW 2
+
+/* 256x256 equality matrix from a list of (a,b) pairs; identity always included. */
+void orc_build_equality(const unsigned char *pairs, int npairs, unsigned char *table /* 65536 */)
+{
+    memset(table, 0, 65536);
+    for (int c = 0; c < 256; c++) table[c * 256 + c] = 1;
+    for (int p = 0; p < npairs; p++) {
+        unsigned a = pairs[2 * p], b = pairs[2 * p + 1];
+        table[a * 256 + b] = 1;
+        table[b * 256 + a] = 1;
+    }
+}
+
+/* Fill last row D[m][0..n] of the DP described above. row must hold n+1 ints. */
+static void dp_last_row(const unsigned char *q, int m, const unsigned char *t, int n,
+                        int free_start, const unsigned char *eq, int *row)
+{
+    int *prev = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    for (int j = 0; j <= n; j++) prev[j] = free_start ? 0 : j;
+    for (int i = 1; i <= m; i++) {
+        row[0] = i;
+        const unsigned char *eqrow = eq + (size_t)q[i - 1] * 256;
+        for (int j = 1; j <= n; j++) {
+            int sub = prev[j - 1] + (eqrow[t[j - 1]] ? 0 : 1);
+            int del = prev[j] + 1;
+            int ins = row[j - 1] + 1;
+            int v = sub < del ? sub : del;
+            row[j] = v < ins ? v : ins;
+        }
+        memcpy(prev, row, sizeof(int) * (size_t)(n + 1));
+    }
+    if (m == 0) memcpy(row, prev, sizeof(int) * (size_t)(n + 1));
+    free(prev);
+}
+
+/*
+ * Returns 0 on success. *dist = -1 when no alignment within k.
+ * starts[i] == INT32_MIN encodes Python's `None` start.
+ * *nloc is the true number of locations; at most `cap` are written.
+ */
+int orc_align(const unsigned char *q, int m, const unsigned char *t, int n,
+              int mode, int k, const unsigned char *eq,
+              int *dist, int *nloc, int *starts, int *ends, int cap)
+{
+    *nloc = 0;
+    if (m == 0 || n == 0) {
+        if (mode == ORC_MODE_NW) {
+            *dist = m > n ? m : n;
+            if (cap > 0) { starts[0] = INT32_MIN; ends[0] = n - 1; }
+        } else {
+            *dist = m;
+            if (cap > 0) { starts[0] = INT32_MIN; ends[0] = -1; }
+        }
+        *nloc = 1;
+        return 0;
+    }
+    int *row = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    if (!row) return 1;
+    dp_last_row(q, m, t, n, mode == ORC_MODE_HW, eq, row);
+
+    if (mode == ORC_MODE_NW) {
+        int d = row[n];
+        free(row);
+        if (k >= 0 && d > k) { *dist = -1; return 0; }
+        *dist = d;
+        *nloc = 1;
+        if (cap > 0) { starts[0] = 0; ends[0] = n - 1; }
+        return 0;
+    }
+
+    int j0 = (m % 64 != 0) ? 0 : 1; /* column 0 visible only through padding rows */
+    int best = row[j0];
+    for (int j = j0 + 1; j <= n; j++) if (row[j] < best) best = row[j];
+    if (k >= 0 && best > k) { *dist = -1; free(row); return 0; }
+    *dist = best;
+
+    unsigned char *rq = NULL, *rt = NULL;
+    int *rrow = NULL;
+    if (mode == ORC_MODE_HW) {
+        rq = (unsigned char *)malloc((size_t)m);
+        rt = (unsigned char *)malloc((size_t)n);
+        rrow = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+        for (int i = 0; i < m; i++) rq[i] = q[m - 1 - i];
+    }
+    int cnt = 0;
+    for (int j = j0; j <= n; j++) {
+        if (row[j] != best) continue;
+        int e = j - 1;
+        int s = 0;
+        if (mode == ORC_MODE_HW && e >= 0) {
+            /* reverse SHW pass over rev(t[0..e]); last equal-best end wins */
+            int len = e + 1;
+            for (int x = 0; x < len; x++) rt[x] = t[e - x];
+            dp_last_row(rq, m, rt, len, 0, eq, rrow);
+            int rbest = rrow[1], rpos = 0;
+            for (int x = 1; x <= len; x++) {
+                if (rrow[x] < rbest) { rbest = rrow[x]; rpos = x - 1; }
+                else if (rrow[x] == rbest) rpos = x - 1;
+            }
+            s = e - rpos;
+        }
+        if (cnt < cap) { starts[cnt] = s; ends[cnt] = e; }
+        cnt++;
+    }
+    *nloc = cnt;
+    free(row); free(rq); free(rt); free(rrow);
+    return 0;
+}
