@@ -1,0 +1,249 @@
+/*
+ * specimux_b200.h -- C ABI of the B200 read-matching library (libspecimux_b200.so).
+ *
+ * Drop-in boundary for specimux's per-read matching path.  The reference has no FFI: its seam is
+ * the Python callable
+ *     process_sequences(seq_records, parameters, specimens, args, prefilter, trace_logger, record_offset)
+ *         (reference: src/specimux/demultiplex.py:108-212)
+ * whose arithmetic is edlib.align behind align_seq (src/specimux/alignment.py:21-50).  This header is
+ * what a ctypes/cffi stub inside that function binds; every entry point cites the
+ * reference code it replaces.  Plain pointers and sizes only; no C++/torch types; errors are non-zero
+ * int codes plus a thread-local message (smx_last_error) -- nothing throws across the boundary.
+ *
+ * Threading: one context per GPU; a context is not re-entrant.  Do not fork after smx_create.
+ */
+#ifndef SPECIMUX_B200_H
+#define SPECIMUX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMX_ABI_VERSION 1
+
+#define SMX_MAX_PRIMERS 64      /* canonical primers (distinct sequences)                         */
+#define SMX_MAX_PATTERN 64      /* primer / barcode length handled by the single-thread kernels   */
+#define SMX_MAX_SEARCH_LEN 1024 /* --search-len                                                   */
+
+/* error codes */
+#define SMX_OK 0
+#define SMX_ERR_ARG 1        /* invalid argument / table                                        */
+#define SMX_ERR_CUDA 2       /* CUDA runtime failure (message has the CUDA error string)        */
+#define SMX_ERR_NO_DEVICE 3  /* no usable GPU: the library has no CPU path by design            */
+#define SMX_ERR_CAPACITY 4   /* caller-provided result buffer too small (see smx_result_bound)  */
+#define SMX_ERR_INTERNAL 5
+
+/* trim modes (reference: constants.py:40-45 TrimMode) */
+#define SMX_TRIM_NONE 0
+#define SMX_TRIM_PRIMERS 1
+#define SMX_TRIM_BARCODES 2
+#define SMX_TRIM_TAILS 3
+
+/* resolution types (reference: constants.py:54-61 ResolutionType) */
+#define SMX_RES_FULL_MATCH 1
+#define SMX_RES_PARTIAL_FORWARD 2
+#define SMX_RES_PARTIAL_REVERSE 3
+#define SMX_RES_MULTIPLE_SPECIMENS 4
+#define SMX_RES_UNKNOWN 5
+#define SMX_RES_DEREPLICATED_FULL 6
+
+/*
+ * Pattern / match tables.  Replaces the in-memory registries the reference builds in
+ * databases.py:123-308 (Specimens), models.py:20-31 (PrimerInfo) and the thresholds of
+ * orchestration.py:548-641 (setup_match_parameters).  All arrays are caller-owned and copied.
+ *
+ * Primers are the reference's *canonical* primers (Specimens._primers, keyed by sequence,
+ * databases.py:152-165) in first-appearance order.  Barcodes are listed per primer in the pinned
+ * order the host iterates them (reference iterates a Python set, demultiplex.py:781).
+ */
+typedef struct smx_tables {
+    uint32_t n_primers;
+    const char *primer_seq;        /* concatenated forward-sense primer strings (upper-case IUPAC)   */
+    const char *primer_rc;         /* concatenated reverse complements (what match_one_end searches) */
+    const uint32_t *primer_off;    /* n_primers+1 offsets into both strings                          */
+    const uint8_t *primer_dir;     /* 0 = forward, 1 = reverse (constants.py:100-103)                */
+    const int32_t *primer_k;       /* max edit distance per primer (orchestration.py:603-614)        */
+    const int32_t *primer_file_index; /* order in primers.fasta (io_utils.py:279)                    */
+
+    /* per-primer barcode lists: primer p owns entries [pb_off[p], pb_off[p+1]) of pb_barcode, each a
+     * global barcode id; forward primers index the b1 namespace, reverse primers the b2 namespace.  */
+    const uint32_t *pb_off;        /* n_primers+1 */
+    const uint32_t *pb_barcode;
+
+    uint32_t n_b1, n_b2;           /* distinct forward / reverse barcodes                            */
+    const char *b1_rc;             /* concatenated reverse complements of forward barcodes           */
+    const uint32_t *b1_off;        /* n_b1+1 */
+    const char *b2_rc;
+    const uint32_t *b2_off;        /* n_b2+1 */
+
+    /* primer pairs in the reference's candidate enumeration order (demultiplex.py:699-700):
+     * for fwd in get_primers(FWD): for rev in get_paired_primers(fwd).                              */
+    uint32_t n_pairs;
+    const uint32_t *pair_fwd;
+    const uint32_t *pair_rev;
+    const int32_t *pair_pool;      /* get_pool_from_primers(fwd, rev), demultiplex.py:640-665; -1 = none */
+
+    /* specimen rows in file order (databases.py:167).  p1_mask / p2_mask: bit c set iff canonical
+     * primer c is (by identity) one of the row's resolved primers (databases.py:224-225,241; Q7).  */
+    uint32_t n_specimens;
+    const uint32_t *spec_b1;
+    const uint32_t *spec_b2;
+    const uint64_t *spec_p1_mask;
+    const uint64_t *spec_p2_mask;
+    const int32_t *spec_pool;
+} smx_tables;
+
+/* Flags that change results (reference: cli.py:23-41, models.py:331-338 MatchParameters). */
+typedef struct smx_params {
+    int32_t search_len;        /* -l / --search-len                                                */
+    int32_t max_dist_index;    /* barcode threshold k_idx                                          */
+    int32_t barcode_length;    /* Specimens.b_length(), databases.py:273                           */
+    int32_t preorient;         /* !--disable-preorient                                             */
+    int32_t prefilter;         /* !--disable-prefilter: emulate the Bloom prefilter exactly (Q5)   */
+    int32_t trim;              /* SMX_TRIM_*                                                       */
+    int32_t dereplicate_best;  /* --dereplicate best (1) | none (0)                                */
+    int32_t min_length;        /* -1 = off                                                         */
+    int32_t max_length;        /* -1 = off                                                         */
+} smx_params;
+
+/*
+ * One batch of reads, packed by the host batching layer.
+ *  packed2  : 2 bits per base, A=0 C=1 G=2 T=3, base i of read r at bit 2*(i%16) of word
+ *             word_off[r] + i/16 (little-endian within the word); non-ACGT bases hold 0 there.
+ *  packed4  : optional exact side stream for reads containing any non-ACGT symbol (NULL if none).
+ *             For such a read r, off4[r] != UINT64_MAX and packed4 holds the forward strand then the
+ *             reverse-complement strand (Biopython ambiguous-DNA complement, U->A), each
+ *             ceil(len/8) words of 4-bit codes:
+ *               A0 C1 G2 T3 R4 Y5 S6 W7 K8 M9 B10 D11 H12 V13 N14, 15 = any other byte (matches nothing)
+ */
+typedef struct smx_batch {
+    uint32_t n_reads;
+    const uint32_t *packed2;
+    uint64_t packed2_words;
+    const uint64_t *word_off;   /* n_reads */
+    const uint32_t *lengths;    /* n_reads */
+    const uint32_t *packed4;    /* may be NULL */
+    uint64_t packed4_words;
+    const uint64_t *off4;       /* may be NULL when packed4 is NULL */
+} smx_batch;
+
+/*
+ * One output record == one WriteOperation of the reference (models.py:341-357), before string
+ * formatting.  Coordinates are in the orientation-normalised sequence (candidate.sequence) and
+ * already include the reference's mutating-trim behaviour.  INT32_MIN = None.
+ */
+typedef struct smx_record {
+    uint32_t read;             /* index of the read in the batch                                  */
+    int32_t sample;            /* specimen row | global b1 id | global b2 id | -1, by `resolution` */
+    int32_t trim_start;        /* slice [trim_start, trim_end) of the oriented read               */
+    int32_t trim_end;
+    int32_t p1_loc[2];         /* WriteOperation.p1_location (start, end)                         */
+    int32_t p2_loc[2];
+    int32_t b1_loc[2];
+    int32_t b2_loc[2];
+    int16_t pool;              /* pool id, -1 = "unknown"                                         */
+    int16_t p1;                /* canonical primer index or -1 = "unknown"                        */
+    int16_t p2;
+    int8_t dist[4];            /* p1, b1, b2, p2 edit distances, -1 = 'X' (models.py:206-218)      */
+    uint8_t resolution;        /* SMX_RES_*                                                       */
+    uint8_t reverse;           /* 1: the record carries the reverse-complemented read             */
+    uint8_t trim_empty;        /* 1: empty-trim fallback record (demultiplex.py:47-73)            */
+    uint8_t candidate;         /* index of the candidate match within the read (trace ids)        */
+    uint8_t pad[2];
+} smx_record;               /* 64 bytes */
+
+/* Optional per-search detail (level-1 results), used by parity tests and trace emission.
+ * Slot index: ((strand * n_primers + primer) * n_reads + read); strand 0 = read as given,
+ * 1 = its reverse complement.  Coordinates are the values align_seq reports (alignment.py:49). */
+typedef struct smx_primer_hit {
+    int32_t first_start;       /* start of locations()[0]                                         */
+    int32_t first_end;         /* end of locations()[0] (smallest end)                            */
+    int16_t distance;          /* -1 = no match within k                                          */
+    uint16_t n_locations;      /* number of equal-best end positions                              */
+} smx_primer_hit;
+
+/* Barcode slot index: (bslot_base[strand * n_primers + primer] + j) * n_reads + read for the j-th
+ * barcode of the primer; bslot_base is the running sum of barcode-list lengths over
+ * (strand, primer) pairs in index order.  Valid only where the primer slot matched.             */
+typedef struct smx_barcode_hit {
+    uint64_t end_mask;         /* bit j: flank column j is an equal-best SHW end (end = start + j) */
+    int32_t search_start;      /* barcode_search_start of the winning primer location             */
+    int16_t distance;          /* -1 = none within k_idx at any primer location                   */
+    uint16_t pad;
+} smx_barcode_hit;
+
+typedef struct smx_results {
+    /* per read: records [rec_offset[r], rec_offset[r+1]) ; rec_offset has n_reads+1 entries */
+    uint32_t *rec_offset;
+    smx_record *records;
+    uint64_t records_cap;      /* capacity of `records` (see smx_result_bound)                    */
+    uint64_t n_records;        /* out                                                             */
+    uint64_t n_matched;        /* out: reads with >= 1 full match (demultiplex.py:199-201)        */
+    uint8_t *endmask_bits;     /* optional, may be NULL: per primer slot, search_len bits
+                                  (ceil(search_len/32) words) of equal-best end positions          */
+    smx_primer_hit *primer_hits;   /* optional, may be NULL: 2 * n_primers * n_reads entries      */
+    smx_barcode_hit *barcode_hits; /* optional, may be NULL: 2 * sum(barcodes) * n_reads entries  */
+} smx_results;
+
+typedef struct smx_ctx smx_ctx;
+
+/* ABI version of the loaded library. */
+int smx_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread. */
+const char *smx_last_error(void);
+
+/* Number of visible CUDA devices (0 when none; never an error). */
+int smx_device_count(void);
+
+/* Build a context on `device`: copies the tables, builds IUPAC-aware Peq masks (edlib
+ * additionalEqualities semantics, constants.py:13-20) and the specimen lookup table.
+ * Replaces read_primers_file/read_specimen_file products + setup_match_parameters thresholds. */
+int smx_create(int device, const smx_tables *tables, const smx_params *params, smx_ctx **out);
+
+void smx_destroy(smx_ctx *ctx);
+
+/* Upper bound on records for a batch of n reads (sizing of smx_results.records). */
+uint64_t smx_result_bound(const smx_ctx *ctx, uint32_t n_reads);
+
+/* Whole path for one batch with HOST buffers: H2D copy, window staging, primer HW search,
+ * barcode SHW search, selection/dereplication, D2H of the records.
+ * Replaces process_sequences' matching and selection (demultiplex.py:108-212,216-598,602-820). */
+int smx_match_batch(smx_ctx *ctx, const smx_batch *batch, smx_results *out);
+
+/* Split form of smx_match_batch for pipelining and device-resident timing. */
+int smx_upload_batch(smx_ctx *ctx, const smx_batch *batch);   /* H2D only                         */
+int smx_run_resident(smx_ctx *ctx);                           /* kernels only, on the last upload  */
+int smx_download_results(smx_ctx *ctx, smx_results *out);     /* D2H only                         */
+
+/* CUDA-event time (ms) of the last smx_run_resident, and of its stages:
+ * stage 0 staging, 1 primer search, 2 barcode search, 3 selection. */
+int smx_last_timing(const smx_ctx *ctx, float *total_ms, float stage_ms[4]);
+
+/* Number of kernel launches issued by the last smx_run_resident. */
+int smx_last_launch_count(const smx_ctx *ctx);
+
+/* Work done by the last smx_run_resident, counted on the device with the SURVEY.md 8d formulas:
+ * cells[0] = HW cells, cells[1] = SHW cells, wordcols[0..1] the same in 32-bit word-columns. */
+int smx_last_work(const smx_ctx *ctx, uint64_t cells[2], uint64_t wordcols[2]);
+
+/* Batched global (NW) edit distances between all pairs of `n` strings, on the GPU.
+ * Replaces the O(B^2) edlib.align(task="distance") loop of orchestration.py:549-555.
+ * out[i*n + j] = distance(seq_i, seq_j). */
+int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint32_t n, int32_t *out);
+
+/* Host-side packer (no matching): ASCII reads -> the smx_batch encoding above.
+ * Replaces nothing in the reference (it works on Python strings); part of the batching layer.
+ * Call with out arrays sized by smx_pack_bound. Returns the number of flagged (packed4) reads in
+ * *n_flagged. */
+void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint64_t *packed2_words, uint64_t *packed4_words_max);
+int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
+                   uint32_t *packed2, uint64_t *word_off, uint32_t *lengths,
+                   uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECIMUX_B200_H */

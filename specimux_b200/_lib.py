@@ -1,0 +1,113 @@
+"""ctypes binding of libspecimux_b200.so (include/specimux_b200.h).
+
+Loading fails loudly when the library has not been built (`python -c "import __graft_entry__ as g;
+g.build()"` or `make -C specimux_b200/csrc`); compute entry points fail loudly without a GPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspecimux_b200.so")
+
+SMX_OK, SMX_ERR_ARG, SMX_ERR_CUDA, SMX_ERR_NO_DEVICE, SMX_ERR_CAPACITY, SMX_ERR_INTERNAL = range(6)
+TRIM_CODES = {"none": 0, "primers": 1, "barcodes": 2, "tails": 3}
+NONE = -(2 ** 31)
+
+u8p, u32p, u64p, i32p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                         C.POINTER(C.c_int32))
+
+
+class SmxTables(C.Structure):
+    _fields_ = [("n_primers", C.c_uint32), ("primer_seq", C.c_char_p), ("primer_rc", C.c_char_p),
+                ("primer_off", u32p), ("primer_dir", u8p), ("primer_k", i32p), ("primer_file_index", i32p),
+                ("pb_off", u32p), ("pb_barcode", u32p),
+                ("n_b1", C.c_uint32), ("n_b2", C.c_uint32),
+                ("b1_rc", C.c_char_p), ("b1_off", u32p), ("b2_rc", C.c_char_p), ("b2_off", u32p),
+                ("n_pairs", C.c_uint32), ("pair_fwd", u32p), ("pair_rev", u32p), ("pair_pool", i32p),
+                ("n_specimens", C.c_uint32), ("spec_b1", u32p), ("spec_b2", u32p),
+                ("spec_p1_mask", u64p), ("spec_p2_mask", u64p), ("spec_pool", i32p)]
+
+
+class SmxParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("search_len", "max_dist_index", "barcode_length", "preorient",
+                                         "prefilter", "trim", "dereplicate_best", "min_length", "max_length")]
+
+
+class SmxBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("packed2", u32p), ("packed2_words", C.c_uint64),
+                ("word_off", u64p), ("lengths", u32p), ("packed4", u32p), ("packed4_words", C.c_uint64),
+                ("off4", u64p)]
+
+
+class SmxResults(C.Structure):
+    _fields_ = [("rec_offset", u32p), ("records", C.c_void_p), ("records_cap", C.c_uint64),
+                ("n_records", C.c_uint64), ("n_matched", C.c_uint64), ("endmask_bits", C.c_void_p),
+                ("primer_hits", C.c_void_p), ("barcode_hits", C.c_void_p)]
+
+
+RECORD_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<i4"), ("trim_end", "<i4"),
+                         ("p1_loc", "<i4", (2,)), ("p2_loc", "<i4", (2,)), ("b1_loc", "<i4", (2,)),
+                         ("b2_loc", "<i4", (2,)), ("pool", "<i2"), ("p1", "<i2"), ("p2", "<i2"),
+                         ("dist", "i1", (4,)), ("resolution", "u1"), ("reverse", "u1"), ("trim_empty", "u1"),
+                         ("candidate", "u1"), ("pad", "u1", (2,))])
+PRIMER_HIT_DTYPE = np.dtype([("first_start", "<i4"), ("first_end", "<i4"), ("distance", "<i2"),
+                             ("n_locations", "<u2")])
+BARCODE_HIT_DTYPE = np.dtype([("end_mask", "<u8"), ("search_start", "<i4"), ("distance", "<i2"), ("pad", "<u2")])
+assert RECORD_DTYPE.itemsize == 64 and PRIMER_HIT_DTYPE.itemsize == 12 and BARCODE_HIT_DTYPE.itemsize == 16
+
+EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create", "smx_destroy",
+           "smx_result_bound", "smx_match_batch", "smx_upload_batch", "smx_run_resident",
+           "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
+           "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads"]
+
+
+class SmxError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libspecimux_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """The CUDA library.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `make -C specimux_b200/csrc` (or __graft_entry__.build()); "
+                              "specimux_b200 has no CPU matching path" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.smx_last_error.restype = C.c_char_p
+        lib.smx_result_bound.restype = C.c_uint64
+        lib.smx_result_bound.argtypes = [C.c_void_p, C.c_uint32]
+        lib.smx_create.argtypes = [C.c_int, C.POINTER(SmxTables), C.POINTER(SmxParams), C.POINTER(C.c_void_p)]
+        lib.smx_destroy.argtypes = [C.c_void_p]
+        lib.smx_destroy.restype = None
+        for fn in ("smx_match_batch",):
+            getattr(lib, fn).argtypes = [C.c_void_p, C.POINTER(SmxBatch), C.POINTER(SmxResults)]
+        lib.smx_upload_batch.argtypes = [C.c_void_p, C.POINTER(SmxBatch)]
+        lib.smx_run_resident.argtypes = [C.c_void_p]
+        lib.smx_download_results.argtypes = [C.c_void_p, C.POINTER(SmxResults)]
+        lib.smx_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.smx_last_launch_count.argtypes = [C.c_void_p]
+        lib.smx_last_work.argtypes = [C.c_void_p, u64p, u64p]
+        lib.smx_pairwise_nw.argtypes = [C.c_int, C.c_char_p, u32p, C.c_uint32, i32p]
+        lib.smx_pack_bound.argtypes = [u64p, C.c_uint32, u64p, u64p]
+        lib.smx_pack_bound.restype = None
+        lib.smx_pack_reads.argtypes = [C.c_char_p, u64p, C.c_uint32, u32p, u64p, u32p, u32p, u64p, u64p, u32p]
+        if lib.smx_abi_version() != 1:
+            raise ImportError("libspecimux_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != SMX_OK:
+        raise SmxError(rc, load().smx_last_error().decode("utf-8", "replace"))
+
+
+def ptr(arr, typ):
+    return arr.ctypes.data_as(typ)

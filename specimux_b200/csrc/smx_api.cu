@@ -1,0 +1,429 @@
+// smx_api.cu -- C ABI of libspecimux_b200.so (see include/specimux_b200.h).
+// Context / table construction, batch buffers, kernel launches.  No CPU matching path exists:
+// without a usable GPU every compute entry point fails with SMX_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "smx_host_tables.hpp"
+#include "smx_kernels.cuh"
+
+using namespace smx;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver          \
+                            ? SMX_ERR_NO_DEVICE : SMX_ERR_CUDA,                               \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) {
+    cudaError_t e = d.ensure(h.size() ? h.size() : 1);
+    if (e != cudaSuccess) return e;
+    if (h.empty()) return cudaSuccess;
+    return cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+struct smx_ctx {
+    int device = 0;
+    Tables t;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // table storage
+    DevBuf<u64> peq_rc, peq_rcrev, peq_fw, bpeq, spec_key, spec_p1, spec_p2;
+    DevBuf<unsigned char> b_len;
+    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row;
+    DevBuf<i32> pair_pool, spec_pool;
+    int max_nb = 0;
+    // batch storage
+    Batch b;
+    DevBuf<u32> packed2, lengths, packed4, win, endmask, rec_count, rec_offset, block_sums;
+    DevBuf<u64> word_off, off4;
+    DevBuf<smx_primer_hit> phit;
+    DevBuf<unsigned char> orient_hit, read_flags;
+    DevBuf<smx_barcode_hit> bhit;
+    DevBuf<smx_record> records;
+    DevBuf<unsigned long long> counters;   // 4 work counters + matched + (u32) overflow + (u32) total
+    bool have_batch = false, have_results = false;
+    u64 n_records = 0, n_matched = 0;
+    unsigned long long work[4] = {0, 0, 0, 0};
+    float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
+    int launches = 0;
+};
+
+extern "C" {
+
+int smx_abi_version(void) { return SMX_ABI_VERSION; }
+
+const char *smx_last_error(void) { return g_err; }
+
+int smx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void smx_destroy(smx_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bpeq.release();
+    c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
+    c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
+    c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release();
+    c->packed2.release(); c->lengths.release(); c->packed4.release(); c->win.release(); c->endmask.release();
+    c->rec_count.release(); c->rec_offset.release(); c->block_sums.release(); c->word_off.release();
+    c->off4.release(); c->phit.release(); c->orient_hit.release(); c->read_flags.release(); c->bhit.release();
+    c->records.release(); c->counters.release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx **out) {
+    if (!tb || !pr || !out) return fail(SMX_ERR_ARG, "smx_create: null argument");
+    *out = nullptr;
+    HostTables ht;
+    if (!ht.build(tb, pr)) return fail(SMX_ERR_ARG, "smx_create: %s", ht.error.c_str());
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SMX_ERR_NO_DEVICE, "smx_create: no CUDA device (%s); this library has no CPU path",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    }
+    if (device < 0 || device >= ndev) return fail(SMX_ERR_ARG, "smx_create: device %d of %d", device, ndev);
+
+    smx_ctx *c = new smx_ctx();
+    c->device = device;
+    c->max_nb = ht.max_nb;
+#define CUC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            int rc_ = fail(SMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));             \
+            smx_destroy(c);                                                                           \
+            return rc_;                                                                               \
+        }                                                                                             \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CUC(cudaEventCreate(&e));
+    CUC(upload(c->peq_rc, ht.peq_rc)); CUC(upload(c->peq_rcrev, ht.peq_rcrev)); CUC(upload(c->peq_fw, ht.peq_fw));
+    CUC(upload(c->bpeq, ht.bpeq)); CUC(upload(c->b_len, ht.b_len)); CUC(upload(c->pb_barcode, ht.pb_barcode));
+    CUC(upload(c->pair_fwd, ht.pair_fwd)); CUC(upload(c->pair_rev, ht.pair_rev)); CUC(upload(c->pair_pool, ht.pair_pool));
+    CUC(upload(c->spec_key, ht.spec_key)); CUC(upload(c->spec_key_off, ht.spec_key_off));
+    CUC(upload(c->spec_row, ht.spec_row)); CUC(upload(c->spec_p1, ht.spec_p1)); CUC(upload(c->spec_p2, ht.spec_p2));
+    CUC(upload(c->spec_pool, ht.spec_pool));
+    CUC(c->counters.ensure(8));
+    ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->bpeq.p, c->b_len.p, c->pb_barcode.p,
+                    c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
+                    c->spec_row.p, c->spec_p1.p, c->spec_p2.p, c->spec_pool.p);
+    c->t = ht.t;
+    memset(&c->b, 0, sizeof(c->b));
+    size_t smem = (size_t)ht.max_nb * 16 * sizeof(u64);
+    if (smem > 48 * 1024) {
+        CUC(cudaFuncSetAttribute(k_barcode_search<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUC(cudaFuncSetAttribute(k_barcode_search<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+#undef CUC
+    *out = c;
+    return SMX_OK;
+}
+
+uint64_t smx_result_bound(const smx_ctx *c, uint32_t n_reads) {
+    // Every read yields >= 1 record; multi-record reads (tied specimens / partial barcodes) are rare.
+    // smx_download_results reports SMX_ERR_CAPACITY with the exact need if this is ever exceeded.
+    (void)c;
+    return (uint64_t)n_reads * 2 + 1024;
+}
+
+int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
+    if (!c || !in) return fail(SMX_ERR_ARG, "smx_upload_batch: null argument");
+    if (in->n_reads == 0) return fail(SMX_ERR_ARG, "smx_upload_batch: empty batch");
+    if ((in->packed4 == nullptr) != (in->off4 == nullptr) && in->packed4_words)
+        return fail(SMX_ERR_ARG, "smx_upload_batch: packed4 and off4 must be given together");
+    CU(cudaSetDevice(c->device));
+    const Tables &t = c->t;
+    const u32 n = in->n_reads, n_pad = (n + 127u) & ~127u;
+    const int nP = t.n_primers;
+    CU(c->packed2.ensure(in->packed2_words + 1)); CU(c->word_off.ensure(n)); CU(c->lengths.ensure(n));
+    bool flagged = in->packed4 && in->off4 && in->packed4_words;
+    if (flagged) { CU(c->packed4.ensure(in->packed4_words)); CU(c->off4.ensure(n)); }
+    CU(c->win.ensure((size_t)2 * t.wpw * n_pad));
+    CU(c->phit.ensure((size_t)2 * nP * n_pad));
+    CU(c->endmask.ensure((size_t)2 * nP * t.mw * n_pad));
+    CU(c->orient_hit.ensure((size_t)2 * nP * n_pad));
+    CU(c->bhit.ensure((size_t)t.total_bslots * n_pad));
+    CU(c->rec_count.ensure(n)); CU(c->rec_offset.ensure((size_t)n + 1)); CU(c->read_flags.ensure(n));
+    CU(c->block_sums.ensure((n + kScanBlock - 1) / kScanBlock + 1));
+    CU(cudaMemcpyAsync(c->packed2.p, in->packed2, in->packed2_words * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->word_off.p, in->word_off, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->lengths.p, in->lengths, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (flagged) {
+        CU(cudaMemcpyAsync(c->packed4.p, in->packed4, in->packed4_words * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->off4.p, in->off4, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    }
+    Batch &b = c->b;
+    b.n_reads = n; b.n_pad = n_pad;
+    b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
+    b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
+    b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.orient_hit = c->orient_hit.p;
+    b.bhit = c->bhit.p; b.rec_count = c->rec_count.p; b.rec_offset = c->rec_offset.p;
+    b.records = nullptr; b.read_flags = c->read_flags.p; b.counters = c->counters.p;
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_batch = true; c->have_results = false;
+    return SMX_OK;
+}
+
+int smx_run_resident(smx_ctx *c) {
+    if (!c) return fail(SMX_ERR_ARG, "smx_run_resident: null context");
+    if (!c->have_batch) return fail(SMX_ERR_ARG, "smx_run_resident: no batch uploaded");
+    CU(cudaSetDevice(c->device));
+    const Tables &t = c->t;
+    Batch &b = c->b;
+    const u32 n = b.n_reads;
+    const int nP = t.n_primers;
+    cudaStream_t st = c->stream;
+    int launches = 0;
+    CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
+    CU(cudaEventRecord(c->ev[0], st));
+    {   // stage 0
+        dim3 grid((n + 127) / 128, 2 * t.wpw);
+        k_stage_windows<<<grid, 128, 0, st>>>(b);
+        ++launches;
+    }
+    CU(cudaEventRecord(c->ev[1], st));
+    {   // stage 1
+        dim3 grid((n + 127) / 128, 2 * nP);
+        if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(b);
+        else k_primer_search<u32><<<grid, 128, 0, st>>>(b);
+        ++launches;
+    }
+    CU(cudaEventRecord(c->ev[2], st));
+    for (int s = 0; s < 2; ++s)   // stage 2
+        for (int p = 0; p < nP; ++p) {
+            int nb = (int)(t.pb_off[p + 1] - t.pb_off[p]);
+            if (!nb) continue;
+            u64 warps = (u64)n * ((nb + 31) / 32);
+            u64 blocks = (warps * 32 + 255) / 256;
+            size_t smem = (size_t)nb * 16 * sizeof(u64);
+            if (t.buse64) k_barcode_search<u64><<<(unsigned)blocks, 256, smem, st>>>(b, p, s);
+            else k_barcode_search<u32><<<(unsigned)blocks, 256, smem, st>>>(b, p, s);
+            ++launches;
+        }
+    CU(cudaEventRecord(c->ev[3], st));
+    {   // stage 3: count, scan, write
+        unsigned blocks = (n + 127) / 128;
+        if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b, 0); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b, 0);
+        unsigned sblocks = (n + kScanBlock - 1) / kScanBlock;
+        k_scan_block_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p);
+        k_scan_spine<<<1, kScanBlock, 0, st>>>(c->block_sums.p, sblocks, (u32 *)(c->counters.p + 6));
+        k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p, b.rec_offset);
+        k_count_flags<<<(n + 255) / 256, 256, 0, st>>>(b.read_flags, n, c->counters.p + 4, (unsigned *)(c->counters.p + 5));
+        launches += 5;
+        unsigned long long host_counters[8];
+        CU(cudaMemcpyAsync(host_counters, c->counters.p, sizeof(host_counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        u64 total = (u32)host_counters[6];
+        if ((u32)host_counters[5])
+            return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceeded an internal tie/group capacity",
+                        (unsigned)(u32)host_counters[5]);
+        CU(c->records.ensure(total + 1));
+        b.records = c->records.p;
+        if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b, 1); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b, 1);
+        ++launches;
+        c->n_records = total;
+        c->n_matched = host_counters[4];
+        for (int i = 0; i < 4; ++i) c->work[i] = host_counters[i];
+    }
+    CU(cudaEventRecord(c->ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    CU(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[4]));
+    c->launches = launches;
+    c->have_results = true;
+    return SMX_OK;
+}
+
+int smx_download_results(smx_ctx *c, smx_results *out) {
+    if (!c || !out) return fail(SMX_ERR_ARG, "smx_download_results: null argument");
+    if (!c->have_results) return fail(SMX_ERR_ARG, "smx_download_results: nothing to download");
+    CU(cudaSetDevice(c->device));
+    const Batch &b = c->b;
+    const Tables &t = c->t;
+    const u32 n = b.n_reads;
+    out->n_records = c->n_records;
+    out->n_matched = c->n_matched;
+    if (c->n_records > out->records_cap)
+        return fail(SMX_ERR_CAPACITY, "smx_download_results: %llu records, capacity %llu",
+                    (unsigned long long)c->n_records, (unsigned long long)out->records_cap);
+    cudaStream_t st = c->stream;
+    if (out->rec_offset)
+        CU(cudaMemcpyAsync(out->rec_offset, b.rec_offset, ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    if (out->records && c->n_records)
+        CU(cudaMemcpyAsync(out->records, b.records, c->n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
+    // level-1 detail is stored padded ([slot][n_pad]) on the device and returned dense ([slot][n])
+    if (out->primer_hits)
+        CU(cudaMemcpy2DAsync(out->primer_hits, (size_t)n * sizeof(smx_primer_hit), b.phit,
+                             (size_t)b.n_pad * sizeof(smx_primer_hit), (size_t)n * sizeof(smx_primer_hit),
+                             (size_t)2 * t.n_primers, cudaMemcpyDeviceToHost, st));
+    if (out->endmask_bits)
+        CU(cudaMemcpy2DAsync(out->endmask_bits, (size_t)n * sizeof(u32), b.endmask, (size_t)b.n_pad * sizeof(u32),
+                             (size_t)n * sizeof(u32), (size_t)2 * t.n_primers * t.mw, cudaMemcpyDeviceToHost, st));
+    if (out->barcode_hits && t.total_bslots)
+        CU(cudaMemcpy2DAsync(out->barcode_hits, (size_t)n * sizeof(smx_barcode_hit), b.bhit,
+                             (size_t)b.n_pad * sizeof(smx_barcode_hit), (size_t)n * sizeof(smx_barcode_hit),
+                             (size_t)t.total_bslots, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SMX_OK;
+}
+
+int smx_match_batch(smx_ctx *c, const smx_batch *in, smx_results *out) {
+    int rc = smx_upload_batch(c, in);
+    if (rc) return rc;
+    rc = smx_run_resident(c);
+    if (rc) return rc;
+    return smx_download_results(c, out);
+}
+
+int smx_last_timing(const smx_ctx *c, float *total_ms, float stage_ms[4]) {
+    if (!c) return fail(SMX_ERR_ARG, "smx_last_timing: null context");
+    if (total_ms) *total_ms = c->total_ms;
+    if (stage_ms) for (int i = 0; i < 4; ++i) stage_ms[i] = c->stage_ms[i];
+    return SMX_OK;
+}
+
+int smx_last_launch_count(const smx_ctx *c) { return c ? c->launches : 0; }
+
+int smx_last_work(const smx_ctx *c, uint64_t cells[2], uint64_t wordcols[2]) {
+    if (!c || !c->have_results) return fail(SMX_ERR_ARG, "smx_last_work: no results");
+    cells[0] = c->work[0]; cells[1] = c->work[1];
+    wordcols[0] = c->work[2]; wordcols[1] = c->work[3];
+    return SMX_OK;
+}
+
+int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint32_t n, int32_t *out) {
+    if (!seqs || !seq_off || !out) return fail(SMX_ERR_ARG, "smx_pairwise_nw: null argument");
+    if (n == 0) return SMX_OK;
+    for (u32 i = 0; i < n; ++i)
+        if (seq_off[i + 1] - seq_off[i] > 64) return fail(SMX_ERR_ARG, "smx_pairwise_nw: sequence %u longer than 64", i);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SMX_ERR_NO_DEVICE, "smx_pairwise_nw: no CUDA device; this library has no CPU path");
+    }
+    CU(cudaSetDevice(device));
+    char *d_seq = nullptr; u32 *d_off = nullptr; i32 *d_out = nullptr;
+    size_t bytes = seq_off[n];
+    CU(cudaMalloc((void **)&d_seq, bytes ? bytes : 1));
+    CU(cudaMalloc((void **)&d_off, (size_t)(n + 1) * sizeof(u32)));
+    CU(cudaMalloc((void **)&d_out, (size_t)n * n * sizeof(i32)));
+    CU(cudaMemcpy(d_seq, seqs, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_off, seq_off, (size_t)(n + 1) * sizeof(u32), cudaMemcpyHostToDevice));
+    u64 total = (u64)n * n;
+    k_pairwise_nw<<<(unsigned)((total + 127) / 128), 128>>>(d_seq, d_off, n, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, total * sizeof(i32), cudaMemcpyDeviceToHost));
+    cudaFree(d_seq); cudaFree(d_off); cudaFree(d_out);
+    return SMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side packer (batching layer; no matching happens here).
+
+void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint64_t *packed2_words, uint64_t *packed4_words_max) {
+    uint64_t w2 = 0, w4 = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        uint64_t len = seq_off[r + 1] - seq_off[r];
+        w2 += (len + 15) / 16;
+        w4 += 2 * ((len + 7) / 8);
+    }
+    if (packed2_words) *packed2_words = w2 + 1;
+    if (packed4_words_max) *packed4_words_max = w4 + 1;
+}
+
+int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
+                   uint32_t *packed2, uint64_t *word_off, uint32_t *lengths,
+                   uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged) {
+    if (!bases || !seq_off || !packed2 || !word_off || !lengths)
+        return fail(SMX_ERR_ARG, "smx_pack_reads: null argument");
+    uint64_t w2 = 0, w4 = 0;
+    uint32_t flagged = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const unsigned char *s = (const unsigned char *)bases + seq_off[r];
+        uint64_t len = seq_off[r + 1] - seq_off[r];
+        if (len > 0xFFFFFFFFull) return fail(SMX_ERR_ARG, "smx_pack_reads: read %u too long", r);
+        word_off[r] = w2;
+        lengths[r] = (uint32_t)len;
+        bool exotic = false;
+        uint64_t nw = (len + 15) / 16;
+        for (uint64_t w = 0; w < nw; ++w) {
+            uint32_t v = 0;
+            uint64_t lim = std::min<uint64_t>(16, len - w * 16);
+            for (uint64_t i = 0; i < lim; ++i) {
+                int c = read_code(s[w * 16 + i]);
+                if (c > 3) { exotic = true; c = 0; }
+                v |= (uint32_t)c << (2 * i);
+            }
+            packed2[w2 + w] = v;
+        }
+        w2 += nw;
+        if (off4) off4[r] = ~0ull;
+        if (exotic) {
+            if (!packed4 || !off4) return fail(SMX_ERR_ARG, "smx_pack_reads: read %u needs the packed4 stream", r);
+            off4[r] = w4;
+            uint64_t n4 = (len + 7) / 8;
+            for (uint64_t w = 0; w < 2 * n4; ++w) packed4[w4 + w] = 0;
+            for (uint64_t i = 0; i < len; ++i) {
+                packed4[w4 + i / 8] |= (uint32_t)read_code(s[i]) << (4 * (i % 8));
+                uint64_t x = len - 1 - i;     // position in the reverse-complement strand
+                packed4[w4 + n4 + x / 8] |= (uint32_t)read_code_rc(s[i]) << (4 * (x % 8));
+            }
+            w4 += 2 * n4;
+            ++flagged;
+        }
+    }
+    if (packed4_words) *packed4_words = w4;
+    if (n_flagged) *n_flagged = flagged;
+    return SMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,763 @@
+// smx_core.cuh -- host/device core of the B200 read-matching path.
+//
+// Everything here is pure integer logic written as __host__ __device__ inline functions so the CUDA
+// kernels (smx_kernels.cuh) and the CPU-side kernel simulator used by the unit tests
+// (tests/hostsim) execute the very same code.  Reference semantics are cited per function
+// (paths relative to /root/reference/src/specimux/).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/specimux_b200.h"
+
+#if defined(__CUDACC__)
+#define SMX_HD __host__ __device__ __forceinline__
+#else
+#define SMX_HD inline
+#endif
+
+namespace smx {
+
+static_assert(sizeof(smx_record) == 64, "smx_record layout");
+static_assert(sizeof(smx_primer_hit) == 12, "smx_primer_hit layout");
+static_assert(sizeof(smx_barcode_hit) == 16, "smx_barcode_hit layout");
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+
+constexpr int kSymOther = 15;       // read symbol that matches nothing (lower case, unknown bytes)
+constexpr int kNone = INT32_MIN;    // Python None in coordinates
+constexpr int kMaxPairs = 64;       // candidate slots per read = 2 * pairs
+constexpr int kMaxGroups = 24;      // dereplication groups tracked per read
+constexpr int kMaxTies = 8;         // equal-best barcodes tracked per end
+
+// ---------------------------------------------------------------------------------------------
+// Symbols.  4-bit read codes: A0 C1 G2 T3 R4 Y5 S6 W7 K8 M9 B10 D11 H12 V13 N14 other15.
+
+SMX_HD int sym_complement(int c) {
+    // Biopython ambiguous-DNA complement restricted to the 16 codes (Bio.Seq).
+    // A<->T C<->G R<->Y S W K<->M B<->V D<->H N other
+    const u64 table = 0xFE'A'B'C'D'8'9'7'6'4'5'0'1'2'3ull;   // nibble i = complement of code i
+    return (int)((table >> (4 * c)) & 15);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Window geometry.  Exact Python-slice semantics of align_seq (alignment.py:37-49) for the primer
+// search window of match_one_end (demultiplex.py:757-758), including reads shorter than the
+// search length.
+
+struct Geo {
+    int n;       // read length
+    int woff;    // X index of staged symbol 0; the staged buffer is X[woff : n]
+    int wl;      // staged symbols = min(n, L)
+    int start;   // staged index where the primer search window begins
+    int wlen;    // primer search window length
+    int delta;   // reported coordinate = X index + delta
+    bool regular;
+};
+
+SMX_HD Geo make_geo(int n, int L) {
+    Geo g;
+    g.n = n;
+    int raw = n - L;                       // search_start (demultiplex.py:757)
+    g.woff = raw > 0 ? raw : 0;
+    g.wl = n - g.woff;
+    int off, shift;
+    if (raw >= 0) { off = raw; shift = raw; }
+    else if (raw == -1) { off = 0; shift = 0; }                    // alignment.py:37
+    else { off = n + raw; if (off < 0) off = 0; shift = raw; }      // negative Python slice start
+    g.start = off - g.woff;
+    g.wlen = n - off;
+    g.delta = shift - off;
+    g.regular = raw >= -1;
+    return g;
+}
+
+// Barcode flank of match_one_end (demultiplex.py:787-800) for a primer end reported at e_rep.
+struct Flank {
+    int bs;        // barcode_search_start as passed to align_seq
+    int a_align;   // X index where the aligned flank starts (alignment.py:37-40)
+    int a_pref;    // X index where the prefilter's flank starts (demultiplex.py:789)
+    int bshift;    // value added to SHW locations (alignment.py:49)
+};
+
+SMX_HD Flank make_flank(int e_rep, int n) {
+    Flank f;
+    f.bs = e_rep + 1;
+    if (f.bs == -1) {
+        f.a_align = 0; f.bshift = 0;
+        f.a_pref = n > 0 ? n - 1 : 0;
+    } else if (f.bs < 0) {
+        int a = n + f.bs; if (a < 0) a = 0;
+        f.a_align = f.a_pref = a; f.bshift = f.bs;
+    } else {
+        int a = f.bs < n ? f.bs : n;
+        f.a_align = f.a_pref = a; f.bshift = f.bs;
+    }
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Myers / Hyyro bit-vector column step.  The pattern is TOP-aligned in the word (row m is the
+// sign bit) so the score delta of the last row is a plain shift.  Bits below the pattern are
+// neutral: HW initialises them Pv=1 (they keep emitting Ph=Mh=0, i.e. D[0][j]=0), SHW/NW shift a 1
+// in at bit 0 every column (D[0][j]=j).  Restates edlib's calculateBlock (the arithmetic behind
+// alignment.py:42) for a single block.
+
+template <typename W> struct WordBits;
+template <> struct WordBits<u32> { static constexpr int bits = 32; };
+template <> struct WordBits<u64> { static constexpr int bits = 64; };
+
+template <typename W, bool kShiftInOne>
+SMX_HD int myers_step(W Eq, W &Pv, W &Mv) {
+    constexpr int B = WordBits<W>::bits;
+    W Xv = Eq | Mv;
+    W Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    W Ph = Mv | ~(Xh | Pv);
+    W Mh = Pv & Xh;
+    int d = (int)(Ph >> (B - 1)) - (int)(Mh >> (B - 1));
+    Ph = (Ph << 1) | (W)(kShiftInOne ? 1 : 0);
+    Mh = Mh << 1;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+    return d;
+}
+
+template <typename W> SMX_HD W pattern_mask(int m) {
+    constexpr int B = WordBits<W>::bits;
+    return m >= B ? ~(W)0 : (~(W)0) << (B - m);
+}
+
+// Peq tables are stored as u64 with the pattern top-aligned at bit 63; a 32-bit kernel uses the
+// high half.
+template <typename W> SMX_HD W peq_word(u64 v);
+template <> SMX_HD u32 peq_word<u32>(u64 v) { return (u32)(v >> 32); }
+template <> SMX_HD u64 peq_word<u64>(u64 v) { return v; }
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident tables (plain pointers; filled by smx_api.cu).
+
+struct Tables {
+    int n_primers, n_pairs, n_specimens, n_keys;
+    int L, wpw, mw;                 // search_len, staged words per window (8 syms/word), mask words
+    int k_idx, blen_max;
+    int preorient, prefilter, trim, derep_best, min_length, max_length;
+    int total_bslots;               // sum over (strand, primer) of barcode-list lengths
+    int use64;                      // any primer longer than 32
+    int buse64;                     // any barcode longer than 32 - k (needs 64-bit words / masks)
+
+    unsigned char p_len[SMX_MAX_PRIMERS];
+    signed char p_k[SMX_MAX_PRIMERS];
+    unsigned char p_dir[SMX_MAX_PRIMERS];
+    int p_fidx[SMX_MAX_PRIMERS];
+    u32 pb_off[SMX_MAX_PRIMERS + 1];
+    u32 bslot_base[2 * SMX_MAX_PRIMERS];
+
+    const u64 *peq_rc;       // [primer][16]   primer_rc, top-aligned
+    const u64 *peq_rcrev;    // [primer][16]   reversed primer_rc (start-recovery pass)
+    const u64 *peq_fw;       // [primer][16]   forward-sense primer (explicit orientation test)
+    const u64 *bpeq;         // [list entry][16] barcode_rc
+    const unsigned char *b_len;    // [list entry]
+    const u32 *pb_barcode;   // [list entry] global barcode id
+
+    const u32 *pair_fwd, *pair_rev;
+    const i32 *pair_pool;
+
+    const u64 *spec_key;     // sorted unique (b1 << 32 | b2)
+    const u32 *spec_key_off; // n_keys+1 -> rows of that key in file order
+    const u32 *spec_row;     // row indices
+    const u64 *spec_p1_mask, *spec_p2_mask;   // by row
+    const i32 *spec_pool;    // by row
+};
+
+// Per-batch device buffers.
+struct Batch {
+    u32 n_reads, n_pad;
+    const u32 *packed2;
+    const u64 *word_off;
+    const u32 *lengths;
+    const u32 *packed4;
+    const u64 *off4;         // nullptr when no read is flagged
+    u32 *win;                // staged 4-bit windows [(strand*wpw + w) * n_pad + read]
+    // level-1 results
+    smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
+    u32 *endmask;            // [(slot*mw + w) * n_pad + read]
+    unsigned char *orient_hit;   // [slot * n_pad + read]  explicit orientation test (irregular reads)
+    smx_barcode_hit *bhit;   // [bslot * n_pad + read]
+    // level-2 results
+    u32 *rec_count;          // per read
+    u32 *rec_offset;         // exclusive scan (n_reads + 1)
+    smx_record *records;
+    unsigned char *read_flags;   // bit0: read had a full match; bit1: internal cap overflow
+    unsigned long long *counters;    // [0] HW cells [1] SHW cells [2] HW wordcols [3] SHW wordcols
+};
+
+SMX_HD bool read_is_flagged(const Batch &b, u32 r) {
+    return b.off4 != nullptr && b.off4[r] != ~0ull;
+}
+
+// Symbol x of strand `strand` of read r, straight from the packed streams.
+SMX_HD int sym_at(const Batch &b, u32 r, int strand, int x, int n) {
+    if (read_is_flagged(b, r)) {
+        u64 base = b.off4[r] + (strand ? (u64)((n + 7) >> 3) : 0);
+        u32 w = b.packed4[base + (u64)(x >> 3)];
+        return (int)((w >> (4 * (x & 7))) & 15);
+    }
+    int i = strand ? n - 1 - x : x;
+    u32 w = b.packed2[b.word_off[r] + (u64)(i >> 4)];
+    int c = (int)((w >> (2 * (i & 15))) & 3);
+    return strand ? 3 - c : c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Primer HW search over the staged window (demultiplex.py:765 -> alignment.py:21-50 -> edlib HW).
+// `load(p)` returns the 4-bit symbol at staged position p.
+
+template <typename W> struct HwResult {
+    int best;       // min over columns of D[m][j]
+    int first;      // staged position of the first column attaining `best`
+};
+
+// Start recovery (edlib: reverse SHW pass with k = best, LAST equal-best end wins).
+// Returns the number of columns walked back from the end to the start: start = end - ret.
+template <typename W, typename Load>
+SMX_HD int hw_start_back(const u64 *peq_rev, int m, int best, int e_pos, int start_pos, Load load) {
+    W Pv = pattern_mask<W>(m), Mv = 0;
+    int score = m;
+    int cols = e_pos - start_pos + 1;
+    int lim = m + best;
+    if (cols > lim) cols = lim;
+    int last = m - 1;           // falls back to an m-long hit (never used: a best column exists)
+    for (int j = 0; j < cols; ++j) {
+        int c = load(e_pos - j);
+        W Eq = peq_word<W>(peq_rev[c]);
+        score += myers_step<W, true>(Eq, Pv, Mv);
+        if (score == best) last = j;
+    }
+    return last;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Barcode SHW search (demultiplex.py:799-800).  Only the first m+k flank columns can hold a
+// distance <= k, so at most m+k <= 64 columns are processed and the equal-best ends fit a u64.
+
+template <typename W, typename Load>
+SMX_HD void shw_search(const u64 *peq, int m, int cols, Load load, int &best, u64 &mask) {
+    W Pv = pattern_mask<W>(m), Mv = 0;
+    int score = m;
+    best = m + 1;
+    mask = 0;
+    for (int j = 0; j < cols; ++j) {
+        int c = load(j);
+        W Eq = peq_word<W>(peq[c]);
+        score += myers_step<W, true>(Eq, Pv, Mv);
+        if (score < best) { best = score; mask = 0; }
+        if (score == best) mask |= 1ull << j;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Specimen lookup (databases.py:219-245).
+
+SMX_HD int spec_find_key(const Tables &t, u32 b1, u32 b2) {
+    u64 key = ((u64)b1 << 32) | b2;
+    int lo = 0, hi = t.n_keys - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        u64 v = t.spec_key[mid];
+        if (v == key) return mid;
+        if (v < key) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+// First specimen row (file order) with exactly (b1, b2, p1, p2); -1 if none.  specimen_for_exact_match.
+SMX_HD int spec_exact(const Tables &t, u32 b1, u32 b2, int p1, int p2) {
+    int k = spec_find_key(t, b1, b2);
+    if (k < 0) return -1;
+    for (u32 i = t.spec_key_off[k]; i < t.spec_key_off[k + 1]; ++i) {
+        u32 row = t.spec_row[i];
+        if (((t.spec_p1_mask[row] >> p1) & 1) && ((t.spec_p2_mask[row] >> p2) & 1)) return (int)row;
+    }
+    return -1;
+}
+
+// Count of rows matching (b1, b2, p1, p2) and the smallest such row.  specimens_for_barcodes_and_primers.
+SMX_HD void spec_all(const Tables &t, u32 b1, u32 b2, int p1, int p2, int &count, int &min_row) {
+    int k = spec_find_key(t, b1, b2);
+    if (k < 0) return;
+    for (u32 i = t.spec_key_off[k]; i < t.spec_key_off[k + 1]; ++i) {
+        u32 row = t.spec_row[i];
+        if (((t.spec_p1_mask[row] >> p1) & 1) && ((t.spec_p2_mask[row] >> p2) & 1)) {
+            ++count;
+            if (min_row < 0 || (int)row < min_row) min_row = (int)row;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Selection / dereplication / specimen resolution / trimming for one read
+// (demultiplex.py:126-210, 216-598; models.py:72-328).  One thread runs this per read.
+
+struct EndInfo {            // one (strand, primer) slot as seen by a candidate
+    int matched;
+    int pd;                 // primer distance
+    int ps, pe;             // first location, reported X coordinates
+    int nhits;              // barcodes within k_idx
+    int bd;                 // best barcode distance
+    int nbest;              // number of barcodes at bd
+    int best[kMaxTies];     // their list positions (ascending = pinned order)
+    int strand, primer;
+};
+
+struct SelectCtx {
+    const Tables *t;
+    const Batch *b;
+    u32 read;
+    int n;
+};
+
+SMX_HD u32 slot_index(const Tables &t, int strand, int primer) { return (u32)(strand * t.n_primers + primer); }
+
+SMX_HD const smx_barcode_hit &bhit_at(const SelectCtx &c, int strand, int primer, int j) {
+    u64 bslot = (u64)c.t->bslot_base[slot_index(*c.t, strand, primer)] + (u64)j;
+    return c.b->bhit[bslot * c.b->n_pad + c.read];
+}
+
+SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e, bool &overflow) {
+    const Tables &t = *c.t;
+    const smx_primer_hit &ph = c.b->phit[(u64)slot_index(t, strand, primer) * c.b->n_pad + c.read];
+    e.strand = strand; e.primer = primer;
+    e.matched = ph.distance >= 0;
+    e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
+    e.nhits = 0; e.bd = -1; e.nbest = 0;
+    if (!e.matched) return;
+    int nb = (int)(t.pb_off[primer + 1] - t.pb_off[primer]);
+    int bd = 1 << 20;
+    for (int j = 0; j < nb; ++j) {
+        int d = bhit_at(c, strand, primer, j).distance;
+        if (d < 0) continue;
+        ++e.nhits;
+        if (d < bd) { bd = d; e.nbest = 0; }
+        if (d == bd) {
+            if (e.nbest < kMaxTies) e.best[e.nbest] = j; else overflow = true;
+            ++e.nbest;
+        }
+    }
+    if (e.nhits) e.bd = bd;
+    if (e.nbest > kMaxTies) e.nbest = kMaxTies;
+}
+
+struct Cand {               // CandidateMatch (models.py:72-95) by reference to its two ends
+    int pair, rc;           // rc = 1: candidate built on the reverse-complemented read
+    int e1, e2;             // indices into the per-read EndInfo cache (always valid)
+};
+
+SMX_HD int cand_score(const EndInfo &a, const EndInfo &b) {   // demultiplex.py:226-236
+    bool p1 = a.matched, p2 = b.matched, b1 = a.nhits > 0, b2 = b.nhits > 0;
+    if (p1 && p2 && b1 && b2) return 5;
+    if (p1 && p2 && (b1 || b2)) return 4;
+    if ((p1 || p2) && (b1 || b2)) return 3;
+    if (p1 && p2) return 2;
+    if (p1 || p2) return 1;
+    return 0;
+}
+
+// Emits records for one read.  `emit` = nullptr counts only.  Returns the number of records.
+struct Emitter {
+    smx_record *out;        // may be nullptr (count pass)
+    u32 count;
+    bool full;
+};
+
+struct TrimState {          // cumulative trim_locations() shift per candidate
+    int cand[kMaxGroups];
+    int shift[kMaxGroups];
+    int n;
+};
+
+SMX_HD int trim_shift_get(const TrimState &s, int cand) {
+    for (int i = 0; i < s.n; ++i) if (s.cand[i] == cand) return s.shift[i];
+    return 0;
+}
+SMX_HD void trim_shift_add(TrimState &s, int cand, int v, bool &overflow) {
+    for (int i = 0; i < s.n; ++i) if (s.cand[i] == cand) { s.shift[i] += v; return; }
+    if (s.n < kMaxGroups) { s.cand[s.n] = cand; s.shift[s.n] = v; ++s.n; } else overflow = true;
+}
+
+// intertail_extent's folds over barcode locations with the reference's -1 sentinel
+// (models.py:300-319).  Hits are visited in stable distance order, locations ascending.
+SMX_HD void tails_fold(const SelectCtx &c, const EndInfo &e, bool is_b1, int shift, int &acc) {
+    if (!e.matched || e.nhits == 0) return;
+    const Tables &t = *c.t;
+    int nb = (int)(t.pb_off[e.primer + 1] - t.pb_off[e.primer]);
+    for (int d = 0; d <= t.k_idx; ++d) {
+        for (int j = 0; j < nb; ++j) {
+            const smx_barcode_hit &h = bhit_at(c, e.strand, e.primer, j);
+            if (h.distance != d) continue;
+            int bshift = h.search_start == -1 ? 0 : h.search_start;
+            u64 m = h.end_mask;
+            while (m) {
+#if defined(__CUDA_ARCH__)
+                int col = __ffsll((long long)m) - 1;
+#else
+                int col = __builtin_ctzll(m);
+#endif
+                m &= m - 1;
+                int s_x = bshift, e_x = bshift + col;          // SHW location in X coordinates
+                if (is_b1) {
+                    int l0 = c.n - e_x - 1 - shift;             // reversed(): (len-e-1, len-s-1)
+                    acc = (acc == -1) ? l0 : (l0 < acc ? l0 : acc);
+                } else {
+                    int l1 = e_x + 1 - shift;
+                    acc = (acc == -1) ? l1 : (l1 > acc ? l1 : acc);
+                }
+                (void)s_x;
+            }
+        }
+    }
+}
+
+SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &overflow,
+                        int cand_idx, const Cand &cd, const EndInfo &e1, const EndInfo &e2,
+                        int sample, int resolution, int pool) {
+    const Tables &t = *c.t;
+    int n = c.n;
+    int shift = trim_shift_get(ts, cand_idx);
+    bool m1 = e1.matched, m2 = e2.matched;
+    // candidate coordinates (p1/b1 were searched on the opposite strand and reversed, models.py:52-63)
+    int p1s = kNone, p1e = kNone, p2s = kNone, p2e = kNone;
+    if (m1) { p1s = n - e1.pe - 1 - shift; p1e = n - e1.ps - 1 - shift; }
+    if (m2) { p2s = e2.ps - shift; p2e = e2.pe - shift; }
+    int b1s = kNone, b1e = kNone, b2s = kNone, b2e = kNone;
+    if (m1 && e1.nhits) {
+        const smx_barcode_hit &h = bhit_at(c, e1.strand, e1.primer, e1.best[0]);
+        int bshift = h.search_start == -1 ? 0 : h.search_start;
+#if defined(__CUDA_ARCH__)
+        int col = __ffsll((long long)h.end_mask) - 1;
+#else
+        int col = __builtin_ctzll(h.end_mask);
+#endif
+        b1s = n - (bshift + col) - 1 - shift; b1e = n - bshift - 1 - shift;
+    }
+    if (m2 && e2.nhits) {
+        const smx_barcode_hit &h = bhit_at(c, e2.strand, e2.primer, e2.best[0]);
+        int bshift = h.search_start == -1 ? 0 : h.search_start;
+#if defined(__CUDA_ARCH__)
+        int col = __ffsll((long long)h.end_mask) - 1;
+#else
+        int col = __builtin_ctzll(h.end_mask);
+#endif
+        b2s = bshift - shift; b2e = bshift + col - shift;
+    }
+    int s = 0, e = n;
+    bool empty = false;
+    if (t.trim != SMX_TRIM_NONE) {
+        int ps = m1 ? p1e + 1 : 0;                 // interprimer_extent, models.py:278-287
+        int pe = m2 ? p2s : n;
+        if (t.trim == SMX_TRIM_PRIMERS) { s = ps; e = pe; }
+        else if (t.trim == SMX_TRIM_BARCODES) {     // models.py:289-298
+            s = m1 ? p1s : 0;
+            e = m2 ? p2e + 1 : n;
+        } else {                                    // models.py:300-319
+            int fs = -1, fe = -1;
+            tails_fold(c, e1, true, shift, fs);
+            tails_fold(c, e2, false, shift, fe);
+            if (fs == -1) { fs = ps - t.blen_max; if (fs < 0) fs = 0; }
+            if (fe == -1) { fe = pe + t.blen_max; if (fe > n) fe = n; }
+            s = fs; e = fe;
+        }
+        if (s >= e) empty = true;                   // demultiplex.py:47
+    }
+    if (em.out) {
+        smx_record &r = em.out[em.count];
+        r.read = c.read;
+        r.reverse = (unsigned char)cd.rc;
+        r.candidate = (unsigned char)cand_idx;
+        r.dist[0] = (signed char)(m1 ? e1.pd : -1);
+        r.dist[1] = (signed char)((m1 && e1.nhits) ? e1.bd : -1);
+        r.dist[2] = (signed char)((m2 && e2.nhits) ? e2.bd : -1);
+        r.dist[3] = (signed char)(m2 ? e2.pd : -1);
+        r.pad[0] = r.pad[1] = 0;
+        if (empty) {
+            r.sample = -1; r.resolution = SMX_RES_UNKNOWN; r.pool = -1; r.p1 = -1; r.p2 = -1;
+            r.trim_start = 0; r.trim_end = n; r.trim_empty = 1;
+            r.p1_loc[0] = p1s; r.p1_loc[1] = p1e; r.p2_loc[0] = p2s; r.p2_loc[1] = p2e;
+            r.b1_loc[0] = b1s; r.b1_loc[1] = b1e; r.b2_loc[0] = b2s; r.b2_loc[1] = b2e;
+        } else {
+            int ds = (t.trim != SMX_TRIM_NONE) ? s : 0;   // trim_locations(s), demultiplex.py:76
+            r.sample = sample; r.resolution = (unsigned char)resolution; r.pool = (int16_t)pool;
+            r.p1 = (int16_t)(m1 ? e1.primer : -1); r.p2 = (int16_t)(m2 ? e2.primer : -1);
+            r.trim_start = s; r.trim_end = e; r.trim_empty = 0;
+            r.p1_loc[0] = m1 ? p1s - ds : kNone; r.p1_loc[1] = m1 ? p1e - ds : kNone;
+            r.p2_loc[0] = m2 ? p2s - ds : kNone; r.p2_loc[1] = m2 ? p2e - ds : kNone;
+            r.b1_loc[0] = b1s == kNone ? kNone : b1s - ds; r.b1_loc[1] = b1e == kNone ? kNone : b1e - ds;
+            r.b2_loc[0] = b2s == kNone ? kNone : b2s - ds; r.b2_loc[1] = b2e == kNone ? kNone : b2e - ds;
+        }
+    }
+    if (!empty && t.trim != SMX_TRIM_NONE) trim_shift_add(ts, cand_idx, s, overflow);
+    ++em.count;
+}
+
+// resolve_specimen (demultiplex.py:541-598).
+SMX_HD void resolve(const SelectCtx &c, const EndInfo &e1, const EndInfo &e2, int pair_pool,
+                    int &sample, int &resolution, int &pool) {
+    const Tables &t = *c.t;
+    sample = -1; pool = pair_pool; resolution = SMX_RES_UNKNOWN;
+    bool b1 = e1.matched && e1.nhits > 0, b2 = e2.matched && e2.nhits > 0;
+    if (e1.matched && e2.matched && b1 && b2) {
+        int count = 0, min_row = -1;
+        for (int i = 0; i < e1.nbest; ++i)
+            for (int j = 0; j < e2.nbest; ++j)
+                spec_all(t, t.pb_barcode[t.pb_off[e1.primer] + e1.best[i]],
+                         t.pb_barcode[t.pb_off[e2.primer] + e2.best[j]], e1.primer, e2.primer, count, min_row);
+        if (count > 1) { sample = min_row; resolution = SMX_RES_MULTIPLE_SPECIMENS; pool = t.spec_pool[min_row]; }
+        else if (count == 1) { sample = min_row; resolution = SMX_RES_FULL_MATCH; pool = t.spec_pool[min_row]; }
+        return;
+    }
+    if (b1 && !b2 && e1.nbest == 1) {
+        resolution = SMX_RES_PARTIAL_FORWARD;
+        sample = (int)t.pb_barcode[t.pb_off[e1.primer] + e1.best[0]];
+    } else if (b2 && !b1 && e2.nbest == 1) {
+        resolution = SMX_RES_PARTIAL_REVERSE;
+        sample = (int)t.pb_barcode[t.pb_off[e2.primer] + e2.best[0]];
+    }
+}
+
+struct Group {      // one dereplication group (demultiplex.py:322-382 / :416-467)
+    int key;        // specimen row, or for partial groups (direction << 30 | global barcode id)
+    int cand;       // best candidate so far
+    int k0, k1, k2, k3;   // sort key of the best
+};
+
+SMX_HD bool key_less(int a0, int a1, int a2, int a3, const Group &g) {
+    if (a0 != g.k0) return a0 < g.k0;
+    if (a1 != g.k1) return a1 < g.k1;
+    if (a2 != g.k2) return a2 < g.k2;
+    return a3 < g.k3;
+}
+
+// Whole per-read selection.  ends: cache of 2*n_primers EndInfo (index strand*n_primers+primer).
+SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsigned char &flags) {
+    const Tables &t = *c.t;
+    const Batch &b = *c.b;
+    Emitter em; em.out = out; em.count = 0; em.full = false;
+    TrimState ts; ts.n = 0;
+    bool overflow = false;
+    int n = c.n;
+    flags = 0;
+    if ((t.min_length != -1 && n < t.min_length) || (t.max_length != -1 && n > t.max_length)) return 0;
+
+    Geo g = make_geo(n, t.L);
+    bool irregular = !g.regular || read_is_flagged(b, c.read);
+    for (int s = 0; s < 2; ++s)
+        for (int p = 0; p < t.n_primers; ++p) load_end(c, s, p, ends[s * t.n_primers + p], overflow);
+
+    // determine_orientation (demultiplex.py:602-638).  For regular reads the head-window test of a
+    // forward-sense primer equals the tail-window match of its reverse complement on the other
+    // strand, so it is read off the slots; irregular reads ran it explicitly.
+    int orient = 3;
+    if (t.preorient) {
+        int fwd = 0, rev = 0;
+        for (int p = 0; p < t.n_primers; ++p) {
+            int hit_s, hit_rs;   // forward-sense primer found in head of s / head of rs
+            if (irregular) {
+                hit_s = b.orient_hit[(u64)slot_index(t, 0, p) * b.n_pad + c.read];
+                hit_rs = b.orient_hit[(u64)slot_index(t, 1, p) * b.n_pad + c.read];
+            } else {
+                hit_s = ends[1 * t.n_primers + p].matched;
+                hit_rs = ends[0 * t.n_primers + p].matched;
+            }
+            if (t.p_dir[p] == 0) { fwd += hit_s; rev += hit_rs; }
+            else { fwd += hit_rs; rev += hit_s; }
+        }
+        orient = (fwd > 0 && rev == 0) ? 1 : (rev > 0 && fwd == 0) ? 2 : 3;
+    }
+
+    // find_candidate_matches (demultiplex.py:699-741) + select_best_matches (:216-259)
+    int top = 0;
+    for (int pr = 0; pr < t.n_pairs; ++pr)
+        for (int rc = 0; rc < 2; ++rc) {
+            if (rc == 0 ? (orient == 2) : (orient == 1)) continue;
+            const EndInfo &a = ends[(rc ? 0 : 1) * t.n_primers + (int)t.pair_fwd[pr]];
+            const EndInfo &z = ends[(rc ? 1 : 0) * t.n_primers + (int)t.pair_rev[pr]];
+            int sc = cand_score(a, z);
+            if (sc > top) top = sc;
+        }
+    if (top == 0) {
+        // no candidate at all: minimal match object (demultiplex.py:202-210)
+        EndInfo none; none.matched = 0; none.nhits = 0; none.nbest = 0; none.pd = -1; none.bd = -1;
+        none.ps = none.pe = 0; none.strand = 0; none.primer = 0;
+        Cand cd; cd.pair = -1; cd.rc = 0; cd.e1 = cd.e2 = 0;
+        emit_record(c, em, ts, overflow, 0, cd, none, none, -1, SMX_RES_UNKNOWN, -1);
+        if (overflow) flags |= 2;
+        return em.count;
+    }
+
+    // Walk the equal-best candidates in reference order.  Candidate index = position among *kept*
+    // candidates (match_counter, demultiplex.py:702,720).
+    auto for_each_top = [&](auto &&fn) {
+        int kept = 0;
+        for (int pr = 0; pr < t.n_pairs; ++pr)
+            for (int rc = 0; rc < 2; ++rc) {
+                if (rc == 0 ? (orient == 2) : (orient == 1)) continue;
+                int i1 = (rc ? 0 : 1) * t.n_primers + (int)t.pair_fwd[pr];
+                int i2 = (rc ? 1 : 0) * t.n_primers + (int)t.pair_rev[pr];
+                int sc = cand_score(ends[i1], ends[i2]);
+                if (sc == 0) continue;
+                int idx = kept++;
+                if (sc != top) continue;
+                Cand cd; cd.pair = pr; cd.rc = rc; cd.e1 = i1; cd.e2 = i2;
+                fn(idx, cd);
+            }
+    };
+
+    if (!t.derep_best) {
+        for_each_top([&](int idx, const Cand &cd) {
+            int sample, res, pool;
+            resolve(c, ends[cd.e1], ends[cd.e2], t.pair_pool[cd.pair], sample, res, pool);
+            emit_record(c, em, ts, overflow, idx, cd, ends[cd.e1], ends[cd.e2], sample, res, pool);
+            if (res == SMX_RES_FULL_MATCH) em.full = true;
+        });
+        if (em.full) flags |= 1;
+        if (overflow) flags |= 2;
+        return em.count;
+    }
+
+    // dereplicate_matches (demultiplex.py:262-393).  Groups in dict-insertion order; the None group
+    // is one entry (key -1) whose members are re-walked afterwards.
+    Group groups[kMaxGroups];
+    Cand gcand[kMaxGroups];
+    int ng = 0;
+    int none_pos = -1;
+    for_each_top([&](int idx, const Cand &cd) {
+        const EndInfo &a = ends[cd.e1];
+        const EndInfo &z = ends[cd.e2];
+        bool full = a.matched && z.matched && a.nhits > 0 && z.nhits > 0;
+        bool found = false;
+        if (full) {
+            for (int i = 0; i < a.nbest; ++i)
+                for (int j = 0; j < z.nbest; ++j) {
+                    int row = spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + a.best[i]],
+                                         t.pb_barcode[t.pb_off[z.primer] + z.best[j]], a.primer, z.primer);
+                    if (row < 0) continue;
+                    found = true;
+                    int k0 = a.bd + z.bd, k1 = a.pd + z.pd, k2 = t.p_fidx[a.primer] + t.p_fidx[z.primer];
+                    int gi = -1;
+                    for (int q = 0; q < ng; ++q) if (groups[q].key == row) { gi = q; break; }
+                    if (gi < 0) {
+                        if (ng >= kMaxGroups) { overflow = true; continue; }
+                        gi = ng++;
+                        groups[gi].key = row; groups[gi].cand = idx; gcand[gi] = cd;
+                        groups[gi].k0 = k0; groups[gi].k1 = k1; groups[gi].k2 = k2; groups[gi].k3 = 0;
+                    } else if (key_less(k0, k1, k2, 0, groups[gi])) {
+                        groups[gi].cand = idx; gcand[gi] = cd;
+                        groups[gi].k0 = k0; groups[gi].k1 = k1; groups[gi].k2 = k2;
+                    }
+                }
+        }
+        if (!found && none_pos < 0) {
+            if (ng >= kMaxGroups) { overflow = true; return; }
+            none_pos = ng;
+            groups[ng].key = -1; groups[ng].cand = -1; ++ng;
+        }
+    });
+
+    for (int gi = 0; gi < ng; ++gi) {
+        if (groups[gi].key >= 0) {
+            const Cand &cd = gcand[gi];
+            int row = groups[gi].key;
+            emit_record(c, em, ts, overflow, groups[gi].cand, cd, ends[cd.e1], ends[cd.e2], row,
+                        SMX_RES_DEREPLICATED_FULL, t.spec_pool[row]);
+            em.full = true;
+            continue;
+        }
+        // --- the None group: partials, unknowns, others (demultiplex.py:332-365) ---
+        auto in_none = [&](const Cand &cd) {
+            const EndInfo &a = ends[cd.e1];
+            const EndInfo &z = ends[cd.e2];
+            bool full = a.matched && z.matched && a.nhits > 0 && z.nhits > 0;
+            if (!full) return true;
+            for (int i = 0; i < a.nbest; ++i)
+                for (int j = 0; j < z.nbest; ++j)
+                    if (spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + a.best[i]],
+                                   t.pb_barcode[t.pb_off[z.primer] + z.best[j]], a.primer, z.primer) >= 0)
+                        return false;
+            return true;
+        };
+        // dereplicate_partial_matches (:396-477)
+        Group pg[kMaxGroups];
+        Cand pcand[kMaxGroups];
+        int npg = 0;
+        for_each_top([&](int idx, const Cand &cd) {
+            if (!in_none(cd)) return;
+            const EndInfo &a = ends[cd.e1];
+            const EndInfo &z = ends[cd.e2];
+            bool hb1 = a.matched && a.nhits > 0, hb2 = z.matched && z.nhits > 0;
+            if (hb1 == hb2) return;
+            const EndInfo &be = hb1 ? a : z;
+            int pcnt = (a.matched ? 1 : 0) + (z.matched ? 1 : 0);
+            int pdist = (a.matched ? a.pd : 0) + (z.matched ? z.pd : 0);
+            int fidx = (a.matched ? t.p_fidx[a.primer] : 0) + (z.matched ? t.p_fidx[z.primer] : 0);
+            for (int i = 0; i < be.nbest; ++i) {
+                int key = (hb1 ? 0 : (1 << 30)) | (int)t.pb_barcode[t.pb_off[be.primer] + be.best[i]];
+                int q = -1;
+                for (int x = 0; x < npg; ++x) if (pg[x].key == key) { q = x; break; }
+                if (q < 0) {
+                    if (npg >= kMaxGroups) { overflow = true; continue; }
+                    q = npg++;
+                    pg[q].key = key; pg[q].cand = idx; pcand[q] = cd;
+                    pg[q].k0 = be.bd; pg[q].k1 = -pcnt; pg[q].k2 = pdist; pg[q].k3 = fidx;
+                } else if (key_less(be.bd, -pcnt, pdist, fidx, pg[q])) {
+                    pg[q].cand = idx; pcand[q] = cd;
+                    pg[q].k0 = be.bd; pg[q].k1 = -pcnt; pg[q].k2 = pdist; pg[q].k3 = fidx;
+                }
+            }
+        });
+        for (int q = 0; q < npg; ++q) {
+            const Cand &cd = pcand[q];
+            int sample, res, pool;
+            resolve(c, ends[cd.e1], ends[cd.e2], t.pair_pool[cd.pair], sample, res, pool);
+            emit_record(c, em, ts, overflow, pg[q].cand, cd, ends[cd.e1], ends[cd.e2], sample, res, pool);
+            if (res == SMX_RES_FULL_MATCH) em.full = true;
+        }
+        // dereplicate_unknown_matches (:480-538)
+        Group ug; ug.cand = -1; ug.key = 0; ug.k0 = ug.k1 = ug.k2 = ug.k3 = 0;
+        Cand ucand; ucand.pair = 0; ucand.rc = 0; ucand.e1 = ucand.e2 = 0;
+        for_each_top([&](int idx, const Cand &cd) {
+            if (!in_none(cd)) return;
+            const EndInfo &a = ends[cd.e1];
+            const EndInfo &z = ends[cd.e2];
+            bool hb1 = a.matched && a.nhits > 0, hb2 = z.matched && z.nhits > 0;
+            if (hb1 || hb2) return;
+            int pcnt = (a.matched ? 1 : 0) + (z.matched ? 1 : 0);
+            int pdist = (a.matched ? a.pd : 0) + (z.matched ? z.pd : 0);
+            int fidx = (a.matched ? t.p_fidx[a.primer] : 999) + (z.matched ? t.p_fidx[z.primer] : 999);
+            if (ug.cand < 0 || key_less(-pcnt, pdist, fidx, 0, ug)) {
+                ug.cand = idx; ucand = cd; ug.k0 = -pcnt; ug.k1 = pdist; ug.k2 = fidx; ug.k3 = 0;
+            }
+        });
+        if (ug.cand >= 0) {
+            int sample, res, pool;
+            resolve(c, ends[ucand.e1], ends[ucand.e2], t.pair_pool[ucand.pair], sample, res, pool);
+            emit_record(c, em, ts, overflow, ug.cand, ucand, ends[ucand.e1], ends[ucand.e2], sample, res, pool);
+        }
+        // others: both barcodes but no specimen (:361-363)
+        for_each_top([&](int idx, const Cand &cd) {
+            if (!in_none(cd)) return;
+            const EndInfo &a = ends[cd.e1];
+            const EndInfo &z = ends[cd.e2];
+            bool hb1 = a.matched && a.nhits > 0, hb2 = z.matched && z.nhits > 0;
+            if (!(hb1 && hb2)) return;
+            int sample, res, pool;
+            resolve(c, a, z, t.pair_pool[cd.pair], sample, res, pool);
+            emit_record(c, em, ts, overflow, idx, cd, a, z, sample, res, pool);
+            if (res == SMX_RES_FULL_MATCH) em.full = true;
+        });
+    }
+    if (em.full) flags |= 1;
+    if (overflow) flags |= 2;
+    return em.count;
+}
+
+}  // namespace smx

@@ -1,0 +1,196 @@
+// smx_host_tables.hpp -- host-side construction of the match tables (shared by the CUDA API and
+// the CPU kernel simulator used in unit tests).  Builds IUPAC-aware Peq masks with edlib's
+// additionalEqualities semantics (reference: constants.py:13-20, alignment.py:42) and the
+// (b1, b2) -> specimen rows lookup (databases.py:219-245).
+#pragma once
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "smx_core.cuh"
+
+namespace smx {
+
+static const char kCodes[] = "ACGTRYSWKMBDHVN";
+
+inline int code_of(char ch) {
+    const char *p = strchr(kCodes, ch);
+    return (p && ch) ? (int)(p - kCodes) : -1;
+}
+
+// base set of an IUPAC code as a 4-bit mask over A,C,G,T (constants.py:13-20)
+inline int base_set(int code) {
+    static const int sets[15] = {1, 2, 4, 8, 1 | 4, 2 | 8, 2 | 4, 1 | 8, 4 | 8, 1 | 2,
+                                 2 | 4 | 8, 1 | 4 | 8, 1 | 2 | 8, 1 | 2 | 4, 15};
+    return sets[code];
+}
+
+// edlib additionalEqualities semantics: a == b, or (code, base) listed in either order.
+inline bool sym_equal(int pat, int rd) {
+    if (rd == kSymOther) return false;
+    if (pat == rd) return true;
+    if (pat >= 4 && rd < 4) return (base_set(pat) >> rd) & 1;
+    if (rd >= 4 && pat < 4) return (base_set(rd) >> pat) & 1;
+    return false;
+}
+
+inline bool build_peq(const char *s, int m, bool reversed, u64 *out /*16*/) {
+    for (int c = 0; c < 16; ++c) out[c] = 0;
+    for (int i = 0; i < m; ++i) {
+        int pc = code_of(s[reversed ? m - 1 - i : i]);
+        if (pc < 0) return false;
+        for (int c = 0; c < 16; ++c)
+            if (sym_equal(pc, c)) out[c] |= 1ull << (64 - m + i);
+    }
+    return true;
+}
+
+
+struct HostTables {
+    Tables t;
+    std::vector<u64> peq_rc, peq_rcrev, peq_fw, bpeq, spec_key, spec_p1, spec_p2;
+    std::vector<unsigned char> b_len;
+    std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row;
+    std::vector<i32> pair_pool, spec_pool;
+    int max_nb = 0;
+    std::string error;
+
+    bool err(const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        error = buf;
+        return false;
+    }
+
+    // Validates and builds everything; on success `t` holds HOST pointers into the vectors.
+    bool build(const smx_tables *tb, const smx_params *pr) {
+        if (!tb || !pr) return err("null argument");
+        if (tb->n_primers == 0 || tb->n_primers > SMX_MAX_PRIMERS)
+            return err("n_primers=%u outside 1..%d", tb->n_primers, SMX_MAX_PRIMERS);
+        if (tb->n_pairs > (uint32_t)kMaxPairs) return err("%u primer pairs exceed the supported %d", tb->n_pairs, kMaxPairs);
+        if (pr->search_len < 1 || pr->search_len > SMX_MAX_SEARCH_LEN)
+            return err("search_len=%d outside 1..%d", pr->search_len, SMX_MAX_SEARCH_LEN);
+        if (pr->trim < SMX_TRIM_NONE || pr->trim > SMX_TRIM_TAILS) return err("bad trim mode");
+        memset(&t, 0, sizeof(t));
+        const int nP = (int)tb->n_primers;
+        t.n_primers = nP; t.n_pairs = (int)tb->n_pairs; t.n_specimens = (int)tb->n_specimens;
+        t.L = pr->search_len; t.wpw = (t.L + 7) / 8; t.mw = (t.L + 31) / 32;
+        t.k_idx = pr->max_dist_index; t.blen_max = pr->barcode_length;
+        t.preorient = pr->preorient != 0; t.prefilter = pr->prefilter != 0; t.trim = pr->trim;
+        t.derep_best = pr->dereplicate_best != 0; t.min_length = pr->min_length; t.max_length = pr->max_length;
+        if (t.k_idx < 0) return err("negative barcode distance threshold");
+
+        peq_rc.assign((size_t)nP * 16, 0); peq_rcrev.assign((size_t)nP * 16, 0); peq_fw.assign((size_t)nP * 16, 0);
+        for (int p = 0; p < nP; ++p) {
+            int m = (int)(tb->primer_off[p + 1] - tb->primer_off[p]);
+            if (m < 1 || m > SMX_MAX_PATTERN) return err("primer %d length %d outside 1..%d", p, m, SMX_MAX_PATTERN);
+            int k = tb->primer_k[p];
+            if (k < 0 || k >= m) return err("primer %d max distance %d must be in [0, length %d)", p, k, m);
+            t.p_len[p] = (unsigned char)m; t.p_k[p] = (signed char)k; t.p_dir[p] = tb->primer_dir[p];
+            t.p_fidx[p] = tb->primer_file_index[p];
+            if (m > 32) t.use64 = 1;
+            if (!build_peq(tb->primer_rc + tb->primer_off[p], m, false, &peq_rc[(size_t)p * 16]) ||
+                !build_peq(tb->primer_rc + tb->primer_off[p], m, true, &peq_rcrev[(size_t)p * 16]) ||
+                !build_peq(tb->primer_seq + tb->primer_off[p], m, false, &peq_fw[(size_t)p * 16]))
+                return err("primer %d has a non-IUPAC character", p);
+            t.pb_off[p] = tb->pb_off[p];
+        }
+        t.pb_off[nP] = tb->pb_off[nP];
+        const u32 n_list = tb->pb_off[nP];
+        bpeq.assign((size_t)n_list * 16, 0);
+        b_len.assign(n_list, 0);
+        pb_barcode.assign(tb->pb_barcode, tb->pb_barcode + n_list);
+        max_nb = 0;
+        for (int p = 0; p < nP; ++p) {
+            int nb = (int)(tb->pb_off[p + 1] - tb->pb_off[p]);
+            max_nb = std::max(max_nb, nb);
+            bool fwd = tb->primer_dir[p] == 0;
+            for (u32 e = tb->pb_off[p]; e < tb->pb_off[p + 1]; ++e) {
+                u32 id = tb->pb_barcode[e];
+                if (id >= (fwd ? tb->n_b1 : tb->n_b2)) return err("barcode id out of range");
+                const u32 *off = fwd ? tb->b1_off : tb->b2_off;
+                const char *s = (fwd ? tb->b1_rc : tb->b2_rc) + off[id];
+                int m = (int)(off[id + 1] - off[id]);
+                if (m < 1 || m + t.k_idx > SMX_MAX_PATTERN)
+                    return err("barcode length %d + k %d exceeds %d", m, t.k_idx, SMX_MAX_PATTERN);
+                if (t.k_idx >= m) return err("barcode distance threshold %d must be below barcode length %d", t.k_idx, m);
+                if (m > 32) t.buse64 = 1;
+                if (!build_peq(s, m, false, &bpeq[(size_t)e * 16])) return err("barcode has a non-IUPAC character");
+                if (t.prefilter)
+                    for (int i = 0; i < m; ++i)
+                        if (code_of(s[i]) > 3)
+                            return err("Bloom-prefilter emulation needs A/C/G/T-only barcodes; pass prefilter=0 "
+                                       "(--disable-prefilter)");
+                b_len[e] = (unsigned char)m;
+            }
+        }
+        u32 run = 0;
+        for (int s = 0; s < 2; ++s)
+            for (int p = 0; p < nP; ++p) { t.bslot_base[s * nP + p] = run; run += tb->pb_off[p + 1] - tb->pb_off[p]; }
+        t.total_bslots = (int)run;
+
+        for (u32 i = 0; i < tb->n_pairs; ++i)
+            if (tb->pair_fwd[i] >= (u32)nP || tb->pair_rev[i] >= (u32)nP) return err("pair index out of range");
+        pair_fwd.assign(tb->pair_fwd, tb->pair_fwd + tb->n_pairs);
+        pair_rev.assign(tb->pair_rev, tb->pair_rev + tb->n_pairs);
+        pair_pool.assign(tb->pair_pool, tb->pair_pool + tb->n_pairs);
+
+        // specimen lookup: rows grouped by (b1, b2), file order inside a group
+        spec_row.resize(tb->n_specimens);
+        for (u32 i = 0; i < tb->n_specimens; ++i) spec_row[i] = i;
+        auto key_of = [&](u32 r) { return ((u64)tb->spec_b1[r] << 32) | tb->spec_b2[r]; };
+        std::stable_sort(spec_row.begin(), spec_row.end(), [&](u32 a, u32 c) { return key_of(a) < key_of(c); });
+        spec_key.clear(); spec_key_off.clear();
+        for (u32 i = 0; i < tb->n_specimens; ++i) {
+            u64 k = key_of(spec_row[i]);
+            if (spec_key.empty() || spec_key.back() != k) { spec_key.push_back(k); spec_key_off.push_back(i); }
+        }
+        spec_key_off.push_back(tb->n_specimens);
+        t.n_keys = (int)spec_key.size();
+        spec_p1.assign(tb->spec_p1_mask, tb->spec_p1_mask + tb->n_specimens);
+        spec_p2.assign(tb->spec_p2_mask, tb->spec_p2_mask + tb->n_specimens);
+        spec_pool.assign(tb->spec_pool, tb->spec_pool + tb->n_specimens);
+        for (u32 i = 0; i < tb->n_specimens; ++i)
+            if (tb->spec_pool[i] < -1 || tb->spec_pool[i] > 32767) return err("specimen pool id out of range");
+        set_pointers(peq_rc.data(), peq_rcrev.data(), peq_fw.data(), bpeq.data(), b_len.data(), pb_barcode.data(),
+                     pair_fwd.data(), pair_rev.data(), pair_pool.data(), spec_key.data(), spec_key_off.data(),
+                     spec_row.data(), spec_p1.data(), spec_p2.data(), spec_pool.data());
+        return true;
+    }
+
+    void set_pointers(const u64 *a, const u64 *b, const u64 *c, const u64 *d, const unsigned char *e, const u32 *f,
+                      const u32 *g, const u32 *h, const i32 *i, const u64 *j, const u32 *k, const u32 *l,
+                      const u64 *m, const u64 *n, const i32 *o) {
+        t.peq_rc = a; t.peq_rcrev = b; t.peq_fw = c; t.bpeq = d; t.b_len = e; t.pb_barcode = f;
+        t.pair_fwd = g; t.pair_rev = h; t.pair_pool = i; t.spec_key = j; t.spec_key_off = k; t.spec_row = l;
+        t.spec_p1_mask = m; t.spec_p2_mask = n; t.spec_pool = o;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Host-side packer (batching layer; no matching happens here).
+
+inline int read_code(unsigned char ch) {
+    switch (ch) {
+        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+        case 'R': return 4; case 'Y': return 5; case 'S': return 6; case 'W': return 7;
+        case 'K': return 8; case 'M': return 9; case 'B': return 10; case 'D': return 11;
+        case 'H': return 12; case 'V': return 13; case 'N': return 14;
+        default: return kSymOther;
+    }
+}
+
+// symbol of the reverse-complement strand for an input byte (Bio.Seq: complement, case kept, U->A)
+inline int read_code_rc(unsigned char ch) {
+    if (ch == 'U') return 0;
+    int c = read_code(ch);
+    return c == kSymOther ? kSymOther : sym_complement(c);
+}
+
+}  // namespace smx

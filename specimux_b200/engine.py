@@ -1,0 +1,189 @@
+"""Batching layer over the C ABI: pack reads, run the GPU path, hand back numpy records.
+
+`Matcher` owns one device context (one per GPU; not re-entrant).  There is no CPU path: a
+missing library raises ImportError, a missing GPU raises SmxError(SMX_ERR_NO_DEVICE).
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class PackedBatch:
+    """Reads in the smx_batch encoding (2-bit stream + optional exact 4-bit side stream)."""
+
+    def __init__(self, bases: Sequence[str], binding=None):
+        lib = (binding or _lib.load())
+        n = len(bases)
+        lens = np.fromiter((len(s) for s in bases), dtype=np.uint64, count=n)
+        seq_off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(lens, out=seq_off[1:])
+        blob = "".join(bases).encode("latin-1", "replace")
+        self._init_from_blob(lib, blob, seq_off)
+
+    @classmethod
+    def from_blob(cls, blob: bytes, seq_off: np.ndarray, binding=None):
+        self = cls.__new__(cls)
+        self._init_from_blob(binding or _lib.load(), blob, np.ascontiguousarray(seq_off, dtype=np.uint64))
+        return self
+
+    def _init_from_blob(self, lib, blob, seq_off):
+        n = len(seq_off) - 1
+        w2, w4 = C.c_uint64(0), C.c_uint64(0)
+        lib.smx_pack_bound(_lib.ptr(seq_off, _lib.u64p), n, C.byref(w2), C.byref(w4))
+        self.n_reads = n
+        self.packed2 = np.zeros(int(w2.value), dtype=np.uint32)
+        self.word_off = np.zeros(max(n, 1), dtype=np.uint64)
+        self.lengths = np.zeros(max(n, 1), dtype=np.uint32)
+        packed4 = np.zeros(int(w4.value), dtype=np.uint32)
+        self.off4 = np.zeros(max(n, 1), dtype=np.uint64)
+        used4, flagged = C.c_uint64(0), C.c_uint32(0)
+        _lib.check(lib.smx_pack_reads(blob, _lib.ptr(seq_off, _lib.u64p), n, _lib.ptr(self.packed2, _lib.u32p),
+                                      _lib.ptr(self.word_off, _lib.u64p), _lib.ptr(self.lengths, _lib.u32p),
+                                      _lib.ptr(packed4, _lib.u32p), _lib.ptr(self.off4, _lib.u64p),
+                                      C.byref(used4), C.byref(flagged)))
+        self.n_flagged = int(flagged.value)
+        self.packed4 = packed4[:int(used4.value)].copy() if self.n_flagged else None
+        self.h2d_bytes = (self.packed2.nbytes + self.word_off.nbytes + self.lengths.nbytes +
+                          (self.packed4.nbytes + self.off4.nbytes if self.n_flagged else 0))
+
+    def c_batch(self) -> "_lib.SmxBatch":
+        b = _lib.SmxBatch()
+        b.n_reads = self.n_reads
+        b.packed2 = _lib.ptr(self.packed2, _lib.u32p)
+        b.packed2_words = len(self.packed2)
+        b.word_off = _lib.ptr(self.word_off, _lib.u64p)
+        b.lengths = _lib.ptr(self.lengths, _lib.u32p)
+        if self.n_flagged:
+            b.packed4 = _lib.ptr(self.packed4, _lib.u32p)
+            b.packed4_words = len(self.packed4)
+            b.off4 = _lib.ptr(self.off4, _lib.u64p)
+        else:
+            b.packed4 = None
+            b.packed4_words = 0
+            b.off4 = None
+        return b
+
+
+class BatchResult:
+    def __init__(self, rec_offset, records, n_matched, primer_hits=None, endmask=None, barcode_hits=None):
+        self.rec_offset = rec_offset
+        self.records = records
+        self.n_matched = n_matched
+        self.primer_hits = primer_hits      # [2*n_primers, n_reads]
+        self.endmask = endmask              # [2*n_primers, mask_words, n_reads] uint32
+        self.barcode_hits = barcode_hits    # [total_barcode_slots, n_reads]
+
+
+class Matcher:
+    """One device context.  `binding` lets the unit tests drive the same code through the CPU
+    kernel simulator (tests/hostsim); the product never passes it."""
+
+    def __init__(self, tables, device: int = 0, binding=None):
+        self.tables = tables
+        self._binding = binding
+        self._ctx = C.c_void_p(None)
+        if binding is None:
+            self._lib = _lib.load()
+            _lib.check(self._lib.smx_create(device, tables.tables_ref(), tables.params_ref(), C.byref(self._ctx)))
+        else:
+            self._lib = None
+
+    def close(self):
+        if self._lib is not None and self._ctx:
+            self._lib.smx_destroy(self._ctx)
+            self._ctx = C.c_void_p(None)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- results allocation ---------------------------------------------------------------
+    def _alloc_results(self, n, detail, cap=None):
+        t = self.tables
+        cap = int(cap if cap is not None else 2 * n + 1024)
+        res = _lib.SmxResults()
+        rec_offset = np.zeros(n + 1, dtype=np.uint32)
+        records = np.zeros(cap, dtype=_lib.RECORD_DTYPE)
+        res.rec_offset = _lib.ptr(rec_offset, _lib.u32p)
+        res.records = records.ctypes.data
+        res.records_cap = cap
+        ph = em = bh = None
+        if detail:
+            ph = np.zeros((2 * t.n_primers, n), dtype=_lib.PRIMER_HIT_DTYPE)
+            em = np.zeros((2 * t.n_primers, t.mask_words, n), dtype=np.uint32)
+            bh = np.zeros((max(t.total_barcode_slots, 1), n), dtype=_lib.BARCODE_HIT_DTYPE)
+            res.primer_hits = ph.ctypes.data
+            res.endmask_bits = em.ctypes.data
+            res.barcode_hits = bh.ctypes.data
+        return res, rec_offset, records, ph, em, bh
+
+    def _finish(self, res, rec_offset, records, ph, em, bh):
+        return BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh)
+
+    # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
+    def match(self, batch: PackedBatch, detail: bool = False) -> BatchResult:
+        cb = batch.c_batch()
+        cap = None
+        while True:
+            res, rec_offset, records, ph, em, bh = self._alloc_results(batch.n_reads, detail, cap)
+            if self._binding is not None:
+                rc = self._binding.hostsim_match_batch(self.tables.tables_ref(), self.tables.params_ref(),
+                                                       C.byref(cb), C.byref(res))
+                if rc == _lib.SMX_ERR_CAPACITY:
+                    cap = int(res.n_records)
+                    continue
+                if rc != 0:
+                    raise _lib.SmxError(rc, self._binding.hostsim_last_error().decode())
+            else:
+                rc = self._lib.smx_match_batch(self._ctx, C.byref(cb), C.byref(res))
+                if rc == _lib.SMX_ERR_CAPACITY:
+                    cap = int(res.n_records)
+                    continue
+                _lib.check(rc)
+            return self._finish(res, rec_offset, records, ph, em, bh)
+
+    # -- split form -------------------------------------------------------------------------
+    def upload(self, batch: PackedBatch):
+        self._resident_n = batch.n_reads
+        cb = batch.c_batch()
+        _lib.check(self._lib.smx_upload_batch(self._ctx, C.byref(cb)))
+
+    def run_resident(self):
+        _lib.check(self._lib.smx_run_resident(self._ctx))
+
+    def download(self, detail: bool = False) -> BatchResult:
+        cap = None
+        while True:
+            res, rec_offset, records, ph, em, bh = self._alloc_results(self._resident_n, detail, cap)
+            rc = self._lib.smx_download_results(self._ctx, C.byref(res))
+            if rc == _lib.SMX_ERR_CAPACITY:
+                cap = int(res.n_records)
+                continue
+            _lib.check(rc)
+            return self._finish(res, rec_offset, records, ph, em, bh)
+
+    def last_timing(self):
+        total = C.c_float(0)
+        stages = (C.c_float * 4)()
+        _lib.check(self._lib.smx_last_timing(self._ctx, C.byref(total), stages))
+        return float(total.value), [float(x) for x in stages]
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.smx_last_launch_count(self._ctx))
+
+    def last_work(self):
+        cells = (C.c_uint64 * 2)()
+        wcols = (C.c_uint64 * 2)()
+        _lib.check(self._lib.smx_last_work(self._ctx, cells, wcols))
+        return [int(x) for x in cells], [int(x) for x in wcols]
