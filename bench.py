@@ -1,0 +1,295 @@
+#!/usr/bin/env python3
+"""bench.py -- reads/s demultiplexed on the BASELINE.json headline workload.
+
+One "step" = one pass of the whole hot path (window staging, primer HW search in both
+orientations, barcode SHW search, selection/dereplication) over one batch of synthetic reads of
+the named shape.  `value` is measured with the packed reads already resident in HBM (CUDA events
+around the kernels); `e2e` goes through the public C-ABI call with HOST buffers (H2D + kernels +
+D2H inside the timed region).  Reads are independent, so N GPUs = N ranks each processing its own
+batch of the same shape (weak scaling), no collective on the data path; torch.distributed is used
+only for the barrier and the max-over-ranks of the timings.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the headline metric is quoted on
+    "ont037": dict(reads=765_000, desc="ONT037-shape synthetic: 768 specimens (8x96 13-nt barcodes), ITS1F/ITS4, "
+                                       "765k reads ~700 bp, 7% ONT-like errors, mixed orientation"),
+    "dense": dict(reads=2_000_000, desc="dense 96x96 dual-index grid (9,216 specimens), ~700 bp, 12% errors"),
+    "multipool": dict(reads=5_000_000, desc="multi-pool ITS + RPB2 (IUPAC) + shared primers"),
+    "long": dict(reads=20_000_000, desc="long amplicon 2-4 kb, widened search windows"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dataset(name, n_reads, seed_shift):
+    """Synthetic dataset (cached under /tmp as .npz so the two arms of one box share it)."""
+    from specimux_b200 import synth
+    cache = "/tmp/smx_bench_%s_%d_%d.npz" % (name, n_reads, seed_shift)
+    base = synth.CONFIGS[name](n_reads=64, with_quals=False)     # tables only (cheap)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        base.codes, base.offsets = z["codes"], z["offsets"]
+        return base
+    t0 = time.time()
+    fn = synth.CONFIGS[name]
+    defaults = {"ont037": 37, "multipool": 3, "long": 4, "dense": 5}
+    ds = fn(n_reads=n_reads, seed=defaults[name] + 1000 * seed_shift, with_quals=False)
+    # keep the barcode tables of the canonical seed (rank-independent tables, rank-dependent reads)
+    if seed_shift:
+        ds.primers, ds.specimens = base.primers, base.specimens
+    log("generated %s x %d reads in %.1fs" % (name, n_reads, time.time() - t0))
+    try:
+        np.savez(cache + ".tmp.npz", codes=ds.codes, offsets=ds.offsets)
+        os.replace(cache + ".tmp.npz", cache)
+    except OSError:
+        pass
+    return ds
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference path (oracle port; the real specimux +
+    edlib cannot run on the GPU box) on all host cores, bounded sample per step."""
+    rank, _local, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    wl = WORKLOADS[args.config]
+    cores = cpu_bench.host_cores()
+    sample = args.ref_sample if args.ref_sample else max(2000, 600 * cores)
+    ds = dataset(args.config, max(sample, 64), 0) if sample <= 8192 else dataset(args.config, sample, 0)
+    reads = ds.reads(0, sample)
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_bench.run(ds.primers, ds.specimens, reads, ds.search_len, processes=cores)
+        if i >= args.warmup:
+            times.append(res["seconds"])
+    ms = 1000.0 * sum(times) / len(times)
+    value = sample / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "reads/sec demuxed (whole box)", "value": value, "unit": "reads/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.config, "description": wl["desc"], "search_len": ds.search_len},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                             "sample": "first %d reads of the workload per step, oracle port of specimux's "
+                                       "process_sequences over a C edlib restatement, %d worker processes" % (sample, cores)},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="ont037", choices=list(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (testing only)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="reads per step of the reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="reads of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("note: --warmup %d < 3; timing hygiene asks for >= 3" % args.warmup)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, local, world = dist_env()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+
+    from specimux_b200 import _lib
+    from specimux_b200.engine import Matcher, PackedBatch
+    from specimux_b200.models import MatchParameters
+    from specimux_b200.tables import MatchTables
+    from specimux_b200.orchestration import thresholds_for
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+
+    lib = _lib.load()          # raises if the CUDA library is missing -- there is no CPU path
+    if lib.smx_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the matching has no CPU fallback")
+
+    wl = WORKLOADS[args.config]
+    n_reads = args.reads or wl["reads"]
+    ds = dataset(args.config, n_reads, rank)
+    specimens = H.build_specimens(ds.primers, ds.specimens)
+    k_idx, k_primers = thresholds_for(specimens, device=local)
+    params = MatchParameters(k_primers, k_idx, ds.search_len, True)
+    tables = MatchTables(specimens, params, trim="barcodes", dereplicate="best", prefilter=True)
+    matcher = Matcher(tables, device=local)
+
+    t0 = time.time()
+    ascii_blob = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].tobytes()
+    batch = PackedBatch.from_blob(ascii_blob, ds.offsets.astype(np.uint64))
+    del ascii_blob
+    log("rank %d: packed %d reads (%.1f MB) in %.1fs" % (rank, n_reads, batch.h2d_bytes / 1e6, time.time() - t0))
+
+    import ctypes
+    peaks = (ctypes.c_double * 3)()
+    _lib.check(lib.smx_int_alu_peak(local, peaks))
+    int_peak = max(peaks)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    matcher.upload(batch)
+    for _ in range(args.warmup):
+        matcher.run_resident()
+    barrier()
+    step_ms, stage_ms = [], []
+    with ClockSampler(local) as clocks:
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            matcher.run_resident()                       # synchronises the stream internally
+            tot, st = matcher.last_timing()
+            step_ms.append(tot)
+            stage_ms.append(st)
+        wall_ms = (time.perf_counter() - t_wall) * 1000.0 / args.steps
+    barrier()
+    launches = matcher.last_launch_count()
+    cells, wcols = matcher.last_work()
+    res = matcher.download()
+    ms = float(np.mean(step_ms))
+    st = np.mean(np.array(stage_ms), axis=0)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        r = matcher.match(batch)
+    barrier()
+    t_e2e = time.perf_counter()
+    for _ in range(args.steps):
+        r = matcher.match(batch)
+    e2e_ms = (time.perf_counter() - t_e2e) * 1000.0 / args.steps
+    barrier()
+    d2h = r.records.nbytes + r.rec_offset.nbytes
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        total_reads = n_reads * world
+        value = total_reads / (ms / 1000.0)
+        alg_ops = 15.0 * (wcols[0] + wcols[1])
+        gcups = (cells[0] + cells[1]) / (ms / 1000.0) / 1e9
+        dom = int(np.argmax(st))
+        dom_name = ["stage_windows", "primer_search", "barcode_search", "select"][dom]
+        dom_ops = 15.0 * (wcols[1] if dom == 2 else wcols[0] if dom == 1 else 0)
+        achieved = dom_ops / (st[dom] / 1000.0) / 1e12 if st[dom] > 0 else 0.0
+        hbm_bytes = batch.h2d_bytes + res.records.nbytes
+        line = {
+            "metric": "reads/sec demuxed (whole box)", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.config, "description": wl["desc"], "reads_per_gpu": n_reads,
+                       "search_len": ds.search_len, "k_index": k_idx, "dereplicate": "best", "trim": "barcodes",
+                       "l2": "inputs + intermediates per step (%.0f MB packed reads, %.1f GB hit tables) exceed the 126 MB L2"
+                             % (batch.h2d_bytes / 1e6, tables.total_barcode_slots * 16.0 * n_reads / 1e9)},
+            "gcups": gcups, "cells_per_read": (cells[0] + cells[1]) / n_reads,
+            "stage_ms": {"stage_windows": st[0], "primer_search": st[1], "barcode_search": st[2], "select": st[3]},
+            "wall_ms_per_step": wall_ms,
+            "roofline": {"bound": "int_alu", "kernel": dom_name, "achieved": achieved, "peak": int_peak,
+                         "unit": "Tops/s", "frac": achieved / int_peak if int_peak else None,
+                         "whole_step_frac": (alg_ops / (ms / 1000.0) / 1e12) / int_peak if int_peak else None,
+                         "peak_source": "measured in this run by smx_int_alu_peak (LOP3 %.2f / IADD3 %.2f / mix %.2f Tops/s)"
+                                        % (peaks[0], peaks[1], peaks[2]),
+                         "algorithmic_ops": "15 int ops x 32-bit word-columns (SURVEY.md 8d)",
+                         "traffic": None,
+                         "hbm_sanity_gbs": hbm_bytes / (ms / 1000.0) / 1e9},
+            "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": "reads/s",
+                    "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms, "api": "smx_match_batch (host buffers: H2D + kernels + D2H)"},
+            "gpu_launches": int(launches * args.steps),
+            "clocks": clocks.summary(),
+            "records_per_step": int(len(res.records)), "matched_reads": int(res.n_matched),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import cpu_bench
+            sample = min(args.cpu_sample, n_reads)
+            reads = ds.reads(0, sample)
+            cb = cpu_bench.run(ds.primers, ds.specimens, reads, ds.search_len, processes=1)
+            line["cpu_baseline"] = {"value": cb["reads_per_s"], "unit": "reads/s", "cores": 1, "kind": "port",
+                                    "sample": "first %d reads of the workload, %.1f s on one host core "
+                                              "(oracle port of specimux process_sequences)" % (sample, cb["seconds"])}
+        print(json.dumps(line, default=float), flush=True)
+    matcher.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -234,6 +234,15 @@ int smx_last_work(const smx_ctx *ctx, uint64_t cells[2], uint64_t wordcols[2]);
  * out[i*n + j] = distance(seq_i, seq_j). */
 int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint32_t n, int32_t *out);
 
+/* Integer-ALU roofline denominator: measured throughput (10^12 ops/s) of independent 32-bit
+ * LOP3 (logic) and IADD3 (add) chains over the whole chip, the two instruction classes of the
+ * Myers column step.  out[0] = LOP3-only, out[1] = IADD3-only, out[2] = 1:1 mix. */
+int smx_int_alu_peak(int device, double out_tops[3]);
+
+/* Pinned host memory for batch / result buffers (cudaHostAlloc / cudaFreeHost). */
+void *smx_host_alloc(uint64_t bytes);
+void smx_host_free(void *p);
+
 /* Host-side packer (no matching): ASCII reads -> the smx_batch encoding above.
  * Replaces nothing in the reference (it works on Python strings); part of the batching layer.
  * Call with out arrays sized by smx_pack_bound. Returns the number of flagged (packed4) reads in

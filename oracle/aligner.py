@@ -36,7 +36,27 @@ def lib():
     return _lib
 
 
+_eq_by_id = {}
+
+
+def bloom_yes(barcode, flank, k):
+    """C version of oracle.pipeline._bloom_yes_py (same semantics, see edlib_restated.c)."""
+    b = barcode.encode("latin-1")
+    f = flank[:max(0, len(barcode) - k)].encode("latin-1", "replace")
+    return bool(lib().orc_bloom_yes(b, len(b), f, len(f), int(k)))
+
+
 def equality_table(pairs):
+    hit = _eq_by_id.get(id(pairs))
+    if hit is not None and hit[0] is pairs:
+        return hit[1]
+    tab = _equality_table(pairs)
+    if pairs is not None:
+        _eq_by_id[id(pairs)] = (pairs, tab)
+    return tab
+
+
+def _equality_table(pairs):
     key = tuple((str(a), str(b)) for a, b in pairs) if pairs else ()
     tab = _eq_cache.get(key)
     if tab is None:

@@ -150,3 +150,38 @@ int orc_align(const unsigned char *q, int m, const unsigned char *t, int n,
     free(row); free(rq); free(rt); free(rrow);
     return 0;
 }
+
+/*
+ * Exact-set emulation of the reference's Bloom prefilter query
+ * (src/specimux/bloom_filter.py:70-101 _generate_variants, :176-186 match):
+ * the key barcode + flank[:m-k] is in the filter iff some string within k single-character edits
+ * of `barcode` (substituted / inserted characters drawn from "ACGT" only) has flank[:m-k] as its
+ * first m-k characters.  Constrained Levenshtein DP of t = flank[:m-k] against every prefix of the
+ * barcode.  (pybloomfilter's ~5 % hash false positives are not reproduced: SURVEY.md Q5.)
+ */
+int orc_bloom_yes(const unsigned char *barcode, int m, const unsigned char *flank, int flen, int k)
+{
+    int n = m - k;
+    if (flen < n) return 0;
+    if (n <= 0) return 1;
+    const int INF = 1000000;
+    int *prev = (int *)malloc(sizeof(int) * (size_t)(m + 1));
+    int *cur = (int *)malloc(sizeof(int) * (size_t)(m + 1));
+    for (int j = 0; j <= m; j++) prev[j] = j;
+    for (int i = 1; i <= n; i++) {
+        unsigned char ch = flank[i - 1];
+        int creatable = (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T');
+        cur[0] = creatable ? prev[0] + 1 : INF;
+        for (int j = 1; j <= m; j++) {
+            int best = (ch == barcode[j - 1]) ? prev[j - 1] : (creatable ? prev[j - 1] + 1 : INF);
+            if (creatable && prev[j] + 1 < best) best = prev[j] + 1;
+            if (cur[j - 1] + 1 < best) best = cur[j - 1] + 1;
+            cur[j] = best < INF ? best : INF;
+        }
+        int *tmp = prev; prev = cur; cur = tmp;
+    }
+    int best = prev[0];
+    for (int j = 1; j <= m; j++) if (prev[j] < best) best = prev[j];
+    free(prev); free(cur);
+    return best <= k;
+}

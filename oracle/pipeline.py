@@ -208,6 +208,10 @@ def align_window(query, target, k, start, end, mode):
 
 
 def _bloom_yes(barcode_rc, flank, k):
+    return aligner.bloom_yes(barcode_rc, flank, k)
+
+
+def _bloom_yes_py(barcode_rc, flank, k):
     """bloom_filter.py:70-101,176-186 with an exact set (no hash false positives):
     key barcode_rc + flank[:m-k] is present iff some string within k edits of barcode_rc
     (edits introduce only A/C/G/T) has flank[:m-k] as its first m-k characters."""

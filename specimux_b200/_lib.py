@@ -60,7 +60,8 @@ assert RECORD_DTYPE.itemsize == 64 and PRIMER_HIT_DTYPE.itemsize == 12 and BARCO
 EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create", "smx_destroy",
            "smx_result_bound", "smx_match_batch", "smx_upload_batch", "smx_run_resident",
            "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
-           "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads"]
+           "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads", "smx_int_alu_peak", "smx_host_alloc",
+           "smx_host_free"]
 
 
 class SmxError(RuntimeError):
@@ -98,6 +99,11 @@ def load():
         lib.smx_pack_bound.argtypes = [u64p, C.c_uint32, u64p, u64p]
         lib.smx_pack_bound.restype = None
         lib.smx_pack_reads.argtypes = [C.c_char_p, u64p, C.c_uint32, u32p, u64p, u32p, u32p, u64p, u64p, u32p]
+        lib.smx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        lib.smx_host_alloc.argtypes = [C.c_uint64]
+        lib.smx_host_alloc.restype = C.c_void_p
+        lib.smx_host_free.argtypes = [C.c_void_p]
+        lib.smx_host_free.restype = None
         if lib.smx_abi_version() != 1:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib

@@ -366,6 +366,55 @@ int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint3
     return SMX_OK;
 }
 
+int smx_int_alu_peak(int device, double out_tops[3]) {
+    if (!out_tops) return fail(SMX_ERR_ARG, "smx_int_alu_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SMX_ERR_NO_DEVICE, "smx_int_alu_peak: no CUDA device");
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    u32 *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_out, 4));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    const double ops = (double)blocks * threads * iters * 64.0;
+    for (int mode = 0; mode < 3; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CU(cudaEventRecord(e0));
+            if (mode == 0) k_int_peak<0><<<blocks, threads>>>(d_out, iters, 17u + rep);
+            else if (mode == 1) k_int_peak<1><<<blocks, threads>>>(d_out, iters, 17u + rep);
+            else k_int_peak<2><<<blocks, threads>>>(d_out, iters, 17u + rep);
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        out_tops[mode] = ops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    return SMX_OK;
+}
+
+void *smx_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(SMX_ERR_CUDA, "smx_host_alloc: cudaHostAlloc(%llu) failed", (unsigned long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void smx_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host-side packer (batching layer; no matching happens here).
 

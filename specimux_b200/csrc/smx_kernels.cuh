@@ -352,6 +352,29 @@ __global__ void k_pairwise_nw(const char *seqs, const u32 *off, u32 n, i32 *out)
     }
     out[idx] = score;
 }
+// Integer-ALU peak microbenchmark: 8 independent chains per thread, fully unrolled.
+// MODE 0: LOP3 only, 1: IADD3 only, 2: alternating.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_peak(u32 *out, int iters, u32 seed) {
+    u32 a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = seed * (threadIdx.x + 1) + j * 0x9E3779B9u + blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                u32 x = a[j], y = a[(j + 1) & 7], z = a[(j + 3) & 7];
+                bool logic = MODE == 0 || (MODE == 2 && ((j + u) & 1));
+                a[j] = logic ? ((x & y) ^ z) : (x + y + z);
+            }
+        }
+    }
+    u32 r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r ^= a[j];
+    if (r == 0x12345678u) out[0] = r;       // practically never; keeps the chains alive
+}
 #endif  // __CUDACC__
 
 }  // namespace smx

@@ -1,0 +1,185 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the golden vectors and -- at
+full BASELINE sizes -- size-independent properties.  Needs a GPU: `pytest -m gpu`."""
+import argparse
+
+import numpy as np
+import pytest
+
+import helpers as H
+from specimux_b200 import synth
+from specimux_b200.demultiplex import process_sequences, records_to_write_ops
+from specimux_b200.engine import Matcher, PackedBatch
+from specimux_b200.models import MatchParameters
+from specimux_b200.orchestration import thresholds_for
+from specimux_b200.tables import MatchTables
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden_cases():
+    for name in H.golden_names():
+        for run in H.load_golden(name)["runs"]:
+            yield name, run
+
+
+@pytest.mark.parametrize("name,run_name", list(_golden_cases()))
+def test_cuda_matches_golden(name, run_name):
+    g = H.load_golden(name)
+    run = g["runs"][run_name]
+    specimens = H.build_specimens(g["primers"], g["specimens"])
+    args = H.make_args(run["flags"])
+    params = H.params_from_run(run, specimens)
+    ops, total, matched = process_sequences(H.records(g["reads"]), params, specimens, args, H.prefilter_for(args))
+    assert (total, matched) == (run["total"], run["matched"])
+    H.assert_ops_equal([H.op_to_dict(o) for o in ops], run["ops"], "%s/%s" % (name, run_name))
+
+
+def test_thresholds_on_gpu_match_golden():
+    """setup_match_parameters' NW distances (orchestration.py:549-600) computed by the GPU kernel."""
+    for name in ("fixture", "synth_ont037", "synth_dense", "synth_multipool"):
+        g = H.load_golden(name)
+        run = g["runs"]["default"]
+        specimens = H.build_specimens(g["primers"], g["specimens"])
+        k_idx, k_primers = thresholds_for(specimens)
+        assert k_idx == run["k_index"], name
+        assert k_primers == run["k_primers"], name
+
+
+def _setup(ds, **flags):
+    specimens = H.build_specimens(ds.primers, ds.specimens)
+    k_idx, k_primers = thresholds_for(specimens)
+    params = MatchParameters(k_primers, k_idx, ds.search_len, not flags.get("disable_preorient", False))
+    args = H.make_args(dict(flags, search_len=ds.search_len))
+    return specimens, params, args
+
+
+@pytest.mark.parametrize("cfg,n,flags", [
+    ("ont037", 1500, {}), ("ont037", 800, {"dereplicate": "none", "trim": "tails"}),
+    ("dense", 1200, {}), ("dense", 600, {"dereplicate": "none", "trim": "primers"}),
+    ("multipool", 1200, {}), ("multipool", 600, {"disable_preorient": True, "trim": "tails"}),
+    ("long", 300, {}),
+])
+def test_cuda_matches_live_oracle(cfg, n, flags):
+    """Seeded synthetic slices (different seeds from the goldens), oracle run live as the checker."""
+    from oracle import pipeline as orc
+    ds = synth.CONFIGS[cfg](n_reads=n, seed=1234 + n)
+    reads = ds.reads()
+    tables = orc.Tables(ds.primers, ds.specimens)
+    oparams = orc.setup_params(tables, search_len=ds.search_len, preorient=not flags.get("disable_preorient", False),
+                               trim=flags.get("trim", "barcodes"), dereplicate=flags.get("dereplicate", "best"))
+    expected, total, matched = orc.process_reads(tables, oparams, reads)
+    specimens, params, args = _setup(ds, **flags)
+    assert params.max_dist_index == oparams.max_dist_index
+    ops, n_total, n_matched = process_sequences(H.records(reads), params, specimens, args, H.prefilter_for(args))
+    assert (n_total, n_matched) == (total, matched)
+    H.assert_ops_equal([H.op_to_dict(o) for o in ops], [H.op_to_dict(o) for o in expected], cfg)
+
+
+def test_level1_detail_matches_oracle():
+    """Every primer distance / first location / end count and every barcode distance / end set."""
+    from oracle import pipeline as orc
+    g = H.load_golden("fixture_crafted")
+    run = g["runs"]["no_prefilter"]
+    reads = [tuple(r) for r in g["reads"]]
+    specimens = H.build_specimens(g["primers"], g["specimens"])
+    params = H.params_from_run(run, specimens)
+    mt = MatchTables(specimens, params, prefilter=False)
+    with Matcher(mt) as m:
+        res = m.match(PackedBatch([r[1] for r in reads]), detail=True)
+    tables = orc.Tables([tuple(p) for p in g["primers"]], [tuple(s) for s in g["specimens"]])
+    oparams = orc.Params(dict(run["k_primers"]), run["k_index"], prefilter=False)
+    oprimers = list(tables.by_seq.values())
+    nP = len(oprimers)
+    checked = 0
+    for r, (_rid, bases, _q) in enumerate(reads):
+        strands = (bases, orc.revcomp(bases))
+        for s in range(2):
+            for p, prim in enumerate(oprimers):
+                pd, plocs, hits = orc.match_one_end(tables, oparams, strands[s], prim)
+                ph = res.primer_hits[s * nP + p, r]
+                assert int(ph["distance"]) == pd, (r, s, p)
+                if pd < 0:
+                    continue
+                assert (int(ph["first_start"]), int(ph["first_end"])) == tuple(plocs[0]), (r, s, p, plocs)
+                assert int(ph["n_locations"]) == len(plocs)
+                hitmap = {b: (d, locs) for b, d, locs in hits}
+                base = sum(len(q.barcodes) for q in oprimers) * s + sum(len(q.barcodes) for q in oprimers[:p])
+                for j, bc in enumerate(prim.barcodes):
+                    bh = res.barcode_hits[base + j, r]
+                    if bc in hitmap:
+                        d, locs = hitmap[bc]
+                        assert int(bh["distance"]) == d, (r, s, p, bc)
+                        shift = 0 if int(bh["search_start"]) == -1 else int(bh["search_start"])
+                        ends = [shift + c for c in range(64) if (int(bh["end_mask"]) >> c) & 1]
+                        assert ends == [e for _s, e in locs], (r, s, p, bc, ends, locs)
+                        checked += 1
+                    else:
+                        assert int(bh["distance"]) == -1, (r, s, p, bc)
+    assert checked > 20
+
+
+@pytest.mark.parametrize("cfg,n", [("ont037", 30000), ("dense", 20000), ("multipool", 20000)])
+def test_cuda_equals_kernel_simulator_at_scale(cfg, n):
+    """Bit-identical records between the CUDA launch and the CPU loop over the same thread routines:
+    catches indexing / race / launch-geometry faults the small oracle cases cannot."""
+    ds = synth.CONFIGS[cfg](n_reads=n, seed=77)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params)
+    blob = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].tobytes()
+    batch = PackedBatch.from_blob(blob, ds.offsets.astype(np.uint64))
+    with Matcher(mt) as m:
+        gpu = m.match(batch, detail=True)
+    sim = Matcher(mt, binding=H.hostsim_binding()).match(batch, detail=True)
+    assert gpu.n_matched == sim.n_matched
+    assert np.array_equal(gpu.rec_offset, sim.rec_offset)
+    assert gpu.records.tobytes() == sim.records.tobytes()
+    assert np.array_equal(gpu.primer_hits, sim.primer_hits)
+
+
+def test_full_size_properties_ont037():
+    """BASELINE config 2 at full size (765k reads): determinism, batch-split invariance,
+    reverse-complement invariance of the specimen calls, and agreement with the generator's truth."""
+    ds = synth.ont037(n_reads=765_000, with_quals=False)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    blob = lut[ds.codes].tobytes()
+    offs = ds.offsets.astype(np.uint64)
+    with Matcher(mt) as m:
+        whole = m.match(PackedBatch.from_blob(blob, offs))
+        again = m.match(PackedBatch.from_blob(blob, offs))
+        assert whole.records.tobytes() == again.records.tobytes()          # deterministic
+        # batch-split invariance: three uneven pieces give the same records
+        cuts = [0, 100_001, 400_000, 765_000]
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            sub = PackedBatch.from_blob(blob[int(offs[a]):int(offs[b])], offs[a:b + 1] - offs[a])
+            r = m.match(sub)
+            rec = r.records.copy()
+            rec["read"] += a
+            parts.append(rec)
+        assert np.concatenate(parts).tobytes() == whole.records.tobytes()
+        # reverse-complement invariance: same sample / distances, `reverse` flipped
+        n_rc = 200_000
+        sub_codes = ds.codes[:int(ds.offsets[n_rc])]
+        lens = np.diff(ds.offsets[:n_rc + 1])
+        start = np.repeat(ds.offsets[:n_rc], lens)
+        pos = np.arange(sub_codes.shape[0]) - start
+        rc_codes = 3 - sub_codes[start + np.repeat(lens, lens) - 1 - pos]
+        rc = m.match(PackedBatch.from_blob(lut[rc_codes].tobytes(), offs[:n_rc + 1]))
+    first = whole.records[whole.rec_offset[:n_rc]]
+    first_rc = rc.records[rc.rec_offset[:n_rc]]
+    single = (np.diff(whole.rec_offset[:n_rc + 1]) == 1) & (np.diff(rc.rec_offset[:n_rc + 1]) == 1)
+    full = single & (first["resolution"] == 6)
+    assert np.array_equal(first["sample"][full], first_rc["sample"][full])
+    assert np.array_equal(first["dist"][full], first_rc["dist"][full])
+    assert np.all(first["reverse"][full] != first_rc["reverse"][full])
+    assert np.array_equal(first["trim_end"][full] - first["trim_start"][full],
+                          first_rc["trim_end"][full] - first_rc["trim_start"][full])
+    # truth: a dereplicated full match must name the specimen the read was generated from
+    rec = whole.records
+    fullrec = rec[rec["resolution"] == 6]
+    truth = ds.truth["specimen"][fullrec["read"]]
+    agree = np.mean(fullrec["sample"] == truth)
+    assert agree > 0.999, agree
+    assert whole.n_matched / ds.n_reads > 0.90
