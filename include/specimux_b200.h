@@ -171,7 +171,7 @@ typedef struct smx_barcode_hit {
     uint64_t end_mask;         /* bit j: flank column j is an equal-best SHW end (end = start + j) */
     int32_t search_start;      /* barcode_search_start of the winning primer location             */
     int16_t distance;          /* -1 = none within k_idx at any primer location                   */
-    uint16_t pad;
+    uint16_t barcode;          /* position j of the barcode in its primer's list                  */
 } smx_barcode_hit;
 
 typedef struct smx_results {

@@ -65,9 +65,10 @@ struct smx_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // table storage
-    DevBuf<u64> peq_rc, peq_rcrev, peq_fw, bpeq, spec_key, spec_p1, spec_p2;
-    DevBuf<unsigned char> b_len;
-    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row;
+    DevBuf<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
+    DevBuf<unsigned char> b_len, bw_len, bw_primer;
+    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
+    DevBuf<unsigned short> bw_list;
     DevBuf<i32> pair_pool, spec_pool;
     int max_nb = 0;
     // batch storage
@@ -75,8 +76,10 @@ struct smx_ctx {
     DevBuf<u32> packed2, lengths, packed4, win, endmask, rec_count, rec_offset, block_sums;
     DevBuf<u64> word_off, off4;
     DevBuf<smx_primer_hit> phit;
-    DevBuf<unsigned char> orient_hit, read_flags;
-    DevBuf<smx_barcode_hit> bhit;
+    DevBuf<unsigned char> orient_hit, read_flags, bh_count;
+    DevBuf<smx_barcode_hit> bh_list;
+    DevBuf<u32> slot_list, slot_count, big_list;
+    DevBuf<unsigned char> big_scratch;
     DevBuf<smx_record> records;
     DevBuf<unsigned long long> counters;   // 4 work counters + matched + (u32) overflow + (u32) total
     bool have_batch = false, have_results = false;
@@ -85,6 +88,22 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
     int launches = 0;
 };
+
+// rec_count -> rec_offset (exclusive scan), flag counters, then one D2H of the 8 counters.
+static cudaError_t scan_and_count(smx_ctx *c, int &launches, unsigned long long host_counters[8]) {
+    Batch &b = c->b;
+    const u32 n = b.n_reads;
+    cudaStream_t st = c->stream;
+    unsigned sblocks = (n + kScanBlock - 1) / kScanBlock;
+    k_scan_block_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p);
+    k_scan_spine<<<1, kScanBlock, 0, st>>>(c->block_sums.p, sblocks, (u32 *)(c->counters.p + 6));
+    k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p, b.rec_offset);
+    k_count_flags<<<(n + 255) / 256, 256, 0, st>>>(b.read_flags, n, c->counters.p + 4, (unsigned *)(c->counters.p + 5));
+    launches += 4;
+    cudaError_t e = cudaMemcpyAsync(host_counters, c->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
 
 extern "C" {
 
@@ -102,13 +121,15 @@ void smx_destroy(smx_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bpeq.release();
+    c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bw_len.release(); c->bw_primer.release(); c->bw_row.release();
+    c->bw_valid.release(); c->beq.release(); c->bw_list.release(); c->bh_count.release(); c->bh_list.release();
+    c->slot_list.release(); c->slot_count.release(); c->big_list.release(); c->big_scratch.release();
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release();
     c->packed2.release(); c->lengths.release(); c->packed4.release(); c->win.release(); c->endmask.release();
     c->rec_count.release(); c->rec_offset.release(); c->block_sums.release(); c->word_off.release();
-    c->off4.release(); c->phit.release(); c->orient_hit.release(); c->read_flags.release(); c->bhit.release();
+    c->off4.release(); c->phit.release(); c->orient_hit.release(); c->read_flags.release();
     c->records.release(); c->counters.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -145,21 +166,23 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUC(cudaEventCreate(&e));
     CUC(upload(c->peq_rc, ht.peq_rc)); CUC(upload(c->peq_rcrev, ht.peq_rcrev)); CUC(upload(c->peq_fw, ht.peq_fw));
-    CUC(upload(c->bpeq, ht.bpeq)); CUC(upload(c->b_len, ht.b_len)); CUC(upload(c->pb_barcode, ht.pb_barcode));
+    CUC(upload(c->b_len, ht.b_len)); CUC(upload(c->pb_barcode, ht.pb_barcode));
+    CUC(upload(c->bw_len, ht.bw_len)); CUC(upload(c->bw_primer, ht.bw_primer)); CUC(upload(c->bw_row, ht.bw_row));
+    CUC(upload(c->bw_valid, ht.bw_valid)); CUC(upload(c->bw_list, ht.bw_list)); CUC(upload(c->beq, ht.beq));
     CUC(upload(c->pair_fwd, ht.pair_fwd)); CUC(upload(c->pair_rev, ht.pair_rev)); CUC(upload(c->pair_pool, ht.pair_pool));
     CUC(upload(c->spec_key, ht.spec_key)); CUC(upload(c->spec_key_off, ht.spec_key_off));
     CUC(upload(c->spec_row, ht.spec_row)); CUC(upload(c->spec_p1, ht.spec_p1)); CUC(upload(c->spec_p2, ht.spec_p2));
     CUC(upload(c->spec_pool, ht.spec_pool));
     CUC(c->counters.ensure(8));
-    ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->bpeq.p, c->b_len.p, c->pb_barcode.p,
+    ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
+    ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,
                     c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
                     c->spec_row.p, c->spec_p1.p, c->spec_p2.p, c->spec_pool.p);
     c->t = ht.t;
     memset(&c->b, 0, sizeof(c->b));
-    size_t smem = (size_t)ht.max_nb * 16 * sizeof(u64);
-    if (smem > 48 * 1024) {
-        CUC(cudaFuncSetAttribute(k_barcode_search<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUC(cudaFuncSetAttribute(k_barcode_search<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ht.t.k_idx > 8) {
+        smx_destroy(c);
+        return fail(SMX_ERR_ARG, "smx_create: barcode distance threshold %d exceeds the supported 8", ht.t.k_idx);
     }
 #undef CUC
     *out = c;
@@ -189,7 +212,9 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     CU(c->phit.ensure((size_t)2 * nP * n_pad));
     CU(c->endmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(c->orient_hit.ensure((size_t)2 * nP * n_pad));
-    CU(c->bhit.ensure((size_t)t.total_bslots * n_pad));
+    CU(c->slot_list.ensure((size_t)2 * nP * n_pad)); CU(c->slot_count.ensure((size_t)2 * nP));
+    CU(c->bh_count.ensure((size_t)2 * t.n_bwords * n_pad + 1));
+    CU(c->bh_list.ensure((size_t)2 * t.n_bwords * t.hit_cap * n_pad + 1));
     CU(c->rec_count.ensure(n)); CU(c->rec_offset.ensure((size_t)n + 1)); CU(c->read_flags.ensure(n));
     CU(c->block_sums.ensure((n + kScanBlock - 1) / kScanBlock + 1));
     CU(cudaMemcpyAsync(c->packed2.p, in->packed2, in->packed2_words * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
@@ -204,7 +229,8 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
     b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
     b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.orient_hit = c->orient_hit.p;
-    b.bhit = c->bhit.p; b.rec_count = c->rec_count.p; b.rec_offset = c->rec_offset.p;
+    b.slot_list = c->slot_list.p; b.slot_count = c->slot_count.p; b.bh_count = c->bh_count.p; b.bh_list = c->bh_list.p;
+    b.rec_count = c->rec_count.p; b.rec_offset = c->rec_offset.p;
     b.records = nullptr; b.read_flags = c->read_flags.p; b.counters = c->counters.p;
     CU(cudaStreamSynchronize(c->stream));
     c->have_batch = true; c->have_results = false;
@@ -223,6 +249,7 @@ int smx_run_resident(smx_ctx *c) {
     int launches = 0;
     CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(c->slot_count.p, 0, (size_t)2 * nP * sizeof(u32), st));
     CU(cudaEventRecord(c->ev[0], st));
     {   // stage 0
         dim3 grid((n + 127) / 128, 2 * t.wpw);
@@ -237,38 +264,68 @@ int smx_run_resident(smx_ctx *c) {
         ++launches;
     }
     CU(cudaEventRecord(c->ev[2], st));
-    for (int s = 0; s < 2; ++s)   // stage 2
-        for (int p = 0; p < nP; ++p) {
-            int nb = (int)(t.pb_off[p + 1] - t.pb_off[p]);
-            if (!nb) continue;
-            u64 warps = (u64)n * ((nb + 31) / 32);
-            u64 blocks = (warps * 32 + 255) / 256;
-            size_t smem = (size_t)nb * 16 * sizeof(u64);
-            if (t.buse64) k_barcode_search<u64><<<(unsigned)blocks, 256, smem, st>>>(b, p, s);
-            else k_barcode_search<u32><<<(unsigned)blocks, 256, smem, st>>>(b, p, s);
+    const unsigned blocks = (n + 127) / 128;
+    unsigned long long host_counters[8];
+    for (;;) {
+        if (t.n_bwords) {   // stage 2
+            dim3 grid(blocks, 2 * t.n_bwords);
+            switch (t.k_idx) {
+#define SMX_K2(KK) case KK: k_barcode_bitsliced<KK><<<grid, 128, 0, st>>>(b); break;
+                SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
+#undef SMX_K2
+                default: return fail(SMX_ERR_INTERNAL, "unsupported k_idx");
+            }
             ++launches;
         }
-    CU(cudaEventRecord(c->ev[3], st));
-    {   // stage 3: count, scan, write
-        unsigned blocks = (n + 127) / 128;
+        CU(cudaEventRecord(c->ev[3], st));
+        // stage 3: count, scan
         if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b, 0); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b, 0);
-        unsigned sblocks = (n + kScanBlock - 1) / kScanBlock;
-        k_scan_block_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p);
-        k_scan_spine<<<1, kScanBlock, 0, st>>>(c->block_sums.p, sblocks, (u32 *)(c->counters.p + 6));
-        k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p, b.rec_offset);
-        k_count_flags<<<(n + 255) / 256, 256, 0, st>>>(b.read_flags, n, c->counters.p + 4, (unsigned *)(c->counters.p + 5));
-        launches += 5;
-        unsigned long long host_counters[8];
-        CU(cudaMemcpyAsync(host_counters, c->counters.p, sizeof(host_counters), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        ++launches;
+        CU(scan_and_count(c, launches, host_counters));
+        if (host_counters[7] == 0) break;
+        // a hit sub-list overflowed: second GPU pass with a larger capacity (never a CPU fallback)
+        if (c->t.hit_cap >= kMaxWordHits) return fail(SMX_ERR_INTERNAL, "hit list overflow at maximum capacity");
+        c->t.hit_cap = std::min(kMaxWordHits, c->t.hit_cap * 4);
+        CU(c->bh_list.ensure((size_t)2 * t.n_bwords * c->t.hit_cap * b.n_pad + 1));
+        b.bh_list = c->bh_list.p;
+        CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(c->counters.p + 3, 0, 5 * sizeof(unsigned long long), st));
+    }
+    std::vector<u32> big_list;
+    if ((u32)host_counters[5]) {
+        // some reads overflowed the thread-local group storage: second GPU pass for those reads only,
+        // on kBigGroups-entry global scratch
+        std::vector<unsigned char> flags(n);
+        CU(cudaMemcpy(flags.data(), b.read_flags, n, cudaMemcpyDeviceToHost));
+        for (u32 r = 0; r < n; ++r) if (flags[r] & 2) big_list.push_back(r);
+        CU(c->big_list.ensure(big_list.size()));
+        CU(cudaMemcpy(c->big_list.p, big_list.data(), big_list.size() * sizeof(u32), cudaMemcpyHostToDevice));
+        const size_t chunk = 512;
+        CU(c->big_scratch.ensure(std::min(chunk, big_list.size()) * kBigScratchBytes));
+        for (size_t off = 0; off < big_list.size(); off += chunk) {
+            u32 cnt = (u32)std::min(chunk, big_list.size() - off);
+            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(b, c->big_list.p + off, cnt, c->big_scratch.p, 0);
+            ++launches;
+        }
+        CU(cudaMemsetAsync(c->counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
+        CU(scan_and_count(c, launches, host_counters));
+        if ((u32)(host_counters[5] >> 32))
+            return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceed %d dereplication groups",
+                        (unsigned)(host_counters[5] >> 32), kBigGroups);
+    }
+    {
         u64 total = (u32)host_counters[6];
-        if ((u32)host_counters[5])
-            return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceeded an internal tie/group capacity",
-                        (unsigned)(u32)host_counters[5]);
         CU(c->records.ensure(total + 1));
         b.records = c->records.p;
         if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b, 1); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b, 1);
         ++launches;
+        const size_t chunk = 512;
+        for (size_t off = 0; off < big_list.size(); off += chunk) {
+            u32 cnt = (u32)std::min(chunk, big_list.size() - off);
+            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(b, c->big_list.p + off, cnt, c->big_scratch.p, 1);
+            ++launches;
+        }
         c->n_records = total;
         c->n_matched = host_counters[4];
         for (int i = 0; i < 4; ++i) c->work[i] = host_counters[i];
@@ -308,11 +365,35 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     if (out->endmask_bits)
         CU(cudaMemcpy2DAsync(out->endmask_bits, (size_t)n * sizeof(u32), b.endmask, (size_t)b.n_pad * sizeof(u32),
                              (size_t)n * sizeof(u32), (size_t)2 * t.n_primers * t.mw, cudaMemcpyDeviceToHost, st));
-    if (out->barcode_hits && t.total_bslots)
-        CU(cudaMemcpy2DAsync(out->barcode_hits, (size_t)n * sizeof(smx_barcode_hit), b.bhit,
-                             (size_t)b.n_pad * sizeof(smx_barcode_hit), (size_t)n * sizeof(smx_barcode_hit),
-                             (size_t)t.total_bslots, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (out->barcode_hits && t.total_bslots) {
+        // expand the compact per-bword hit lists into the dense [barcode slot][read] detail layout
+        std::vector<smx_primer_hit> ph((size_t)2 * t.n_primers * b.n_pad);
+        std::vector<unsigned char> cnt((size_t)2 * t.n_bwords * b.n_pad);
+        std::vector<smx_barcode_hit> lst((size_t)2 * t.n_bwords * t.hit_cap * b.n_pad);
+        std::vector<unsigned char> bwp(t.n_bwords);
+        CU(cudaMemcpy(ph.data(), b.phit, ph.size() * sizeof(smx_primer_hit), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(cnt.data(), b.bh_count, cnt.size(), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(lst.data(), b.bh_list, lst.size() * sizeof(smx_barcode_hit), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(bwp.data(), t.bw_primer, bwp.size(), cudaMemcpyDeviceToHost));
+        smx_barcode_hit none;
+        none.end_mask = 0; none.search_start = 0; none.distance = -1; none.barcode = 0;
+        for (size_t i = 0; i < (size_t)t.total_bslots * n; ++i) out->barcode_hits[i] = none;
+        for (int sd = 0; sd < 2; ++sd)
+            for (int g = 0; g < t.n_bwords; ++g) {
+                int p = bwp[g];
+                u32 slot = (u32)(sd * t.n_primers + p);
+                u64 gslot = (u64)sd * t.n_bwords + g;
+                for (u32 r = 0; r < n; ++r) {
+                    if (ph[(size_t)slot * b.n_pad + r].distance < 0) continue;
+                    int k = std::min<int>(cnt[gslot * b.n_pad + r], t.hit_cap);
+                    for (int e = 0; e < k; ++e) {
+                        const smx_barcode_hit &h = lst[(gslot * t.hit_cap + e) * b.n_pad + r];
+                        out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r] = h;
+                    }
+                }
+            }
+    }
     return SMX_OK;
 }
 

@@ -28,8 +28,8 @@ typedef int32_t i32;
 constexpr int kSymOther = 15;       // read symbol that matches nothing (lower case, unknown bytes)
 constexpr int kNone = INT32_MIN;    // Python None in coordinates
 constexpr int kMaxPairs = 64;       // candidate slots per read = 2 * pairs
-constexpr int kMaxGroups = 24;      // dereplication groups tracked per read
-constexpr int kMaxTies = 8;         // equal-best barcodes tracked per end
+constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in the first pass
+constexpr int kBigGroups = 4096;    // ... in the second pass over reads that overflowed the first
 
 // ---------------------------------------------------------------------------------------------
 // Symbols.  4-bit read codes: A0 C1 G2 T3 R4 Y5 S6 W7 K8 M9 B10 D11 H12 V13 N14 other15.
@@ -144,7 +144,7 @@ struct Tables {
     int preorient, prefilter, trim, derep_best, min_length, max_length;
     int total_bslots;               // sum over (strand, primer) of barcode-list lengths
     int use64;                      // any primer longer than 32
-    int buse64;                     // any barcode longer than 32 - k (needs 64-bit words / masks)
+    int hit_cap;                    // entries per (read, strand, bword) hit sub-list
 
     unsigned char p_len[SMX_MAX_PRIMERS];
     signed char p_k[SMX_MAX_PRIMERS];
@@ -156,9 +156,20 @@ struct Tables {
     const u64 *peq_rc;       // [primer][16]   primer_rc, top-aligned
     const u64 *peq_rcrev;    // [primer][16]   reversed primer_rc (start-recovery pass)
     const u64 *peq_fw;       // [primer][16]   forward-sense primer (explicit orientation test)
-    const u64 *bpeq;         // [list entry][16] barcode_rc
     const unsigned char *b_len;    // [list entry]
     const u32 *pb_barcode;   // [list entry] global barcode id
+
+    // Bit-sliced barcode match table: barcodes of one primer and one length are grouped 32 to a
+    // "bword"; beq[(bw_row[g] + i) * 16 + sym] has bit q set iff row i (0-based) of the q-th
+    // barcode_rc of bword g equals read symbol `sym` (edlib additionalEqualities semantics).
+    int n_bwords;
+    u32 bw_off[SMX_MAX_PRIMERS + 1];   // primer p owns bwords [bw_off[p], bw_off[p+1])
+    const unsigned char *bw_len;       // [bword] barcode length m
+    const unsigned char *bw_primer;    // [bword] owning primer
+    const u32 *bw_row;                 // [bword] first row in beq
+    const u32 *bw_valid;               // [bword] mask of populated bit lanes
+    const unsigned short *bw_list;     // [bword][32] position j in the primer's barcode list
+    const u32 *beq;
 
     const u32 *pair_fwd, *pair_rev;
     const i32 *pair_pool;
@@ -183,14 +194,26 @@ struct Batch {
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
     u32 *endmask;            // [(slot*mw + w) * n_pad + read]
     unsigned char *orient_hit;   // [slot * n_pad + read]  explicit orientation test (irregular reads)
-    smx_barcode_hit *bhit;   // [bslot * n_pad + read]
+    u32 *slot_list;          // [slot * n_pad + i]  reads whose (strand, primer) slot matched (unordered)
+    u32 *slot_count;         // [slot]
+    unsigned char *bh_count; // [gslot * n_pad + read], gslot = strand * n_bwords + bword; may exceed hit_cap
+    smx_barcode_hit *bh_list;    // [(gslot * hit_cap + e) * n_pad + read], ascending barcode position
     // level-2 results
     u32 *rec_count;          // per read
     u32 *rec_offset;         // exclusive scan (n_reads + 1)
     smx_record *records;
     unsigned char *read_flags;   // bit0: read had a full match; bit1: internal cap overflow
     unsigned long long *counters;    // [0] HW cells [1] SHW cells [2] HW wordcols [3] SHW wordcols
+                                     // [4] matched reads [5] lo: select overflow, hi: hit-list overflow [6] records
 };
+
+SMX_HD void counter_add(unsigned long long *p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
 
 SMX_HD bool read_is_flagged(const Batch &b, u32 r) {
     return b.off4 != nullptr && b.off4[r] != ~0ull;
@@ -235,25 +258,6 @@ SMX_HD int hw_start_back(const u64 *peq_rev, int m, int best, int e_pos, int sta
         if (score == best) last = j;
     }
     return last;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Barcode SHW search (demultiplex.py:799-800).  Only the first m+k flank columns can hold a
-// distance <= k, so at most m+k <= 64 columns are processed and the equal-best ends fit a u64.
-
-template <typename W, typename Load>
-SMX_HD void shw_search(const u64 *peq, int m, int cols, Load load, int &best, u64 &mask) {
-    W Pv = pattern_mask<W>(m), Mv = 0;
-    int score = m;
-    best = m + 1;
-    mask = 0;
-    for (int j = 0; j < cols; ++j) {
-        int c = load(j);
-        W Eq = peq_word<W>(peq[c]);
-        score += myers_step<W, true>(Eq, Pv, Mv);
-        if (score < best) { best = score; mask = 0; }
-        if (score == best) mask |= 1ull << j;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -306,7 +310,7 @@ struct EndInfo {            // one (strand, primer) slot as seen by a candidate
     int nhits;              // barcodes within k_idx
     int bd;                 // best barcode distance
     int nbest;              // number of barcodes at bd
-    int best[kMaxTies];     // their list positions (ascending = pinned order)
+    int first_best;         // list position of the first of them (pinned order)
     int strand, primer;
 };
 
@@ -319,33 +323,56 @@ struct SelectCtx {
 
 SMX_HD u32 slot_index(const Tables &t, int strand, int primer) { return (u32)(strand * t.n_primers + primer); }
 
-SMX_HD const smx_barcode_hit &bhit_at(const SelectCtx &c, int strand, int primer, int j) {
-    u64 bslot = (u64)c.t->bslot_base[slot_index(*c.t, strand, primer)] + (u64)j;
-    return c.b->bhit[bslot * c.b->n_pad + c.read];
+// Barcode hits of one (strand, primer) slot live in per-bword sub-lists (written by stage 2, each
+// ascending in barcode position).  next_hit() walks the union in ascending position.
+SMX_HD bool next_hit(const SelectCtx &c, int strand, int primer, int after_j, smx_barcode_hit &out) {
+    const Tables &t = *c.t;
+    bool found = false;
+    for (u32 g = t.bw_off[primer]; g < t.bw_off[primer + 1]; ++g) {
+        u64 gslot = (u64)strand * t.n_bwords + g;
+        int cnt = c.b->bh_count[gslot * c.b->n_pad + c.read];
+        if (cnt > t.hit_cap) cnt = t.hit_cap;
+        for (int e = 0; e < cnt; ++e) {
+            const smx_barcode_hit &h = c.b->bh_list[(gslot * t.hit_cap + e) * c.b->n_pad + c.read];
+            int j = (int)h.barcode;
+            if (j <= after_j) continue;
+            if (!found || j < (int)out.barcode) { out = h; found = true; }
+            break;      // sub-list is ascending: the first j > after_j is this list's candidate
+        }
+    }
+    return found;
 }
 
-SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e, bool &overflow) {
+SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
     const Tables &t = *c.t;
     const smx_primer_hit &ph = c.b->phit[(u64)slot_index(t, strand, primer) * c.b->n_pad + c.read];
     e.strand = strand; e.primer = primer;
     e.matched = ph.distance >= 0;
     e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
-    e.nhits = 0; e.bd = -1; e.nbest = 0;
+    e.nhits = 0; e.bd = -1; e.nbest = 0; e.first_best = -1;
     if (!e.matched) return;
-    int nb = (int)(t.pb_off[primer + 1] - t.pb_off[primer]);
     int bd = 1 << 20;
-    for (int j = 0; j < nb; ++j) {
-        int d = bhit_at(c, strand, primer, j).distance;
-        if (d < 0) continue;
+    smx_barcode_hit h;
+    int after = -1;
+    while (next_hit(c, strand, primer, after, h)) {
+        after = (int)h.barcode;
+        int d = h.distance;
         ++e.nhits;
         if (d < bd) { bd = d; e.nbest = 0; }
-        if (d == bd) {
-            if (e.nbest < kMaxTies) e.best[e.nbest] = j; else overflow = true;
-            ++e.nbest;
-        }
+        if (d == bd) { if (e.nbest == 0) e.first_best = after; ++e.nbest; }
     }
     if (e.nhits) e.bd = bd;
-    if (e.nbest > kMaxTies) e.nbest = kMaxTies;
+}
+
+// Equal-best barcodes of an end in pinned order (models.py:116-126 best_b1 / best_b2): the list
+// position after `after_j`, or -1.
+SMX_HD int next_best(const SelectCtx &c, const EndInfo &e, int after_j) {
+    smx_barcode_hit h;
+    while (next_hit(c, e.strand, e.primer, after_j, h)) {
+        after_j = (int)h.barcode;
+        if (h.distance == e.bd) return after_j;
+    }
+    return -1;
 }
 
 struct Cand {               // CandidateMatch (models.py:72-95) by reference to its two ends
@@ -371,9 +398,9 @@ struct Emitter {
 };
 
 struct TrimState {          // cumulative trim_locations() shift per candidate
-    int cand[kMaxGroups];
-    int shift[kMaxGroups];
-    int n;
+    int *cand;
+    int *shift;
+    int n, cap;
 };
 
 SMX_HD int trim_shift_get(const TrimState &s, int cand) {
@@ -382,29 +409,34 @@ SMX_HD int trim_shift_get(const TrimState &s, int cand) {
 }
 SMX_HD void trim_shift_add(TrimState &s, int cand, int v, bool &overflow) {
     for (int i = 0; i < s.n; ++i) if (s.cand[i] == cand) { s.shift[i] += v; return; }
-    if (s.n < kMaxGroups) { s.cand[s.n] = cand; s.shift[s.n] = v; ++s.n; } else overflow = true;
+    if (s.n < s.cap) { s.cand[s.n] = cand; s.shift[s.n] = v; ++s.n; } else overflow = true;
 }
 
 // intertail_extent's folds over barcode locations with the reference's -1 sentinel
 // (models.py:300-319).  Hits are visited in stable distance order, locations ascending.
+SMX_HD int lowest_bit64(u64 m) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
+#endif
+}
+
 SMX_HD void tails_fold(const SelectCtx &c, const EndInfo &e, bool is_b1, int shift, int &acc) {
     if (!e.matched || e.nhits == 0) return;
     const Tables &t = *c.t;
-    int nb = (int)(t.pb_off[e.primer + 1] - t.pb_off[e.primer]);
     for (int d = 0; d <= t.k_idx; ++d) {
-        for (int j = 0; j < nb; ++j) {
-            const smx_barcode_hit &h = bhit_at(c, e.strand, e.primer, j);
+        smx_barcode_hit h;
+        int after = -1;
+        while (next_hit(c, e.strand, e.primer, after, h)) {
+            after = (int)h.barcode;
             if (h.distance != d) continue;
             int bshift = h.search_start == -1 ? 0 : h.search_start;
             u64 m = h.end_mask;
             while (m) {
-#if defined(__CUDA_ARCH__)
-                int col = __ffsll((long long)m) - 1;
-#else
-                int col = __builtin_ctzll(m);
-#endif
+                int col = lowest_bit64(m);
                 m &= m - 1;
-                int s_x = bshift, e_x = bshift + col;          // SHW location in X coordinates
+                int e_x = bshift + col;                        // SHW location (bshift, e_x) in X coordinates
                 if (is_b1) {
                     int l0 = c.n - e_x - 1 - shift;             // reversed(): (len-e-1, len-s-1)
                     acc = (acc == -1) ? l0 : (l0 < acc ? l0 : acc);
@@ -412,7 +444,6 @@ SMX_HD void tails_fold(const SelectCtx &c, const EndInfo &e, bool is_b1, int shi
                     int l1 = e_x + 1 - shift;
                     acc = (acc == -1) ? l1 : (l1 > acc ? l1 : acc);
                 }
-                (void)s_x;
             }
         }
     }
@@ -431,23 +462,17 @@ SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &ov
     if (m2) { p2s = e2.ps - shift; p2e = e2.pe - shift; }
     int b1s = kNone, b1e = kNone, b2s = kNone, b2e = kNone;
     if (m1 && e1.nhits) {
-        const smx_barcode_hit &h = bhit_at(c, e1.strand, e1.primer, e1.best[0]);
+        smx_barcode_hit h;
+        next_hit(c, e1.strand, e1.primer, e1.first_best - 1, h);
         int bshift = h.search_start == -1 ? 0 : h.search_start;
-#if defined(__CUDA_ARCH__)
-        int col = __ffsll((long long)h.end_mask) - 1;
-#else
-        int col = __builtin_ctzll(h.end_mask);
-#endif
+        int col = lowest_bit64(h.end_mask);
         b1s = n - (bshift + col) - 1 - shift; b1e = n - bshift - 1 - shift;
     }
     if (m2 && e2.nhits) {
-        const smx_barcode_hit &h = bhit_at(c, e2.strand, e2.primer, e2.best[0]);
+        smx_barcode_hit h;
+        next_hit(c, e2.strand, e2.primer, e2.first_best - 1, h);
         int bshift = h.search_start == -1 ? 0 : h.search_start;
-#if defined(__CUDA_ARCH__)
-        int col = __ffsll((long long)h.end_mask) - 1;
-#else
-        int col = __builtin_ctzll(h.end_mask);
-#endif
+        int col = lowest_bit64(h.end_mask);
         b2s = bshift - shift; b2e = bshift + col - shift;
     }
     int s = 0, e = n;
@@ -507,20 +532,20 @@ SMX_HD void resolve(const SelectCtx &c, const EndInfo &e1, const EndInfo &e2, in
     bool b1 = e1.matched && e1.nhits > 0, b2 = e2.matched && e2.nhits > 0;
     if (e1.matched && e2.matched && b1 && b2) {
         int count = 0, min_row = -1;
-        for (int i = 0; i < e1.nbest; ++i)
-            for (int j = 0; j < e2.nbest; ++j)
-                spec_all(t, t.pb_barcode[t.pb_off[e1.primer] + e1.best[i]],
-                         t.pb_barcode[t.pb_off[e2.primer] + e2.best[j]], e1.primer, e2.primer, count, min_row);
+        for (int j1 = next_best(c, e1, -1); j1 >= 0; j1 = next_best(c, e1, j1))
+            for (int j2 = next_best(c, e2, -1); j2 >= 0; j2 = next_best(c, e2, j2))
+                spec_all(t, t.pb_barcode[t.pb_off[e1.primer] + j1], t.pb_barcode[t.pb_off[e2.primer] + j2],
+                         e1.primer, e2.primer, count, min_row);
         if (count > 1) { sample = min_row; resolution = SMX_RES_MULTIPLE_SPECIMENS; pool = t.spec_pool[min_row]; }
         else if (count == 1) { sample = min_row; resolution = SMX_RES_FULL_MATCH; pool = t.spec_pool[min_row]; }
         return;
     }
     if (b1 && !b2 && e1.nbest == 1) {
         resolution = SMX_RES_PARTIAL_FORWARD;
-        sample = (int)t.pb_barcode[t.pb_off[e1.primer] + e1.best[0]];
+        sample = (int)t.pb_barcode[t.pb_off[e1.primer] + e1.first_best];
     } else if (b2 && !b1 && e2.nbest == 1) {
         resolution = SMX_RES_PARTIAL_REVERSE;
-        sample = (int)t.pb_barcode[t.pb_off[e2.primer] + e2.best[0]];
+        sample = (int)t.pb_barcode[t.pb_off[e2.primer] + e2.first_best];
     }
 }
 
@@ -537,21 +562,31 @@ SMX_HD bool key_less(int a0, int a1, int a2, int a3, const Group &g) {
     return a3 < g.k3;
 }
 
+// Working storage of select_read.  The first pass keeps it in thread-local arrays of kSmallGroups
+// entries; reads that overflow are re-run by a second GPU pass on kBigGroups-entry global scratch.
+struct SelectStore {
+    Group *groups; Cand *gcand;     // specimen groups
+    Group *pg; Cand *pcand;         // partial (direction, barcode) groups
+    int *ts_cand, *ts_shift;        // trim shifts
+    int cap;
+};
+
 // Whole per-read selection.  ends: cache of 2*n_primers EndInfo (index strand*n_primers+primer).
-SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsigned char &flags) {
+SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, unsigned char &flags) {
     const Tables &t = *c.t;
     const Batch &b = *c.b;
     Emitter em; em.out = out; em.count = 0; em.full = false;
-    TrimState ts; ts.n = 0;
+    TrimState ts; ts.n = 0; ts.cap = st.cap; ts.cand = st.ts_cand; ts.shift = st.ts_shift;
     bool overflow = false;
     int n = c.n;
     flags = 0;
+    const int kMaxGroups = st.cap;
     if ((t.min_length != -1 && n < t.min_length) || (t.max_length != -1 && n > t.max_length)) return 0;
 
     Geo g = make_geo(n, t.L);
     bool irregular = !g.regular || read_is_flagged(b, c.read);
     for (int s = 0; s < 2; ++s)
-        for (int p = 0; p < t.n_primers; ++p) load_end(c, s, p, ends[s * t.n_primers + p], overflow);
+        for (int p = 0; p < t.n_primers; ++p) load_end(c, s, p, ends[s * t.n_primers + p]);
 
     // determine_orientation (demultiplex.py:602-638).  For regular reads the head-window test of a
     // forward-sense primer equals the tail-window match of its reverse complement on the other
@@ -586,7 +621,7 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsig
         }
     if (top == 0) {
         // no candidate at all: minimal match object (demultiplex.py:202-210)
-        EndInfo none; none.matched = 0; none.nhits = 0; none.nbest = 0; none.pd = -1; none.bd = -1;
+        EndInfo none; none.matched = 0; none.nhits = 0; none.nbest = 0; none.first_best = -1; none.pd = -1; none.bd = -1;
         none.ps = none.pe = 0; none.strand = 0; none.primer = 0;
         Cand cd; cd.pair = -1; cd.rc = 0; cd.e1 = cd.e2 = 0;
         emit_record(c, em, ts, overflow, 0, cd, none, none, -1, SMX_RES_UNKNOWN, -1);
@@ -626,8 +661,8 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsig
 
     // dereplicate_matches (demultiplex.py:262-393).  Groups in dict-insertion order; the None group
     // is one entry (key -1) whose members are re-walked afterwards.
-    Group groups[kMaxGroups];
-    Cand gcand[kMaxGroups];
+    Group *groups = st.groups;
+    Cand *gcand = st.gcand;
     int ng = 0;
     int none_pos = -1;
     for_each_top([&](int idx, const Cand &cd) {
@@ -636,10 +671,10 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsig
         bool full = a.matched && z.matched && a.nhits > 0 && z.nhits > 0;
         bool found = false;
         if (full) {
-            for (int i = 0; i < a.nbest; ++i)
-                for (int j = 0; j < z.nbest; ++j) {
-                    int row = spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + a.best[i]],
-                                         t.pb_barcode[t.pb_off[z.primer] + z.best[j]], a.primer, z.primer);
+            for (int j1 = next_best(c, a, -1); j1 >= 0; j1 = next_best(c, a, j1))
+                for (int j2 = next_best(c, z, -1); j2 >= 0; j2 = next_best(c, z, j2)) {
+                    int row = spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + j1],
+                                         t.pb_barcode[t.pb_off[z.primer] + j2], a.primer, z.primer);
                     if (row < 0) continue;
                     found = true;
                     int k0 = a.bd + z.bd, k1 = a.pd + z.pd, k2 = t.p_fidx[a.primer] + t.p_fidx[z.primer];
@@ -678,16 +713,16 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsig
             const EndInfo &z = ends[cd.e2];
             bool full = a.matched && z.matched && a.nhits > 0 && z.nhits > 0;
             if (!full) return true;
-            for (int i = 0; i < a.nbest; ++i)
-                for (int j = 0; j < z.nbest; ++j)
-                    if (spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + a.best[i]],
-                                   t.pb_barcode[t.pb_off[z.primer] + z.best[j]], a.primer, z.primer) >= 0)
+            for (int j1 = next_best(c, a, -1); j1 >= 0; j1 = next_best(c, a, j1))
+                for (int j2 = next_best(c, z, -1); j2 >= 0; j2 = next_best(c, z, j2))
+                    if (spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + j1], t.pb_barcode[t.pb_off[z.primer] + j2],
+                                   a.primer, z.primer) >= 0)
                         return false;
             return true;
         };
         // dereplicate_partial_matches (:396-477)
-        Group pg[kMaxGroups];
-        Cand pcand[kMaxGroups];
+        Group *pg = st.pg;
+        Cand *pcand = st.pcand;
         int npg = 0;
         for_each_top([&](int idx, const Cand &cd) {
             if (!in_none(cd)) return;
@@ -699,8 +734,8 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsig
             int pcnt = (a.matched ? 1 : 0) + (z.matched ? 1 : 0);
             int pdist = (a.matched ? a.pd : 0) + (z.matched ? z.pd : 0);
             int fidx = (a.matched ? t.p_fidx[a.primer] : 0) + (z.matched ? t.p_fidx[z.primer] : 0);
-            for (int i = 0; i < be.nbest; ++i) {
-                int key = (hb1 ? 0 : (1 << 30)) | (int)t.pb_barcode[t.pb_off[be.primer] + be.best[i]];
+            for (int jb = next_best(c, be, -1); jb >= 0; jb = next_best(c, be, jb)) {
+                int key = (hb1 ? 0 : (1 << 30)) | (int)t.pb_barcode[t.pb_off[be.primer] + jb];
                 int q = -1;
                 for (int x = 0; x < npg; ++x) if (pg[x].key == key) { q = x; break; }
                 if (q < 0) {
@@ -758,6 +793,23 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, smx_record *out, unsig
     if (em.full) flags |= 1;
     if (overflow) flags |= 2;
     return em.count;
+}
+
+// Bytes of global scratch one read needs in the second pass.
+constexpr size_t kBigScratchBytes = (size_t)kBigGroups * (2 * sizeof(Group) + 2 * sizeof(Cand) + 2 * sizeof(int)) +
+                                    2 * SMX_MAX_PRIMERS * sizeof(EndInfo);
+
+SMX_HD SelectStore big_store(unsigned char *base, EndInfo *&ends) {
+    SelectStore st;
+    st.groups = (Group *)base; base += kBigGroups * sizeof(Group);
+    st.pg = (Group *)base; base += kBigGroups * sizeof(Group);
+    st.gcand = (Cand *)base; base += kBigGroups * sizeof(Cand);
+    st.pcand = (Cand *)base; base += kBigGroups * sizeof(Cand);
+    st.ts_cand = (int *)base; base += kBigGroups * sizeof(int);
+    st.ts_shift = (int *)base; base += kBigGroups * sizeof(int);
+    ends = (EndInfo *)base;
+    st.cap = kBigGroups;
+    return st;
 }
 
 }  // namespace smx

@@ -51,9 +51,10 @@ inline bool build_peq(const char *s, int m, bool reversed, u64 *out /*16*/) {
 
 struct HostTables {
     Tables t;
-    std::vector<u64> peq_rc, peq_rcrev, peq_fw, bpeq, spec_key, spec_p1, spec_p2;
-    std::vector<unsigned char> b_len;
-    std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row;
+    std::vector<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
+    std::vector<unsigned char> b_len, bw_len, bw_primer;
+    std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
+    std::vector<unsigned short> bw_list;
     std::vector<i32> pair_pool, spec_pool;
     int max_nb = 0;
     std::string error;
@@ -103,7 +104,7 @@ struct HostTables {
         }
         t.pb_off[nP] = tb->pb_off[nP];
         const u32 n_list = tb->pb_off[nP];
-        bpeq.assign((size_t)n_list * 16, 0);
+        std::vector<std::string> b_str(n_list);
         b_len.assign(n_list, 0);
         pb_barcode.assign(tb->pb_barcode, tb->pb_barcode + n_list);
         max_nb = 0;
@@ -120,8 +121,8 @@ struct HostTables {
                 if (m < 1 || m + t.k_idx > SMX_MAX_PATTERN)
                     return err("barcode length %d + k %d exceeds %d", m, t.k_idx, SMX_MAX_PATTERN);
                 if (t.k_idx >= m) return err("barcode distance threshold %d must be below barcode length %d", t.k_idx, m);
-                if (m > 32) t.buse64 = 1;
-                if (!build_peq(s, m, false, &bpeq[(size_t)e * 16])) return err("barcode has a non-IUPAC character");
+                for (int i = 0; i < m; ++i) if (code_of(s[i]) < 0) return err("barcode has a non-IUPAC character");
+                b_str[e].assign(s, s + m);
                 if (t.prefilter)
                     for (int i = 0; i < m; ++i)
                         if (code_of(s[i]) > 3)
@@ -130,6 +131,43 @@ struct HostTables {
                 b_len[e] = (unsigned char)m;
             }
         }
+        // bit-sliced barcode words: per primer, barcodes grouped by length, 32 to a word
+        bw_len.clear(); bw_primer.clear(); bw_row.clear(); bw_valid.clear(); bw_list.clear(); beq.clear();
+        for (int p = 0; p < nP; ++p) {
+            t.bw_off[p] = (u32)bw_len.size();
+            std::vector<int> lens;
+            for (u32 e = tb->pb_off[p]; e < tb->pb_off[p + 1]; ++e) lens.push_back(b_len[e]);
+            std::sort(lens.begin(), lens.end());
+            lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+            for (int m : lens) {
+                std::vector<u32> members;
+                for (u32 e = tb->pb_off[p]; e < tb->pb_off[p + 1]; ++e) if (b_len[e] == m) members.push_back(e);
+                for (size_t base = 0; base < members.size(); base += 32) {
+                    size_t cnt = std::min<size_t>(32, members.size() - base);
+                    bw_len.push_back((unsigned char)m);
+                    bw_primer.push_back((unsigned char)p);
+                    bw_row.push_back((u32)(beq.size() / 16));
+                    bw_valid.push_back(cnt == 32 ? ~0u : ((1u << cnt) - 1));
+                    size_t row0 = beq.size();
+                    beq.resize(row0 + (size_t)m * 16, 0);
+                    for (size_t q = 0; q < 32; ++q) {
+                        if (q >= cnt) { bw_list.push_back(0); continue; }
+                        u32 e = members[base + q];
+                        bw_list.push_back((unsigned short)(e - tb->pb_off[p]));
+                        for (int i = 0; i < m; ++i) {
+                            int pc = code_of(b_str[e][i]);
+                            for (int c = 0; c < 16; ++c)
+                                if (sym_equal(pc, c)) beq[row0 + (size_t)i * 16 + c] |= 1u << q;
+                        }
+                    }
+                }
+            }
+        }
+        t.bw_off[nP] = (u32)bw_len.size();
+        t.n_bwords = (int)bw_len.size();
+        t.hit_cap = 4;
+        if (tb->pb_off[nP] - tb->pb_off[0] > 65535) return err("more than 65535 barcodes for one primer");
+
         u32 run = 0;
         for (int s = 0; s < 2; ++s)
             for (int p = 0; p < nP; ++p) { t.bslot_base[s * nP + p] = run; run += tb->pb_off[p + 1] - tb->pb_off[p]; }
@@ -158,16 +196,22 @@ struct HostTables {
         spec_pool.assign(tb->spec_pool, tb->spec_pool + tb->n_specimens);
         for (u32 i = 0; i < tb->n_specimens; ++i)
             if (tb->spec_pool[i] < -1 || tb->spec_pool[i] > 32767) return err("specimen pool id out of range");
-        set_pointers(peq_rc.data(), peq_rcrev.data(), peq_fw.data(), bpeq.data(), b_len.data(), pb_barcode.data(),
+        set_pointers(peq_rc.data(), peq_rcrev.data(), peq_fw.data(), b_len.data(), pb_barcode.data(),
                      pair_fwd.data(), pair_rev.data(), pair_pool.data(), spec_key.data(), spec_key_off.data(),
                      spec_row.data(), spec_p1.data(), spec_p2.data(), spec_pool.data());
+        set_bword_pointers(bw_len.data(), bw_primer.data(), bw_row.data(), bw_valid.data(), bw_list.data(), beq.data());
         return true;
     }
 
-    void set_pointers(const u64 *a, const u64 *b, const u64 *c, const u64 *d, const unsigned char *e, const u32 *f,
+    void set_bword_pointers(const unsigned char *len, const unsigned char *prim, const u32 *row, const u32 *valid,
+                            const unsigned short *list, const u32 *eq) {
+        t.bw_len = len; t.bw_primer = prim; t.bw_row = row; t.bw_valid = valid; t.bw_list = list; t.beq = eq;
+    }
+
+    void set_pointers(const u64 *a, const u64 *b, const u64 *c, const unsigned char *e, const u32 *f,
                       const u32 *g, const u32 *h, const i32 *i, const u64 *j, const u32 *k, const u32 *l,
                       const u64 *m, const u64 *n, const i32 *o) {
-        t.peq_rc = a; t.peq_rcrev = b; t.peq_fw = c; t.bpeq = d; t.b_len = e; t.pb_barcode = f;
+        t.peq_rc = a; t.peq_rcrev = b; t.peq_fw = c; t.b_len = e; t.pb_barcode = f;
         t.pair_fwd = g; t.pair_rev = h; t.pair_pool = i; t.spec_key = j; t.spec_key_off = k; t.spec_row = l;
         t.spec_p1_mask = m; t.spec_p2_mask = n; t.spec_pool = o;
     }

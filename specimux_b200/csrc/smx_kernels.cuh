@@ -35,7 +35,7 @@ SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int
 // Stage 1.  match_one_end's primer search (demultiplex.py:757-766) for one (read, strand, primer).
 
 template <typename W>
-SMX_HD void primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
+SMX_HD bool primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
                                  const u64 *peq, const u64 *peq_rev, const u64 *peq_fw) {
     const int n = (int)b.lengths[read];
     const Geo g = make_geo(n, t.L);
@@ -123,65 +123,263 @@ SMX_HD void primer_search_thread(const Tables &t, const Batch &b, u32 read, int 
         ohit = bst <= k;
     }
     b.orient_hit[hit_idx] = ohit;
+    return h.distance >= 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 2.  match_one_end's barcode loop (demultiplex.py:781-815) for one (read, strand, primer,
-// barcode j): SHW search at every equal-best primer end, strictly-smallest distance wins.
-// Returns the SHW cells / word-columns this thread accounts for (SURVEY.md 8d formula).
+// Stage 2.  match_one_end's barcode loop (demultiplex.py:781-815): for one matched (read, strand,
+// primer) slot and one bword (<= 32 barcodes of one length), the SHW distance of every barcode at
+// every equal-best primer end; strictly-smallest distance over the ends wins (first end on ties).
+//
+// The DP is evaluated BIT-SLICED ACROSS BARCODES: bit q of every machine word belongs to barcode q,
+// and one Myers/Hyyro cell update (6 three-input logic ops on the +-1 delta planes) advances cell
+// (i, j) of all 32 barcodes at once.  Only the Ukkonen band |i - j| <= k is evaluated (anything
+// outside costs > k); cells beyond the band edge are assumed one worse than their in-band
+// neighbour, which keeps every value <= k exact.  Row m is read out through a small bit-sliced
+// counter anchored on the band's lower diagonal (D[k][0] = k).
+// Plain-logic restatement of edlib SHW (alignment.py:42 with mode='SHW') for bounded k.
 
-template <typename W>
-SMX_HD void barcode_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer, int j,
-                                  const u64 *peq, int m, unsigned long long &cells, unsigned long long &wcols) {
+template <int K> struct BitSliced {
+    static constexpr int NT = 2 * K + 1;                       // band width
+    static constexpr int NB = K <= 1 ? 3 : (K <= 4 ? 4 : 5);   // counter bits: values up to 3K+1 matter
+
+    struct Out { u32 rp[NT > 1 ? NT - 1 : 1], rm[NT > 1 ? NT - 1 : 1], cnt[NB], over; };
+
+    // One cell of the automaton for 32 barcodes.
+    static SMX_HD void cell(u32 Eq, u32 Pv, u32 Mv, u32 Ph, u32 Mh, u32 &oPv, u32 &oMv, u32 &oPh, u32 &oMh, u32 &inc) {
+        u32 Xv = Eq | Mv, Xh = Eq | Mh;
+        oPv = Mh | ~(Xv | Ph);
+        oMv = Ph & Xv;
+        oPh = Mv | ~(Xh | Pv);
+        oMh = Pv & Xh;
+        inc = ~(Xv | Mh);                                      // D[i][j] - D[i-1][j-1]
+    }
+
+    // beq_rows: table rows of this bword ([i][16]); rowwin(i): nibble t = 4-bit symbol of flank
+    // column i-K+t (1-based columns), kSymOther beyond the flank.
+    template <typename RowWin>
+    static SMX_HD void run(const u32 *beq_rows, int m, RowWin rowwin, Out &o) {
+        u32 HP[NT], HM[NT];                                    // horizontal deltas of the previous row
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < NT; ++t) { HP[t] = ~0u; HM[t] = 0; }    // row 0: D[0][j] = j
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int b = 0; b < NB; ++b) o.cnt[b] = (K >> b) & 1 ? ~0u : 0u;    // anchor D[K][0] = K
+        o.over = 0;
+        for (int i = 1; i <= m; ++i) {
+            const u32 *row = beq_rows + (i - 1) * 16;
+            const u64 W = rowwin(i);
+            u32 Pv = ~0u, Mv = 0;                              // column 0 / below the band: +1
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int t = 0; t < NT; ++t) {
+                int j = i - K + t;
+                if (j < 1) continue;                           // uniform over the warp
+                u32 Ph = t < NT - 1 ? HP[t + 1] : ~0u;          // above the band: +1
+                u32 Mh = t < NT - 1 ? HM[t + 1] : 0u;
+                u32 Eq = row[(u32)(W >> (4 * t)) & 15u];
+                u32 nPv, nMv, nPh, nMh, inc;
+                cell(Eq, Pv, Mv, Ph, Mh, nPv, nMv, nPh, nMh, inc);
+                if (t == 0) {                                   // lower diagonal: anchor += inc
+                    u32 x = inc;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int b = 0; b < NB; ++b) { u32 c = o.cnt[b] & x; o.cnt[b] ^= x; x = c; }
+                    o.over |= x;
+                }
+                HP[t] = nPh; HM[t] = nMh;                       // becomes index t-1+1 of the next row
+                Pv = nPv; Mv = nMv;
+            }
+            // shift the window by one column for the next row: entry t of the next row is column
+            // (i+1)-K+t = this row's t+1
+            // (done implicitly: next row reads HP[t+1], this row wrote HP[t] for its own column t)
+        }
+        // After the last row HP[t]/HM[t] hold Delta-h of row m at column m-K+t.
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 1; t < NT; ++t) { o.rp[t - 1] = HP[t]; o.rm[t - 1] = HM[t]; }
+    }
+};
+// value <= K on NB bit-planes (K compile-time)
+template <int K, int NB> SMX_HD u32 planes_le(const u32 *v) {
+    u32 gt = 0, eq = ~0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = NB - 1; b >= 0; --b) {
+        if ((K >> b) & 1) eq &= v[b];
+        else { gt |= eq & v[b]; eq &= ~v[b]; }
+    }
+    return ~gt;
+}
+
+SMX_HD int popcount32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+SMX_HD int lowest_bit32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
+constexpr int kMaxWordHits = 32;
+
+// One (matched slot, bword).  `beq_rows` points at the bword's [m][16] table (shared memory in the
+// CUDA launch).  Accumulates the SURVEY.md 8d work formula into cells / wcols.
+template <int K>
+SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer, u32 g,
+                                     const u32 *beq_rows, unsigned long long &cells, unsigned long long &wcols) {
+    typedef BitSliced<K> BS;
     const u32 slot = slot_index(t, strand, primer);
     const smx_primer_hit ph = b.phit[(u64)slot * b.n_pad + read];
-    if (ph.distance < 0) return;
+    const u64 gslot = (u64)strand * t.n_bwords + g;
+    if (ph.distance < 0) { b.bh_count[gslot * b.n_pad + read] = 0; return; }
     const int n = (int)b.lengths[read];
-    const Geo g = make_geo(n, t.L);
+    const Geo geo = make_geo(n, t.L);
     const u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
-    const int k = t.k_idx;
+    const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
+    const int m = t.bw_len[g];
+    const u32 valid = t.bw_valid[g];
+    const int nbits = popcount32(valid);
+    const bool small = m + K <= 16;            // whole flank fits one 64-bit register
 
-    smx_barcode_hit out;
-    out.distance = -1; out.end_mask = 0; out.search_start = 0; out.pad = 0;
+    smx_barcode_hit hits[kMaxWordHits];
+    int nh = 0;
     for (int mwi = 0; mwi < t.mw; ++mwi) {
         u32 word = emask[(u64)mwi * b.n_pad];
         while (word) {
-#if defined(__CUDA_ARCH__)
-            int bit = __ffs((int)word) - 1;
-#else
-            int bit = __builtin_ctz(word);
-#endif
+            int p = mwi * 32 + lowest_bit32(word);
             word &= word - 1;
-            int p = mwi * 32 + bit;
-            int e_rep = g.woff + p + g.delta;
-            Flank f = make_flank(e_rep, n);
-            int fl = n - f.a_align;
-            int cols = fl < m + k ? fl : m + k;
-            cells += (unsigned long long)m * (unsigned long long)cols;
-            wcols += (unsigned long long)((m + 31) >> 5) * (unsigned long long)cols;
+            const Flank f = make_flank(geo.woff + p + geo.delta, n);
+            const int fl = n - f.a_align;
+            const int cols = fl < m + K ? fl : m + K;
+            if (cols > 0) {
+                cells += (unsigned long long)nbits * m * cols;
+                wcols += (unsigned long long)nbits * ((m + 31) >> 5) * cols;
+            }
+            const int base = f.a_align - geo.woff;          // staged index of flank column 1
+            u64 F = ~0ull;
+            if (small && cols > 0) {
+                // 16 symbols starting at staged position `base`, symbols >= cols forced to "other"
+                int w0 = base >> 3, sh = 4 * (base & 7);
+                u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
+                u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
+                u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
+                u64 lo = ((u64)a1 << 32) | a0, hi = a2;
+                F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+                if (cols < 16) F |= ~0ull << (4 * cols);
+            }
             if (t.prefilter) {
                 // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key
                 // barcode_rc + flank[:m-k] can only be present if those m-k symbols exist and are
                 // all A/C/G/T; for such flanks the filter has no false negatives.
-                int need = m - k;
+                const int need = m - K;
                 if (n - f.a_pref < need) continue;
                 bool acgt = true;
-                for (int x = 0; x < need; ++x)
-                    if (staged_sym(t, b, read, strand, f.a_pref - g.woff + x) > 3) { acgt = false; break; }
+                if (small && f.a_pref == f.a_align) {
+                    u64 chk = need >= 16 ? ~0ull : ((1ull << (4 * need)) - 1);
+                    acgt = (F & chk & 0xCCCCCCCCCCCCCCCCull) == 0;
+                } else {
+                    for (int x = 0; x < need; ++x)
+                        if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { acgt = false; break; }
+                }
                 if (!acgt) continue;
             }
-            if (cols <= 0) continue;                 // empty target: edlib reports distance m > k
-            int base = f.a_align - g.woff;
-            auto load = [&](int x) { return staged_sym(t, b, read, strand, base + x); };
-            int best; u64 mask;
-            shw_search<W>(peq, m, cols, load, best, mask);
-            if (best <= k && (out.distance < 0 || best < out.distance)) {
-                out.distance = (int16_t)best; out.end_mask = mask; out.search_start = f.bs;
+            if (cols < m - K || cols <= 0) continue;         // D[m][j] >= m - j > K for every column
+            typename BS::Out o;
+            if (small) {
+                auto rowwin = [&](int i) -> u64 {
+                    int shn = i - K - 1;                      // first column of the band, 0-based symbol
+                    return shn >= 0 ? (F >> (4 * shn)) : (F << (4 * -shn));
+                };
+                BS::run(beq_rows, m, rowwin, o);
+            } else {
+                auto rowwin = [&](int i) -> u64 {
+                    u64 W = 0;
+                    for (int tt = 0; tt < BS::NT; ++tt) {
+                        int j = i - K + tt;
+                        u64 c = (j >= 1 && j <= cols) ? (u64)staged_sym(t, b, read, strand, base + j - 1) : 15ull;
+                        W |= c << (4 * tt);
+                    }
+                    return W;
+                };
+                BS::run(beq_rows, m, rowwin, o);
+            }
+            // bit-sliced test "some in-range column has D[m][j] <= K"
+            u32 v[BS::NB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < BS::NB; ++q) v[q] = o.cnt[q];
+            u32 ov = o.over;
+            u32 flag = (m - K <= cols) ? (planes_le<K, BS::NB>(v) & ~ov) : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int tt = 1; tt < BS::NT; ++tt) {
+                u32 x = o.rp[tt - 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int q = 0; q < BS::NB; ++q) { u32 c = v[q] & x; v[q] ^= x; x = c; }
+                ov |= x;
+                x = o.rm[tt - 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int q = 0; q < BS::NB; ++q) { u32 br = ~v[q] & x; v[q] ^= x; x = br; }
+                if (m - K + tt <= cols) flag |= planes_le<K, BS::NB>(v) & ~ov;
+            }
+            flag &= valid;
+            // exact scalar read-out of the few flagged barcodes
+            while (flag) {
+                int q = lowest_bit32(flag);
+                flag &= flag - 1;
+                int val = 0;
+                for (int bb = 0; bb < BS::NB; ++bb) val |= (int)((o.cnt[bb] >> q) & 1) << bb;
+                int best = 1 << 20;
+                u64 mask = 0;
+                for (int tt = 0; tt < BS::NT; ++tt) {
+                    if (tt > 0) val += (int)((o.rp[tt - 1] >> q) & 1) - (int)((o.rm[tt - 1] >> q) & 1);
+                    int col = m - K + tt;
+                    if (col > cols) break;
+                    if (val < best) { best = val; mask = 0; }
+                    if (val == best) mask |= 1ull << (col - 1);
+                }
+                if (best > K) continue;
+                int j = (int)t.bw_list[(u64)g * 32 + q];
+                int pos = 0;
+                while (pos < nh && (int)hits[pos].barcode < j) ++pos;
+                if (pos < nh && (int)hits[pos].barcode == j) {
+                    if (best < hits[pos].distance) {           // strictly smaller wins (demultiplex.py:809)
+                        hits[pos].distance = (int16_t)best; hits[pos].end_mask = mask; hits[pos].search_start = f.bs;
+                    }
+                } else {
+                    for (int x = nh; x > pos; --x) hits[x] = hits[x - 1];
+                    hits[pos].barcode = (uint16_t)j; hits[pos].distance = (int16_t)best;
+                    hits[pos].end_mask = mask; hits[pos].search_start = f.bs;
+                    ++nh;
+                }
             }
         }
     }
-    u64 bslot = (u64)t.bslot_base[slot] + (u64)j;
-    b.bhit[bslot * b.n_pad + read] = out;
+    b.bh_count[gslot * b.n_pad + read] = (unsigned char)nh;
+    if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
+    int lim = nh < t.hit_cap ? nh : t.hit_cap;
+    for (int e = 0; e < lim; ++e) b.bh_list[(gslot * t.hit_cap + e) * b.n_pad + read] = hits[e];
 }
 
 #if defined(__CUDACC__)
@@ -211,10 +409,22 @@ __global__ void __launch_bounds__(128) k_primer_search(Batch b) {
     __syncthreads();
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0;
+    bool matched = false;
     if (read < b.n_reads) {
-        primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[1], s_peq[2]);
+        matched = primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[1], s_peq[2]);
         int n = (int)b.lengths[read];
         cells = (unsigned long long)(n < c_tables.L ? n : c_tables.L);       // HW columns of this search
+    }
+    // compact list of matched reads per slot (warp-aggregated append; order is irrelevant)
+    {
+        const unsigned ball = __ballot_sync(0xffffffffu, matched);
+        if (ball) {
+            const int lane = threadIdx.x & 31;
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(&b.slot_count[blockIdx.y], (u32)__popc(ball));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (matched) b.slot_list[(u64)blockIdx.y * b.n_pad + base + __popc(ball & ((1u << lane) - 1))] = read;
+        }
     }
     for (int o = 16; o; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
     if ((threadIdx.x & 31) == 0 && cells) {
@@ -224,43 +434,73 @@ __global__ void __launch_bounds__(128) k_primer_search(Batch b) {
     }
 }
 
-// One warp per (read, group of 32 barcodes); lanes = barcodes.  Shared Peq layout [barcode][16].
-template <typename W>
-__global__ void __launch_bounds__(256) k_barcode_search(Batch b, int primer, int strand) {
-    extern __shared__ u64 s_bpeq[];            // nb * 16
+// One thread per (matched slot entry, bword); the bword's bit-sliced table sits in shared memory.
+template <int K>
+__global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
+    __shared__ u32 s_beq[SMX_MAX_PATTERN * 16];
     const Tables &t = c_tables;
-    const int nb = (int)(t.pb_off[primer + 1] - t.pb_off[primer]);
-    for (int i = threadIdx.x; i < nb * 16; i += blockDim.x) s_bpeq[i] = t.bpeq[(u64)t.pb_off[primer] * 16 + i];
+    const u32 g = blockIdx.y % t.n_bwords;
+    const int strand = blockIdx.y / t.n_bwords;
+    const int primer = t.bw_primer[g];
+    const u32 slot = slot_index(t, strand, primer);
+    const u32 cnt = b.slot_count[slot];
+    if (blockIdx.x * blockDim.x >= cnt) return;
+    const int m = t.bw_len[g];
+    for (int i = threadIdx.x; i < m * 16; i += blockDim.x) s_beq[i] = t.beq[(u64)t.bw_row[g] * 16 + i];
     __syncthreads();
-    const int groups = (nb + 31) >> 5;
-    const int lane = threadIdx.x & 31;
-    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    u32 read = (u32)(warp / groups);
-    int j = (int)(warp % groups) * 32 + lane;
+    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0, wcols = 0;
-    if (read < b.n_reads && j < nb)
-        barcode_search_thread<W>(t, b, read, strand, primer, j, s_bpeq + j * 16, t.b_len[t.pb_off[primer] + j],
-                                 cells, wcols);
+    if (idx < cnt) {
+        const u32 read = b.slot_list[(u64)slot * b.n_pad + idx];
+        barcode_bitsliced_thread<K>(t, b, read, strand, primer, g, s_beq, cells, wcols);
+    }
     for (int o = 16; o; o >>= 1) {
         cells += __shfl_down_sync(0xffffffffu, cells, o);
         wcols += __shfl_down_sync(0xffffffffu, wcols, o);
     }
-    if (lane == 0 && cells) {
+    if ((threadIdx.x & 31) == 0 && cells) {
         atomicAdd(&b.counters[1], cells);
         atomicAdd(&b.counters[3], wcols);
     }
 }
 
+// First pass: one thread per read, working storage in thread-local arrays.  write_pass = 0 counts
+// records (and flags reads whose groups overflow kSmallGroups), write_pass = 1 writes them.
 template <int MAXP>
 __global__ void __launch_bounds__(128) k_select(Batch b, int write_pass) {
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     if (read >= b.n_reads) return;
+    if (write_pass && (b.read_flags[read] & 2)) return;        // handled by k_select_big
     EndInfo ends[2 * MAXP];
+    Group groups[kSmallGroups], pg[kSmallGroups];
+    Cand gcand[kSmallGroups], pcand[kSmallGroups];
+    int ts_cand[kSmallGroups], ts_shift[kSmallGroups];
+    SelectStore st;
+    st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
+    st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
     SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
     unsigned char flags;
     smx_record *out = write_pass ? b.records + b.rec_offset[read] : nullptr;
-    u32 cnt = select_read(c, ends, out, flags);
+    u32 cnt = select_read(c, ends, st, out, flags);
     if (!write_pass) { b.rec_count[read] = cnt; b.read_flags[read] = flags; }
+}
+
+// Second pass over the (rare) reads flagged by the first: same routine, kBigGroups-entry storage
+// in global scratch.  One thread per flagged read.
+__global__ void __launch_bounds__(32) k_select_big(Batch b, const u32 *list, u32 n_list, unsigned char *scratch, int write_pass) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    u32 read = list[i];
+    EndInfo *ends;
+    SelectStore st = big_store(scratch + (size_t)i * kBigScratchBytes, ends);
+    SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
+    unsigned char flags;
+    smx_record *out = write_pass ? b.records + b.rec_offset[read] : nullptr;
+    u32 cnt = select_read(c, ends, st, out, flags);
+    if (!write_pass) {
+        b.rec_count[read] = cnt;
+        b.read_flags[read] = (unsigned char)((flags & 1) | 2 | ((flags & 2) ? 4 : 0));   // bit2: still overflowing
+    }
 }
 
 // Exclusive scan of rec_count -> rec_offset (n+1 entries), three small kernels.
@@ -321,14 +561,18 @@ __global__ void k_scan_apply(const u32 *in, u32 n, const u32 *block_sums, u32 *o
     if (i == n - 1) out[n] = block_sums[blockIdx.x] + s[threadIdx.x];
 }
 
+// counters[4] += reads with a full match; counters[5] lo += reads needing the big pass (bit1),
+// hi += reads that overflowed even the big pass (bit2).
 __global__ void k_count_flags(const unsigned char *flags, u32 n, unsigned long long *matched, unsigned int *overflow) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned f = i < n ? flags[i] : 0;
     unsigned m = __ballot_sync(0xffffffffu, f & 1);
     unsigned o = __ballot_sync(0xffffffffu, f & 2);
+    unsigned h = __ballot_sync(0xffffffffu, f & 4);
     if ((threadIdx.x & 31) == 0) {
         if (m) atomicAdd(matched, (unsigned long long)__popc(m));
         if (o) atomicAdd(overflow, (unsigned)__popc(o));
+        if (h) atomicAdd(overflow + 1, (unsigned)__popc(h));
     }
 }
 

@@ -94,7 +94,7 @@ def hostsim_binding():
         srcs = [os.path.join(d, "hostsim.cpp")] + [os.path.join(ROOT, "specimux_b200", "csrc", f)
                                                    for f in ("smx_core.cuh", "smx_kernels.cuh", "smx_host_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-maybe-uninitialized",
                                    "-o", so, srcs[0]])
         lib = ctypes.CDLL(so)
         lib.hostsim_last_error.restype = ctypes.c_char_p

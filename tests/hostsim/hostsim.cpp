@@ -26,7 +26,9 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     std::vector<u32> win((size_t)2 * t.wpw * n_pad), endmask((size_t)2 * nP * t.mw * n_pad), rec_count(n), rec_offset(n + 1);
     std::vector<smx_primer_hit> phit((size_t)2 * nP * n_pad);
     std::vector<unsigned char> orient_hit((size_t)2 * nP * n_pad), flags(n);
-    std::vector<smx_barcode_hit> bhit((size_t)t.total_bslots * n_pad);
+    std::vector<u32> slot_list((size_t)2 * nP * n_pad + 1), slot_count((size_t)2 * nP + 1, 0);
+    std::vector<unsigned char> bh_count((size_t)2 * t.n_bwords * n_pad + 1);
+    std::vector<smx_barcode_hit> bh_list;
     unsigned long long counters[8] = {0};
     Batch b;
     memset(&b, 0, sizeof(b));
@@ -35,7 +37,8 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     bool flagged = in->packed4 && in->off4 && in->packed4_words;
     b.packed4 = flagged ? in->packed4 : nullptr; b.off4 = flagged ? in->off4 : nullptr;
     b.win = win.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.orient_hit = orient_hit.data();
-    b.bhit = bhit.data(); b.rec_count = rec_count.data(); b.rec_offset = rec_offset.data();
+    b.slot_list = slot_list.data(); b.slot_count = slot_count.data(); b.bh_count = bh_count.data();
+    b.rec_count = rec_count.data(); b.rec_offset = rec_offset.data();
     b.read_flags = flags.data(); b.counters = counters;
 
     for (u32 r = 0; r < n; ++r)
@@ -47,28 +50,56 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                 if (t.use64) primer_search_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
                 else primer_search_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
             }
-    for (int s = 0; s < 2; ++s)
-        for (int p = 0; p < nP; ++p) {
-            int nb = (int)(t.pb_off[p + 1] - t.pb_off[p]);
-            for (u32 r = 0; r < n; ++r)
-                for (int j = 0; j < nb; ++j) {
-                    const u64 *peq = t.bpeq + ((size_t)t.pb_off[p] + j) * 16;
-                    int m = t.b_len[t.pb_off[p] + j];
-                    if (t.buse64) barcode_search_thread<u64>(t, b, r, s, p, j, peq, m, counters[1], counters[3]);
-                    else barcode_search_thread<u32>(t, b, r, s, p, j, peq, m, counters[1], counters[3]);
+    Tables &tm = ht.t;
+    for (;;) {
+        bh_list.assign((size_t)2 * t.n_bwords * t.hit_cap * n_pad + 1, smx_barcode_hit());
+        b.bh_list = bh_list.data();
+        counters[1] = counters[3] = counters[7] = 0;
+        for (int s = 0; s < 2; ++s)
+            for (int g = 0; g < t.n_bwords; ++g) {
+                const u32 *rows = t.beq + (size_t)t.bw_row[g] * 16;
+                int p = t.bw_primer[g];
+                for (u32 r = 0; r < n; ++r) {
+                    switch (t.k_idx) {
+#define SMX_K2(KK) case KK: barcode_bitsliced_thread<KK>(t, b, r, s, p, (u32)g, rows, counters[1], counters[3]); break;
+                        SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
+#undef SMX_K2
+                        default: snprintf(g_err, sizeof(g_err), "unsupported k_idx"); return SMX_ERR_ARG;
+                    }
                 }
+            }
+        if (counters[7] == 0) break;
+        if (tm.hit_cap >= kMaxWordHits) { snprintf(g_err, sizeof(g_err), "hit list overflow"); return SMX_ERR_INTERNAL; }
+        tm.hit_cap = std::min(kMaxWordHits, tm.hit_cap * 4);
+    }
+    std::vector<unsigned char> big(kBigScratchBytes);
+    auto run_select = [&](u32 r, smx_record *dst, unsigned char &f) -> u32 {
+        SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
+        EndInfo ends[2 * SMX_MAX_PRIMERS];
+        Group groups[kSmallGroups], pg[kSmallGroups];
+        Cand gcand[kSmallGroups], pcand[kSmallGroups];
+        int ts_cand[kSmallGroups], ts_shift[kSmallGroups];
+        SelectStore st;
+        st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
+        st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
+        u32 cnt = select_read(c, ends, st, dst, f);
+        if (f & 2) {            // second pass on the big scratch, as k_select_big does
+            EndInfo *bends;
+            SelectStore bst = big_store(big.data(), bends);
+            cnt = select_read(c, bends, bst, dst, f);
+            if (f & 2) f |= 4;
         }
-    std::vector<EndInfo> ends(2 * SMX_MAX_PRIMERS);
+        return cnt;
+    };
     u64 total = 0, matched = 0;
     for (u32 r = 0; r < n; ++r) {
-        SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
         unsigned char f;
-        rec_count[r] = select_read(c, ends.data(), nullptr, f);
+        rec_count[r] = run_select(r, nullptr, f);
         flags[r] = f;
         rec_offset[r] = (u32)total;
         total += rec_count[r];
         matched += f & 1;
-        if (f & 2) { snprintf(g_err, sizeof(g_err), "read %u exceeded an internal tie/group capacity", r); return SMX_ERR_INTERNAL; }
+        if (f & 4) { snprintf(g_err, sizeof(g_err), "read %u exceeds %d dereplication groups", r, kBigGroups); return SMX_ERR_INTERNAL; }
     }
     rec_offset[n] = (u32)total;
     out->n_records = total; out->n_matched = matched;
@@ -76,14 +107,31 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     std::vector<smx_record> records(total + 1);
     b.records = records.data();
     for (u32 r = 0; r < n; ++r) {
-        SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
         unsigned char f;
-        select_read(c, ends.data(), records.data() + rec_offset[r], f);
+        run_select(r, records.data() + rec_offset[r], f);
     }
     if (out->rec_offset) memcpy(out->rec_offset, rec_offset.data(), (size_t)(n + 1) * sizeof(u32));
     if (out->records && total) memcpy(out->records, records.data(), total * sizeof(smx_record));
     if (out->primer_hits) memcpy(out->primer_hits, phit.data(), phit.size() * sizeof(smx_primer_hit));
     if (out->endmask_bits) memcpy(out->endmask_bits, endmask.data(), endmask.size() * sizeof(u32));
-    if (out->barcode_hits && !bhit.empty()) memcpy(out->barcode_hits, bhit.data(), bhit.size() * sizeof(smx_barcode_hit));
+    if (out->barcode_hits && t.total_bslots) {
+        smx_barcode_hit none;
+        none.end_mask = 0; none.search_start = 0; none.distance = -1; none.barcode = 0;
+        for (size_t i = 0; i < (size_t)t.total_bslots * n; ++i) out->barcode_hits[i] = none;
+        for (int sd = 0; sd < 2; ++sd)
+            for (int g = 0; g < t.n_bwords; ++g) {
+                int p = t.bw_primer[g];
+                u32 slot = (u32)(sd * nP + p);
+                u64 gslot = (u64)sd * t.n_bwords + g;
+                for (u32 r = 0; r < n; ++r) {
+                    if (phit[(size_t)slot * n_pad + r].distance < 0) continue;
+                    int k = std::min<int>(bh_count[gslot * n_pad + r], t.hit_cap);
+                    for (int e = 0; e < k; ++e) {
+                        const smx_barcode_hit &h = bh_list[(gslot * t.hit_cap + e) * n_pad + r];
+                        out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r] = h;
+                    }
+                }
+            }
+    }
     return SMX_OK;
 }

@@ -183,3 +183,26 @@ def test_full_size_properties_ont037():
     agree = np.mean(fullrec["sample"] == truth)
     assert agree > 0.99, agree      # the rest are genuine mis-calls of the reference algorithm at 7 % error
     assert whole.n_matched / ds.n_reads > 0.90
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_cuda_random_tables_match_live_oracle(seed):
+    """Same randomised tables/reads as tests/test_random_tables_hostsim.py, through the CUDA library
+    (exercises mixed barcode lengths, k = 0..5, hit-list and group overflow second passes)."""
+    from oracle import pipeline as orc
+    from test_random_tables_hostsim import make_case
+    primers, specimens_rows, reads, k_idx, flags = make_case(seed)
+    try:
+        tables = orc.Tables(primers, specimens_rows)
+    except ValueError:
+        pytest.skip("generator produced an invalid table")
+    oparams = orc.setup_params(tables, index_edit_distance=k_idx, search_len=flags["search_len"],
+                               preorient=not flags["disable_preorient"], prefilter=not flags["disable_prefilter"],
+                               trim=flags["trim"], dereplicate=flags["dereplicate"])
+    expected, total, matched = orc.process_reads(tables, oparams, reads)
+    sp = H.build_specimens(primers, specimens_rows)
+    params = MatchParameters(dict(oparams.max_dist_primers), k_idx, flags["search_len"], not flags["disable_preorient"])
+    args = H.make_args(flags)
+    ops, n, m = process_sequences(H.records(reads), params, sp, args, H.prefilter_for(args))
+    assert (n, m) == (total, matched)
+    H.assert_ops_equal([H.op_to_dict(o) for o in ops], [H.op_to_dict(o) for o in expected], "seed %d" % seed)

@@ -1,0 +1,141 @@
+"""Randomised tables and reads (mixed barcode lengths, IUPAC-degenerate primers, shared primers,
+wildcards, every k from 0 to 5, N / IUPAC / lower-case symbols, reads shorter than the search
+window): CUDA per-thread routines (via the CPU kernel simulator) against the live oracle."""
+import random
+
+import pytest
+
+import helpers as H
+from oracle import pipeline as orc
+from specimux_b200.demultiplex import process_sequences
+from specimux_b200.models import MatchParameters
+from specimux_b200.seqio import reverse_complement
+
+IUPAC = {"R": "AG", "Y": "CT", "S": "CG", "W": "AT", "K": "GT", "M": "AC", "B": "CGT", "D": "AGT", "H": "ACT",
+         "V": "ACG", "N": "ACGT"}
+
+
+def rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def mutate(rng, s, rate):
+    out = []
+    for c in s:
+        u = rng.random()
+        if u < rate * 0.4:
+            out.append(rng.choice("ACGT"))
+        elif u < rate * 0.7:
+            out.append(rng.choice("ACGT") + c)
+        elif u < rate:
+            continue
+        else:
+            out.append(c)
+    return "".join(out)
+
+
+def instantiate(rng, s):
+    return "".join(rng.choice(IUPAC[c]) if c in IUPAC else c for c in s)
+
+
+def make_case(seed):
+    rng = random.Random(seed)
+    n_fwd, n_rev = rng.randint(1, 3), rng.randint(1, 3)
+    pools = ["P%d" % i for i in range(rng.randint(1, 2))]
+    primers = []
+    for i in range(n_fwd + n_rev):
+        seq = rand_seq(rng, rng.randint(16, 26))
+        if rng.random() < 0.5:
+            seq = "".join(rng.choice("RYNWM") if rng.random() < 0.12 else c for c in seq)
+        ppools = sorted(rng.sample(pools, rng.randint(1, len(pools))))
+        primers.append(("F%d" % i if i < n_fwd else "R%d" % i, seq, "forward" if i < n_fwd else "reverse", ppools))
+    for pool in pools:      # every pool needs both directions
+        for direction in ("forward", "reverse"):
+            if not any(pool in p[3] and p[2] == direction for p in primers):
+                idx = next(i for i, p in enumerate(primers) if p[2] == direction)
+                primers[idx] = (primers[idx][0], primers[idx][1], direction, sorted(set(primers[idx][3]) | {pool}))
+    lens = [rng.choice([9, 11, 13, 13, 13, 16]) for _ in range(2)]
+    mixed = rng.random() < 0.4
+    nb1, nb2 = rng.randint(2, 40), rng.randint(2, 70)
+
+    def barcodes(n, ln):
+        out = set()
+        while len(out) < n:
+            out.add(rand_seq(rng, rng.choice([ln, ln - 2, ln + 1]) if mixed else ln))
+        return sorted(out, key=lambda _: rng.random())
+    b1s, b2s = barcodes(nb1, lens[0]), barcodes(nb2, lens[1])
+    specimens = []
+    seen = set()
+    for i in range(rng.randint(3, 120)):
+        pool = rng.choice(pools)
+        fw = [p for p in primers if p[2] == "forward" and pool in p[3]]
+        rv = [p for p in primers if p[2] == "reverse" and pool in p[3]]
+        p1 = "*" if rng.random() < 0.15 else rng.choice(fw)[0]
+        p2 = "-" if rng.random() < 0.1 else rng.choice(rv)[0]
+        b1, b2 = rng.choice(b1s), rng.choice(b2s)
+        if (pool, b1, b2, p1, p2) in seen:
+            continue
+        seen.add((pool, b1, b2, p1, p2))
+        specimens.append(("S%03d" % i, pool, b1, p1, b2, p2))
+    k_idx = rng.choice([0, 1, 2, 3, 3, 4, 5])
+    k_idx = min(k_idx, min(len(b) for b in b1s + b2s) - 1)
+    L = rng.choice([40, 80, 80, 120, 200])
+    reads = []
+    by_name = {p[0]: p for p in primers}
+    for r in range(rng.randint(40, 90)):
+        sp = rng.choice(specimens)
+        fw = [p for p in primers if p[2] == "forward" and sp[1] in p[3]]
+        rv = [p for p in primers if p[2] == "reverse" and sp[1] in p[3]]
+        p1 = by_name[sp[3]] if sp[3] in by_name else rng.choice(fw)
+        p2 = by_name[sp[5]] if sp[5] in by_name else rng.choice(rv)
+        kind = rng.random()
+        insert = rand_seq(rng, rng.randint(0, 300))
+        left = rand_seq(rng, rng.randint(0, 25)) + sp[2] + instantiate(rng, p1[1])
+        right = reverse_complement(instantiate(rng, p2[1])) + reverse_complement(sp[4]) + rand_seq(rng, rng.randint(0, 25))
+        if kind < 0.1:
+            s = insert
+        elif kind < 0.2:
+            s = left + insert
+        elif kind < 0.3:
+            s = insert + right
+        else:
+            s = left + insert + right
+        s = mutate(rng, s, rng.choice([0.0, 0.05, 0.12]))
+        if rng.random() < 0.5:
+            s = reverse_complement(s)
+        u = rng.random()
+        if u < 0.1:
+            s = "".join("N" if rng.random() < 0.05 else c for c in s)
+        elif u < 0.15:
+            s = "".join(rng.choice("RYKMSWBDHV") if rng.random() < 0.05 else c for c in s)
+        elif u < 0.2:
+            s = s[:30].lower() + s[30:]
+        elif u < 0.3:
+            s = s[:rng.randint(0, L + 3)]
+        elif u < 0.35:
+            s = s[len(s) - min(len(s), rng.randint(0, L + 3)):]
+        reads.append(("r%04d" % r, s, "".join(chr(33 + rng.randint(2, 40)) for _ in s)))
+    flags = dict(search_len=L, trim=rng.choice(["barcodes", "primers", "tails", "none"]),
+                 dereplicate=rng.choice(["best", "none"]), disable_preorient=rng.random() < 0.3,
+                 disable_prefilter=rng.random() < 0.5)
+    return primers, specimens, reads, k_idx, flags
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_case(seed):
+    primers, specimens, reads, k_idx, flags = make_case(seed)
+    try:
+        tables = orc.Tables(primers, specimens)
+    except ValueError:
+        pytest.skip("generator produced an invalid table")
+    oparams = orc.setup_params(tables, index_edit_distance=k_idx, search_len=flags["search_len"],
+                               preorient=not flags["disable_preorient"], prefilter=not flags["disable_prefilter"],
+                               trim=flags["trim"], dereplicate=flags["dereplicate"])
+    expected, total, matched = orc.process_reads(tables, oparams, reads)
+    sp = H.build_specimens(primers, specimens)
+    params = MatchParameters(dict(oparams.max_dist_primers), k_idx, flags["search_len"], not flags["disable_preorient"])
+    args = H.make_args(flags)
+    ops, n, m = process_sequences(H.records(reads), params, sp, args, H.prefilter_for(args), None, 0,
+                                  _binding=H.hostsim_binding())
+    assert (n, m) == (total, matched)
+    H.assert_ops_equal([H.op_to_dict(o) for o in ops], [H.op_to_dict(o) for o in expected], "seed %d" % seed)
