@@ -112,6 +112,9 @@ typedef struct smx_params {
  * One batch of reads, packed by the host batching layer.
  *  packed2  : 2 bits per base, A=0 C=1 G=2 T=3, base i of read r at bit 2*(i%16) of word
  *             word_off[r] + i/16 (little-endian within the word); non-ACGT bases hold 0 there.
+ *  clip_len : 0 = whole reads are packed.  Otherwise every read longer than 2*clip_len is stored as
+ *             its first clip_len bases followed by its last clip_len bases (the only bases the
+ *             path ever looks at when clip_len >= search_len); `lengths` keeps the TRUE length.
  *  packed4  : optional exact side stream for reads containing any non-ACGT symbol (NULL if none).
  *             For such a read r, off4[r] != UINT64_MAX and packed4 holds the forward strand then the
  *             reverse-complement strand (Biopython ambiguous-DNA complement, U->A), each
@@ -127,6 +130,7 @@ typedef struct smx_batch {
     const uint32_t *packed4;    /* may be NULL */
     uint64_t packed4_words;
     const uint64_t *off4;       /* may be NULL when packed4 is NULL */
+    uint32_t clip_len;          /* see above; must be 0 or >= search_len */
 } smx_batch;
 
 /*
@@ -239,6 +243,9 @@ int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint3
  * Myers column step.  out[0] = LOP3-only, out[1] = IADD3-only, out[2] = 1:1 mix. */
 int smx_int_alu_peak(int device, double out_tops[3]);
 
+/* Evict the L2 cache (writes a buffer larger than L2) -- timing hygiene between benchmark steps. */
+int smx_flush_l2(smx_ctx *ctx);
+
 /* Pinned host memory for batch / result buffers (cudaHostAlloc / cudaFreeHost). */
 void *smx_host_alloc(uint64_t bytes);
 void smx_host_free(void *p);
@@ -247,8 +254,9 @@ void smx_host_free(void *p);
  * Replaces nothing in the reference (it works on Python strings); part of the batching layer.
  * Call with out arrays sized by smx_pack_bound. Returns the number of flagged (packed4) reads in
  * *n_flagged. */
-void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint64_t *packed2_words, uint64_t *packed4_words_max);
-int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
+void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
+                    uint64_t *packed2_words, uint64_t *packed4_words_max);
+int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
                    uint32_t *packed2, uint64_t *word_off, uint32_t *lengths,
                    uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged);
 

@@ -38,7 +38,7 @@ class SmxParams(C.Structure):
 class SmxBatch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("packed2", u32p), ("packed2_words", C.c_uint64),
                 ("word_off", u64p), ("lengths", u32p), ("packed4", u32p), ("packed4_words", C.c_uint64),
-                ("off4", u64p)]
+                ("off4", u64p), ("clip_len", C.c_uint32)]
 
 
 class SmxResults(C.Structure):
@@ -61,7 +61,7 @@ EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create"
            "smx_result_bound", "smx_match_batch", "smx_upload_batch", "smx_run_resident",
            "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
            "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads", "smx_int_alu_peak", "smx_host_alloc",
-           "smx_host_free"]
+           "smx_host_free", "smx_flush_l2"]
 
 
 class SmxError(RuntimeError):
@@ -96,14 +96,15 @@ def load():
         lib.smx_last_launch_count.argtypes = [C.c_void_p]
         lib.smx_last_work.argtypes = [C.c_void_p, u64p, u64p]
         lib.smx_pairwise_nw.argtypes = [C.c_int, C.c_char_p, u32p, C.c_uint32, i32p]
-        lib.smx_pack_bound.argtypes = [u64p, C.c_uint32, u64p, u64p]
+        lib.smx_pack_bound.argtypes = [u64p, C.c_uint32, C.c_uint32, u64p, u64p]
         lib.smx_pack_bound.restype = None
-        lib.smx_pack_reads.argtypes = [C.c_char_p, u64p, C.c_uint32, u32p, u64p, u32p, u32p, u64p, u64p, u32p]
+        lib.smx_pack_reads.argtypes = [C.c_char_p, u64p, C.c_uint32, C.c_uint32, u32p, u64p, u32p, u32p, u64p, u64p, u32p]
         lib.smx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         lib.smx_host_alloc.argtypes = [C.c_uint64]
         lib.smx_host_alloc.restype = C.c_void_p
         lib.smx_host_free.argtypes = [C.c_void_p]
         lib.smx_host_free.restype = None
+        lib.smx_flush_l2.argtypes = [C.c_void_p]
         if lib.smx_abi_version() != 1:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib
@@ -117,3 +118,39 @@ def check(rc):
 
 def ptr(arr, typ):
     return arr.ctypes.data_as(typ)
+
+
+class HostBuffer:
+    """numpy view over pinned host memory (cudaHostAlloc through the library); falls back to ordinary
+    pageable memory when no GPU driver is present (packing still works on a CPU-only box)."""
+
+    def __init__(self, count, dtype):
+        dtype = np.dtype(dtype)
+        self.nbytes = max(1, int(count) * dtype.itemsize)
+        self._ptr = None
+        try:
+            p = load().smx_host_alloc(self.nbytes)
+        except Exception:
+            p = None
+        if p:
+            self._ptr = p
+            raw = (C.c_char * self.nbytes).from_address(p)
+            self.array = np.frombuffer(raw, dtype=dtype, count=int(count))
+        else:
+            self.array = np.empty(int(count), dtype=dtype)
+
+    @property
+    def pinned(self):
+        return self._ptr is not None
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            load().smx_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

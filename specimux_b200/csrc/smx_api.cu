@@ -199,6 +199,8 @@ uint64_t smx_result_bound(const smx_ctx *c, uint32_t n_reads) {
 int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     if (!c || !in) return fail(SMX_ERR_ARG, "smx_upload_batch: null argument");
     if (in->n_reads == 0) return fail(SMX_ERR_ARG, "smx_upload_batch: empty batch");
+    if (in->clip_len && (int)in->clip_len < c->t.L)
+        return fail(SMX_ERR_ARG, "smx_upload_batch: clip_len %u is below search_len %d", in->clip_len, c->t.L);
     if ((in->packed4 == nullptr) != (in->off4 == nullptr) && in->packed4_words)
         return fail(SMX_ERR_ARG, "smx_upload_batch: packed4 and off4 must be given together");
     CU(cudaSetDevice(c->device));
@@ -225,7 +227,7 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
         CU(cudaMemcpyAsync(c->off4.p, in->off4, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     }
     Batch &b = c->b;
-    b.n_reads = n; b.n_pad = n_pad;
+    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len;
     b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
     b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
     b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.orient_hit = c->orient_hit.p;
@@ -482,6 +484,16 @@ int smx_int_alu_peak(int device, double out_tops[3]) {
     return SMX_OK;
 }
 
+int smx_flush_l2(smx_ctx *c) {
+    if (!c) return fail(SMX_ERR_ARG, "smx_flush_l2: null context");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = 512ull << 20;
+    CU(c->big_scratch.ensure(bytes));
+    CU(cudaMemsetAsync(c->big_scratch.p, 0x5a, bytes, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SMX_OK;
+}
+
 void *smx_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -499,10 +511,12 @@ void smx_host_free(void *p) {
 // ------------------------------------------------------------------------------------------------
 // Host-side packer (batching layer; no matching happens here).
 
-void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint64_t *packed2_words, uint64_t *packed4_words_max) {
+void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
+                    uint64_t *packed2_words, uint64_t *packed4_words_max) {
     uint64_t w2 = 0, w4 = 0;
     for (uint32_t r = 0; r < n_reads; ++r) {
         uint64_t len = seq_off[r + 1] - seq_off[r];
+        if (clip_len && len > 2ull * clip_len) len = 2ull * clip_len;
         w2 += (len + 15) / 16;
         w4 += 2 * ((len + 7) / 8);
     }
@@ -510,7 +524,7 @@ void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint64_t *packed2
     if (packed4_words_max) *packed4_words_max = w4 + 1;
 }
 
-int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
+int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
                    uint32_t *packed2, uint64_t *word_off, uint32_t *lengths,
                    uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged) {
     if (!bases || !seq_off || !packed2 || !word_off || !lengths)
@@ -519,17 +533,22 @@ int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
     uint32_t flagged = 0;
     for (uint32_t r = 0; r < n_reads; ++r) {
         const unsigned char *s = (const unsigned char *)bases + seq_off[r];
-        uint64_t len = seq_off[r + 1] - seq_off[r];
-        if (len > 0xFFFFFFFFull) return fail(SMX_ERR_ARG, "smx_pack_reads: read %u too long", r);
+        const uint64_t len = seq_off[r + 1] - seq_off[r];
+        if (len > 0x7FFFFFFFull) return fail(SMX_ERR_ARG, "smx_pack_reads: read %u too long", r);
+        const bool clipped = clip_len && len > 2ull * clip_len;
+        const uint64_t slen = clipped ? 2ull * clip_len : len;     // stored bases
+        const uint64_t skip = len - slen;                          // bases dropped from the middle
+        // stored index i -> source index
+        auto src = [&](uint64_t i) { return (clipped && i >= clip_len) ? i + skip : i; };
         word_off[r] = w2;
         lengths[r] = (uint32_t)len;
         bool exotic = false;
-        uint64_t nw = (len + 15) / 16;
+        const uint64_t nw = (slen + 15) / 16;
         for (uint64_t w = 0; w < nw; ++w) {
             uint32_t v = 0;
-            uint64_t lim = std::min<uint64_t>(16, len - w * 16);
+            uint64_t lim = std::min<uint64_t>(16, slen - w * 16);
             for (uint64_t i = 0; i < lim; ++i) {
-                int c = read_code(s[w * 16 + i]);
+                int c = read_code(s[src(w * 16 + i)]);
                 if (c > 3) { exotic = true; c = 0; }
                 v |= (uint32_t)c << (2 * i);
             }
@@ -540,12 +559,15 @@ int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
         if (exotic) {
             if (!packed4 || !off4) return fail(SMX_ERR_ARG, "smx_pack_reads: read %u needs the packed4 stream", r);
             off4[r] = w4;
-            uint64_t n4 = (len + 7) / 8;
+            const uint64_t n4 = (slen + 7) / 8;
             for (uint64_t w = 0; w < 2 * n4; ++w) packed4[w4 + w] = 0;
-            for (uint64_t i = 0; i < len; ++i) {
-                packed4[w4 + i / 8] |= (uint32_t)read_code(s[i]) << (4 * (i % 8));
-                uint64_t x = len - 1 - i;     // position in the reverse-complement strand
-                packed4[w4 + n4 + x / 8] |= (uint32_t)read_code_rc(s[i]) << (4 * (x % 8));
+            for (uint64_t i = 0; i < slen; ++i) {
+                unsigned char ch = s[src(i)];
+                packed4[w4 + i / 8] |= (uint32_t)read_code(ch) << (4 * (i % 8));
+                // the reverse-complement strand is clipped the same way: its stored index of the
+                // base at source position p is the stored index of (len-1-p) mirrored
+                uint64_t x = slen - 1 - i;
+                packed4[w4 + n4 + x / 8] |= (uint32_t)read_code_rc(ch) << (4 * (x % 8));
             }
             w4 += 2 * n4;
             ++flagged;

@@ -189,6 +189,7 @@ struct Batch {
     const u32 *lengths;
     const u32 *packed4;
     const u64 *off4;         // nullptr when no read is flagged
+    u32 clip;                // 0, or reads longer than 2*clip are stored as head clip + tail clip bases
     u32 *win;                // staged 4-bit windows [(strand*wpw + w) * n_pad + read]
     // level-1 results
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
@@ -219,14 +220,25 @@ SMX_HD bool read_is_flagged(const Batch &b, u32 r) {
     return b.off4 != nullptr && b.off4[r] != ~0ull;
 }
 
+// Stored position of base x of an n-long strand under clipping (only x < clip or x >= n - clip
+// are ever requested when clip >= search_len).
+SMX_HD int stored_pos(const Batch &b, int x, int n) {
+    if (b.clip == 0 || n <= 2 * (int)b.clip) return x;
+    return x < (int)b.clip ? x : x - (n - 2 * (int)b.clip);
+}
+SMX_HD int stored_len(const Batch &b, int n) {
+    return (b.clip == 0 || n <= 2 * (int)b.clip) ? n : 2 * (int)b.clip;
+}
+
 // Symbol x of strand `strand` of read r, straight from the packed streams.
 SMX_HD int sym_at(const Batch &b, u32 r, int strand, int x, int n) {
     if (read_is_flagged(b, r)) {
-        u64 base = b.off4[r] + (strand ? (u64)((n + 7) >> 3) : 0);
-        u32 w = b.packed4[base + (u64)(x >> 3)];
-        return (int)((w >> (4 * (x & 7))) & 15);
+        u64 base = b.off4[r] + (strand ? (u64)((stored_len(b, n) + 7) >> 3) : 0);
+        int xs = stored_pos(b, x, n);
+        u32 w = b.packed4[base + (u64)(xs >> 3)];
+        return (int)((w >> (4 * (xs & 7))) & 15);
     }
-    int i = strand ? n - 1 - x : x;
+    int i = stored_pos(b, strand ? n - 1 - x : x, n);
     u32 w = b.packed2[b.word_off[r] + (u64)(i >> 4)];
     int c = (int)((w >> (2 * (i & 15))) & 3);
     return strand ? 3 - c : c;

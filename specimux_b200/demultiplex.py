@@ -105,8 +105,8 @@ def process_sequences(seq_records: List, parameters: MatchParameters, specimens,
         bases.append(b)
         quals.append(q)
         ids.append(rec.id)
-    batch = PackedBatch(bases, binding=None)
-    result = matcher.match(batch)
+    batch = PackedBatch(bases, clip=parameters.search_len)
+    result = matcher.match(batch, reuse=True)
     trace_ids = None
     if trace_logger is not None:
         from .trace import emit_batch_trace

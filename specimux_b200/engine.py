@@ -12,35 +12,37 @@ from . import _lib
 
 
 class PackedBatch:
-    """Reads in the smx_batch encoding (2-bit stream + optional exact 4-bit side stream)."""
+    """Reads in the smx_batch encoding (2-bit stream + optional exact 4-bit side stream), held in
+    pinned host memory.  `clip` (0 or >= search_len) stores only the first/last `clip` bases of
+    longer reads -- the only bases the path looks at -- which cuts packing work and H2D bytes."""
 
-    def __init__(self, bases: Sequence[str], binding=None):
-        lib = (binding or _lib.load())
+    def __init__(self, bases: Sequence[str], clip: int = 0):
         n = len(bases)
         lens = np.fromiter((len(s) for s in bases), dtype=np.uint64, count=n)
         seq_off = np.zeros(n + 1, dtype=np.uint64)
         np.cumsum(lens, out=seq_off[1:])
         blob = "".join(bases).encode("latin-1", "replace")
-        self._init_from_blob(lib, blob, seq_off)
+        self._init_from_blob(blob, seq_off, clip)
 
     @classmethod
-    def from_blob(cls, blob: bytes, seq_off: np.ndarray, binding=None):
+    def from_blob(cls, blob: bytes, seq_off: np.ndarray, clip: int = 0):
         self = cls.__new__(cls)
-        self._init_from_blob(binding or _lib.load(), blob, np.ascontiguousarray(seq_off, dtype=np.uint64))
+        self._init_from_blob(blob, np.ascontiguousarray(seq_off, dtype=np.uint64), clip)
         return self
 
-    def _init_from_blob(self, lib, blob, seq_off):
+    def _init_from_blob(self, blob, seq_off, clip):
+        lib = _lib.load()
         n = len(seq_off) - 1
         w2, w4 = C.c_uint64(0), C.c_uint64(0)
-        lib.smx_pack_bound(_lib.ptr(seq_off, _lib.u64p), n, C.byref(w2), C.byref(w4))
+        lib.smx_pack_bound(_lib.ptr(seq_off, _lib.u64p), n, clip, C.byref(w2), C.byref(w4))
         self.n_reads = n
-        self.packed2 = np.zeros(int(w2.value), dtype=np.uint32)
-        self.word_off = np.zeros(max(n, 1), dtype=np.uint64)
-        self.lengths = np.zeros(max(n, 1), dtype=np.uint32)
+        self.clip = int(clip)
+        self._bufs = [_lib.HostBuffer(int(w2.value), np.uint32), _lib.HostBuffer(max(n, 1), np.uint64),
+                      _lib.HostBuffer(max(n, 1), np.uint32), _lib.HostBuffer(max(n, 1), np.uint64)]
+        self.packed2, self.word_off, self.lengths, self.off4 = (hb.array for hb in self._bufs)
         packed4 = np.zeros(int(w4.value), dtype=np.uint32)
-        self.off4 = np.zeros(max(n, 1), dtype=np.uint64)
         used4, flagged = C.c_uint64(0), C.c_uint32(0)
-        _lib.check(lib.smx_pack_reads(blob, _lib.ptr(seq_off, _lib.u64p), n, _lib.ptr(self.packed2, _lib.u32p),
+        _lib.check(lib.smx_pack_reads(blob, _lib.ptr(seq_off, _lib.u64p), n, clip, _lib.ptr(self.packed2, _lib.u32p),
                                       _lib.ptr(self.word_off, _lib.u64p), _lib.ptr(self.lengths, _lib.u32p),
                                       _lib.ptr(packed4, _lib.u32p), _lib.ptr(self.off4, _lib.u64p),
                                       C.byref(used4), C.byref(flagged)))
@@ -52,6 +54,7 @@ class PackedBatch:
     def c_batch(self) -> "_lib.SmxBatch":
         b = _lib.SmxBatch()
         b.n_reads = self.n_reads
+        b.clip_len = self.clip
         b.packed2 = _lib.ptr(self.packed2, _lib.u32p)
         b.packed2_words = len(self.packed2)
         b.word_off = _lib.ptr(self.word_off, _lib.u64p)
@@ -109,12 +112,22 @@ class Matcher:
             pass
 
     # -- results allocation ---------------------------------------------------------------
-    def _alloc_results(self, n, detail, cap=None):
+    def _alloc_results(self, n, detail, cap=None, reuse=False):
         t = self.tables
-        cap = int(cap if cap is not None else 2 * n + 1024)
+        cap = int(cap if cap is not None else n + n // 8 + 1024)
         res = _lib.SmxResults()
-        rec_offset = np.zeros(n + 1, dtype=np.uint32)
-        records = np.zeros(cap, dtype=_lib.RECORD_DTYPE)
+        if reuse:
+            # pinned pool reused across calls: the previous call's result arrays are overwritten
+            pool = self.__dict__.setdefault("_result_pool", {})
+            if pool.get("n", -1) < n + 1:
+                pool["n"], pool["off"] = n + 1, _lib.HostBuffer(n + 1, np.uint32)
+            if pool.get("cap", -1) < cap:
+                pool["cap"], pool["rec"] = cap, _lib.HostBuffer(cap, _lib.RECORD_DTYPE)
+            rec_offset = pool["off"].array[:n + 1]
+            records = pool["rec"].array[:cap]
+        else:
+            rec_offset = np.empty(n + 1, dtype=np.uint32)
+            records = np.empty(cap, dtype=_lib.RECORD_DTYPE)
         res.rec_offset = _lib.ptr(rec_offset, _lib.u32p)
         res.records = records.ctypes.data
         res.records_cap = cap
@@ -132,11 +145,12 @@ class Matcher:
         return BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh)
 
     # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
-    def match(self, batch: PackedBatch, detail: bool = False) -> BatchResult:
+    def match(self, batch: PackedBatch, detail: bool = False, reuse: bool = False) -> BatchResult:
+        """`reuse=True` returns views into a pinned pool that the next reuse=True call overwrites."""
         cb = batch.c_batch()
         cap = None
         while True:
-            res, rec_offset, records, ph, em, bh = self._alloc_results(batch.n_reads, detail, cap)
+            res, rec_offset, records, ph, em, bh = self._alloc_results(batch.n_reads, detail, cap, reuse)
             if self._binding is not None:
                 rc = self._binding.hostsim_match_batch(self.tables.tables_ref(), self.tables.params_ref(),
                                                        C.byref(cb), C.byref(res))
@@ -162,16 +176,19 @@ class Matcher:
     def run_resident(self):
         _lib.check(self._lib.smx_run_resident(self._ctx))
 
-    def download(self, detail: bool = False) -> BatchResult:
+    def download(self, detail: bool = False, reuse: bool = False) -> BatchResult:
         cap = None
         while True:
-            res, rec_offset, records, ph, em, bh = self._alloc_results(self._resident_n, detail, cap)
+            res, rec_offset, records, ph, em, bh = self._alloc_results(self._resident_n, detail, cap, reuse)
             rc = self._lib.smx_download_results(self._ctx, C.byref(res))
             if rc == _lib.SMX_ERR_CAPACITY:
                 cap = int(res.n_records)
                 continue
             _lib.check(rc)
             return self._finish(res, rec_offset, records, ph, em, bh)
+
+    def flush_l2(self):
+        _lib.check(self._lib.smx_flush_l2(self._ctx))
 
     def last_timing(self):
         total = C.c_float(0)

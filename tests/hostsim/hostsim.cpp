@@ -32,7 +32,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     unsigned long long counters[8] = {0};
     Batch b;
     memset(&b, 0, sizeof(b));
-    b.n_reads = n; b.n_pad = n_pad;
+    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len;
     b.packed2 = in->packed2; b.word_off = in->word_off; b.lengths = in->lengths;
     bool flagged = in->packed4 && in->off4 && in->packed4_words;
     b.packed4 = flagged ? in->packed4 : nullptr; b.off4 = flagged ? in->off4 : nullptr;
