@@ -78,7 +78,10 @@ struct smx_ctx {
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
     DevBuf<smx_barcode_hit> bh_list;
-    DevBuf<u32> slot_list, slot_count, big_list;
+    DevBuf<u32> slot_count, ent_base, ent_read, rec_extra, big_list;
+    DevBuf<unsigned short> ent_pos;
+    DevBuf<smx_record> rec_stage, rec_pool;
+    u32 e_cap = 0, pool_cap = 0;
     DevBuf<unsigned char> big_scratch;
     DevBuf<smx_record> records;
     DevBuf<unsigned long long> counters;   // 4 work counters + matched + (u32) overflow + (u32) total
@@ -88,6 +91,23 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
     int launches = 0;
 };
+
+static cudaError_t ensure_entry_buffers(smx_ctx *c) {
+    const Tables &t = c->t;
+    cudaError_t e;
+    if ((e = c->ent_read.ensure((size_t)2 * t.n_primers * c->e_cap)) != cudaSuccess) return e;
+    if ((e = c->ent_pos.ensure((size_t)2 * t.n_primers * c->e_cap)) != cudaSuccess) return e;
+    if ((e = c->bh_count.ensure((size_t)2 * t.n_bwords * c->e_cap + 1)) != cudaSuccess) return e;
+    if ((e = c->bh_list.ensure((size_t)2 * t.n_bwords * t.hit_cap * c->e_cap + 1)) != cudaSuccess) return e;
+    return c->rec_pool.ensure(c->pool_cap);
+}
+
+static void bind_entry_buffers(smx_ctx *c) {
+    Batch &b = c->b;
+    b.e_cap = c->e_cap; b.pool_cap = c->pool_cap;
+    b.ent_read = c->ent_read.p; b.ent_pos = c->ent_pos.p; b.bh_count = c->bh_count.p; b.bh_list = c->bh_list.p;
+    b.rec_pool = c->rec_pool.p;
+}
 
 // rec_count -> rec_offset (exclusive scan), flag counters, then one D2H of the 8 counters.
 static cudaError_t scan_and_count(smx_ctx *c, int &launches, unsigned long long host_counters[8]) {
@@ -123,7 +143,8 @@ void smx_destroy(smx_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bw_len.release(); c->bw_primer.release(); c->bw_row.release();
     c->bw_valid.release(); c->beq.release(); c->bw_list.release(); c->bh_count.release(); c->bh_list.release();
-    c->slot_list.release(); c->slot_count.release(); c->big_list.release(); c->big_scratch.release();
+    c->slot_count.release(); c->ent_base.release(); c->ent_read.release(); c->ent_pos.release();
+    c->rec_extra.release(); c->rec_stage.release(); c->rec_pool.release(); c->big_list.release(); c->big_scratch.release();
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release();
@@ -214,9 +235,11 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     CU(c->phit.ensure((size_t)2 * nP * n_pad));
     CU(c->endmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(c->orient_hit.ensure((size_t)2 * nP * n_pad));
-    CU(c->slot_list.ensure((size_t)2 * nP * n_pad)); CU(c->slot_count.ensure((size_t)2 * nP));
-    CU(c->bh_count.ensure((size_t)2 * t.n_bwords * n_pad + 1));
-    CU(c->bh_list.ensure((size_t)2 * t.n_bwords * t.hit_cap * n_pad + 1));
+    CU(c->slot_count.ensure((size_t)2 * nP)); CU(c->ent_base.ensure((size_t)2 * nP * n_pad));
+    if (c->e_cap < n_pad) c->e_cap = n_pad;
+    if (c->pool_cap < n_pad / 8 + 1024) c->pool_cap = n_pad / 8 + 1024;
+    CU(ensure_entry_buffers(c));
+    CU(c->rec_stage.ensure(n_pad)); CU(c->rec_extra.ensure(n_pad)); CU(c->rec_pool.ensure(c->pool_cap));
     CU(c->rec_count.ensure(n)); CU(c->rec_offset.ensure((size_t)n + 1)); CU(c->read_flags.ensure(n));
     CU(c->block_sums.ensure((n + kScanBlock - 1) / kScanBlock + 1));
     CU(cudaMemcpyAsync(c->packed2.p, in->packed2, in->packed2_words * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
@@ -231,7 +254,9 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
     b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
     b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.orient_hit = c->orient_hit.p;
-    b.slot_list = c->slot_list.p; b.slot_count = c->slot_count.p; b.bh_count = c->bh_count.p; b.bh_list = c->bh_list.p;
+    b.slot_count = c->slot_count.p; b.ent_base = c->ent_base.p;
+    b.rec_stage = c->rec_stage.p; b.rec_extra = c->rec_extra.p;
+    bind_entry_buffers(c);
     b.rec_count = c->rec_count.p; b.rec_offset = c->rec_offset.p;
     b.records = nullptr; b.read_flags = c->read_flags.p; b.counters = c->counters.p;
     CU(cudaStreamSynchronize(c->stream));
@@ -251,53 +276,80 @@ int smx_run_resident(smx_ctx *c) {
     int launches = 0;
     CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(c->slot_count.p, 0, (size_t)2 * nP * sizeof(u32), st));
     CU(cudaEventRecord(c->ev[0], st));
     {   // stage 0
         dim3 grid((n + 127) / 128, 2 * t.wpw);
         k_stage_windows<<<grid, 128, 0, st>>>(b);
         ++launches;
     }
-    CU(cudaEventRecord(c->ev[1], st));
-    {   // stage 1
-        dim3 grid((n + 127) / 128, 2 * nP);
-        if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(b);
-        else k_primer_search<u32><<<grid, 128, 0, st>>>(b);
-        ++launches;
-    }
-    CU(cudaEventRecord(c->ev[2], st));
     const unsigned blocks = (n + 127) / 128;
     unsigned long long host_counters[8];
+    std::vector<u32> slot_counts((size_t)2 * nP);
+    int from = 1;                      // stage to (re)start from
     for (;;) {
-        if (t.n_bwords) {   // stage 2
-            dim3 grid(blocks, 2 * t.n_bwords);
-            switch (t.k_idx) {
-#define SMX_K2(KK) case KK: k_barcode_bitsliced<KK><<<grid, 128, 0, st>>>(b); break;
-                SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
-#undef SMX_K2
-                default: return fail(SMX_ERR_INTERNAL, "unsupported k_idx");
-            }
+        if (from <= 1) {   // stage 1
+            CU(cudaMemsetAsync(c->slot_count.p, 0, (size_t)2 * nP * sizeof(u32), st));
+            CU(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned long long), st));
+            CU(cudaEventRecord(c->ev[1], st));
+            dim3 grid(blocks, 2 * nP);
+            if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(b);
+            else k_primer_search<u32><<<grid, 128, 0, st>>>(b);
             ++launches;
         }
+        if (from <= 2) {   // stage 2
+            CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(unsigned long long), st));
+            CU(cudaEventRecord(c->ev[2], st));
+            if (t.n_bwords) {
+                dim3 grid((b.e_cap + 127) / 128, 2 * t.n_bwords);
+                switch (t.k_idx) {
+#define SMX_K2(KK) case KK: k_barcode_bitsliced<KK><<<grid, 128, 0, st>>>(b); break;
+                    SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
+#undef SMX_K2
+                    default: return fail(SMX_ERR_INTERNAL, "unsupported k_idx");
+                }
+                ++launches;
+            }
+        }
+        // stage 3: single-pass selection, scan
+        CU(cudaMemsetAsync(c->counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
         CU(cudaEventRecord(c->ev[3], st));
-        // stage 3: count, scan
-        if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b, 0); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b, 0);
+        if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b);
         ++launches;
+        CU(cudaMemcpyAsync(slot_counts.data(), c->slot_count.p, slot_counts.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
         CU(scan_and_count(c, launches, host_counters));
-        if (host_counters[7] == 0) break;
-        // a hit sub-list overflowed: second GPU pass with a larger capacity (never a CPU fallback)
-        if (c->t.hit_cap >= kMaxWordHits) return fail(SMX_ERR_INTERNAL, "hit list overflow at maximum capacity");
-        c->t.hit_cap = std::min(kMaxWordHits, c->t.hit_cap * 4);
-        CU(c->bh_list.ensure((size_t)2 * t.n_bwords * c->t.hit_cap * b.n_pad + 1));
-        b.bh_list = c->bh_list.p;
-        CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(c->counters.p + 3, 0, 5 * sizeof(unsigned long long), st));
+        // capacity checks: every overflow is resolved by a second GPU pass with larger buffers
+        u32 max_entries = 0;
+        for (u32 v : slot_counts) max_entries = std::max(max_entries, v);
+        if (max_entries > c->e_cap) {
+            c->e_cap = (max_entries + 127u) & ~127u;
+            CU(ensure_entry_buffers(c)); bind_entry_buffers(c);
+            from = 1;
+            continue;
+        }
+        if (host_counters[7]) {
+            if (c->t.hit_cap >= kMaxWordHits) return fail(SMX_ERR_INTERNAL, "hit list overflow at maximum capacity");
+            c->t.hit_cap = std::min(kMaxWordHits, c->t.hit_cap * 4);
+            CU(ensure_entry_buffers(c)); bind_entry_buffers(c);
+            CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
+            from = 2;
+            continue;
+        }
+        u32 pool_used = (u32)(host_counters[6] >> 32);
+        if (pool_used > c->pool_cap) {
+            c->pool_cap = pool_used + 1024;
+            CU(ensure_entry_buffers(c)); bind_entry_buffers(c);
+            from = 3;
+            continue;
+        }
+        break;
     }
     std::vector<u32> big_list;
     if ((u32)host_counters[5]) {
-        // some reads overflowed the thread-local group storage: second GPU pass for those reads only,
-        // on kBigGroups-entry global scratch
+        // some reads overflowed the thread-local group storage (or emit many records): second GPU
+        // pass for those reads only, on kBigGroups-entry global scratch
         std::vector<unsigned char> flags(n);
         CU(cudaMemcpy(flags.data(), b.read_flags, n, cudaMemcpyDeviceToHost));
         for (u32 r = 0; r < n; ++r) if (flags[r] & 2) big_list.push_back(r);
@@ -310,7 +362,8 @@ int smx_run_resident(smx_ctx *c) {
             k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(b, c->big_list.p + off, cnt, c->big_scratch.p, 0);
             ++launches;
         }
-        CU(cudaMemsetAsync(c->counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(c->counters.p + 4, 0, 2 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(c->counters.p + 6, 0, sizeof(u32), st));
         CU(scan_and_count(c, launches, host_counters));
         if ((u32)(host_counters[5] >> 32))
             return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceed %d dereplication groups",
@@ -320,7 +373,7 @@ int smx_run_resident(smx_ctx *c) {
         u64 total = (u32)host_counters[6];
         CU(c->records.ensure(total + 1));
         b.records = c->records.p;
-        if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b, 1); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b, 1);
+        k_compact_records<<<(n + 255) / 256, 256, 0, st>>>(b);
         ++launches;
         const size_t chunk = 512;
         for (size_t off = 0; off < big_list.size(); off += chunk) {
@@ -369,12 +422,15 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
                              (size_t)n * sizeof(u32), (size_t)2 * t.n_primers * t.mw, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (out->barcode_hits && t.total_bslots) {
-        // expand the compact per-bword hit lists into the dense [barcode slot][read] detail layout
+        // expand the compact per-(entry, bword) hit lists into the dense [barcode slot][read] detail
+        // layout, merging a barcode's hits over the primer end locations (strictly smaller wins)
         std::vector<smx_primer_hit> ph((size_t)2 * t.n_primers * b.n_pad);
-        std::vector<unsigned char> cnt((size_t)2 * t.n_bwords * b.n_pad);
-        std::vector<smx_barcode_hit> lst((size_t)2 * t.n_bwords * t.hit_cap * b.n_pad);
+        std::vector<u32> ebase((size_t)2 * t.n_primers * b.n_pad);
+        std::vector<unsigned char> cnt((size_t)2 * t.n_bwords * b.e_cap);
+        std::vector<smx_barcode_hit> lst((size_t)2 * t.n_bwords * t.hit_cap * b.e_cap);
         std::vector<unsigned char> bwp(t.n_bwords);
         CU(cudaMemcpy(ph.data(), b.phit, ph.size() * sizeof(smx_primer_hit), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(ebase.data(), b.ent_base, ebase.size() * sizeof(u32), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(cnt.data(), b.bh_count, cnt.size(), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(lst.data(), b.bh_list, lst.size() * sizeof(smx_barcode_hit), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(bwp.data(), t.bw_primer, bwp.size(), cudaMemcpyDeviceToHost));
@@ -387,11 +443,16 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
                 u32 slot = (u32)(sd * t.n_primers + p);
                 u64 gslot = (u64)sd * t.n_bwords + g;
                 for (u32 r = 0; r < n; ++r) {
-                    if (ph[(size_t)slot * b.n_pad + r].distance < 0) continue;
-                    int k = std::min<int>(cnt[gslot * b.n_pad + r], t.hit_cap);
-                    for (int e = 0; e < k; ++e) {
-                        const smx_barcode_hit &h = lst[(gslot * t.hit_cap + e) * b.n_pad + r];
-                        out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r] = h;
+                    const smx_primer_hit &h0 = ph[(size_t)slot * b.n_pad + r];
+                    if (h0.distance < 0) continue;
+                    for (u32 l = 0; l < h0.n_locations; ++l) {
+                        u64 e = (u64)ebase[(size_t)slot * b.n_pad + r] + l;
+                        int k = std::min<int>(cnt[gslot * b.e_cap + e], t.hit_cap);
+                        for (int x = 0; x < k; ++x) {
+                            const smx_barcode_hit &h = lst[(gslot * t.hit_cap + x) * b.e_cap + e];
+                            smx_barcode_hit &dst = out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r];
+                            if (dst.distance < 0 || h.distance < dst.distance) dst = h;
+                        }
                     }
                 }
             }

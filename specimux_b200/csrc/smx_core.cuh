@@ -195,10 +195,21 @@ struct Batch {
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
     u32 *endmask;            // [(slot*mw + w) * n_pad + read]
     unsigned char *orient_hit;   // [slot * n_pad + read]  explicit orientation test (irregular reads)
-    u32 *slot_list;          // [slot * n_pad + i]  reads whose (strand, primer) slot matched (unordered)
-    u32 *slot_count;         // [slot]
-    unsigned char *bh_count; // [gslot * n_pad + read], gslot = strand * n_bwords + bword; may exceed hit_cap
-    smx_barcode_hit *bh_list;    // [(gslot * hit_cap + e) * n_pad + read], ascending barcode position
+    // One work entry per (matched slot, equal-best primer end location); a read's entries are
+    // consecutive and in ascending end order.  e_cap entries are allocated per slot.
+    u32 e_cap;
+    u32 *slot_count;         // [slot] entries appended (may exceed e_cap -> the library re-runs larger)
+    u32 *ent_base;           // [slot * n_pad + read] first entry of the read in this slot
+    u32 *ent_read;           // [slot * e_cap + e]
+    unsigned short *ent_pos; // [slot * e_cap + e] staged position of the primer end
+    // Barcode hits of entry e for bword g, gslot = strand * n_bwords + g:
+    unsigned char *bh_count; // [gslot * e_cap + e]; may exceed hit_cap (-> re-run with a larger cap)
+    smx_barcode_hit *bh_list;    // [(gslot * hit_cap + h) * e_cap + e], ascending barcode position
+    // single-pass selection: first record of every read + pool for the (rare) further records
+    smx_record *rec_stage;   // [read]
+    smx_record *rec_pool;    // extra records, contiguous per read
+    u32 *rec_extra;          // [read] index of the read's 2nd record in rec_pool
+    u32 pool_cap;
     // level-2 results
     u32 *rec_count;          // per read
     u32 *rec_offset;         // exclusive scan (n_reads + 1)
@@ -335,21 +346,35 @@ struct SelectCtx {
 
 SMX_HD u32 slot_index(const Tables &t, int strand, int primer) { return (u32)(strand * t.n_primers + primer); }
 
-// Barcode hits of one (strand, primer) slot live in per-bword sub-lists (written by stage 2, each
-// ascending in barcode position).  next_hit() walks the union in ascending position.
+// Barcode hits of one (strand, primer) slot live in per-(end location, bword) sub-lists written by
+// stage 2, each ascending in barcode position.  next_hit() walks their union in ascending
+// position; for a barcode found at several primer end locations the strictly smallest distance
+// wins and ties keep the earliest location (demultiplex.py:786-812).
 SMX_HD bool next_hit(const SelectCtx &c, int strand, int primer, int after_j, smx_barcode_hit &out) {
     const Tables &t = *c.t;
+    const Batch &b = *c.b;
+    const u32 slot = (u32)(strand * t.n_primers + primer);
+    const u64 hidx = (u64)slot * b.n_pad + c.read;
+    const u32 e0 = b.ent_base[hidx];
+    u32 nloc = b.phit[hidx].n_locations;
+    if (e0 >= b.e_cap) return false;
+    if (e0 + nloc > b.e_cap) nloc = b.e_cap - e0;
     bool found = false;
-    for (u32 g = t.bw_off[primer]; g < t.bw_off[primer + 1]; ++g) {
-        u64 gslot = (u64)strand * t.n_bwords + g;
-        int cnt = c.b->bh_count[gslot * c.b->n_pad + c.read];
-        if (cnt > t.hit_cap) cnt = t.hit_cap;
-        for (int e = 0; e < cnt; ++e) {
-            const smx_barcode_hit &h = c.b->bh_list[(gslot * t.hit_cap + e) * c.b->n_pad + c.read];
-            int j = (int)h.barcode;
-            if (j <= after_j) continue;
-            if (!found || j < (int)out.barcode) { out = h; found = true; }
-            break;      // sub-list is ascending: the first j > after_j is this list's candidate
+    for (u32 l = 0; l < nloc; ++l) {
+        const u64 e = (u64)e0 + l;
+        for (u32 g = t.bw_off[primer]; g < t.bw_off[primer + 1]; ++g) {
+            const u64 gslot = (u64)strand * t.n_bwords + g;
+            int cnt = b.bh_count[gslot * b.e_cap + e];
+            if (cnt > t.hit_cap) cnt = t.hit_cap;
+            for (int x = 0; x < cnt; ++x) {
+                const smx_barcode_hit &h = b.bh_list[(gslot * t.hit_cap + x) * b.e_cap + e];
+                int j = (int)h.barcode;
+                if (j <= after_j) continue;
+                if (!found || j < (int)out.barcode || (j == (int)out.barcode && h.distance < out.distance)) {
+                    out = h; found = true;
+                }
+                break;      // sub-list is ascending: the first j > after_j is this list's candidate
+            }
         }
     }
     return found;
@@ -405,6 +430,7 @@ SMX_HD int cand_score(const EndInfo &a, const EndInfo &b) {   // demultiplex.py:
 // Emits records for one read.  `emit` = nullptr counts only.  Returns the number of records.
 struct Emitter {
     smx_record *out;        // may be nullptr (count pass)
+    u32 cap;                // records `out` can hold; further records are only counted
     u32 count;
     bool full;
 };
@@ -506,7 +532,7 @@ SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &ov
         }
         if (s >= e) empty = true;                   // demultiplex.py:47
     }
-    if (em.out) {
+    if (em.out && em.count < em.cap) {
         smx_record &r = em.out[em.count];
         r.read = c.read;
         r.reverse = (unsigned char)cd.rc;
@@ -584,10 +610,11 @@ struct SelectStore {
 };
 
 // Whole per-read selection.  ends: cache of 2*n_primers EndInfo (index strand*n_primers+primer).
-SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, unsigned char &flags) {
+SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, u32 out_cap,
+                       unsigned char &flags) {
     const Tables &t = *c.t;
     const Batch &b = *c.b;
-    Emitter em; em.out = out; em.count = 0; em.full = false;
+    Emitter em; em.out = out; em.cap = out_cap; em.count = 0; em.full = false;
     TrimState ts; ts.n = 0; ts.cap = st.cap; ts.cand = st.ts_cand; ts.shift = st.ts_shift;
     bool overflow = false;
     int n = c.n;

@@ -13,9 +13,44 @@ namespace smx {
 // Stage 0.  Staged buffer of strand X = X[woff : n] (the last min(n, L) symbols), 8 symbols/word.
 // Strand 1 is the reverse complement (demultiplex.py:142; Bio.Seq complement table).
 
+// 8 consecutive 2-bit codes -> 8 nibbles
+SMX_HD u32 spread2to4(u32 v) {
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    return v;
+}
+
 SMX_HD void stage_window_word(const Tables &t, const Batch &b, u32 read, int strand, int w) {
     int n = (int)b.lengths[read];
     Geo g = make_geo(n, t.L);
+    if (!read_is_flagged(b, read)) {
+        // fast path: the staged symbols are one contiguous run of the 2-bit stream (the tail of the
+        // read for strand 0, its head read backwards and complemented for strand 1)
+        int valid = g.wl - 8 * w;
+        valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
+        u32 out = 0;
+        if (valid) {
+            int x0 = g.woff + 8 * w;                          // strand coordinate of symbol 0
+            int first = strand ? (n - 1 - x0) - 7 : stored_pos(b, x0, n);   // stored index of the lowest base needed
+            int lo = first < 0 ? 0 : first;
+            const u32 *src = b.packed2 + b.word_off[read] + (u64)(lo >> 4);
+            u64 pair = (u64)src[0] | ((u64)src[1] << 32);
+            u32 v = (u32)(pair >> (2 * (lo & 15))) & 0xFFFFu;
+            if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below
+            if (strand) {                                      // reverse the 8 codes and complement
+                v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+                v = ((v & 0x0F0Fu) << 4) | ((v >> 4) & 0x0F0Fu);
+                v = ((v & 0x00FFu) << 8) | ((v >> 8) & 0x00FFu);
+                v ^= 0xFFFFu;
+            }
+            out = spread2to4(v);
+        }
+        if (valid < 8) out |= ~0u << (4 * valid);
+        b.win[((u64)strand * t.wpw + w) * b.n_pad + read] = out;
+        return;
+    }
     u32 out = 0;
     for (int i = 0; i < 8; ++i) {
         int p = w * 8 + i;
@@ -35,7 +70,7 @@ SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int
 // Stage 1.  match_one_end's primer search (demultiplex.py:757-766) for one (read, strand, primer).
 
 template <typename W>
-SMX_HD bool primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
+SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
                                  const u64 *peq, const u64 *peq_rev, const u64 *peq_fw) {
     const int n = (int)b.lengths[read];
     const Geo g = make_geo(n, t.L);
@@ -123,7 +158,7 @@ SMX_HD bool primer_search_thread(const Tables &t, const Batch &b, u32 read, int 
         ohit = bst <= k;
     }
     b.orient_hit[hit_idx] = ohit;
-    return h.distance >= 0;
+    return h.distance >= 0 ? (int)h.n_locations : 0;      // work entries this slot needs
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,149 +272,151 @@ SMX_HD int lowest_bit32(u32 v) {
 
 constexpr int kMaxWordHits = 32;
 
-// One (matched slot, bword).  `beq_rows` points at the bword's [m][16] table (shared memory in the
-// CUDA launch).  Accumulates the SURVEY.md 8d work formula into cells / wcols.
+// One work entry (matched slot of a read, one equal-best primer end at staged position p) and one
+// bword.  `beq_rows` points at the bword's [m][16] table (shared memory in the CUDA launch).
+// Accumulates the SURVEY.md 8d work formula into cells / wcols.
 template <int K>
-SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer, u32 g,
-                                     const u32 *beq_rows, unsigned long long &cells, unsigned long long &wcols) {
+SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, int p, u64 entry, int strand,
+                                     int primer, u32 g, const u32 *beq_rows,
+                                     unsigned long long &cells, unsigned long long &wcols) {
     typedef BitSliced<K> BS;
-    const u32 slot = slot_index(t, strand, primer);
-    const smx_primer_hit ph = b.phit[(u64)slot * b.n_pad + read];
     const u64 gslot = (u64)strand * t.n_bwords + g;
-    if (ph.distance < 0) { b.bh_count[gslot * b.n_pad + read] = 0; return; }
+    unsigned char &out_count = b.bh_count[gslot * b.e_cap + entry];
+    out_count = 0;
     const int n = (int)b.lengths[read];
     const Geo geo = make_geo(n, t.L);
-    const u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
     const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
     const int m = t.bw_len[g];
     const u32 valid = t.bw_valid[g];
     const int nbits = popcount32(valid);
     const bool small = m + K <= 16;            // whole flank fits one 64-bit register
 
-    smx_barcode_hit hits[kMaxWordHits];
+    const Flank f = make_flank(geo.woff + p + geo.delta, n);
+    const int fl = n - f.a_align;
+    const int cols = fl < m + K ? fl : m + K;
+    if (cols > 0) {
+        cells += (unsigned long long)nbits * m * cols;
+        wcols += (unsigned long long)nbits * ((m + 31) >> 5) * cols;
+    }
+    const int base = f.a_align - geo.woff;          // staged index of flank column 1
+    u64 F = ~0ull;
+    if (small && cols > 0) {
+        // 16 symbols starting at staged position `base`, symbols >= cols forced to "other"
+        int w0 = base >> 3, sh = 4 * (base & 7);
+        u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
+        u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
+        u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
+        u64 lo = ((u64)a1 << 32) | a0, hi = a2;
+        F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        if (cols < 16) F |= ~0ull << (4 * cols);
+    }
+    if (t.prefilter) {
+        // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key
+        // barcode_rc + flank[:m-k] can only be present if those m-k symbols exist and are
+        // all A/C/G/T; for such flanks the filter has no false negatives.
+        const int need = m - K;
+        if (n - f.a_pref < need) return;
+        bool acgt = true;
+        if (small && f.a_pref == f.a_align) {
+            u64 chk = need >= 16 ? ~0ull : ((1ull << (4 * need)) - 1);
+            acgt = (F & chk & 0xCCCCCCCCCCCCCCCCull) == 0;
+        } else {
+            for (int x = 0; x < need; ++x)
+                if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { acgt = false; break; }
+        }
+        if (!acgt) return;
+    }
+    if (cols < m - K || cols <= 0) return;           // D[m][j] >= m - j > K for every column
+    typename BS::Out o;
+    if (small) {
+        auto rowwin = [&](int i) -> u64 {
+            int shn = i - K - 1;                      // first column of the band, 0-based symbol
+            return shn >= 0 ? (F >> (4 * shn)) : (F << (4 * -shn));
+        };
+        BS::run(beq_rows, m, rowwin, o);
+    } else {
+        auto rowwin = [&](int i) -> u64 {
+            u64 W = 0;
+            for (int tt = 0; tt < BS::NT; ++tt) {
+                int j = i - K + tt;
+                u64 c = (j >= 1 && j <= cols) ? (u64)staged_sym(t, b, read, strand, base + j - 1) : 15ull;
+                W |= c << (4 * tt);
+            }
+            return W;
+        };
+        BS::run(beq_rows, m, rowwin, o);
+    }
+    // bit-sliced test "some in-range column has D[m][j] <= K"
+    u32 v[BS::NB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < BS::NB; ++q) v[q] = o.cnt[q];
+    u32 ov = o.over;
+    u32 flag = (m - K <= cols) ? (planes_le<K, BS::NB>(v) & ~ov) : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int tt = 1; tt < BS::NT; ++tt) {
+        u32 x = o.rp[tt - 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < BS::NB; ++q) { u32 c = v[q] & x; v[q] ^= x; x = c; }
+        ov |= x;
+        x = o.rm[tt - 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < BS::NB; ++q) { u32 br = ~v[q] & x; v[q] ^= x; x = br; }
+        if (m - K + tt <= cols) flag |= planes_le<K, BS::NB>(v) & ~ov;
+    }
+    flag &= valid;
+    // exact scalar read-out of the few flagged barcodes (ascending bit = ascending list position)
     int nh = 0;
+    while (flag) {
+        int q = lowest_bit32(flag);
+        flag &= flag - 1;
+        int val = 0;
+        for (int bb = 0; bb < BS::NB; ++bb) val |= (int)((o.cnt[bb] >> q) & 1) << bb;
+        int best = 1 << 20;
+        u64 mask = 0;
+        for (int tt = 0; tt < BS::NT; ++tt) {
+            if (tt > 0) val += (int)((o.rp[tt - 1] >> q) & 1) - (int)((o.rm[tt - 1] >> q) & 1);
+            int col = m - K + tt;
+            if (col > cols) break;
+            if (val < best) { best = val; mask = 0; }
+            if (val == best) mask |= 1ull << (col - 1);
+        }
+        if (best > K) continue;
+        if (nh < t.hit_cap) {
+            smx_barcode_hit h;
+            h.barcode = t.bw_list[(u64)g * 32 + q]; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = f.bs;
+            b.bh_list[(gslot * t.hit_cap + nh) * b.e_cap + entry] = h;
+        }
+        ++nh;
+    }
+    out_count = (unsigned char)nh;
+    if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
+}
+
+// Work-entry bookkeeping of stage 1: entries [base, base + nloc) of `slot` for one matched read.
+SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u32 base) {
+    b.ent_base[(u64)slot * b.n_pad + read] = base;
+    const u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
+    u32 e = base;
     for (int mwi = 0; mwi < t.mw; ++mwi) {
         u32 word = emask[(u64)mwi * b.n_pad];
         while (word) {
             int p = mwi * 32 + lowest_bit32(word);
             word &= word - 1;
-            const Flank f = make_flank(geo.woff + p + geo.delta, n);
-            const int fl = n - f.a_align;
-            const int cols = fl < m + K ? fl : m + K;
-            if (cols > 0) {
-                cells += (unsigned long long)nbits * m * cols;
-                wcols += (unsigned long long)nbits * ((m + 31) >> 5) * cols;
+            if (e < b.e_cap) {
+                b.ent_read[(u64)slot * b.e_cap + e] = read;
+                b.ent_pos[(u64)slot * b.e_cap + e] = (unsigned short)p;
             }
-            const int base = f.a_align - geo.woff;          // staged index of flank column 1
-            u64 F = ~0ull;
-            if (small && cols > 0) {
-                // 16 symbols starting at staged position `base`, symbols >= cols forced to "other"
-                int w0 = base >> 3, sh = 4 * (base & 7);
-                u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
-                u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
-                u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
-                u64 lo = ((u64)a1 << 32) | a0, hi = a2;
-                F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
-                if (cols < 16) F |= ~0ull << (4 * cols);
-            }
-            if (t.prefilter) {
-                // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key
-                // barcode_rc + flank[:m-k] can only be present if those m-k symbols exist and are
-                // all A/C/G/T; for such flanks the filter has no false negatives.
-                const int need = m - K;
-                if (n - f.a_pref < need) continue;
-                bool acgt = true;
-                if (small && f.a_pref == f.a_align) {
-                    u64 chk = need >= 16 ? ~0ull : ((1ull << (4 * need)) - 1);
-                    acgt = (F & chk & 0xCCCCCCCCCCCCCCCCull) == 0;
-                } else {
-                    for (int x = 0; x < need; ++x)
-                        if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { acgt = false; break; }
-                }
-                if (!acgt) continue;
-            }
-            if (cols < m - K || cols <= 0) continue;         // D[m][j] >= m - j > K for every column
-            typename BS::Out o;
-            if (small) {
-                auto rowwin = [&](int i) -> u64 {
-                    int shn = i - K - 1;                      // first column of the band, 0-based symbol
-                    return shn >= 0 ? (F >> (4 * shn)) : (F << (4 * -shn));
-                };
-                BS::run(beq_rows, m, rowwin, o);
-            } else {
-                auto rowwin = [&](int i) -> u64 {
-                    u64 W = 0;
-                    for (int tt = 0; tt < BS::NT; ++tt) {
-                        int j = i - K + tt;
-                        u64 c = (j >= 1 && j <= cols) ? (u64)staged_sym(t, b, read, strand, base + j - 1) : 15ull;
-                        W |= c << (4 * tt);
-                    }
-                    return W;
-                };
-                BS::run(beq_rows, m, rowwin, o);
-            }
-            // bit-sliced test "some in-range column has D[m][j] <= K"
-            u32 v[BS::NB];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int q = 0; q < BS::NB; ++q) v[q] = o.cnt[q];
-            u32 ov = o.over;
-            u32 flag = (m - K <= cols) ? (planes_le<K, BS::NB>(v) & ~ov) : 0u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int tt = 1; tt < BS::NT; ++tt) {
-                u32 x = o.rp[tt - 1];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int q = 0; q < BS::NB; ++q) { u32 c = v[q] & x; v[q] ^= x; x = c; }
-                ov |= x;
-                x = o.rm[tt - 1];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int q = 0; q < BS::NB; ++q) { u32 br = ~v[q] & x; v[q] ^= x; x = br; }
-                if (m - K + tt <= cols) flag |= planes_le<K, BS::NB>(v) & ~ov;
-            }
-            flag &= valid;
-            // exact scalar read-out of the few flagged barcodes
-            while (flag) {
-                int q = lowest_bit32(flag);
-                flag &= flag - 1;
-                int val = 0;
-                for (int bb = 0; bb < BS::NB; ++bb) val |= (int)((o.cnt[bb] >> q) & 1) << bb;
-                int best = 1 << 20;
-                u64 mask = 0;
-                for (int tt = 0; tt < BS::NT; ++tt) {
-                    if (tt > 0) val += (int)((o.rp[tt - 1] >> q) & 1) - (int)((o.rm[tt - 1] >> q) & 1);
-                    int col = m - K + tt;
-                    if (col > cols) break;
-                    if (val < best) { best = val; mask = 0; }
-                    if (val == best) mask |= 1ull << (col - 1);
-                }
-                if (best > K) continue;
-                int j = (int)t.bw_list[(u64)g * 32 + q];
-                int pos = 0;
-                while (pos < nh && (int)hits[pos].barcode < j) ++pos;
-                if (pos < nh && (int)hits[pos].barcode == j) {
-                    if (best < hits[pos].distance) {           // strictly smaller wins (demultiplex.py:809)
-                        hits[pos].distance = (int16_t)best; hits[pos].end_mask = mask; hits[pos].search_start = f.bs;
-                    }
-                } else {
-                    for (int x = nh; x > pos; --x) hits[x] = hits[x - 1];
-                    hits[pos].barcode = (uint16_t)j; hits[pos].distance = (int16_t)best;
-                    hits[pos].end_mask = mask; hits[pos].search_start = f.bs;
-                    ++nh;
-                }
-            }
+            ++e;
         }
     }
-    b.bh_count[gslot * b.n_pad + read] = (unsigned char)nh;
-    if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
-    int lim = nh < t.hit_cap ? nh : t.hit_cap;
-    for (int e = 0; e < lim; ++e) b.bh_list[(gslot * t.hit_cap + e) * b.n_pad + read] = hits[e];
 }
 
 #if defined(__CUDACC__)
@@ -409,21 +446,27 @@ __global__ void __launch_bounds__(128) k_primer_search(Batch b) {
     __syncthreads();
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0;
-    bool matched = false;
+    int nloc = 0;
     if (read < b.n_reads) {
-        matched = primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[1], s_peq[2]);
+        nloc = primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[1], s_peq[2]);
         int n = (int)b.lengths[read];
         cells = (unsigned long long)(n < c_tables.L ? n : c_tables.L);       // HW columns of this search
     }
-    // compact list of matched reads per slot (warp-aggregated append; order is irrelevant)
+    // work entries, one per equal-best end location: warp-aggregated allocation, a read's entries
+    // stay consecutive (the order of reads inside the list is irrelevant)
     {
-        const unsigned ball = __ballot_sync(0xffffffffu, matched);
-        if (ball) {
-            const int lane = threadIdx.x & 31;
+        const int lane = threadIdx.x & 31;
+        int incl = nloc;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
             u32 base = 0;
-            if (lane == 0) base = atomicAdd(&b.slot_count[blockIdx.y], (u32)__popc(ball));
+            if (lane == 0) base = atomicAdd(&b.slot_count[blockIdx.y], (u32)total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (matched) b.slot_list[(u64)blockIdx.y * b.n_pad + base + __popc(ball & ((1u << lane) - 1))] = read;
+            if (nloc) write_entries(c_tables, b, blockIdx.y, read, base + (u32)(incl - nloc));
         }
     }
     for (int o = 16; o; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
@@ -443,7 +486,8 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
     const int strand = blockIdx.y / t.n_bwords;
     const int primer = t.bw_primer[g];
     const u32 slot = slot_index(t, strand, primer);
-    const u32 cnt = b.slot_count[slot];
+    u32 cnt = b.slot_count[slot];
+    if (cnt > b.e_cap) cnt = b.e_cap;
     if (blockIdx.x * blockDim.x >= cnt) return;
     const int m = t.bw_len[g];
     for (int i = threadIdx.x; i < m * 16; i += blockDim.x) s_beq[i] = t.beq[(u64)t.bw_row[g] * 16 + i];
@@ -451,8 +495,9 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
     const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0, wcols = 0;
     if (idx < cnt) {
-        const u32 read = b.slot_list[(u64)slot * b.n_pad + idx];
-        barcode_bitsliced_thread<K>(t, b, read, strand, primer, g, s_beq, cells, wcols);
+        const u32 read = b.ent_read[(u64)slot * b.e_cap + idx];
+        const int p = b.ent_pos[(u64)slot * b.e_cap + idx];
+        barcode_bitsliced_thread<K>(t, b, read, p, idx, strand, primer, g, s_beq, cells, wcols);
     }
     for (int o = 16; o; o >>= 1) {
         cells += __shfl_down_sync(0xffffffffu, cells, o);
@@ -464,25 +509,51 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
     }
 }
 
-// First pass: one thread per read, working storage in thread-local arrays.  write_pass = 0 counts
-// records (and flags reads whose groups overflow kSmallGroups), write_pass = 1 writes them.
+constexpr int kInlineRecords = 4;
+
+// Selection, single pass: one thread per read, working storage in thread-local arrays.  Records
+// are produced once into a small local buffer; the first goes to rec_stage[read], further ones
+// (rare) to a contiguous block of rec_pool.  Reads whose groups overflow kSmallGroups or that
+// emit more than kInlineRecords records are flagged (bit1) for k_select_big.
 template <int MAXP>
-__global__ void __launch_bounds__(128) k_select(Batch b, int write_pass) {
+__global__ void __launch_bounds__(128) k_select(Batch b) {
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     if (read >= b.n_reads) return;
-    if (write_pass && (b.read_flags[read] & 2)) return;        // handled by k_select_big
     EndInfo ends[2 * MAXP];
     Group groups[kSmallGroups], pg[kSmallGroups];
     Cand gcand[kSmallGroups], pcand[kSmallGroups];
     int ts_cand[kSmallGroups], ts_shift[kSmallGroups];
+    smx_record local[kInlineRecords];
     SelectStore st;
     st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
     st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
     SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
     unsigned char flags;
-    smx_record *out = write_pass ? b.records + b.rec_offset[read] : nullptr;
-    u32 cnt = select_read(c, ends, st, out, flags);
-    if (!write_pass) { b.rec_count[read] = cnt; b.read_flags[read] = flags; }
+    u32 cnt = select_read(c, ends, st, local, kInlineRecords, flags);
+    if (cnt > kInlineRecords) flags |= 2;
+    b.rec_count[read] = cnt;
+    b.read_flags[read] = flags;
+    if (flags & 2) return;
+    if (cnt >= 1) b.rec_stage[read] = local[0];
+    if (cnt >= 2) {
+        u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt - 1);
+        b.rec_extra[read] = base;
+        if (base + cnt - 1 <= b.pool_cap)
+            for (u32 i = 1; i < cnt; ++i) b.rec_pool[base + i - 1] = local[i];
+    }
+}
+
+// Moves staged records to their final, read-ordered positions.
+__global__ void __launch_bounds__(256) k_compact_records(Batch b) {
+    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
+    if (read >= b.n_reads) return;
+    if (b.read_flags[read] & 2) return;                       // written by k_select_big
+    u32 cnt = b.rec_count[read];
+    if (!cnt) return;
+    u32 off = b.rec_offset[read];
+    b.records[off] = b.rec_stage[read];
+    u32 base = cnt > 1 ? b.rec_extra[read] : 0;
+    for (u32 i = 1; i < cnt; ++i) b.records[off + i] = b.rec_pool[base + i - 1];
 }
 
 // Second pass over the (rare) reads flagged by the first: same routine, kBigGroups-entry storage
@@ -496,7 +567,7 @@ __global__ void __launch_bounds__(32) k_select_big(Batch b, const u32 *list, u32
     SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
     unsigned char flags;
     smx_record *out = write_pass ? b.records + b.rec_offset[read] : nullptr;
-    u32 cnt = select_read(c, ends, st, out, flags);
+    u32 cnt = select_read(c, ends, st, out, 0xFFFFFFFFu, flags);
     if (!write_pass) {
         b.rec_count[read] = cnt;
         b.read_flags[read] = (unsigned char)((flags & 1) | 2 | ((flags & 2) ? 4 : 0));   // bit2: still overflowing

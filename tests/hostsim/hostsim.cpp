@@ -26,9 +26,11 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     std::vector<u32> win((size_t)2 * t.wpw * n_pad), endmask((size_t)2 * nP * t.mw * n_pad), rec_count(n), rec_offset(n + 1);
     std::vector<smx_primer_hit> phit((size_t)2 * nP * n_pad);
     std::vector<unsigned char> orient_hit((size_t)2 * nP * n_pad), flags(n);
-    std::vector<u32> slot_list((size_t)2 * nP * n_pad + 1), slot_count((size_t)2 * nP + 1, 0);
-    std::vector<unsigned char> bh_count((size_t)2 * t.n_bwords * n_pad + 1);
+    std::vector<u32> slot_count((size_t)2 * nP + 1, 0), ent_base((size_t)2 * nP * n_pad + 1), ent_read;
+    std::vector<unsigned short> ent_pos;
+    std::vector<unsigned char> bh_count;
     std::vector<smx_barcode_hit> bh_list;
+    u32 e_cap = 16;        // deliberately tiny: exercises the capacity re-run
     unsigned long long counters[8] = {0};
     Batch b;
     memset(&b, 0, sizeof(b));
@@ -37,31 +39,47 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     bool flagged = in->packed4 && in->off4 && in->packed4_words;
     b.packed4 = flagged ? in->packed4 : nullptr; b.off4 = flagged ? in->off4 : nullptr;
     b.win = win.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.orient_hit = orient_hit.data();
-    b.slot_list = slot_list.data(); b.slot_count = slot_count.data(); b.bh_count = bh_count.data();
+    b.slot_count = slot_count.data(); b.ent_base = ent_base.data();
     b.rec_count = rec_count.data(); b.rec_offset = rec_offset.data();
     b.read_flags = flags.data(); b.counters = counters;
 
     for (u32 r = 0; r < n; ++r)
         for (int s = 0; s < 2; ++s)
             for (int w = 0; w < t.wpw; ++w) stage_window_word(t, b, r, s, w);
-    for (int s = 0; s < 2; ++s)
-        for (int p = 0; p < nP; ++p)
-            for (u32 r = 0; r < n; ++r) {
-                if (t.use64) primer_search_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
-                else primer_search_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
-            }
     Tables &tm = ht.t;
-    for (;;) {
-        bh_list.assign((size_t)2 * t.n_bwords * t.hit_cap * n_pad + 1, smx_barcode_hit());
-        b.bh_list = bh_list.data();
+    for (;;) {      // stage 1 + 2, re-run on capacity overflow exactly as the CUDA library does
+        ent_read.assign((size_t)2 * nP * e_cap + 1, 0); ent_pos.assign((size_t)2 * nP * e_cap + 1, 0);
+        bh_count.assign((size_t)2 * t.n_bwords * e_cap + 1, 0);
+        bh_list.assign((size_t)2 * t.n_bwords * t.hit_cap * e_cap + 1, smx_barcode_hit());
+        b.e_cap = e_cap; b.ent_read = ent_read.data(); b.ent_pos = ent_pos.data();
+        b.bh_count = bh_count.data(); b.bh_list = bh_list.data();
+        std::fill(slot_count.begin(), slot_count.end(), 0u);
         counters[1] = counters[3] = counters[7] = 0;
+        for (int s = 0; s < 2; ++s)
+            for (int p = 0; p < nP; ++p)
+                for (u32 r = 0; r < n; ++r) {
+                    int nloc;
+                    if (t.use64) nloc = primer_search_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
+                    else nloc = primer_search_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
+                    if (nloc) {
+                        u32 slot = (u32)(s * nP + p);
+                        write_entries(t, b, slot, r, slot_count[slot]);
+                        slot_count[slot] += (u32)nloc;
+                    }
+                }
+        u32 max_entries = 0;
+        for (u32 v : slot_count) max_entries = std::max(max_entries, v);
+        if (max_entries > e_cap) { e_cap = max_entries; continue; }
         for (int s = 0; s < 2; ++s)
             for (int g = 0; g < t.n_bwords; ++g) {
                 const u32 *rows = t.beq + (size_t)t.bw_row[g] * 16;
                 int p = t.bw_primer[g];
-                for (u32 r = 0; r < n; ++r) {
+                u32 slot = (u32)(s * nP + p);
+                for (u32 e = 0; e < slot_count[slot]; ++e) {
+                    u32 r = ent_read[(size_t)slot * e_cap + e];
+                    int pos = ent_pos[(size_t)slot * e_cap + e];
                     switch (t.k_idx) {
-#define SMX_K2(KK) case KK: barcode_bitsliced_thread<KK>(t, b, r, s, p, (u32)g, rows, counters[1], counters[3]); break;
+#define SMX_K2(KK) case KK: barcode_bitsliced_thread<KK>(t, b, r, pos, e, s, p, (u32)g, rows, counters[1], counters[3]); break;
                         SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
 #undef SMX_K2
                         default: snprintf(g_err, sizeof(g_err), "unsupported k_idx"); return SMX_ERR_ARG;
@@ -82,11 +100,11 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         SelectStore st;
         st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
         st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
-        u32 cnt = select_read(c, ends, st, dst, f);
+        u32 cnt = select_read(c, ends, st, dst, 0xFFFFFFFFu, f);
         if (f & 2) {            // second pass on the big scratch, as k_select_big does
             EndInfo *bends;
             SelectStore bst = big_store(big.data(), bends);
-            cnt = select_read(c, bends, bst, dst, f);
+            cnt = select_read(c, bends, bst, dst, 0xFFFFFFFFu, f);
             if (f & 2) f |= 4;
         }
         return cnt;
@@ -124,11 +142,16 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                 u32 slot = (u32)(sd * nP + p);
                 u64 gslot = (u64)sd * t.n_bwords + g;
                 for (u32 r = 0; r < n; ++r) {
-                    if (phit[(size_t)slot * n_pad + r].distance < 0) continue;
-                    int k = std::min<int>(bh_count[gslot * n_pad + r], t.hit_cap);
-                    for (int e = 0; e < k; ++e) {
-                        const smx_barcode_hit &h = bh_list[(gslot * t.hit_cap + e) * n_pad + r];
-                        out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r] = h;
+                    const smx_primer_hit &h0 = phit[(size_t)slot * n_pad + r];
+                    if (h0.distance < 0) continue;
+                    for (u32 l = 0; l < h0.n_locations; ++l) {
+                        u64 e = (u64)ent_base[(size_t)slot * n_pad + r] + l;
+                        int k = std::min<int>(bh_count[gslot * e_cap + e], t.hit_cap);
+                        for (int x = 0; x < k; ++x) {
+                            const smx_barcode_hit &h = bh_list[(gslot * t.hit_cap + x) * e_cap + e];
+                            smx_barcode_hit &dst = out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r];
+                            if (dst.distance < 0 || h.distance < dst.distance) dst = h;
+                        }
                     }
                 }
             }
