@@ -69,7 +69,8 @@ struct smx_ctx {
     DevBuf<unsigned char> b_len, bw_len, bw_primer;
     DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     DevBuf<unsigned short> bw_list;
-    DevBuf<i32> pair_pool, spec_pool;
+    DevBuf<i32> pair_pool, spec_pool, spec_dense;
+    DevBuf<SlotSum> ssum;
     int max_nb = 0;
     // batch storage
     Batch b;
@@ -147,7 +148,7 @@ void smx_destroy(smx_ctx *c) {
     c->rec_extra.release(); c->rec_stage.release(); c->rec_pool.release(); c->big_list.release(); c->big_scratch.release();
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
-    c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release();
+    c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release(); c->ssum.release();
     c->packed2.release(); c->lengths.release(); c->packed4.release(); c->win.release(); c->endmask.release();
     c->rec_count.release(); c->rec_offset.release(); c->block_sums.release(); c->word_off.release();
     c->off4.release(); c->phit.release(); c->orient_hit.release(); c->read_flags.release();
@@ -194,12 +195,14 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->spec_key, ht.spec_key)); CUC(upload(c->spec_key_off, ht.spec_key_off));
     CUC(upload(c->spec_row, ht.spec_row)); CUC(upload(c->spec_p1, ht.spec_p1)); CUC(upload(c->spec_p2, ht.spec_p2));
     CUC(upload(c->spec_pool, ht.spec_pool));
+    CUC(upload(c->spec_dense, ht.spec_dense));
     CUC(c->counters.ensure(8));
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
     ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,
                     c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
                     c->spec_row.p, c->spec_p1.p, c->spec_p2.p, c->spec_pool.p);
     c->t = ht.t;
+    c->t.spec_dense = ht.spec_dense.empty() ? nullptr : c->spec_dense.p;
     memset(&c->b, 0, sizeof(c->b));
     if (ht.t.k_idx > 8) {
         smx_destroy(c);
@@ -236,6 +239,7 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     CU(c->endmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(c->orient_hit.ensure((size_t)2 * nP * n_pad));
     CU(c->slot_count.ensure((size_t)2 * nP)); CU(c->ent_base.ensure((size_t)2 * nP * n_pad));
+    CU(c->ssum.ensure((size_t)2 * nP * n_pad));
     if (c->e_cap < n_pad) c->e_cap = n_pad;
     if (c->pool_cap < n_pad / 8 + 1024) c->pool_cap = n_pad / 8 + 1024;
     CU(ensure_entry_buffers(c));
@@ -254,7 +258,7 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
     b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
     b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.orient_hit = c->orient_hit.p;
-    b.slot_count = c->slot_count.p; b.ent_base = c->ent_base.p;
+    b.slot_count = c->slot_count.p; b.ent_base = c->ent_base.p; b.ssum = c->ssum.p;
     b.rec_stage = c->rec_stage.p; b.rec_extra = c->rec_extra.p;
     bind_entry_buffers(c);
     b.rec_count = c->rec_count.p; b.rec_offset = c->rec_offset.p;
@@ -316,8 +320,12 @@ int smx_run_resident(smx_ctx *c) {
         // stage 3: single-pass selection, scan
         CU(cudaMemsetAsync(c->counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
         CU(cudaEventRecord(c->ev[3], st));
+        {
+            dim3 sgrid((n + 255) / 256, 2 * nP);
+            k_slot_summary<<<sgrid, 256, 0, st>>>(b);
+        }
         if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b);
-        ++launches;
+        launches += 2;
         CU(cudaMemcpyAsync(slot_counts.data(), c->slot_count.p, slot_counts.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
         CU(scan_and_count(c, launches, host_counters));
         // capacity checks: every overflow is resolved by a second GPU pass with larger buffers

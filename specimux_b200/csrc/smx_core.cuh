@@ -174,12 +174,27 @@ struct Tables {
     const u32 *pair_fwd, *pair_rev;
     const i32 *pair_pool;
 
+    const i32 *spec_dense;   // optional [b1 * n_b2 + b2] -> key index or -1 (nullptr when too large)
+    int n_b2;
     const u64 *spec_key;     // sorted unique (b1 << 32 | b2)
     const u32 *spec_key_off; // n_keys+1 -> rows of that key in file order
     const u32 *spec_row;     // row indices
     const u64 *spec_p1_mask, *spec_p2_mask;   // by row
     const i32 *spec_pool;    // by row
 };
+
+// Per-(slot, read) digest of the barcode hit lists, produced by the summary kernel so that the
+// selection stage does not walk the lists in the common case.
+struct SlotSum {
+    u64 first_mask;            // end mask of the first equal-best barcode
+    i32 first_ss;              // its barcode_search_start
+    unsigned short first_best; // its list position
+    unsigned short nhits;      // barcodes within k_idx (saturating)
+    unsigned short nbest;      // barcodes at the best distance (saturating)
+    signed char bd;            // best distance, -1 = none
+    unsigned char pad;
+};
+static_assert(sizeof(SlotSum) == 24, "SlotSum layout");
 
 // Per-batch device buffers.
 struct Batch {
@@ -205,6 +220,7 @@ struct Batch {
     // Barcode hits of entry e for bword g, gslot = strand * n_bwords + g:
     unsigned char *bh_count; // [gslot * e_cap + e]; may exceed hit_cap (-> re-run with a larger cap)
     smx_barcode_hit *bh_list;    // [(gslot * hit_cap + h) * e_cap + e], ascending barcode position
+    SlotSum *ssum;           // [slot * n_pad + read]
     // single-pass selection: first record of every read + pool for the (rare) further records
     smx_record *rec_stage;   // [read]
     smx_record *rec_pool;    // extra records, contiguous per read
@@ -287,6 +303,7 @@ SMX_HD int hw_start_back(const u64 *peq_rev, int m, int best, int e_pos, int sta
 // Specimen lookup (databases.py:219-245).
 
 SMX_HD int spec_find_key(const Tables &t, u32 b1, u32 b2) {
+    if (t.spec_dense) return t.spec_dense[(u64)b1 * t.n_b2 + b2];
     u64 key = ((u64)b1 << 32) | b2;
     int lo = 0, hi = t.n_keys - 1;
     while (lo <= hi) {
@@ -334,6 +351,8 @@ struct EndInfo {            // one (strand, primer) slot as seen by a candidate
     int bd;                 // best barcode distance
     int nbest;              // number of barcodes at bd
     int first_best;         // list position of the first of them (pinned order)
+    int first_ss;           // barcode_search_start of that hit
+    u64 first_mask;         // its SHW end mask
     int strand, primer;
 };
 
@@ -380,25 +399,39 @@ SMX_HD bool next_hit(const SelectCtx &c, int strand, int primer, int after_j, sm
     return found;
 }
 
-SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
-    const Tables &t = *c.t;
-    const smx_primer_hit &ph = c.b->phit[(u64)slot_index(t, strand, primer) * c.b->n_pad + c.read];
-    e.strand = strand; e.primer = primer;
-    e.matched = ph.distance >= 0;
-    e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
-    e.nhits = 0; e.bd = -1; e.nbest = 0; e.first_best = -1;
-    if (!e.matched) return;
-    int bd = 1 << 20;
+// Walks the hit lists of one matched slot once (summary kernel).
+SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &o) {
+    o.first_mask = 0; o.first_ss = 0; o.first_best = 0; o.nhits = 0; o.nbest = 0; o.bd = -1; o.pad = 0;
+    int bd = 1 << 20, nhits = 0, nbest = 0;
     smx_barcode_hit h;
     int after = -1;
     while (next_hit(c, strand, primer, after, h)) {
         after = (int)h.barcode;
         int d = h.distance;
-        ++e.nhits;
-        if (d < bd) { bd = d; e.nbest = 0; }
-        if (d == bd) { if (e.nbest == 0) e.first_best = after; ++e.nbest; }
+        ++nhits;
+        if (d < bd) { bd = d; nbest = 0; }
+        if (d == bd) {
+            if (nbest == 0) { o.first_best = (unsigned short)after; o.first_mask = h.end_mask; o.first_ss = h.search_start; }
+            ++nbest;
+        }
     }
-    if (e.nhits) e.bd = bd;
+    if (nhits) o.bd = (signed char)bd;
+    o.nhits = (unsigned short)(nhits > 65535 ? 65535 : nhits);
+    o.nbest = (unsigned short)(nbest > 65535 ? 65535 : nbest);
+}
+
+SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
+    const Tables &t = *c.t;
+    const u64 idx = (u64)slot_index(t, strand, primer) * c.b->n_pad + c.read;
+    const smx_primer_hit &ph = c.b->phit[idx];
+    e.strand = strand; e.primer = primer;
+    e.matched = ph.distance >= 0;
+    e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
+    e.nhits = 0; e.bd = -1; e.nbest = 0; e.first_best = -1; e.first_ss = 0; e.first_mask = 0;
+    if (!e.matched) return;
+    const SlotSum &ss = c.b->ssum[idx];
+    e.nhits = ss.nhits; e.bd = ss.bd; e.nbest = ss.nbest;
+    e.first_best = ss.nhits ? (int)ss.first_best : -1; e.first_ss = ss.first_ss; e.first_mask = ss.first_mask;
 }
 
 // Equal-best barcodes of an end in pinned order (models.py:116-126 best_b1 / best_b2): the list
@@ -500,17 +533,13 @@ SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &ov
     if (m2) { p2s = e2.ps - shift; p2e = e2.pe - shift; }
     int b1s = kNone, b1e = kNone, b2s = kNone, b2e = kNone;
     if (m1 && e1.nhits) {
-        smx_barcode_hit h;
-        next_hit(c, e1.strand, e1.primer, e1.first_best - 1, h);
-        int bshift = h.search_start == -1 ? 0 : h.search_start;
-        int col = lowest_bit64(h.end_mask);
+        int bshift = e1.first_ss == -1 ? 0 : e1.first_ss;
+        int col = lowest_bit64(e1.first_mask);
         b1s = n - (bshift + col) - 1 - shift; b1e = n - bshift - 1 - shift;
     }
     if (m2 && e2.nhits) {
-        smx_barcode_hit h;
-        next_hit(c, e2.strand, e2.primer, e2.first_best - 1, h);
-        int bshift = h.search_start == -1 ? 0 : h.search_start;
-        int col = lowest_bit64(h.end_mask);
+        int bshift = e2.first_ss == -1 ? 0 : e2.first_ss;
+        int col = lowest_bit64(e2.first_mask);
         b2s = bshift - shift; b2e = bshift + col - shift;
     }
     int s = 0, e = n;
@@ -661,6 +690,7 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st,
     if (top == 0) {
         // no candidate at all: minimal match object (demultiplex.py:202-210)
         EndInfo none; none.matched = 0; none.nhits = 0; none.nbest = 0; none.first_best = -1; none.pd = -1; none.bd = -1;
+        none.first_ss = 0; none.first_mask = 0;
         none.ps = none.pe = 0; none.strand = 0; none.primer = 0;
         Cand cd; cd.pair = -1; cd.rc = 0; cd.e1 = cd.e2 = 0;
         emit_record(c, em, ts, overflow, 0, cd, none, none, -1, SMX_RES_UNKNOWN, -1);
@@ -685,6 +715,34 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st,
                 fn(idx, cd);
             }
     };
+
+    // Fast path (the overwhelmingly common case): a single equal-best candidate whose ends carry at
+    // most one equal-best barcode each.  Every branch of dereplicate_matches / resolve_specimen
+    // then reduces to one record, with no grouping.
+    {
+        int n_top = 0, top_idx = 0;
+        Cand top_cd; top_cd.pair = 0; top_cd.rc = 0; top_cd.e1 = top_cd.e2 = 0;
+        for_each_top([&](int idx, const Cand &cd) { if (n_top++ == 0) { top_idx = idx; top_cd = cd; } });
+        const EndInfo &a = ends[top_cd.e1];
+        const EndInfo &z = ends[top_cd.e2];
+        if (n_top == 1 && a.nbest <= 1 && z.nbest <= 1) {
+            int sample = -1, res = SMX_RES_UNKNOWN, pool = t.pair_pool[top_cd.pair];
+            bool done = false;
+            if (t.derep_best && a.matched && z.matched && a.nhits > 0 && z.nhits > 0) {
+                int row = spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + a.first_best],
+                                     t.pb_barcode[t.pb_off[z.primer] + z.first_best], a.primer, z.primer);
+                if (row >= 0) { sample = row; res = SMX_RES_DEREPLICATED_FULL; pool = t.spec_pool[row]; em.full = true; done = true; }
+            }
+            if (!done) {
+                resolve(c, a, z, t.pair_pool[top_cd.pair], sample, res, pool);
+                if (res == SMX_RES_FULL_MATCH) em.full = true;
+            }
+            emit_record(c, em, ts, overflow, top_idx, top_cd, a, z, sample, res, pool);
+            if (em.full) flags |= 1;
+            if (overflow) flags |= 2;
+            return em.count;
+        }
+    }
 
     if (!t.derep_best) {
         for_each_top([&](int idx, const Cand &cd) {

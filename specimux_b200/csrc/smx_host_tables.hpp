@@ -55,7 +55,7 @@ struct HostTables {
     std::vector<unsigned char> b_len, bw_len, bw_primer;
     std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     std::vector<unsigned short> bw_list;
-    std::vector<i32> pair_pool, spec_pool;
+    std::vector<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
     std::string error;
 
@@ -191,6 +191,14 @@ struct HostTables {
         }
         spec_key_off.push_back(tb->n_specimens);
         t.n_keys = (int)spec_key.size();
+        t.n_b2 = (int)tb->n_b2;
+        spec_dense.clear();
+        if ((u64)tb->n_b1 * tb->n_b2 <= (4u << 20) && tb->n_b1 && tb->n_b2) {
+            spec_dense.assign((size_t)tb->n_b1 * tb->n_b2, -1);
+            for (size_t i = 0; i < spec_key.size(); ++i)
+                spec_dense[(size_t)(spec_key[i] >> 32) * tb->n_b2 + (u32)spec_key[i]] = (i32)i;
+        }
+        t.spec_dense = spec_dense.empty() ? nullptr : spec_dense.data();
         spec_p1.assign(tb->spec_p1_mask, tb->spec_p1_mask + tb->n_specimens);
         spec_p2.assign(tb->spec_p2_mask, tb->spec_p2_mask + tb->n_specimens);
         spec_pool.assign(tb->spec_pool, tb->spec_pool + tb->n_specimens);

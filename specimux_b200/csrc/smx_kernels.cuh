@@ -509,6 +509,20 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
     }
 }
 
+// Stage 3a: digest of every matched slot's hit lists (one thread per (read, slot), high occupancy).
+__global__ void __launch_bounds__(256) k_slot_summary(Batch b) {
+    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
+    if (read >= b.n_reads) return;
+    const Tables &t = c_tables;
+    const int primer = blockIdx.y % t.n_primers, strand = blockIdx.y / t.n_primers;
+    const u64 idx = (u64)blockIdx.y * b.n_pad + read;
+    if (b.phit[idx].distance < 0) return;
+    SelectCtx c; c.t = &t; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
+    SlotSum ss;
+    summarize_slot(c, strand, primer, ss);
+    b.ssum[idx] = ss;
+}
+
 constexpr int kInlineRecords = 4;
 
 // Selection, single pass: one thread per read, working storage in thread-local arrays.  Records

@@ -90,6 +90,16 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         if (tm.hit_cap >= kMaxWordHits) { snprintf(g_err, sizeof(g_err), "hit list overflow"); return SMX_ERR_INTERNAL; }
         tm.hit_cap = std::min(kMaxWordHits, tm.hit_cap * 4);
     }
+    std::vector<SlotSum> ssum((size_t)2 * nP * n_pad + 1);
+    b.ssum = ssum.data();
+    for (int s = 0; s < 2; ++s)
+        for (int p = 0; p < nP; ++p)
+            for (u32 r = 0; r < n; ++r) {
+                size_t idx = (size_t)(s * nP + p) * n_pad + r;
+                if (phit[idx].distance < 0) continue;
+                SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
+                summarize_slot(c, s, p, ssum[idx]);
+            }
     std::vector<unsigned char> big(kBigScratchBytes);
     auto run_select = [&](u32 r, smx_record *dst, unsigned char &f) -> u32 {
         SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
