@@ -105,3 +105,142 @@ def setup_match_parameters(args, specimens, device: int = 0) -> MatchParameters:
     else:
         logging.info("Barcode prefiltering disabled, may run slower")
     return MatchParameters(thr, k_idx, args.search_len, not args.disable_preorient)
+
+
+# ---------------------------------------------------------------------------------------------
+# Output tree (reference orchestration.py:240-372) and the drivers (reference :153-237, :458-545)
+
+def _write_primers(path_dir: str, fwd_primers, rev_primers):
+    with open(os.path.join(path_dir, "primers.fasta"), "w") as f:
+        for p in fwd_primers:
+            f.write(f">{p.name} position=forward pool={','.join(p.pools)}\n{p.primer}\n")
+        for p in rev_primers:
+            f.write(f">{p.name} position=reverse pool={','.join(p.pools)}\n{p.primer}\n")
+    with open(os.path.join(path_dir, "primers.txt"), "w") as f:
+        for p in list(fwd_primers) + list(rev_primers):
+            f.write(f">{p.name}\n{p.primer}\n")
+
+
+def create_output_files(args, specimens):
+    """reference: orchestration.py:314-372 -- directory tree + primers.fasta / primers.txt files."""
+    if not args.output_to_files:
+        return
+    out = args.output_dir
+    os.makedirs(out, exist_ok=True)
+    kinds = ["full", "partial", "unknown"]
+    for kind in kinds:
+        os.makedirs(os.path.join(out, kind), exist_ok=True)
+    for kind in ("partial", "unknown"):
+        os.makedirs(os.path.join(out, kind, "unknown", "unknown-unknown"), exist_ok=True)
+    registry = specimens._primer_registry
+    for pool in registry.get_pools():
+        fwd, rev = registry.get_pool_primers(pool, Primer.FWD), registry.get_pool_primers(pool, Primer.REV)
+        for kind in kinds:
+            os.makedirs(os.path.join(out, kind, pool), exist_ok=True)
+        _write_primers(os.path.join(out, "full", pool), fwd, rev)
+        for f in fwd:
+            for r in rev:
+                for kind in kinds:
+                    os.makedirs(os.path.join(out, kind, pool, f"{f.name}-{r.name}"), exist_ok=True)
+                _write_primers(os.path.join(out, "full", pool, f"{f.name}-{r.name}"), [f], [r])
+            for kind in ("partial", "unknown"):
+                os.makedirs(os.path.join(out, kind, pool, f"{f.name}-unknown"), exist_ok=True)
+        for r in rev:
+            for kind in ("partial", "unknown"):
+                os.makedirs(os.path.join(out, kind, pool, f"unknown-{r.name}"), exist_ok=True)
+
+
+def iter_batches(seq_records, batch_size: int, max_seqs: int, all_seqs: bool):
+    """reference: orchestration.py:447-456."""
+    num = 0
+    while all_seqs or num < max_seqs:
+        to_read = batch_size if all_seqs else min(batch_size, max_seqs - num)
+        batch = list(itertools.islice(seq_records, to_read))
+        if not batch:
+            break
+        yield batch
+        num += len(batch)
+
+
+GPU_BATCH_READS = 65536       # reads per GPU call (the reference hands 1000-read batches to CPU workers)
+
+
+def _visible_gpus() -> int:
+    return int(_lib.load().smx_device_count())
+
+
+def _run(args, multi: bool):
+    primer_registry = read_primers_file(args.primer_file)
+    specimens = read_specimen_file(args.specimen_file, primer_registry)
+    specimens.validate()
+    parameters = setup_match_parameters(args, specimens)
+    seq_records = open_sequence_file(args.sequence_file, args)
+    create_output_files(args, specimens)
+    start = timeit.default_timer()
+    if getattr(args, "start_seq", 1) > 1:
+        for _ in itertools.islice(seq_records, args.start_seq - 1):
+            pass
+    all_seqs = args.num_seqs < 0
+    n_visible = _visible_gpus()
+    if n_visible < 1:
+        raise RuntimeError("specimux_b200: no CUDA device visible; the matching has no CPU fallback")
+    n_gpus = n_visible if (multi and args.threads <= 0) else max(1, min(n_visible, args.threads if multi else 1))
+    logging.info(f"Will run on {n_gpus} GPU(s), {GPU_BATCH_READS} reads per batch")
+    prefilter = PassthroughPrefilter() if args.disable_prefilter else BloomEmulationPrefilter()
+    stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
+    trace_logger = None
+    if args.diagnostics and args.output_to_files:
+        from .trace import TraceLogger
+        trace_logger = TraceLogger(True, args.diagnostics, args.output_dir, "main", stamp)
+
+    from concurrent.futures import ThreadPoolExecutor
+    from collections import deque
+    total = matched = 0
+    offset = 0
+    output_manager = OutputManager(args.output_dir, args.output_file_prefix, args.isfastq) if args.output_to_files else None
+    if output_manager:
+        output_manager.__enter__()
+    try:
+        # One feeder thread per GPU (ctypes releases the GIL inside the C call); batches are dealt
+        # round-robin and their results consumed in submission order, so the per-file record order
+        # is the input order (= the reference's `-t 1` order) for any GPU count.
+        with ThreadPoolExecutor(max_workers=n_gpus) as pool:
+            pending = deque()
+
+            def drain(limit):
+                nonlocal total, matched
+                while len(pending) > limit:
+                    ops, n, m = pending.popleft().result()
+                    for op in ops:
+                        output_write_operation(op, output_manager, args, trace_logger)
+                    total += n
+                    matched += m
+
+            for i, batch in enumerate(iter_batches(seq_records, GPU_BATCH_READS, args.num_seqs, all_seqs)):
+                # tracing needs the batch processed in the main thread order; it still runs on the GPU
+                fut = pool.submit(process_sequences, batch, parameters, specimens, args, prefilter,
+                                  trace_logger if n_gpus == 1 else None, offset, i % n_gpus)
+                offset += len(batch)
+                pending.append(fut)
+                drain(2 * n_gpus)
+            drain(0)
+    finally:
+        if output_manager:
+            output_manager.__exit__(None, None, None)
+        if trace_logger:
+            trace_logger.close()
+    if total > 0:
+        logging.info(f"Processed {total:,} sequences, match rate: {matched / total:.1%}")
+    logging.info(f"Elapsed time: {timeit.default_timer() - start:.2f} seconds")
+    if args.output_to_files:
+        cleanup_empty_directories(args.output_dir)
+
+
+def specimux_mp(args):
+    """reference: orchestration.py:153-237 -- file output, all GPUs (one feeder thread per GPU)."""
+    _run(args, multi=True)
+
+
+def specimux(args):
+    """reference: orchestration.py:458-545 -- console output, one GPU."""
+    _run(args, multi=False)
