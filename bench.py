@@ -119,7 +119,7 @@ def run_reference(args):
     from oracle import cpu_bench
     wl = WORKLOADS[args.config]
     cores = cpu_bench.host_cores()
-    sample = args.ref_sample if args.ref_sample else max(2000, 600 * cores)
+    sample = args.ref_sample if args.ref_sample else max(4000, 2000 * cores)
     ds = dataset(args.config, max(sample, 64), 0) if sample <= 8192 else dataset(args.config, sample, 0)
     reads = ds.reads(0, sample)
     times = []
@@ -247,10 +247,13 @@ def main():
         value = total_reads / (ms / 1000.0)
         alg_ops = 15.0 * (wcols[0] + wcols[1])
         gcups = (cells[0] + cells[1]) / (ms / 1000.0) / 1e9
-        dom = int(np.argmax(st))
-        dom_name = ["stage_windows", "primer_search", "barcode_search", "select"][dom]
-        dom_ops = 15.0 * (wcols[1] if dom == 2 else wcols[0] if dom == 1 else 0)
-        achieved = dom_ops / (st[dom] / 1000.0) / 1e12 if st[dom] > 0 else 0.0
+        # the two DP kernels: stage 1 (primer HW) and stage 2 (barcode SHW); the dominant one by time
+        k_ops = {"primer_search": 15.0 * wcols[0], "barcode_search": 15.0 * wcols[1]}
+        k_ms = {"primer_search": st[1], "barcode_search": st[2]}
+        dom_name = max(k_ms, key=k_ms.get)
+        achieved = k_ops[dom_name] / (k_ms[dom_name] / 1000.0) / 1e12 if k_ms[dom_name] > 0 else 0.0
+        other = "barcode_search" if dom_name == "primer_search" else "primer_search"
+        other_achieved = k_ops[other] / (k_ms[other] / 1000.0) / 1e12 if k_ms[other] > 0 else 0.0
         hbm_bytes = batch.h2d_bytes + res.records.nbytes
         line = {
             "metric": "reads/sec demuxed (whole box)", "value": value, "unit": "reads/s", "n_gpus": world,
@@ -269,6 +272,10 @@ def main():
                          "peak_source": "measured in this run by smx_int_alu_peak (LOP3 %.2f / IADD3 %.2f / mix %.2f Tops/s)"
                                         % (peaks[0], peaks[1], peaks[2]),
                          "algorithmic_ops": "15 int ops x 32-bit word-columns (SURVEY.md 8d)",
+                         "other_dp_kernel": {"kernel": other, "achieved": other_achieved,
+                                             "frac": other_achieved / int_peak if int_peak else None,
+                                             "note": "the bit-sliced barcode kernel executes far fewer than 15 ops per "
+                                                     "algorithmic word-column, so its fraction exceeds 1"},
                          "traffic": None,
                          "hbm_sanity_gbs": hbm_bytes / (ms / 1000.0) / 1e9},
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": "reads/s",

@@ -74,7 +74,7 @@ struct smx_ctx {
     int max_nb = 0;
     // batch storage
     Batch b;
-    DevBuf<u32> packed2, lengths, packed4, win, endmask, rec_count, rec_offset, block_sums;
+    DevBuf<u32> packed2, lengths, packed4, win, endmask, impmask, rec_count, rec_offset, block_sums;
     DevBuf<u64> word_off, off4;
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
@@ -149,7 +149,7 @@ void smx_destroy(smx_ctx *c) {
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release(); c->ssum.release();
-    c->packed2.release(); c->lengths.release(); c->packed4.release(); c->win.release(); c->endmask.release();
+    c->packed2.release(); c->lengths.release(); c->packed4.release(); c->win.release(); c->endmask.release(); c->impmask.release();
     c->rec_count.release(); c->rec_offset.release(); c->block_sums.release(); c->word_off.release();
     c->off4.release(); c->phit.release(); c->orient_hit.release(); c->read_flags.release();
     c->records.release(); c->counters.release();
@@ -237,6 +237,7 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     CU(c->win.ensure((size_t)2 * t.wpw * n_pad));
     CU(c->phit.ensure((size_t)2 * nP * n_pad));
     CU(c->endmask.ensure((size_t)2 * nP * t.mw * n_pad));
+    CU(c->impmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(c->orient_hit.ensure((size_t)2 * nP * n_pad));
     CU(c->slot_count.ensure((size_t)2 * nP)); CU(c->ent_base.ensure((size_t)2 * nP * n_pad));
     CU(c->ssum.ensure((size_t)2 * nP * n_pad));
@@ -257,7 +258,7 @@ int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len;
     b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
     b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
-    b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.orient_hit = c->orient_hit.p;
+    b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.impmask = c->impmask.p; b.orient_hit = c->orient_hit.p;
     b.slot_count = c->slot_count.p; b.ent_base = c->ent_base.p; b.ssum = c->ssum.p;
     b.rec_stage = c->rec_stage.p; b.rec_extra = c->rec_extra.p;
     bind_entry_buffers(c);
@@ -299,7 +300,10 @@ int smx_run_resident(smx_ctx *c) {
             dim3 grid(blocks, 2 * nP);
             if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(b);
             else k_primer_search<u32><<<grid, 128, 0, st>>>(b);
-            ++launches;
+            dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
+            if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, st>>>(b);
+            else k_primer_start<u32><<<sgrid, 128, 0, st>>>(b);
+            launches += 2;
         }
         if (from <= 2) {   // stage 2
             CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned long long), st));

@@ -209,6 +209,7 @@ struct Batch {
     // level-1 results
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
     u32 *endmask;            // [(slot*mw + w) * n_pad + read]
+    u32 *impmask;            // same shape: columns where the running best improved (stage-1 scratch)
     unsigned char *orient_hit;   // [slot * n_pad + read]  explicit orientation test (irregular reads)
     // One work entry per (matched slot, equal-best primer end location); a read's entries are
     // consecutive and in ascending end order.  e_cap entries are allocated per slot.

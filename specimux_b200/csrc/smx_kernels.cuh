@@ -66,12 +66,64 @@ SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int
     return (int)((w >> (4 * (p & 7))) & 15);
 }
 
+SMX_HD int popcount32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+SMX_HD int count_leading_zeros32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return __builtin_clz(v);
+#endif
+}
+
+SMX_HD int lowest_bit32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stage 1.  match_one_end's primer search (demultiplex.py:757-766) for one (read, strand, primer).
 
+SMX_HD u32 funnel_in_sign(u32 hist, u32 x) {      // (hist << 1) | (x >> 31): one SHF on the GPU
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(x, hist, 1);
+#else
+    return (hist << 1) | (x >> 31);
+#endif
+}
+
+SMX_HD u32 bit_reverse32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+
+// Forward pass.  Returns the number of equal-best end locations (0 = no match within k) and
+// leaves distance / first_end / n_locations in phit, the end mask in endmask.  The start of the
+// first location is recovered later by primer_start_thread (one thread per work entry).
+//
+// Bookkeeping is kept off the critical ALU path: per column only the running minimum is updated
+// (1 op) and two sign bits are shifted into history words (1 op each): "score == running best" and
+// "score improved the running best".  After the loop the last improvement marks the first
+// equal-best end and every earlier equality bit is stale.
 template <typename W>
 SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
-                                 const u64 *peq, const u64 *peq_rev, const u64 *peq_fw) {
+                                const u64 *peq, const u64 *peq_fw) {
     const int n = (int)b.lengths[read];
     const Geo g = make_geo(n, t.L);
     const int m = t.p_len[primer], k = t.p_k[primer];
@@ -79,12 +131,14 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
     const u64 hit_idx = (u64)slot * b.n_pad + read;
     const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
     u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
+    u32 *imask = b.impmask + (u64)slot * t.mw * b.n_pad + read;
 
     W Pv = ~(W)0, Mv = 0;
-    int score = m, best = m + 1, first = 0;
+    int score = m, best = m + 1;
     const int p_begin = g.start, p_end = g.wl;
     for (int mwi = 0; mwi < t.mw; ++mwi) {
-        u32 mask = 0;
+        u32 eqh = 0, imh = 0;
+        int done = 0;                                       // columns shifted into the histories
         for (int q = 0; q < 4; ++q) {
             int w = mwi * 4 + q;
             if (w >= t.wpw || w * 8 >= p_end) break;
@@ -97,49 +151,59 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
                     W Eq = peq_word<W>(peq[word & 15]);
                     word >>= 4;
                     score += myers_step<W, false>(Eq, Pv, Mv);
-                    int p = w * 8 + i;
-                    if (score < best) { best = score; first = p; }
-                    if (score == best) mask |= 1u << (q * 8 + i);
+                    imh = funnel_in_sign(imh, (u32)(score - best));          // score < best
+                    best = score < best ? score : best;
+                    eqh = funnel_in_sign(eqh, (u32)(score - best - 1));       // score == best
                 }
+                done += 8;
             } else {
                 for (int i = 0; i < 8; ++i) {
                     int p = w * 8 + i;
                     int c = (int)(word & 15);
                     word >>= 4;
-                    if (p < p_begin || p >= p_end) continue;
-                    W Eq = peq_word<W>(peq[c]);
-                    score += myers_step<W, false>(Eq, Pv, Mv);
-                    if (score < best) { best = score; first = p; }
-                    if (score == best) mask |= 1u << (q * 8 + i);
+                    u32 im = 0, eq = 0;
+                    if (p >= p_begin && p < p_end) {
+                        W Eq = peq_word<W>(peq[c]);
+                        score += myers_step<W, false>(Eq, Pv, Mv);
+                        im = score < best ? 0x80000000u : 0u;
+                        best = score < best ? score : best;
+                        eq = score == best ? 0x80000000u : 0u;
+                    }
+                    imh = funnel_in_sign(imh, im);
+                    eqh = funnel_in_sign(eqh, eq);
                 }
+                done += 8;
             }
         }
-        emask[(u64)mwi * b.n_pad] = mask;
+        // histories hold column c of this word at bit (done-1-c): reverse into bit c
+        eqh = done ? bit_reverse32(eqh) >> (32 - done) : 0u;
+        imh = done ? bit_reverse32(imh) >> (32 - done) : 0u;
+        emask[(u64)mwi * b.n_pad] = eqh;
+        imask[(u64)mwi * b.n_pad] = imh;
     }
 
     smx_primer_hit h;
     h.distance = -1; h.n_locations = 0; h.first_start = 0; h.first_end = 0;
+    int nloc = 0;
     if (best <= k) {
-        // bits set before `first` belong to an older (larger) best: clear them, count the rest
-        int nloc = 0;
+        // last improvement = first equal-best end; equality bits before it are stale
+        int first = 0;
+        for (int mwi = t.mw - 1; mwi >= 0; --mwi) {
+            u32 v = imask[(u64)mwi * b.n_pad];
+            if (v) { first = mwi * 32 + 31 - count_leading_zeros32(v); break; }
+        }
         for (int mwi = 0; mwi < t.mw; ++mwi) {
             u32 v = emask[(u64)mwi * b.n_pad];
             int lo = mwi * 32;
             if (lo + 32 <= first) v = 0;
             else if (lo < first) v &= ~0u << (first - lo);
             emask[(u64)mwi * b.n_pad] = v;
-#if defined(__CUDA_ARCH__)
-            nloc += __popc(v);
-#else
-            nloc += __builtin_popcount(v);
-#endif
+            nloc += popcount32(v);
         }
-        auto load = [&](int p) { return staged_sym(t, b, read, strand, p); };
-        int back = hw_start_back<W>(peq_rev, m, best, first, g.start, load);
         h.distance = (int16_t)best;
         h.n_locations = (uint16_t)nloc;
         h.first_end = g.woff + first + g.delta;
-        h.first_start = g.woff + first - back + g.delta;
+        h.first_start = h.first_end;                       // filled in by primer_start_thread
     }
     b.phit[hit_idx] = h;
 
@@ -158,7 +222,25 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
         ohit = bst <= k;
     }
     b.orient_hit[hit_idx] = ohit;
-    return h.distance >= 0 ? (int)h.n_locations : 0;      // work entries this slot needs
+    return nloc;
+}
+
+// Start recovery for the first equal-best end of a matched slot (edlib: reverse SHW pass with
+// k = best, the LAST equal-best reverse end wins = longest alignment).  One thread per work entry;
+// only a read's first entry does the work.
+template <typename W>
+SMX_HD void primer_start_thread(const Tables &t, const Batch &b, u32 slot, u32 entry, const u64 *peq_rev) {
+    const u32 read = b.ent_read[(u64)slot * b.e_cap + entry];
+    const u64 hit_idx = (u64)slot * b.n_pad + read;
+    if (b.ent_base[hit_idx] != entry) return;              // not the first location of its read
+    const int strand = (int)slot / t.n_primers, primer = (int)slot % t.n_primers;
+    const int n = (int)b.lengths[read];
+    const Geo g = make_geo(n, t.L);
+    smx_primer_hit &h = b.phit[hit_idx];
+    const int first = (int)b.ent_pos[(u64)slot * b.e_cap + entry];
+    auto load = [&](int p) { return staged_sym(t, b, read, strand, p); };
+    int back = hw_start_back<W>(peq_rev, t.p_len[primer], h.distance, first, g.start, load);
+    h.first_start = h.first_end - back;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -252,22 +334,6 @@ template <int K, int NB> SMX_HD u32 planes_le(const u32 *v) {
         else { gt |= eq & v[b]; eq &= ~v[b]; }
     }
     return ~gt;
-}
-
-SMX_HD int popcount32(u32 v) {
-#if defined(__CUDA_ARCH__)
-    return __popc(v);
-#else
-    return __builtin_popcount(v);
-#endif
-}
-
-SMX_HD int lowest_bit32(u32 v) {
-#if defined(__CUDA_ARCH__)
-    return __ffs((int)v) - 1;
-#else
-    return __builtin_ctz(v);
-#endif
 }
 
 constexpr int kMaxWordHits = 32;
@@ -448,7 +514,7 @@ __global__ void __launch_bounds__(128) k_primer_search(Batch b) {
     unsigned long long cells = 0;
     int nloc = 0;
     if (read < b.n_reads) {
-        nloc = primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[1], s_peq[2]);
+        nloc = primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2]);
         int n = (int)b.lengths[read];
         cells = (unsigned long long)(n < c_tables.L ? n : c_tables.L);       // HW columns of this search
     }
@@ -475,6 +541,20 @@ __global__ void __launch_bounds__(128) k_primer_search(Batch b) {
         atomicAdd(&b.counters[0], cells * (unsigned long long)m);
         atomicAdd(&b.counters[2], cells * (unsigned long long)((m + 31) >> 5));
     }
+}
+
+// Start recovery over the compact work-entry lists (full warps instead of the ~50 % matched lanes).
+template <typename W>
+__global__ void __launch_bounds__(128) k_primer_start(Batch b) {
+    __shared__ u64 s_rev[16];
+    const u32 slot = blockIdx.y;
+    u32 cnt = b.slot_count[slot];
+    if (cnt > b.e_cap) cnt = b.e_cap;
+    if (blockIdx.x * blockDim.x >= cnt) return;
+    if (threadIdx.x < 16) s_rev[threadIdx.x] = c_tables.peq_rcrev[(slot % c_tables.n_primers) * 16 + threadIdx.x];
+    __syncthreads();
+    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < cnt) primer_start_thread<W>(c_tables, b, slot, idx, s_rev);
 }
 
 // One thread per (matched slot entry, bword); the bword's bit-sliced table sits in shared memory.

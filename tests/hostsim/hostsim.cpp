@@ -23,7 +23,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     const Tables &t = ht.t;
     const u32 n = in->n_reads, n_pad = n;
     const int nP = t.n_primers;
-    std::vector<u32> win((size_t)2 * t.wpw * n_pad), endmask((size_t)2 * nP * t.mw * n_pad), rec_count(n), rec_offset(n + 1);
+    std::vector<u32> win((size_t)2 * t.wpw * n_pad), endmask((size_t)2 * nP * t.mw * n_pad), impmask((size_t)2 * nP * t.mw * n_pad), rec_count(n), rec_offset(n + 1);
     std::vector<smx_primer_hit> phit((size_t)2 * nP * n_pad);
     std::vector<unsigned char> orient_hit((size_t)2 * nP * n_pad), flags(n);
     std::vector<u32> slot_count((size_t)2 * nP + 1, 0), ent_base((size_t)2 * nP * n_pad + 1), ent_read;
@@ -38,7 +38,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     b.packed2 = in->packed2; b.word_off = in->word_off; b.lengths = in->lengths;
     bool flagged = in->packed4 && in->off4 && in->packed4_words;
     b.packed4 = flagged ? in->packed4 : nullptr; b.off4 = flagged ? in->off4 : nullptr;
-    b.win = win.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.orient_hit = orient_hit.data();
+    b.win = win.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.impmask = impmask.data(); b.orient_hit = orient_hit.data();
     b.slot_count = slot_count.data(); b.ent_base = ent_base.data();
     b.rec_count = rec_count.data(); b.rec_offset = rec_offset.data();
     b.read_flags = flags.data(); b.counters = counters;
@@ -59,8 +59,8 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
             for (int p = 0; p < nP; ++p)
                 for (u32 r = 0; r < n; ++r) {
                     int nloc;
-                    if (t.use64) nloc = primer_search_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
-                    else nloc = primer_search_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_rcrev + p * 16, t.peq_fw + p * 16);
+                    if (t.use64) nloc = primer_search_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
+                    else nloc = primer_search_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
                     if (nloc) {
                         u32 slot = (u32)(s * nP + p);
                         write_entries(t, b, slot, r, slot_count[slot]);
@@ -70,6 +70,11 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         u32 max_entries = 0;
         for (u32 v : slot_count) max_entries = std::max(max_entries, v);
         if (max_entries > e_cap) { e_cap = max_entries; continue; }
+        for (u32 slot = 0; slot < (u32)(2 * nP); ++slot)
+            for (u32 e = 0; e < slot_count[slot]; ++e) {
+                const u64 *rev = t.peq_rcrev + (size_t)(slot % nP) * 16;
+                if (t.use64) primer_start_thread<u64>(t, b, slot, e, rev); else primer_start_thread<u32>(t, b, slot, e, rev);
+            }
         for (int s = 0; s < 2; ++s)
             for (int g = 0; g < t.n_bwords; ++g) {
                 const u32 *rows = t.beq + (size_t)t.bw_row[g] * 16;
