@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,71 +60,311 @@ template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) 
 
 }  // namespace
 
-struct smx_ctx {
-    int device = 0;
-    Tables t;
+// One pipeline lane: a stream plus every per-batch device buffer.  Lane 0 serves the resident API
+// (upload / run / download on a whole batch); smx_match_batch splits large batches into chunks that
+// rotate over all lanes so one chunk's H2D, another's kernels and a third's D2H overlap.
+constexpr int kLanes = 3;
+
+struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    // table storage
-    DevBuf<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
-    DevBuf<unsigned char> b_len, bw_len, bw_primer;
-    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
-    DevBuf<unsigned short> bw_list;
-    DevBuf<i32> pair_pool, spec_pool, spec_dense;
-    DevBuf<SlotSum> ssum;
-    int max_nb = 0;
-    // batch storage
     Batch b;
-    DevBuf<u32> packed2, lengths, packed4, win, endmask, impmask, rec_count, rec_offset, block_sums;
+    DevBuf<u32> packed2, lengths, packed4, win, endmask, impmask, rec_count, rec_offset, rec_offset_out, block_sums;
     DevBuf<u64> word_off, off4;
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
     DevBuf<smx_barcode_hit> bh_list;
     DevBuf<u32> slot_count, ent_base, ent_read, rec_extra, big_list;
     DevBuf<unsigned short> ent_pos;
-    DevBuf<smx_record> rec_stage, rec_pool;
-    u32 e_cap = 0, pool_cap = 0;
+    DevBuf<SlotSum> ssum;
+    DevBuf<smx_record> rec_stage, rec_pool, records;
     DevBuf<unsigned char> big_scratch;
-    DevBuf<smx_record> records;
-    DevBuf<unsigned long long> counters;   // 4 work counters + matched + (u32) overflow + (u32) total
+    DevBuf<unsigned long long> counters;   // 4 work counters + matched + (u32) overflow + (u32) total + hit overflow
+    u32 e_cap = 0, pool_cap = 0;
+    int hit_cap = 0;                        // hit sub-list capacity the lane's buffers are laid out for
+    unsigned long long *h_counters = nullptr;   // pinned: 8 counters
+    u32 *h_slot_counts = nullptr;               // pinned: 2 * SMX_MAX_PRIMERS
+    std::vector<u32> big_list_host;
     bool have_batch = false, have_results = false;
     u64 n_records = 0, n_matched = 0;
     unsigned long long work[4] = {0, 0, 0, 0};
-    float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
     int launches = 0;
+
+    void release() {
+        packed2.release(); lengths.release(); packed4.release(); win.release(); endmask.release(); impmask.release();
+        rec_count.release(); rec_offset.release(); rec_offset_out.release(); block_sums.release(); word_off.release();
+        off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
+        slot_count.release(); ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
+        ent_pos.release(); ssum.release(); rec_stage.release(); rec_pool.release(); records.release();
+        big_scratch.release(); counters.release();
+        if (h_counters) cudaFreeHost(h_counters);
+        if (h_slot_counts) cudaFreeHost(h_slot_counts);
+        h_counters = nullptr; h_slot_counts = nullptr;
+        for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    }
 };
 
-static cudaError_t ensure_entry_buffers(smx_ctx *c) {
+struct smx_ctx {
+    int device = 0;
+    Tables t;
+    // table storage
+    DevBuf<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
+    DevBuf<unsigned char> b_len, bw_len, bw_primer;
+    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
+    DevBuf<unsigned short> bw_list;
+    DevBuf<i32> pair_pool, spec_pool, spec_dense;
+    int max_nb = 0;
+    Lane lane[kLanes];
+    DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
+    DevBuf<unsigned char> l2_scratch;
+    u32 chunk_reads = 128 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK)
+    float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
+    int last_chunks = 0;
+};
+
+static cudaError_t lane_init(Lane &ln) {
+    cudaError_t e;
+    if (ln.stream) return cudaSuccess;
+    if ((e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (auto &ev : ln.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void **)&ln.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void **)&ln.h_slot_counts, 2 * SMX_MAX_PRIMERS * sizeof(u32), cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = ln.counters.ensure(8)) != cudaSuccess) return e;
+    memset(&ln.b, 0, sizeof(ln.b));
+    return cudaSuccess;
+}
+
+static cudaError_t ensure_entry_buffers(smx_ctx *c, Lane &ln) {
     const Tables &t = c->t;
     cudaError_t e;
-    if ((e = c->ent_read.ensure((size_t)2 * t.n_primers * c->e_cap)) != cudaSuccess) return e;
-    if ((e = c->ent_pos.ensure((size_t)2 * t.n_primers * c->e_cap)) != cudaSuccess) return e;
-    if ((e = c->bh_count.ensure((size_t)2 * t.n_bwords * c->e_cap + 1)) != cudaSuccess) return e;
-    if ((e = c->bh_list.ensure((size_t)2 * t.n_bwords * t.hit_cap * c->e_cap + 1)) != cudaSuccess) return e;
-    return c->rec_pool.ensure(c->pool_cap);
+    if ((e = ln.ent_read.ensure((size_t)2 * t.n_primers * ln.e_cap)) != cudaSuccess) return e;
+    if ((e = ln.ent_pos.ensure((size_t)2 * t.n_primers * ln.e_cap)) != cudaSuccess) return e;
+    if ((e = ln.bh_count.ensure((size_t)2 * t.n_bwords * ln.e_cap + 1)) != cudaSuccess) return e;
+    if ((e = ln.bh_list.ensure((size_t)2 * t.n_bwords * ln.hit_cap * ln.e_cap + 1)) != cudaSuccess) return e;
+    if ((e = ln.rec_pool.ensure(ln.pool_cap)) != cudaSuccess) return e;
+    Batch &b = ln.b;
+    b.e_cap = ln.e_cap; b.pool_cap = ln.pool_cap;
+    b.ent_read = ln.ent_read.p; b.ent_pos = ln.ent_pos.p; b.bh_count = ln.bh_count.p; b.bh_list = ln.bh_list.p;
+    b.rec_pool = ln.rec_pool.p;
+    return cudaSuccess;
 }
 
-static void bind_entry_buffers(smx_ctx *c) {
-    Batch &b = c->b;
-    b.e_cap = c->e_cap; b.pool_cap = c->pool_cap;
-    b.ent_read = c->ent_read.p; b.ent_pos = c->ent_pos.p; b.bh_count = c->bh_count.p; b.bh_list = c->bh_list.p;
-    b.rec_pool = c->rec_pool.p;
+// Tables as launched from this lane (the hit sub-list capacity is a per-lane layout parameter).
+static Tables lane_tables(const smx_ctx *c, const Lane &ln) {
+    Tables t = c->t;
+    t.hit_cap = ln.hit_cap;
+    return t;
 }
 
-// rec_count -> rec_offset (exclusive scan), flag counters, then one D2H of the 8 counters.
-static cudaError_t scan_and_count(smx_ctx *c, int &launches, unsigned long long host_counters[8]) {
-    Batch &b = c->b;
+// H2D of reads [r0, r1) of `in` onto the lane (asynchronous on the lane's stream) and binding of
+// every per-batch buffer.  `shared4`: device copy of the whole packed4 stream (pipelined mode) or
+// nullptr (the lane uploads it itself; only valid for r0 == 0, r1 == n_reads).
+static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1, const u32 *shared4) {
+    const Tables &t = c->t;
+    const u32 n = r1 - r0, n_pad = (n + 127u) & ~127u;
+    const int nP = t.n_primers;
+    const u64 w0 = in->word_off[r0];
+    const u64 w1 = (r1 < in->n_reads) ? std::min<u64>(in->word_off[r1] + 1, in->packed2_words) : in->packed2_words;
+    if (w1 < w0) return fail(SMX_ERR_ARG, "smx_batch: word_off is not ascending");
+    CU(lane_init(ln));
+    CU(ln.packed2.ensure(w1 - w0 + 2)); CU(ln.word_off.ensure(n)); CU(ln.lengths.ensure(n));
+    const bool flagged = in->packed4 && in->off4 && in->packed4_words;
+    if (flagged) { CU(ln.off4.ensure(n)); if (!shared4) CU(ln.packed4.ensure(in->packed4_words)); }
+    CU(ln.win.ensure((size_t)2 * t.wpw * n_pad));
+    CU(ln.phit.ensure((size_t)2 * nP * n_pad));
+    CU(ln.endmask.ensure((size_t)2 * nP * t.mw * n_pad));
+    CU(ln.impmask.ensure((size_t)2 * nP * t.mw * n_pad));
+    CU(ln.orient_hit.ensure((size_t)2 * nP * n_pad));
+    CU(ln.slot_count.ensure((size_t)2 * nP)); CU(ln.ent_base.ensure((size_t)2 * nP * n_pad));
+    CU(ln.ssum.ensure((size_t)2 * nP * n_pad));
+    if (ln.e_cap < n_pad) ln.e_cap = n_pad;
+    if (ln.pool_cap < n_pad / 8 + 1024) ln.pool_cap = n_pad / 8 + 1024;
+    if (ln.hit_cap < c->t.hit_cap) ln.hit_cap = c->t.hit_cap;
+    CU(ensure_entry_buffers(c, ln));
+    CU(ln.rec_stage.ensure(n_pad)); CU(ln.rec_extra.ensure(n_pad));
+    CU(ln.rec_count.ensure(n)); CU(ln.rec_offset.ensure((size_t)n + 1)); CU(ln.rec_offset_out.ensure((size_t)n + 1));
+    CU(ln.read_flags.ensure(n));
+    CU(ln.block_sums.ensure((n + kScanBlock - 1) / kScanBlock + 1));
+    cudaStream_t st = ln.stream;
+    CU(cudaMemcpyAsync(ln.packed2.p, in->packed2 + w0, (w1 - w0) * sizeof(u32), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ln.word_off.p, in->word_off + r0, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ln.lengths.p, in->lengths + r0, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, st));
+    if (flagged) {
+        if (!shared4)
+            CU(cudaMemcpyAsync(ln.packed4.p, in->packed4, in->packed4_words * sizeof(u32), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ln.off4.p, in->off4 + r0, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, st));
+    }
+    Batch &b = ln.b;
+    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len; b.word_base = w0; b.read_base = r0;
+    b.packed2 = ln.packed2.p; b.word_off = ln.word_off.p; b.lengths = ln.lengths.p;
+    b.packed4 = flagged ? (shared4 ? shared4 : ln.packed4.p) : nullptr; b.off4 = flagged ? ln.off4.p : nullptr;
+    b.win = ln.win.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
+    b.slot_count = ln.slot_count.p; b.ent_base = ln.ent_base.p; b.ssum = ln.ssum.p;
+    b.rec_stage = ln.rec_stage.p; b.rec_extra = ln.rec_extra.p;
+    b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
+    b.records = nullptr; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
+    ln.have_batch = true; ln.have_results = false;
+    ln.launches = 0;
+    return SMX_OK;
+}
+
+// rec_count -> rec_offset (exclusive scan), flag counters, then the asynchronous D2H of the counters.
+static cudaError_t enqueue_scan_and_count(Lane &ln) {
+    Batch &b = ln.b;
     const u32 n = b.n_reads;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = ln.stream;
     unsigned sblocks = (n + kScanBlock - 1) / kScanBlock;
-    k_scan_block_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p);
-    k_scan_spine<<<1, kScanBlock, 0, st>>>(c->block_sums.p, sblocks, (u32 *)(c->counters.p + 6));
-    k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, c->block_sums.p, b.rec_offset);
-    k_count_flags<<<(n + 255) / 256, 256, 0, st>>>(b.read_flags, n, c->counters.p + 4, (unsigned *)(c->counters.p + 5));
-    launches += 4;
-    cudaError_t e = cudaMemcpyAsync(host_counters, c->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(st);
+    k_scan_block_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, ln.block_sums.p);
+    k_scan_spine<<<1, kScanBlock, 0, st>>>(ln.block_sums.p, sblocks, (u32 *)(ln.counters.p + 6));
+    k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, ln.block_sums.p, b.rec_offset);
+    k_count_flags<<<(n + 255) / 256, 256, 0, st>>>(b.read_flags, n, ln.counters.p + 4, (unsigned *)(ln.counters.p + 5));
+    ln.launches += 4;
+    return cudaMemcpyAsync(ln.h_counters, ln.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+}
+
+// Enqueues stages `from`..3 (0 = from window staging) through the scan and the counter read-back.
+// Nothing here synchronises; lane_resolve() looks at the counters.
+static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
+    const Tables t = lane_tables(c, ln);
+    Batch &b = ln.b;
+    const u32 n = b.n_reads;
+    const int nP = t.n_primers;
+    cudaStream_t st = ln.stream;
+    const unsigned blocks = (n + 127) / 128;
+    if (from <= 0) {
+        CU(cudaMemsetAsync(ln.counters.p, 0, 8 * sizeof(unsigned long long), st));
+        if (timed) CU(cudaEventRecord(ln.ev[0], st));
+        dim3 grid(blocks, 2 * t.wpw);
+        k_stage_windows<<<grid, 128, 0, st>>>(t, b);
+        ++ln.launches;
+    }
+    if (from <= 1) {   // stage 1
+        CU(cudaMemsetAsync(ln.slot_count.p, 0, (size_t)2 * nP * sizeof(u32), st));
+        CU(cudaMemsetAsync(ln.counters.p, 0, sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p + 2, 0, sizeof(unsigned long long), st));
+        if (timed) CU(cudaEventRecord(ln.ev[1], st));
+        dim3 grid(blocks, 2 * nP);
+        if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(t, b);
+        else k_primer_search<u32><<<grid, 128, 0, st>>>(t, b);
+        dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
+        if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, st>>>(t, b);
+        else k_primer_start<u32><<<sgrid, 128, 0, st>>>(t, b);
+        ln.launches += 2;
+    }
+    if (from <= 2) {   // stage 2
+        CU(cudaMemsetAsync(ln.counters.p + 1, 0, sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p + 3, 0, sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p + 7, 0, sizeof(unsigned long long), st));
+        if (timed) CU(cudaEventRecord(ln.ev[2], st));
+        if (t.n_bwords) {
+            dim3 grid((b.e_cap + 127) / 128, 2 * t.n_bwords);
+            switch (t.k_idx) {
+#define SMX_K2(KK) case KK: k_barcode_bitsliced<KK><<<grid, 128, 0, st>>>(t, b); break;
+                SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
+#undef SMX_K2
+                default: return fail(SMX_ERR_INTERNAL, "unsupported k_idx");
+            }
+            ++ln.launches;
+        }
+    }
+    // stage 3: slot digests, single-pass selection, scan
+    CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
+    if (timed) CU(cudaEventRecord(ln.ev[3], st));
+    {
+        dim3 sgrid((n + 255) / 256, 2 * nP);
+        k_slot_summary<<<sgrid, 256, 0, st>>>(t, b);
+    }
+    if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(t, b); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
+    ln.launches += 2;
+    CU(cudaMemcpyAsync(ln.h_slot_counts, ln.slot_count.p, (size_t)2 * nP * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CU(enqueue_scan_and_count(ln));
+    return SMX_OK;
+}
+
+// Waits for the lane's counters and resolves every capacity overflow by re-running the affected
+// stages with larger buffers (never "unsupported"); runs the second selection pass for reads that
+// overflowed the thread-local group storage.  On return n_records / n_matched / work are final.
+static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
+    Batch &b = ln.b;
+    const u32 n = b.n_reads;
+    const int nP = c->t.n_primers;
+    cudaStream_t st = ln.stream;
+    for (;;) {
+        CU(cudaStreamSynchronize(st));
+        unsigned long long *hc = ln.h_counters;
+        u32 max_entries = 0;
+        for (int i = 0; i < 2 * nP; ++i) max_entries = std::max(max_entries, ln.h_slot_counts[i]);
+        int from = -1;
+        if (max_entries > ln.e_cap) {
+            ln.e_cap = (max_entries + 127u) & ~127u;
+            from = 1;
+        } else if (hc[7]) {
+            if (ln.hit_cap >= kMaxWordHits) return fail(SMX_ERR_INTERNAL, "hit list overflow at maximum capacity");
+            ln.hit_cap = std::min(kMaxWordHits, ln.hit_cap * 4);
+            if (c->t.hit_cap < ln.hit_cap) c->t.hit_cap = ln.hit_cap;     // later uploads start there
+            from = 2;
+        } else if ((u32)(hc[6] >> 32) > ln.pool_cap) {
+            ln.pool_cap = (u32)(hc[6] >> 32) + 1024;
+            from = 3;
+        }
+        if (from < 0) break;
+        CU(ensure_entry_buffers(c, ln));
+        int rc = lane_enqueue(c, ln, from, timed);
+        if (rc) return rc;
+    }
+    ln.big_list_host.clear();
+    if ((u32)ln.h_counters[5]) {
+        // some reads overflowed the thread-local group storage (or emit many records): second GPU
+        // pass for those reads only, on kBigGroups-entry global scratch
+        const Tables t = lane_tables(c, ln);
+        std::vector<unsigned char> flags(n);
+        CU(cudaMemcpyAsync(flags.data(), b.read_flags, n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<u32> &big_list = ln.big_list_host;
+        for (u32 r = 0; r < n; ++r) if (flags[r] & 2) big_list.push_back(r);
+        CU(ln.big_list.ensure(big_list.size()));
+        CU(cudaMemcpyAsync(ln.big_list.p, big_list.data(), big_list.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+        const size_t chunk = 512;
+        CU(ln.big_scratch.ensure(std::min(chunk, big_list.size()) * kBigScratchBytes));
+        for (size_t off = 0; off < big_list.size(); off += chunk) {
+            u32 cnt = (u32)std::min(chunk, big_list.size() - off);
+            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 0);
+            ++ln.launches;
+        }
+        CU(cudaMemsetAsync(ln.counters.p + 4, 0, 2 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p + 6, 0, sizeof(u32), st));
+        CU(enqueue_scan_and_count(ln));
+        CU(cudaStreamSynchronize(st));
+        if ((u32)(ln.h_counters[5] >> 32))
+            return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceed %d dereplication groups",
+                        (unsigned)(ln.h_counters[5] >> 32), kBigGroups);
+    }
+    ln.n_records = (u32)ln.h_counters[6];
+    ln.n_matched = ln.h_counters[4];
+    for (int i = 0; i < 4; ++i) ln.work[i] = ln.h_counters[i];
+    return SMX_OK;
+}
+
+// Read-ordered compaction of the lane's records (asynchronous).
+static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
+    const Tables t = lane_tables(c, ln);
+    Batch &b = ln.b;
+    cudaStream_t st = ln.stream;
+    CU(ln.records.ensure(ln.n_records + 1));
+    b.records = ln.records.p;
+    k_compact_records<<<(unsigned)(((u64)b.n_reads * 4 + 255) / 256), 256, 0, st>>>(t, b, rec_base, ln.rec_offset_out.p);
+    ++ln.launches;
+    const size_t chunk = 512;
+    for (size_t off = 0; off < ln.big_list_host.size(); off += chunk) {
+        u32 cnt = (u32)std::min(chunk, ln.big_list_host.size() - off);
+        k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 1);
+        ++ln.launches;
+    }
+    if (timed) CU(cudaEventRecord(ln.ev[4], st));
+    CU(cudaGetLastError());
+    ln.have_results = true;
+    return SMX_OK;
 }
 
 extern "C" {
@@ -141,20 +382,14 @@ int smx_device_count(void) {
 void smx_destroy(smx_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &ln : c->lane) if (ln.stream) cudaStreamSynchronize(ln.stream);
+    for (auto &ln : c->lane) ln.release();
     c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bw_len.release(); c->bw_primer.release(); c->bw_row.release();
-    c->bw_valid.release(); c->beq.release(); c->bw_list.release(); c->bh_count.release(); c->bh_list.release();
-    c->slot_count.release(); c->ent_base.release(); c->ent_read.release(); c->ent_pos.release();
-    c->rec_extra.release(); c->rec_stage.release(); c->rec_pool.release(); c->big_list.release(); c->big_scratch.release();
+    c->bw_valid.release(); c->beq.release(); c->bw_list.release();
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
-    c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release(); c->ssum.release();
-    c->packed2.release(); c->lengths.release(); c->packed4.release(); c->win.release(); c->endmask.release(); c->impmask.release();
-    c->rec_count.release(); c->rec_offset.release(); c->block_sums.release(); c->word_off.release();
-    c->off4.release(); c->phit.release(); c->orient_hit.release(); c->read_flags.release();
-    c->records.release(); c->counters.release();
-    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release();
+    c->shared_packed4.release(); c->l2_scratch.release();
     delete c;
 }
 
@@ -163,6 +398,8 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     *out = nullptr;
     HostTables ht;
     if (!ht.build(tb, pr)) return fail(SMX_ERR_ARG, "smx_create: %s", ht.error.c_str());
+    if (ht.t.k_idx > 8)
+        return fail(SMX_ERR_ARG, "smx_create: barcode distance threshold %d exceeds the supported 8", ht.t.k_idx);
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) {
@@ -185,8 +422,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         }                                                                                             \
     } while (0)
     CUC(cudaSetDevice(device));
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto &e : c->ev) CUC(cudaEventCreate(&e));
+    CUC(lane_init(c->lane[0]));
     CUC(upload(c->peq_rc, ht.peq_rc)); CUC(upload(c->peq_rcrev, ht.peq_rcrev)); CUC(upload(c->peq_fw, ht.peq_fw));
     CUC(upload(c->b_len, ht.b_len)); CUC(upload(c->pb_barcode, ht.pb_barcode));
     CUC(upload(c->bw_len, ht.bw_len)); CUC(upload(c->bw_primer, ht.bw_primer)); CUC(upload(c->bw_row, ht.bw_row));
@@ -196,19 +432,18 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->spec_row, ht.spec_row)); CUC(upload(c->spec_p1, ht.spec_p1)); CUC(upload(c->spec_p2, ht.spec_p2));
     CUC(upload(c->spec_pool, ht.spec_pool));
     CUC(upload(c->spec_dense, ht.spec_dense));
-    CUC(c->counters.ensure(8));
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
     ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,
                     c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
                     c->spec_row.p, c->spec_p1.p, c->spec_p2.p, c->spec_pool.p);
     c->t = ht.t;
     c->t.spec_dense = ht.spec_dense.empty() ? nullptr : c->spec_dense.p;
-    memset(&c->b, 0, sizeof(c->b));
-    if (ht.t.k_idx > 8) {
-        smx_destroy(c);
-        return fail(SMX_ERR_ARG, "smx_create: barcode distance threshold %d exceeds the supported 8", ht.t.k_idx);
-    }
 #undef CUC
+    if (const char *env = getenv("SMX_PIPELINE_CHUNK")) {
+        long v = atol(env);
+        if (v >= 128) c->chunk_reads = (u32)std::min<long>(v, 1L << 30);
+        else if (v == 0) c->chunk_reads = 0;                   // 0 disables the pipelined form
+    }
     *out = c;
     return SMX_OK;
 }
@@ -220,210 +455,63 @@ uint64_t smx_result_bound(const smx_ctx *c, uint32_t n_reads) {
     return (uint64_t)n_reads * 2 + 1024;
 }
 
-int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
-    if (!c || !in) return fail(SMX_ERR_ARG, "smx_upload_batch: null argument");
-    if (in->n_reads == 0) return fail(SMX_ERR_ARG, "smx_upload_batch: empty batch");
+static int check_batch(const smx_ctx *c, const smx_batch *in, const char *who) {
+    if (!c || !in) return fail(SMX_ERR_ARG, "%s: null argument", who);
+    if (in->n_reads == 0) return fail(SMX_ERR_ARG, "%s: empty batch", who);
+    if (!in->packed2 || !in->word_off || !in->lengths) return fail(SMX_ERR_ARG, "%s: null batch array", who);
     if (in->clip_len && (int)in->clip_len < c->t.L)
-        return fail(SMX_ERR_ARG, "smx_upload_batch: clip_len %u is below search_len %d", in->clip_len, c->t.L);
+        return fail(SMX_ERR_ARG, "%s: clip_len %u is below search_len %d", who, in->clip_len, c->t.L);
     if ((in->packed4 == nullptr) != (in->off4 == nullptr) && in->packed4_words)
-        return fail(SMX_ERR_ARG, "smx_upload_batch: packed4 and off4 must be given together");
+        return fail(SMX_ERR_ARG, "%s: packed4 and off4 must be given together", who);
+    return SMX_OK;
+}
+
+int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
+    int rc = check_batch(c, in, "smx_upload_batch");
+    if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    const Tables &t = c->t;
-    const u32 n = in->n_reads, n_pad = (n + 127u) & ~127u;
-    const int nP = t.n_primers;
-    CU(c->packed2.ensure(in->packed2_words + 1)); CU(c->word_off.ensure(n)); CU(c->lengths.ensure(n));
-    bool flagged = in->packed4 && in->off4 && in->packed4_words;
-    if (flagged) { CU(c->packed4.ensure(in->packed4_words)); CU(c->off4.ensure(n)); }
-    CU(c->win.ensure((size_t)2 * t.wpw * n_pad));
-    CU(c->phit.ensure((size_t)2 * nP * n_pad));
-    CU(c->endmask.ensure((size_t)2 * nP * t.mw * n_pad));
-    CU(c->impmask.ensure((size_t)2 * nP * t.mw * n_pad));
-    CU(c->orient_hit.ensure((size_t)2 * nP * n_pad));
-    CU(c->slot_count.ensure((size_t)2 * nP)); CU(c->ent_base.ensure((size_t)2 * nP * n_pad));
-    CU(c->ssum.ensure((size_t)2 * nP * n_pad));
-    if (c->e_cap < n_pad) c->e_cap = n_pad;
-    if (c->pool_cap < n_pad / 8 + 1024) c->pool_cap = n_pad / 8 + 1024;
-    CU(ensure_entry_buffers(c));
-    CU(c->rec_stage.ensure(n_pad)); CU(c->rec_extra.ensure(n_pad)); CU(c->rec_pool.ensure(c->pool_cap));
-    CU(c->rec_count.ensure(n)); CU(c->rec_offset.ensure((size_t)n + 1)); CU(c->read_flags.ensure(n));
-    CU(c->block_sums.ensure((n + kScanBlock - 1) / kScanBlock + 1));
-    CU(cudaMemcpyAsync(c->packed2.p, in->packed2, in->packed2_words * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->word_off.p, in->word_off, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->lengths.p, in->lengths, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-    if (flagged) {
-        CU(cudaMemcpyAsync(c->packed4.p, in->packed4, in->packed4_words * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->off4.p, in->off4, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    }
-    Batch &b = c->b;
-    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len;
-    b.packed2 = c->packed2.p; b.word_off = c->word_off.p; b.lengths = c->lengths.p;
-    b.packed4 = flagged ? c->packed4.p : nullptr; b.off4 = flagged ? c->off4.p : nullptr;
-    b.win = c->win.p; b.phit = c->phit.p; b.endmask = c->endmask.p; b.impmask = c->impmask.p; b.orient_hit = c->orient_hit.p;
-    b.slot_count = c->slot_count.p; b.ent_base = c->ent_base.p; b.ssum = c->ssum.p;
-    b.rec_stage = c->rec_stage.p; b.rec_extra = c->rec_extra.p;
-    bind_entry_buffers(c);
-    b.rec_count = c->rec_count.p; b.rec_offset = c->rec_offset.p;
-    b.records = nullptr; b.read_flags = c->read_flags.p; b.counters = c->counters.p;
-    CU(cudaStreamSynchronize(c->stream));
-    c->have_batch = true; c->have_results = false;
+    Lane &ln = c->lane[0];
+    rc = lane_upload(c, ln, in, 0, in->n_reads, nullptr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ln.stream));
     return SMX_OK;
 }
 
 int smx_run_resident(smx_ctx *c) {
     if (!c) return fail(SMX_ERR_ARG, "smx_run_resident: null context");
-    if (!c->have_batch) return fail(SMX_ERR_ARG, "smx_run_resident: no batch uploaded");
+    Lane &ln = c->lane[0];
+    if (!ln.have_batch) return fail(SMX_ERR_ARG, "smx_run_resident: no batch uploaded");
     CU(cudaSetDevice(c->device));
-    const Tables &t = c->t;
-    Batch &b = c->b;
-    const u32 n = b.n_reads;
-    const int nP = t.n_primers;
-    cudaStream_t st = c->stream;
-    int launches = 0;
-    CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
-    CU(cudaEventRecord(c->ev[0], st));
-    {   // stage 0
-        dim3 grid((n + 127) / 128, 2 * t.wpw);
-        k_stage_windows<<<grid, 128, 0, st>>>(b);
-        ++launches;
-    }
-    const unsigned blocks = (n + 127) / 128;
-    unsigned long long host_counters[8];
-    std::vector<u32> slot_counts((size_t)2 * nP);
-    int from = 1;                      // stage to (re)start from
-    for (;;) {
-        if (from <= 1) {   // stage 1
-            CU(cudaMemsetAsync(c->slot_count.p, 0, (size_t)2 * nP * sizeof(u32), st));
-            CU(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));
-            CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned long long), st));
-            CU(cudaEventRecord(c->ev[1], st));
-            dim3 grid(blocks, 2 * nP);
-            if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(b);
-            else k_primer_search<u32><<<grid, 128, 0, st>>>(b);
-            dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
-            if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, st>>>(b);
-            else k_primer_start<u32><<<sgrid, 128, 0, st>>>(b);
-            launches += 2;
-        }
-        if (from <= 2) {   // stage 2
-            CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned long long), st));
-            CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned long long), st));
-            CU(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(unsigned long long), st));
-            CU(cudaEventRecord(c->ev[2], st));
-            if (t.n_bwords) {
-                dim3 grid((b.e_cap + 127) / 128, 2 * t.n_bwords);
-                switch (t.k_idx) {
-#define SMX_K2(KK) case KK: k_barcode_bitsliced<KK><<<grid, 128, 0, st>>>(b); break;
-                    SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
-#undef SMX_K2
-                    default: return fail(SMX_ERR_INTERNAL, "unsupported k_idx");
-                }
-                ++launches;
-            }
-        }
-        // stage 3: single-pass selection, scan
-        CU(cudaMemsetAsync(c->counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
-        CU(cudaEventRecord(c->ev[3], st));
-        {
-            dim3 sgrid((n + 255) / 256, 2 * nP);
-            k_slot_summary<<<sgrid, 256, 0, st>>>(b);
-        }
-        if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(b); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(b);
-        launches += 2;
-        CU(cudaMemcpyAsync(slot_counts.data(), c->slot_count.p, slot_counts.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CU(scan_and_count(c, launches, host_counters));
-        // capacity checks: every overflow is resolved by a second GPU pass with larger buffers
-        u32 max_entries = 0;
-        for (u32 v : slot_counts) max_entries = std::max(max_entries, v);
-        if (max_entries > c->e_cap) {
-            c->e_cap = (max_entries + 127u) & ~127u;
-            CU(ensure_entry_buffers(c)); bind_entry_buffers(c);
-            from = 1;
-            continue;
-        }
-        if (host_counters[7]) {
-            if (c->t.hit_cap >= kMaxWordHits) return fail(SMX_ERR_INTERNAL, "hit list overflow at maximum capacity");
-            c->t.hit_cap = std::min(kMaxWordHits, c->t.hit_cap * 4);
-            CU(ensure_entry_buffers(c)); bind_entry_buffers(c);
-            CU(cudaMemcpyToSymbolAsync(c_tables, &c->t, sizeof(Tables), 0, cudaMemcpyHostToDevice, st));
-            from = 2;
-            continue;
-        }
-        u32 pool_used = (u32)(host_counters[6] >> 32);
-        if (pool_used > c->pool_cap) {
-            c->pool_cap = pool_used + 1024;
-            CU(ensure_entry_buffers(c)); bind_entry_buffers(c);
-            from = 3;
-            continue;
-        }
-        break;
-    }
-    std::vector<u32> big_list;
-    if ((u32)host_counters[5]) {
-        // some reads overflowed the thread-local group storage (or emit many records): second GPU
-        // pass for those reads only, on kBigGroups-entry global scratch
-        std::vector<unsigned char> flags(n);
-        CU(cudaMemcpy(flags.data(), b.read_flags, n, cudaMemcpyDeviceToHost));
-        for (u32 r = 0; r < n; ++r) if (flags[r] & 2) big_list.push_back(r);
-        CU(c->big_list.ensure(big_list.size()));
-        CU(cudaMemcpy(c->big_list.p, big_list.data(), big_list.size() * sizeof(u32), cudaMemcpyHostToDevice));
-        const size_t chunk = 512;
-        CU(c->big_scratch.ensure(std::min(chunk, big_list.size()) * kBigScratchBytes));
-        for (size_t off = 0; off < big_list.size(); off += chunk) {
-            u32 cnt = (u32)std::min(chunk, big_list.size() - off);
-            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(b, c->big_list.p + off, cnt, c->big_scratch.p, 0);
-            ++launches;
-        }
-        CU(cudaMemsetAsync(c->counters.p + 4, 0, 2 * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(c->counters.p + 6, 0, sizeof(u32), st));
-        CU(scan_and_count(c, launches, host_counters));
-        if ((u32)(host_counters[5] >> 32))
-            return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceed %d dereplication groups",
-                        (unsigned)(host_counters[5] >> 32), kBigGroups);
-    }
-    {
-        u64 total = (u32)host_counters[6];
-        CU(c->records.ensure(total + 1));
-        b.records = c->records.p;
-        k_compact_records<<<(n + 255) / 256, 256, 0, st>>>(b);
-        ++launches;
-        const size_t chunk = 512;
-        for (size_t off = 0; off < big_list.size(); off += chunk) {
-            u32 cnt = (u32)std::min(chunk, big_list.size() - off);
-            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(b, c->big_list.p + off, cnt, c->big_scratch.p, 1);
-            ++launches;
-        }
-        c->n_records = total;
-        c->n_matched = host_counters[4];
-        for (int i = 0; i < 4; ++i) c->work[i] = host_counters[i];
-    }
-    CU(cudaEventRecord(c->ev[4], st));
-    CU(cudaStreamSynchronize(st));
+    ln.launches = 0;
+    int rc = lane_enqueue(c, ln, 0, true);
+    if (rc) return rc;
+    if ((rc = lane_resolve(c, ln, true))) return rc;
+    if ((rc = lane_compact(c, ln, 0, true))) return rc;
+    CU(cudaStreamSynchronize(ln.stream));
     CU(cudaGetLastError());
-    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
-    CU(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[4]));
-    c->launches = launches;
-    c->have_results = true;
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&c->stage_ms[i], ln.ev[i], ln.ev[i + 1]));
+    CU(cudaEventElapsedTime(&c->total_ms, ln.ev[0], ln.ev[4]));
     return SMX_OK;
 }
 
 int smx_download_results(smx_ctx *c, smx_results *out) {
     if (!c || !out) return fail(SMX_ERR_ARG, "smx_download_results: null argument");
-    if (!c->have_results) return fail(SMX_ERR_ARG, "smx_download_results: nothing to download");
+    Lane &ln = c->lane[0];
+    if (!ln.have_results) return fail(SMX_ERR_ARG, "smx_download_results: nothing to download");
     CU(cudaSetDevice(c->device));
-    const Batch &b = c->b;
-    const Tables &t = c->t;
+    const Batch &b = ln.b;
+    const Tables t = lane_tables(c, ln);
     const u32 n = b.n_reads;
-    out->n_records = c->n_records;
-    out->n_matched = c->n_matched;
-    if (c->n_records > out->records_cap)
+    out->n_records = ln.n_records;
+    out->n_matched = ln.n_matched;
+    if (ln.n_records > out->records_cap)
         return fail(SMX_ERR_CAPACITY, "smx_download_results: %llu records, capacity %llu",
-                    (unsigned long long)c->n_records, (unsigned long long)out->records_cap);
-    cudaStream_t st = c->stream;
+                    (unsigned long long)ln.n_records, (unsigned long long)out->records_cap);
+    cudaStream_t st = ln.stream;
     if (out->rec_offset)
         CU(cudaMemcpyAsync(out->rec_offset, b.rec_offset, ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    if (out->records && c->n_records)
-        CU(cudaMemcpyAsync(out->records, b.records, c->n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
+    if (out->records && ln.n_records)
+        CU(cudaMemcpyAsync(out->records, b.records, ln.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
     // level-1 detail is stored padded ([slot][n_pad]) on the device and returned dense ([slot][n])
     if (out->primer_hits)
         CU(cudaMemcpy2DAsync(out->primer_hits, (size_t)n * sizeof(smx_primer_hit), b.phit,
@@ -472,13 +560,98 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     return SMX_OK;
 }
 
+// Pipelined form of the whole path for large batches: the reads are cut into chunks that rotate
+// over kLanes lanes (stream + buffers each), so chunk i+1's H2D, chunk i's kernels and chunk i-1's
+// D2H run concurrently (two copy engines + the SMs).  Results land in the caller's arrays exactly
+// as the one-shot form writes them.
+static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *out) {
+    const u32 n = in->n_reads, chunk = c->chunk_reads;
+    const u32 n_chunks = (n + chunk - 1) / chunk;
+    const u32 per = (((n + n_chunks - 1) / n_chunks) + 127u) & ~127u;      // even split, 128-read aligned
+    const u32 *shared4 = nullptr;
+    if (in->packed4 && in->off4 && in->packed4_words) {
+        CU(c->shared_packed4.ensure(in->packed4_words));
+        CU(cudaMemcpy(c->shared_packed4.p, in->packed4, in->packed4_words * sizeof(u32), cudaMemcpyHostToDevice));
+        shared4 = c->shared_packed4.p;
+    }
+    u64 rec_base = 0, matched = 0;
+    bool overflow = false;
+    int rc = SMX_OK;
+    auto bounds = [&](u32 i, u32 &r0, u32 &r1) { r0 = std::min<u64>((u64)i * per, n); r1 = std::min<u64>((u64)(i + 1) * per, n); };
+    auto finish = [&](u32 i) -> int {
+        Lane &ln = c->lane[i % kLanes];
+        u32 r0, r1;
+        bounds(i, r0, r1);
+        int r = lane_resolve(c, ln, false);
+        if (r) return r;
+        if (rec_base + ln.n_records > out->records_cap || rec_base + ln.n_records > 0xFFFFFFFFull) overflow = true;
+        if (!overflow) {
+            if ((r = lane_compact(c, ln, (u32)rec_base, false))) return r;
+            if (out->rec_offset)
+                CU(cudaMemcpyAsync(out->rec_offset + r0, ln.rec_offset_out.p, (size_t)(r1 - r0) * sizeof(u32),
+                                   cudaMemcpyDeviceToHost, ln.stream));
+            if (out->records && ln.n_records)
+                CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, ln.n_records * sizeof(smx_record),
+                                   cudaMemcpyDeviceToHost, ln.stream));
+        }
+        rec_base += ln.n_records;
+        matched += ln.n_matched;
+        return SMX_OK;
+    };
+    u32 issued = 0, finished = 0;
+    for (; issued < n_chunks && rc == SMX_OK; ++issued) {
+        // a lane is reused only after its previous chunk has been finished (stream order covers the rest)
+        while (rc == SMX_OK && issued - finished >= (u32)kLanes) rc = finish(finished++);
+        if (rc) break;
+        Lane &ln = c->lane[issued % kLanes];
+        u32 r0, r1;
+        bounds(issued, r0, r1);
+        if (r0 >= r1) { ln.have_batch = false; continue; }
+        if ((rc = lane_upload(c, ln, in, r0, r1, shared4))) break;
+        if ((rc = lane_enqueue(c, ln, 0, false))) break;
+        // keep at most kLanes - 1 chunks ahead so the finished chunk's D2H starts while the next computes
+        while (rc == SMX_OK && issued + 1 - finished >= (u32)kLanes) rc = finish(finished++);
+    }
+    while (rc == SMX_OK && finished < issued) rc = finish(finished++);
+    for (auto &ln : c->lane) if (ln.stream) cudaStreamSynchronize(ln.stream);
+    c->lane[0].have_batch = false; c->lane[0].have_results = false;     // the resident API needs a fresh upload
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    out->n_records = rec_base;
+    out->n_matched = matched;
+    c->last_chunks = (int)n_chunks;
+    if (overflow)
+        return fail(SMX_ERR_CAPACITY, "smx_match_batch: %llu records, capacity %llu",
+                    (unsigned long long)rec_base, (unsigned long long)out->records_cap);
+    if (out->rec_offset) out->rec_offset[n] = (u32)rec_base;
+    return SMX_OK;
+}
+
 int smx_match_batch(smx_ctx *c, const smx_batch *in, smx_results *out) {
-    int rc = smx_upload_batch(c, in);
+    if (!out) return fail(SMX_ERR_ARG, "smx_match_batch: null argument");
+    int rc = check_batch(c, in, "smx_match_batch");
+    if (rc) return rc;
+    const bool detail = out->primer_hits || out->endmask_bits || out->barcode_hits;
+    if (!detail && c->chunk_reads && in->n_reads >= 2 * (u64)c->chunk_reads) {
+        CU(cudaSetDevice(c->device));
+        return match_batch_pipelined(c, in, out);
+    }
+    c->last_chunks = 1;
+    rc = smx_upload_batch(c, in);
     if (rc) return rc;
     rc = smx_run_resident(c);
     if (rc) return rc;
     return smx_download_results(c, out);
 }
+
+int smx_set_pipeline_chunk(smx_ctx *c, uint32_t reads_per_chunk) {
+    if (!c) return fail(SMX_ERR_ARG, "smx_set_pipeline_chunk: null context");
+    if (reads_per_chunk && reads_per_chunk < 128) return fail(SMX_ERR_ARG, "smx_set_pipeline_chunk: chunk below 128 reads");
+    c->chunk_reads = reads_per_chunk;
+    return SMX_OK;
+}
+
+int smx_last_chunk_count(const smx_ctx *c) { return c ? c->last_chunks : 0; }
 
 int smx_last_timing(const smx_ctx *c, float *total_ms, float stage_ms[4]) {
     if (!c) return fail(SMX_ERR_ARG, "smx_last_timing: null context");
@@ -487,12 +660,18 @@ int smx_last_timing(const smx_ctx *c, float *total_ms, float stage_ms[4]) {
     return SMX_OK;
 }
 
-int smx_last_launch_count(const smx_ctx *c) { return c ? c->launches : 0; }
+int smx_last_launch_count(const smx_ctx *c) {
+    if (!c) return 0;
+    int total = 0;
+    for (const auto &ln : c->lane) total += ln.launches;
+    return total;
+}
 
 int smx_last_work(const smx_ctx *c, uint64_t cells[2], uint64_t wordcols[2]) {
-    if (!c || !c->have_results) return fail(SMX_ERR_ARG, "smx_last_work: no results");
-    cells[0] = c->work[0]; cells[1] = c->work[1];
-    wordcols[0] = c->work[2]; wordcols[1] = c->work[3];
+    if (!c || !c->lane[0].have_results) return fail(SMX_ERR_ARG, "smx_last_work: no results");
+    const Lane &ln = c->lane[0];
+    cells[0] = ln.work[0]; cells[1] = ln.work[1];
+    wordcols[0] = ln.work[2]; wordcols[1] = ln.work[3];
     return SMX_OK;
 }
 
@@ -561,9 +740,9 @@ int smx_flush_l2(smx_ctx *c) {
     if (!c) return fail(SMX_ERR_ARG, "smx_flush_l2: null context");
     CU(cudaSetDevice(c->device));
     const size_t bytes = 512ull << 20;
-    CU(c->big_scratch.ensure(bytes));
-    CU(cudaMemsetAsync(c->big_scratch.p, 0x5a, bytes, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(c->l2_scratch.ensure(bytes));
+    CU(cudaMemsetAsync(c->l2_scratch.p, 0x5a, bytes, c->lane[0].stream));
+    CU(cudaStreamSynchronize(c->lane[0].stream));
     return SMX_OK;
 }
 

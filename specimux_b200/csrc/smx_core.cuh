@@ -205,6 +205,8 @@ struct Batch {
     const u32 *packed4;
     const u64 *off4;         // nullptr when no read is flagged
     u32 clip;                // 0, or reads longer than 2*clip are stored as head clip + tail clip bases
+    u64 word_base;           // word_off values are absolute stream offsets; packed2[0] is stream word word_base
+    u32 read_base;           // index of this (sub-)batch's read 0 in the caller's batch (smx_record.read)
     u32 *win;                // staged 4-bit windows [(strand*wpw + w) * n_pad + read]
     // level-1 results
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
@@ -267,7 +269,7 @@ SMX_HD int sym_at(const Batch &b, u32 r, int strand, int x, int n) {
         return (int)((w >> (4 * (xs & 7))) & 15);
     }
     int i = stored_pos(b, strand ? n - 1 - x : x, n);
-    u32 w = b.packed2[b.word_off[r] + (u64)(i >> 4)];
+    u32 w = b.packed2[b.word_off[r] - b.word_base + (u64)(i >> 4)];
     int c = (int)((w >> (2 * (i & 15))) & 3);
     return strand ? 3 - c : c;
 }
@@ -564,7 +566,7 @@ SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &ov
     }
     if (em.out && em.count < em.cap) {
         smx_record &r = em.out[em.count];
-        r.read = c.read;
+        r.read = c.read + c.b->read_base;
         r.reverse = (unsigned char)cd.rc;
         r.candidate = (unsigned char)cand_idx;
         r.dist[0] = (signed char)(m1 ? e1.pd : -1);

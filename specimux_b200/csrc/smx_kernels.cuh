@@ -35,7 +35,7 @@ SMX_HD void stage_window_word(const Tables &t, const Batch &b, u32 read, int str
             int x0 = g.woff + 8 * w;                          // strand coordinate of symbol 0
             int first = strand ? (n - 1 - x0) - 7 : stored_pos(b, x0, n);   // stored index of the lowest base needed
             int lo = first < 0 ? 0 : first;
-            const u32 *src = b.packed2 + b.word_off[read] + (u64)(lo >> 4);
+            const u32 *src = b.packed2 + (b.word_off[read] - b.word_base) + (u64)(lo >> 4);
             u64 pair = (u64)src[0] | ((u64)src[1] << 32);
             u32 v = (u32)(pair >> (2 * (lo & 15))) & 0xFFFFu;
             if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below
@@ -490,9 +490,11 @@ SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u
 // __global__ wrappers.  Tables live in __constant__ memory, Peq masks are staged once per block
 // in shared memory.
 
-__constant__ Tables c_tables;
+// Tables and Batch travel as __grid_constant__ kernel parameters (constant bank, per launch), so
+// several contexts / pipeline lanes can be in flight on one device without sharing a symbol.
+#define SMX_KARGS const __grid_constant__ Tables c_tables, const __grid_constant__ Batch b
 
-__global__ void k_stage_windows(Batch b) {
+__global__ void k_stage_windows(SMX_KARGS) {
     // grid: x over reads, y over (strand, word)
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     if (read >= b.n_reads) return;
@@ -501,7 +503,7 @@ __global__ void k_stage_windows(Batch b) {
 }
 
 template <typename W>
-__global__ void __launch_bounds__(128) k_primer_search(Batch b) {
+__global__ void __launch_bounds__(128) k_primer_search(SMX_KARGS) {
     // grid: x over reads, y = strand * n_primers + primer
     __shared__ u64 s_peq[3][16];
     const int primer = blockIdx.y % c_tables.n_primers, strand = blockIdx.y / c_tables.n_primers;
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(128) k_primer_search(Batch b) {
 
 // Start recovery over the compact work-entry lists (full warps instead of the ~50 % matched lanes).
 template <typename W>
-__global__ void __launch_bounds__(128) k_primer_start(Batch b) {
+__global__ void __launch_bounds__(128) k_primer_start(SMX_KARGS) {
     __shared__ u64 s_rev[16];
     const u32 slot = blockIdx.y;
     u32 cnt = b.slot_count[slot];
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(128) k_primer_start(Batch b) {
 
 // One thread per (matched slot entry, bword); the bword's bit-sliced table sits in shared memory.
 template <int K>
-__global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
+__global__ void __launch_bounds__(128) k_barcode_bitsliced(SMX_KARGS) {
     __shared__ u32 s_beq[SMX_MAX_PATTERN * 16];
     const Tables &t = c_tables;
     const u32 g = blockIdx.y % t.n_bwords;
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(Batch b) {
 }
 
 // Stage 3a: digest of every matched slot's hit lists (one thread per (read, slot), high occupancy).
-__global__ void __launch_bounds__(256) k_slot_summary(Batch b) {
+__global__ void __launch_bounds__(256) k_slot_summary(SMX_KARGS) {
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     if (read >= b.n_reads) return;
     const Tables &t = c_tables;
@@ -610,7 +612,7 @@ constexpr int kInlineRecords = 4;
 // (rare) to a contiguous block of rec_pool.  Reads whose groups overflow kSmallGroups or that
 // emit more than kInlineRecords records are flagged (bit1) for k_select_big.
 template <int MAXP>
-__global__ void __launch_bounds__(128) k_select(Batch b) {
+__global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     if (read >= b.n_reads) return;
     EndInfo ends[2 * MAXP];
@@ -637,22 +639,29 @@ __global__ void __launch_bounds__(128) k_select(Batch b) {
     }
 }
 
-// Moves staged records to their final, read-ordered positions.
-__global__ void __launch_bounds__(256) k_compact_records(Batch b) {
-    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
+// Moves staged records to their final, read-ordered positions.  rec_offset_out (optional) receives
+// the read's record offset in the caller's whole batch (this sub-batch's records start at rec_base).
+__global__ void __launch_bounds__(256) k_compact_records(SMX_KARGS, u32 rec_base, u32 *rec_offset_out) {
+    // four threads per read, one 16-byte quarter of the 64-byte record each: coalesced both ways
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 read = tid >> 2, q = tid & 3;
     if (read >= b.n_reads) return;
+    const u32 off = b.rec_offset[read];
+    if (rec_offset_out && q == 0) rec_offset_out[read] = off + rec_base;
     if (b.read_flags[read] & 2) return;                       // written by k_select_big
-    u32 cnt = b.rec_count[read];
+    const u32 cnt = b.rec_count[read];
     if (!cnt) return;
-    u32 off = b.rec_offset[read];
-    b.records[off] = b.rec_stage[read];
-    u32 base = cnt > 1 ? b.rec_extra[read] : 0;
-    for (u32 i = 1; i < cnt; ++i) b.records[off + i] = b.rec_pool[base + i - 1];
+    uint4 *dst = reinterpret_cast<uint4 *>(b.records + off);
+    dst[q] = reinterpret_cast<const uint4 *>(b.rec_stage + read)[q];
+    if (cnt > 1) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.rec_pool + b.rec_extra[read]);
+        for (u32 i = q; i < 4 * (cnt - 1); i += 4) dst[4 + i] = src[i];
+    }
 }
 
 // Second pass over the (rare) reads flagged by the first: same routine, kBigGroups-entry storage
 // in global scratch.  One thread per flagged read.
-__global__ void __launch_bounds__(32) k_select_big(Batch b, const u32 *list, u32 n_list, unsigned char *scratch, int write_pass) {
+__global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u32 n_list, unsigned char *scratch, int write_pass) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_list) return;
     u32 read = list[i];

@@ -187,6 +187,13 @@ class Matcher:
             _lib.check(rc)
             return self._finish(res, rec_offset, records, ph, em, bh)
 
+    def set_pipeline_chunk(self, reads_per_chunk: int):
+        """Chunk size of the pipelined smx_match_batch (0 = always one shot)."""
+        _lib.check(self._lib.smx_set_pipeline_chunk(self._ctx, int(reads_per_chunk)))
+
+    def last_chunk_count(self) -> int:
+        return int(self._lib.smx_last_chunk_count(self._ctx))
+
     def flush_l2(self):
         _lib.check(self._lib.smx_flush_l2(self._ctx))
 

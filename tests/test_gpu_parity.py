@@ -136,6 +136,36 @@ def test_cuda_equals_kernel_simulator_at_scale(cfg, n):
     assert np.array_equal(gpu.primer_hits, sim.primer_hits)
 
 
+@pytest.mark.parametrize("cfg,n,chunk", [("ont037", 20000, 1024), ("dense", 12000, 1152), ("multipool", 9000, 128)])
+def test_pipelined_match_equals_one_shot(cfg, n, chunk):
+    """smx_match_batch's chunked, three-stream form returns exactly the one-shot result (records,
+    offsets, matched count), including reads on the exact 4-bit side stream and multi-record reads."""
+    ds = synth.CONFIGS[cfg](n_reads=n, seed=4242)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params, dereplicate="none" if cfg == "dense" else "best")
+    codes = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].copy()
+    rng = np.random.default_rng(5)
+    hits = rng.choice(codes.shape[0], size=codes.shape[0] // 4000, replace=False)
+    codes[hits] = np.frombuffer(b"NRYn", dtype=np.uint8)[rng.integers(0, 4, size=hits.shape[0])]
+    batch = PackedBatch.from_blob(codes.tobytes(), ds.offsets.astype(np.uint64), clip=ds.search_len)
+    assert batch.n_flagged > 0
+    with Matcher(mt) as m:
+        m.set_pipeline_chunk(0)
+        one = m.match(batch)
+        assert m.last_chunk_count() == 1
+        m.set_pipeline_chunk(chunk)
+        for _ in range(2):
+            piped = m.match(batch)
+            assert m.last_chunk_count() == -(-n // chunk)
+            assert piped.n_matched == one.n_matched
+            assert np.array_equal(piped.rec_offset, one.rec_offset)
+            assert piped.records.tobytes() == one.records.tobytes()
+        # the resident API still works after a pipelined call
+        m.upload(batch)
+        m.run_resident()
+        assert m.download().records.tobytes() == one.records.tobytes()
+
+
 def test_full_size_properties_ont037():
     """BASELINE config 2 at full size (765k reads): determinism, batch-split invariance,
     reverse-complement invariance of the specimen calls, and agreement with the generator's truth."""
