@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="reads per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=12000, help="reads of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=-1, help="reads per pipeline chunk of smx_match_batch (-1 = library default)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: --warmup %d < 3; timing hygiene asks for >= 3" % args.warmup)
@@ -226,6 +227,8 @@ def main():
     st = np.mean(np.array(stage_ms), axis=0)
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
+    if args.chunk >= 0:
+        matcher.set_pipeline_chunk(args.chunk)
     for _ in range(min(args.warmup, 2)):
         r = matcher.match(batch, reuse=True)
     barrier()
@@ -280,7 +283,9 @@ def main():
                          "hbm_sanity_gbs": hbm_bytes / (ms / 1000.0) / 1e9},
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": "reads/s",
                     "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "api": "smx_match_batch (pinned host buffers, reads clipped to head/tail search_len bases: H2D + kernels + D2H)"},
+                    "ms_per_step": e2e_ms, "chunks": matcher.last_chunk_count(),
+                    "api": "smx_match_batch (pinned host buffers, reads clipped to head/tail search_len bases; "
+                           "H2D + kernels + D2H, chunks pipelined over three streams)"},
             "gpu_launches": int(launches * args.steps),
             "clocks": clocks.summary(),
             "records_per_step": int(len(res.records)), "matched_reads": int(res.n_matched),

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -64,9 +65,13 @@ template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) 
 // (upload / run / download on a whole batch); smx_match_batch splits large batches into chunks that
 // rotate over all lanes so one chunk's H2D, another's kernels and a third's D2H overlap.
 constexpr int kLanes = 3;
+constexpr size_t kCtlWords = 8 + SMX_MAX_PRIMERS;     // unsigned long long words of a lane's control block
 
 struct Lane {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // H2D + kernels
+    cudaStream_t out_stream = nullptr;      // D2H of finished results (pipelined form)
+    cudaEvent_t ev_ready = nullptr, ev_drained = nullptr;   // records compacted / records copied out
+    bool drain_pending = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     Batch b;
     DevBuf<u32> packed2, lengths, packed4, win, endmask, impmask, rec_count, rec_offset, rec_offset_out, block_sums;
@@ -74,16 +79,18 @@ struct Lane {
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
     DevBuf<smx_barcode_hit> bh_list;
-    DevBuf<u32> slot_count, ent_base, ent_read, rec_extra, big_list;
+    DevBuf<u32> ent_base, ent_read, rec_extra, big_list;
     DevBuf<unsigned short> ent_pos;
     DevBuf<SlotSum> ssum;
     DevBuf<smx_record> rec_stage, rec_pool, records;
     DevBuf<unsigned char> big_scratch;
-    DevBuf<unsigned long long> counters;   // 4 work counters + matched + (u32) overflow + (u32) total + hit overflow
+    // control block: 8 counters (4 work, matched, (u32,u32) overflow, (u32,u32) total/pool, hit overflow)
+    // followed by the 2 * SMX_MAX_PRIMERS per-slot entry counts -- one memset, one read-back
+    DevBuf<unsigned long long> counters;
     u32 e_cap = 0, pool_cap = 0;
     int hit_cap = 0;                        // hit sub-list capacity the lane's buffers are laid out for
-    unsigned long long *h_counters = nullptr;   // pinned: 8 counters
-    u32 *h_slot_counts = nullptr;               // pinned: 2 * SMX_MAX_PRIMERS
+    unsigned long long *h_counters = nullptr;   // pinned mirror of the control block
+    u32 *h_slot_counts = nullptr;               // = (u32 *)(h_counters + 8)
     std::vector<u32> big_list_host;
     bool have_batch = false, have_results = false;
     u64 n_records = 0, n_matched = 0;
@@ -94,13 +101,15 @@ struct Lane {
         packed2.release(); lengths.release(); packed4.release(); win.release(); endmask.release(); impmask.release();
         rec_count.release(); rec_offset.release(); rec_offset_out.release(); block_sums.release(); word_off.release();
         off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
-        slot_count.release(); ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
+        ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
         ent_pos.release(); ssum.release(); rec_stage.release(); rec_pool.release(); records.release();
         big_scratch.release(); counters.release();
         if (h_counters) cudaFreeHost(h_counters);
-        if (h_slot_counts) cudaFreeHost(h_slot_counts);
         h_counters = nullptr; h_slot_counts = nullptr;
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (ev_ready) { cudaEventDestroy(ev_ready); ev_ready = nullptr; }
+        if (ev_drained) { cudaEventDestroy(ev_drained); ev_drained = nullptr; }
+        if (out_stream) { cudaStreamDestroy(out_stream); out_stream = nullptr; }
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 };
@@ -121,16 +130,20 @@ struct smx_ctx {
     u32 chunk_reads = 128 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK)
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
     int last_chunks = 0;
+    bool trace = false;
 };
 
 static cudaError_t lane_init(Lane &ln) {
     cudaError_t e;
     if (ln.stream) return cudaSuccess;
     if ((e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&ln.out_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ln.ev_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto &ev : ln.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
-    if ((e = cudaHostAlloc((void **)&ln.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
-    if ((e = cudaHostAlloc((void **)&ln.h_slot_counts, 2 * SMX_MAX_PRIMERS * sizeof(u32), cudaHostAllocDefault)) != cudaSuccess) return e;
-    if ((e = ln.counters.ensure(8)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void **)&ln.h_counters, kCtlWords * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
+    ln.h_slot_counts = (u32 *)(ln.h_counters + 8);
+    if ((e = ln.counters.ensure(kCtlWords)) != cudaSuccess) return e;
     memset(&ln.b, 0, sizeof(ln.b));
     return cudaSuccess;
 }
@@ -176,9 +189,9 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     CU(ln.endmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(ln.impmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(ln.orient_hit.ensure((size_t)2 * nP * n_pad));
-    CU(ln.slot_count.ensure((size_t)2 * nP)); CU(ln.ent_base.ensure((size_t)2 * nP * n_pad));
+    CU(ln.ent_base.ensure((size_t)2 * nP * n_pad));
     CU(ln.ssum.ensure((size_t)2 * nP * n_pad));
-    if (ln.e_cap < n_pad) ln.e_cap = n_pad;
+    if (ln.e_cap < n_pad + n_pad / 4) ln.e_cap = n_pad + n_pad / 4;     // ~1.2 equal-best ends per matched slot is typical
     if (ln.pool_cap < n_pad / 8 + 1024) ln.pool_cap = n_pad / 8 + 1024;
     if (ln.hit_cap < c->t.hit_cap) ln.hit_cap = c->t.hit_cap;
     CU(ensure_entry_buffers(c, ln));
@@ -200,7 +213,7 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     b.packed2 = ln.packed2.p; b.word_off = ln.word_off.p; b.lengths = ln.lengths.p;
     b.packed4 = flagged ? (shared4 ? shared4 : ln.packed4.p) : nullptr; b.off4 = flagged ? ln.off4.p : nullptr;
     b.win = ln.win.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
-    b.slot_count = ln.slot_count.p; b.ent_base = ln.ent_base.p; b.ssum = ln.ssum.p;
+    b.slot_count = (u32 *)(ln.counters.p + 8); b.ent_base = ln.ent_base.p; b.ssum = ln.ssum.p;
     b.rec_stage = ln.rec_stage.p; b.rec_extra = ln.rec_extra.p;
     b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
     b.records = nullptr; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
@@ -209,18 +222,18 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     return SMX_OK;
 }
 
-// rec_count -> rec_offset (exclusive scan), flag counters, then the asynchronous D2H of the counters.
+// rec_count -> rec_offset (exclusive scan), flag counters, then the asynchronous read-back of the
+// whole control block (counters + per-slot entry counts).
 static cudaError_t enqueue_scan_and_count(Lane &ln) {
     Batch &b = ln.b;
     const u32 n = b.n_reads;
     cudaStream_t st = ln.stream;
     unsigned sblocks = (n + kScanBlock - 1) / kScanBlock;
-    k_scan_block_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, ln.block_sums.p);
-    k_scan_spine<<<1, kScanBlock, 0, st>>>(ln.block_sums.p, sblocks, (u32 *)(ln.counters.p + 6));
-    k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, ln.block_sums.p, b.rec_offset);
-    k_count_flags<<<(n + 255) / 256, 256, 0, st>>>(b.read_flags, n, ln.counters.p + 4, (unsigned *)(ln.counters.p + 5));
-    ln.launches += 4;
-    return cudaMemcpyAsync(ln.h_counters, ln.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    k_scan_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, b.read_flags, n, ln.block_sums.p, ln.counters.p + 4,
+                                                (unsigned *)(ln.counters.p + 5));
+    k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, ln.block_sums.p, b.rec_offset, (u32 *)(ln.counters.p + 6));
+    ln.launches += 2;
+    return cudaMemcpyAsync(ln.h_counters, ln.counters.p, kCtlWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
 }
 
 // Enqueues stages `from`..3 (0 = from window staging) through the scan and the counter read-back.
@@ -233,16 +246,14 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     cudaStream_t st = ln.stream;
     const unsigned blocks = (n + 127) / 128;
     if (from <= 0) {
-        CU(cudaMemsetAsync(ln.counters.p, 0, 8 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
         if (timed) CU(cudaEventRecord(ln.ev[0], st));
         dim3 grid(blocks, 2 * t.wpw);
         k_stage_windows<<<grid, 128, 0, st>>>(t, b);
         ++ln.launches;
     }
     if (from <= 1) {   // stage 1
-        CU(cudaMemsetAsync(ln.slot_count.p, 0, (size_t)2 * nP * sizeof(u32), st));
-        CU(cudaMemsetAsync(ln.counters.p, 0, sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ln.counters.p + 2, 0, sizeof(unsigned long long), st));
+        if (from == 1) CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));   // re-run
         if (timed) CU(cudaEventRecord(ln.ev[1], st));
         dim3 grid(blocks, 2 * nP);
         if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(t, b);
@@ -253,9 +264,10 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         ln.launches += 2;
     }
     if (from <= 2) {   // stage 2
-        CU(cudaMemsetAsync(ln.counters.p + 1, 0, sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ln.counters.p + 3, 0, sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ln.counters.p + 7, 0, sizeof(unsigned long long), st));
+        if (from == 2) {                                                                                     // re-run
+            CU(cudaMemsetAsync(ln.counters.p + 1, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(ln.counters.p + 3, 0, 5 * sizeof(unsigned long long), st));
+        }
         if (timed) CU(cudaEventRecord(ln.ev[2], st));
         if (t.n_bwords) {
             dim3 grid((b.e_cap + 127) / 128, 2 * t.n_bwords);
@@ -269,7 +281,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         }
     }
     // stage 3: slot digests, single-pass selection, scan
-    CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
+    if (from == 3) CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));          // re-run
     if (timed) CU(cudaEventRecord(ln.ev[3], st));
     {
         dim3 sgrid((n + 255) / 256, 2 * nP);
@@ -277,7 +289,6 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     }
     if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(t, b); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
     ln.launches += 2;
-    CU(cudaMemcpyAsync(ln.h_slot_counts, ln.slot_count.p, (size_t)2 * nP * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CU(enqueue_scan_and_count(ln));
     return SMX_OK;
 }
@@ -351,6 +362,7 @@ static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
     const Tables t = lane_tables(c, ln);
     Batch &b = ln.b;
     cudaStream_t st = ln.stream;
+    if (ln.drain_pending) { CU(cudaStreamWaitEvent(ln.stream, ln.ev_drained, 0)); ln.drain_pending = false; }
     CU(ln.records.ensure(ln.n_records + 1));
     b.records = ln.records.p;
     k_compact_records<<<(unsigned)(((u64)b.n_reads * 4 + 255) / 256), 256, 0, st>>>(t, b, rec_base, ln.rec_offset_out.p);
@@ -382,7 +394,7 @@ int smx_device_count(void) {
 void smx_destroy(smx_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (auto &ln : c->lane) if (ln.stream) cudaStreamSynchronize(ln.stream);
+    for (auto &ln : c->lane) if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamSynchronize(ln.out_stream); }
     for (auto &ln : c->lane) ln.release();
     c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bw_len.release(); c->bw_primer.release(); c->bw_row.release();
     c->bw_valid.release(); c->beq.release(); c->bw_list.release();
@@ -444,6 +456,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         if (v >= 128) c->chunk_reads = (u32)std::min<long>(v, 1L << 30);
         else if (v == 0) c->chunk_reads = 0;                   // 0 disables the pipelined form
     }
+    if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
     return SMX_OK;
 }
@@ -577,6 +590,17 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
     u64 rec_base = 0, matched = 0;
     bool overflow = false;
     int rc = SMX_OK;
+    // SMX_PIPELINE_TRACE=1: per-chunk device timeline (events) + host enqueue times on stderr
+    const bool trace = c->trace;
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> thost;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    if (trace) {
+        tev.resize((size_t)n_chunks * 4); thost.assign((size_t)n_chunks * 4, 0.0);
+        for (auto &e : tev) cudaEventCreate(&e);
+    }
+    auto mark = [&](u32 i, int k, cudaStream_t st) { if (trace) { cudaEventRecord(tev[(size_t)i * 4 + k], st); thost[(size_t)i * 4 + k] = now_ms() - t_begin; } };
     auto bounds = [&](u32 i, u32 &r0, u32 &r1) { r0 = std::min<u64>((u64)i * per, n); r1 = std::min<u64>((u64)(i + 1) * per, n); };
     auto finish = [&](u32 i) -> int {
         Lane &ln = c->lane[i % kLanes];
@@ -587,12 +611,18 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         if (rec_base + ln.n_records > out->records_cap || rec_base + ln.n_records > 0xFFFFFFFFull) overflow = true;
         if (!overflow) {
             if ((r = lane_compact(c, ln, (u32)rec_base, false))) return r;
+            // the copy-out runs on its own stream so the lane's next H2D + kernels need not wait for it
+            CU(cudaEventRecord(ln.ev_ready, ln.stream));
+            CU(cudaStreamWaitEvent(ln.out_stream, ln.ev_ready, 0));
             if (out->rec_offset)
                 CU(cudaMemcpyAsync(out->rec_offset + r0, ln.rec_offset_out.p, (size_t)(r1 - r0) * sizeof(u32),
-                                   cudaMemcpyDeviceToHost, ln.stream));
+                                   cudaMemcpyDeviceToHost, ln.out_stream));
             if (out->records && ln.n_records)
                 CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, ln.n_records * sizeof(smx_record),
-                                   cudaMemcpyDeviceToHost, ln.stream));
+                                   cudaMemcpyDeviceToHost, ln.out_stream));
+            CU(cudaEventRecord(ln.ev_drained, ln.out_stream));
+            ln.drain_pending = true;
+            mark(i, 3, ln.out_stream);
         }
         rec_base += ln.n_records;
         matched += ln.n_matched;
@@ -607,13 +637,26 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         u32 r0, r1;
         bounds(issued, r0, r1);
         if (r0 >= r1) { ln.have_batch = false; continue; }
+        mark(issued, 0, ln.stream);
         if ((rc = lane_upload(c, ln, in, r0, r1, shared4))) break;
+        mark(issued, 1, ln.stream);
         if ((rc = lane_enqueue(c, ln, 0, false))) break;
+        mark(issued, 2, ln.stream);
         // keep at most kLanes - 1 chunks ahead so the finished chunk's D2H starts while the next computes
         while (rc == SMX_OK && issued + 1 - finished >= (u32)kLanes) rc = finish(finished++);
     }
     while (rc == SMX_OK && finished < issued) rc = finish(finished++);
-    for (auto &ln : c->lane) if (ln.stream) cudaStreamSynchronize(ln.stream);
+    for (auto &ln : c->lane) if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamSynchronize(ln.out_stream); ln.drain_pending = false; }
+    if (trace) {
+        fprintf(stderr, "[smx pipeline] %u chunks of %u reads, host total %.3f ms\n", n_chunks, per, now_ms() - t_begin);
+        for (u32 i = 0; i < n_chunks && rc == SMX_OK && !overflow; ++i) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[(size_t)i * 4 + k]);
+            fprintf(stderr, "[smx pipeline] chunk %u dev: h2d %.3f-%.3f kernels-end %.3f d2h-end %.3f | host enq: %.3f %.3f %.3f %.3f\n",
+                    i, t[0], t[1], t[2], t[3], thost[i * 4], thost[i * 4 + 1], thost[i * 4 + 2], thost[i * 4 + 3]);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     c->lane[0].have_batch = false; c->lane[0].have_results = false;     // the resident API needs a fresh upload
     if (rc) return rc;
     CU(cudaGetLastError());

@@ -677,68 +677,32 @@ __global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u
     }
 }
 
-// Exclusive scan of rec_count -> rec_offset (n+1 entries), three small kernels.
+// Exclusive scan of rec_count -> rec_offset (n+1 entries) in two launches.
 constexpr int kScanBlock = 1024;
 
-__global__ void k_scan_block_sums(const u32 *in, u32 n, u32 *block_sums) {
-    __shared__ u32 s[32];
-    u32 i = blockIdx.x * kScanBlock + threadIdx.x;
-    u32 v = i < n ? in[i] : 0;
+__device__ __forceinline__ u32 block_sum_1024(u32 v, u32 *s /*32*/) {
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x < 32) {
         v = s[threadIdx.x];
         for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+        if (threadIdx.x == 0) s[0] = v;
     }
-}
-
-__global__ void k_scan_spine(u32 *block_sums, u32 nblocks, u32 *total) {
-    // single block; serial over chunks of 1024 with a running carry
-    __shared__ u32 s[kScanBlock];
-    __shared__ u32 carry;
-    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (u32 base = 0; base < nblocks; base += kScanBlock) {
-        u32 i = base + threadIdx.x;
-        u32 v = i < nblocks ? block_sums[i] : 0;
-        s[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < kScanBlock; o <<= 1) {
-            u32 x = threadIdx.x >= (u32)o ? s[threadIdx.x - o] : 0;
-            __syncthreads();
-            s[threadIdx.x] += x;
-            __syncthreads();
-        }
-        if (i < nblocks) block_sums[i] = carry + s[threadIdx.x] - v;     // exclusive
-        __syncthreads();
-        if (threadIdx.x == 0) carry += s[kScanBlock - 1];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
+    v = s[0];
+    __syncthreads();
+    return v;
 }
 
-__global__ void k_scan_apply(const u32 *in, u32 n, const u32 *block_sums, u32 *out) {
-    __shared__ u32 s[kScanBlock];
+// Pass 1: per-block record totals, plus the per-read flag counters:
+// *matched += reads with a full match; overflow[0] += reads needing the big pass (bit1),
+// overflow[1] += reads that overflowed even the big pass (bit2).
+__global__ void __launch_bounds__(kScanBlock) k_scan_sums(const u32 *in, const unsigned char *flags, u32 n, u32 *block_sums,
+                                                          unsigned long long *matched, unsigned int *overflow) {
+    __shared__ u32 s[32];
     u32 i = blockIdx.x * kScanBlock + threadIdx.x;
     u32 v = i < n ? in[i] : 0;
-    s[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < kScanBlock; o <<= 1) {
-        u32 x = threadIdx.x >= (u32)o ? s[threadIdx.x - o] : 0;
-        __syncthreads();
-        s[threadIdx.x] += x;
-        __syncthreads();
-    }
-    if (i < n) out[i] = block_sums[blockIdx.x] + s[threadIdx.x] - v;
-    if (i == n - 1) out[n] = block_sums[blockIdx.x] + s[threadIdx.x];
-}
-
-// counters[4] += reads with a full match; counters[5] lo += reads needing the big pass (bit1),
-// hi += reads that overflowed even the big pass (bit2).
-__global__ void k_count_flags(const unsigned char *flags, u32 n, unsigned long long *matched, unsigned int *overflow) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned f = i < n ? flags[i] : 0;
     unsigned m = __ballot_sync(0xffffffffu, f & 1);
     unsigned o = __ballot_sync(0xffffffffu, f & 2);
@@ -748,6 +712,41 @@ __global__ void k_count_flags(const unsigned char *flags, u32 n, unsigned long l
         if (o) atomicAdd(overflow, (unsigned)__popc(o));
         if (h) atomicAdd(overflow + 1, (unsigned)__popc(h));
     }
+    u32 total = block_sum_1024(v, s);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// Pass 2: every block sums the totals of the blocks before it (a few thousand values at most),
+// scans its own 1024 counts and writes the offsets; the last block also writes the grand total.
+__global__ void __launch_bounds__(kScanBlock) k_scan_apply(const u32 *in, u32 n, const u32 *block_sums, u32 *out, u32 *total) {
+    __shared__ u32 s[kScanBlock];
+    __shared__ u32 red[32];
+    u32 pre = 0;
+    for (u32 j = threadIdx.x; j < blockIdx.x; j += kScanBlock) pre += block_sums[j];
+    const u32 base = block_sum_1024(pre, red);
+    u32 i = blockIdx.x * kScanBlock + threadIdx.x;
+    u32 v = i < n ? in[i] : 0;
+    // warp scan, then scan of the 32 warp totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+    }
+    if (lane == 31) s[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = s[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 x = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += x;
+        }
+        s[32 + lane] = wi - w;          // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const u32 excl = base + s[32 + warp] + incl - v;
+    if (i < n) out[i] = excl;
+    if (i == n - 1) { out[n] = excl + v; *total = excl + v; }
 }
 
 // Batched global (NW) distances for setup_match_parameters (orchestration.py:549-555):
