@@ -322,6 +322,63 @@ template <int K> struct BitSliced {
 #endif
         for (int t = 1; t < NT; ++t) { o.rp[t - 1] = HP[t]; o.rm[t - 1] = HM[t]; }
     }
+
+    // Small form (m + K <= 16): the whole flank sits in one 64-bit register F (nibble j-1 = symbol of
+    // column j, kSymOther beyond the flank).  One table address is formed per COLUMN (beq row 0 of
+    // that column's symbol); the rows are fully unrolled, so every cell's Eq is a single load at a
+    // compile-time offset from its column's address -- no per-cell shift / mask / scale arithmetic.
+    static constexpr int kSmallRows = 16 - K > 0 ? 16 - K : 0;
+    static SMX_HD void run_small(const u32 *beq_rows, int m, u64 F, Out &o) {
+        const u32 *col[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 16; ++j) col[j] = beq_rows + (u32)((F >> (4 * j)) & 15u);
+        u32 HP[NT], HM[NT];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < NT; ++t) { HP[t] = ~0u; HM[t] = 0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int b = 0; b < NB; ++b) o.cnt[b] = (K >> b) & 1 ? ~0u : 0u;
+        o.over = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 1; i <= kSmallRows; ++i) {
+            if (i <= m) {                                       // uniform over the block
+                u32 Pv = ~0u, Mv = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int t = 0; t < NT; ++t) {
+                    const int j = i - K + t;                    // compile-time
+                    if (j < 1 || j > 16) continue;
+                    u32 Ph = t < NT - 1 ? HP[t + 1] : ~0u;
+                    u32 Mh = t < NT - 1 ? HM[t + 1] : 0u;
+                    u32 Eq = col[j - 1][(i - 1) * 16];
+                    u32 nPv, nMv, nPh, nMh, inc;
+                    cell(Eq, Pv, Mv, Ph, Mh, nPv, nMv, nPh, nMh, inc);
+                    if (t == 0) {
+                        u32 x = inc;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                        for (int b = 0; b < NB; ++b) { u32 c = o.cnt[b] & x; o.cnt[b] ^= x; x = c; }
+                        o.over |= x;
+                    }
+                    HP[t] = nPh; HM[t] = nMh;
+                    Pv = nPv; Mv = nMv;
+                }
+            }
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 1; t < NT; ++t) { o.rp[t - 1] = HP[t]; o.rm[t - 1] = HM[t]; }
+    }
 };
 // value <= K on NB bit-planes (K compile-time)
 template <int K, int NB> SMX_HD u32 planes_le(const u32 *v) {
@@ -395,11 +452,7 @@ SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, 
     if (cols < m - K || cols <= 0) return;           // D[m][j] >= m - j > K for every column
     typename BS::Out o;
     if (small) {
-        auto rowwin = [&](int i) -> u64 {
-            int shn = i - K - 1;                      // first column of the band, 0-based symbol
-            return shn >= 0 ? (F >> (4 * shn)) : (F << (4 * -shn));
-        };
-        BS::run(beq_rows, m, rowwin, o);
+        BS::run_small(beq_rows, m, F, o);
     } else {
         auto rowwin = [&](int i) -> u64 {
             u64 W = 0;
