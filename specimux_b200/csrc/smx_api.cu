@@ -65,16 +65,19 @@ template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) 
 // (upload / run / download on a whole batch); smx_match_batch splits large batches into chunks that
 // rotate over all lanes so one chunk's H2D, another's kernels and a third's D2H overlap.
 constexpr int kLanes = 3;
+constexpr int kAuxStreams = 2;
 constexpr size_t kCtlWords = 8 + SMX_MAX_PRIMERS;     // unsigned long long words of a lane's control block
 
 struct Lane {
     cudaStream_t stream = nullptr;          // H2D + kernels
     cudaStream_t out_stream = nullptr;      // D2H of finished results (pipelined form)
     cudaEvent_t ev_ready = nullptr, ev_drained = nullptr;   // records compacted / records copied out
+    cudaStream_t aux[kAuxStreams] = {};     // the per-primer sliced searches run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
     bool drain_pending = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     Batch b;
-    DevBuf<u32> packed2, lengths, packed4, win, endmask, impmask, rec_count, rec_offset, rec_offset_out, block_sums;
+    DevBuf<u32> packed2, lengths, packed4, win, win2, tmix, endmask, impmask, rec_count, rec_offset, rec_offset_out, block_sums;
     DevBuf<u64> word_off, off4;
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
@@ -98,7 +101,7 @@ struct Lane {
     int launches = 0;
 
     void release() {
-        packed2.release(); lengths.release(); packed4.release(); win.release(); endmask.release(); impmask.release();
+        packed2.release(); lengths.release(); packed4.release(); win.release(); win2.release(); tmix.release(); endmask.release(); impmask.release();
         rec_count.release(); rec_offset.release(); rec_offset_out.release(); block_sums.release(); word_off.release();
         off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
         ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
@@ -108,6 +111,9 @@ struct Lane {
         h_counters = nullptr; h_slot_counts = nullptr;
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_ready) { cudaEventDestroy(ev_ready); ev_ready = nullptr; }
+        if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+        for (auto &e : ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto &a : aux) if (a) { cudaStreamDestroy(a); a = nullptr; }
         if (ev_drained) { cudaEventDestroy(ev_drained); ev_drained = nullptr; }
         if (out_stream) { cudaStreamDestroy(out_stream); out_stream = nullptr; }
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
@@ -124,6 +130,7 @@ struct smx_ctx {
     DevBuf<unsigned short> bw_list;
     DevBuf<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
+    std::vector<unsigned char> prow_code;   // [primer][32] pattern row codes (sliced primer search)
     Lane lane[kLanes];
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
     DevBuf<unsigned char> l2_scratch;
@@ -139,6 +146,9 @@ static cudaError_t lane_init(Lane &ln) {
     if ((e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithFlags(&ln.out_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (auto &a : ln.aux) if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (auto &j : ln.ev_join) if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto &ev : ln.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     if ((e = cudaHostAlloc((void **)&ln.h_counters, kCtlWords * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
@@ -185,6 +195,8 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     const bool flagged = in->packed4 && in->off4 && in->packed4_words;
     if (flagged) { CU(ln.off4.ensure(n)); if (!shared4) CU(ln.packed4.ensure(in->packed4_words)); }
     CU(ln.win.ensure((size_t)2 * t.wpw * n_pad));
+    CU(ln.win2.ensure((size_t)2 * t.nw2 * n_pad));
+    if (t.sliced) CU(ln.tmix.ensure((size_t)2 * nP * t.nw2 * n_pad));
     CU(ln.phit.ensure((size_t)2 * nP * n_pad));
     CU(ln.endmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(ln.impmask.ensure((size_t)2 * nP * t.mw * n_pad));
@@ -212,7 +224,7 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len; b.word_base = w0; b.read_base = r0;
     b.packed2 = ln.packed2.p; b.word_off = ln.word_off.p; b.lengths = ln.lengths.p;
     b.packed4 = flagged ? (shared4 ? shared4 : ln.packed4.p) : nullptr; b.off4 = flagged ? ln.off4.p : nullptr;
-    b.win = ln.win.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
+    b.win = ln.win.p; b.win2 = ln.win2.p; b.tmix = ln.tmix.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
     b.slot_count = (u32 *)(ln.counters.p + 8); b.ent_base = ln.ent_base.p; b.ssum = ln.ssum.p;
     b.rec_stage = ln.rec_stage.p; b.rec_extra = ln.rec_extra.p;
     b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
@@ -248,16 +260,50 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     if (from <= 0) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
         if (timed) CU(cudaEventRecord(ln.ev[0], st));
-        dim3 grid(blocks, 2 * t.wpw);
+        dim3 grid(blocks, 2 * t.nw2);
         k_stage_windows<<<grid, 128, 0, st>>>(t, b);
         ++ln.launches;
     }
     if (from <= 1) {   // stage 1
         if (from == 1) CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));   // re-run
         if (timed) CU(cudaEventRecord(ln.ev[1], st));
-        dim3 grid(blocks, 2 * nP);
-        if (t.use64) k_primer_search<u64><<<grid, 128, 0, st>>>(t, b);
-        else k_primer_search<u32><<<grid, 128, 0, st>>>(t, b);
+        if (t.sliced) {
+            // forward pass bit-sliced across reads, one launch per primer (pattern length = template)
+            // The primers' kernels are independent and each fills only ~2.5 warps per scheduler at
+            // 765k reads, so they run concurrently on auxiliary streams (fork / join on events).
+            dim3 sgrid((b.n_pad / 32 + kSlicedBlock - 1) / kSlicedBlock, 2);
+            const bool fork = nP > 1;
+            if (fork) CU(cudaEventRecord(ln.ev_fork, st));
+            for (int p = 0; p < nP; ++p) {
+                cudaStream_t ps = fork ? ln.aux[p % kAuxStreams] : st;
+                if (fork && p < kAuxStreams) CU(cudaStreamWaitEvent(ps, ln.ev_fork, 0));
+                RowOffsets ro;
+                bool degenerate = false;
+                for (int i = 0; i < 32; ++i) {
+                    int code = i < t.p_len[p] ? c->prow_code[(size_t)p * 32 + i] : 0;
+                    degenerate |= code > 3;
+                    ro.off[i] = (unsigned short)(code * kSlicedBlock * sizeof(u32));
+                }
+                switch (t.p_len[p]) {
+#define SMX_M(MM) case MM: k_primer_sliced<MM><<<sgrid, kSlicedBlock, 0, ps>>>(t, b, p, ro, degenerate ? 1 : 0); break;
+                    SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
+                    SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
+                    SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
+                    SMX_M(32)
+#undef SMX_M
+                    default: return fail(SMX_ERR_INTERNAL, "sliced primer search: pattern length %d", (int)t.p_len[p]);
+                }
+                ++ln.launches;
+            }
+            if (fork)
+                for (int a = 0; a < kAuxStreams && a < nP; ++a) {
+                    CU(cudaEventRecord(ln.ev_join[a], ln.aux[a]));
+                    CU(cudaStreamWaitEvent(st, ln.ev_join[a], 0));
+                }
+        }
+        dim3 grid((n + kFinishBlock - 1) / kFinishBlock, 2 * nP);
+        if (t.use64) k_primer_search<u64><<<grid, kFinishBlock, 0, st>>>(t, b);
+        else k_primer_search<u32><<<grid, kFinishBlock, 0, st>>>(t, b);
         dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
         if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, st>>>(t, b);
         else k_primer_start<u32><<<sgrid, 128, 0, st>>>(t, b);
@@ -424,6 +470,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     smx_ctx *c = new smx_ctx();
     c->device = device;
     c->max_nb = ht.max_nb;
+    c->prow_code = ht.prow_code;
 #define CUC(call)                                                                                     \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \
@@ -456,6 +503,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         if (v >= 128) c->chunk_reads = (u32)std::min<long>(v, 1L << 30);
         else if (v == 0) c->chunk_reads = 0;                   // 0 disables the pipelined form
     }
+    if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
     return SMX_OK;

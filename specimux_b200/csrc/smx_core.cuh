@@ -140,6 +140,8 @@ template <> SMX_HD u64 peq_word<u64>(u64 v) { return v; }
 struct Tables {
     int n_primers, n_pairs, n_specimens, n_keys;
     int L, wpw, mw;                 // search_len, staged words per window (8 syms/word), mask words
+    int nw2;                        // 2-bit window words per strand (16 symbols each) = blocks of the sliced primer search
+    int sliced;                     // stage 1 runs bit-sliced across reads (all primers <= 32 nt)
     int k_idx, blen_max;
     int preorient, prefilter, trim, derep_best, min_length, max_length;
     int total_bslots;               // sum over (strand, primer) of barcode-list lengths
@@ -208,6 +210,9 @@ struct Batch {
     u64 word_base;           // word_off values are absolute stream offsets; packed2[0] is stream word word_base
     u32 read_base;           // index of this (sub-)batch's read 0 in the caller's batch (smx_record.read)
     u32 *win;                // staged 4-bit windows [(strand*wpw + w) * n_pad + read]
+    u32 *win2;               // staged 2-bit windows [(strand*nw2 + w2) * n_pad + read], 16 symbols/word (unflagged reads)
+    u32 *tmix;               // sliced primer search output [(slot*nw2 + blk) * n_pad + read]: bit 2c = equal-best so far,
+                             // bit 2c+1 = improvement, for column 16*blk + c
     // level-1 results
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
     u32 *endmask;            // [(slot*mw + w) * n_pad + read]

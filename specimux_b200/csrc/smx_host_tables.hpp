@@ -56,6 +56,7 @@ struct HostTables {
     std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     std::vector<unsigned short> bw_list;
     std::vector<i32> pair_pool, spec_pool, spec_dense;
+    std::vector<unsigned char> prow_code;      // [primer][32] IUPAC code of primer_rc row i (sliced primer search)
     int max_nb = 0;
     std::string error;
 
@@ -81,13 +82,14 @@ struct HostTables {
         memset(&t, 0, sizeof(t));
         const int nP = (int)tb->n_primers;
         t.n_primers = nP; t.n_pairs = (int)tb->n_pairs; t.n_specimens = (int)tb->n_specimens;
-        t.L = pr->search_len; t.wpw = (t.L + 7) / 8; t.mw = (t.L + 31) / 32;
+        t.L = pr->search_len; t.wpw = (t.L + 7) / 8; t.mw = (t.L + 31) / 32; t.nw2 = (t.L + 15) / 16;
         t.k_idx = pr->max_dist_index; t.blen_max = pr->barcode_length;
         t.preorient = pr->preorient != 0; t.prefilter = pr->prefilter != 0; t.trim = pr->trim;
         t.derep_best = pr->dereplicate_best != 0; t.min_length = pr->min_length; t.max_length = pr->max_length;
         if (t.k_idx < 0) return err("negative barcode distance threshold");
 
         peq_rc.assign((size_t)nP * 16, 0); peq_rcrev.assign((size_t)nP * 16, 0); peq_fw.assign((size_t)nP * 16, 0);
+        prow_code.assign((size_t)nP * 32, 0);
         for (int p = 0; p < nP; ++p) {
             int m = (int)(tb->primer_off[p + 1] - tb->primer_off[p]);
             if (m < 1 || m > SMX_MAX_PATTERN) return err("primer %d length %d outside 1..%d", p, m, SMX_MAX_PATTERN);
@@ -100,9 +102,11 @@ struct HostTables {
                 !build_peq(tb->primer_rc + tb->primer_off[p], m, true, &peq_rcrev[(size_t)p * 16]) ||
                 !build_peq(tb->primer_seq + tb->primer_off[p], m, false, &peq_fw[(size_t)p * 16]))
                 return err("primer %d has a non-IUPAC character", p);
+            for (int i = 0; i < m && i < 32; ++i) prow_code[(size_t)p * 32 + i] = (unsigned char)code_of(tb->primer_rc[tb->primer_off[p] + i]);
             t.pb_off[p] = tb->pb_off[p];
         }
         t.pb_off[nP] = tb->pb_off[nP];
+        t.sliced = !t.use64;
         const u32 n_list = tb->pb_off[nP];
         std::vector<std::string> b_str(n_list);
         b_len.assign(n_list, 0);

@@ -22,43 +22,72 @@ SMX_HD u32 spread2to4(u32 v) {
     return v;
 }
 
-SMX_HD void stage_window_word(const Tables &t, const Batch &b, u32 read, int strand, int w) {
-    int n = (int)b.lengths[read];
-    Geo g = make_geo(n, t.L);
+SMX_HD u32 bit_reverse32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+
+// 16 consecutive 2-bit codes -> the same 16 bases read backwards and complemented
+SMX_HD u32 revcomp16(u32 v) {
+    v = bit_reverse32(v);
+    v = ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);
+    return ~v;
+}
+
+// One thread stages 16 symbols of one strand: the 2-bit word win2[w2] (input of the sliced primer
+// search) and the two 4-bit words win[2*w2], win[2*w2+1] (barcode stage, start recovery, classic
+// primer search).  Positions past the staged length hold kSymOther in `win`.
+SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int strand, int w2) {
+    const int n = (int)b.lengths[read];
+    const Geo g = make_geo(n, t.L);
+    u32 *wlo = b.win + ((u64)strand * t.wpw + 2 * w2) * b.n_pad + read;
+    const bool has_hi = 2 * w2 + 1 < t.wpw;
+    int valid = g.wl - 16 * w2;
+    valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
     if (!read_is_flagged(b, read)) {
         // fast path: the staged symbols are one contiguous run of the 2-bit stream (the tail of the
         // read for strand 0, its head read backwards and complemented for strand 1)
-        int valid = g.wl - 8 * w;
-        valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
-        u32 out = 0;
+        u32 v = 0;
         if (valid) {
-            int x0 = g.woff + 8 * w;                          // strand coordinate of symbol 0
-            int first = strand ? (n - 1 - x0) - 7 : stored_pos(b, x0, n);   // stored index of the lowest base needed
-            int lo = first < 0 ? 0 : first;
+            const int x0 = g.woff + 16 * w2;                  // strand coordinate of symbol 0
+            const int first = strand ? (n - 1 - x0) - 15 : stored_pos(b, x0, n);   // stored index of the lowest base needed
+            const int lo = first < 0 ? 0 : first;
             const u32 *src = b.packed2 + (b.word_off[read] - b.word_base) + (u64)(lo >> 4);
-            u64 pair = (u64)src[0] | ((u64)src[1] << 32);
-            u32 v = (u32)(pair >> (2 * (lo & 15))) & 0xFFFFu;
+            const u64 pair = (u64)src[0] | ((u64)src[1] << 32);
+            v = (u32)(pair >> (2 * (lo & 15)));
             if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below
-            if (strand) {                                      // reverse the 8 codes and complement
-                v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
-                v = ((v & 0x0F0Fu) << 4) | ((v >> 4) & 0x0F0Fu);
-                v = ((v & 0x00FFu) << 8) | ((v >> 8) & 0x00FFu);
-                v ^= 0xFFFFu;
-            }
-            out = spread2to4(v);
+            if (strand) v = revcomp16(v);
         }
-        if (valid < 8) out |= ~0u << (4 * valid);
-        b.win[((u64)strand * t.wpw + w) * b.n_pad + read] = out;
+        b.win2[((u64)strand * t.nw2 + w2) * b.n_pad + read] = v;
+        const int vlo = valid > 8 ? 8 : valid, vhi = valid > 8 ? valid - 8 : 0;
+        u32 out = spread2to4(v);
+        if (vlo < 8) out |= ~0u << (4 * vlo);
+        wlo[0] = out;
+        if (has_hi) {
+            out = spread2to4(v >> 16);
+            if (vhi < 8) out |= ~0u << (4 * vhi);
+            wlo[b.n_pad] = out;
+        }
         return;
     }
-    u32 out = 0;
-    for (int i = 0; i < 8; ++i) {
-        int p = w * 8 + i;
-        int c = kSymOther;
-        if (p < g.wl) c = sym_at(b, read, strand, g.woff + p, n);
-        out |= (u32)c << (4 * i);
+    b.win2[((u64)strand * t.nw2 + w2) * b.n_pad + read] = 0;      // flagged reads take the classic search
+    for (int h = 0; h < (has_hi ? 2 : 1); ++h) {
+        u32 out = 0;
+        for (int i = 0; i < 8; ++i) {
+            int p = w2 * 16 + h * 8 + i;
+            int c = kSymOther;
+            if (p < g.wl) c = sym_at(b, read, strand, g.woff + p, n);
+            out |= (u32)c << (4 * i);
+        }
+        wlo[(u64)h * b.n_pad] = out;
     }
-    b.win[((u64)strand * t.wpw + w) * b.n_pad + read] = out;
 }
 
 SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int p) {
@@ -101,34 +130,20 @@ SMX_HD u32 funnel_in_sign(u32 hist, u32 x) {      // (hist << 1) | (x >> 31): on
 #endif
 }
 
-SMX_HD u32 bit_reverse32(u32 v) {
-#if defined(__CUDA_ARCH__)
-    return __brev(v);
-#else
-    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
-    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
-    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
-    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
-    return (v >> 16) | (v << 16);
-#endif
-}
-
-// Forward pass.  Returns the number of equal-best end locations (0 = no match within k) and
-// leaves distance / first_end / n_locations in phit, the end mask in endmask.  The start of the
-// first location is recovered later by primer_start_thread (one thread per work entry).
+// Classic forward pass (one thread per (read window, primer), single-word Myers/Hyyro HW).
+// Leaves "score == running best" / "score improved the running best" column histories in
+// endmask / impmask and returns the best distance (m + 1 when the window is empty).
 //
 // Bookkeeping is kept off the critical ALU path: per column only the running minimum is updated
-// (1 op) and two sign bits are shifted into history words (1 op each): "score == running best" and
-// "score improved the running best".  After the loop the last improvement marks the first
-// equal-best end and every earlier equality bit is stale.
+// (1 op) and two sign bits are shifted into history words (1 op each).  After the loop the last
+// improvement marks the first equal-best end and every earlier equality bit is stale
+// (primer_tail).
 template <typename W>
-SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
-                                const u64 *peq, const u64 *peq_fw) {
+SMX_HD int primer_forward_classic(const Tables &t, const Batch &b, u32 read, int strand, int primer, const u64 *peq) {
     const int n = (int)b.lengths[read];
     const Geo g = make_geo(n, t.L);
-    const int m = t.p_len[primer], k = t.p_k[primer];
+    const int m = t.p_len[primer];
     const u32 slot = slot_index(t, strand, primer);
-    const u64 hit_idx = (u64)slot * b.n_pad + read;
     const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
     u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
     u32 *imask = b.impmask + (u64)slot * t.mw * b.n_pad + read;
@@ -181,12 +196,24 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
         emask[(u64)mwi * b.n_pad] = eqh;
         imask[(u64)mwi * b.n_pad] = imh;
     }
+    return best;
+}
 
+// From the column histories to the primer hit: the last improvement is the first equal-best end,
+// equality bits before it are stale.  Returns the number of equal-best end locations (0 = no
+// match within k); the start of the first location is recovered later by primer_start_thread.
+SMX_HD int primer_tail(const Tables &t, const Batch &b, u32 read, int strand, int primer, int best) {
+    const int n = (int)b.lengths[read];
+    const Geo g = make_geo(n, t.L);
+    const int k = t.p_k[primer];
+    const u32 slot = slot_index(t, strand, primer);
+    const u64 hit_idx = (u64)slot * b.n_pad + read;
+    u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
+    const u32 *imask = b.impmask + (u64)slot * t.mw * b.n_pad + read;
     smx_primer_hit h;
     h.distance = -1; h.n_locations = 0; h.first_start = 0; h.first_end = 0;
     int nloc = 0;
     if (best <= k) {
-        // last improvement = first equal-best end; equality bits before it are stale
         int first = 0;
         for (int mwi = t.mw - 1; mwi >= 0; --mwi) {
             u32 v = imask[(u64)mwi * b.n_pad];
@@ -206,9 +233,16 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
         h.first_start = h.first_end;                       // filled in by primer_start_thread
     }
     b.phit[hit_idx] = h;
+    return nloc;
+}
 
-    // determine_orientation (demultiplex.py:602-638), explicit form, only where the tail-window
-    // equivalence does not hold: reads shorter than search_len-1 (Q1) or with non-ACGT symbols.
+// determine_orientation (demultiplex.py:602-638), explicit form, only where the tail-window
+// equivalence does not hold: reads shorter than search_len-1 (Q1) or with non-ACGT symbols.
+template <typename W>
+SMX_HD void primer_orient_explicit(const Tables &t, const Batch &b, u32 read, int strand, int primer, const u64 *peq_fw) {
+    const int n = (int)b.lengths[read];
+    const Geo g = make_geo(n, t.L);
+    const int m = t.p_len[primer], k = t.p_k[primer];
     unsigned char ohit = 0;
     if (t.preorient && (!g.regular || read_is_flagged(b, read))) {
         int cols = n < t.L ? n : t.L;
@@ -221,7 +255,233 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
         }
         ohit = bst <= k;
     }
-    b.orient_hit[hit_idx] = ohit;
+    b.orient_hit[(u64)slot_index(t, strand, primer) * b.n_pad + read] = ohit;
+}
+
+// The whole classic stage-1 search of one (read, strand, primer).
+template <typename W>
+SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
+                                const u64 *peq, const u64 *peq_fw) {
+    int best = primer_forward_classic<W>(t, b, read, strand, primer, peq);
+    int nloc = primer_tail(t, b, read, strand, primer, best);
+    primer_orient_explicit<W>(t, b, read, strand, primer, peq_fw);
+    return nloc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1, sliced form: the HW search evaluated BIT-SLICED ACROSS READS.  One thread owns a group
+// of 32 reads (bit r of every word = read 32*group + r) and one (strand, primer); a Myers/Hyyro
+// cell update (6 three-input logic ops) advances cell (i, j) of all 32 windows at once, so a
+// column of an m-row pattern costs 6m + ~20 integer ops per 32 reads instead of ~29 per read.
+// Only reads whose window is the regular full-length A/C/G/T case take part (n >= search_len,
+// not on the 4-bit side stream); the others run the classic per-thread search.
+//
+// Per block of 16 columns: the group's 32 two-bit window words are transposed in registers into
+// 32 bit-planes (2 per column), the 16 columns are evaluated, each column's "equal to the running
+// best" / "improved the running best" planes replace the consumed input planes, and one more
+// transpose turns them into a per-read word of interleaved (equal, improved) bits.  The running
+// best itself is never materialised: best = m - (number of improvements).
+
+// In-register 32x32 bit-matrix transpose: afterwards bit r of a[c] is the former bit c of a[r].
+SMX_HD void transpose32(u32 (&a)[32]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int s = 0; s < 5; ++s) {
+        const int j = 16 >> s;
+        const u32 m = s == 0 ? 0x0000FFFFu : s == 1 ? 0x00FF00FFu : s == 2 ? 0x0F0F0F0Fu : s == 3 ? 0x33333333u : 0x55555555u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 32; ++k) {
+            if (k & j) continue;
+            u32 x = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k + j] ^= x;
+            a[k] ^= x << j;
+        }
+    }
+}
+
+// Byte offsets (into the thread's code-plane scratch) of the Eq plane of every pattern row.
+struct RowOffsets { unsigned short off[32]; };
+
+constexpr int kSlicedCodes = 15;        // scratch planes per thread: one per IUPAC pattern code
+
+template <int M> struct SlicedBits { static constexpr int NB = M < 2 ? 1 : M < 4 ? 2 : M < 8 ? 3 : M < 16 ? 4 : M < 32 ? 5 : 6; };
+
+// sp: this thread's kSlicedCodes code planes, sa: its 32-word plane buffer (both with element
+// stride STRIDE: shared memory columns on the GPU).  The column loop and the two transposes are
+// kept ROLLED: the generation that unrolled 16 columns was instruction-fetch bound (ncu:
+// stall_no_instruction the top stall at 40 % issue utilisation).
+template <int M, int STRIDE>
+SMX_HD void primer_sliced_thread(const Tables &t, const Batch &b, u32 group, int strand, int primer,
+                                 const RowOffsets &ro, bool degenerate, u32 *sp, u32 *sa) {
+    constexpr int NB = SlicedBits<M>::NB;
+    const u32 slot = slot_index(t, strand, primer);
+    u32 VP[M], VM[M];                                   // vertical deltas of the previous column
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < M; ++i) { VP[i] = ~0u; VM[i] = 0u; }        // D[i][0] = i
+    u32 d[NB];                                          // score - running best, bit-sliced
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NB; ++q) d[q] = 0u;
+    u32 zero = ~0u;                                     // score == running best
+    for (int blk = 0; blk < t.nw2; ++blk) {
+        u32 a[32];
+        const u32 *src = b.win2 + ((u64)strand * t.nw2 + blk) * b.n_pad + (u64)group * 32;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+            uint4 v = *reinterpret_cast<const uint4 *>(src + r);
+            a[r] = v.x; a[r + 1] = v.y; a[r + 2] = v.z; a[r + 3] = v.w;
+        }
+#else
+        for (int r = 0; r < 32; ++r) a[r] = src[r];
+#endif
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int phase = 0; phase < 2; ++phase) {
+            // phase 0: reads x code bits -> code-bit planes x reads; phase 1: column results -> per-read words
+            transpose32(a);
+            if (phase) break;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < 32; ++r) sa[r * STRIDE] = a[r];     // sa[2c] / sa[2c+1]: low / high code bit of column c
+            int ncols = t.L - blk * 16;
+            ncols = ncols > 16 ? 16 : ncols;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int c = 0; c < ncols; ++c) {
+                const u32 b0 = sa[(2 * c) * STRIDE], b1 = sa[(2 * c + 1) * STRIDE];
+                sp[0 * STRIDE] = ~(b0 | b1);            // A
+                sp[1 * STRIDE] = b0 & ~b1;              // C
+                sp[2 * STRIDE] = b1 & ~b0;              // G
+                sp[3 * STRIDE] = b0 & b1;               // T
+                if (degenerate) {                       // uniform; IUPAC base sets (constants.py:13-20)
+                    sp[4 * STRIDE] = ~b0;               // R = A|G
+                    sp[5 * STRIDE] = b0;                // Y = C|T
+                    sp[6 * STRIDE] = b0 ^ b1;           // S = C|G
+                    sp[7 * STRIDE] = ~(b0 ^ b1);        // W = A|T
+                    sp[8 * STRIDE] = b1;                // K = G|T
+                    sp[9 * STRIDE] = ~b1;               // M = A|C
+                    sp[10 * STRIDE] = b0 | b1;          // B = not A
+                    sp[11 * STRIDE] = ~(b0 & ~b1);      // D = not C
+                    sp[12 * STRIDE] = ~(b1 & ~b0);      // H = not G
+                    sp[13 * STRIDE] = ~(b0 & b1);       // V = not T
+                    sp[14 * STRIDE] = ~0u;              // N
+                }
+                u32 Ph = 0u, Mh = 0u;                   // row 0: D[0][j] = 0 (HW)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int i = 0; i < M; ++i) {
+                    const u32 Eq = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(sp) + ro.off[i]);
+                    const u32 Pv = VP[i], Mv = VM[i];
+                    const u32 Xv = Eq | Mv, Xh = Eq | Mh;
+                    VP[i] = Mh | ~(Xv | Ph);
+                    VM[i] = Ph & Xv;
+                    const u32 nPh = Mv | ~(Xh | Pv);
+                    Mh = Pv & Xh;
+                    Ph = nPh;
+                }
+                // score += Ph - Mh against the running best: the difference saturates at 0 from below
+                const u32 imp = Mh & zero, dec = Mh & ~zero;
+                u32 x = Ph | dec;
+                u32 carry = d[0] & x;
+                d[0] ^= x;
+                u32 any = d[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int q = 1; q < NB; ++q) {          // + (dec ? all-ones : 0) + carry
+                    const u32 sum = d[q] ^ dec ^ carry;
+                    carry = (d[q] & dec) | (d[q] & carry) | (dec & carry);
+                    d[q] = sum;
+                    any |= sum;
+                }
+                zero = ~any;
+                sa[(2 * c) * STRIDE] = zero;
+                sa[(2 * c + 1) * STRIDE] = imp;
+            }
+            for (int c = ncols; c < 16; ++c) { sa[(2 * c) * STRIDE] = 0u; sa[(2 * c + 1) * STRIDE] = 0u; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < 32; ++r) a[r] = sa[r * STRIDE];
+        }
+        // a[r]: read r's interleaved (equal, improved) bits of the block's 16 columns
+        u32 *dst = b.tmix + ((u64)slot * t.nw2 + blk) * b.n_pad + (u64)group * 32;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) *reinterpret_cast<uint4 *>(dst + r) = make_uint4(a[r], a[r + 1], a[r + 2], a[r + 3]);
+#else
+        for (int r = 0; r < 32; ++r) dst[r] = a[r];
+#endif
+    }
+}
+
+SMX_HD u32 compress_even_bits(u32 x) {                 // bits 0,2,4,.. -> bits 0..15
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
+SMX_HD bool sliced_eligible(const Tables &t, const Batch &b, u32 read) {
+    return t.sliced && !read_is_flagged(b, read) && (int)b.lengths[read] >= t.L;
+}
+
+// Stage 1 per (read, strand, primer) after the sliced pass: eligible reads decode their column
+// histories from tmix, every other read runs the classic search.  Returns the number of
+// equal-best end locations.
+template <typename W>
+SMX_HD int primer_finish_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
+                                const u64 *peq, const u64 *peq_fw) {
+    if (!sliced_eligible(t, b, read)) return primer_search_thread<W>(t, b, read, strand, primer, peq, peq_fw);
+    const u32 slot = slot_index(t, strand, primer);
+    const u64 hit_idx = (u64)slot * b.n_pad + read;
+    u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
+    const u32 *mix = b.tmix + (u64)slot * t.nw2 * b.n_pad + read;
+    // pass 1: number of improvements (-> best) and the column of the last one (-> first equal-best end)
+    int improvements = 0, first = 0;
+    for (int blk = 0; blk < t.nw2; ++blk) {
+        const u32 im = compress_even_bits(mix[(u64)blk * b.n_pad] >> 1);
+        improvements += popcount32(im);
+        if (im) first = blk * 16 + 31 - count_leading_zeros32(im);
+    }
+    const int best = (int)t.p_len[primer] - improvements;
+    b.orient_hit[hit_idx] = 0;                          // eligible reads never need the explicit test
+    smx_primer_hit h;
+    h.distance = -1; h.n_locations = 0; h.first_start = 0; h.first_end = 0;
+    int nloc = 0;
+    if (best <= t.p_k[primer]) {
+        // pass 2: equality bits from the last improvement on are the equal-best ends
+        for (int mwi = 0; mwi < t.mw; ++mwi) {
+            u32 v = compress_even_bits(mix[(u64)(2 * mwi) * b.n_pad]);
+            if (2 * mwi + 1 < t.nw2) v |= compress_even_bits(mix[(u64)(2 * mwi + 1) * b.n_pad]) << 16;
+            const int lo = mwi * 32;
+            if (lo + 32 <= first) v = 0;
+            else if (lo < first) v &= ~0u << (first - lo);
+            emask[(u64)mwi * b.n_pad] = v;
+            nloc += popcount32(v);
+        }
+        const Geo g = make_geo((int)b.lengths[read], t.L);
+        h.distance = (int16_t)best;
+        h.n_locations = (uint16_t)nloc;
+        h.first_end = g.woff + first + g.delta;
+        h.first_start = h.first_end;                    // filled in by primer_start_thread
+    } else {
+        for (int mwi = 0; mwi < t.mw; ++mwi) emask[(u64)mwi * b.n_pad] = 0;
+    }
+    b.phit[hit_idx] = h;
     return nloc;
 }
 
@@ -547,18 +807,47 @@ SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u
 // several contexts / pipeline lanes can be in flight on one device without sharing a symbol.
 #define SMX_KARGS const __grid_constant__ Tables c_tables, const __grid_constant__ Batch b
 
-__global__ void k_stage_windows(SMX_KARGS) {
-    // grid: x over reads, y over (strand, word)
+__global__ void __launch_bounds__(128) k_stage_windows(SMX_KARGS) {
+    // grid: x over reads, y over (strand, 16-symbol word)
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     if (read >= b.n_reads) return;
-    int strand = blockIdx.y / c_tables.wpw, w = blockIdx.y % c_tables.wpw;
-    stage_window_word(c_tables, b, read, strand, w);
+    int strand = blockIdx.y / c_tables.nw2, w2 = blockIdx.y % c_tables.nw2;
+    stage_window_pair(c_tables, b, read, strand, w2);
+}
+
+// Sliced primer search: one thread per (group of 32 reads, strand) for one primer of length M.
+constexpr int kSlicedBlock = 64;        // small blocks: equal-length tasks, let the block scheduler balance the SMs
+template <int M>
+__global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
+    __shared__ u32 s_planes[(kSlicedCodes + 32) * kSlicedBlock];
+    const u32 group = blockIdx.x * kSlicedBlock + threadIdx.x;
+    if (group >= b.n_pad / 32) return;
+    primer_sliced_thread<M, kSlicedBlock>(c_tables, b, group, (int)blockIdx.y, primer, ro, degenerate != 0,
+                                          s_planes + threadIdx.x, s_planes + kSlicedCodes * kSlicedBlock + threadIdx.x);
+}
+
+constexpr int kFinishBlock = 256;
+
+// Block-wide sum of a 64-bit value into one atomicAdd (same-address atomics from every warp were
+// the top stall of this kernel: ncu source view, 35 % of samples on the atomic's return).
+__device__ __forceinline__ void block_counter_add(unsigned long long v, unsigned long long *dst, unsigned long long *s_tmp /*32*/) {
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < (blockDim.x >> 5) ? s_tmp[threadIdx.x] : 0ull;
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0 && v) atomicAdd(dst, v);
+    }
+    __syncthreads();
 }
 
 template <typename W>
-__global__ void __launch_bounds__(128) k_primer_search(SMX_KARGS) {
+__global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
     // grid: x over reads, y = strand * n_primers + primer
     __shared__ u64 s_peq[3][16];
+    __shared__ u32 s_wtot[kFinishBlock / 32 + 1];
+    __shared__ unsigned long long s_tmp[32];
     const int primer = blockIdx.y % c_tables.n_primers, strand = blockIdx.y / c_tables.n_primers;
     if (threadIdx.x < 48) {
         const u64 *src = threadIdx.x < 16 ? c_tables.peq_rc : threadIdx.x < 32 ? c_tables.peq_rcrev : c_tables.peq_fw;
@@ -569,33 +858,33 @@ __global__ void __launch_bounds__(128) k_primer_search(SMX_KARGS) {
     unsigned long long cells = 0;
     int nloc = 0;
     if (read < b.n_reads) {
-        nloc = primer_search_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2]);
+        nloc = primer_finish_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2]);
         int n = (int)b.lengths[read];
         cells = (unsigned long long)(n < c_tables.L ? n : c_tables.L);       // HW columns of this search
     }
-    // work entries, one per equal-best end location: warp-aggregated allocation, a read's entries
-    // stay consecutive (the order of reads inside the list is irrelevant)
+    // work entries, one per equal-best end location: block-aggregated allocation (one atomic per
+    // block), a read's entries stay consecutive (the order of reads inside the list is irrelevant)
     {
-        const int lane = threadIdx.x & 31;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         int incl = nloc;
         for (int o = 1; o < 32; o <<= 1) {
             int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(&b.slot_count[blockIdx.y], (u32)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (nloc) write_entries(c_tables, b, blockIdx.y, read, base + (u32)(incl - nloc));
+        if (lane == 31) s_wtot[warp] = (u32)incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (int w = 0; w < kFinishBlock / 32; ++w) { u32 v = s_wtot[w]; s_wtot[w] = run; run += v; }
+            u32 base = run ? atomicAdd(&b.slot_count[blockIdx.y], run) : 0u;
+            s_wtot[kFinishBlock / 32] = base;
         }
+        __syncthreads();
+        if (nloc) write_entries(c_tables, b, blockIdx.y, read, s_wtot[kFinishBlock / 32] + s_wtot[warp] + (u32)(incl - nloc));
     }
-    for (int o = 16; o; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
-    if ((threadIdx.x & 31) == 0 && cells) {
-        int m = c_tables.p_len[primer];
-        atomicAdd(&b.counters[0], cells * (unsigned long long)m);
-        atomicAdd(&b.counters[2], cells * (unsigned long long)((m + 31) >> 5));
-    }
+    const int m = c_tables.p_len[primer];
+    block_counter_add(cells * (unsigned long long)m, &b.counters[0], s_tmp);
+    block_counter_add(cells * (unsigned long long)((m + 31) >> 5), &b.counters[2], s_tmp);
 }
 
 // Start recovery over the compact work-entry lists (full warps instead of the ~50 % matched lanes).
@@ -634,14 +923,9 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(SMX_KARGS) {
         const int p = b.ent_pos[(u64)slot * b.e_cap + idx];
         barcode_bitsliced_thread<K>(t, b, read, p, idx, strand, primer, g, s_beq, cells, wcols);
     }
-    for (int o = 16; o; o >>= 1) {
-        cells += __shfl_down_sync(0xffffffffu, cells, o);
-        wcols += __shfl_down_sync(0xffffffffu, wcols, o);
-    }
-    if ((threadIdx.x & 31) == 0 && cells) {
-        atomicAdd(&b.counters[1], cells);
-        atomicAdd(&b.counters[3], wcols);
-    }
+    __shared__ unsigned long long s_tmp[32];
+    block_counter_add(cells, &b.counters[1], s_tmp);
+    block_counter_add(wcols, &b.counters[3], s_tmp);
 }
 
 // Stage 3a: digest of every matched slot's hit lists (one thread per (read, slot), high occupancy).

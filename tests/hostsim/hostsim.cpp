@@ -21,9 +21,9 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     HostTables ht;
     if (!ht.build(tb, pr)) { snprintf(g_err, sizeof(g_err), "%s", ht.error.c_str()); return SMX_ERR_ARG; }
     const Tables &t = ht.t;
-    const u32 n = in->n_reads, n_pad = n;
+    const u32 n = in->n_reads, n_pad = (n + 31u) & ~31u;      // whole groups of 32 reads for the sliced search
     const int nP = t.n_primers;
-    std::vector<u32> win((size_t)2 * t.wpw * n_pad), endmask((size_t)2 * nP * t.mw * n_pad), impmask((size_t)2 * nP * t.mw * n_pad), rec_count(n), rec_offset(n + 1);
+    std::vector<u32> win((size_t)2 * t.wpw * n_pad), win2((size_t)2 * t.nw2 * n_pad, 0), tmix((size_t)2 * nP * t.nw2 * n_pad + 1, 0), endmask((size_t)2 * nP * t.mw * n_pad), impmask((size_t)2 * nP * t.mw * n_pad), rec_count(n), rec_offset(n + 1);
     std::vector<smx_primer_hit> phit((size_t)2 * nP * n_pad);
     std::vector<unsigned char> orient_hit((size_t)2 * nP * n_pad), flags(n);
     std::vector<u32> slot_count((size_t)2 * nP + 1, 0), ent_base((size_t)2 * nP * n_pad + 1), ent_read;
@@ -38,14 +38,36 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     b.packed2 = in->packed2; b.word_off = in->word_off; b.lengths = in->lengths;
     bool flagged = in->packed4 && in->off4 && in->packed4_words;
     b.packed4 = flagged ? in->packed4 : nullptr; b.off4 = flagged ? in->off4 : nullptr;
-    b.win = win.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.impmask = impmask.data(); b.orient_hit = orient_hit.data();
+    b.win = win.data(); b.win2 = win2.data(); b.tmix = tmix.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.impmask = impmask.data(); b.orient_hit = orient_hit.data();
     b.slot_count = slot_count.data(); b.ent_base = ent_base.data();
     b.rec_count = rec_count.data(); b.rec_offset = rec_offset.data();
     b.read_flags = flags.data(); b.counters = counters;
 
     for (u32 r = 0; r < n; ++r)
         for (int s = 0; s < 2; ++s)
-            for (int w = 0; w < t.wpw; ++w) stage_window_word(t, b, r, s, w);
+            for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, r, s, w2);
+    if (t.sliced)       // forward pass bit-sliced across reads: one "thread" per (group of 32 reads, strand, primer)
+        for (int p = 0; p < nP; ++p) {
+            RowOffsets ro;
+            bool degenerate = false;
+            for (int i = 0; i < 32; ++i) {
+                int code = i < t.p_len[p] ? ht.prow_code[(size_t)p * 32 + i] : 0;
+                degenerate |= code > 3;
+                ro.off[i] = (unsigned short)(code * sizeof(u32));
+            }
+            u32 scratch[kSlicedCodes], planes[32];
+            for (int s = 0; s < 2; ++s)
+                for (u32 g = 0; g < n_pad / 32; ++g)
+                    switch (t.p_len[p]) {
+#define SMX_M(MM) case MM: primer_sliced_thread<MM, 1>(t, b, g, s, p, ro, degenerate, scratch, planes); break;
+                        SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
+                        SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
+                        SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
+                        SMX_M(32)
+#undef SMX_M
+                        default: snprintf(g_err, sizeof(g_err), "sliced primer length"); return SMX_ERR_INTERNAL;
+                    }
+        }
     Tables &tm = ht.t;
     for (;;) {      // stage 1 + 2, re-run on capacity overflow exactly as the CUDA library does
         ent_read.assign((size_t)2 * nP * e_cap + 1, 0); ent_pos.assign((size_t)2 * nP * e_cap + 1, 0);
@@ -59,8 +81,8 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
             for (int p = 0; p < nP; ++p)
                 for (u32 r = 0; r < n; ++r) {
                     int nloc;
-                    if (t.use64) nloc = primer_search_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
-                    else nloc = primer_search_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
+                    if (t.use64) nloc = primer_finish_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
+                    else nloc = primer_finish_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
                     if (nloc) {
                         u32 slot = (u32)(s * nP + p);
                         write_entries(t, b, slot, r, slot_count[slot]);
@@ -145,8 +167,13 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     }
     if (out->rec_offset) memcpy(out->rec_offset, rec_offset.data(), (size_t)(n + 1) * sizeof(u32));
     if (out->records && total) memcpy(out->records, records.data(), total * sizeof(smx_record));
-    if (out->primer_hits) memcpy(out->primer_hits, phit.data(), phit.size() * sizeof(smx_primer_hit));
-    if (out->endmask_bits) memcpy(out->endmask_bits, endmask.data(), endmask.size() * sizeof(u32));
+    // level-1 detail is kept padded ([row][n_pad]) and returned dense ([row][n])
+    if (out->primer_hits)
+        for (size_t row = 0; row < (size_t)2 * nP; ++row)
+            memcpy(out->primer_hits + row * n, phit.data() + row * n_pad, (size_t)n * sizeof(smx_primer_hit));
+    if (out->endmask_bits)
+        for (size_t row = 0; row < (size_t)2 * nP * t.mw; ++row)
+            memcpy(out->endmask_bits + row * n * sizeof(u32), endmask.data() + row * n_pad, (size_t)n * sizeof(u32));
     if (out->barcode_hits && t.total_bslots) {
         smx_barcode_hit none;
         none.end_mask = 0; none.search_start = 0; none.distance = -1; none.barcode = 0;
