@@ -221,6 +221,7 @@ def main():
         wall_ms = (time.perf_counter() - t_wall) * 1000.0 / args.steps     # includes the L2 flushes
     barrier()
     launches = matcher.last_launch_count()
+    deferred = matcher.last_deferred()
     cells, wcols = matcher.last_work()
     res = matcher.download()
     ms = float(np.mean(step_ms))
@@ -289,6 +290,7 @@ def main():
             "gpu_launches": int(launches * args.steps),
             "clocks": clocks.summary(),
             "records_per_step": int(len(res.records)), "matched_reads": int(res.n_matched),
+            "reads_on_general_selection_path": int(deferred),
         }
         if not args.no_cpu_baseline and world == 1:
             from oracle import cpu_bench

@@ -224,6 +224,10 @@ int smx_match_batch(smx_ctx *ctx, const smx_batch *batch, smx_results *out);
 int smx_set_pipeline_chunk(smx_ctx *ctx, uint32_t reads_per_chunk);
 int smx_last_chunk_count(const smx_ctx *ctx);   /* chunks used by the last smx_match_batch */
 
+/* Reads of the last smx_run_resident that left the fast selection kernel for the general one
+ * (several equal-best candidates, tied barcodes, TAILS trimming): a tuning statistic. */
+uint64_t smx_last_deferred(const smx_ctx *ctx);
+
 /* Split form of smx_match_batch for pipelining and device-resident timing. */
 int smx_upload_batch(smx_ctx *ctx, const smx_batch *batch);   /* H2D only                         */
 int smx_run_resident(smx_ctx *ctx);                           /* kernels only, on the last upload  */

@@ -66,7 +66,7 @@ template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) 
 // rotate over all lanes so one chunk's H2D, another's kernels and a third's D2H overlap.
 constexpr int kLanes = 3;
 constexpr int kAuxStreams = 2;
-constexpr size_t kCtlWords = 8 + SMX_MAX_PRIMERS;     // unsigned long long words of a lane's control block
+constexpr size_t kCtlWords = kCtrWords + SMX_MAX_PRIMERS;     // unsigned long long words of a lane's control block
 
 struct Lane {
     cudaStream_t stream = nullptr;          // H2D + kernels
@@ -84,7 +84,7 @@ struct Lane {
     DevBuf<smx_barcode_hit> bh_list;
     DevBuf<u32> ent_base, ent_read, rec_extra, big_list;
     DevBuf<unsigned short> ent_pos;
-    DevBuf<SlotSum> ssum;
+    DevBuf<u32> defer_list;
     DevBuf<smx_record> rec_stage, rec_pool, records;
     DevBuf<unsigned char> big_scratch;
     // control block: 8 counters (4 work, matched, (u32,u32) overflow, (u32,u32) total/pool, hit overflow)
@@ -99,13 +99,14 @@ struct Lane {
     u64 n_records = 0, n_matched = 0;
     unsigned long long work[4] = {0, 0, 0, 0};
     int launches = 0;
+    u32 n_deferred = 0;
 
     void release() {
         packed2.release(); lengths.release(); packed4.release(); win.release(); win2.release(); tmix.release(); endmask.release(); impmask.release();
         rec_count.release(); rec_offset.release(); rec_offset_out.release(); block_sums.release(); word_off.release();
         off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
         ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
-        ent_pos.release(); ssum.release(); rec_stage.release(); rec_pool.release(); records.release();
+        ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release();
         big_scratch.release(); counters.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr; h_slot_counts = nullptr;
@@ -152,7 +153,7 @@ static cudaError_t lane_init(Lane &ln) {
     if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto &ev : ln.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     if ((e = cudaHostAlloc((void **)&ln.h_counters, kCtlWords * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
-    ln.h_slot_counts = (u32 *)(ln.h_counters + 8);
+    ln.h_slot_counts = (u32 *)(ln.h_counters + kCtrWords);
     if ((e = ln.counters.ensure(kCtlWords)) != cudaSuccess) return e;
     memset(&ln.b, 0, sizeof(ln.b));
     return cudaSuccess;
@@ -202,7 +203,7 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     CU(ln.impmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(ln.orient_hit.ensure((size_t)2 * nP * n_pad));
     CU(ln.ent_base.ensure((size_t)2 * nP * n_pad));
-    CU(ln.ssum.ensure((size_t)2 * nP * n_pad));
+    CU(ln.defer_list.ensure(n_pad));
     if (ln.e_cap < n_pad + n_pad / 4) ln.e_cap = n_pad + n_pad / 4;     // ~1.2 equal-best ends per matched slot is typical
     if (ln.pool_cap < n_pad / 8 + 1024) ln.pool_cap = n_pad / 8 + 1024;
     if (ln.hit_cap < c->t.hit_cap) ln.hit_cap = c->t.hit_cap;
@@ -225,7 +226,7 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     b.packed2 = ln.packed2.p; b.word_off = ln.word_off.p; b.lengths = ln.lengths.p;
     b.packed4 = flagged ? (shared4 ? shared4 : ln.packed4.p) : nullptr; b.off4 = flagged ? ln.off4.p : nullptr;
     b.win = ln.win.p; b.win2 = ln.win2.p; b.tmix = ln.tmix.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
-    b.slot_count = (u32 *)(ln.counters.p + 8); b.ent_base = ln.ent_base.p; b.ssum = ln.ssum.p;
+    b.slot_count = (u32 *)(ln.counters.p + kCtrWords); b.ent_base = ln.ent_base.p; b.defer_list = ln.defer_list.p;
     b.rec_stage = ln.rec_stage.p; b.rec_extra = ln.rec_extra.p;
     b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
     b.records = nullptr; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
@@ -312,7 +313,8 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     if (from <= 2) {   // stage 2
         if (from == 2) {                                                                                     // re-run
             CU(cudaMemsetAsync(ln.counters.p + 1, 0, sizeof(unsigned long long), st));
-            CU(cudaMemsetAsync(ln.counters.p + 3, 0, 5 * sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(ln.counters.p + 3, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(ln.counters.p + 7, 0, sizeof(unsigned long long), st));
         }
         if (timed) CU(cudaEventRecord(ln.ev[2], st));
         if (t.n_bwords) {
@@ -327,13 +329,19 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         }
     }
     // stage 3: slot digests, single-pass selection, scan
-    if (from == 3) CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));          // re-run
-    if (timed) CU(cudaEventRecord(ln.ev[3], st));
-    {
-        dim3 sgrid((n + 255) / 256, 2 * nP);
-        k_slot_summary<<<sgrid, 256, 0, st>>>(t, b);
+    if (from >= 2) {                                                                                           // re-run
+        CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p + kCtrDeferred, 0, sizeof(unsigned long long), st));
     }
-    if (nP <= 8) k_select<8><<<blocks, 128, 0, st>>>(t, b); else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
+    if (timed) CU(cudaEventRecord(ln.ev[3], st));
+    // fast path for (nearly) every read, then the general routine over the reads it deferred
+    if (nP <= 8) {
+        k_select_fast<8><<<blocks, 128, 0, st>>>(t, b);
+        k_select<8><<<blocks, 128, 0, st>>>(t, b);
+    } else {
+        k_select_fast<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
+        k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
+    }
     ln.launches += 2;
     CU(enqueue_scan_and_count(ln));
     return SMX_OK;
@@ -399,6 +407,7 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     }
     ln.n_records = (u32)ln.h_counters[6];
     ln.n_matched = ln.h_counters[4];
+    ln.n_deferred = (u32)ln.h_counters[kCtrDeferred];
     for (int i = 0; i < 4; ++i) ln.work[i] = ln.h_counters[i];
     return SMX_OK;
 }
@@ -743,6 +752,8 @@ int smx_set_pipeline_chunk(smx_ctx *c, uint32_t reads_per_chunk) {
 }
 
 int smx_last_chunk_count(const smx_ctx *c) { return c ? c->last_chunks : 0; }
+
+uint64_t smx_last_deferred(const smx_ctx *c) { return c ? c->lane[0].n_deferred : 0; }
 
 int smx_last_timing(const smx_ctx *c, float *total_ms, float stage_ms[4]) {
     if (!c) return fail(SMX_ERR_ARG, "smx_last_timing: null context");

@@ -29,7 +29,10 @@ constexpr int kSymOther = 15;       // read symbol that matches nothing (lower c
 constexpr int kNone = INT32_MIN;    // Python None in coordinates
 constexpr int kMaxPairs = 64;       // candidate slots per read = 2 * pairs
 constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in the first pass
-constexpr int kBigGroups = 4096;    // ... in the second pass over reads that overflowed the first
+constexpr int kBigGroups = 4096;
+// control block of a batch: kCtrWords 64-bit counters followed by the 2 * SMX_MAX_PRIMERS u32 per-slot entry counts
+constexpr int kCtrDeferred = 8;     // (u32) reads left to the general selection kernel
+constexpr int kCtrWords = 10;    // ... in the second pass over reads that overflowed the first
 
 // ---------------------------------------------------------------------------------------------
 // Symbols.  4-bit read codes: A0 C1 G2 T3 R4 Y5 S6 W7 K8 M9 B10 D11 H12 V13 N14 other15.
@@ -228,7 +231,7 @@ struct Batch {
     // Barcode hits of entry e for bword g, gslot = strand * n_bwords + g:
     unsigned char *bh_count; // [gslot * e_cap + e]; may exceed hit_cap (-> re-run with a larger cap)
     smx_barcode_hit *bh_list;    // [(gslot * hit_cap + h) * e_cap + e], ascending barcode position
-    SlotSum *ssum;           // [slot * n_pad + read]
+    u32 *defer_list;         // reads the fast selection kernel left to the general one (count: counters[kCtrDeferred])
     // single-pass selection: first record of every read + pool for the (rare) further records
     smx_record *rec_stage;   // [read]
     smx_record *rec_pool;    // extra records, contiguous per read
@@ -351,18 +354,19 @@ SMX_HD void spec_all(const Tables &t, u32 b1, u32 b2, int p1, int p2, int &count
 // Selection / dereplication / specimen resolution / trimming for one read
 // (demultiplex.py:126-210, 216-598; models.py:72-328).  One thread runs this per read.
 
-struct EndInfo {            // one (strand, primer) slot as seen by a candidate
-    int matched;
-    int pd;                 // primer distance
-    int ps, pe;             // first location, reported X coordinates
-    int nhits;              // barcodes within k_idx
-    int bd;                 // best barcode distance
-    int nbest;              // number of barcodes at bd
-    int first_best;         // list position of the first of them (pinned order)
-    int first_ss;           // barcode_search_start of that hit
-    u64 first_mask;         // its SHW end mask
-    int strand, primer;
+struct EndInfo {            // one (strand, primer) slot as seen by a candidate (kept small: it lives in local memory)
+    u64 first_mask;         // SHW end mask of the first equal-best barcode
+    int ps, pe;             // first primer location, reported X coordinates
+    int first_ss;           // barcode_search_start of the first equal-best barcode
+    int first_best;         // its list position (pinned order), -1 = none
+    short pd;               // primer distance
+    unsigned short nhits;   // barcodes within k_idx
+    unsigned short nbest;   // number of barcodes at bd
+    signed char bd;         // best barcode distance
+    unsigned char matched;
+    unsigned char strand, primer;
 };
+static_assert(sizeof(EndInfo) == 40, "EndInfo layout");
 
 struct SelectCtx {
     const Tables *t;
@@ -407,23 +411,46 @@ SMX_HD bool next_hit(const SelectCtx &c, int strand, int primer, int after_j, sm
     return found;
 }
 
-// Walks the hit lists of one matched slot once (summary kernel).
+// Digest of the hit lists of one matched slot in ONE pass over the per-(location, bword) sub-lists.
+// A barcode found at several primer end locations keeps its strictly smallest distance, ties the
+// earliest location (demultiplex.py:786-812); the best distance over the merged barcodes is simply
+// the minimum over all hits, the equal-best barcodes are those with some hit at that distance, the
+// first of them (pinned order) is the smallest list position, and its location is the earliest one
+// carrying that hit.  nhits counts hits (only zero / non-zero is ever used); nbest is exact for a
+// single location and saturates at 2 otherwise (only 0 / 1 / more is ever used).
 SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &o) {
     o.first_mask = 0; o.first_ss = 0; o.first_best = 0; o.nhits = 0; o.nbest = 0; o.bd = -1; o.pad = 0;
-    int bd = 1 << 20, nhits = 0, nbest = 0;
-    smx_barcode_hit h;
-    int after = -1;
-    while (next_hit(c, strand, primer, after, h)) {
-        after = (int)h.barcode;
-        int d = h.distance;
-        ++nhits;
-        if (d < bd) { bd = d; nbest = 0; }
-        if (d == bd) {
-            if (nbest == 0) { o.first_best = (unsigned short)after; o.first_mask = h.end_mask; o.first_ss = h.search_start; }
-            ++nbest;
+    const Tables &t = *c.t;
+    const Batch &b = *c.b;
+    const u32 slot = (u32)(strand * t.n_primers + primer);
+    const u64 hidx = (u64)slot * b.n_pad + c.read;
+    const u32 e0 = b.ent_base[hidx];
+    u32 nloc = b.phit[hidx].n_locations;
+    if (e0 >= b.e_cap) return;
+    if (e0 + nloc > b.e_cap) nloc = b.e_cap - e0;
+    int bd = 1 << 20, nhits = 0, count = 0, jmin = 1 << 20, jmax = -1;
+    for (u32 l = 0; l < nloc; ++l) {
+        const u64 e = (u64)e0 + l;
+        for (u32 g = t.bw_off[primer]; g < t.bw_off[primer + 1]; ++g) {
+            const u64 gslot = (u64)strand * t.n_bwords + g;
+            int cnt = b.bh_count[gslot * b.e_cap + e];
+            if (cnt > t.hit_cap) cnt = t.hit_cap;
+            for (int x = 0; x < cnt; ++x) {
+                const smx_barcode_hit &h = b.bh_list[(gslot * t.hit_cap + x) * b.e_cap + e];
+                const int d = h.distance, j = (int)h.barcode;
+                ++nhits;
+                if (d < bd) { bd = d; count = 0; jmin = 1 << 20; jmax = -1; }
+                if (d == bd) {
+                    ++count;
+                    if (j < jmin) { jmin = j; o.first_best = h.barcode; o.first_mask = h.end_mask; o.first_ss = h.search_start; }
+                    if (j > jmax) jmax = j;
+                }
+            }
         }
     }
-    if (nhits) o.bd = (signed char)bd;
+    if (!nhits) return;
+    const int nbest = nloc == 1 ? count : (jmin == jmax ? 1 : 2);
+    o.bd = (signed char)bd;
     o.nhits = (unsigned short)(nhits > 65535 ? 65535 : nhits);
     o.nbest = (unsigned short)(nbest > 65535 ? 65535 : nbest);
 }
@@ -432,12 +459,13 @@ SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
     const Tables &t = *c.t;
     const u64 idx = (u64)slot_index(t, strand, primer) * c.b->n_pad + c.read;
     const smx_primer_hit &ph = c.b->phit[idx];
-    e.strand = strand; e.primer = primer;
+    e.strand = (unsigned char)strand; e.primer = (unsigned char)primer;
     e.matched = ph.distance >= 0;
     e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
     e.nhits = 0; e.bd = -1; e.nbest = 0; e.first_best = -1; e.first_ss = 0; e.first_mask = 0;
     if (!e.matched) return;
-    const SlotSum &ss = c.b->ssum[idx];
+    SlotSum ss;
+    summarize_slot(c, strand, primer, ss);
     e.nhits = ss.nhits; e.bd = ss.bd; e.nbest = ss.nbest;
     e.first_best = ss.nhits ? (int)ss.first_best : -1; e.first_ss = ss.first_ss; e.first_mask = ss.first_mask;
 }
@@ -528,6 +556,7 @@ SMX_HD void tails_fold(const SelectCtx &c, const EndInfo &e, bool is_b1, int shi
     }
 }
 
+template <bool kWithTails = true>
 SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &overflow,
                         int cand_idx, const Cand &cd, const EndInfo &e1, const EndInfo &e2,
                         int sample, int resolution, int pool) {
@@ -561,8 +590,10 @@ SMX_HD void emit_record(const SelectCtx &c, Emitter &em, TrimState &ts, bool &ov
             e = m2 ? p2e + 1 : n;
         } else {                                    // models.py:300-319
             int fs = -1, fe = -1;
-            tails_fold(c, e1, true, shift, fs);
-            tails_fold(c, e2, false, shift, fe);
+            if (kWithTails) {
+                tails_fold(c, e1, true, shift, fs);
+                tails_fold(c, e2, false, shift, fe);
+            }
             if (fs == -1) { fs = ps - t.blen_max; if (fs < 0) fs = 0; }
             if (fe == -1) { fe = pe + t.blen_max; if (fe > n) fe = n; }
             s = fs; e = fe;
@@ -624,6 +655,30 @@ SMX_HD void resolve(const SelectCtx &c, const EndInfo &e1, const EndInfo &e2, in
     }
 }
 
+// resolve_specimen when each end has at most one equal-best barcode (then best_b1 / best_b2 are
+// the single barcodes of the digests and no hit list needs walking).
+SMX_HD void resolve_single(const SelectCtx &c, const EndInfo &e1, const EndInfo &e2, int pair_pool,
+                           int &sample, int &resolution, int &pool) {
+    const Tables &t = *c.t;
+    sample = -1; pool = pair_pool; resolution = SMX_RES_UNKNOWN;
+    bool b1 = e1.matched && e1.nhits > 0, b2 = e2.matched && e2.nhits > 0;
+    if (e1.matched && e2.matched && b1 && b2) {
+        int count = 0, min_row = -1;
+        spec_all(t, t.pb_barcode[t.pb_off[e1.primer] + e1.first_best], t.pb_barcode[t.pb_off[e2.primer] + e2.first_best],
+                 e1.primer, e2.primer, count, min_row);
+        if (count > 1) { sample = min_row; resolution = SMX_RES_MULTIPLE_SPECIMENS; pool = t.spec_pool[min_row]; }
+        else if (count == 1) { sample = min_row; resolution = SMX_RES_FULL_MATCH; pool = t.spec_pool[min_row]; }
+        return;
+    }
+    if (b1 && !b2 && e1.nbest == 1) {
+        resolution = SMX_RES_PARTIAL_FORWARD;
+        sample = (int)t.pb_barcode[t.pb_off[e1.primer] + e1.first_best];
+    } else if (b2 && !b1 && e2.nbest == 1) {
+        resolution = SMX_RES_PARTIAL_REVERSE;
+        sample = (int)t.pb_barcode[t.pb_off[e2.primer] + e2.first_best];
+    }
+}
+
 struct Group {      // one dereplication group (demultiplex.py:322-382 / :416-467)
     int key;        // specimen row, or for partial groups (direction << 30 | global barcode id)
     int cand;       // best candidate so far
@@ -646,9 +701,14 @@ struct SelectStore {
     int cap;
 };
 
+constexpr unsigned char kFlagDeferred = 8;   // fast-only pass: the read needs the general routine
+
 // Whole per-read selection.  ends: cache of 2*n_primers EndInfo (index strand*n_primers+primer).
-SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, u32 out_cap,
-                       unsigned char &flags) {
+// kFastOnly = true compiles only the common single-candidate path (no grouping, no list walks,
+// no TAILS fold): reads that need more come back with flags = kFlagDeferred and no record.
+template <bool kFastOnly>
+SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, u32 out_cap,
+                            unsigned char &flags) {
     const Tables &t = *c.t;
     const Batch &b = *c.b;
     Emitter em; em.out = out; em.cap = out_cap; em.count = 0; em.full = false;
@@ -658,6 +718,7 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st,
     flags = 0;
     const int kMaxGroups = st.cap;
     if ((t.min_length != -1 && n < t.min_length) || (t.max_length != -1 && n > t.max_length)) return 0;
+    if (kFastOnly && t.trim == SMX_TRIM_TAILS) { flags = kFlagDeferred; return 0; }     // the tails fold walks the hit lists
 
     Geo g = make_geo(n, t.L);
     bool irregular = !g.regular || read_is_flagged(b, c.read);
@@ -701,7 +762,7 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st,
         none.first_ss = 0; none.first_mask = 0;
         none.ps = none.pe = 0; none.strand = 0; none.primer = 0;
         Cand cd; cd.pair = -1; cd.rc = 0; cd.e1 = cd.e2 = 0;
-        emit_record(c, em, ts, overflow, 0, cd, none, none, -1, SMX_RES_UNKNOWN, -1);
+        emit_record<!kFastOnly>(c, em, ts, overflow, 0, cd, none, none, -1, SMX_RES_UNKNOWN, -1);
         if (overflow) flags |= 2;
         return em.count;
     }
@@ -742,15 +803,16 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st,
                 if (row >= 0) { sample = row; res = SMX_RES_DEREPLICATED_FULL; pool = t.spec_pool[row]; em.full = true; done = true; }
             }
             if (!done) {
-                resolve(c, a, z, t.pair_pool[top_cd.pair], sample, res, pool);
+                resolve_single(c, a, z, t.pair_pool[top_cd.pair], sample, res, pool);
                 if (res == SMX_RES_FULL_MATCH) em.full = true;
             }
-            emit_record(c, em, ts, overflow, top_idx, top_cd, a, z, sample, res, pool);
+            emit_record<!kFastOnly>(c, em, ts, overflow, top_idx, top_cd, a, z, sample, res, pool);
             if (em.full) flags |= 1;
             if (overflow) flags |= 2;
             return em.count;
         }
     }
+    if (kFastOnly) { flags = kFlagDeferred; return 0; }
 
     if (!t.derep_best) {
         for_each_top([&](int idx, const Cand &cd) {
@@ -898,6 +960,11 @@ SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st,
     if (em.full) flags |= 1;
     if (overflow) flags |= 2;
     return em.count;
+}
+
+SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, u32 out_cap,
+                       unsigned char &flags) {
+    return select_read_impl<false>(c, ends, st, out, out_cap, flags);
 }
 
 // Bytes of global scratch one read needs in the second pass.

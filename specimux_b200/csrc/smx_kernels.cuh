@@ -928,30 +928,62 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(SMX_KARGS) {
     block_counter_add(wcols, &b.counters[3], s_tmp);
 }
 
-// Stage 3a: digest of every matched slot's hit lists (one thread per (read, slot), high occupancy).
-__global__ void __launch_bounds__(256) k_slot_summary(SMX_KARGS) {
-    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
-    if (read >= b.n_reads) return;
-    const Tables &t = c_tables;
-    const int primer = blockIdx.y % t.n_primers, strand = blockIdx.y / t.n_primers;
-    const u64 idx = (u64)blockIdx.y * b.n_pad + read;
-    if (b.phit[idx].distance < 0) return;
-    SelectCtx c; c.t = &t; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
-    SlotSum ss;
-    summarize_slot(c, strand, primer, ss);
-    b.ssum[idx] = ss;
-}
-
 constexpr int kInlineRecords = 4;
 
-// Selection, single pass: one thread per read, working storage in thread-local arrays.  Records
-// are produced once into a small local buffer; the first goes to rec_stage[read], further ones
-// (rare) to a contiguous block of rec_pool.  Reads whose groups overflow kSmallGroups or that
+// Stage 3a, fast selection: one thread per read, only the common single-candidate path of the
+// selection routine (slot digests computed on the fly, no grouping, small register footprint so
+// the dependent global loads are hidden by occupancy).  Reads that need the general routine
+// (several equal-best candidates, tied barcodes, TAILS trimming) are appended to defer_list.
+template <int MAXP>
+__global__ void __launch_bounds__(128) k_select_fast(SMX_KARGS) {
+    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
+    bool defer = false;
+    if (read < b.n_reads) {
+        EndInfo ends[2 * MAXP];
+        int ts_cand[1], ts_shift[1];
+        smx_record rec;
+        SelectStore st;
+        st.groups = nullptr; st.gcand = nullptr; st.pg = nullptr; st.pcand = nullptr;
+        st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = 1;
+        SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
+        unsigned char flags;
+        u32 cnt = select_read_impl<true>(c, ends, st, &rec, 1, flags);
+        defer = (flags & kFlagDeferred) != 0;
+        if (!defer) {
+            b.rec_count[read] = cnt;
+            b.read_flags[read] = flags & 1;
+            if (cnt) {
+                uint4 *dst = reinterpret_cast<uint4 *>(b.rec_stage + read);
+                const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd((unsigned int *)&b.counters[kCtrDeferred], (u32)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (defer) b.defer_list[base + __popc(m & ((1u << lane) - 1))] = read;
+    }
+}
+
+// Stage 3b, general selection over the deferred reads: working storage in thread-local arrays.
+// Records are produced once into a small local buffer; the first goes to rec_stage[read], further
+// ones (rare) to a contiguous block of rec_pool.  Reads whose groups overflow kSmallGroups or that
 // emit more than kInlineRecords records are flagged (bit1) for k_select_big.
 template <int MAXP>
 __global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
-    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
-    if (read >= b.n_reads) return;
+    // The routine is long and branchy: when few reads are deferred they are spread one per 8 lanes
+    // so that a warp serialises 4 divergent reads instead of 32.
+    const u32 n_def = (u32)b.counters[kCtrDeferred];
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool spread = (u64)n_def * 8 <= (u64)gridDim.x * blockDim.x;
+    if (spread && (tid & 7)) return;
+    const u32 i = spread ? tid >> 3 : tid;
+    if (i >= n_def) return;
+    const u32 read = b.defer_list[i];
     EndInfo ends[2 * MAXP];
     Group groups[kSmallGroups], pg[kSmallGroups];
     Cand gcand[kSmallGroups], pcand[kSmallGroups];
@@ -972,7 +1004,7 @@ __global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
         u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt - 1);
         b.rec_extra[read] = base;
         if (base + cnt - 1 <= b.pool_cap)
-            for (u32 i = 1; i < cnt; ++i) b.rec_pool[base + i - 1] = local[i];
+            for (u32 i2 = 1; i2 < cnt; ++i2) b.rec_pool[base + i2 - 1] = local[i2];
     }
 }
 

@@ -194,6 +194,9 @@ class Matcher:
     def last_chunk_count(self) -> int:
         return int(self._lib.smx_last_chunk_count(self._ctx))
 
+    def last_deferred(self) -> int:
+        return int(self._lib.smx_last_deferred(self._ctx))
+
     def flush_l2(self):
         _lib.check(self._lib.smx_flush_l2(self._ctx))
 

@@ -31,7 +31,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     std::vector<unsigned char> bh_count;
     std::vector<smx_barcode_hit> bh_list;
     u32 e_cap = 16;        // deliberately tiny: exercises the capacity re-run
-    unsigned long long counters[8] = {0};
+    unsigned long long counters[kCtrWords] = {0};
     Batch b;
     memset(&b, 0, sizeof(b));
     b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len;
@@ -117,16 +117,6 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         if (tm.hit_cap >= kMaxWordHits) { snprintf(g_err, sizeof(g_err), "hit list overflow"); return SMX_ERR_INTERNAL; }
         tm.hit_cap = std::min(kMaxWordHits, tm.hit_cap * 4);
     }
-    std::vector<SlotSum> ssum((size_t)2 * nP * n_pad + 1);
-    b.ssum = ssum.data();
-    for (int s = 0; s < 2; ++s)
-        for (int p = 0; p < nP; ++p)
-            for (u32 r = 0; r < n; ++r) {
-                size_t idx = (size_t)(s * nP + p) * n_pad + r;
-                if (phit[idx].distance < 0) continue;
-                SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
-                summarize_slot(c, s, p, ssum[idx]);
-            }
     std::vector<unsigned char> big(kBigScratchBytes);
     auto run_select = [&](u32 r, smx_record *dst, unsigned char &f) -> u32 {
         SelectCtx c; c.t = &t; c.b = &b; c.read = r; c.n = (int)b.lengths[r];
@@ -137,6 +127,17 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         SelectStore st;
         st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
         st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
+        {   // the fast-only pass first, exactly as k_select_fast does; deferred reads take the general routine
+            SelectStore fst = st;
+            fst.cap = 1;
+            smx_record one;
+            u32 fc = select_read_impl<true>(c, ends, fst, dst ? &one : nullptr, 1, f);
+            if (!(f & kFlagDeferred)) {
+                if (dst && fc) dst[0] = one;
+                f &= 1;
+                return fc;
+            }
+        }
         u32 cnt = select_read(c, ends, st, dst, 0xFFFFFFFFu, f);
         if (f & 2) {            // second pass on the big scratch, as k_select_big does
             EndInfo *bends;
