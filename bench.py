@@ -165,8 +165,9 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        # Plumbing only (barrier + max-over-ranks of three timings): the data path has no collective
+        # (SURVEY.md 8e), so the CPU-side gloo backend is enough and keeps NCCL banners off stdout.
+        dist.init_process_group("gloo")
 
     from specimux_b200 import _lib
     from specimux_b200.engine import Matcher, PackedBatch
@@ -209,7 +210,7 @@ def main():
     for _ in range(args.warmup):
         matcher.run_resident()
     barrier()
-    step_ms, stage_ms = [], []
+    step_ms, stage_ms, kernel_ms = [], [], []
     with ClockSampler(local) as clocks:
         t_wall = time.perf_counter()
         for _ in range(args.steps):
@@ -218,6 +219,7 @@ def main():
             tot, st = matcher.last_timing()
             step_ms.append(tot)
             stage_ms.append(st)
+            kernel_ms.append(matcher.last_kernel_times())
         wall_ms = (time.perf_counter() - t_wall) * 1000.0 / args.steps     # includes the L2 flushes
     barrier()
     launches = matcher.last_launch_count()
@@ -242,7 +244,7 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+        t = torch.tensor([ms, e2e_ms, wall_ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
 
@@ -251,13 +253,24 @@ def main():
         value = total_reads / (ms / 1000.0)
         alg_ops = 15.0 * (wcols[0] + wcols[1])
         gcups = (cells[0] + cells[1]) / (ms / 1000.0) / 1e9
-        # the two DP kernels: stage 1 (primer HW) and stage 2 (barcode SHW); the dominant one by time
-        k_ops = {"primer_search": 15.0 * wcols[0], "barcode_search": 15.0 * wcols[1]}
-        k_ms = {"primer_search": st[1], "barcode_search": st[2]}
-        dom_name = max(k_ms, key=k_ms.get)
-        achieved = k_ops[dom_name] / (k_ms[dom_name] / 1000.0) / 1e12 if k_ms[dom_name] > 0 else 0.0
-        other = "barcode_search" if dom_name == "primer_search" else "primer_search"
-        other_achieved = k_ops[other] / (k_ms[other] / 1000.0) / 1e12 if k_ms[other] > 0 else 0.0
+        # per-kernel durations (CUDA events on the launching stream, mean over the timed steps)
+        kt = {k: float(np.mean([d[k] for d in kernel_ms])) for k in kernel_ms[0]}
+        # the two DP kernels: stage 1 forward pass (primer HW, bit-sliced across reads) and stage 2
+        # (barcode SHW, bit-sliced across barcodes); the dominant one by time carries the roofline
+        k_ops = {"primer_sliced": 15.0 * wcols[0], "barcode_bitsliced": 15.0 * wcols[1]}
+        dom_name = max(k_ops, key=lambda k: kt[k])
+        dp = {}
+        for k, ops in k_ops.items():
+            a_tops = ops / (kt[k] / 1000.0) / 1e12 if kt[k] > 0 else 0.0
+            dp[k] = {"ms": kt[k], "achieved": a_tops, "frac": a_tops / int_peak if int_peak else None}
+        achieved = dp[dom_name]["achieved"]
+        ncu_static = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_latest.json")) as fh:
+                ncu_static = json.load(fh)
+        except OSError:
+            pass
+        ncu_dom = ncu_static.get("kernels", {}).get(dom_name, {})
         hbm_bytes = batch.h2d_bytes + res.records.nbytes
         line = {
             "metric": "reads/sec demuxed (whole box)", "value": value, "unit": "reads/s", "n_gpus": world,
@@ -270,17 +283,21 @@ def main():
             "gcups": gcups, "cells_per_read": (cells[0] + cells[1]) / n_reads,
             "stage_ms": {"stage_windows": st[0], "primer_search": st[1], "barcode_search": st[2], "select": st[3]},
             "wall_ms_per_step": wall_ms,
+            "kernel_ms": kt,
             "roofline": {"bound": "int_alu", "kernel": dom_name, "achieved": achieved, "peak": int_peak,
                          "unit": "Tops/s", "frac": achieved / int_peak if int_peak else None,
                          "whole_step_frac": (alg_ops / (ms / 1000.0) / 1e12) / int_peak if int_peak else None,
-                         "peak_source": "measured in this run by smx_int_alu_peak (LOP3 %.2f / IADD3 %.2f / mix %.2f Tops/s)"
-                                        % (peaks[0], peaks[1], peaks[2]),
-                         "algorithmic_ops": "15 int ops x 32-bit word-columns (SURVEY.md 8d)",
-                         "other_dp_kernel": {"kernel": other, "achieved": other_achieved,
-                                             "frac": other_achieved / int_peak if int_peak else None,
-                                             "note": "the bit-sliced barcode kernel executes far fewer than 15 ops per "
-                                                     "algorithmic word-column, so its fraction exceeds 1"},
-                         "traffic": None,
+                         "peak_source": "measured in this run by smx_int_alu_peak (LOP3 %.2f / IADD3 %.2f / mix %.2f Tops/s); "
+                                        "MEASURED_PEAKS.json has no integer figure" % (peaks[0], peaks[1], peaks[2]),
+                         "algorithmic_ops": "15 int ops x 32-bit word-columns (SURVEY.md 8d), counted on the device",
+                         "dp_kernels": dp,
+                         "note": "both DP kernels are bit-sliced (32 barcodes / 32 reads per machine word, 6 LOP3 per "
+                                 "cell), so they execute far fewer than 15 integer ops per algorithmic word-column "
+                                 "and the algorithmic fraction exceeds 1; alu_pipe_pct_ncu is the EXECUTED ALU-pipe "
+                                 "utilisation of the same kernel from the committed ncu capture",
+                         "alu_pipe_pct_ncu": ncu_dom.get("alu_pipe_pct"),
+                         "traffic": ncu_dom.get("dram_bytes"),
+                         "ncu_capture": ncu_static.get("capture"),
                          "hbm_sanity_gbs": hbm_bytes / (ms / 1000.0) / 1e9},
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": "reads/s",
                     "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(d2h),

@@ -25,6 +25,7 @@ extern "C" {
 
 #define SMX_MAX_PRIMERS 64      /* canonical primers (distinct sequences)                         */
 #define SMX_MAX_PATTERN 64      /* primer / barcode length handled by the single-thread kernels   */
+#define SMX_MAX_LONG_PATTERN 1024 /* primer length handled by the warp-cooperative multi-word kernel */
 #define SMX_MAX_SEARCH_LEN 1024 /* --search-len                                                   */
 
 /* error codes */
@@ -236,6 +237,13 @@ int smx_download_results(smx_ctx *ctx, smx_results *out);     /* D2H only       
 /* CUDA-event time (ms) of the last smx_run_resident, and of its stages:
  * stage 0 staging, 1 primer search, 2 barcode search, 3 selection. */
 int smx_last_timing(const smx_ctx *ctx, float *total_ms, float stage_ms[4]);
+
+/* CUDA-event time (ms) of the individual kernels of the last smx_run_resident (first pass; a
+ * capacity re-run overwrites the marks it passes again).  Fills up to n entries and returns the
+ * number available, in this order: 0 window staging, 1 sliced primer search (all primers, they run
+ * concurrently), 2 primer finish / classic search, 3 primer start recovery, 4 barcode search,
+ * 5 fast selection, 6 general selection, 7 record scan, 8 record compaction. */
+int smx_last_kernel_times(const smx_ctx *ctx, float *ms, int n);
 
 /* Number of kernel launches issued by the last smx_run_resident. */
 int smx_last_launch_count(const smx_ctx *ctx);

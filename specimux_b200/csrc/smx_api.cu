@@ -66,6 +66,8 @@ template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) 
 // rotate over all lanes so one chunk's H2D, another's kernels and a third's D2H overlap.
 constexpr int kLanes = 3;
 constexpr int kAuxStreams = 2;
+constexpr int kKernelMarks = 10;
+constexpr int kKernelTimes = 9;
 constexpr size_t kCtlWords = kCtrWords + SMX_MAX_PRIMERS;     // unsigned long long words of a lane's control block
 
 struct Lane {
@@ -76,6 +78,7 @@ struct Lane {
     cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
     bool drain_pending = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[kKernelMarks] = {};    // per-kernel boundaries of a timed (resident) run
     Batch b;
     DevBuf<u32> packed2, lengths, packed4, win, win2, tmix, endmask, impmask, rec_count, rec_offset, rec_offset_out, block_sums;
     DevBuf<u64> word_off, off4;
@@ -111,6 +114,7 @@ struct Lane {
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr; h_slot_counts = nullptr;
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto &e : kev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_ready) { cudaEventDestroy(ev_ready); ev_ready = nullptr; }
         if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
         for (auto &e : ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -127,7 +131,7 @@ struct smx_ctx {
     // table storage
     DevBuf<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
     DevBuf<unsigned char> b_len, bw_len, bw_primer;
-    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
+    DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq, peq_long;
     DevBuf<unsigned short> bw_list;
     DevBuf<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
@@ -136,7 +140,7 @@ struct smx_ctx {
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
     DevBuf<unsigned char> l2_scratch;
     u32 chunk_reads = 128 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK)
-    float total_ms = 0, stage_ms[4] = {0, 0, 0, 0};
+    float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
 };
@@ -152,6 +156,7 @@ static cudaError_t lane_init(Lane &ln) {
     for (auto &j : ln.ev_join) if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto &ev : ln.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
+    for (auto &ev : ln.kev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     if ((e = cudaHostAlloc((void **)&ln.h_counters, kCtlWords * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
     ln.h_slot_counts = (u32 *)(ln.h_counters + kCtrWords);
     if ((e = ln.counters.ensure(kCtlWords)) != cudaSuccess) return e;
@@ -257,10 +262,12 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     const u32 n = b.n_reads;
     const int nP = t.n_primers;
     cudaStream_t st = ln.stream;
+#define KMARK(i) do { if (timed) CU(cudaEventRecord(ln.kev[i], st)); } while (0)
     const unsigned blocks = (n + 127) / 128;
     if (from <= 0) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
         if (timed) CU(cudaEventRecord(ln.ev[0], st));
+        KMARK(0);
         dim3 grid(blocks, 2 * t.nw2);
         k_stage_windows<<<grid, 128, 0, st>>>(t, b);
         ++ln.launches;
@@ -268,6 +275,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     if (from <= 1) {   // stage 1
         if (from == 1) CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));   // re-run
         if (timed) CU(cudaEventRecord(ln.ev[1], st));
+        KMARK(1);
         if (t.sliced) {
             // forward pass bit-sliced across reads, one launch per primer (pattern length = template)
             // The primers' kernels are independent and each fills only ~2.5 warps per scheduler at
@@ -302,9 +310,24 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
                     CU(cudaStreamWaitEvent(st, ln.ev_join[a], 0));
                 }
         }
+        KMARK(2);
         dim3 grid((n + kFinishBlock - 1) / kFinishBlock, 2 * nP);
         if (t.use64) k_primer_search<u64><<<grid, kFinishBlock, 0, st>>>(t, b);
         else k_primer_search<u32><<<grid, kFinishBlock, 0, st>>>(t, b);
+        for (int p = 0; p < nP; ++p) {
+            if (!t.p_sw[p]) continue;
+            // long primer: warp-cooperative multi-word search, p_sw lanes per read
+            const int sw = t.p_sw[p];
+            dim3 lgrid((unsigned)(((u64)n * sw + 127) / 128), 2);
+            switch (sw) {
+                case 4: k_primer_long<4><<<lgrid, 128, 0, st>>>(t, b, p); break;
+                case 8: k_primer_long<8><<<lgrid, 128, 0, st>>>(t, b, p); break;
+                case 16: k_primer_long<16><<<lgrid, 128, 0, st>>>(t, b, p); break;
+                default: k_primer_long<32><<<lgrid, 128, 0, st>>>(t, b, p); break;
+            }
+            ++ln.launches;
+        }
+        KMARK(3);
         dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
         if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, st>>>(t, b);
         else k_primer_start<u32><<<sgrid, 128, 0, st>>>(t, b);
@@ -317,6 +340,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
             CU(cudaMemsetAsync(ln.counters.p + 7, 0, sizeof(unsigned long long), st));
         }
         if (timed) CU(cudaEventRecord(ln.ev[2], st));
+        KMARK(4);
         if (t.n_bwords) {
             dim3 grid((b.e_cap + 127) / 128, 2 * t.n_bwords);
             switch (t.k_idx) {
@@ -334,16 +358,22 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         CU(cudaMemsetAsync(ln.counters.p + kCtrDeferred, 0, sizeof(unsigned long long), st));
     }
     if (timed) CU(cudaEventRecord(ln.ev[3], st));
+    KMARK(5);
     // fast path for (nearly) every read, then the general routine over the reads it deferred
     if (nP <= 8) {
         k_select_fast<8><<<blocks, 128, 0, st>>>(t, b);
+        KMARK(6);
         k_select<8><<<blocks, 128, 0, st>>>(t, b);
     } else {
         k_select_fast<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
+        KMARK(6);
         k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
     }
     ln.launches += 2;
+    KMARK(7);
     CU(enqueue_scan_and_count(ln));
+    KMARK(8);
+#undef KMARK
     return SMX_OK;
 }
 
@@ -420,6 +450,7 @@ static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
     if (ln.drain_pending) { CU(cudaStreamWaitEvent(ln.stream, ln.ev_drained, 0)); ln.drain_pending = false; }
     CU(ln.records.ensure(ln.n_records + 1));
     b.records = ln.records.p;
+    if (timed) CU(cudaEventRecord(ln.kev[9], st));
     k_compact_records<<<(unsigned)(((u64)b.n_reads * 4 + 255) / 256), 256, 0, st>>>(t, b, rec_base, ln.rec_offset_out.p);
     ++ln.launches;
     const size_t chunk = 512;
@@ -456,7 +487,7 @@ void smx_destroy(smx_ctx *c) {
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release();
-    c->shared_packed4.release(); c->l2_scratch.release();
+    c->shared_packed4.release(); c->l2_scratch.release(); c->peq_long.release();
     delete c;
 }
 
@@ -500,12 +531,14 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->spec_row, ht.spec_row)); CUC(upload(c->spec_p1, ht.spec_p1)); CUC(upload(c->spec_p2, ht.spec_p2));
     CUC(upload(c->spec_pool, ht.spec_pool));
     CUC(upload(c->spec_dense, ht.spec_dense));
+    CUC(upload(c->peq_long, ht.peq_long));
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
     ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,
                     c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
                     c->spec_row.p, c->spec_p1.p, c->spec_p2.p, c->spec_pool.p);
     c->t = ht.t;
     c->t.spec_dense = ht.spec_dense.empty() ? nullptr : c->spec_dense.p;
+    c->t.peq_long = c->peq_long.p;
 #undef CUC
     if (const char *env = getenv("SMX_PIPELINE_CHUNK")) {
         long v = atol(env);
@@ -561,6 +594,8 @@ int smx_run_resident(smx_ctx *c) {
     CU(cudaGetLastError());
     for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&c->stage_ms[i], ln.ev[i], ln.ev[i + 1]));
     CU(cudaEventElapsedTime(&c->total_ms, ln.ev[0], ln.ev[4]));
+    for (int i = 0; i < 8; ++i) CU(cudaEventElapsedTime(&c->kernel_ms[i], ln.kev[i], ln.kev[i + 1]));
+    CU(cudaEventElapsedTime(&c->kernel_ms[8], ln.kev[9], ln.ev[4]));
     return SMX_OK;
 }
 
@@ -760,6 +795,12 @@ int smx_last_timing(const smx_ctx *c, float *total_ms, float stage_ms[4]) {
     if (total_ms) *total_ms = c->total_ms;
     if (stage_ms) for (int i = 0; i < 4; ++i) stage_ms[i] = c->stage_ms[i];
     return SMX_OK;
+}
+
+int smx_last_kernel_times(const smx_ctx *c, float *ms, int n) {
+    if (!c || !ms) return 0;
+    for (int i = 0; i < n && i < kKernelTimes; ++i) ms[i] = c->kernel_ms[i];
+    return kKernelTimes;
 }
 
 int smx_last_launch_count(const smx_ctx *c) {

@@ -151,8 +151,10 @@ struct Tables {
     int use64;                      // any primer longer than 32
     int hit_cap;                    // entries per (read, strand, bword) hit sub-list
 
-    unsigned char p_len[SMX_MAX_PRIMERS];
-    signed char p_k[SMX_MAX_PRIMERS];
+    unsigned short p_len[SMX_MAX_PRIMERS];
+    short p_k[SMX_MAX_PRIMERS];
+    unsigned char p_sw[SMX_MAX_PRIMERS];   // long primers (> 64 nt): lanes per problem of the warp-cooperative search, else 0
+    int p_long[SMX_MAX_PRIMERS];           // long primers: word offset of their tables in peq_long
     unsigned char p_dir[SMX_MAX_PRIMERS];
     int p_fidx[SMX_MAX_PRIMERS];
     u32 pb_off[SMX_MAX_PRIMERS + 1];
@@ -161,6 +163,7 @@ struct Tables {
     const u64 *peq_rc;       // [primer][16]   primer_rc, top-aligned
     const u64 *peq_rcrev;    // [primer][16]   reversed primer_rc (start-recovery pass)
     const u64 *peq_fw;       // [primer][16]   forward-sense primer (explicit orientation test)
+    const u32 *peq_long;     // long primers: [rc | rcrev | fw][16 symbols][p_sw words], pattern top-aligned in 32*p_sw bits
     const unsigned char *b_len;    // [list entry]
     const u32 *pb_barcode;   // [list entry] global barcode id
 

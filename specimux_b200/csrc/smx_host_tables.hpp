@@ -37,6 +37,20 @@ inline bool sym_equal(int pat, int rd) {
     return false;
 }
 
+// Multi-word Peq of a long pattern: row i sits at bit (32*sw - m + i) of a 32*sw-bit vector, word w
+// of symbol c at out[c * sw + w].
+inline bool build_peq_long(const char *s, int m, bool reversed, int sw, u32 *out /*16*sw*/) {
+    for (int i = 0; i < 16 * sw; ++i) out[i] = 0;
+    for (int i = 0; i < m; ++i) {
+        int pc = code_of(s[reversed ? m - 1 - i : i]);
+        if (pc < 0) return false;
+        int pos = 32 * sw - m + i;
+        for (int c = 0; c < 16; ++c)
+            if (sym_equal(pc, c)) out[c * sw + (pos >> 5)] |= 1u << (pos & 31);
+    }
+    return true;
+}
+
 inline bool build_peq(const char *s, int m, bool reversed, u64 *out /*16*/) {
     for (int c = 0; c < 16; ++c) out[c] = 0;
     for (int i = 0; i < m; ++i) {
@@ -56,6 +70,7 @@ struct HostTables {
     std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     std::vector<unsigned short> bw_list;
     std::vector<i32> pair_pool, spec_pool, spec_dense;
+    std::vector<u32> peq_long;
     std::vector<unsigned char> prow_code;      // [primer][32] IUPAC code of primer_rc row i (sliced primer search)
     int max_nb = 0;
     std::string error;
@@ -89,15 +104,32 @@ struct HostTables {
         if (t.k_idx < 0) return err("negative barcode distance threshold");
 
         peq_rc.assign((size_t)nP * 16, 0); peq_rcrev.assign((size_t)nP * 16, 0); peq_fw.assign((size_t)nP * 16, 0);
+        peq_long.clear();
         prow_code.assign((size_t)nP * 32, 0);
         for (int p = 0; p < nP; ++p) {
             int m = (int)(tb->primer_off[p + 1] - tb->primer_off[p]);
-            if (m < 1 || m > SMX_MAX_PATTERN) return err("primer %d length %d outside 1..%d", p, m, SMX_MAX_PATTERN);
+            if (m < 1 || m > SMX_MAX_LONG_PATTERN) return err("primer %d length %d outside 1..%d", p, m, SMX_MAX_LONG_PATTERN);
             int k = tb->primer_k[p];
             if (k < 0 || k >= m) return err("primer %d max distance %d must be in [0, length %d)", p, k, m);
-            t.p_len[p] = (unsigned char)m; t.p_k[p] = (signed char)k; t.p_dir[p] = tb->primer_dir[p];
+            if (k > 127) return err("primer %d max distance %d exceeds 127 (smx_record.dist is 8 bits)", p, k);
+            t.p_len[p] = (unsigned short)m; t.p_k[p] = (short)k; t.p_dir[p] = tb->primer_dir[p];
             t.p_fidx[p] = tb->primer_file_index[p];
             if (m > 32) t.use64 = 1;
+            t.p_sw[p] = 0; t.p_long[p] = -1;
+            if (m > SMX_MAX_PATTERN) {
+                // warp-cooperative multi-word search: lanes per problem = power of two >= ceil(m/32), at least 4
+                int sw = 4;
+                while (32 * sw < m) sw *= 2;
+                t.p_sw[p] = (unsigned char)sw; t.p_long[p] = (int)peq_long.size();
+                size_t base = peq_long.size();
+                peq_long.resize(base + (size_t)3 * 16 * sw, 0);
+                if (!build_peq_long(tb->primer_rc + tb->primer_off[p], m, false, sw, &peq_long[base]) ||
+                    !build_peq_long(tb->primer_rc + tb->primer_off[p], m, true, sw, &peq_long[base + (size_t)16 * sw]) ||
+                    !build_peq_long(tb->primer_seq + tb->primer_off[p], m, false, sw, &peq_long[base + (size_t)32 * sw]))
+                    return err("primer %d has a non-IUPAC character", p);
+                t.pb_off[p] = tb->pb_off[p];
+                continue;
+            }
             if (!build_peq(tb->primer_rc + tb->primer_off[p], m, false, &peq_rc[(size_t)p * 16]) ||
                 !build_peq(tb->primer_rc + tb->primer_off[p], m, true, &peq_rcrev[(size_t)p * 16]) ||
                 !build_peq(tb->primer_seq + tb->primer_off[p], m, false, &peq_fw[(size_t)p * 16]))
@@ -107,6 +139,8 @@ struct HostTables {
         }
         t.pb_off[nP] = tb->pb_off[nP];
         t.sliced = !t.use64;
+        if (peq_long.empty()) peq_long.push_back(0);
+        t.peq_long = peq_long.data();
         const u32 n_list = tb->pb_off[nP];
         std::vector<std::string> b_str(n_list);
         b_len.assign(n_list, 0);

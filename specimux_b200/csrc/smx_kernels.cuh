@@ -798,6 +798,23 @@ SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Long primers: carry-lookahead across the SW words of every segment of a warp at once.  Bit l of
+// G / P says word (lane) l generates a carry / would pass an incoming carry on; the result has bit
+// l set iff a carry enters word l.  One integer addition ripples all segments: the generate bits
+// are injected one position up, the propagate bits let the machine carry run through, and word 0
+// of every segment (never a carry target) is masked out so nothing crosses a segment boundary.
+template <int SW> struct LongSeg {
+    static_assert(SW == 4 || SW == 8 || SW == 16 || SW == 32, "segment width");
+    static constexpr u32 kStart = SW == 32 ? 0x00000001u : SW == 16 ? 0x00010001u : SW == 8 ? 0x01010101u : 0x11111111u;
+};
+
+template <int SW> SMX_HD u32 long_carry_in(u32 G, u32 P) {
+    constexpr u32 inner = ~LongSeg<SW>::kStart;
+    const u32 V = (G << 1) & inner, Pm = P & inner;
+    return ((Pm + V) ^ Pm) & inner;
+}
+
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------
 // __global__ wrappers.  Tables live in __constant__ memory, Peq masks are staged once per block
@@ -849,6 +866,7 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
     __shared__ u32 s_wtot[kFinishBlock / 32 + 1];
     __shared__ unsigned long long s_tmp[32];
     const int primer = blockIdx.y % c_tables.n_primers, strand = blockIdx.y / c_tables.n_primers;
+    if (c_tables.p_sw[primer]) return;                  // long primer: k_primer_long owns this slot
     if (threadIdx.x < 48) {
         const u64 *src = threadIdx.x < 16 ? c_tables.peq_rc : threadIdx.x < 32 ? c_tables.peq_rcrev : c_tables.peq_fw;
         s_peq[threadIdx.x >> 4][threadIdx.x & 15] = src[primer * 16 + (threadIdx.x & 15)];
@@ -887,11 +905,151 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
     block_counter_add(cells * (unsigned long long)((m + 31) >> 5), &b.counters[2], s_tmp);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Long primers (65 .. 1024 nt): warp-cooperative multi-word Myers/Hyyro.  The pattern occupies the
+// top m bits of a 32*SW-bit vector spread over SW consecutive lanes (lane `sub` holds word `sub`;
+// row m is the sign bit of the top lane), so a warp works on 32/SW reads at once.  Per column the
+// only cross-lane traffic is the carry of (Eq & Pv) + Pv -- resolved for all segments at once from
+// two ballots (generate / propagate masks, carry-lookahead by one integer addition) -- and the
+// one-bit shifts of Ph / Mh (__shfl_up).  Same recurrences as myers_step<>, i.e. edlib's
+// calculateBlock over several blocks (alignment.py:42).  One kernel does the forward HW pass, the
+// hit bookkeeping, the reverse pass that recovers the start of the first location, the work
+// entries and, for irregular reads, the explicit orientation test.
+
+// One DP column for every segment of the warp.  Returns the score delta of the last row (only
+// meaningful in a segment's top lane).  Must be called by all 32 lanes.
+template <int SW, bool kShiftInOne>
+__device__ __forceinline__ int long_step(u32 Eq, u32 &Pv, u32 &Mv, int sub, int lane) {
+    const u32 a = Eq & Pv;
+    u32 sum = a + Pv;
+    const u32 G = __ballot_sync(0xffffffffu, sum < a);                 // word generates a carry
+    const u32 P = __ballot_sync(0xffffffffu, sum == 0xFFFFFFFFu);      // word propagates an incoming carry
+    sum += (long_carry_in<SW>(G, P) >> lane) & 1u;
+    const u32 Xh = (sum ^ Pv) | Eq;
+    const u32 Xv = Eq | Mv;
+    u32 Ph = Mv | ~(Xh | Pv);
+    u32 Mh = Pv & Xh;
+    const int d = (int)(Ph >> 31) - (int)(Mh >> 31);
+    u32 Ph_lo = __shfl_up_sync(0xffffffffu, Ph, 1), Mh_lo = __shfl_up_sync(0xffffffffu, Mh, 1);
+    if (sub == 0) { Ph_lo = kShiftInOne ? 0x80000000u : 0u; Mh_lo = 0u; }
+    Ph = __funnelshift_l(Ph_lo, Ph, 1);
+    Mh = __funnelshift_l(Mh_lo, Mh, 1);
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+    return d;
+}
+
+template <int SW>
+__global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
+    // grid: x over (read, word) pairs, y = strand
+    __shared__ u32 s_peq[3][16 * SW];
+    const Tables &t = c_tables;
+    {
+        const u32 *src = t.peq_long + t.p_long[primer];
+        for (int i = threadIdx.x; i < 3 * 16 * SW; i += blockDim.x) s_peq[i / (16 * SW)][i % (16 * SW)] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane % SW;
+    const bool top = sub == SW - 1;
+    const int strand = (int)blockIdx.y;
+    const u32 read = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) / SW);
+    const bool valid = read < b.n_reads;
+    const int m = t.p_len[primer], k = t.p_k[primer];
+    const u32 slot = slot_index(t, strand, primer);
+    const int n = valid ? (int)b.lengths[read] : 0;
+    const Geo g = make_geo(n, t.L);
+    const u64 hit_idx = (u64)slot * b.n_pad + (valid ? read : 0);
+    u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + (valid ? read : 0);
+    u32 *imask = b.impmask + (u64)slot * t.mw * b.n_pad + (valid ? read : 0);
+
+    // ---- forward HW pass over the staged window [g.start, g.wl)
+    const int p_begin = g.start, cols = valid ? g.wl - g.start : 0;
+    if (valid && top) for (int w = 0; w < t.mw; ++w) { emask[(u64)w * b.n_pad] = 0; imask[(u64)w * b.n_pad] = 0; }
+    u32 Pv = ~0u, Mv = 0u;
+    int score = m, best = m + 1;
+    {
+        u32 eqw = 0, imw = 0;
+        int cur = p_begin >> 5;
+        const int maxcols = __reduce_max_sync(0xffffffffu, cols);
+        for (int j = 0; j < maxcols; ++j) {
+            const bool active = j < cols;
+            const int p = p_begin + j;
+            const int c = active ? staged_sym(t, b, read, strand, p) : kSymOther;
+            const u32 sPv = Pv, sMv = Mv;
+            const int d = long_step<SW, false>(s_peq[0][c * SW + sub], Pv, Mv, sub, lane);
+            if (!active) { Pv = sPv; Mv = sMv; }
+            else if (top) {
+                if ((p >> 5) != cur) { emask[(u64)cur * b.n_pad] = eqw; imask[(u64)cur * b.n_pad] = imw; eqw = imw = 0; cur = p >> 5; }
+                score += d;
+                if (score < best) { best = score; imw |= 1u << (p & 31); }
+                if (score == best) eqw |= 1u << (p & 31);
+            }
+        }
+        if (valid && top && cols > 0) { emask[(u64)cur * b.n_pad] = eqw; imask[(u64)cur * b.n_pad] = imw; }
+    }
+    // ---- hit bookkeeping (top lane), then the segment learns (nloc, first, best)
+    int nloc = 0, first = 0;
+    if (valid && top) {
+        nloc = primer_tail(t, b, read, strand, primer, best);
+        if (nloc) first = b.phit[hit_idx].first_end - g.woff - g.delta;
+    }
+    const int src_lane = lane - sub + SW - 1;
+    nloc = __shfl_sync(0xffffffffu, nloc, src_lane);
+    first = __shfl_sync(0xffffffffu, first, src_lane);
+    best = __shfl_sync(0xffffffffu, best, src_lane);
+    // ---- reverse SHW pass from the first equal-best end: the LAST column with score == best is the
+    //      longest alignment (edlib start recovery)
+    {
+        int rcols = 0;
+        if (nloc) { rcols = first - p_begin + 1; if (rcols > m + best) rcols = m + best; }
+        const int maxr = __reduce_max_sync(0xffffffffu, rcols);
+        // pattern mask: bits at positions >= 32*SW - m of the 32*SW-bit vector
+        const int lo = 32 * SW - m - 32 * sub;                // first pattern bit inside this word
+        Pv = lo <= 0 ? ~0u : (lo >= 32 ? 0u : ~0u << lo);
+        Mv = 0u;
+        int rs = m, last = m - 1;
+        for (int j = 0; j < maxr; ++j) {
+            const bool active = j < rcols;
+            const int c = active ? staged_sym(t, b, read, strand, first - j) : kSymOther;
+            const u32 sPv = Pv, sMv = Mv;
+            const int d = long_step<SW, true>(s_peq[1][c * SW + sub], Pv, Mv, sub, lane);
+            if (!active) { Pv = sPv; Mv = sMv; }
+            else if (top) { rs += d; if (rs == best) last = j; }
+        }
+        if (valid && top && nloc) b.phit[hit_idx].first_start = b.phit[hit_idx].first_end - last;
+    }
+    // ---- work entries and counters (top lane; this kernel is the rare path, plain atomics)
+    if (valid && top) {
+        if (nloc) write_entries(t, b, slot, read, atomicAdd(&b.slot_count[slot], (u32)nloc));
+        const unsigned long long hw_cols = (unsigned long long)(n < t.L ? n : t.L);
+        atomicAdd(&b.counters[0], hw_cols * (unsigned long long)m);
+        atomicAdd(&b.counters[2], hw_cols * (unsigned long long)((m + 31) >> 5));
+    }
+    // ---- determine_orientation, explicit form (demultiplex.py:602-638), irregular reads only
+    {
+        const bool need = valid && t.preorient && (!g.regular || read_is_flagged(b, read));
+        const int ocols = need ? (n < t.L ? n : t.L) : 0;
+        const int maxo = __reduce_max_sync(0xffffffffu, ocols);
+        Pv = ~0u; Mv = 0u;
+        int sc = m, bst = m + 1;
+        for (int x = 0; x < maxo; ++x) {
+            const bool active = x < ocols;
+            const int c = active ? sym_at(b, read, strand, x, n) : kSymOther;
+            const u32 sPv = Pv, sMv = Mv;
+            const int d = long_step<SW, false>(s_peq[2][c * SW + sub], Pv, Mv, sub, lane);
+            if (!active) { Pv = sPv; Mv = sMv; }
+            else if (top) { sc += d; if (sc < bst) bst = sc; }
+        }
+        if (valid && top) b.orient_hit[hit_idx] = (unsigned char)(need && bst <= k);
+    }
+}
+
 // Start recovery over the compact work-entry lists (full warps instead of the ~50 % matched lanes).
 template <typename W>
 __global__ void __launch_bounds__(128) k_primer_start(SMX_KARGS) {
     __shared__ u64 s_rev[16];
     const u32 slot = blockIdx.y;
+    if (c_tables.p_sw[slot % c_tables.n_primers]) return;   // long primer: start recovered by k_primer_long
     u32 cnt = b.slot_count[slot];
     if (cnt > b.e_cap) cnt = b.e_cap;
     if (blockIdx.x * blockDim.x >= cnt) return;

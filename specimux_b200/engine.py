@@ -194,6 +194,15 @@ class Matcher:
     def last_chunk_count(self) -> int:
         return int(self._lib.smx_last_chunk_count(self._ctx))
 
+    KERNEL_NAMES = ("stage_windows", "primer_sliced", "primer_finish", "primer_start", "barcode_bitsliced",
+                    "select_fast", "select_general", "scan", "compact_records")
+
+    def last_kernel_times(self):
+        """{kernel: ms} of the last run_resident (CUDA events on the launching stream)."""
+        ms = (C.c_float * len(self.KERNEL_NAMES))()
+        n = self._lib.smx_last_kernel_times(self._ctx, ms, len(self.KERNEL_NAMES))
+        return {k: float(ms[i]) for i, k in enumerate(self.KERNEL_NAMES[:n])}
+
     def last_deferred(self) -> int:
         return int(self._lib.smx_last_deferred(self._ctx))
 

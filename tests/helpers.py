@@ -100,5 +100,6 @@ def hostsim_binding():
         lib.hostsim_last_error.restype = ctypes.c_char_p
         lib.hostsim_match_batch.argtypes = [ctypes.POINTER(_lib.SmxTables), ctypes.POINTER(_lib.SmxParams),
                                             ctypes.POINTER(_lib.SmxBatch), ctypes.POINTER(_lib.SmxResults)]
+        lib.hostsim_check_long_carry.argtypes = [ctypes.c_ulonglong]
         _hostsim = lib
     return _hostsim

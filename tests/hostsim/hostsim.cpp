@@ -15,6 +15,124 @@ using namespace smx;
 
 static char g_err[512] = "";
 
+// ---------------------------------------------------------------------------------------------
+// Long primers (k_primer_long).  The CUDA kernel spreads the 32*SW-bit vectors over SW lanes and
+// resolves carries with ballots; here the same recurrences run over an array of SW words with the
+// carry rippled sequentially.  Same Peq layout (peq_long), same bookkeeping routines (primer_tail,
+// write_entries).  long_carry_in<> -- the kernel's carry-lookahead -- is checked separately by
+// hostsim_check_long_carry().
+struct LongVec {
+    int sw;
+    std::vector<u32> Pv, Mv;
+    explicit LongVec(int sw_) : sw(sw_), Pv(sw_), Mv(sw_) {}
+    int step(const u32 *Eq /*sw words*/, bool shift_in_one) {
+        std::vector<u32> Ph(sw), Mh(sw), Xv(sw);
+        u32 carry = 0;
+        for (int w = 0; w < sw; ++w) {
+            const u32 a = Eq[w] & Pv[w];
+            const unsigned long long full = (unsigned long long)a + Pv[w] + carry;
+            carry = (u32)(full >> 32);
+            const u32 Xh = ((u32)full ^ Pv[w]) | Eq[w];
+            Xv[w] = Eq[w] | Mv[w];
+            Ph[w] = Mv[w] | ~(Xh | Pv[w]);
+            Mh[w] = Pv[w] & Xh;
+        }
+        const int d = (int)(Ph[sw - 1] >> 31) - (int)(Mh[sw - 1] >> 31);
+        for (int w = sw - 1; w >= 0; --w) {
+            const u32 plo = w ? Ph[w - 1] >> 31 : (shift_in_one ? 1u : 0u), mlo = w ? Mh[w - 1] >> 31 : 0u;
+            Ph[w] = (Ph[w] << 1) | plo;
+            Mh[w] = (Mh[w] << 1) | mlo;
+        }
+        for (int w = 0; w < sw; ++w) { Pv[w] = Mh[w] | ~(Xv[w] | Ph[w]); Mv[w] = Ph[w] & Xv[w]; }
+        return d;
+    }
+};
+
+// Returns the number of equal-best end locations of the slot (entries are written by the caller).
+static int primer_long_host(const Tables &t, const Batch &b, u32 read, int strand, int primer) {
+    const int sw = t.p_sw[primer], m = t.p_len[primer], k = t.p_k[primer];
+    const u32 *peq = t.peq_long + t.p_long[primer];
+    const int n = (int)b.lengths[read];
+    const Geo g = make_geo(n, t.L);
+    const u32 slot = slot_index(t, strand, primer);
+    const u64 hit_idx = (u64)slot * b.n_pad + read;
+    u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
+    u32 *imask = b.impmask + (u64)slot * t.mw * b.n_pad + read;
+    for (int w = 0; w < t.mw; ++w) { emask[(u64)w * b.n_pad] = 0; imask[(u64)w * b.n_pad] = 0; }
+    int best = m + 1;
+    {
+        LongVec v(sw);
+        std::fill(v.Pv.begin(), v.Pv.end(), ~0u);
+        int score = m;
+        for (int p = g.start; p < g.wl; ++p) {
+            const int c = staged_sym(t, b, read, strand, p);
+            score += v.step(peq + (size_t)c * sw, false);
+            if (score < best) { best = score; imask[(u64)(p >> 5) * b.n_pad] |= 1u << (p & 31); }
+            if (score == best) emask[(u64)(p >> 5) * b.n_pad] |= 1u << (p & 31);
+        }
+    }
+    const int nloc = primer_tail(t, b, read, strand, primer, best);
+    if (nloc) {
+        const int first = b.phit[hit_idx].first_end - g.woff - g.delta;
+        int rcols = first - g.start + 1;
+        if (rcols > m + best) rcols = m + best;
+        LongVec v(sw);
+        for (int w = 0; w < sw; ++w) {
+            const int lo = 32 * sw - m - 32 * w;
+            v.Pv[w] = lo <= 0 ? ~0u : (lo >= 32 ? 0u : ~0u << lo);
+        }
+        int rs = m, last = m - 1;
+        for (int j = 0; j < rcols; ++j) {
+            const int c = staged_sym(t, b, read, strand, first - j);
+            rs += v.step(peq + (size_t)16 * sw + (size_t)c * sw, true);
+            if (rs == best) last = j;
+        }
+        b.phit[hit_idx].first_start = b.phit[hit_idx].first_end - last;
+    }
+    const unsigned long long hw_cols = (unsigned long long)(n < t.L ? n : t.L);
+    b.counters[0] += hw_cols * (unsigned long long)m;
+    b.counters[2] += hw_cols * (unsigned long long)((m + 31) >> 5);
+    unsigned char ohit = 0;
+    if (t.preorient && (!g.regular || read_is_flagged(b, read))) {
+        LongVec v(sw);
+        std::fill(v.Pv.begin(), v.Pv.end(), ~0u);
+        int sc = m, bst = m + 1;
+        const int cols = n < t.L ? n : t.L;
+        for (int x = 0; x < cols; ++x) {
+            sc += v.step(peq + (size_t)32 * sw + (size_t)sym_at(b, read, strand, x, n) * sw, false);
+            if (sc < bst) bst = sc;
+        }
+        ohit = bst <= k;
+    }
+    b.orient_hit[hit_idx] = ohit;
+    return nloc;
+}
+
+// Exhaustive / randomised check of the kernel's carry-lookahead against a rippled carry chain.
+template <int SW> static int check_long_carry(unsigned long long trials) {
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    for (unsigned long long it = 0; it < trials; ++it) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const u32 G = (u32)x & ~(u32)(x >> 32);       // generate and propagate are mutually exclusive
+        const u32 P = (u32)(x >> 32) & ~G;
+        u32 want = 0;
+        for (int seg = 0; seg < 32 / SW; ++seg) {
+            u32 c = 0;
+            for (int w = 0; w < SW; ++w) {
+                const int l = seg * SW + w;
+                if (c) want |= 1u << l;
+                c = ((G >> l) & 1u) | (((P >> l) & 1u) & c);
+            }
+        }
+        if (long_carry_in<SW>(G, P) != want) return 1;
+    }
+    return 0;
+}
+
+extern "C" int hostsim_check_long_carry(unsigned long long trials) {
+    return check_long_carry<4>(trials) | check_long_carry<8>(trials) | check_long_carry<16>(trials) | check_long_carry<32>(trials);
+}
+
 extern "C" const char *hostsim_last_error(void) { return g_err; }
 
 extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, const smx_batch *in, smx_results *out) {
@@ -81,7 +199,8 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
             for (int p = 0; p < nP; ++p)
                 for (u32 r = 0; r < n; ++r) {
                     int nloc;
-                    if (t.use64) nloc = primer_finish_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
+                    if (t.p_sw[p]) nloc = primer_long_host(t, b, r, s, p);
+                    else if (t.use64) nloc = primer_finish_thread<u64>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
                     else nloc = primer_finish_thread<u32>(t, b, r, s, p, t.peq_rc + p * 16, t.peq_fw + p * 16);
                     if (nloc) {
                         u32 slot = (u32)(s * nP + p);
@@ -94,6 +213,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         if (max_entries > e_cap) { e_cap = max_entries; continue; }
         for (u32 slot = 0; slot < (u32)(2 * nP); ++slot)
             for (u32 e = 0; e < slot_count[slot]; ++e) {
+                if (t.p_sw[slot % nP]) break;        // long primer: start already recovered
                 const u64 *rev = t.peq_rcrev + (size_t)(slot % nP) * 16;
                 if (t.use64) primer_start_thread<u64>(t, b, slot, e, rev); else primer_start_thread<u32>(t, b, slot, e, rev);
             }

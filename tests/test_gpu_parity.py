@@ -236,3 +236,11 @@ def test_cuda_random_tables_match_live_oracle(seed):
     ops, n, m = process_sequences(H.records(reads), params, sp, args, H.prefilter_for(args))
     assert (n, m) == (total, matched)
     H.assert_ops_equal([H.op_to_dict(o) for o in ops], [H.op_to_dict(o) for o in expected], "seed %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(1000, 1016))
+def test_cuda_long_primers_match_live_oracle(seed):
+    """Primers of 65..300 nt: the warp-cooperative multi-word search (k_primer_long: ballot carry
+    lookahead, shuffled Ph/Mh shifts, in-kernel start recovery) against the live oracle."""
+    from test_random_tables_hostsim import make_case, run_case
+    run_case(*make_case(seed, long_primers=True), tag="long seed %d" % seed, binding="cuda")

@@ -38,13 +38,17 @@ def instantiate(rng, s):
     return "".join(rng.choice(IUPAC[c]) if c in IUPAC else c for c in s)
 
 
-def make_case(seed):
+def make_case(seed, long_primers=False):
+    """long_primers: some primers of 65..300 nt (the warp-cooperative multi-word search) and search
+    windows wide enough to hold them."""
     rng = random.Random(seed)
     n_fwd, n_rev = rng.randint(1, 3), rng.randint(1, 3)
     pools = ["P%d" % i for i in range(rng.randint(1, 2))]
     primers = []
     for i in range(n_fwd + n_rev):
         seq = rand_seq(rng, rng.randint(16, 26))
+        if long_primers and (i == 0 or rng.random() < 0.5):
+            seq = rand_seq(rng, rng.choice([65, 66, 96, 97, 127, 128, 129, 150, 200, 256, 257, 300]))
         if rng.random() < 0.5:
             seq = "".join(rng.choice("RYNWM") if rng.random() < 0.12 else c for c in seq)
         ppools = sorted(rng.sample(pools, rng.randint(1, len(pools))))
@@ -80,6 +84,8 @@ def make_case(seed):
     k_idx = rng.choice([0, 1, 2, 3, 3, 4, 5])
     k_idx = min(k_idx, min(len(b) for b in b1s + b2s) - 1)
     L = rng.choice([40, 80, 80, 120, 200])
+    if long_primers:
+        L = rng.choice([120, 200, 333, 512])
     reads = []
     by_name = {p[0]: p for p in primers}
     for r in range(rng.randint(40, 90)):
@@ -121,9 +127,25 @@ def make_case(seed):
     return primers, specimens, reads, k_idx, flags
 
 
+def test_long_primer_carry_lookahead():
+    """The kernel's one-addition carry-lookahead over the words of every segment of a warp
+    (long_carry_in<SW>) against a rippled carry chain, 2M random generate/propagate masks per width."""
+    lib = H.hostsim_binding()
+    assert lib.hostsim_check_long_carry(2_000_000) == 0
+
+
+@pytest.mark.parametrize("seed", range(1000, 1016))
+def test_random_case_long_primers(seed):
+    run_case(*make_case(seed, long_primers=True), tag="long seed %d" % seed)
+
+
 @pytest.mark.parametrize("seed", range(60))
 def test_random_case(seed):
-    primers, specimens, reads, k_idx, flags = make_case(seed)
+    run_case(*make_case(seed), tag="seed %d" % seed)
+
+
+def run_case(primers, specimens, reads, k_idx, flags, tag, binding=None):
+    """binding="cuda": through the CUDA library (GPU tests); default: the CPU kernel simulator."""
     try:
         tables = orc.Tables(primers, specimens)
     except ValueError:
@@ -136,6 +158,6 @@ def test_random_case(seed):
     params = MatchParameters(dict(oparams.max_dist_primers), k_idx, flags["search_len"], not flags["disable_preorient"])
     args = H.make_args(flags)
     ops, n, m = process_sequences(H.records(reads), params, sp, args, H.prefilter_for(args), None, 0,
-                                  _binding=H.hostsim_binding())
+                                  _binding=None if binding == "cuda" else H.hostsim_binding())
     assert (n, m) == (total, matched)
-    H.assert_ops_equal([H.op_to_dict(o) for o in ops], [H.op_to_dict(o) for o in expected], "seed %d" % seed)
+    H.assert_ops_equal([H.op_to_dict(o) for o in ops], [H.op_to_dict(o) for o in expected], tag)
