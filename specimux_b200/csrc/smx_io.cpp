@@ -1,0 +1,591 @@
+// smx_io.cpp -- native FASTQ/FASTA(.gz) reader and per-specimen output-tree writer
+// (include/specimux_io.h).  Host code only: no CUDA, no matching.
+//
+// Behavioural model (cited per function): the reference's use of Bio.SeqIO.parse
+// (io_utils.py:429-450), create_write_operation (demultiplex.py:30-103), OutputManager
+// (io_utils.py:179-268) and output_write_operation (io_utils.py:452-471).
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include "../../include/specimux_io.h"
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Python str whitespace (str.strip / str.split(None) on text decoded as UTF-8).
+// Returns the byte length of the whitespace character starting at p, 0 if none.
+inline int ws_at(const unsigned char *p, const unsigned char *end) {
+    const unsigned char c = *p;
+    if (c < 0x80) return ((c >= 9 && c <= 13) || (c >= 28 && c <= 32)) ? 1 : 0;
+    if (c == 0xC2 && p + 1 < end && (p[1] == 0x85 || p[1] == 0xA0)) return 2;
+    if (p + 2 < end) {
+        if (c == 0xE1 && p[1] == 0x9A && p[2] == 0x80) return 3;                       // U+1680
+        if (c == 0xE2 && p[1] == 0x80 && (p[2] <= 0x8A || p[2] == 0xA8 || p[2] == 0xA9 || p[2] == 0xAF) && p[2] >= 0x80) return 3;
+        if (c == 0xE2 && p[1] == 0x81 && p[2] == 0x9F) return 3;                       // U+205F
+        if (c == 0xE3 && p[1] == 0x80 && p[2] == 0x80) return 3;                       // U+3000
+    }
+    return 0;
+}
+
+// Length of the whitespace character ENDING at end (exclusive), 0 if none.
+inline int ws_before(const unsigned char *begin, const unsigned char *end) {
+    if (end <= begin) return 0;
+    const unsigned char c = end[-1];
+    if (c < 0x80) return ((c >= 9 && c <= 13) || (c >= 28 && c <= 32)) ? 1 : 0;
+    if (end - begin >= 2 && ws_at(end - 2, end) == 2) return 2;
+    if (end - begin >= 3 && ws_at(end - 3, end) == 3) return 3;
+    return 0;
+}
+
+inline void lstrip(const char *&b, const char *e) {
+    for (int n; b < e && (n = ws_at((const unsigned char *)b, (const unsigned char *)e)) != 0;) b += n;
+}
+inline void rstrip(const char *b, const char *&e) {
+    for (int n; e > b && (n = ws_before((const unsigned char *)b, (const unsigned char *)e)) != 0;) e -= n;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Blocks
+
+struct smx_block {
+    std::vector<char> bases, quals, titles;
+    std::vector<uint64_t> seq_off, title_off;
+    std::vector<uint32_t> id_start, id_len;
+    bool has_qual = false;
+    void clear(bool fastq) {
+        bases.clear(); quals.clear(); titles.clear();
+        seq_off.assign(1, 0); title_off.assign(1, 0);
+        id_start.clear(); id_len.clear();
+        has_qual = fastq;
+    }
+    uint32_t n() const { return (uint32_t)id_len.size(); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Reader
+
+struct smx_reader {
+    int fd = -1;
+    gzFile gz = nullptr;
+    bool fastq = true, eof = false;
+    std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    std::string path;
+    // FASTA: the title of the record whose sequence lines are being collected
+    bool fasta_open = false;
+    std::string fasta_title;
+
+    // Fills the buffer; returns false on a read error.
+    bool refill() {
+        if (pos > 0) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+        if (end == buf.size()) buf.resize(buf.size() * 2);
+        long got;
+        if (gz) got = gzread(gz, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
+        else got = (long)read(fd, buf.data() + end, buf.size() - end);
+        if (got < 0) return false;
+        if (got == 0) eof = true;
+        end += (size_t)got;
+        return true;
+    }
+
+    // Next line without its terminator ('\n'; a preceding '\r' is whitespace and stripped by every
+    // consumer).  Returns 0 at end of file, 1 with [b, e) set, -1 on a read error.  The pointers
+    // stay valid until the next call.
+    int line(const char *&b, const char *&e) {
+        for (;;) {
+            const char *nl = (const char *)memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) { b = buf.data() + pos; e = nl; pos = (size_t)(nl - buf.data()) + 1; return 1; }
+            if (eof) {
+                if (pos == end) return 0;
+                b = buf.data() + pos; e = buf.data() + end; pos = end; return 1;
+            }
+            if (!refill()) return -1;
+        }
+    }
+};
+
+namespace {
+
+void add_title(smx_block &blk, const char *b, const char *e) {
+    // record.description = whole title; record.id = first whitespace-delimited token
+    blk.titles.insert(blk.titles.end(), b, e);
+    blk.title_off.push_back(blk.titles.size());
+    const char *ib = b;
+    lstrip(ib, e);
+    const char *ie = ib;
+    while (ie < e && !ws_at((const unsigned char *)ie, (const unsigned char *)e)) ++ie;
+    blk.id_start.push_back((uint32_t)(ib - b));
+    blk.id_len.push_back((uint32_t)(ie - ib));
+}
+
+// One FASTQ record (FastqGeneralIterator semantics as restated in specimux_b200/seqio.py:
+// blank lines between records skipped, multi-line sequence / quality accepted).
+// Returns 1 record parsed, 0 end of file, <0 error.  `blk` may be null (skip).
+int next_fastq(smx_reader &r, smx_block *blk) {
+    const char *b, *e;
+    int rc;
+    for (;;) {
+        if ((rc = r.line(b, e)) <= 0) return rc < 0 ? -SMX_IO_ERR_IO : 0;
+        const char *sb = b, *se = e;
+        lstrip(sb, se);
+        if (sb < se) break;
+    }
+    if (*b != '@') return -fail(SMX_IO_ERR_FORMAT, "Records in Fastq files should start with '@' character");
+    const char *tb = b + 1, *te = e;
+    rstrip(tb, te);
+    std::string title(tb, te);          // kept for the error message and because the buffer may move
+    if (blk) add_title(*blk, title.data(), title.data() + title.size());
+    size_t seq_len = 0, qual_len = 0;
+    // sequence lines up to the '+' line
+    bool first = true;
+    for (;;) {
+        if ((rc = r.line(b, e)) < 0) return -SMX_IO_ERR_IO;
+        if (rc == 0) break;
+        if (!first && b < e && *b == '+') break;
+        if (!first && b == e) { /* empty line is not a '+' line: appended (nothing) */ }
+        const char *sb = b, *se = e;
+        lstrip(sb, se); rstrip(sb, se);
+        if (blk) blk->bases.insert(blk->bases.end(), sb, se);
+        seq_len += (size_t)(se - sb);
+        first = false;
+    }
+    // quality lines until as long as the sequence
+    bool got_one = false;
+    while (!got_one || qual_len < seq_len) {
+        if ((rc = r.line(b, e)) < 0) return -SMX_IO_ERR_IO;
+        if (rc == 0) break;
+        const char *sb = b, *se = e;
+        lstrip(sb, se); rstrip(sb, se);
+        if (blk) blk->quals.insert(blk->quals.end(), sb, se);
+        qual_len += (size_t)(se - sb);
+        got_one = true;
+    }
+    if (qual_len != seq_len)
+        return -fail(SMX_IO_ERR_FORMAT, "Lengths of sequence and quality values differs for %s", title.c_str());
+    if (blk) blk->seq_off.push_back(blk->bases.size());
+    return 1;
+}
+
+// One FASTA record (SimpleFastaParser semantics: lines before the first '>' ignored, sequence
+// lines stripped and concatenated).
+int next_fasta(smx_reader &r, smx_block *blk) {
+    const char *b, *e;
+    int rc;
+    while (!r.fasta_open) {
+        if ((rc = r.line(b, e)) <= 0) return rc < 0 ? -SMX_IO_ERR_IO : 0;
+        if (b < e && *b == '>') {
+            const char *tb = b + 1, *te = e;
+            rstrip(tb, te);
+            r.fasta_title.assign(tb, te);
+            r.fasta_open = true;
+        }
+    }
+    if (blk) add_title(*blk, r.fasta_title.data(), r.fasta_title.data() + r.fasta_title.size());
+    r.fasta_open = false;
+    for (;;) {
+        if ((rc = r.line(b, e)) < 0) return -SMX_IO_ERR_IO;
+        if (rc == 0) break;
+        if (b < e && *b == '>') {
+            const char *tb = b + 1, *te = e;
+            rstrip(tb, te);
+            r.fasta_title.assign(tb, te);
+            r.fasta_open = true;
+            break;
+        }
+        const char *sb = b, *se = e;
+        lstrip(sb, se); rstrip(sb, se);
+        if (blk) blk->bases.insert(blk->bases.end(), sb, se);
+    }
+    if (blk) blk->seq_off.push_back(blk->bases.size());
+    return 1;
+}
+
+bool ends_with(const std::string &s, const char *suffix) {
+    size_t n = strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smx_io_abi_version(void) { return SMX_IO_ABI_VERSION; }
+const char *smx_io_last_error(void) { return g_err; }
+
+int smx_reader_open(const char *path, int is_fastq, smx_reader **out) {
+    if (!path || !out) return fail(SMX_IO_ERR_ARG, "smx_reader_open: null argument");
+    smx_reader *r = new smx_reader();
+    r->path = path;
+    r->fastq = is_fastq != 0;
+    r->buf.resize(8u << 20);
+    if (ends_with(r->path, ".gz") || ends_with(r->path, ".gzip")) {
+        r->gz = gzopen(path, "rb");
+        if (!r->gz) { delete r; return fail(SMX_IO_ERR_OPEN, "cannot open %s: %s", path, strerror(errno)); }
+        gzbuffer(r->gz, 1u << 20);
+    } else {
+        r->fd = open(path, O_RDONLY);
+        if (r->fd < 0) { delete r; return fail(SMX_IO_ERR_OPEN, "cannot open %s: %s", path, strerror(errno)); }
+#ifdef POSIX_FADV_SEQUENTIAL
+        posix_fadvise(r->fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+    }
+    *out = r;
+    return SMX_IO_OK;
+}
+
+void smx_reader_close(smx_reader *r) {
+    if (!r) return;
+    if (r->gz) gzclose(r->gz);
+    if (r->fd >= 0) close(r->fd);
+    delete r;
+}
+
+smx_block *smx_block_create(void) {
+    smx_block *b = new smx_block();
+    b->clear(false);
+    return b;
+}
+
+void smx_block_destroy(smx_block *b) { delete b; }
+
+void smx_block_get(const smx_block *b, smx_block_view *out) {
+    if (!b || !out) return;
+    out->n_reads = b->n();
+    out->bases = b->bases.data();
+    out->seq_off = b->seq_off.data();
+    out->quals = b->has_qual ? b->quals.data() : nullptr;
+    out->titles = b->titles.data();
+    out->title_off = b->title_off.data();
+    out->id_start = b->id_start.data();
+    out->id_len = b->id_len.data();
+}
+
+int smx_reader_next(smx_reader *r, uint32_t max_reads, smx_block *blk) {
+    if (!r || !blk) return fail(SMX_IO_ERR_ARG, "smx_reader_next: null argument");
+    blk->clear(r->fastq);
+    for (uint32_t i = 0; i < max_reads; ++i) {
+        int rc = r->fastq ? next_fastq(*r, blk) : next_fasta(*r, blk);
+        if (rc < 0) {
+            if (-rc == SMX_IO_ERR_IO) return fail(SMX_IO_ERR_IO, "read error on %s", r->path.c_str());
+            return -rc;
+        }
+        if (rc == 0) break;
+    }
+    return SMX_IO_OK;
+}
+
+int smx_reader_skip(smx_reader *r, uint64_t n, uint64_t *skipped) {
+    if (!r) return fail(SMX_IO_ERR_ARG, "smx_reader_skip: null argument");
+    uint64_t done = 0;
+    for (; done < n; ++done) {
+        int rc = r->fastq ? next_fastq(*r, nullptr) : next_fasta(*r, nullptr);
+        if (rc < 0) {
+            if (-rc == SMX_IO_ERR_IO) return fail(SMX_IO_ERR_IO, "read error on %s", r->path.c_str());
+            return -rc;
+        }
+        if (rc == 0) break;
+    }
+    if (skipped) *skipped = done;
+    return SMX_IO_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Writer
+
+namespace {
+
+struct Complement {
+    unsigned char t[256];
+    Complement() {
+        // Bio.Seq's ambiguous-DNA complement (case preserved, U -> A, anything else unchanged),
+        // as the reference applies through SeqRecord.reverse_complement (demultiplex.py:142).
+        for (int i = 0; i < 256; ++i) t[i] = (unsigned char)i;
+        const char *src = "ACGTMRWSYKVHDBXN", *dst = "TGCAKYWSRMBDHVXN";
+        for (int i = 0; src[i]; ++i) {
+            t[(unsigned char)src[i]] = (unsigned char)dst[i];
+            t[(unsigned char)(src[i] + 32)] = (unsigned char)(dst[i] + 32);
+        }
+        t[(unsigned char)'U'] = 'A';
+        t[(unsigned char)'u'] = 'a';
+    }
+};
+const Complement kComplement;
+
+struct OutFile {
+    std::string path;
+    std::vector<char> buf;
+    bool dir_made = false;
+};
+
+constexpr size_t kFlushBytes = 256u << 10;      // per-file buffer before an append
+
+inline void put(std::vector<char> &v, const char *s, size_t n) { v.insert(v.end(), s, s + n); }
+inline void put(std::vector<char> &v, const std::string &s) { v.insert(v.end(), s.begin(), s.end()); }
+inline void put(std::vector<char> &v, char c) { v.push_back(c); }
+
+bool make_dirs(const std::string &dir) {          // os.makedirs(exist_ok=True)
+    struct stat st;
+    if (stat(dir.c_str(), &st) == 0) return S_ISDIR(st.st_mode);
+    size_t slash = dir.find_last_of('/');
+    if (slash != std::string::npos && slash > 0 && !make_dirs(dir.substr(0, slash))) return false;
+    return mkdir(dir.c_str(), 0777) == 0 || errno == EEXIST;
+}
+
+}  // namespace
+
+struct smx_writer {
+    bool to_files = true, fastq = true;
+    std::string dir, prefix, ext;
+    std::vector<std::string> specimen_id, specimen_file, b1_id, b1_file, b2_id, b2_file, pool, primer;
+    std::unordered_map<uint64_t, OutFile> files;      // keyed by packed (level, top, pool, p1, p2, sample kind, sample)
+    std::vector<char> scratch, console;
+    uint64_t n_records = 0, n_bytes = 0;
+    int first_error = SMX_IO_OK;
+    std::string first_error_msg;
+
+    void note_error(int code, const std::string &msg) {
+        if (first_error == SMX_IO_OK) { first_error = code; first_error_msg = msg; }
+    }
+
+    void flush(OutFile &f) {
+        if (f.buf.empty()) return;
+        if (!f.dir_made) {
+            size_t slash = f.path.find_last_of('/');
+            if (slash != std::string::npos && !make_dirs(f.path.substr(0, slash)))
+                note_error(SMX_IO_ERR_OPEN, "cannot create directory for " + f.path + ": " + strerror(errno));
+            f.dir_made = true;
+        }
+        int fd = open(f.path.c_str(), O_WRONLY | O_CREAT | O_APPEND, 0666);
+        if (fd < 0) {
+            note_error(SMX_IO_ERR_OPEN, "cannot open " + f.path + ": " + strerror(errno));
+        } else {
+            size_t off = 0;
+            while (off < f.buf.size()) {
+                ssize_t w = ::write(fd, f.buf.data() + off, f.buf.size() - off);
+                if (w < 0) {
+                    if (errno == EINTR) continue;
+                    note_error(SMX_IO_ERR_IO, "write to " + f.path + ": " + strerror(errno));
+                    break;
+                }
+                off += (size_t)w;
+            }
+            close(fd);
+        }
+        f.buf.clear();
+    }
+
+    void append(uint64_t key, const std::string &path_if_new, const std::vector<char> &content) {
+        auto it = files.find(key);
+        if (it == files.end()) {
+            it = files.emplace(key, OutFile()).first;
+            it->second.path = path_if_new;
+        }
+        OutFile &f = it->second;
+        f.buf.insert(f.buf.end(), content.begin(), content.end());
+        if (f.buf.size() >= kFlushBytes) flush(f);
+    }
+};
+
+namespace {
+
+void copy_names(std::vector<std::string> &dst, const char *const *src, uint32_t n) {
+    dst.clear();
+    for (uint32_t i = 0; i < n; ++i) dst.emplace_back(src && src[i] ? src[i] : "");
+}
+
+// Python slice bounds seq[s:e] for non-None ints.
+inline void py_slice(long long s, long long e, long long len, size_t &a, size_t &b) {
+    if (s < 0) { s += len; if (s < 0) s = 0; } else if (s > len) s = len;
+    if (e < 0) { e += len; if (e < 0) e = 0; } else if (e > len) e = len;
+    if (e < s) e = s;
+    a = (size_t)s; b = (size_t)e;
+}
+
+inline void put_int(std::vector<char> &v, int x) {
+    char tmp[16];
+    int n = snprintf(tmp, sizeof(tmp), "%d", x);
+    put(v, tmp, (size_t)n);
+}
+
+}  // namespace
+
+extern "C" {
+
+int smx_writer_open(const char *output_dir, const char *prefix, int is_fastq, const smx_names *nm, smx_writer **out) {
+    if (!nm || !out) return fail(SMX_IO_ERR_ARG, "smx_writer_open: null argument");
+    smx_writer *w = new smx_writer();
+    w->to_files = output_dir != nullptr;
+    w->fastq = is_fastq != 0;
+    w->dir = output_dir ? output_dir : "";
+    w->prefix = prefix ? prefix : "";
+    w->ext = is_fastq ? ".fastq" : ".fasta";
+    copy_names(w->specimen_id, nm->specimen_id, nm->n_specimens);
+    copy_names(w->specimen_file, nm->specimen_file, nm->n_specimens);
+    copy_names(w->b1_id, nm->b1_id, nm->n_b1);
+    copy_names(w->b1_file, nm->b1_file, nm->n_b1);
+    copy_names(w->b2_id, nm->b2_id, nm->n_b2);
+    copy_names(w->b2_file, nm->b2_file, nm->n_b2);
+    copy_names(w->pool, nm->pool, nm->n_pools);
+    copy_names(w->primer, nm->primer_name, nm->n_primers);
+    if (w->to_files && !make_dirs(w->dir)) {
+        int rc = fail(SMX_IO_ERR_OPEN, "cannot create %s: %s", w->dir.c_str(), strerror(errno));
+        delete w;
+        return rc;
+    }
+    *out = w;
+    return SMX_IO_OK;
+}
+
+int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs, uint64_t n_records) {
+    if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write: null argument");
+    static const std::string kUnknown = "unknown";
+    const uint32_t n_reads = blk->n();
+    std::vector<char> &c = w->scratch;
+    for (uint64_t i = 0; i < n_records; ++i) {
+        const smx_record &rec = recs[i];
+        if (rec.read >= n_reads) return fail(SMX_IO_ERR_ARG, "record %llu names read %u of a %u-read block", (unsigned long long)i, rec.read, n_reads);
+        const uint32_t r = rec.read;
+        const char *seq = blk->bases.data() + blk->seq_off[r];
+        const long long len = (long long)(blk->seq_off[r + 1] - blk->seq_off[r]);
+        const char *qual = blk->has_qual ? blk->quals.data() + blk->seq_off[r] : nullptr;
+        const char *id = blk->titles.data() + blk->title_off[r] + blk->id_start[r];
+        const size_t id_len = blk->id_len[r];
+
+        // names (demultiplex.py:47-73 empty-trim fallback; :541-598 sample ids)
+        const std::string *sample = &kUnknown, *sample_file = &kUnknown, *pool = &kUnknown, *p1 = &kUnknown, *p2 = &kUnknown;
+        int kind = 3;                                   // 0 specimen, 1 b1, 2 b2, 3 unknown
+        uint32_t sidx = 0;
+        size_t a = 0, b = (size_t)len;
+        if (!rec.trim_empty) {
+            py_slice(rec.trim_start, rec.trim_end, len, a, b);
+            const uint8_t res = rec.resolution;
+            if (res == SMX_RES_FULL_MATCH || res == SMX_RES_DEREPLICATED_FULL || res == SMX_RES_MULTIPLE_SPECIMENS) {
+                if (rec.sample < 0 || (uint32_t)rec.sample >= w->specimen_id.size()) return fail(SMX_IO_ERR_ARG, "record %llu: specimen %d out of range", (unsigned long long)i, rec.sample);
+                kind = 0; sidx = (uint32_t)rec.sample; sample = &w->specimen_id[sidx]; sample_file = &w->specimen_file[sidx];
+            } else if (res == SMX_RES_PARTIAL_FORWARD) {
+                if (rec.sample < 0 || (uint32_t)rec.sample >= w->b1_id.size()) return fail(SMX_IO_ERR_ARG, "record %llu: b1 %d out of range", (unsigned long long)i, rec.sample);
+                kind = 1; sidx = (uint32_t)rec.sample; sample = &w->b1_id[sidx]; sample_file = &w->b1_file[sidx];
+            } else if (res == SMX_RES_PARTIAL_REVERSE) {
+                if (rec.sample < 0 || (uint32_t)rec.sample >= w->b2_id.size()) return fail(SMX_IO_ERR_ARG, "record %llu: b2 %d out of range", (unsigned long long)i, rec.sample);
+                kind = 2; sidx = (uint32_t)rec.sample; sample = &w->b2_id[sidx]; sample_file = &w->b2_file[sidx];
+            }
+            if (rec.pool >= 0) { if ((size_t)rec.pool >= w->pool.size()) return fail(SMX_IO_ERR_ARG, "record %llu: pool out of range", (unsigned long long)i); pool = &w->pool[rec.pool]; }
+            if (rec.p1 >= 0) { if ((size_t)rec.p1 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p1 out of range", (unsigned long long)i); p1 = &w->primer[rec.p1]; }
+            if (rec.p2 >= 0) { if ((size_t)rec.p2 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p2 out of range", (unsigned long long)i); p2 = &w->primer[rec.p2]; }
+        }
+
+        // content
+        c.clear();
+        put(c, w->fastq ? '@' : '>');
+        put(c, id, id_len);
+        put(c, ' ');
+        for (int d = 0; d < 4; ++d) {                    // distance_code (models.py:206-218)
+            if (d) put(c, ',');
+            if (rec.dist[d] >= 0) put_int(c, rec.dist[d]); else put(c, 'X');
+        }
+        if (w->to_files) {
+            put(c, " pool=", 6); put(c, *pool);
+            put(c, " primers=", 9); put(c, *p1); put(c, '+'); put(c, *p2);
+        }
+        put(c, ' '); put(c, *sample); put(c, '\n');
+        const size_t n_out = b - a;
+        size_t at = c.size();
+        c.resize(at + n_out);
+        if (rec.reverse) {
+            // oriented read = reverse complement; slice [a, b) of it = original (len-b .. len-a] reversed
+            const char *src = seq + (len - (long long)a) - 1;
+            for (size_t j = 0; j < n_out; ++j) c[at + j] = (char)kComplement.t[(unsigned char)src[-(long long)j]];
+        } else if (n_out) {
+            memcpy(c.data() + at, seq + a, n_out);
+        }
+        put(c, '\n');
+        if (w->fastq) {
+            put(c, "+\n", 2);
+            at = c.size();
+            c.resize(at + n_out);
+            if (!qual) memset(c.data() + at, 'I', n_out);
+            else if (rec.reverse) {
+                const char *src = qual + (len - (long long)a) - 1;
+                for (size_t j = 0; j < n_out; ++j) c[at + j] = src[-(long long)j];
+            } else if (n_out) memcpy(c.data() + at, qual + a, n_out);
+            put(c, '\n');
+        }
+        ++w->n_records;
+        w->n_bytes += c.size();
+
+        if (!w->to_files) {
+            put(w->console, c.data(), c.size());
+            if (w->console.size() >= kFlushBytes) { fwrite(w->console.data(), 1, w->console.size(), stdout); w->console.clear(); }
+            continue;
+        }
+        // OutputManager._make_filename (io_utils.py:206-220)
+        const uint8_t res = rec.trim_empty ? (uint8_t)SMX_RES_UNKNOWN : rec.resolution;
+        const int top = res == SMX_RES_UNKNOWN ? 2 : (res == SMX_RES_PARTIAL_FORWARD || res == SMX_RES_PARTIAL_REVERSE) ? 1 : 0;
+        const uint64_t pool_i = (uint64_t)(pool == &kUnknown ? 0 : rec.pool + 1);
+        const uint64_t p1_i = (uint64_t)(p1 == &kUnknown ? 0 : rec.p1 + 1), p2_i = (uint64_t)(p2 == &kUnknown ? 0 : rec.p2 + 1);
+        const uint64_t skey = ((uint64_t)kind << 30) | sidx;
+        const uint64_t key = ((uint64_t)top << 62) | (pool_i << 52) | (p1_i << 44) | (p2_i << 36) | skey;
+        static const char *kTop[3] = {"full", "partial", "unknown"};
+        if (w->files.find(key) == w->files.end()) {
+            std::string path = w->dir + "/" + kTop[top] + "/" + *pool + "/" + *p1 + "-" + *p2 + "/" + w->prefix + *sample_file + w->ext;
+            w->append(key, path, c);
+        } else {
+            w->append(key, std::string(), c);
+        }
+        if (!rec.trim_empty && (rec.resolution == SMX_RES_FULL_MATCH || rec.resolution == SMX_RES_DEREPLICATED_FULL)) {
+            // pool-level duplicate of full matches (io_utils.py:259-268)
+            const uint64_t pkey = (3ull << 62) | (pool_i << 52) | skey;
+            if (w->files.find(pkey) == w->files.end()) {
+                std::string path = w->dir + "/full/" + *pool + "/" + w->prefix + *sample_file + w->ext;
+                w->append(pkey, path, c);
+            } else {
+                w->append(pkey, std::string(), c);
+            }
+        }
+    }
+    if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());
+    return SMX_IO_OK;
+}
+
+int smx_writer_close(smx_writer *w) {
+    if (!w) return SMX_IO_OK;
+    for (auto &kv : w->files) w->flush(kv.second);
+    if (!w->console.empty()) fwrite(w->console.data(), 1, w->console.size(), stdout);
+    if (!w->to_files) fflush(stdout);
+    int rc = w->first_error;
+    if (rc != SMX_IO_OK) fail(rc, "%s", w->first_error_msg.c_str());
+    delete w;
+    return rc;
+}
+
+void smx_writer_stats(const smx_writer *w, uint64_t *records, uint64_t *bytes) {
+    if (!w) return;
+    if (records) *records = w->n_records;
+    if (bytes) *bytes = w->n_bytes;
+}
+
+}  // extern "C"
