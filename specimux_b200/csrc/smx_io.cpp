@@ -7,7 +7,9 @@
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -335,17 +337,53 @@ struct Complement {
 };
 const Complement kComplement;
 
+// Growable byte buffer without value-initialisation (std::vector<char>::resize zero-fills what the
+// formatter overwrites straight away; realloc can also remap large blocks instead of copying them).
+struct Bytes {
+    char *p = nullptr;
+    size_t n = 0, cap = 0;
+    Bytes() = default;
+    Bytes(const Bytes &) = delete;
+    Bytes &operator=(const Bytes &) = delete;
+    Bytes(Bytes &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    ~Bytes() { free(p); }
+    char *grow(size_t extra) {           // room for `extra` more bytes; returns the write position
+        if (n + extra > cap) {
+            size_t want = cap ? cap * 2 : 4096;
+            while (want < n + extra) want *= 2;
+            char *q = (char *)realloc(p, want);
+            if (!q) throw std::bad_alloc();
+            p = q; cap = want;
+        }
+        return p + n;
+    }
+    bool empty() const { return n == 0; }
+    size_t size() const { return n; }
+    const char *data() const { return p; }
+    void clear() { n = 0; }
+};
+
 struct OutFile {
     std::string path;
-    std::vector<char> buf;
+    Bytes buf;
     bool dir_made = false;
 };
 
-constexpr size_t kFlushBytes = 256u << 10;      // per-file buffer before an append
+// Per-file buffer before an append.  Small on purpose: with ~1,500 open specimen files the buffers
+// are the writer's working set, and first-touch page faults of large buffers cost more than the
+// extra open/append/close calls (measured: tools/io_bench.py).  SMX_IO_FLUSH_KB overrides.
+size_t flush_bytes() {
+    static const size_t v = [] {
+        const char *e = getenv("SMX_IO_FLUSH_KB");
+        long kb = e ? atol(e) : 0;
+        return (size_t)(kb > 0 ? kb : 64) << 10;
+    }();
+    return v;
+}
 
-inline void put(std::vector<char> &v, const char *s, size_t n) { v.insert(v.end(), s, s + n); }
-inline void put(std::vector<char> &v, const std::string &s) { v.insert(v.end(), s.begin(), s.end()); }
-inline void put(std::vector<char> &v, char c) { v.push_back(c); }
+inline void put(Bytes &v, const char *s, size_t n) { memcpy(v.grow(n), s, n); v.n += n; }
+inline void put(Bytes &v, const std::string &s) { put(v, s.data(), s.size()); }
+inline void put(Bytes &v, char c) { *v.grow(1) = c; ++v.n; }
 
 bool make_dirs(const std::string &dir) {          // os.makedirs(exist_ok=True)
     struct stat st;
@@ -362,7 +400,7 @@ struct smx_writer {
     std::string dir, prefix, ext;
     std::vector<std::string> specimen_id, specimen_file, b1_id, b1_file, b2_id, b2_file, pool, primer;
     std::unordered_map<uint64_t, OutFile> files;      // keyed by packed (level, top, pool, p1, p2, sample kind, sample)
-    std::vector<char> scratch, console;
+    Bytes console;
     uint64_t n_records = 0, n_bytes = 0;
     int first_error = SMX_IO_OK;
     std::string first_error_msg;
@@ -398,16 +436,6 @@ struct smx_writer {
         f.buf.clear();
     }
 
-    void append(uint64_t key, const std::string &path_if_new, const std::vector<char> &content) {
-        auto it = files.find(key);
-        if (it == files.end()) {
-            it = files.emplace(key, OutFile()).first;
-            it->second.path = path_if_new;
-        }
-        OutFile &f = it->second;
-        f.buf.insert(f.buf.end(), content.begin(), content.end());
-        if (f.buf.size() >= kFlushBytes) flush(f);
-    }
 };
 
 namespace {
@@ -425,7 +453,7 @@ inline void py_slice(long long s, long long e, long long len, size_t &a, size_t 
     a = (size_t)s; b = (size_t)e;
 }
 
-inline void put_int(std::vector<char> &v, int x) {
+inline void put_int(Bytes &v, int x) {
     char tmp[16];
     int n = snprintf(tmp, sizeof(tmp), "%d", x);
     put(v, tmp, (size_t)n);
@@ -464,7 +492,6 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
     if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write: null argument");
     static const std::string kUnknown = "unknown";
     const uint32_t n_reads = blk->n();
-    std::vector<char> &c = w->scratch;
     for (uint64_t i = 0; i < n_records; ++i) {
         const smx_record &rec = recs[i];
         if (rec.read >= n_reads) return fail(SMX_IO_ERR_ARG, "record %llu names read %u of a %u-read block", (unsigned long long)i, rec.read, n_reads);
@@ -498,8 +525,39 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
             if (rec.p2 >= 0) { if ((size_t)rec.p2 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p2 out of range", (unsigned long long)i); p2 = &w->primer[rec.p2]; }
         }
 
-        // content
-        c.clear();
+        // destination: OutputManager._make_filename (io_utils.py:206-220), or the console buffer
+        OutFile *primary = nullptr, *pool_level = nullptr;
+        if (w->to_files) {
+            const uint8_t res = rec.trim_empty ? (uint8_t)SMX_RES_UNKNOWN : rec.resolution;
+            const int top = res == SMX_RES_UNKNOWN ? 2 : (res == SMX_RES_PARTIAL_FORWARD || res == SMX_RES_PARTIAL_REVERSE) ? 1 : 0;
+            const uint64_t pool_i = (uint64_t)(pool == &kUnknown ? 0 : rec.pool + 1);
+            const uint64_t p1_i = (uint64_t)(p1 == &kUnknown ? 0 : rec.p1 + 1), p2_i = (uint64_t)(p2 == &kUnknown ? 0 : rec.p2 + 1);
+            const uint64_t skey = ((uint64_t)kind << 30) | sidx;
+            const uint64_t key = ((uint64_t)top << 62) | (pool_i << 52) | (p1_i << 44) | (p2_i << 36) | skey;
+            static const char *kTop[3] = {"full", "partial", "unknown"};
+            auto it = w->files.find(key);
+            if (it == w->files.end()) {
+                it = w->files.emplace(key, OutFile()).first;
+                it->second.path = w->dir + "/" + kTop[top] + "/" + *pool + "/" + *p1 + "-" + *p2 + "/" + w->prefix + *sample_file + w->ext;
+            }
+            primary = &it->second;
+            if (!rec.trim_empty && (rec.resolution == SMX_RES_FULL_MATCH || rec.resolution == SMX_RES_DEREPLICATED_FULL)) {
+                // pool-level duplicate of full matches (io_utils.py:259-268)
+                const uint64_t pkey = (3ull << 62) | (pool_i << 52) | skey;
+                auto pit = w->files.find(pkey);
+                if (pit == w->files.end()) {
+                    pit = w->files.emplace(pkey, OutFile()).first;
+                    pit->second.path = w->dir + "/full/" + *pool + "/" + w->prefix + *sample_file + w->ext;
+                    primary = &w->files.find(key)->second;      // emplace may have rehashed
+                }
+                pool_level = &pit->second;
+            }
+        }
+        Bytes &c = primary ? primary->buf : w->console;
+        const size_t rec_begin = c.size();
+
+        // content, formatted in place
+        const size_t n_out = b - a;
         put(c, w->fastq ? '@' : '>');
         put(c, id, id_len);
         put(c, ' ');
@@ -512,59 +570,43 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
             put(c, " primers=", 9); put(c, *p1); put(c, '+'); put(c, *p2);
         }
         put(c, ' '); put(c, *sample); put(c, '\n');
-        const size_t n_out = b - a;
-        size_t at = c.size();
-        c.resize(at + n_out);
-        if (rec.reverse) {
-            // oriented read = reverse complement; slice [a, b) of it = original (len-b .. len-a] reversed
-            const char *src = seq + (len - (long long)a) - 1;
-            for (size_t j = 0; j < n_out; ++j) c[at + j] = (char)kComplement.t[(unsigned char)src[-(long long)j]];
-        } else if (n_out) {
-            memcpy(c.data() + at, seq + a, n_out);
-        }
-        put(c, '\n');
-        if (w->fastq) {
-            put(c, "+\n", 2);
-            at = c.size();
-            c.resize(at + n_out);
-            if (!qual) memset(c.data() + at, 'I', n_out);
-            else if (rec.reverse) {
-                const char *src = qual + (len - (long long)a) - 1;
-                for (size_t j = 0; j < n_out; ++j) c[at + j] = src[-(long long)j];
-            } else if (n_out) memcpy(c.data() + at, qual + a, n_out);
-            put(c, '\n');
-        }
-        ++w->n_records;
-        w->n_bytes += c.size();
-
-        if (!w->to_files) {
-            put(w->console, c.data(), c.size());
-            if (w->console.size() >= kFlushBytes) { fwrite(w->console.data(), 1, w->console.size(), stdout); w->console.clear(); }
-            continue;
-        }
-        // OutputManager._make_filename (io_utils.py:206-220)
-        const uint8_t res = rec.trim_empty ? (uint8_t)SMX_RES_UNKNOWN : rec.resolution;
-        const int top = res == SMX_RES_UNKNOWN ? 2 : (res == SMX_RES_PARTIAL_FORWARD || res == SMX_RES_PARTIAL_REVERSE) ? 1 : 0;
-        const uint64_t pool_i = (uint64_t)(pool == &kUnknown ? 0 : rec.pool + 1);
-        const uint64_t p1_i = (uint64_t)(p1 == &kUnknown ? 0 : rec.p1 + 1), p2_i = (uint64_t)(p2 == &kUnknown ? 0 : rec.p2 + 1);
-        const uint64_t skey = ((uint64_t)kind << 30) | sidx;
-        const uint64_t key = ((uint64_t)top << 62) | (pool_i << 52) | (p1_i << 44) | (p2_i << 36) | skey;
-        static const char *kTop[3] = {"full", "partial", "unknown"};
-        if (w->files.find(key) == w->files.end()) {
-            std::string path = w->dir + "/" + kTop[top] + "/" + *pool + "/" + *p1 + "-" + *p2 + "/" + w->prefix + *sample_file + w->ext;
-            w->append(key, path, c);
-        } else {
-            w->append(key, std::string(), c);
-        }
-        if (!rec.trim_empty && (rec.resolution == SMX_RES_FULL_MATCH || rec.resolution == SMX_RES_DEREPLICATED_FULL)) {
-            // pool-level duplicate of full matches (io_utils.py:259-268)
-            const uint64_t pkey = (3ull << 62) | (pool_i << 52) | skey;
-            if (w->files.find(pkey) == w->files.end()) {
-                std::string path = w->dir + "/full/" + *pool + "/" + w->prefix + *sample_file + w->ext;
-                w->append(pkey, path, c);
-            } else {
-                w->append(pkey, std::string(), c);
+        {
+            char *dst = c.grow(2 * n_out + 4);
+            if (rec.reverse) {
+                // oriented read = reverse complement; its slice [a, b) = original (len-b .. len-a] reversed
+                const unsigned char *src = (const unsigned char *)seq + (len - (long long)a) - 1;
+                const unsigned char *tab = kComplement.t;
+                for (size_t j = 0; j < n_out; ++j) dst[j] = (char)tab[src[-(long long)j]];
+            } else if (n_out) {
+                memcpy(dst, seq + a, n_out);
             }
+            dst += n_out;
+            *dst++ = '\n';
+            if (w->fastq) {
+                *dst++ = '+'; *dst++ = '\n';
+                if (!qual) memset(dst, 'I', n_out);
+                else if (rec.reverse) {
+                    const char *src = qual + (len - (long long)a) - 1;
+                    for (size_t j = 0; j < n_out; ++j) dst[j] = src[-(long long)j];
+                } else if (n_out) memcpy(dst, qual + a, n_out);
+                dst += n_out;
+                *dst++ = '\n';
+            }
+            c.n = (size_t)(dst - c.p);
+        }
+        const size_t rec_bytes = c.size() - rec_begin;
+        ++w->n_records;
+        w->n_bytes += rec_bytes;
+        if (pool_level) {
+            memcpy(pool_level->buf.grow(rec_bytes), c.p + rec_begin, rec_bytes);
+            pool_level->buf.n += rec_bytes;
+            if (pool_level->buf.size() >= flush_bytes()) w->flush(*pool_level);
+        }
+        if (primary) {
+            if (c.size() >= flush_bytes()) w->flush(*primary);
+        } else if (c.size() >= flush_bytes()) {
+            fwrite(c.data(), 1, c.size(), stdout);
+            c.clear();
         }
     }
     if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());

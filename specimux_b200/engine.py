@@ -4,6 +4,7 @@
 missing library raises ImportError, a missing GPU raises SmxError(SMX_ERR_NO_DEVICE).
 """
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -30,19 +31,41 @@ class PackedBatch:
         self._init_from_blob(blob, np.ascontiguousarray(seq_off, dtype=np.uint64), clip)
         return self
 
+    @classmethod
+    def from_block(cls, block, clip: int = 0, reuse: "PackedBatch" = None):
+        """Packs a native_io.ReadBlock straight from the reader's memory (no Python strings).
+        `reuse`: a PackedBatch whose pinned buffers are recycled when they are large enough."""
+        self = reuse if reuse is not None else cls.__new__(cls)
+        self._init_from_blob(block.bases_ptr or b"", block.seq_off(), clip)
+        return self
+
+    def _buffer(self, slot, count, dtype):
+        """Pinned host buffer `slot`, grown geometrically and kept across repacks."""
+        bufs = self.__dict__.setdefault("_bufs", {})
+        hb = bufs.get(slot)
+        if hb is None or len(hb.array) < count:
+            if hb is not None:
+                hb.free()
+            hb = bufs[slot] = _lib.HostBuffer(max(int(count * 1.25), 1), dtype)
+        return hb.array[:count]
+
     def _init_from_blob(self, blob, seq_off, clip):
+        """blob: bytes, or the address of the concatenated bases."""
         lib = _lib.load()
         n = len(seq_off) - 1
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         w2, w4 = C.c_uint64(0), C.c_uint64(0)
         lib.smx_pack_bound(_lib.ptr(seq_off, _lib.u64p), n, clip, C.byref(w2), C.byref(w4))
         self.n_reads = n
         self.clip = int(clip)
-        self._bufs = [_lib.HostBuffer(int(w2.value), np.uint32), _lib.HostBuffer(max(n, 1), np.uint64),
-                      _lib.HostBuffer(max(n, 1), np.uint32), _lib.HostBuffer(max(n, 1), np.uint64)]
-        self.packed2, self.word_off, self.lengths, self.off4 = (hb.array for hb in self._bufs)
+        self.packed2 = self._buffer(0, int(w2.value), np.uint32)
+        self.word_off = self._buffer(1, max(n, 1), np.uint64)
+        self.lengths = self._buffer(2, max(n, 1), np.uint32)
+        self.off4 = self._buffer(3, max(n, 1), np.uint64)
         packed4 = np.zeros(int(w4.value), dtype=np.uint32)
         used4, flagged = C.c_uint64(0), C.c_uint32(0)
-        _lib.check(lib.smx_pack_reads(blob, _lib.ptr(seq_off, _lib.u64p), n, clip, _lib.ptr(self.packed2, _lib.u32p),
+        src = blob if isinstance(blob, (bytes, bytearray)) else C.cast(C.c_void_p(int(blob)), C.c_char_p)
+        _lib.check(lib.smx_pack_reads(src, _lib.ptr(seq_off, _lib.u64p), n, clip, _lib.ptr(self.packed2, _lib.u32p),
                                       _lib.ptr(self.word_off, _lib.u64p), _lib.ptr(self.lengths, _lib.u32p),
                                       _lib.ptr(packed4, _lib.u32p), _lib.ptr(self.off4, _lib.u64p),
                                       C.byref(used4), C.byref(flagged)))
@@ -88,6 +111,7 @@ class Matcher:
         self.tables = tables
         self._binding = binding
         self._ctx = C.c_void_p(None)
+        self._lock = threading.Lock()
         if binding is None:
             self._lib = _lib.load()
             _lib.check(self._lib.smx_create(device, tables.tables_ref(), tables.params_ref(), C.byref(self._ctx)))
@@ -116,9 +140,11 @@ class Matcher:
         t = self.tables
         cap = int(cap if cap is not None else n + n // 8 + 1024)
         res = _lib.SmxResults()
-        if reuse:
-            # pinned pool reused across calls: the previous call's result arrays are overwritten
-            pool = self.__dict__.setdefault("_result_pool", {})
+        if reuse is not None and reuse is not False:
+            # pinned pool reused across calls: the previous call's result arrays are overwritten.
+            # reuse=True: one pool per Matcher; reuse=<dict>: a pool owned by the caller (lets several
+            # results stay alive, e.g. while a writer thread still formats an earlier batch)
+            pool = reuse if isinstance(reuse, dict) else self.__dict__.setdefault("_result_pool", {})
             if pool.get("n", -1) < n + 1:
                 pool["n"], pool["off"] = n + 1, _lib.HostBuffer(n + 1, np.uint32)
             if pool.get("cap", -1) < cap:
@@ -145,8 +171,14 @@ class Matcher:
         return BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh)
 
     # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
-    def match(self, batch: PackedBatch, detail: bool = False, reuse: bool = False) -> BatchResult:
-        """`reuse=True` returns views into a pinned pool that the next reuse=True call overwrites."""
+    def match(self, batch: PackedBatch, detail: bool = False, reuse=False) -> BatchResult:
+        """`reuse=True` returns views into a pinned pool that the next reuse=True call overwrites;
+        `reuse=<dict>` uses (and grows) a caller-owned pool instead.  A context is not re-entrant:
+        calls from several threads are serialised here."""
+        with self._lock:
+            return self._match_locked(batch, detail, reuse)
+
+    def _match_locked(self, batch, detail, reuse):
         cb = batch.c_batch()
         cap = None
         while True:

@@ -174,6 +174,22 @@ def _run(args, multi: bool):
     specimens = read_specimen_file(args.specimen_file, primer_registry)
     specimens.validate()
     parameters = setup_match_parameters(args, specimens)
+    n_visible = _visible_gpus()
+    if n_visible < 1:
+        raise RuntimeError("specimux_b200: no CUDA device visible; the matching has no CPU fallback")
+    n_gpus = n_visible if (multi and args.threads <= 0) else max(1, min(n_visible, args.threads if multi else 1))
+    prefilter = PassthroughPrefilter() if args.disable_prefilter else BloomEmulationPrefilter()
+    if _native_eligible(args):
+        create_output_files(args, specimens)
+        start = timeit.default_timer()
+        logging.info(f"Will run on {n_gpus} GPU(s), {GPU_BATCH_READS} reads per batch, native reader/writer")
+        total, matched = _run_native(args, specimens, parameters, n_gpus, prefilter)
+        if total > 0:
+            logging.info(f"Processed {total:,} sequences, match rate: {matched / total:.1%}")
+        logging.info(f"Elapsed time: {timeit.default_timer() - start:.2f} seconds")
+        if args.output_to_files:
+            cleanup_empty_directories(args.output_dir)
+        return
     seq_records = open_sequence_file(args.sequence_file, args)
     create_output_files(args, specimens)
     start = timeit.default_timer()
@@ -181,12 +197,7 @@ def _run(args, multi: bool):
         for _ in itertools.islice(seq_records, args.start_seq - 1):
             pass
     all_seqs = args.num_seqs < 0
-    n_visible = _visible_gpus()
-    if n_visible < 1:
-        raise RuntimeError("specimux_b200: no CUDA device visible; the matching has no CPU fallback")
-    n_gpus = n_visible if (multi and args.threads <= 0) else max(1, min(n_visible, args.threads if multi else 1))
     logging.info(f"Will run on {n_gpus} GPU(s), {GPU_BATCH_READS} reads per batch")
-    prefilter = PassthroughPrefilter() if args.disable_prefilter else BloomEmulationPrefilter()
     stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
     trace_logger = None
     if args.diagnostics and args.output_to_files:
@@ -234,6 +245,118 @@ def _run(args, multi: bool):
     logging.info(f"Elapsed time: {timeit.default_timer() - start:.2f} seconds")
     if args.output_to_files:
         cleanup_empty_directories(args.output_dir)
+
+
+def _native_eligible(args) -> bool:
+    """The native reader / writer route carries everything except per-read trace events, which
+    need Python-side record objects (trace.py)."""
+    return not args.diagnostics and os.environ.get("SMX_NATIVE_IO", "1") != "0"
+
+
+def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=None):
+    """FASTQ/FASTA file -> output tree with no per-read Python objects: native reader -> 2-bit packer
+    -> smx_match_batch on `n_gpus` GPUs -> native writer.  Three kinds of threads run concurrently
+    (every stage is a GIL-free C call): this thread reads + packs, one feeder thread per GPU matches,
+    one writer thread formats and appends in submission order, so per-file record order is the input
+    order (= the reference's `-t 1` order) for any GPU count.
+    Returns (total reads, matched reads)."""
+    import queue
+    import threading
+    from .demultiplex import get_matcher
+    from .engine import PackedBatch
+    from .io_utils import detect_file_format
+    from .native_io import FastxReader, ReadBlock, TreeWriter
+
+    fmt = detect_file_format(args.sequence_file)
+    args.isfastq = fmt == "fastq"
+    matchers = [get_matcher(parameters, specimens, args, prefilter, dev, _binding) for dev in range(n_gpus)]
+    reader = FastxReader(args.sequence_file, args.isfastq)
+    writer = TreeWriter(args.output_dir if args.output_to_files else None, args.output_file_prefix, args.isfastq,
+                        matchers[0].tables)
+
+    class Job:
+        def __init__(self):
+            self.block, self.batch, self.pool = ReadBlock(), None, {}
+            self.result = self.error = None
+            self.done = threading.Event()
+
+    n_jobs = 2 * n_gpus + 2
+    free = queue.Queue()
+    for _ in range(n_jobs):
+        free.put(Job())
+    gpu_q = [queue.Queue() for _ in range(n_gpus)]
+    write_q = queue.Queue()
+    errors = []
+    counts = [0, 0]
+
+    def gpu_worker(dev):
+        while True:
+            job = gpu_q[dev].get()
+            if job is None:
+                return
+            try:
+                job.result = matchers[dev].match(job.batch, reuse=job.pool)
+            except BaseException as e:          # surfaced by the writer thread in submission order
+                job.error = e
+            job.done.set()
+
+    def write_worker():
+        while True:
+            job = write_q.get()
+            if job is None:
+                return
+            job.done.wait()
+            try:
+                if job.error is not None:
+                    raise job.error
+                if not errors:
+                    writer.write(job.block, job.result.records)
+                    counts[0] += job.block.n_reads
+                    counts[1] += job.result.n_matched
+            except BaseException as e:
+                errors.append(e)
+            job.result = job.error = None
+            job.done.clear()
+            free.put(job)
+
+    threads = [threading.Thread(target=gpu_worker, args=(d,), daemon=True) for d in range(n_gpus)]
+    threads.append(threading.Thread(target=write_worker, daemon=True))
+    for t in threads:
+        t.start()
+    try:
+        if getattr(args, "start_seq", 1) > 1:
+            reader.skip(args.start_seq - 1)
+        remaining = args.num_seqs if args.num_seqs >= 0 else None
+        i = 0
+        while not errors and (remaining is None or remaining > 0):
+            job = free.get()
+            want = GPU_BATCH_READS if remaining is None else min(GPU_BATCH_READS, remaining)
+            reader.next_block(want, job.block)
+            if job.block.n_reads == 0:
+                free.put(job)
+                break
+            if remaining is not None:
+                remaining -= job.block.n_reads
+            job.batch = PackedBatch.from_block(job.block, clip=parameters.search_len, reuse=job.batch)
+            write_q.put(job)                     # submission order = output order
+            gpu_q[i % n_gpus].put(job)
+            i += 1
+    except BaseException as e:
+        errors.append(e)
+    finally:
+        for q in gpu_q:
+            q.put(None)
+        write_q.put(None)
+        for t in threads:
+            t.join()
+        reader.close()
+        try:
+            writer.close()
+        except BaseException as e:
+            errors.append(e)
+    if errors:
+        raise errors[0]
+    return counts[0], counts[1]
 
 
 def specimux_mp(args):

@@ -61,6 +61,40 @@ def test_full_pipeline_matches_reference_expected_output(tmp_path):
         assert produced[k] == expected[k], k
 
 
+@pytest.mark.parametrize("native", ["1", "0"])
+def test_full_pipeline_both_io_routes_match_reference_expected_output(tmp_path, native):
+    """No -d: the native reader/writer route (SMX_NATIVE_IO=1, default) and the Python-object route
+    (SMX_NATIVE_IO=0) both reproduce the reference's expected_output tree byte for byte."""
+    g, p, s, q = _write_inputs(tmp_path, "fixture")
+    out = str(tmp_path / "out")
+    env = dict(os.environ, SMX_NATIVE_IO=native)
+    r = subprocess.run([sys.executable, "-m", "specimux_b200.cli", p, s, q, "-F", "-O", out], capture_output=True,
+                       text=True, cwd=H.ROOT, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    assert "Processed 40 sequences" in r.stderr
+    assert ("native reader/writer" in r.stderr) == (native == "1")
+    produced = {k: v for k, v in _tree(out).items() if k != "log.txt"}
+    expected = g["expected_output"]
+    assert sorted(produced) == sorted(expected)
+    for k in expected:
+        assert produced[k] == expected[k], k
+
+
+def test_native_route_gzip_input_and_console_output(tmp_path):
+    import gzip
+    g, p, s, q = _write_inputs(tmp_path, "fixture")
+    with open(q, "rb") as src, gzip.open(q + ".gz", "wb") as dst:
+        dst.write(src.read())
+    a = _run_cli(p, s, q, "-n", "12")
+    b = _run_cli(p, s, q + ".gz", "-n", "12")
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert a.stdout == b.stdout and a.stdout.count("\n") >= 48
+    env = dict(os.environ, SMX_NATIVE_IO="0")
+    c = subprocess.run([sys.executable, "-m", "specimux_b200.cli", p, s, q, "-n", "12"], capture_output=True, text=True,
+                       cwd=H.ROOT, timeout=600, env=env)
+    assert c.returncode == 0 and c.stdout == a.stdout
+
+
 @pytest.mark.parametrize("n", [5, 10, 20])
 def test_partial_sequences(tmp_path, n):
     g, p, s, q = _write_inputs(tmp_path, "fixture")
