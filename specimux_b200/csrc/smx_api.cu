@@ -64,7 +64,7 @@ template <typename T> cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h) 
 // One pipeline lane: a stream plus every per-batch device buffer.  Lane 0 serves the resident API
 // (upload / run / download on a whole batch); smx_match_batch splits large batches into chunks that
 // rotate over all lanes so one chunk's H2D, another's kernels and a third's D2H overlap.
-constexpr int kLanes = 3;
+constexpr int kMaxLanes = 8;          // upper bound; the number in use is smx_ctx::n_lanes (SMX_PIPELINE_LANES)
 constexpr int kAuxStreams = 2;
 constexpr int kKernelMarks = 10;
 constexpr int kKernelTimes = 9;
@@ -136,7 +136,8 @@ struct smx_ctx {
     DevBuf<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
     std::vector<unsigned char> prow_code;   // [primer][32] pattern row codes (sliced primer search)
-    Lane lane[kLanes];
+    Lane lane[kMaxLanes];
+    int n_lanes = 3;
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
     DevBuf<unsigned char> l2_scratch;
     u32 chunk_reads = 128 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK)
@@ -545,6 +546,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         if (v >= 128) c->chunk_reads = (u32)std::min<long>(v, 1L << 30);
         else if (v == 0) c->chunk_reads = 0;                   // 0 disables the pipelined form
     }
+    if (const char *env = getenv("SMX_PIPELINE_LANES")) c->n_lanes = std::max(2, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
@@ -666,7 +668,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
 }
 
 // Pipelined form of the whole path for large batches: the reads are cut into chunks that rotate
-// over kLanes lanes (stream + buffers each), so chunk i+1's H2D, chunk i's kernels and chunk i-1's
+// over n_lanes lanes (stream + buffers each), so chunk i+1's H2D, chunk i's kernels and chunk i-1's
 // D2H run concurrently (two copy engines + the SMs).  Results land in the caller's arrays exactly
 // as the one-shot form writes them.
 static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *out) {
@@ -695,7 +697,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
     auto mark = [&](u32 i, int k, cudaStream_t st) { if (trace) { cudaEventRecord(tev[(size_t)i * 4 + k], st); thost[(size_t)i * 4 + k] = now_ms() - t_begin; } };
     auto bounds = [&](u32 i, u32 &r0, u32 &r1) { r0 = std::min<u64>((u64)i * per, n); r1 = std::min<u64>((u64)(i + 1) * per, n); };
     auto finish = [&](u32 i) -> int {
-        Lane &ln = c->lane[i % kLanes];
+        Lane &ln = c->lane[i % c->n_lanes];
         u32 r0, r1;
         bounds(i, r0, r1);
         int r = lane_resolve(c, ln, false);
@@ -723,9 +725,9 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
     u32 issued = 0, finished = 0;
     for (; issued < n_chunks && rc == SMX_OK; ++issued) {
         // a lane is reused only after its previous chunk has been finished (stream order covers the rest)
-        while (rc == SMX_OK && issued - finished >= (u32)kLanes) rc = finish(finished++);
+        while (rc == SMX_OK && issued - finished >= (u32)c->n_lanes) rc = finish(finished++);
         if (rc) break;
-        Lane &ln = c->lane[issued % kLanes];
+        Lane &ln = c->lane[issued % c->n_lanes];
         u32 r0, r1;
         bounds(issued, r0, r1);
         if (r0 >= r1) { ln.have_batch = false; continue; }
@@ -734,8 +736,8 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         mark(issued, 1, ln.stream);
         if ((rc = lane_enqueue(c, ln, 0, false))) break;
         mark(issued, 2, ln.stream);
-        // keep at most kLanes - 1 chunks ahead so the finished chunk's D2H starts while the next computes
-        while (rc == SMX_OK && issued + 1 - finished >= (u32)kLanes) rc = finish(finished++);
+        // keep at most n_lanes - 1 chunks ahead so the finished chunk's D2H starts while the next computes
+        while (rc == SMX_OK && issued + 1 - finished >= (u32)c->n_lanes) rc = finish(finished++);
     }
     while (rc == SMX_OK && finished < issued) rc = finish(finished++);
     for (auto &ln : c->lane) if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamSynchronize(ln.out_stream); ln.drain_pending = false; }

@@ -217,8 +217,8 @@ struct Batch {
     u32 read_base;           // index of this (sub-)batch's read 0 in the caller's batch (smx_record.read)
     u32 *win;                // staged 4-bit windows [(strand*wpw + w) * n_pad + read]
     u32 *win2;               // staged 2-bit windows [(strand*nw2 + w2) * n_pad + read], 16 symbols/word (unflagged reads)
-    u32 *tmix;               // sliced primer search output [(slot*nw2 + blk) * n_pad + read]: bit 2c = equal-best so far,
-                             // bit 2c+1 = improvement, for column 16*blk + c
+    u32 *tmix;               // sliced primer search output [(slot*nw2 + blk) * n_pad + read]: bit c = equal-best so far,
+                             // bit 16+c = improvement, for column 16*blk + c
     // level-1 results
     smx_primer_hit *phit;    // [slot * n_pad + read], slot = strand*n_primers + primer
     u32 *endmask;            // [(slot*mw + w) * n_pad + read]

@@ -309,8 +309,9 @@ constexpr int kSlicedCodes = 15;        // scratch planes per thread: one per IU
 
 template <int M> struct SlicedBits { static constexpr int NB = M < 2 ? 1 : M < 4 ? 2 : M < 8 ? 3 : M < 16 ? 4 : M < 32 ? 5 : 6; };
 
-// sp: this thread's kSlicedCodes code planes, sa: its 32-word plane buffer (both with element
-// stride STRIDE: shared memory columns on the GPU).  The column loop and the two transposes are
+// sp: this thread's kSlicedCodes code planes, sa: its 32-word plane buffer followed by 16 more
+// planes for the "improved" results (all with element stride STRIDE: shared memory columns on the
+// GPU).  The column loop and the two transposes are
 // kept ROLLED: the generation that unrolled 16 columns was instruction-fetch bound (ncu:
 // stall_no_instruction the top stall at 40 % issue utilisation).
 template <int M, int STRIDE>
@@ -406,16 +407,19 @@ SMX_HD void primer_sliced_thread(const Tables &t, const Batch &b, u32 group, int
                     any |= sum;
                 }
                 zero = ~any;
-                sa[(2 * c) * STRIDE] = zero;
-                sa[(2 * c + 1) * STRIDE] = imp;
+                // results: "equal" plane of column c over the (already consumed) input plane c,
+                // "improved" plane into the 16 extra planes -- so that after the second transpose a
+                // read's word is (improved bits << 16) | equal bits with no bit shuffling left to do
+                sa[c * STRIDE] = zero;
+                sa[(32 + c) * STRIDE] = imp;
             }
-            for (int c = ncols; c < 16; ++c) { sa[(2 * c) * STRIDE] = 0u; sa[(2 * c + 1) * STRIDE] = 0u; }
+            for (int c = ncols; c < 16; ++c) { sa[c * STRIDE] = 0u; sa[(32 + c) * STRIDE] = 0u; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int r = 0; r < 32; ++r) a[r] = sa[r * STRIDE];
+            for (int r = 0; r < 16; ++r) { a[r] = sa[r * STRIDE]; a[16 + r] = sa[(32 + r) * STRIDE]; }
         }
-        // a[r]: read r's interleaved (equal, improved) bits of the block's 16 columns
+        // a[r]: read r's word of the block's 16 columns: bit c = equal-best so far, bit 16 + c = improvement
         u32 *dst = b.tmix + ((u64)slot * t.nw2 + blk) * b.n_pad + (u64)group * 32;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -424,15 +428,6 @@ SMX_HD void primer_sliced_thread(const Tables &t, const Batch &b, u32 group, int
         for (int r = 0; r < 32; ++r) dst[r] = a[r];
 #endif
     }
-}
-
-SMX_HD u32 compress_even_bits(u32 x) {                 // bits 0,2,4,.. -> bits 0..15
-    x &= 0x55555555u;
-    x = (x | (x >> 1)) & 0x33333333u;
-    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-    x = (x | (x >> 4)) & 0x00FF00FFu;
-    x = (x | (x >> 8)) & 0x0000FFFFu;
-    return x;
 }
 
 SMX_HD bool sliced_eligible(const Tables &t, const Batch &b, u32 read) {
@@ -453,7 +448,7 @@ SMX_HD int primer_finish_thread(const Tables &t, const Batch &b, u32 read, int s
     // pass 1: number of improvements (-> best) and the column of the last one (-> first equal-best end)
     int improvements = 0, first = 0;
     for (int blk = 0; blk < t.nw2; ++blk) {
-        const u32 im = compress_even_bits(mix[(u64)blk * b.n_pad] >> 1);
+        const u32 im = mix[(u64)blk * b.n_pad] >> 16;
         improvements += popcount32(im);
         if (im) first = blk * 16 + 31 - count_leading_zeros32(im);
     }
@@ -465,8 +460,8 @@ SMX_HD int primer_finish_thread(const Tables &t, const Batch &b, u32 read, int s
     if (best <= t.p_k[primer]) {
         // pass 2: equality bits from the last improvement on are the equal-best ends
         for (int mwi = 0; mwi < t.mw; ++mwi) {
-            u32 v = compress_even_bits(mix[(u64)(2 * mwi) * b.n_pad]);
-            if (2 * mwi + 1 < t.nw2) v |= compress_even_bits(mix[(u64)(2 * mwi + 1) * b.n_pad]) << 16;
+            u32 v = mix[(u64)(2 * mwi) * b.n_pad] & 0xFFFFu;
+            if (2 * mwi + 1 < t.nw2) v |= mix[(u64)(2 * mwi + 1) * b.n_pad] << 16;
             const int lo = mwi * 32;
             if (lo + 32 <= first) v = 0;
             else if (lo < first) v &= ~0u << (first - lo);
@@ -836,7 +831,7 @@ __global__ void __launch_bounds__(128) k_stage_windows(SMX_KARGS) {
 constexpr int kSlicedBlock = 64;        // small blocks: equal-length tasks, let the block scheduler balance the SMs
 template <int M>
 __global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
-    __shared__ u32 s_planes[(kSlicedCodes + 32) * kSlicedBlock];
+    __shared__ u32 s_planes[(kSlicedCodes + 48) * kSlicedBlock];
     const u32 group = blockIdx.x * kSlicedBlock + threadIdx.x;
     if (group >= b.n_pad / 32) return;
     primer_sliced_thread<M, kSlicedBlock>(c_tables, b, group, (int)blockIdx.y, primer, ro, degenerate != 0,
@@ -845,18 +840,20 @@ __global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int p
 
 constexpr int kFinishBlock = 256;
 
-// Block-wide sum of a 64-bit value into one atomicAdd (same-address atomics from every warp were
-// the top stall of this kernel: ncu source view, 35 % of samples on the atomic's return).
-__device__ __forceinline__ void block_counter_add(unsigned long long v, unsigned long long *dst, unsigned long long *s_tmp /*32*/) {
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+// Work counters.  Every thread of a block contributes a small 32-bit count `v` (DP columns, or
+// barcode lanes x columns); the block adds v_total * mul0 and v_total * mul1 to two 64-bit device
+// counters.  One REDUX per warp, one shared atomic per warp, two global atomics per block (the
+// first form -- a shuffle tree per counter and two barriers each -- was 9 % of the barcode
+// kernel's instructions and 14 % of its stall samples: profiles/r1_v14_ncu_full.md).
+__device__ __forceinline__ void block_work_add(u32 v, unsigned long long mul0, unsigned long long *dst0,
+                                               unsigned long long mul1, unsigned long long *dst1, u32 *s_acc /*1, zeroed*/) {
+    const u32 wsum = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(s_acc, wsum);
     __syncthreads();
-    if (threadIdx.x < 32) {
-        v = threadIdx.x < (blockDim.x >> 5) ? s_tmp[threadIdx.x] : 0ull;
-        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0 && v) atomicAdd(dst, v);
+    if (threadIdx.x == 0) {
+        const unsigned long long tot = *s_acc;
+        if (tot) { atomicAdd(dst0, tot * mul0); atomicAdd(dst1, tot * mul1); }
     }
-    __syncthreads();
 }
 
 template <typename W>
@@ -864,21 +861,22 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
     // grid: x over reads, y = strand * n_primers + primer
     __shared__ u64 s_peq[3][16];
     __shared__ u32 s_wtot[kFinishBlock / 32 + 1];
-    __shared__ unsigned long long s_tmp[32];
+    __shared__ u32 s_acc;
     const int primer = blockIdx.y % c_tables.n_primers, strand = blockIdx.y / c_tables.n_primers;
     if (c_tables.p_sw[primer]) return;                  // long primer: k_primer_long owns this slot
+    if (threadIdx.x == 64) s_acc = 0;
     if (threadIdx.x < 48) {
         const u64 *src = threadIdx.x < 16 ? c_tables.peq_rc : threadIdx.x < 32 ? c_tables.peq_rcrev : c_tables.peq_fw;
         s_peq[threadIdx.x >> 4][threadIdx.x & 15] = src[primer * 16 + (threadIdx.x & 15)];
     }
     __syncthreads();
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long cells = 0;
+    u32 cells = 0;
     int nloc = 0;
     if (read < b.n_reads) {
         nloc = primer_finish_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2]);
         int n = (int)b.lengths[read];
-        cells = (unsigned long long)(n < c_tables.L ? n : c_tables.L);       // HW columns of this search
+        cells = (u32)(n < c_tables.L ? n : c_tables.L);                      // HW columns of this search
     }
     // work entries, one per equal-best end location: block-aggregated allocation (one atomic per
     // block), a read's entries stay consecutive (the order of reads inside the list is irrelevant)
@@ -901,8 +899,7 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
         if (nloc) write_entries(c_tables, b, blockIdx.y, read, s_wtot[kFinishBlock / 32] + s_wtot[warp] + (u32)(incl - nloc));
     }
     const int m = c_tables.p_len[primer];
-    block_counter_add(cells * (unsigned long long)m, &b.counters[0], s_tmp);
-    block_counter_add(cells * (unsigned long long)((m + 31) >> 5), &b.counters[2], s_tmp);
+    block_work_add(cells, (unsigned long long)m, &b.counters[0], (unsigned long long)((m + 31) >> 5), &b.counters[2], &s_acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1072,6 +1069,8 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(SMX_KARGS) {
     if (cnt > b.e_cap) cnt = b.e_cap;
     if (blockIdx.x * blockDim.x >= cnt) return;
     const int m = t.bw_len[g];
+    __shared__ u32 s_acc;
+    if (threadIdx.x == 0) s_acc = 0;
     for (int i = threadIdx.x; i < m * 16; i += blockDim.x) s_beq[i] = t.beq[(u64)t.bw_row[g] * 16 + i];
     __syncthreads();
     const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1081,9 +1080,10 @@ __global__ void __launch_bounds__(128) k_barcode_bitsliced(SMX_KARGS) {
         const int p = b.ent_pos[(u64)slot * b.e_cap + idx];
         barcode_bitsliced_thread<K>(t, b, read, p, idx, strand, primer, g, s_beq, cells, wcols);
     }
-    __shared__ unsigned long long s_tmp[32];
-    block_counter_add(cells, &b.counters[1], s_tmp);
-    block_counter_add(wcols, &b.counters[3], s_tmp);
+    // m is uniform over the block: cells = m * S, word-columns = ceil(m/32) * S with S = sum of lanes x columns
+    const unsigned long long wmul = (unsigned long long)((m + 31) >> 5);
+    (void)cells;
+    block_work_add((u32)(wcols / wmul), (unsigned long long)m, &b.counters[1], wmul, &b.counters[3], &s_acc);
 }
 
 constexpr int kInlineRecords = 4;

@@ -173,7 +173,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                 degenerate |= code > 3;
                 ro.off[i] = (unsigned short)(code * sizeof(u32));
             }
-            u32 scratch[kSlicedCodes], planes[32];
+            u32 scratch[kSlicedCodes], planes[48];
             for (int s = 0; s < 2; ++s)
                 for (u32 g = 0; g < n_pad / 32; ++g)
                     switch (t.p_len[p]) {
