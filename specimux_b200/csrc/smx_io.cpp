@@ -8,9 +8,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -395,17 +399,50 @@ bool make_dirs(const std::string &dir) {          // os.makedirs(exist_ok=True)
 
 }  // namespace
 
+// One formatted-record destination.  A file is owned by exactly one worker thread (fixed at
+// creation), so its buffer and its appends need no lock and keep arrival order.
+struct Target {
+    OutFile file;
+    int owner = 0;
+};
+
+// What the planning pass resolves for a record: names, slice bounds, destinations.
+struct Plan {
+    const std::string *sample, *pool, *p1, *p2;
+    size_t a, b;                 // slice [a, b) of the oriented read
+    Target *primary, *pool_level;
+};
+
+struct Task { uint32_t rec; Target *dst; };
+
 struct smx_writer {
     bool to_files = true, fastq = true;
     std::string dir, prefix, ext;
     std::vector<std::string> specimen_id, specimen_file, b1_id, b1_file, b2_id, b2_file, pool, primer;
-    std::unordered_map<uint64_t, OutFile> files;      // keyed by packed (level, top, pool, p1, p2, sample kind, sample)
+    std::unordered_map<uint64_t, Target *> files;     // keyed by packed (level, top, pool, p1, p2, sample kind, sample)
+    std::vector<Target *> all_files;
     Bytes console;
     uint64_t n_records = 0, n_bytes = 0;
+    std::mutex err_mu;
     int first_error = SMX_IO_OK;
     std::string first_error_msg;
 
+    // worker pool (file output only): thread t formats the tasks of the files it owns
+    int n_threads = 1;
+    std::vector<std::thread> threads;
+    std::vector<std::vector<Task>> tasks;             // per thread, in record order
+    std::vector<uint64_t> thread_bytes;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    const smx_block *cur_blk = nullptr;
+    const smx_record *cur_recs = nullptr;
+    const std::vector<Plan> *cur_plans = nullptr;
+
     void note_error(int code, const std::string &msg) {
+        std::lock_guard<std::mutex> g(err_mu);
         if (first_error == SMX_IO_OK) { first_error = code; first_error_msg = msg; }
     }
 
@@ -436,6 +473,21 @@ struct smx_writer {
         f.buf.clear();
     }
 
+    Target *target(uint64_t key, const std::string &path) {
+        auto it = files.find(key);
+        if (it != files.end()) return it->second;
+        Target *t = new Target();
+        t->file.path = path;
+        t->owner = (int)(all_files.size() % (size_t)n_threads);
+        all_files.push_back(t);
+        files.emplace(key, t);
+        return t;
+    }
+
+    void format(Bytes &c, const smx_block &blk, const smx_record &rec, const Plan &pl);
+    void run_tasks(int t);
+    void worker(int t);
+    ~smx_writer() { for (Target *t : all_files) delete t; }
 };
 
 namespace {
@@ -459,7 +511,86 @@ inline void put_int(Bytes &v, int x) {
     put(v, tmp, (size_t)n);
 }
 
+const std::string kUnknown = "unknown";
+
 }  // namespace
+
+// One record, formatted in place at the end of `c` (create_write_operation's string work,
+// demultiplex.py:30-103, and the header of OutputManager.write_sequence, io_utils.py:245-256).
+void smx_writer::format(Bytes &c, const smx_block &blk, const smx_record &rec, const Plan &pl) {
+    const uint32_t r = rec.read;
+    const char *seq = blk.bases.data() + blk.seq_off[r];
+    const long long len = (long long)(blk.seq_off[r + 1] - blk.seq_off[r]);
+    const char *qual = blk.has_qual ? blk.quals.data() + blk.seq_off[r] : nullptr;
+    const char *id = blk.titles.data() + blk.title_off[r] + blk.id_start[r];
+    const size_t id_len = blk.id_len[r], a = pl.a, n_out = pl.b - pl.a;
+    put(c, fastq ? '@' : '>');
+    put(c, id, id_len);
+    put(c, ' ');
+    for (int d = 0; d < 4; ++d) {                    // distance_code (models.py:206-218)
+        if (d) put(c, ',');
+        if (rec.dist[d] >= 0) put_int(c, rec.dist[d]); else put(c, 'X');
+    }
+    if (to_files) {
+        put(c, " pool=", 6); put(c, *pl.pool);
+        put(c, " primers=", 9); put(c, *pl.p1); put(c, '+'); put(c, *pl.p2);
+    }
+    put(c, ' '); put(c, *pl.sample); put(c, '\n');
+    char *dst = c.grow(2 * n_out + 4);
+    if (rec.reverse) {
+        // oriented read = reverse complement; its slice [a, b) = original (len-b .. len-a] reversed
+        const unsigned char *src = (const unsigned char *)seq + (len - (long long)a) - 1;
+        const unsigned char *tab = kComplement.t;
+        for (size_t j = 0; j < n_out; ++j) dst[j] = (char)tab[src[-(long long)j]];
+    } else if (n_out) {
+        memcpy(dst, seq + a, n_out);
+    }
+    dst += n_out;
+    *dst++ = '\n';
+    if (fastq) {
+        *dst++ = '+'; *dst++ = '\n';
+        if (!qual) memset(dst, 'I', n_out);          // get_quality_seq: [40] * len (alignment.py:52-56)
+        else if (rec.reverse) {
+            const char *src = qual + (len - (long long)a) - 1;
+            for (size_t j = 0; j < n_out; ++j) dst[j] = src[-(long long)j];
+        } else if (n_out) memcpy(dst, qual + a, n_out);
+        dst += n_out;
+        *dst++ = '\n';
+    }
+    c.n = (size_t)(dst - c.p);
+}
+
+void smx_writer::run_tasks(int t) {
+    uint64_t bytes = 0;
+    for (const Task &k : tasks[t]) {
+        Bytes &buf = k.dst->file.buf;
+        const size_t before = buf.size();
+        const Plan &pl = (*cur_plans)[k.rec];
+        format(buf, *cur_blk, cur_recs[k.rec], pl);
+        if (k.dst == pl.primary) bytes += buf.size() - before;      // payload counted once per record
+        if (buf.size() >= flush_bytes()) flush(k.dst->file);
+    }
+    thread_bytes[t] = bytes;
+}
+
+void smx_writer::worker(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+        }
+        try {
+            run_tasks(t);
+        } catch (const std::exception &e) {
+            note_error(SMX_IO_ERR_IO, std::string("writer thread: ") + e.what());
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        if (--pending == 0) cv_done.notify_one();
+    }
+}
 
 extern "C" {
 
@@ -484,130 +615,107 @@ int smx_writer_open(const char *output_dir, const char *prefix, int is_fastq, co
         delete w;
         return rc;
     }
+    if (w->to_files) {
+        // formatting + appending is spread over worker threads by destination file
+        const char *e = getenv("SMX_IO_THREADS");
+        int n = e ? atoi(e) : 0;
+        if (n <= 0) {
+            unsigned hw = std::thread::hardware_concurrency();
+            n = (int)std::min<unsigned>(8u, std::max<unsigned>(1u, hw / 2));
+        }
+        w->n_threads = std::min(n, 64);
+    }
+    w->tasks.resize((size_t)w->n_threads);
+    w->thread_bytes.assign((size_t)w->n_threads, 0);
+    if (w->n_threads > 1)
+        for (int t = 0; t < w->n_threads; ++t) w->threads.emplace_back(&smx_writer::worker, w, t);
     *out = w;
     return SMX_IO_OK;
 }
 
 int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs, uint64_t n_records) {
     if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write: null argument");
-    static const std::string kUnknown = "unknown";
+    if (n_records > 0xFFFFFFFFull) return fail(SMX_IO_ERR_ARG, "smx_writer_write: too many records in one call");
     const uint32_t n_reads = blk->n();
+    std::vector<Plan> plans((size_t)n_records);
+    for (auto &t : w->tasks) t.clear();
+    // ---- planning pass (this thread): names, slice bounds, destination files
     for (uint64_t i = 0; i < n_records; ++i) {
         const smx_record &rec = recs[i];
         if (rec.read >= n_reads) return fail(SMX_IO_ERR_ARG, "record %llu names read %u of a %u-read block", (unsigned long long)i, rec.read, n_reads);
-        const uint32_t r = rec.read;
-        const char *seq = blk->bases.data() + blk->seq_off[r];
-        const long long len = (long long)(blk->seq_off[r + 1] - blk->seq_off[r]);
-        const char *qual = blk->has_qual ? blk->quals.data() + blk->seq_off[r] : nullptr;
-        const char *id = blk->titles.data() + blk->title_off[r] + blk->id_start[r];
-        const size_t id_len = blk->id_len[r];
-
+        const long long len = (long long)(blk->seq_off[rec.read + 1] - blk->seq_off[rec.read]);
+        Plan &pl = plans[i];
         // names (demultiplex.py:47-73 empty-trim fallback; :541-598 sample ids)
-        const std::string *sample = &kUnknown, *sample_file = &kUnknown, *pool = &kUnknown, *p1 = &kUnknown, *p2 = &kUnknown;
+        const std::string *sample_file = &kUnknown;
+        pl.sample = pl.pool = pl.p1 = pl.p2 = &kUnknown;
+        pl.primary = pl.pool_level = nullptr;
         int kind = 3;                                   // 0 specimen, 1 b1, 2 b2, 3 unknown
         uint32_t sidx = 0;
-        size_t a = 0, b = (size_t)len;
+        pl.a = 0; pl.b = (size_t)len;
         if (!rec.trim_empty) {
-            py_slice(rec.trim_start, rec.trim_end, len, a, b);
+            py_slice(rec.trim_start, rec.trim_end, len, pl.a, pl.b);
             const uint8_t res = rec.resolution;
             if (res == SMX_RES_FULL_MATCH || res == SMX_RES_DEREPLICATED_FULL || res == SMX_RES_MULTIPLE_SPECIMENS) {
                 if (rec.sample < 0 || (uint32_t)rec.sample >= w->specimen_id.size()) return fail(SMX_IO_ERR_ARG, "record %llu: specimen %d out of range", (unsigned long long)i, rec.sample);
-                kind = 0; sidx = (uint32_t)rec.sample; sample = &w->specimen_id[sidx]; sample_file = &w->specimen_file[sidx];
+                kind = 0; sidx = (uint32_t)rec.sample; pl.sample = &w->specimen_id[sidx]; sample_file = &w->specimen_file[sidx];
             } else if (res == SMX_RES_PARTIAL_FORWARD) {
                 if (rec.sample < 0 || (uint32_t)rec.sample >= w->b1_id.size()) return fail(SMX_IO_ERR_ARG, "record %llu: b1 %d out of range", (unsigned long long)i, rec.sample);
-                kind = 1; sidx = (uint32_t)rec.sample; sample = &w->b1_id[sidx]; sample_file = &w->b1_file[sidx];
+                kind = 1; sidx = (uint32_t)rec.sample; pl.sample = &w->b1_id[sidx]; sample_file = &w->b1_file[sidx];
             } else if (res == SMX_RES_PARTIAL_REVERSE) {
                 if (rec.sample < 0 || (uint32_t)rec.sample >= w->b2_id.size()) return fail(SMX_IO_ERR_ARG, "record %llu: b2 %d out of range", (unsigned long long)i, rec.sample);
-                kind = 2; sidx = (uint32_t)rec.sample; sample = &w->b2_id[sidx]; sample_file = &w->b2_file[sidx];
+                kind = 2; sidx = (uint32_t)rec.sample; pl.sample = &w->b2_id[sidx]; sample_file = &w->b2_file[sidx];
             }
-            if (rec.pool >= 0) { if ((size_t)rec.pool >= w->pool.size()) return fail(SMX_IO_ERR_ARG, "record %llu: pool out of range", (unsigned long long)i); pool = &w->pool[rec.pool]; }
-            if (rec.p1 >= 0) { if ((size_t)rec.p1 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p1 out of range", (unsigned long long)i); p1 = &w->primer[rec.p1]; }
-            if (rec.p2 >= 0) { if ((size_t)rec.p2 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p2 out of range", (unsigned long long)i); p2 = &w->primer[rec.p2]; }
+            if (rec.pool >= 0) { if ((size_t)rec.pool >= w->pool.size()) return fail(SMX_IO_ERR_ARG, "record %llu: pool out of range", (unsigned long long)i); pl.pool = &w->pool[rec.pool]; }
+            if (rec.p1 >= 0) { if ((size_t)rec.p1 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p1 out of range", (unsigned long long)i); pl.p1 = &w->primer[rec.p1]; }
+            if (rec.p2 >= 0) { if ((size_t)rec.p2 >= w->primer.size()) return fail(SMX_IO_ERR_ARG, "record %llu: p2 out of range", (unsigned long long)i); pl.p2 = &w->primer[rec.p2]; }
         }
-
-        // destination: OutputManager._make_filename (io_utils.py:206-220), or the console buffer
-        OutFile *primary = nullptr, *pool_level = nullptr;
-        if (w->to_files) {
-            const uint8_t res = rec.trim_empty ? (uint8_t)SMX_RES_UNKNOWN : rec.resolution;
-            const int top = res == SMX_RES_UNKNOWN ? 2 : (res == SMX_RES_PARTIAL_FORWARD || res == SMX_RES_PARTIAL_REVERSE) ? 1 : 0;
-            const uint64_t pool_i = (uint64_t)(pool == &kUnknown ? 0 : rec.pool + 1);
-            const uint64_t p1_i = (uint64_t)(p1 == &kUnknown ? 0 : rec.p1 + 1), p2_i = (uint64_t)(p2 == &kUnknown ? 0 : rec.p2 + 1);
-            const uint64_t skey = ((uint64_t)kind << 30) | sidx;
-            const uint64_t key = ((uint64_t)top << 62) | (pool_i << 52) | (p1_i << 44) | (p2_i << 36) | skey;
-            static const char *kTop[3] = {"full", "partial", "unknown"};
-            auto it = w->files.find(key);
-            if (it == w->files.end()) {
-                it = w->files.emplace(key, OutFile()).first;
-                it->second.path = w->dir + "/" + kTop[top] + "/" + *pool + "/" + *p1 + "-" + *p2 + "/" + w->prefix + *sample_file + w->ext;
+        if (!w->to_files) continue;
+        // destination: OutputManager._make_filename (io_utils.py:206-220)
+        const uint8_t res = rec.trim_empty ? (uint8_t)SMX_RES_UNKNOWN : rec.resolution;
+        const int top = res == SMX_RES_UNKNOWN ? 2 : (res == SMX_RES_PARTIAL_FORWARD || res == SMX_RES_PARTIAL_REVERSE) ? 1 : 0;
+        const uint64_t pool_i = (uint64_t)(pl.pool == &kUnknown ? 0 : rec.pool + 1);
+        const uint64_t p1_i = (uint64_t)(pl.p1 == &kUnknown ? 0 : rec.p1 + 1), p2_i = (uint64_t)(pl.p2 == &kUnknown ? 0 : rec.p2 + 1);
+        const uint64_t skey = ((uint64_t)kind << 30) | sidx;
+        const uint64_t key = ((uint64_t)top << 62) | (pool_i << 52) | (p1_i << 44) | (p2_i << 36) | skey;
+        static const char *kTop[3] = {"full", "partial", "unknown"};
+        auto it = w->files.find(key);
+        pl.primary = it != w->files.end() ? it->second
+                   : w->target(key, w->dir + "/" + kTop[top] + "/" + *pl.pool + "/" + *pl.p1 + "-" + *pl.p2 + "/" + w->prefix + *sample_file + w->ext);
+        w->tasks[(size_t)pl.primary->owner].push_back(Task{(uint32_t)i, pl.primary});
+        if (!rec.trim_empty && (rec.resolution == SMX_RES_FULL_MATCH || rec.resolution == SMX_RES_DEREPLICATED_FULL)) {
+            // pool-level duplicate of full matches (io_utils.py:259-268)
+            const uint64_t pkey = (3ull << 62) | (pool_i << 52) | skey;
+            auto pit = w->files.find(pkey);
+            pl.pool_level = pit != w->files.end() ? pit->second
+                          : w->target(pkey, w->dir + "/full/" + *pl.pool + "/" + w->prefix + *sample_file + w->ext);
+            w->tasks[(size_t)pl.pool_level->owner].push_back(Task{(uint32_t)i, pl.pool_level});
+        }
+    }
+    w->n_records += n_records;
+    // ---- formatting
+    if (!w->to_files) {
+        for (uint64_t i = 0; i < n_records; ++i) {
+            const size_t before = w->console.size();
+            w->format(w->console, *blk, recs[i], plans[i]);
+            w->n_bytes += w->console.size() - before;
+            if (w->console.size() >= flush_bytes()) { fwrite(w->console.data(), 1, w->console.size(), stdout); w->console.clear(); }
+        }
+    } else {
+        w->cur_blk = blk; w->cur_recs = recs; w->cur_plans = &plans;
+        if (w->n_threads > 1) {
+            {
+                std::lock_guard<std::mutex> lk(w->mu);
+                w->pending = w->n_threads;
+                ++w->generation;
             }
-            primary = &it->second;
-            if (!rec.trim_empty && (rec.resolution == SMX_RES_FULL_MATCH || rec.resolution == SMX_RES_DEREPLICATED_FULL)) {
-                // pool-level duplicate of full matches (io_utils.py:259-268)
-                const uint64_t pkey = (3ull << 62) | (pool_i << 52) | skey;
-                auto pit = w->files.find(pkey);
-                if (pit == w->files.end()) {
-                    pit = w->files.emplace(pkey, OutFile()).first;
-                    pit->second.path = w->dir + "/full/" + *pool + "/" + w->prefix + *sample_file + w->ext;
-                    primary = &w->files.find(key)->second;      // emplace may have rehashed
-                }
-                pool_level = &pit->second;
-            }
+            w->cv_go.notify_all();
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv_done.wait(lk, [&] { return w->pending == 0; });
+        } else {
+            try { w->run_tasks(0); } catch (const std::exception &e) { w->note_error(SMX_IO_ERR_IO, e.what()); }
         }
-        Bytes &c = primary ? primary->buf : w->console;
-        const size_t rec_begin = c.size();
-
-        // content, formatted in place
-        const size_t n_out = b - a;
-        put(c, w->fastq ? '@' : '>');
-        put(c, id, id_len);
-        put(c, ' ');
-        for (int d = 0; d < 4; ++d) {                    // distance_code (models.py:206-218)
-            if (d) put(c, ',');
-            if (rec.dist[d] >= 0) put_int(c, rec.dist[d]); else put(c, 'X');
-        }
-        if (w->to_files) {
-            put(c, " pool=", 6); put(c, *pool);
-            put(c, " primers=", 9); put(c, *p1); put(c, '+'); put(c, *p2);
-        }
-        put(c, ' '); put(c, *sample); put(c, '\n');
-        {
-            char *dst = c.grow(2 * n_out + 4);
-            if (rec.reverse) {
-                // oriented read = reverse complement; its slice [a, b) = original (len-b .. len-a] reversed
-                const unsigned char *src = (const unsigned char *)seq + (len - (long long)a) - 1;
-                const unsigned char *tab = kComplement.t;
-                for (size_t j = 0; j < n_out; ++j) dst[j] = (char)tab[src[-(long long)j]];
-            } else if (n_out) {
-                memcpy(dst, seq + a, n_out);
-            }
-            dst += n_out;
-            *dst++ = '\n';
-            if (w->fastq) {
-                *dst++ = '+'; *dst++ = '\n';
-                if (!qual) memset(dst, 'I', n_out);
-                else if (rec.reverse) {
-                    const char *src = qual + (len - (long long)a) - 1;
-                    for (size_t j = 0; j < n_out; ++j) dst[j] = src[-(long long)j];
-                } else if (n_out) memcpy(dst, qual + a, n_out);
-                dst += n_out;
-                *dst++ = '\n';
-            }
-            c.n = (size_t)(dst - c.p);
-        }
-        const size_t rec_bytes = c.size() - rec_begin;
-        ++w->n_records;
-        w->n_bytes += rec_bytes;
-        if (pool_level) {
-            memcpy(pool_level->buf.grow(rec_bytes), c.p + rec_begin, rec_bytes);
-            pool_level->buf.n += rec_bytes;
-            if (pool_level->buf.size() >= flush_bytes()) w->flush(*pool_level);
-        }
-        if (primary) {
-            if (c.size() >= flush_bytes()) w->flush(*primary);
-        } else if (c.size() >= flush_bytes()) {
-            fwrite(c.data(), 1, c.size(), stdout);
-            c.clear();
-        }
+        for (uint64_t v : w->thread_bytes) w->n_bytes += v;
+        w->cur_blk = nullptr; w->cur_recs = nullptr; w->cur_plans = nullptr;
     }
     if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());
     return SMX_IO_OK;
@@ -615,7 +723,12 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
 
 int smx_writer_close(smx_writer *w) {
     if (!w) return SMX_IO_OK;
-    for (auto &kv : w->files) w->flush(kv.second);
+    if (!w->threads.empty()) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->stop = true; }
+        w->cv_go.notify_all();
+        for (auto &t : w->threads) t.join();
+    }
+    for (Target *t : w->all_files) w->flush(t->file);
     if (!w->console.empty()) fwrite(w->console.data(), 1, w->console.size(), stdout);
     if (!w->to_files) fflush(stdout);
     int rc = w->first_error;
