@@ -234,6 +234,13 @@ int smx_upload_batch(smx_ctx *ctx, const smx_batch *batch);   /* H2D only       
 int smx_run_resident(smx_ctx *ctx);                           /* kernels only, on the last upload  */
 int smx_download_results(smx_ctx *ctx, smx_results *out);     /* D2H only                         */
 
+/* The resident form cuts batches of >= 131072 reads into `n_sub_batches` (default 3, env
+ * SMX_RESIDENT_SPLIT, 1..8) pieces that run concurrently on separate streams: one piece's
+ * latency-bound tail (general selection, scan, compaction) overlaps another's ALU-bound search
+ * kernels.  Results are identical.  With more than one piece the per-stage / per-kernel times below
+ * read 0 (the kernels overlap); set 1 to measure them.  Takes effect at the next smx_upload_batch. */
+int smx_set_resident_split(smx_ctx *ctx, uint32_t n_sub_batches);
+
 /* CUDA-event time (ms) of the last smx_run_resident, and of its stages:
  * stage 0 staging, 1 primer search, 2 barcode search, 3 selection. */
 int smx_last_timing(const smx_ctx *ctx, float *total_ms, float stage_ms[4]);

@@ -61,7 +61,7 @@ EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create"
            "smx_result_bound", "smx_match_batch", "smx_upload_batch", "smx_run_resident",
            "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
            "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads", "smx_int_alu_peak", "smx_host_alloc",
-           "smx_host_free", "smx_flush_l2", "smx_set_pipeline_chunk", "smx_last_chunk_count", "smx_last_deferred", "smx_last_kernel_times"]
+           "smx_host_free", "smx_flush_l2", "smx_set_pipeline_chunk", "smx_last_chunk_count", "smx_last_deferred", "smx_last_kernel_times", "smx_set_resident_split"]
 
 
 class SmxError(RuntimeError):
@@ -110,6 +110,7 @@ def load():
         lib.smx_last_deferred.argtypes = [C.c_void_p]
         lib.smx_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         lib.smx_last_deferred.restype = C.c_uint64
+        lib.smx_set_resident_split.argtypes = [C.c_void_p, C.c_uint32]
         if lib.smx_abi_version() != 1:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib

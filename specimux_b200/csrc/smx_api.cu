@@ -138,6 +138,12 @@ struct smx_ctx {
     std::vector<unsigned char> prow_code;   // [primer][32] pattern row codes (sliced primer search)
     Lane lane[kMaxLanes];
     int n_lanes = 3;
+    // resident (upload / run / download) form: a large batch is cut into `resident_split` sub-batches
+    // that run concurrently on separate lanes, so one sub-batch's latency-bound tail (general
+    // selection, scan, compaction) overlaps another's ALU-bound search kernels
+    int resident_split = 3, resident_lanes = 1;
+    u32 resident_n = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane_done[kMaxLanes] = {};
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
     DevBuf<unsigned char> l2_scratch;
     u32 chunk_reads = 128 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK)
@@ -483,6 +489,9 @@ void smx_destroy(smx_ctx *c) {
     cudaSetDevice(c->device);
     for (auto &ln : c->lane) if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamSynchronize(ln.out_stream); }
     for (auto &ln : c->lane) ln.release();
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    for (auto &e : c->ev_lane_done) if (e) cudaEventDestroy(e);
     c->peq_rc.release(); c->peq_rcrev.release(); c->peq_fw.release(); c->bw_len.release(); c->bw_primer.release(); c->bw_row.release();
     c->bw_valid.release(); c->beq.release(); c->bw_list.release();
     c->spec_key.release(); c->spec_p1.release(); c->spec_p2.release(); c->b_len.release();
@@ -547,6 +556,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         else if (v == 0) c->chunk_reads = 0;                   // 0 disables the pipelined form
     }
     if (const char *env = getenv("SMX_PIPELINE_LANES")) c->n_lanes = std::max(2, std::min(kMaxLanes, atoi(env)));
+    if (const char *env = getenv("SMX_RESIDENT_SPLIT")) c->resident_split = std::max(1, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
@@ -571,33 +581,102 @@ static int check_batch(const smx_ctx *c, const smx_batch *in, const char *who) {
     return SMX_OK;
 }
 
+constexpr u32 kResidentSplitMin = 1u << 17;     // batches below this many reads stay on one lane
+
+static void resident_bounds(const smx_ctx *c, int i, u32 &r0, u32 &r1) {
+    const u32 n = c->resident_n;
+    const u32 per = (((n + (u32)c->resident_lanes - 1) / (u32)c->resident_lanes) + 127u) & ~127u;
+    r0 = (u32)std::min<u64>((u64)i * per, n);
+    r1 = (u32)std::min<u64>((u64)(i + 1) * per, n);
+}
+
 int smx_upload_batch(smx_ctx *c, const smx_batch *in) {
     int rc = check_batch(c, in, "smx_upload_batch");
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    Lane &ln = c->lane[0];
-    rc = lane_upload(c, ln, in, 0, in->n_reads, nullptr);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(ln.stream));
+    c->resident_n = in->n_reads;
+    c->resident_lanes = (c->resident_split > 1 && in->n_reads >= kResidentSplitMin) ? c->resident_split : 1;
+    for (auto &ln : c->lane) { ln.have_batch = false; ln.have_results = false; }
+    if (c->resident_lanes == 1) {
+        Lane &ln = c->lane[0];
+        rc = lane_upload(c, ln, in, 0, in->n_reads, nullptr);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ln.stream));
+        return SMX_OK;
+    }
+    const u32 *shared4 = nullptr;
+    if (in->packed4 && in->off4 && in->packed4_words) {
+        CU(c->shared_packed4.ensure(in->packed4_words));
+        CU(cudaMemcpy(c->shared_packed4.p, in->packed4, in->packed4_words * sizeof(u32), cudaMemcpyHostToDevice));
+        shared4 = c->shared_packed4.p;
+    }
+    for (int i = 0; i < c->resident_lanes; ++i) {
+        u32 r0, r1;
+        resident_bounds(c, i, r0, r1);
+        if (r0 >= r1) { c->resident_lanes = i; break; }
+        if ((rc = lane_upload(c, c->lane[i], in, r0, r1, shared4))) return rc;
+    }
+    for (int i = 0; i < c->resident_lanes; ++i) CU(cudaStreamSynchronize(c->lane[i].stream));
+    return SMX_OK;
+}
+
+int smx_set_resident_split(smx_ctx *c, uint32_t n_sub_batches) {
+    if (!c) return fail(SMX_ERR_ARG, "smx_set_resident_split: null context");
+    if (n_sub_batches < 1 || n_sub_batches > (uint32_t)kMaxLanes)
+        return fail(SMX_ERR_ARG, "smx_set_resident_split: 1..%d sub-batches", kMaxLanes);
+    c->resident_split = (int)n_sub_batches;
     return SMX_OK;
 }
 
 int smx_run_resident(smx_ctx *c) {
     if (!c) return fail(SMX_ERR_ARG, "smx_run_resident: null context");
-    Lane &ln = c->lane[0];
-    if (!ln.have_batch) return fail(SMX_ERR_ARG, "smx_run_resident: no batch uploaded");
+    if (!c->lane[0].have_batch) return fail(SMX_ERR_ARG, "smx_run_resident: no batch uploaded");
     CU(cudaSetDevice(c->device));
-    ln.launches = 0;
-    int rc = lane_enqueue(c, ln, 0, true);
-    if (rc) return rc;
-    if ((rc = lane_resolve(c, ln, true))) return rc;
-    if ((rc = lane_compact(c, ln, 0, true))) return rc;
-    CU(cudaStreamSynchronize(ln.stream));
+    int rc;
+    if (c->resident_lanes == 1) {
+        Lane &ln = c->lane[0];
+        ln.launches = 0;
+        if ((rc = lane_enqueue(c, ln, 0, true))) return rc;
+        if ((rc = lane_resolve(c, ln, true))) return rc;
+        if ((rc = lane_compact(c, ln, 0, true))) return rc;
+        CU(cudaStreamSynchronize(ln.stream));
+        CU(cudaGetLastError());
+        for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&c->stage_ms[i], ln.ev[i], ln.ev[i + 1]));
+        CU(cudaEventElapsedTime(&c->total_ms, ln.ev[0], ln.ev[4]));
+        for (int i = 0; i < 8; ++i) CU(cudaEventElapsedTime(&c->kernel_ms[i], ln.kev[i], ln.kev[i + 1]));
+        CU(cudaEventElapsedTime(&c->kernel_ms[8], ln.kev[9], ln.ev[4]));
+        return SMX_OK;
+    }
+    // concurrent sub-batches: every lane starts after t0 (recorded on lane 0) and lane 0 joins them
+    // all before t1, so t1 - t0 is the device time of the whole batch.  Per-kernel marks are not
+    // taken here (kernels of different lanes overlap); a split of 1 measures them.
+    const int S = c->resident_lanes;
+    if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
+    for (int i = 1; i < S; ++i) if (!c->ev_lane_done[i]) CU(cudaEventCreateWithFlags(&c->ev_lane_done[i], cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_t0, c->lane[0].stream));
+    for (int i = 1; i < S; ++i) CU(cudaStreamWaitEvent(c->lane[i].stream, c->ev_t0, 0));
+    for (int i = 0; i < S; ++i) {
+        c->lane[i].launches = 0;
+        if ((rc = lane_enqueue(c, c->lane[i], 0, false))) return rc;
+    }
+    u64 rec_base = 0;
+    for (int i = 0; i < S; ++i) {
+        Lane &ln = c->lane[i];
+        if ((rc = lane_resolve(c, ln, false))) return rc;
+        if (rec_base + ln.n_records > 0xFFFFFFFFull) return fail(SMX_ERR_CAPACITY, "smx_run_resident: more than 2^32 records");
+        if ((rc = lane_compact(c, ln, (u32)rec_base, false))) return rc;
+        rec_base += ln.n_records;
+    }
+    for (int i = 1; i < S; ++i) {
+        CU(cudaEventRecord(c->ev_lane_done[i], c->lane[i].stream));
+        CU(cudaStreamWaitEvent(c->lane[0].stream, c->ev_lane_done[i], 0));
+    }
+    CU(cudaEventRecord(c->ev_t1, c->lane[0].stream));
+    CU(cudaStreamSynchronize(c->lane[0].stream));
     CU(cudaGetLastError());
-    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&c->stage_ms[i], ln.ev[i], ln.ev[i + 1]));
-    CU(cudaEventElapsedTime(&c->total_ms, ln.ev[0], ln.ev[4]));
-    for (int i = 0; i < 8; ++i) CU(cudaEventElapsedTime(&c->kernel_ms[i], ln.kev[i], ln.kev[i + 1]));
-    CU(cudaEventElapsedTime(&c->kernel_ms[8], ln.kev[9], ln.ev[4]));
+    CU(cudaEventElapsedTime(&c->total_ms, c->ev_t0, c->ev_t1));
+    for (auto &v : c->stage_ms) v = 0.f;
+    for (auto &v : c->kernel_ms) v = 0.f;
     return SMX_OK;
 }
 
@@ -606,6 +685,31 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     Lane &ln = c->lane[0];
     if (!ln.have_results) return fail(SMX_ERR_ARG, "smx_download_results: nothing to download");
     CU(cudaSetDevice(c->device));
+    if (c->resident_lanes > 1) {
+        if (out->primer_hits || out->endmask_bits || out->barcode_hits)
+            return fail(SMX_ERR_ARG, "smx_download_results: per-search detail needs an unsplit batch (smx_set_resident_split(ctx, 1))");
+        u64 total = 0, matched = 0;
+        for (int i = 0; i < c->resident_lanes; ++i) { total += c->lane[i].n_records; matched += c->lane[i].n_matched; }
+        out->n_records = total;
+        out->n_matched = matched;
+        if (total > out->records_cap)
+            return fail(SMX_ERR_CAPACITY, "smx_download_results: %llu records, capacity %llu",
+                        (unsigned long long)total, (unsigned long long)out->records_cap);
+        u64 rec_base = 0;
+        for (int i = 0; i < c->resident_lanes; ++i) {
+            Lane &l = c->lane[i];
+            u32 r0, r1;
+            resident_bounds(c, i, r0, r1);
+            if (out->rec_offset)
+                CU(cudaMemcpyAsync(out->rec_offset + r0, l.rec_offset_out.p, (size_t)(r1 - r0) * sizeof(u32), cudaMemcpyDeviceToHost, l.stream));
+            if (out->records && l.n_records)
+                CU(cudaMemcpyAsync(out->records + rec_base, l.records.p, (size_t)l.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, l.stream));
+            rec_base += l.n_records;
+        }
+        for (int i = 0; i < c->resident_lanes; ++i) CU(cudaStreamSynchronize(c->lane[i].stream));
+        if (out->rec_offset) out->rec_offset[c->resident_n] = (u32)total;
+        return SMX_OK;
+    }
     const Batch &b = ln.b;
     const Tables t = lane_tables(c, ln);
     const u32 n = b.n_reads;
@@ -774,7 +878,10 @@ int smx_match_batch(smx_ctx *c, const smx_batch *in, smx_results *out) {
         return match_batch_pipelined(c, in, out);
     }
     c->last_chunks = 1;
+    const int split = c->resident_split;
+    if (detail) c->resident_split = 1;          // the per-search detail arrays are laid out for one lane
     rc = smx_upload_batch(c, in);
+    c->resident_split = split;
     if (rc) return rc;
     rc = smx_run_resident(c);
     if (rc) return rc;
@@ -790,7 +897,12 @@ int smx_set_pipeline_chunk(smx_ctx *c, uint32_t reads_per_chunk) {
 
 int smx_last_chunk_count(const smx_ctx *c) { return c ? c->last_chunks : 0; }
 
-uint64_t smx_last_deferred(const smx_ctx *c) { return c ? c->lane[0].n_deferred : 0; }
+uint64_t smx_last_deferred(const smx_ctx *c) {
+    if (!c) return 0;
+    uint64_t v = 0;
+    for (int i = 0; i < std::max(1, c->resident_lanes); ++i) v += c->lane[i].n_deferred;
+    return v;
+}
 
 int smx_last_timing(const smx_ctx *c, float *total_ms, float stage_ms[4]) {
     if (!c) return fail(SMX_ERR_ARG, "smx_last_timing: null context");
@@ -814,9 +926,12 @@ int smx_last_launch_count(const smx_ctx *c) {
 
 int smx_last_work(const smx_ctx *c, uint64_t cells[2], uint64_t wordcols[2]) {
     if (!c || !c->lane[0].have_results) return fail(SMX_ERR_ARG, "smx_last_work: no results");
-    const Lane &ln = c->lane[0];
-    cells[0] = ln.work[0]; cells[1] = ln.work[1];
-    wordcols[0] = ln.work[2]; wordcols[1] = ln.work[3];
+    cells[0] = cells[1] = wordcols[0] = wordcols[1] = 0;
+    for (int i = 0; i < std::max(1, c->resident_lanes); ++i) {
+        const Lane &ln = c->lane[i];
+        cells[0] += ln.work[0]; cells[1] += ln.work[1];
+        wordcols[0] += ln.work[2]; wordcols[1] += ln.work[3];
+    }
     return SMX_OK;
 }
 

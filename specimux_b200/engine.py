@@ -223,6 +223,10 @@ class Matcher:
         """Chunk size of the pipelined smx_match_batch (0 = always one shot)."""
         _lib.check(self._lib.smx_set_pipeline_chunk(self._ctx, int(reads_per_chunk)))
 
+    def set_resident_split(self, n_sub_batches: int):
+        """Sub-batches the resident form runs concurrently (1 = one lane, per-kernel times available)."""
+        _lib.check(self._lib.smx_set_resident_split(self._ctx, int(n_sub_batches)))
+
     def last_chunk_count(self) -> int:
         return int(self._lib.smx_last_chunk_count(self._ctx))
 

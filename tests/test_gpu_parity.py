@@ -244,3 +244,43 @@ def test_cuda_long_primers_match_live_oracle(seed):
     lookahead, shuffled Ph/Mh shifts, in-kernel start recovery) against the live oracle."""
     from test_random_tables_hostsim import make_case, run_case
     run_case(*make_case(seed, long_primers=True), tag="long seed %d" % seed, binding="cuda")
+
+
+@pytest.mark.parametrize("cfg,n", [("ont037", 300_000), ("dense", 150_000), ("multipool", 140_000)])
+def test_resident_sub_batches_equal_one_lane(cfg, n):
+    """upload / run_resident / download with the batch cut into concurrent sub-batches (2, 3, 5 lanes)
+    returns exactly the one-lane records, offsets, matched count and work counters; reads on the exact
+    4-bit side stream included."""
+    ds = synth.CONFIGS[cfg](n_reads=n, seed=99, with_quals=False)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params, dereplicate="none" if cfg == "dense" else "best")
+    codes = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].copy()
+    rng = np.random.default_rng(6)
+    hits = rng.choice(codes.shape[0], size=codes.shape[0] // 5000, replace=False)
+    codes[hits] = np.frombuffer(b"NRYn", dtype=np.uint8)[rng.integers(0, 4, size=hits.shape[0])]
+    batch = PackedBatch.from_blob(codes.tobytes(), ds.offsets.astype(np.uint64), clip=ds.search_len)
+    with Matcher(mt) as m:
+        m.set_resident_split(1)
+        m.upload(batch)
+        m.run_resident()
+        one = m.download()
+        work = m.last_work()
+        assert m.last_timing()[0] > 0 and sum(m.last_kernel_times().values()) > 0
+        for split in (2, 3, 5):
+            m.set_resident_split(split)
+            m.upload(batch)
+            for _ in range(2):
+                m.run_resident()
+                got = m.download()
+                assert got.n_matched == one.n_matched
+                assert np.array_equal(got.rec_offset, one.rec_offset)
+                assert got.records.tobytes() == one.records.tobytes()
+                assert m.last_work() == work
+                assert m.last_timing()[0] > 0
+        # a pipelined host-buffer call in between does not disturb the resident state machine
+        m.set_resident_split(3)
+        piped = m.match(batch)
+        assert piped.records.tobytes() == one.records.tobytes()
+        m.upload(batch)
+        m.run_resident()
+        assert m.download().records.tobytes() == one.records.tobytes()
