@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="reads per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=12000, help="reads of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--split", type=int, default=3, help="concurrent sub-batches of the resident run (1 = one lane)")
+    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of the resident run (1 = one lane)")
     ap.add_argument("--chunk", type=int, default=-1, help="reads per pipeline chunk of smx_match_batch (-1 = library default)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -208,7 +208,7 @@ def main():
             dist.barrier()
 
     # ---- device-resident timing ------------------------------------------------------------
-    # (a) the measured configuration: the resident batch runs as concurrent sub-batches (default 3)
+    # (a) the measured configuration: the resident batch runs as concurrent sub-batches (default 2)
     matcher.upload(batch)
     for _ in range(args.warmup):
         matcher.run_resident()

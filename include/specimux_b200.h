@@ -234,7 +234,7 @@ int smx_upload_batch(smx_ctx *ctx, const smx_batch *batch);   /* H2D only       
 int smx_run_resident(smx_ctx *ctx);                           /* kernels only, on the last upload  */
 int smx_download_results(smx_ctx *ctx, smx_results *out);     /* D2H only                         */
 
-/* The resident form cuts batches of >= 131072 reads into `n_sub_batches` (default 3, env
+/* The resident form cuts batches of >= 131072 reads into `n_sub_batches` (default 2, env
  * SMX_RESIDENT_SPLIT, 1..8) pieces that run concurrently on separate streams: one piece's
  * latency-bound tail (general selection, scan, compaction) overlaps another's ALU-bound search
  * kernels.  Results are identical.  With more than one piece the per-stage / per-kernel times below

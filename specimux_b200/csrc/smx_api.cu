@@ -141,7 +141,7 @@ struct smx_ctx {
     // resident (upload / run / download) form: a large batch is cut into `resident_split` sub-batches
     // that run concurrently on separate lanes, so one sub-batch's latency-bound tail (general
     // selection, scan, compaction) overlaps another's ALU-bound search kernels
-    int resident_split = 3, resident_lanes = 1;
+    int resident_split = 2, resident_lanes = 1;
     u32 resident_n = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane_done[kMaxLanes] = {};
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once

@@ -161,8 +161,34 @@ int next_fastq(smx_reader &r, smx_block *blk) {
     if (*b != '@') return -fail(SMX_IO_ERR_FORMAT, "Records in Fastq files should start with '@' character");
     const char *tb = b + 1, *te = e;
     rstrip(tb, te);
-    std::string title(tb, te);          // kept for the error message and because the buffer may move
-    if (blk) add_title(*blk, title.data(), title.data() + title.size());
+    std::string skipped_title;           // skip mode only: the title is needed for an error message
+    if (blk) add_title(*blk, tb, te); else skipped_title.assign(tb, te);
+    // Fast path: the common four-line record lying completely in the buffer (one memchr per line,
+    // one memcpy each for bases and qualities).  Anything else -- wrapped sequence or quality lines,
+    // a record cut by the end of the buffer or of the file -- takes the general path below, which
+    // starts again right after the title line (nothing is consumed here unless the record fits).
+    {
+        const char *p = r.buf.data() + r.pos, *end = r.buf.data() + r.end;
+        const char *nl1 = (const char *)memchr(p, '\n', (size_t)(end - p));
+        if (nl1 && nl1 + 1 < end && nl1[1] == '+') {
+            const char *nl2 = (const char *)memchr(nl1 + 1, '\n', (size_t)(end - nl1 - 1));
+            const char *nl3 = nl2 ? (const char *)memchr(nl2 + 1, '\n', (size_t)(end - nl2 - 1)) : nullptr;
+            if (nl3) {
+                const char *sb = p, *se = nl1, *qb = nl2 + 1, *qe = nl3;
+                lstrip(sb, se); rstrip(sb, se);
+                lstrip(qb, qe); rstrip(qb, qe);
+                if (se - sb == qe - qb && se > sb) {
+                    if (blk) {
+                        blk->bases.insert(blk->bases.end(), sb, se);
+                        blk->quals.insert(blk->quals.end(), qb, qe);
+                        blk->seq_off.push_back(blk->bases.size());
+                    }
+                    r.pos = (size_t)(nl3 - r.buf.data()) + 1;
+                    return 1;
+                }
+            }
+        }
+    }
     size_t seq_len = 0, qual_len = 0;
     // sequence lines up to the '+' line
     bool first = true;
@@ -170,7 +196,6 @@ int next_fastq(smx_reader &r, smx_block *blk) {
         if ((rc = r.line(b, e)) < 0) return -SMX_IO_ERR_IO;
         if (rc == 0) break;
         if (!first && b < e && *b == '+') break;
-        if (!first && b == e) { /* empty line is not a '+' line: appended (nothing) */ }
         const char *sb = b, *se = e;
         lstrip(sb, se); rstrip(sb, se);
         if (blk) blk->bases.insert(blk->bases.end(), sb, se);
@@ -188,8 +213,12 @@ int next_fastq(smx_reader &r, smx_block *blk) {
         qual_len += (size_t)(se - sb);
         got_one = true;
     }
-    if (qual_len != seq_len)
+    if (qual_len != seq_len) {
+        std::string title = blk ? std::string(blk->titles.data() + blk->title_off[blk->title_off.size() - 2],
+                                              blk->titles.data() + blk->title_off.back())
+                                : skipped_title;
         return -fail(SMX_IO_ERR_FORMAT, "Lengths of sequence and quality values differs for %s", title.c_str());
+    }
     if (blk) blk->seq_off.push_back(blk->bases.size());
     return 1;
 }
