@@ -249,7 +249,7 @@ int smx_last_timing(const smx_ctx *ctx, float *total_ms, float stage_ms[4]);
  * capacity re-run overwrites the marks it passes again).  Fills up to n entries and returns the
  * number available, in this order: 0 window staging, 1 sliced primer search (all primers, they run
  * concurrently), 2 primer finish / classic search, 3 primer start recovery, 4 barcode search,
- * 5 fast selection, 6 general selection, 7 record scan, 8 record compaction. */
+ * 5 fast selection, 6 general selection, 7 record scan + compaction (one kernel), 8 offset rebase. */
 int smx_last_kernel_times(const smx_ctx *ctx, float *ms, int n);
 
 /* Number of kernel launches issued by the last smx_run_resident. */

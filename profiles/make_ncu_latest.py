@@ -8,7 +8,8 @@ import sys
 
 NAMES = [("k_stage_windows", "stage_windows"), ("k_primer_sliced", "primer_sliced"), ("k_primer_search", "primer_finish"),
          ("k_primer_start", "primer_start"), ("k_barcode_bitsliced", "barcode_bitsliced"), ("k_select_fast", "select_fast"),
-         ("k_select<", "select_general"), ("k_scan", "scan"), ("k_compact_records", "compact_records")]
+         ("k_select<", "select_general"), ("k_scan_compact", "scan_compact"), ("k_rebase_offsets", "rebase_offsets"), ("k_scan", "scan"),
+         ("k_compact_records", "compact_records")]
 
 
 def main(path, capture):

@@ -80,7 +80,7 @@ struct Lane {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[kKernelMarks] = {};    // per-kernel boundaries of a timed (resident) run
     Batch b;
-    DevBuf<u32> packed2, lengths, packed4, win, win2, tmix, endmask, impmask, rec_count, rec_offset, rec_offset_out, block_sums;
+    DevBuf<u32> packed2, lengths, packed4, win, win2, tmix, endmask, impmask, rec_count, rec_offset, rec_offset_out, ticket;
     DevBuf<u64> word_off, off4;
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
@@ -93,6 +93,9 @@ struct Lane {
     // control block: 8 counters (4 work, matched, (u32,u32) overflow, (u32,u32) total/pool, hit overflow)
     // followed by the 2 * SMX_MAX_PRIMERS per-slot entry counts -- one memset, one read-back
     DevBuf<unsigned long long> counters;
+    DevBuf<unsigned long long> tile_status;     // k_scan_compact: look-back status words (epoch-tagged, never cleared)
+    u32 tickets_issued = 0, epoch = 0;          // cumulative tile tickets / launch epoch of k_scan_compact
+    cudaEvent_t ev_counters = nullptr;          // control block has reached the pinned mirror
     u32 e_cap = 0, pool_cap = 0;
     int hit_cap = 0;                        // hit sub-list capacity the lane's buffers are laid out for
     unsigned long long *h_counters = nullptr;   // pinned mirror of the control block
@@ -106,7 +109,7 @@ struct Lane {
 
     void release() {
         packed2.release(); lengths.release(); packed4.release(); win.release(); win2.release(); tmix.release(); endmask.release(); impmask.release();
-        rec_count.release(); rec_offset.release(); rec_offset_out.release(); block_sums.release(); word_off.release();
+        rec_count.release(); rec_offset.release(); rec_offset_out.release(); ticket.release(); tile_status.release(); word_off.release();
         off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
         ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
         ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release();
@@ -116,6 +119,7 @@ struct Lane {
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &e : kev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_ready) { cudaEventDestroy(ev_ready); ev_ready = nullptr; }
+        if (ev_counters) { cudaEventDestroy(ev_counters); ev_counters = nullptr; }
         if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
         for (auto &e : ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &a : aux) if (a) { cudaStreamDestroy(a); a = nullptr; }
@@ -162,6 +166,7 @@ static cudaError_t lane_init(Lane &ln) {
     for (auto &a : ln.aux) if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (auto &j : ln.ev_join) if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ln.ev_counters, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto &ev : ln.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     for (auto &ev : ln.kev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     if ((e = cudaHostAlloc((void **)&ln.h_counters, kCtlWords * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
@@ -223,8 +228,25 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     CU(ln.rec_stage.ensure(n_pad)); CU(ln.rec_extra.ensure(n_pad));
     CU(ln.rec_count.ensure(n)); CU(ln.rec_offset.ensure((size_t)n + 1)); CU(ln.rec_offset_out.ensure((size_t)n + 1));
     CU(ln.read_flags.ensure(n));
-    CU(ln.block_sums.ensure((n + kScanBlock - 1) / kScanBlock + 1));
     cudaStream_t st = ln.stream;
+    {
+        const size_t tiles = ((size_t)n + kScanTile - 1) / kScanTile + 1;
+        if (ln.tile_status.cap < tiles) {       // fresh status words must not carry a plausible epoch tag
+            CU(ln.tile_status.ensure(tiles));
+            CU(cudaMemsetAsync(ln.tile_status.p, 0, ln.tile_status.cap * sizeof(unsigned long long), st));
+        }
+        if (!ln.ticket.p) {
+            CU(ln.ticket.ensure(1));
+            CU(cudaMemsetAsync(ln.ticket.p, 0, sizeof(u32), st));
+            ln.tickets_issued = 0;
+        }
+    }
+    // compacted records: one per read plus whatever the pool can hold (grown by lane_resolve if a
+    // second selection pass produces more)
+    if (ln.records.cap < (size_t)n_pad + ln.pool_cap + 1) {
+        if (ln.drain_pending) CU(cudaEventSynchronize(ln.ev_drained));      // the old buffer is still being copied out
+        CU(ln.records.ensure((size_t)n_pad + ln.pool_cap + 1));
+    }
     CU(cudaMemcpyAsync(ln.packed2.p, in->packed2 + w0, (w1 - w0) * sizeof(u32), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ln.word_off.p, in->word_off + r0, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ln.lengths.p, in->lengths + r0, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, st));
@@ -241,24 +263,41 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     b.slot_count = (u32 *)(ln.counters.p + kCtrWords); b.ent_base = ln.ent_base.p; b.defer_list = ln.defer_list.p;
     b.rec_stage = ln.rec_stage.p; b.rec_extra = ln.rec_extra.p;
     b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
-    b.records = nullptr; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
+    b.records = ln.records.p; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
     ln.have_batch = true; ln.have_results = false;
     ln.launches = 0;
     return SMX_OK;
 }
 
-// rec_count -> rec_offset (exclusive scan), flag counters, then the asynchronous read-back of the
-// whole control block (counters + per-slot entry counts).
-static cudaError_t enqueue_scan_and_count(Lane &ln) {
+// rec_count -> rec_offset, flag counters and the read-ordered compaction of the records in one
+// launch (k_scan_compact), then the asynchronous read-back of the whole control block (counters +
+// per-slot entry counts).  Nothing waits for the host here: the records buffer is sized up front and
+// lane_resolve() re-runs this step if a second selection pass outgrows it.
+static cudaError_t enqueue_scan_compact(smx_ctx *c, Lane &ln) {
     Batch &b = ln.b;
     const u32 n = b.n_reads;
     cudaStream_t st = ln.stream;
-    unsigned sblocks = (n + kScanBlock - 1) / kScanBlock;
-    k_scan_sums<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, b.read_flags, n, ln.block_sums.p, ln.counters.p + 4,
-                                                (unsigned *)(ln.counters.p + 5));
-    k_scan_apply<<<sblocks, kScanBlock, 0, st>>>(b.rec_count, n, ln.block_sums.p, b.rec_offset, (u32 *)(ln.counters.p + 6));
-    ln.launches += 2;
-    return cudaMemcpyAsync(ln.h_counters, ln.counters.p, kCtlWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    cudaError_t e;
+    if (ln.drain_pending) {                 // the previous chunk's records are still being copied out of ln.records
+        if ((e = cudaStreamWaitEvent(st, ln.ev_drained, 0)) != cudaSuccess) return e;
+        ln.drain_pending = false;
+    }
+    const unsigned tiles = (n + kScanTile - 1) / kScanTile;
+    ln.epoch = ln.epoch % ((1u << 30) - 1u) + 1u;
+    const u32 cap = (u32)std::min<size_t>(ln.records.cap, 0xFFFFFFFFu);
+    k_scan_compact<<<tiles, kScanThreads, 0, st>>>(lane_tables(c, ln), b, cap, ln.tile_status.p, ln.ticket.p, ln.tickets_issued, ln.epoch);
+    ln.tickets_issued += tiles;
+    ++ln.launches;
+    if ((e = cudaMemcpyAsync(ln.h_counters, ln.counters.p, kCtlWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    return cudaEventRecord(ln.ev_counters, st);
+}
+
+// Zeroes what k_scan_compact accumulates into (matched reads, overflow flags, record total) but
+// keeps the pool usage in the upper half of counter 6.
+static cudaError_t reset_scan_counters(Lane &ln) {
+    cudaError_t e = cudaMemsetAsync(ln.counters.p + 4, 0, 2 * sizeof(unsigned long long), ln.stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(ln.counters.p + 6, 0, sizeof(u32), ln.stream);
 }
 
 // Enqueues stages `from`..3 (0 = from window staging) through the scan and the counter read-back.
@@ -378,7 +417,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     }
     ln.launches += 2;
     KMARK(7);
-    CU(enqueue_scan_and_count(ln));
+    CU(enqueue_scan_compact(c, ln));
     KMARK(8);
 #undef KMARK
     return SMX_OK;
@@ -393,7 +432,7 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     const int nP = c->t.n_primers;
     cudaStream_t st = ln.stream;
     for (;;) {
-        CU(cudaStreamSynchronize(st));
+        CU(cudaEventSynchronize(ln.ev_counters));
         unsigned long long *hc = ln.h_counters;
         u32 max_entries = 0;
         for (int i = 0; i < 2 * nP; ++i) max_entries = std::max(max_entries, ln.h_slot_counts[i]);
@@ -411,15 +450,16 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
             from = 3;
         }
         if (from < 0) break;
+        CU(cudaStreamSynchronize(st));              // buffers are about to be replaced
         CU(ensure_entry_buffers(c, ln));
         int rc = lane_enqueue(c, ln, from, timed);
         if (rc) return rc;
     }
     ln.big_list_host.clear();
+    const Tables t = lane_tables(c, ln);
     if ((u32)ln.h_counters[5]) {
         // some reads overflowed the thread-local group storage (or emit many records): second GPU
         // pass for those reads only, on kBigGroups-entry global scratch
-        const Tables t = lane_tables(c, ln);
         std::vector<unsigned char> flags(n);
         CU(cudaMemcpyAsync(flags.data(), b.read_flags, n, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -434,13 +474,31 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
             k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 0);
             ++ln.launches;
         }
-        CU(cudaMemsetAsync(ln.counters.p + 4, 0, 2 * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ln.counters.p + 6, 0, sizeof(u32), st));
-        CU(enqueue_scan_and_count(ln));
-        CU(cudaStreamSynchronize(st));
+        CU(reset_scan_counters(ln));
+        CU(enqueue_scan_compact(c, ln));            // offsets again, now with the big reads' record counts
+        CU(cudaEventSynchronize(ln.ev_counters));
         if ((u32)(ln.h_counters[5] >> 32))
             return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceed %d dereplication groups",
                         (unsigned)(ln.h_counters[5] >> 32), kBigGroups);
+    }
+    if ((u32)ln.h_counters[6] > ln.records.cap) {
+        // more records than the compaction buffer holds (k_scan_compact skipped what did not fit)
+        CU(cudaStreamSynchronize(st));
+        if (ln.drain_pending) { CU(cudaEventSynchronize(ln.ev_drained)); ln.drain_pending = false; }
+        CU(ln.records.ensure((size_t)(u32)ln.h_counters[6] + 1024));
+        b.records = ln.records.p;
+        CU(reset_scan_counters(ln));
+        CU(enqueue_scan_compact(c, ln));
+        CU(cudaEventSynchronize(ln.ev_counters));
+    }
+    if (!ln.big_list_host.empty()) {
+        // the big reads' records go straight to their compacted positions
+        const size_t chunk = 512;
+        for (size_t off = 0; off < ln.big_list_host.size(); off += chunk) {
+            u32 cnt = (u32)std::min(chunk, ln.big_list_host.size() - off);
+            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 1);
+            ++ln.launches;
+        }
     }
     ln.n_records = (u32)ln.h_counters[6];
     ln.n_matched = ln.h_counters[4];
@@ -449,23 +507,15 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     return SMX_OK;
 }
 
-// Read-ordered compaction of the lane's records (asynchronous).
+// The records are already compacted (k_scan_compact); what is left is the sub-batch's record offsets
+// in the caller's whole batch (asynchronous).
 static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
-    const Tables t = lane_tables(c, ln);
+    (void)c;
     Batch &b = ln.b;
     cudaStream_t st = ln.stream;
-    if (ln.drain_pending) { CU(cudaStreamWaitEvent(ln.stream, ln.ev_drained, 0)); ln.drain_pending = false; }
-    CU(ln.records.ensure(ln.n_records + 1));
-    b.records = ln.records.p;
     if (timed) CU(cudaEventRecord(ln.kev[9], st));
-    k_compact_records<<<(unsigned)(((u64)b.n_reads * 4 + 255) / 256), 256, 0, st>>>(t, b, rec_base, ln.rec_offset_out.p);
+    k_rebase_offsets<<<(b.n_reads + 255) / 256, 256, 0, st>>>(b.rec_offset, b.n_reads, rec_base, ln.rec_offset_out.p);
     ++ln.launches;
-    const size_t chunk = 512;
-    for (size_t off = 0; off < ln.big_list_host.size(); off += chunk) {
-        u32 cnt = (u32)std::min(chunk, ln.big_list_host.size() - off);
-        k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 1);
-        ++ln.launches;
-    }
     if (timed) CU(cudaEventRecord(ln.ev[4], st));
     CU(cudaGetLastError());
     ln.have_results = true;

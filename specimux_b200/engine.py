@@ -231,7 +231,7 @@ class Matcher:
         return int(self._lib.smx_last_chunk_count(self._ctx))
 
     KERNEL_NAMES = ("stage_windows", "primer_sliced", "primer_finish", "primer_start", "barcode_bitsliced",
-                    "select_fast", "select_general", "scan", "compact_records")
+                    "select_fast", "select_general", "scan_compact", "rebase_offsets")
 
     def last_kernel_times(self):
         """{kernel: ms} of the last run_resident (CUDA events on the launching stream)."""
