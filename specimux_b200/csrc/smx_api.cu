@@ -95,6 +95,7 @@ struct Lane {
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned long long> tile_status;     // k_scan_compact: look-back status words (epoch-tagged, never cleared)
     u32 tickets_issued = 0, epoch = 0;          // cumulative tile tickets / launch epoch of k_scan_compact
+    const u32 *offsets_src = nullptr;           // record offsets to copy out: rec_offset, or its rebased copy
     cudaEvent_t ev_counters = nullptr;          // control block has reached the pinned mirror
     u32 e_cap = 0, pool_cap = 0;
     int hit_cap = 0;                        // hit sub-list capacity the lane's buffers are laid out for
@@ -154,6 +155,7 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
+    bool ramp = true;                       // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=0 disables)
 };
 
 static cudaError_t lane_init(Lane &ln) {
@@ -514,8 +516,12 @@ static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
     Batch &b = ln.b;
     cudaStream_t st = ln.stream;
     if (timed) CU(cudaEventRecord(ln.kev[9], st));
-    k_rebase_offsets<<<(b.n_reads + 255) / 256, 256, 0, st>>>(b.rec_offset, b.n_reads, rec_base, ln.rec_offset_out.p);
-    ++ln.launches;
+    ln.offsets_src = b.rec_offset;
+    if (rec_base) {
+        k_rebase_offsets<<<(b.n_reads + 255) / 256, 256, 0, st>>>(b.rec_offset, b.n_reads, rec_base, ln.rec_offset_out.p);
+        ++ln.launches;
+        ln.offsets_src = ln.rec_offset_out.p;
+    }
     if (timed) CU(cudaEventRecord(ln.ev[4], st));
     CU(cudaGetLastError());
     ln.have_results = true;
@@ -608,6 +614,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_PIPELINE_LANES")) c->n_lanes = std::max(2, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_RESIDENT_SPLIT")) c->resident_split = std::max(1, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
+    if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
     return SMX_OK;
@@ -751,7 +758,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
             u32 r0, r1;
             resident_bounds(c, i, r0, r1);
             if (out->rec_offset)
-                CU(cudaMemcpyAsync(out->rec_offset + r0, l.rec_offset_out.p, (size_t)(r1 - r0) * sizeof(u32), cudaMemcpyDeviceToHost, l.stream));
+                CU(cudaMemcpyAsync(out->rec_offset + r0, l.offsets_src, (size_t)(r1 - r0) * sizeof(u32), cudaMemcpyDeviceToHost, l.stream));
             if (out->records && l.n_records)
                 CU(cudaMemcpyAsync(out->records + rec_base, l.records.p, (size_t)l.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, l.stream));
             rec_base += l.n_records;
@@ -827,8 +834,23 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
 // as the one-shot form writes them.
 static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *out) {
     const u32 n = in->n_reads, chunk = c->chunk_reads;
-    const u32 n_chunks = (n + chunk - 1) / chunk;
-    const u32 per = (((n + n_chunks - 1) / n_chunks) + 127u) & ~127u;      // even split, 128-read aligned
+    // Chunk boundaries (128-read aligned).  The first two chunks are a quarter and a half of the
+    // nominal size: the copy-out engine is the bottleneck of the pipeline (64-byte records), and it
+    // idles until the first chunk has gone through every kernel -- a small first chunk gets there
+    // sooner.  The rest is split evenly.
+    std::vector<u32> cuts{0};
+    if (c->ramp && (u64)n > 2ull * chunk) {
+        const u32 c0 = ((chunk / 4) + 127u) & ~127u, c1 = ((chunk / 2) + 127u) & ~127u;
+        cuts.push_back(c0);
+        cuts.push_back(c0 + c1);
+    }
+    {
+        const u32 rest = n - cuts.back();
+        const u32 k = (rest + chunk - 1) / chunk;
+        const u32 per = (((rest + k - 1) / k) + 127u) & ~127u;
+        while (cuts.back() < n) cuts.push_back((u32)std::min<u64>((u64)cuts.back() + per, n));
+    }
+    const u32 n_chunks = (u32)cuts.size() - 1;
     const u32 *shared4 = nullptr;
     if (in->packed4 && in->off4 && in->packed4_words) {
         CU(c->shared_packed4.ensure(in->packed4_words));
@@ -849,7 +871,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         for (auto &e : tev) cudaEventCreate(&e);
     }
     auto mark = [&](u32 i, int k, cudaStream_t st) { if (trace) { cudaEventRecord(tev[(size_t)i * 4 + k], st); thost[(size_t)i * 4 + k] = now_ms() - t_begin; } };
-    auto bounds = [&](u32 i, u32 &r0, u32 &r1) { r0 = std::min<u64>((u64)i * per, n); r1 = std::min<u64>((u64)(i + 1) * per, n); };
+    auto bounds = [&](u32 i, u32 &r0, u32 &r1) { r0 = cuts[i]; r1 = cuts[i + 1]; };
     auto finish = [&](u32 i) -> int {
         Lane &ln = c->lane[i % c->n_lanes];
         u32 r0, r1;
@@ -863,7 +885,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
             CU(cudaEventRecord(ln.ev_ready, ln.stream));
             CU(cudaStreamWaitEvent(ln.out_stream, ln.ev_ready, 0));
             if (out->rec_offset)
-                CU(cudaMemcpyAsync(out->rec_offset + r0, ln.rec_offset_out.p, (size_t)(r1 - r0) * sizeof(u32),
+                CU(cudaMemcpyAsync(out->rec_offset + r0, ln.offsets_src, (size_t)(r1 - r0) * sizeof(u32),
                                    cudaMemcpyDeviceToHost, ln.out_stream));
             if (out->records && ln.n_records)
                 CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, ln.n_records * sizeof(smx_record),
@@ -896,7 +918,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
     while (rc == SMX_OK && finished < issued) rc = finish(finished++);
     for (auto &ln : c->lane) if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamSynchronize(ln.out_stream); ln.drain_pending = false; }
     if (trace) {
-        fprintf(stderr, "[smx pipeline] %u chunks of %u reads, host total %.3f ms\n", n_chunks, per, now_ms() - t_begin);
+        fprintf(stderr, "[smx pipeline] %u chunks (first %u, last %u reads), host total %.3f ms\n", n_chunks, cuts[1] - cuts[0], cuts[n_chunks] - cuts[n_chunks - 1], now_ms() - t_begin);
         for (u32 i = 0; i < n_chunks && rc == SMX_OK && !overflow; ++i) {
             float t[4];
             for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[(size_t)i * 4 + k]);

@@ -1199,6 +1199,7 @@ constexpr int kScanTile = 1024, kScanThreads = 256;
 __global__ void __launch_bounds__(kScanThreads) k_scan_compact(SMX_KARGS, u32 rec_cap, unsigned long long *tile_status,
                                                                u32 *ticket, u32 ticket_base, u32 epoch) {
     __shared__ u32 s_off[kScanTile + 1];
+    __shared__ unsigned char s_big[kScanTile];
     __shared__ u32 s_warp[kScanThreads / 32];
     __shared__ u32 s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
@@ -1270,23 +1271,36 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_compact(SMX_KARGS, u32 re
     u32 off = s_prefix + s_warp[warp] + incl - tsum;
     for (int i = 0; i < 4; ++i) {
         s_off[threadIdx.x * 4 + i] = off;
+        s_big[threadIdx.x * 4 + i] = (unsigned char)(f[i] & 2);
         if (r0 + i < n) b.rec_offset[r0 + i] = off;
         off += c[i];
     }
     if (threadIdx.x == kScanThreads - 1) s_off[kScanTile] = off;
     __syncthreads();
-    // compaction of the tile's records
+    // compaction of the tile's records: four quarters in flight per thread (loads first, then stores)
     const u32 tile_r0 = tile * kScanTile;
-    for (u32 idx = threadIdx.x; idx < kScanTile * 4; idx += kScanThreads) {
-        const u32 lr = idx >> 2, q = idx & 3, read = tile_r0 + lr;
-        if (read >= n) break;
-        const u32 o = s_off[lr], cnt = s_off[lr + 1] - o;
-        if (!cnt || (b.read_flags[read] & 2) || (u64)o + cnt > rec_cap) continue;   // k_select_big writes flagged reads
-        uint4 *dst = reinterpret_cast<uint4 *>(b.records + o);
-        dst[q] = reinterpret_cast<const uint4 *>(b.rec_stage + read)[q];
-        if (cnt > 1) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(b.rec_pool + b.rec_extra[read]);
-            for (u32 i = q; i < 4 * (cnt - 1); i += 4) dst[4 + i] = src[i];
+#pragma unroll 1
+    for (u32 base = 0; base < kScanTile * 4; base += 4 * kScanThreads) {
+        uint4 v[4];
+        u32 o[4], cnt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 idx = base + k * kScanThreads + threadIdx.x, lr = idx >> 2, read = tile_r0 + lr;
+            o[k] = s_off[lr];
+            cnt[k] = read < n ? s_off[lr + 1] - o[k] : 0u;
+            if (cnt[k] && (s_big[lr] || (u64)o[k] + cnt[k] > rec_cap)) cnt[k] = 0;      // k_select_big writes flagged reads
+            if (cnt[k]) v[k] = reinterpret_cast<const uint4 *>(b.rec_stage + read)[idx & 3];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!cnt[k]) continue;
+            const u32 idx = base + k * kScanThreads + threadIdx.x, q = idx & 3, read = tile_r0 + (idx >> 2);
+            uint4 *dst = reinterpret_cast<uint4 *>(b.records + o[k]);
+            dst[q] = v[k];
+            if (cnt[k] > 1) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(b.rec_pool + b.rec_extra[read]);
+                for (u32 i = q; i < 4 * (cnt[k] - 1); i += 4) dst[4 + i] = src[i];
+            }
         }
     }
 }

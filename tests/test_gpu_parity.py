@@ -156,7 +156,7 @@ def test_pipelined_match_equals_one_shot(cfg, n, chunk):
         m.set_pipeline_chunk(chunk)
         for _ in range(2):
             piped = m.match(batch)
-            assert m.last_chunk_count() == -(-n // chunk)
+            assert -(-n // chunk) <= m.last_chunk_count() <= -(-n // chunk) + 2      # two small ramp-up chunks
             assert piped.n_matched == one.n_matched
             assert np.array_equal(piped.rec_offset, one.rec_offset)
             assert piped.records.tobytes() == one.records.tobytes()
