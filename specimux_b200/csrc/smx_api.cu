@@ -155,7 +155,9 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
-    bool ramp = true;                       // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=0 disables)
+    bool ramp = false;                      // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
+                                            // measured slower on config 2: 1.83 vs 1.76 ms, the extra chunks cost more
+                                            // kernel-chain latency than the earlier first copy-out saves)
 };
 
 static cudaError_t lane_init(Lane &ln) {
@@ -834,10 +836,9 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
 // as the one-shot form writes them.
 static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *out) {
     const u32 n = in->n_reads, chunk = c->chunk_reads;
-    // Chunk boundaries (128-read aligned).  The first two chunks are a quarter and a half of the
-    // nominal size: the copy-out engine is the bottleneck of the pipeline (64-byte records), and it
-    // idles until the first chunk has gone through every kernel -- a small first chunk gets there
-    // sooner.  The rest is split evenly.
+    // Chunk boundaries (128-read aligned), an even split.  Optionally (SMX_PIPELINE_RAMP=1) the first
+    // two chunks are a quarter and a half of the nominal size so that the copy-out engine starts
+    // earlier.
     std::vector<u32> cuts{0};
     if (c->ramp && (u64)n > 2ull * chunk) {
         const u32 c0 = ((chunk / 4) + 127u) & ~127u, c1 = ((chunk / 2) + 127u) & ~127u;
