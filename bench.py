@@ -182,6 +182,8 @@ def main():
     if lib.smx_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the matching has no CPU fallback")
 
+    numa = _lib.bind_thread_to_gpu_numa_node(local)      # before any pinned allocation (first touch)
+    log("rank %d: GPU %d on NUMA node %s" % (rank, local, "%d (%d cpus)" % numa if numa else "unknown"))
     wl = WORKLOADS[args.config]
     n_reads = args.reads or wl["reads"]
     ds = dataset(args.config, n_reads, rank)
@@ -329,6 +331,7 @@ def main():
                     "api": "smx_match_batch (pinned host buffers, reads clipped to head/tail search_len bases; "
                            "H2D + kernels + D2H, chunks pipelined over three streams)"},
             "gpu_launches": int(launches * args.steps),
+            "host_numa_node": numa[0] if numa else None,
             "clocks": clocks.summary(),
             "records_per_step": int(len(res.records)), "matched_reads": int(res.n_matched),
             "reads_on_general_selection_path": int(deferred),

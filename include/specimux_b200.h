@@ -203,6 +203,10 @@ const char *smx_last_error(void);
 /* Number of visible CUDA devices (0 when none; never an error). */
 int smx_device_count(void);
 
+/* PCI bus id of a device ("0000:1b:00.0"), so that the host layer can pin its feeder thread and its
+ * pinned buffers to the NUMA node the GPU hangs off (the host is the scaling limiter). */
+int smx_device_pci_bus_id(int device, char *out, int len);
+
 /* Build a context on `device`: copies the tables, builds IUPAC-aware Peq masks (edlib
  * additionalEqualities semantics, constants.py:13-20) and the specimen lookup table.
  * Replaces read_primers_file/read_specimen_file products + setup_match_parameters thresholds. */

@@ -61,7 +61,8 @@ EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create"
            "smx_result_bound", "smx_match_batch", "smx_upload_batch", "smx_run_resident",
            "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
            "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads", "smx_int_alu_peak", "smx_host_alloc",
-           "smx_host_free", "smx_flush_l2", "smx_set_pipeline_chunk", "smx_last_chunk_count", "smx_last_deferred", "smx_last_kernel_times", "smx_set_resident_split"]
+           "smx_host_free", "smx_flush_l2", "smx_set_pipeline_chunk", "smx_last_chunk_count", "smx_last_deferred", "smx_last_kernel_times", "smx_set_resident_split",
+           "smx_device_pci_bus_id"]
 
 
 class SmxError(RuntimeError):
@@ -111,6 +112,7 @@ def load():
         lib.smx_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         lib.smx_last_deferred.restype = C.c_uint64
         lib.smx_set_resident_split.argtypes = [C.c_void_p, C.c_uint32]
+        lib.smx_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
         if lib.smx_abi_version() != 1:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib
@@ -160,3 +162,34 @@ class HostBuffer:
             self.free()
         except Exception:
             pass
+
+
+def bind_thread_to_gpu_numa_node(device: int):
+    """Restricts the calling thread to the CPUs of the NUMA node `device` is attached to, so that the
+    pinned buffers it allocates next (first touch) and its copies stay local to the GPU's PCIe root.
+    Returns (node, n_cpus) or None when the topology is unknown (single node, containers, no sysfs)."""
+    try:
+        buf = C.create_string_buffer(32)
+        if load().smx_device_pci_bus_id(device, buf, 32) != SMX_OK:
+            return None
+        bus = buf.value.decode().lower()
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except (OSError, ValueError, AttributeError):
+        return None

@@ -536,6 +536,12 @@ int smx_abi_version(void) { return SMX_ABI_VERSION; }
 
 const char *smx_last_error(void) { return g_err; }
 
+int smx_device_pci_bus_id(int device, char *out, int len) {
+    if (!out || len < 16) return fail(SMX_ERR_ARG, "smx_device_pci_bus_id: buffer too small");
+    CU(cudaDeviceGetPCIBusId(out, len, device));
+    return SMX_OK;
+}
+
 int smx_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

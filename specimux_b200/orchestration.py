@@ -290,6 +290,7 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
     counts = [0, 0]
 
     def gpu_worker(dev):
+        _lib.bind_thread_to_gpu_numa_node(dev)
         while True:
             job = gpu_q[dev].get()
             if job is None:
