@@ -284,3 +284,74 @@ def test_resident_sub_batches_equal_one_lane(cfg, n):
         m.upload(batch)
         m.run_resident()
         assert m.download().records.tobytes() == one.records.tobytes()
+
+
+def _edge_batches():
+    rng = np.random.default_rng(17)
+    g = H.load_golden("fixture")
+    good = [r[1] for r in g["reads"]]
+
+    def rnd(n):
+        return "".join(rng.choice(list("ACGT"), size=n)) if n else ""
+    yield "one_read", [good[0]]
+    yield "one_empty_read", [""]
+    yield "all_empty", [""] * 130
+    yield "n127", (good * 4)[:127]
+    yield "n128", (good * 4)[:128]
+    yield "n129", (good * 4)[:129]
+    yield "every_length_0_to_260", [rnd(n) for n in range(261)]
+    yield "tiny_and_huge", [rnd(1), good[1], rnd(120_000) + good[2] + rnd(70_000), rnd(2), good[3][:79], good[3][:80], good[3][:81]]
+    yield "all_flagged", [s[:10] + "N" + s[11:] for s in good] + ["N" * 300, "acgt" * 50, "RYKM" * 40]
+    yield "good_reads_embedded_in_long_reads", [rnd(5000) + s + rnd(5000) for s in good[:10]] + good
+
+
+@pytest.mark.parametrize("name,reads", list(_edge_batches()), ids=[n for n, _ in _edge_batches()])
+@pytest.mark.parametrize("clip", [0, 80])
+def test_edge_case_batches_equal_kernel_simulator(name, reads, clip):
+    """Degenerate batch shapes through the C ABI: bit-identical records, offsets and per-search detail between
+    the CUDA launch and the CPU loop over the same per-thread routines."""
+    g = H.load_golden("fixture")
+    run = g["runs"]["default"]
+    specimens = H.build_specimens(g["primers"], g["specimens"])
+    params = H.params_from_run(run, specimens)
+    mt = MatchTables(specimens, params, trim="tails")
+    batch = PackedBatch(reads, clip=clip)
+    with Matcher(mt) as m:
+        for detail in (True, False):
+            gpu = m.match(batch, detail=detail)
+            sim = Matcher(mt, binding=H.hostsim_binding()).match(batch, detail=detail)
+            assert gpu.n_matched == sim.n_matched
+            assert np.array_equal(gpu.rec_offset, sim.rec_offset)
+            assert gpu.records.tobytes() == sim.records.tobytes()
+            if detail:
+                assert np.array_equal(gpu.primer_hits, sim.primer_hits)
+                assert np.array_equal(gpu.endmask, sim.endmask)
+                assert np.array_equal(gpu.barcode_hits, sim.barcode_hits)
+
+
+def test_contexts_are_independent_and_reusable():
+    """Two contexts on one device driven from two threads, created and destroyed repeatedly."""
+    import threading
+    ds = synth.ont037(n_reads=20_000, seed=5, with_quals=False)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params)
+    blob = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].tobytes()
+    batch = PackedBatch.from_blob(blob, ds.offsets.astype(np.uint64), clip=ds.search_len)
+    with Matcher(mt) as m:
+        want = m.match(batch).records.tobytes()
+    errors = []
+
+    def work():
+        try:
+            for _ in range(3):
+                with Matcher(mt) as mm:
+                    for _ in range(3):
+                        assert mm.match(batch).records.tobytes() == want
+        except BaseException as e:      # surfaced below
+            errors.append(e)
+    threads = [threading.Thread(target=work) for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
