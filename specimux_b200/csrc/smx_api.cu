@@ -155,19 +155,23 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
+    bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
     bool ramp = false;                      // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
                                             // measured slower on config 2: 1.83 vs 1.76 ms, the extra chunks cost more
                                             // kernel-chain latency than the earlier first copy-out saves)
 };
 
-static cudaError_t lane_init(Lane &ln) {
+// `prio`: CUDA stream priority of the lane (lower number = served first).  Lanes are filled in index
+// order, so with SMX_PIPELINE_PRIORITIES=1 pending blocks of an earlier chunk are scheduled before a
+// later one's instead of all in-flight chunks sharing the SMs evenly and finishing together.
+static cudaError_t lane_init(Lane &ln, int prio = 0) {
     cudaError_t e;
     if (ln.stream) return cudaSuccess;
-    if ((e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&ln.stream, cudaStreamNonBlocking, prio)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithFlags(&ln.out_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-    for (auto &a : ln.aux) if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (auto &a : ln.aux) if ((e = cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, prio)) != cudaSuccess) return e;
     for (auto &j : ln.ev_join) if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_counters, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -212,7 +216,16 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     const u64 w0 = in->word_off[r0];
     const u64 w1 = (r1 < in->n_reads) ? std::min<u64>(in->word_off[r1] + 1, in->packed2_words) : in->packed2_words;
     if (w1 < w0) return fail(SMX_ERR_ARG, "smx_batch: word_off is not ascending");
-    CU(lane_init(ln));
+    {
+        int prio = 0;
+        if (c->lane_priorities) {
+            int lo = 0, hi = 0;                                 // hi = greatest priority (numerically lowest)
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            const int idx = (int)(&ln - c->lane);
+            prio = std::min(lo, hi + idx);
+        }
+        CU(lane_init(ln, prio));
+    }
     CU(ln.packed2.ensure(w1 - w0 + 2)); CU(ln.word_off.ensure(n)); CU(ln.lengths.ensure(n));
     const bool flagged = in->packed4 && in->off4 && in->packed4_words;
     if (flagged) { CU(ln.off4.ensure(n)); if (!shared4) CU(ln.packed4.ensure(in->packed4_words)); }
@@ -595,7 +608,12 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         }                                                                                             \
     } while (0)
     CUC(cudaSetDevice(device));
-    CUC(lane_init(c->lane[0]));
+    {
+        int prio = 0;
+        if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
+        if (c->lane_priorities) { int lo = 0; CUC(cudaDeviceGetStreamPriorityRange(&lo, &prio)); }
+        CUC(lane_init(c->lane[0], prio));
+    }
     CUC(upload(c->peq_rc, ht.peq_rc)); CUC(upload(c->peq_rcrev, ht.peq_rcrev)); CUC(upload(c->peq_fw, ht.peq_fw));
     CUC(upload(c->b_len, ht.b_len)); CUC(upload(c->pb_barcode, ht.pb_barcode));
     CUC(upload(c->bw_len, ht.bw_len)); CUC(upload(c->bw_primer, ht.bw_primer)); CUC(upload(c->bw_row, ht.bw_row));
@@ -622,6 +640,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_PIPELINE_LANES")) c->n_lanes = std::max(2, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_RESIDENT_SPLIT")) c->resident_split = std::max(1, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
+    if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
