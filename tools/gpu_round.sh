@@ -2,8 +2,8 @@
 # One GPU-box visit: parity tests, bench, ncu launch list, ncu full capture of the stage kernels.
 # usage (from the repo root, on the GPU box): bash tools/gpu_round.sh TAG [skip-tests]
 TAG=${1:-dev}
-# kernels of one resident step on one lane: stage, sliced x primers, finish, start, barcode, 2 x select, scan_compact, rebase
-SKIP=${SKIP:-30}
+# 9 kernels per resident step on one lane (stage, sliced x 2 primers, finish, start, barcode, 2 x select, scan_compact); skip = split pass (warm-up + step) + attribution warm-up
+SKIP=${SKIP:-27}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L
@@ -15,5 +15,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
   -k regex:"k_primer_sliced|k_primer_search|k_primer_start|k_barcode_bitsliced|k_select|k_stage_windows|k_rebase_offsets|k_scan" \
-  --launch-skip $SKIP -c 10 -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --split 1 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+  --launch-skip $SKIP -c 9 -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --split 1 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ncu -i $OUT/prof_$TAG.ncu-rep --page raw --csv > $OUT/raw_$TAG.csv 2>/dev/null
