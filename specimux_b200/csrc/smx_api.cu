@@ -331,8 +331,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
         if (timed) CU(cudaEventRecord(ln.ev[0], st));
         KMARK(0);
-        dim3 grid(blocks, 2 * t.nw2);
-        k_stage_windows<<<grid, 128, 0, st>>>(t, b);
+        k_stage_windows<<<(n + kStageBlock - 1) / kStageBlock, kStageBlock, 0, st>>>(t, b);
         ++ln.launches;
     }
     if (from <= 1) {   // stage 1

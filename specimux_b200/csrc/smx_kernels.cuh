@@ -44,7 +44,9 @@ SMX_HD u32 revcomp16(u32 v) {
 // One thread stages 16 symbols of one strand: the 2-bit word win2[w2] (input of the sliced primer
 // search) and the two 4-bit words win[2*w2], win[2*w2+1] (barcode stage, start recovery, classic
 // primer search).  Positions past the staged length hold kSymOther in `win`.
-SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int strand, int w2) {
+// `src2` / `src2_origin`: where the read's 2-bit words are read from -- src2[word_off[read] - src2_origin + i];
+// the packed stream itself (b.packed2, b.word_base) or a block's shared-memory copy of its reads' words.
+SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int strand, int w2, const u32 *src2, u64 src2_origin) {
     const int n = (int)b.lengths[read];
     const Geo g = make_geo(n, t.L);
     u32 *wlo = b.win + ((u64)strand * t.wpw + 2 * w2) * b.n_pad + read;
@@ -59,7 +61,7 @@ SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int str
             const int x0 = g.woff + 16 * w2;                  // strand coordinate of symbol 0
             const int first = strand ? (n - 1 - x0) - 15 : stored_pos(b, x0, n);   // stored index of the lowest base needed
             const int lo = first < 0 ? 0 : first;
-            const u32 *src = b.packed2 + (b.word_off[read] - b.word_base) + (u64)(lo >> 4);
+            const u32 *src = src2 + (b.word_off[read] - src2_origin) + (u64)(lo >> 4);
             const u64 pair = (u64)src[0] | ((u64)src[1] << 32);
             v = (u32)(pair >> (2 * (lo & 15)));
             if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below
@@ -819,12 +821,37 @@ template <int SW> SMX_HD u32 long_carry_in(u32 G, u32 P) {
 // several contexts / pipeline lanes can be in flight on one device without sharing a symbol.
 #define SMX_KARGS const __grid_constant__ Tables c_tables, const __grid_constant__ Batch b
 
-__global__ void __launch_bounds__(128) k_stage_windows(SMX_KARGS) {
-    // grid: x over reads, y over (strand, 16-symbol word)
-    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
+// One block stages the windows of 128 consecutive reads.  Their 2-bit words are one contiguous range
+// of the packed stream (reads are packed back to back), so the block first copies that range into
+// shared memory with fully coalesced loads and every thread then cuts its read's 2 * nw2 windows
+// out of the copy; the stores are coalesced across the block's reads as before.  The first form --
+// one thread per (read, window word), each loading its two words straight from the stream -- made a
+// warp touch 32 different reads' lines per load and was the top kernel of the long-amplicon config
+// (457 us of 1,279; profiles/r1_v20_bench_long.json).  Blocks whose reads span more than the tile
+// (unclipped long reads) read the stream directly.
+constexpr int kStageBlock = 128;
+constexpr u32 kStageTileWords = 8192;           // 32 KB of shared memory: 128 reads x up to 64 words (1024 bases)
+
+__global__ void __launch_bounds__(kStageBlock) k_stage_windows(SMX_KARGS) {
+    __shared__ u32 s_src[kStageTileWords + 2];
+    const Tables &t = c_tables;
+    const u32 r0 = blockIdx.x * kStageBlock;
+    const u32 r1 = r0 + kStageBlock < b.n_reads ? r0 + kStageBlock : b.n_reads;
+    const u64 w0 = b.word_off[r0];
+    const u64 w1 = b.word_off[r1 - 1] + (u64)((stored_len(b, (int)b.lengths[r1 - 1]) + 15) >> 4);
+    const bool tiled = w1 - w0 <= kStageTileWords;
+    if (tiled) {
+        const u32 span = (u32)(w1 - w0) + 2;                                  // window extraction reads one word past the read
+        const u32 *g = b.packed2 + (w0 - b.word_base);
+        for (u32 i = threadIdx.x; i < span; i += kStageBlock) s_src[i] = g[i];
+    }
+    __syncthreads();
+    const u32 read = r0 + threadIdx.x;
     if (read >= b.n_reads) return;
-    int strand = blockIdx.y / c_tables.nw2, w2 = blockIdx.y % c_tables.nw2;
-    stage_window_pair(c_tables, b, read, strand, w2);
+    const u32 *src2 = tiled ? s_src : b.packed2;
+    const u64 origin = tiled ? w0 : b.word_base;
+    for (int s = 0; s < 2; ++s)
+        for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, read, s, w2, src2, origin);
 }
 
 // Sliced primer search: one thread per (group of 32 reads, strand) for one primer of length M.
