@@ -331,7 +331,11 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
         if (timed) CU(cudaEventRecord(ln.ev[0], st));
         KMARK(0);
-        k_stage_windows<<<(n + kStageBlock - 1) / kStageBlock, kStageBlock, 0, st>>>(t, b);
+        // shared-memory tile: 128 reads x the words of a clipped read (+1 word of slack per read, +2 per tile)
+        u32 tile_words = 0;
+        if (b.clip) tile_words = (u32)kStageBlock * ((2 * b.clip + 15) / 16 + 1) + 2;
+        if (tile_words * sizeof(u32) > 48u * 1024u) tile_words = 0;           // beyond the default dynamic limit: direct loads
+        k_stage_windows<<<(n + kStageBlock - 1) / kStageBlock, dim3(kStageBlock, 2), tile_words * sizeof(u32), st>>>(t, b, tile_words);
         ++ln.launches;
     }
     if (from <= 1) {   // stage 1

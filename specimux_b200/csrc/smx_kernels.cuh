@@ -827,31 +827,32 @@ template <int SW> SMX_HD u32 long_carry_in(u32 G, u32 P) {
 // out of the copy; the stores are coalesced across the block's reads as before.  The first form --
 // one thread per (read, window word), each loading its two words straight from the stream -- made a
 // warp touch 32 different reads' lines per load and was the top kernel of the long-amplicon config
-// (457 us of 1,279; profiles/r1_v20_bench_long.json).  Blocks whose reads span more than the tile
-// (unclipped long reads) read the stream directly.
-constexpr int kStageBlock = 128;
-constexpr u32 kStageTileWords = 8192;           // 32 KB of shared memory: 128 reads x up to 64 words (1024 bases)
+// (457 us of 1,279; profiles/r1_v20_bench_long.json).  The tile is dynamic shared memory sized by the
+// host for the batch's clip length (128 reads x the most words a clipped read can have); blocks whose
+// reads span more than that (unclipped long reads) read the stream directly.
+constexpr int kStageBlock = 128;                // reads per block; blockDim = (kStageBlock, 2 strands)
 
-__global__ void __launch_bounds__(kStageBlock) k_stage_windows(SMX_KARGS) {
-    __shared__ u32 s_src[kStageTileWords + 2];
+// tile_words: capacity of the dynamic shared-memory tile in words (0 = always read the stream directly)
+__global__ void __launch_bounds__(2 * kStageBlock) k_stage_windows(SMX_KARGS, u32 tile_words) {
+    extern __shared__ u32 s_src[];
     const Tables &t = c_tables;
     const u32 r0 = blockIdx.x * kStageBlock;
     const u32 r1 = r0 + kStageBlock < b.n_reads ? r0 + kStageBlock : b.n_reads;
     const u64 w0 = b.word_off[r0];
     const u64 w1 = b.word_off[r1 - 1] + (u64)((stored_len(b, (int)b.lengths[r1 - 1]) + 15) >> 4);
-    const bool tiled = w1 - w0 <= kStageTileWords;
+    const bool tiled = w1 - w0 + 2 <= tile_words;                             // window extraction reads one word past the read
     if (tiled) {
-        const u32 span = (u32)(w1 - w0) + 2;                                  // window extraction reads one word past the read
+        const u32 span = (u32)(w1 - w0) + 2;
         const u32 *g = b.packed2 + (w0 - b.word_base);
-        for (u32 i = threadIdx.x; i < span; i += kStageBlock) s_src[i] = g[i];
+        for (u32 i = threadIdx.y * kStageBlock + threadIdx.x; i < span; i += 2 * kStageBlock) s_src[i] = g[i];
     }
     __syncthreads();
     const u32 read = r0 + threadIdx.x;
     if (read >= b.n_reads) return;
     const u32 *src2 = tiled ? s_src : b.packed2;
     const u64 origin = tiled ? w0 : b.word_base;
-    for (int s = 0; s < 2; ++s)
-        for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, read, s, w2, src2, origin);
+    const int strand = (int)threadIdx.y;
+    for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, read, strand, w2, src2, origin);
 }
 
 // Sliced primer search: one thread per (group of 32 reads, strand) for one primer of length M.
