@@ -147,6 +147,7 @@ struct smx_ctx {
     // that run concurrently on separate lanes, so one sub-batch's latency-bound tail (general
     // selection, scan, compaction) overlaps another's ALU-bound search kernels
     int resident_split = 2, resident_lanes = 1;
+    int resident_skew = 50;                 // two sub-batches: percent of the reads in the first (SMX_RESIDENT_SKEW)
     u32 resident_n = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane_done[kMaxLanes] = {};
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
@@ -641,6 +642,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
         else if (v == 0) c->chunk_reads = 0;                   // 0 disables the pipelined form
     }
     if (const char *env = getenv("SMX_PIPELINE_LANES")) c->n_lanes = std::max(2, std::min(kMaxLanes, atoi(env)));
+    if (const char *env = getenv("SMX_RESIDENT_SKEW")) c->resident_skew = std::max(10, std::min(90, atoi(env)));
     if (const char *env = getenv("SMX_RESIDENT_SPLIT")) c->resident_split = std::max(1, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
@@ -672,6 +674,13 @@ constexpr u32 kResidentSplitMin = 1u << 17;     // batches below this many reads
 
 static void resident_bounds(const smx_ctx *c, int i, u32 &r0, u32 &r1) {
     const u32 n = c->resident_n;
+    if (c->resident_lanes == 2 && c->resident_skew != 50) {
+        // uneven halves: the lanes then reach their latency-bound selection tails at different times
+        const u32 mid = (u32)(((u64)n * (u32)c->resident_skew / 100u) + 127u) & ~127u;
+        r0 = i == 0 ? 0 : std::min(mid, n);
+        r1 = i == 0 ? std::min(mid, n) : n;
+        return;
+    }
     const u32 per = (((n + (u32)c->resident_lanes - 1) / (u32)c->resident_lanes) + 127u) & ~127u;
     r0 = (u32)std::min<u64>((u64)i * per, n);
     r1 = (u32)std::min<u64>((u64)(i + 1) * per, n);

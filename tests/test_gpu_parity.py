@@ -118,7 +118,7 @@ def test_level1_detail_matches_oracle():
     assert checked > 20
 
 
-@pytest.mark.parametrize("cfg,n", [("ont037", 30000), ("dense", 20000), ("multipool", 20000)])
+@pytest.mark.parametrize("cfg,n", [("ont037", 30000), ("dense", 20000), ("multipool", 20000), ("long", 8000)])
 def test_cuda_equals_kernel_simulator_at_scale(cfg, n):
     """Bit-identical records between the CUDA launch and the CPU loop over the same thread routines:
     catches indexing / race / launch-geometry faults the small oracle cases cannot."""
@@ -355,3 +355,43 @@ def test_contexts_are_independent_and_reusable():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("cfg,n,min_agree,min_rate", [("dense", 400_000, 0.95, 0.80), ("multipool", 400_000, 0.98, 0.88),
+                                                      ("long", 120_000, 0.98, 0.88)])
+def test_properties_at_scale_other_configs(cfg, n, min_agree, min_rate):
+    """BASELINE configs 3-5 at six-figure read counts, through size-independent properties: determinism,
+    one-shot == pipelined == resident sub-batches, batch-split invariance, and agreement of every
+    dereplicated full match with the specimen the generator drew the read from."""
+    ds = synth.CONFIGS[cfg](n_reads=n, with_quals=False)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    blob = lut[ds.codes].tobytes()
+    offs = ds.offsets.astype(np.uint64)
+    batch = PackedBatch.from_blob(blob, offs, clip=ds.search_len)
+    with Matcher(mt) as m:
+        m.set_pipeline_chunk(0)
+        whole = m.match(batch)
+        assert m.match(batch).records.tobytes() == whole.records.tobytes()            # deterministic
+        m.set_pipeline_chunk(65536)
+        piped = m.match(batch)
+        assert m.last_chunk_count() > 2
+        assert piped.records.tobytes() == whole.records.tobytes() and np.array_equal(piped.rec_offset, whole.rec_offset)
+        m.set_resident_split(3)
+        m.upload(batch)
+        m.run_resident()
+        assert m.download().records.tobytes() == whole.records.tobytes()
+        cut = n // 3 + 17
+        parts = []
+        for a, b in ((0, cut), (cut, n)):
+            r = m.match(PackedBatch.from_blob(blob[int(offs[a]):int(offs[b])], offs[a:b + 1] - offs[a], clip=ds.search_len))
+            rec = r.records.copy()
+            rec["read"] += a
+            parts.append(rec)
+        assert np.concatenate(parts).tobytes() == whole.records.tobytes()            # batch-split invariance
+    rec = whole.records
+    full = rec[rec["resolution"] == 6]
+    agree = float(np.mean(full["sample"] == ds.truth["specimen"][full["read"]]))
+    assert agree > min_agree, agree
+    assert whole.n_matched / n > min_rate, whole.n_matched / n
