@@ -374,7 +374,7 @@ def test_properties_at_scale_other_configs(cfg, n, min_agree, min_rate):
         m.set_pipeline_chunk(0)
         whole = m.match(batch)
         assert m.match(batch).records.tobytes() == whole.records.tobytes()            # deterministic
-        m.set_pipeline_chunk(65536)
+        m.set_pipeline_chunk(32768)
         piped = m.match(batch)
         assert m.last_chunk_count() > 2
         assert piped.records.tobytes() == whole.records.tobytes() and np.array_equal(piped.rec_offset, whole.rec_offset)
