@@ -156,6 +156,7 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
+    bool overlap_start = true;              // start recovery beside the barcode search (SMX_OVERLAP_START=0 disables)
     bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
     bool ramp = false;                      // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
                                             // measured slower on config 2: 1.83 vs 1.76 ms, the extra chunks cost more
@@ -327,6 +328,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     const int nP = t.n_primers;
     cudaStream_t st = ln.stream;
 #define KMARK(i) do { if (timed) CU(cudaEventRecord(ln.kev[i], st)); } while (0)
+    bool start_forked = false;
     const unsigned blocks = (n + 127) / 128;
     if (from <= 0) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
@@ -395,9 +397,22 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
             ++ln.launches;
         }
         KMARK(3);
+        // Start recovery and the barcode search both consume the work entries and are independent of
+        // each other (selection needs both); neither fills the ALU pipe alone (ncu: 68 % / 80 %), so
+        // when this call also enqueues stage 2 the start recovery goes to an auxiliary stream and
+        // runs beside the barcode kernel.  A timed one-lane run keeps them back to back so that the
+        // per-kernel marks stay meaningful.
         dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
-        if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, st>>>(t, b);
-        else k_primer_start<u32><<<sgrid, 128, 0, st>>>(t, b);
+        cudaStream_t ss = st;
+        if (!timed && c->overlap_start) {
+            ss = ln.aux[0];
+            CU(cudaEventRecord(ln.ev_fork, st));
+            CU(cudaStreamWaitEvent(ss, ln.ev_fork, 0));
+            start_forked = true;
+        }
+        if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, ss>>>(t, b);
+        else k_primer_start<u32><<<sgrid, 128, 0, ss>>>(t, b);
+        if (start_forked) CU(cudaEventRecord(ln.ev_join[0], ss));
         ln.launches += 2;
     }
     if (from <= 2) {   // stage 2
@@ -419,6 +434,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
             ++ln.launches;
         }
     }
+    if (start_forked) CU(cudaStreamWaitEvent(st, ln.ev_join[0], 0));
     // stage 3: slot digests, single-pass selection, scan
     if (from >= 2) {                                                                                           // re-run
         CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
@@ -646,6 +662,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_RESIDENT_SPLIT")) c->resident_split = std::max(1, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
+    if (const char *env = getenv("SMX_OVERLAP_START")) c->overlap_start = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
