@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SMX_ABI_VERSION 1
+#define SMX_ABI_VERSION 2
 
 #define SMX_MAX_PRIMERS 64      /* canonical primers (distinct sequences)                         */
 #define SMX_MAX_PATTERN 64      /* primer / barcode length handled by the single-thread kernels   */
@@ -190,6 +190,12 @@ typedef struct smx_results {
                                   (ceil(search_len/32) words) of equal-best end positions          */
     smx_primer_hit *primer_hits;   /* optional, may be NULL: 2 * n_primers * n_reads entries      */
     smx_barcode_hit *barcode_hits; /* optional, may be NULL: 2 * sum(barcodes) * n_reads entries  */
+    uint8_t *orient_hits;      /* optional, may be NULL: 2 * n_primers * n_reads flags of the explicit
+                                  determine_orientation test (demultiplex.py:602-638): entry
+                                  (strand * n_primers + primer) * n_reads + read = forward-sense primer found in the
+                                  first search_len bases of that strand.  Only computed for reads where it can differ
+                                  from the tail-window match of the other strand (shorter than search_len - 1, or
+                                  with non-ACGT symbols); 0 elsewhere.  Used by the trace replay.                 */
 } smx_results;
 
 typedef struct smx_ctx smx_ctx;

@@ -44,7 +44,7 @@ class SmxBatch(C.Structure):
 class SmxResults(C.Structure):
     _fields_ = [("rec_offset", u32p), ("records", C.c_void_p), ("records_cap", C.c_uint64),
                 ("n_records", C.c_uint64), ("n_matched", C.c_uint64), ("endmask_bits", C.c_void_p),
-                ("primer_hits", C.c_void_p), ("barcode_hits", C.c_void_p)]
+                ("primer_hits", C.c_void_p), ("barcode_hits", C.c_void_p), ("orient_hits", C.c_void_p)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<i4"), ("trim_end", "<i4"),
@@ -113,7 +113,7 @@ def load():
         lib.smx_last_deferred.restype = C.c_uint64
         lib.smx_set_resident_split.argtypes = [C.c_void_p, C.c_uint32]
         lib.smx_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
-        if lib.smx_abi_version() != 1:
+        if lib.smx_abi_version() != 2:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -799,7 +799,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     if (!ln.have_results) return fail(SMX_ERR_ARG, "smx_download_results: nothing to download");
     CU(cudaSetDevice(c->device));
     if (c->resident_lanes > 1) {
-        if (out->primer_hits || out->endmask_bits || out->barcode_hits)
+        if (out->primer_hits || out->endmask_bits || out->barcode_hits || out->orient_hits)
             return fail(SMX_ERR_ARG, "smx_download_results: per-search detail needs an unsplit batch (smx_set_resident_split(ctx, 1))");
         u64 total = 0, matched = 0;
         for (int i = 0; i < c->resident_lanes; ++i) { total += c->lane[i].n_records; matched += c->lane[i].n_matched; }
@@ -840,6 +840,9 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     if (out->primer_hits)
         CU(cudaMemcpy2DAsync(out->primer_hits, (size_t)n * sizeof(smx_primer_hit), b.phit,
                              (size_t)b.n_pad * sizeof(smx_primer_hit), (size_t)n * sizeof(smx_primer_hit),
+                             (size_t)2 * t.n_primers, cudaMemcpyDeviceToHost, st));
+    if (out->orient_hits)
+        CU(cudaMemcpy2DAsync(out->orient_hits, (size_t)n, b.orient_hit, (size_t)b.n_pad, (size_t)n,
                              (size_t)2 * t.n_primers, cudaMemcpyDeviceToHost, st));
     if (out->endmask_bits)
         CU(cudaMemcpy2DAsync(out->endmask_bits, (size_t)n * sizeof(u32), b.endmask, (size_t)b.n_pad * sizeof(u32),
@@ -999,7 +1002,7 @@ int smx_match_batch(smx_ctx *c, const smx_batch *in, smx_results *out) {
     if (!out) return fail(SMX_ERR_ARG, "smx_match_batch: null argument");
     int rc = check_batch(c, in, "smx_match_batch");
     if (rc) return rc;
-    const bool detail = out->primer_hits || out->endmask_bits || out->barcode_hits;
+    const bool detail = out->primer_hits || out->endmask_bits || out->barcode_hits || out->orient_hits;
     if (!detail && c->chunk_reads && in->n_reads >= 2 * (u64)c->chunk_reads) {
         CU(cudaSetDevice(c->device));
         return match_batch_pipelined(c, in, out);

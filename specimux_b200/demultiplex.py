@@ -106,10 +106,13 @@ def process_sequences(seq_records: List, parameters: MatchParameters, specimens,
         quals.append(q)
         ids.append(rec.id)
     batch = PackedBatch(bases, clip=parameters.search_len)
-    result = matcher.match(batch, reuse=True)
     trace_ids = None
-    if trace_logger is not None:
+    if trace_logger is not None and getattr(trace_logger, "enabled", True):
+        # tracing narrates every search: ask the device for the per-search detail arrays as well
         from .trace import emit_batch_trace
-        trace_ids = emit_batch_trace(trace_logger, matcher, result, seq_records, record_offset, args)
+        result = matcher.match(batch, detail=True)
+        trace_ids = emit_batch_trace(trace_logger, matcher, result, seq_records, record_offset, args, specimens, parameters)
+    else:
+        result = matcher.match(batch, reuse=True)
     ops = records_to_write_ops(matcher.tables, result, ids, bases, quals, trace_ids)
     return ops, n, result.n_matched

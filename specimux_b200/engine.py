@@ -94,13 +94,14 @@ class PackedBatch:
 
 
 class BatchResult:
-    def __init__(self, rec_offset, records, n_matched, primer_hits=None, endmask=None, barcode_hits=None):
+    def __init__(self, rec_offset, records, n_matched, primer_hits=None, endmask=None, barcode_hits=None, orient_hits=None):
         self.rec_offset = rec_offset
         self.records = records
         self.n_matched = n_matched
         self.primer_hits = primer_hits      # [2*n_primers, n_reads]
         self.endmask = endmask              # [2*n_primers, mask_words, n_reads] uint32
         self.barcode_hits = barcode_hits    # [total_barcode_slots, n_reads]
+        self.orient_hits = orient_hits      # [2*n_primers, n_reads] uint8 (explicit orientation test, irregular reads)
 
 
 class Matcher:
@@ -157,18 +158,21 @@ class Matcher:
         res.rec_offset = _lib.ptr(rec_offset, _lib.u32p)
         res.records = records.ctypes.data
         res.records_cap = cap
-        ph = em = bh = None
+        ph = em = bh = oh = None
         if detail:
             ph = np.zeros((2 * t.n_primers, n), dtype=_lib.PRIMER_HIT_DTYPE)
             em = np.zeros((2 * t.n_primers, t.mask_words, n), dtype=np.uint32)
             bh = np.zeros((max(t.total_barcode_slots, 1), n), dtype=_lib.BARCODE_HIT_DTYPE)
             res.primer_hits = ph.ctypes.data
             res.endmask_bits = em.ctypes.data
+            oh = np.zeros((2 * t.n_primers, n), dtype=np.uint8)
             res.barcode_hits = bh.ctypes.data
-        return res, rec_offset, records, ph, em, bh
+            res.orient_hits = oh.ctypes.data
+        return res, rec_offset, records, ph, em, (bh, oh)
 
     def _finish(self, res, rec_offset, records, ph, em, bh):
-        return BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh)
+        bh, oh = bh
+        return BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh, oh)
 
     # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
     def match(self, batch: PackedBatch, detail: bool = False, reuse=False) -> BatchResult:

@@ -163,6 +163,7 @@ def iter_batches(seq_records, batch_size: int, max_seqs: int, all_seqs: bool):
 
 
 GPU_BATCH_READS = 65536       # reads per GPU call (the reference hands 1000-read batches to CPU workers)
+TRACE_BATCH_READS = 4096      # with -d the per-search detail arrays come back too (one entry per barcode and read)
 
 
 def _visible_gpus() -> int:
@@ -227,7 +228,8 @@ def _run(args, multi: bool):
                     total += n
                     matched += m
 
-            for i, batch in enumerate(iter_batches(seq_records, GPU_BATCH_READS, args.num_seqs, all_seqs)):
+            per_call = TRACE_BATCH_READS if trace_logger is not None else GPU_BATCH_READS
+            for i, batch in enumerate(iter_batches(seq_records, per_call, args.num_seqs, all_seqs)):
                 # tracing needs the batch processed in the main thread order; it still runs on the GPU
                 fut = pool.submit(process_sequences, batch, parameters, specimens, args, prefilter,
                                   trace_logger if n_gpus == 1 else None, offset, i % n_gpus)

@@ -292,6 +292,9 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     if (out->primer_hits)
         for (size_t row = 0; row < (size_t)2 * nP; ++row)
             memcpy(out->primer_hits + row * n, phit.data() + row * n_pad, (size_t)n * sizeof(smx_primer_hit));
+    if (out->orient_hits)
+        for (size_t row = 0; row < (size_t)2 * nP; ++row)
+            memcpy(out->orient_hits + row * n, orient_hit.data() + row * n_pad, (size_t)n);
     if (out->endmask_bits)
         for (size_t row = 0; row < (size_t)2 * nP * t.mw; ++row)
             memcpy(out->endmask_bits + row * n * sizeof(u32), endmask.data() + row * n_pad, (size_t)n * sizeof(u32));

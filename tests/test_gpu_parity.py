@@ -395,3 +395,17 @@ def test_properties_at_scale_other_configs(cfg, n, min_agree, min_rate):
     agree = float(np.mean(full["sample"] == ds.truth["specimen"][full["read"]]))
     assert agree > min_agree, agree
     assert whole.n_matched / n > min_rate, whole.n_matched / n
+
+
+def _trace_cases():
+    import test_trace_events as TT
+    return TT.load_cases(), TT.case_ids()
+
+
+@pytest.mark.parametrize("idx", range(len(_trace_cases()[0])), ids=_trace_cases()[1])
+def test_cuda_trace_events_match_reference_stream(idx, tmp_path):
+    """The trace narrated from the CUDA library's detail arrays equals the unmodified reference's event stream."""
+    import test_trace_events as TT
+    case = TT.load_cases()[idx]
+    got, _ops = TT.product_events(case, tmp_path, None)
+    TT.compare(case, got)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libspecimux_b200.so does not export %s" % name
     assert set(_lib.EXPORTS) == declared
-    assert lib.smx_abi_version() == 1
+    assert lib.smx_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
