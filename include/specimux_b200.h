@@ -179,6 +179,14 @@ typedef struct smx_barcode_hit {
     uint16_t barcode;          /* position j of the barcode in its primer's list                  */
 } smx_barcode_hit;
 
+/* One barcode hit at ONE primer end location (the unmerged form of smx_barcode_hit, for -d3 traces). */
+typedef struct smx_barcode_loc_hit {
+    uint32_t read;
+    uint16_t slot;             /* strand * n_primers + primer                                      */
+    uint16_t location;         /* index of the primer end location in ascending end order          */
+    smx_barcode_hit hit;       /* hit.barcode = position in the primer's list; hit.search_start = that location's */
+} smx_barcode_loc_hit;      /* 24 bytes */
+
 typedef struct smx_results {
     /* per read: records [rec_offset[r], rec_offset[r+1]) ; rec_offset has n_reads+1 entries */
     uint32_t *rec_offset;
@@ -196,6 +204,10 @@ typedef struct smx_results {
                                   first search_len bases of that strand.  Only computed for reads where it can differ
                                   from the tail-window match of the other strand (shorter than search_len - 1, or
                                   with non-ACGT symbols); 0 elsewhere.  Used by the trace replay.                 */
+    smx_barcode_loc_hit *barcode_loc_hits; /* optional (needs barcode_hits too): every barcode hit at every primer
+                                  end location, in no particular order; at most barcode_loc_cap entries are written */
+    uint64_t barcode_loc_cap;
+    uint64_t n_barcode_loc_hits; /* out: entries that exist (may exceed the capacity: call again with more)       */
 } smx_results;
 
 typedef struct smx_ctx smx_ctx;

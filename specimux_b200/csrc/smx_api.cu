@@ -864,6 +864,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
         smx_barcode_hit none;
         none.end_mask = 0; none.search_start = 0; none.distance = -1; none.barcode = 0;
         for (size_t i = 0; i < (size_t)t.total_bslots * n; ++i) out->barcode_hits[i] = none;
+        uint64_t n_loc_hits = 0;
         for (int sd = 0; sd < 2; ++sd)
             for (int g = 0; g < t.n_bwords; ++g) {
                 int p = bwp[g];
@@ -879,10 +880,18 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
                             const smx_barcode_hit &h = lst[(gslot * t.hit_cap + x) * b.e_cap + e];
                             smx_barcode_hit &dst = out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r];
                             if (dst.distance < 0 || h.distance < dst.distance) dst = h;
+                            if (out->barcode_loc_hits) {
+                                if (n_loc_hits < out->barcode_loc_cap) {
+                                    smx_barcode_loc_hit &lh = out->barcode_loc_hits[n_loc_hits];
+                                    lh.read = r; lh.slot = (uint16_t)slot; lh.location = (uint16_t)l; lh.hit = h;
+                                }
+                                ++n_loc_hits;
+                            }
                         }
                     }
                 }
             }
+        out->n_barcode_loc_hits = n_loc_hits;
     }
     return SMX_OK;
 }
@@ -1003,6 +1012,7 @@ int smx_match_batch(smx_ctx *c, const smx_batch *in, smx_results *out) {
     int rc = check_batch(c, in, "smx_match_batch");
     if (rc) return rc;
     const bool detail = out->primer_hits || out->endmask_bits || out->barcode_hits || out->orient_hits;
+    out->n_barcode_loc_hits = 0;
     if (!detail && c->chunk_reads && in->n_reads >= 2 * (u64)c->chunk_reads) {
         CU(cudaSetDevice(c->device));
         return match_batch_pipelined(c, in, out);

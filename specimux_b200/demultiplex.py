@@ -110,7 +110,7 @@ def process_sequences(seq_records: List, parameters: MatchParameters, specimens,
     if trace_logger is not None and getattr(trace_logger, "enabled", True):
         # tracing narrates every search: ask the device for the per-search detail arrays as well
         from .trace import emit_batch_trace
-        result = matcher.match(batch, detail=True)
+        result = matcher.match(batch, detail="locations" if getattr(trace_logger, "verbosity", 1) >= 3 else True)
         trace_ids = emit_batch_trace(trace_logger, matcher, result, seq_records, record_offset, args, specimens, parameters)
     else:
         result = matcher.match(batch, reuse=True)

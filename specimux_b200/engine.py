@@ -102,6 +102,7 @@ class BatchResult:
         self.endmask = endmask              # [2*n_primers, mask_words, n_reads] uint32
         self.barcode_hits = barcode_hits    # [total_barcode_slots, n_reads]
         self.orient_hits = orient_hits      # [2*n_primers, n_reads] uint8 (explicit orientation test, irregular reads)
+        self.barcode_loc_hits = None        # detail="locations": every barcode hit at every primer end location
 
 
 class Matcher:
@@ -168,11 +169,20 @@ class Matcher:
             oh = np.zeros((2 * t.n_primers, n), dtype=np.uint8)
             res.barcode_hits = bh.ctypes.data
             res.orient_hits = oh.ctypes.data
-        return res, rec_offset, records, ph, em, (bh, oh)
+            lh = None
+            if detail == "locations":
+                lh = np.zeros(max(int(self.__dict__.get("_loc_cap", 0)), 64 * n + 1024), dtype=_lib.BARCODE_LOC_HIT_DTYPE)
+                res.barcode_loc_hits = lh.ctypes.data
+                res.barcode_loc_cap = len(lh)
+            return res, rec_offset, records, ph, em, (bh, oh, lh)
+        return res, rec_offset, records, ph, em, (bh, None, None)
 
     def _finish(self, res, rec_offset, records, ph, em, bh):
-        bh, oh = bh
-        return BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh, oh)
+        bh, oh, lh = bh
+        out = BatchResult(rec_offset, records[:int(res.n_records)], int(res.n_matched), ph, em, bh, oh)
+        if lh is not None:
+            out.barcode_loc_hits = lh[:min(int(res.n_barcode_loc_hits), len(lh))]
+        return out
 
     # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
     def match(self, batch: PackedBatch, detail: bool = False, reuse=False) -> BatchResult:
@@ -201,6 +211,9 @@ class Matcher:
                     cap = int(res.n_records)
                     continue
                 _lib.check(rc)
+            if detail == "locations" and int(res.n_barcode_loc_hits) > int(res.barcode_loc_cap):
+                self._loc_cap = int(res.n_barcode_loc_hits) + 1024
+                continue
             return self._finish(res, rec_offset, records, ph, em, bh)
 
     # -- split form -------------------------------------------------------------------------

@@ -118,7 +118,7 @@ class TraceLogger:
 
 class _End:
     """One (strand, primer) search as a candidate sees it (demultiplex.py:748-820 match_one_end)."""
-    __slots__ = ("primer", "matched", "dist", "match_pos", "match_end", "barcodes", "n_loc", "loc_starts", "tail")
+    __slots__ = ("primer", "matched", "dist", "match_pos", "match_end", "barcodes", "n_loc", "loc_starts", "tail", "loc_hits")
 
     def __init__(self, primer):
         self.primer = primer
@@ -127,6 +127,7 @@ class _End:
         self.match_pos = -1            # locations()[0] = (match_pos, match_end) in search coordinates
         self.match_end = -1
         self.tail = None               # (min start, max end) over every location of every barcode hit
+        self.loc_hits = None           # -d3: per primer end location {barcode list position: distance}
         self.barcodes = []             # [(barcode, distance, search_start)] sorted by distance, stable
         self.n_loc = 0
         self.loc_starts = []           # barcode_search_start per primer end location
@@ -246,6 +247,12 @@ class _Replay:
         self.rev = specimens.get_primers(Primer.REV)
         self.total_list = self.t.pb_off[-1]
         self.L = parameters.search_len
+        self.loc_hits = None
+        if getattr(result, "barcode_loc_hits", None) is not None:
+            self.loc_hits = {}
+            for h in result.barcode_loc_hits:
+                self.loc_hits.setdefault((int(h["read"]), int(h["slot"]), int(h["location"])), {})[int(h["hit"]["barcode"])] = \
+                    int(h["hit"]["distance"])
 
     def end(self, r, strand, primer, n):
         """The search of `primer` on `strand` (0 = read as given, 1 = its reverse complement)."""
@@ -281,6 +288,8 @@ class _Replay:
                 pos = 32 * w + low.bit_length() - 1
                 e.loc_starts.append(woff + pos + delta + 1)
                 word ^= low
+        if self.loc_hits is not None:
+            e.loc_hits = [self.loc_hits.get((r, strand * self.nP + p, li), {}) for li in range(len(e.loc_starts))]
         return e
 
     def orientation(self, r, n, flagged):
@@ -314,8 +323,7 @@ class _Replay:
 
 def _log_end_searches(tl, sid, end, which_primer, which_barcode, n, L):
     """PRIMER_SEARCH / BARCODE_SEARCH events of one match_one_end call (levels 2 and 3; the logger
-    filters by verbosity).  Successful barcode searches are reported for the primer end location that
-    won the barcode (the per-location results of the other equal-best ends are merged on the GPU)."""
+    filters by verbosity).  Level 3 reads the per-location barcode hits (smx_results.barcode_loc_hits)."""
     ss, se = n - L, n
     tl.log_primer_search(sid, end.primer.name, which_primer, ss, se, False, -1, -1)
     if not end.matched:
@@ -325,10 +333,13 @@ def _log_end_searches(tl, sid, end, which_primer, which_barcode, n, L):
     if tl.verbosity < 3:
         return
     won = {b: (d, s) for b, d, s in end.barcodes}
-    for b in end.primer.barcodes:
-        for bs in end.loc_starts:
+    for j, b in enumerate(end.primer.barcodes):
+        for li, bs in enumerate(end.loc_starts):
             tl.log_barcode_search(sid, b, which_barcode, end.primer.name, bs, n, False, -1, -1)
-            if b in won and won[b][1] == bs:
+            if end.loc_hits is not None:
+                if j in end.loc_hits[li]:
+                    tl.log_barcode_search(sid, b, which_barcode, end.primer.name, bs, n, True, end.loc_hits[li][j], bs)
+            elif b in won and won[b][1] == bs:      # merged detail only: the location that won the barcode
                 tl.log_barcode_search(sid, b, which_barcode, end.primer.name, bs, n, True, won[b][0], bs)
 
 

@@ -302,6 +302,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         smx_barcode_hit none;
         none.end_mask = 0; none.search_start = 0; none.distance = -1; none.barcode = 0;
         for (size_t i = 0; i < (size_t)t.total_bslots * n; ++i) out->barcode_hits[i] = none;
+        uint64_t n_loc_hits = 0;
         for (int sd = 0; sd < 2; ++sd)
             for (int g = 0; g < t.n_bwords; ++g) {
                 int p = t.bw_primer[g];
@@ -317,10 +318,18 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                             const smx_barcode_hit &h = bh_list[(gslot * t.hit_cap + x) * e_cap + e];
                             smx_barcode_hit &dst = out->barcode_hits[((size_t)t.bslot_base[slot] + h.barcode) * n + r];
                             if (dst.distance < 0 || h.distance < dst.distance) dst = h;
+                            if (out->barcode_loc_hits) {
+                                if (n_loc_hits < out->barcode_loc_cap) {
+                                    smx_barcode_loc_hit &lh = out->barcode_loc_hits[n_loc_hits];
+                                    lh.read = r; lh.slot = (uint16_t)slot; lh.location = (uint16_t)l; lh.hit = h;
+                                }
+                                ++n_loc_hits;
+                            }
                         }
                     }
                 }
             }
+        out->n_barcode_loc_hits = n_loc_hits;
     }
     return SMX_OK;
 }

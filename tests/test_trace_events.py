@@ -45,21 +45,8 @@ def product_events(case, tmp_path, binding):
     return [r[3:] for r in rows[1:]], ops
 
 
-def is_barcode_success(e):
-    return e[1] == "BARCODE_SEARCH" and e[7] == "true"
-
-
 def compare(case, got):
     want = case["events"]
-    if case["verbosity"] >= 3:
-        # documented deviation: successful BARCODE_SEARCH events are reported for the primer end location that
-        # won the barcode only (per-location results of the other equal-best ends are merged on the device)
-        extra = [e for e in got if is_barcode_success(e)]
-        full = [e for e in want if is_barcode_success(e)]
-        assert all(e in full for e in extra)
-        assert len(extra) >= 0.9 * len(full)
-        got = [e for e in got if not is_barcode_success(e)]
-        want = [e for e in want if not is_barcode_success(e)]
     for i, (a, b) in enumerate(zip(got, want)):
         assert a == b, "event %d differs\n got      %r\n expected %r" % (i, a, b)
     assert len(got) == len(want)
