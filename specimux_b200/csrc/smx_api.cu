@@ -101,7 +101,6 @@ struct Lane {
     int hit_cap = 0;                        // hit sub-list capacity the lane's buffers are laid out for
     unsigned long long *h_counters = nullptr;   // pinned mirror of the control block
     u32 *h_slot_counts = nullptr;               // = (u32 *)(h_counters + 8)
-    std::vector<u32> big_list_host;
     bool have_batch = false, have_results = false;
     u64 n_records = 0, n_matched = 0;
     unsigned long long work[4] = {0, 0, 0, 0};
@@ -239,7 +238,7 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     CU(ln.impmask.ensure((size_t)2 * nP * t.mw * n_pad));
     CU(ln.orient_hit.ensure((size_t)2 * nP * n_pad));
     CU(ln.ent_base.ensure((size_t)2 * nP * n_pad));
-    CU(ln.defer_list.ensure(n_pad));
+    CU(ln.defer_list.ensure(n_pad)); CU(ln.big_list.ensure(n_pad));
     if (ln.e_cap < n_pad + n_pad / 4) ln.e_cap = n_pad + n_pad / 4;     // ~1.2 equal-best ends per matched slot is typical
     if (ln.pool_cap < n_pad / 8 + 1024) ln.pool_cap = n_pad / 8 + 1024;
     if (ln.hit_cap < c->t.hit_cap) ln.hit_cap = c->t.hit_cap;
@@ -279,7 +278,7 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     b.packed2 = ln.packed2.p; b.word_off = ln.word_off.p; b.lengths = ln.lengths.p;
     b.packed4 = flagged ? (shared4 ? shared4 : ln.packed4.p) : nullptr; b.off4 = flagged ? ln.off4.p : nullptr;
     b.win = ln.win.p; b.win2 = ln.win2.p; b.tmix = ln.tmix.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
-    b.slot_count = (u32 *)(ln.counters.p + kCtrWords); b.ent_base = ln.ent_base.p; b.defer_list = ln.defer_list.p;
+    b.slot_count = (u32 *)(ln.counters.p + kCtrWords); b.ent_base = ln.ent_base.p; b.defer_list = ln.defer_list.p; b.big_list = ln.big_list.p;
     b.rec_stage = ln.rec_stage.p; b.rec_extra = ln.rec_extra.p;
     b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
     b.records = ln.records.p; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
@@ -438,7 +437,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     // stage 3: slot digests, single-pass selection, scan
     if (from >= 2) {                                                                                           // re-run
         CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ln.counters.p + kCtrDeferred, 0, sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ln.counters.p + kCtrDeferred, 0, 2 * sizeof(unsigned long long), st));      // + kCtrBig
     }
     if (timed) CU(cudaEventRecord(ln.ev[3], st));
     KMARK(5);
@@ -465,9 +464,9 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
 // overflowed the thread-local group storage.  On return n_records / n_matched / work are final.
 static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     Batch &b = ln.b;
-    const u32 n = b.n_reads;
     const int nP = c->t.n_primers;
     cudaStream_t st = ln.stream;
+    bool big_done = false;
     for (;;) {
         CU(cudaEventSynchronize(ln.ev_counters));
         unsigned long long *hc = ln.h_counters;
@@ -486,56 +485,46 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
             ln.pool_cap = (u32)(hc[6] >> 32) + 1024;
             from = 3;
         }
-        if (from < 0) break;
-        CU(cudaStreamSynchronize(st));              // buffers are about to be replaced
-        CU(ensure_entry_buffers(c, ln));
-        int rc = lane_enqueue(c, ln, from, timed);
-        if (rc) return rc;
-    }
-    ln.big_list_host.clear();
-    const Tables t = lane_tables(c, ln);
-    if ((u32)ln.h_counters[5]) {
-        // some reads overflowed the thread-local group storage (or emit many records): second GPU
-        // pass for those reads only, on kBigGroups-entry global scratch
-        std::vector<unsigned char> flags(n);
-        CU(cudaMemcpyAsync(flags.data(), b.read_flags, n, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        std::vector<u32> &big_list = ln.big_list_host;
-        for (u32 r = 0; r < n; ++r) if (flags[r] & 2) big_list.push_back(r);
-        CU(ln.big_list.ensure(big_list.size()));
-        CU(cudaMemcpyAsync(ln.big_list.p, big_list.data(), big_list.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
-        const size_t chunk = 512;
-        CU(ln.big_scratch.ensure(std::min(chunk, big_list.size()) * kBigScratchBytes));
-        for (size_t off = 0; off < big_list.size(); off += chunk) {
-            u32 cnt = (u32)std::min(chunk, big_list.size() - off);
-            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 0);
-            ++ln.launches;
+        if (from >= 0) {
+            CU(cudaStreamSynchronize(st));              // buffers are about to be replaced
+            CU(ensure_entry_buffers(c, ln));
+            int rc = lane_enqueue(c, ln, from, timed);
+            if (rc) return rc;
+            big_done = false;
+            continue;
         }
-        CU(reset_scan_counters(ln));
-        CU(enqueue_scan_compact(c, ln));            // offsets again, now with the big reads' record counts
-        CU(cudaEventSynchronize(ln.ev_counters));
-        if ((u32)(ln.h_counters[5] >> 32))
+        const u32 n_big = (u32)hc[kCtrBig];
+        if (n_big && !big_done) {
+            // some reads overflowed the thread-local group storage or emit many records: second GPU
+            // pass for those reads only, on kBigGroups-entry global scratch, list already on the device
+            if (c->trace) fprintf(stderr, "[smx resolve] %u of %u reads take the second selection pass\n", n_big, b.n_reads);
+            const Tables t = lane_tables(c, ln);
+            const size_t chunk = 512;
+            CU(ln.big_scratch.ensure(std::min<size_t>(chunk, n_big) * kBigScratchBytes));
+            for (size_t off = 0; off < n_big; off += chunk) {
+                u32 cnt = (u32)std::min<size_t>(chunk, n_big - off);
+                k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p);
+                ++ln.launches;
+            }
+            CU(reset_scan_counters(ln));
+            CU(enqueue_scan_compact(c, ln));            // offsets and compaction again, now with the big reads' records
+            big_done = true;
+            continue;
+        }
+        if ((u32)(hc[5] >> 32))
             return fail(SMX_ERR_INTERNAL, "selection: %u read(s) exceed %d dereplication groups",
-                        (unsigned)(ln.h_counters[5] >> 32), kBigGroups);
-    }
-    if ((u32)ln.h_counters[6] > ln.records.cap) {
-        // more records than the compaction buffer holds (k_scan_compact skipped what did not fit)
-        CU(cudaStreamSynchronize(st));
-        if (ln.drain_pending) { CU(cudaEventSynchronize(ln.ev_drained)); ln.drain_pending = false; }
-        CU(ln.records.ensure((size_t)(u32)ln.h_counters[6] + 1024));
-        b.records = ln.records.p;
-        CU(reset_scan_counters(ln));
-        CU(enqueue_scan_compact(c, ln));
-        CU(cudaEventSynchronize(ln.ev_counters));
-    }
-    if (!ln.big_list_host.empty()) {
-        // the big reads' records go straight to their compacted positions
-        const size_t chunk = 512;
-        for (size_t off = 0; off < ln.big_list_host.size(); off += chunk) {
-            u32 cnt = (u32)std::min(chunk, ln.big_list_host.size() - off);
-            k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, 1);
-            ++ln.launches;
+                        (unsigned)(hc[5] >> 32), kBigGroups);
+        if ((u32)hc[6] > ln.records.cap) {
+            // more records than the compaction buffer holds (k_scan_compact skipped what did not fit)
+            CU(cudaStreamSynchronize(st));
+            if (ln.drain_pending) { CU(cudaEventSynchronize(ln.ev_drained)); ln.drain_pending = false; }
+            CU(ln.records.ensure((size_t)(u32)hc[6] + 1024));
+            b.records = ln.records.p;
+            CU(reset_scan_counters(ln));
+            CU(enqueue_scan_compact(c, ln));
+            continue;
         }
+        break;
     }
     ln.n_records = (u32)ln.h_counters[6];
     ln.n_matched = ln.h_counters[4];

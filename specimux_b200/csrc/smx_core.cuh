@@ -32,6 +32,7 @@ constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in 
 constexpr int kBigGroups = 4096;
 // control block of a batch: kCtrWords 64-bit counters followed by the 2 * SMX_MAX_PRIMERS u32 per-slot entry counts
 constexpr int kCtrDeferred = 8;     // (u32) reads left to the general selection kernel
+constexpr int kCtrBig = 9;          // (u32) reads left to the second selection pass (k_select_big)
 constexpr int kCtrWords = 10;    // ... in the second pass over reads that overflowed the first
 
 // ---------------------------------------------------------------------------------------------
@@ -235,6 +236,7 @@ struct Batch {
     unsigned char *bh_count; // [gslot * e_cap + e]; may exceed hit_cap (-> re-run with a larger cap)
     smx_barcode_hit *bh_list;    // [(gslot * hit_cap + h) * e_cap + e], ascending barcode position
     u32 *defer_list;         // reads the fast selection kernel left to the general one (count: counters[kCtrDeferred])
+    u32 *big_list;           // reads the general selection left to k_select_big (count: counters[kCtrBig])
     // single-pass selection: first record of every read + pool for the (rare) further records
     smx_record *rec_stage;   // [read]
     smx_record *rec_pool;    // extra records, contiguous per read

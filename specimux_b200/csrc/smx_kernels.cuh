@@ -1184,7 +1184,10 @@ __global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
     if (cnt > kInlineRecords) flags |= 2;
     b.rec_count[read] = cnt;
     b.read_flags[read] = flags;
-    if (flags & 2) return;
+    if (flags & 2) {                                    // second pass: listed on the device, no host round trip
+        b.big_list[atomicAdd((unsigned int *)&b.counters[kCtrBig], 1u)] = read;
+        return;
+    }
     if (cnt >= 1) b.rec_stage[read] = local[0];
     if (cnt >= 2) {
         u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt - 1);
@@ -1195,8 +1198,12 @@ __global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
 }
 
 // Second pass over the (rare) reads flagged by the first: same routine, kBigGroups-entry storage
-// in global scratch.  One thread per flagged read.
-__global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u32 n_list, unsigned char *scratch, int write_pass) {
+// in global scratch.  One thread per flagged read, list built on the device by k_select.  The
+// routine runs twice in the thread (count, then write) and the records take the same route as
+// everybody else's -- first record staged per read, the rest in a contiguous pool block -- so that
+// the scan + compaction that follows needs no special case.  Reads that overflow even this pass
+// keep bit 1 and get bit 2 (the library reports them).
+__global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u32 n_list, unsigned char *scratch) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_list) return;
     u32 read = list[i];
@@ -1204,12 +1211,19 @@ __global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u
     SelectStore st = big_store(scratch + (size_t)i * kBigScratchBytes, ends);
     SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
     unsigned char flags;
-    smx_record *out = write_pass ? b.records + b.rec_offset[read] : nullptr;
-    u32 cnt = select_read(c, ends, st, out, 0xFFFFFFFFu, flags);
-    if (!write_pass) {
-        b.rec_count[read] = cnt;
-        b.read_flags[read] = (unsigned char)((flags & 1) | 2 | ((flags & 2) ? 4 : 0));   // bit2: still overflowing
+    const u32 cnt = select_read(c, ends, st, nullptr, 0xFFFFFFFFu, flags);
+    b.rec_count[read] = cnt;
+    if (flags & 2) {
+        b.read_flags[read] = (unsigned char)((flags & 1) | 2 | 4);
+        return;
     }
+    b.read_flags[read] = (unsigned char)(flags & 1);
+    if (!cnt) return;
+    const u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt);
+    if ((u64)base + cnt > b.pool_cap) return;           // pool overflow: the library grows it and re-runs selection
+    select_read(c, ends, st, b.rec_pool + base, cnt, flags);
+    b.rec_stage[read] = b.rec_pool[base];
+    b.rec_extra[read] = base + 1;
 }
 
 // Stage 3c.  rec_count -> rec_offset (exclusive scan, n + 1 entries), the per-read flag counters, and
