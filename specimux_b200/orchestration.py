@@ -162,7 +162,8 @@ def iter_batches(seq_records, batch_size: int, max_seqs: int, all_seqs: bool):
         num += len(batch)
 
 
-GPU_BATCH_READS = 65536       # reads per GPU call (the reference hands 1000-read batches to CPU workers)
+# reads per GPU call (the reference hands 1000-read batches to CPU workers); SMX_GPU_BATCH_READS overrides
+GPU_BATCH_READS = max(128, int(os.environ.get("SMX_GPU_BATCH_READS", "65536")))
 TRACE_BATCH_READS = 4096      # with -d the per-search detail arrays come back too (one entry per barcode and read)
 
 

@@ -127,3 +127,29 @@ def test_console_output_and_version(tmp_path):
     assert r.returncode == 0 and r.stdout.count("\n") == 20
     v = _run_cli("--version")
     assert v.returncode == 0 and "specimux version" in v.stdout
+
+
+def test_two_gpus_give_the_same_tree_as_one(tmp_path):
+    """`-t 2` deals batches round-robin to two GPUs (one feeder thread each) and writes in submission order:
+    the output tree must be byte-identical to the one-GPU run, on both I/O routes."""
+    from specimux_b200 import _lib, synth
+    if _lib.load().smx_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ds = synth.ont037(n_reads=30_000, seed=11)
+    p, s, q = str(tmp_path / "primers.fasta"), str(tmp_path / "specimens.txt"), str(tmp_path / "reads.fastq")
+    ds.write_tables(p, s)
+    ds.write_fastq(q)
+    trees = {}
+    for route in ("1", "0"):
+        for t in ("1", "2"):
+            out = str(tmp_path / ("out_%s_%s" % (route, t)))
+            env = dict(os.environ, SMX_NATIVE_IO=route, SMX_GPU_BATCH_READS="4096")
+            r = subprocess.run([sys.executable, "-m", "specimux_b200.cli", p, s, q, "-F", "-O", out, "-t", t],
+                               capture_output=True, text=True, cwd=H.ROOT, timeout=900, env=env)
+            assert r.returncode == 0, r.stderr
+            assert ("Will run on %s GPU(s)" % t) in r.stderr
+            trees[(route, t)] = {k: v for k, v in _tree(out).items() if k != "log.txt"}
+    ref = trees[("1", "1")]
+    assert len(ref) > 700
+    for key, tree in trees.items():
+        assert tree == ref, key
