@@ -155,6 +155,7 @@ struct smx_ctx {
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
+    bool tiny_caps = false;                 // SMX_TEST_TINY_CAPS=1: see lane_upload
     bool overlap_start = true;              // start recovery beside the barcode search (SMX_OVERLAP_START=0 disables)
     bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
     bool ramp = false;                      // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
@@ -239,8 +240,15 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     CU(ln.orient_hit.ensure((size_t)2 * nP * n_pad));
     CU(ln.ent_base.ensure((size_t)2 * nP * n_pad));
     CU(ln.defer_list.ensure(n_pad)); CU(ln.big_list.ensure(n_pad));
-    if (ln.e_cap < n_pad + n_pad / 4) ln.e_cap = n_pad + n_pad / 4;     // ~1.2 equal-best ends per matched slot is typical
-    if (ln.pool_cap < n_pad / 8 + 1024) ln.pool_cap = n_pad / 8 + 1024;
+    if (c->tiny_caps) {
+        // test hook (SMX_TEST_TINY_CAPS=1): start every growable buffer far too small so that each
+        // capacity re-run of lane_resolve() is exercised on the device
+        if (ln.e_cap < 128) ln.e_cap = 128;
+        if (ln.pool_cap < 4) ln.pool_cap = 4;
+    } else {
+        if (ln.e_cap < n_pad + n_pad / 4) ln.e_cap = n_pad + n_pad / 4;     // ~1.2 equal-best ends per matched slot is typical
+        if (ln.pool_cap < n_pad / 8 + 1024) ln.pool_cap = n_pad / 8 + 1024;
+    }
     if (ln.hit_cap < c->t.hit_cap) ln.hit_cap = c->t.hit_cap;
     CU(ensure_entry_buffers(c, ln));
     CU(ln.rec_stage.ensure(n_pad)); CU(ln.rec_extra.ensure(n_pad));
@@ -651,6 +659,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_RESIDENT_SPLIT")) c->resident_split = std::max(1, std::min(kMaxLanes, atoi(env)));
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
+    if (const char *env = getenv("SMX_TEST_TINY_CAPS")) c->tiny_caps = atoi(env) != 0;
     if (const char *env = getenv("SMX_OVERLAP_START")) c->overlap_start = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;

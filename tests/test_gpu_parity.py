@@ -409,3 +409,26 @@ def test_cuda_trace_events_match_reference_stream(idx, tmp_path):
     case = TT.load_cases()[idx]
     got, _ops = TT.product_events(case, tmp_path, None)
     TT.compare(case, got)
+
+
+@pytest.mark.parametrize("cfg,n,derep", [("dense", 6000, "none"), ("dense", 6000, "best"), ("multipool", 5000, "none"),
+                                         ("ont037", 4000, "best")])
+def test_capacity_reruns_on_the_device(cfg, n, derep, monkeypatch):
+    """SMX_TEST_TINY_CAPS starts the work-entry, record-pool and compaction buffers far too small, so every
+    capacity re-run of the library (entries -> stage 1 again, pool -> selection again, records -> scan +
+    compaction again, plus the second selection pass) happens on the device; the result must equal the
+    kernel simulator's, one-shot, as resident sub-batches and pipelined."""
+    monkeypatch.setenv("SMX_TEST_TINY_CAPS", "1")
+    ds = synth.CONFIGS[cfg](n_reads=n, seed=31, with_quals=False)
+    specimens, params, args = _setup(ds)
+    mt = MatchTables(specimens, params, dereplicate=derep, trim="tails")
+    blob = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].tobytes()
+    batch = PackedBatch.from_blob(blob, ds.offsets.astype(np.uint64), clip=ds.search_len)
+    sim = Matcher(mt, binding=H.hostsim_binding()).match(batch)
+    with Matcher(mt) as m:
+        for mode in ("one_shot", "pipelined", "again"):
+            m.set_pipeline_chunk(1024 if mode == "pipelined" else 0)
+            got = m.match(batch)
+            assert got.n_matched == sim.n_matched, mode
+            assert np.array_equal(got.rec_offset, sim.rec_offset), mode
+            assert got.records.tobytes() == sim.records.tobytes(), mode
