@@ -460,12 +460,7 @@ SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &
     o.nbest = (unsigned short)(nbest > 65535 ? 65535 : nbest);
 }
 
-// The primer half of a slot (cheap, the same for every thread), and -- separately -- the digest of
-// its barcode hit lists.  select_read_impl() first loads every slot's primer half, then digests the
-// MATCHED slots in a loop over "my k-th matched slot": reads of either orientation match different
-// slots, and a loop over slot indices left half of every warp idle at each iteration (ncu, k_select_fast:
-// 15 of 32 lanes active on average); indexed by rank, all lanes digest one slot per iteration.
-SMX_HD void load_end_primer(const SelectCtx &c, int strand, int primer, EndInfo &e) {
+SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
     const Tables &t = *c.t;
     const u64 idx = (u64)slot_index(t, strand, primer) * c.b->n_pad + c.read;
     const smx_primer_hit &ph = c.b->phit[idx];
@@ -473,11 +468,9 @@ SMX_HD void load_end_primer(const SelectCtx &c, int strand, int primer, EndInfo 
     e.matched = ph.distance >= 0;
     e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
     e.nhits = 0; e.bd = -1; e.nbest = 0; e.first_best = -1; e.first_ss = 0; e.first_mask = 0;
-}
-
-SMX_HD void load_end_barcodes(const SelectCtx &c, EndInfo &e) {
+    if (!e.matched) return;
     SlotSum ss;
-    summarize_slot(c, e.strand, e.primer, ss);
+    summarize_slot(c, strand, primer, ss);
     e.nhits = ss.nhits; e.bd = ss.bd; e.nbest = ss.nbest;
     e.first_best = ss.nhits ? (int)ss.first_best : -1; e.first_ss = ss.first_ss; e.first_mask = ss.first_mask;
 }
@@ -734,21 +727,8 @@ SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore
 
     Geo g = make_geo(n, t.L);
     bool irregular = !g.regular || read_is_flagged(b, c.read);
-    {
-        u64 matched_lo = 0, matched_hi = 0;             // slots 0..63 / 64..127
-        for (int s = 0; s < 2; ++s)
-            for (int p = 0; p < t.n_primers; ++p) {
-                const int slot = s * t.n_primers + p;
-                load_end_primer(c, s, p, ends[slot]);
-                if (ends[slot].matched) { if (slot < 64) matched_lo |= 1ull << slot; else matched_hi |= 1ull << (slot - 64); }
-            }
-        while (matched_lo | matched_hi) {
-            int slot;
-            if (matched_lo) { slot = lowest_bit64(matched_lo); matched_lo &= matched_lo - 1; }
-            else { slot = 64 + lowest_bit64(matched_hi); matched_hi &= matched_hi - 1; }
-            load_end_barcodes(c, ends[slot]);
-        }
-    }
+    for (int s = 0; s < 2; ++s)
+        for (int p = 0; p < t.n_primers; ++p) load_end(c, s, p, ends[s * t.n_primers + p]);
 
     // determine_orientation (demultiplex.py:602-638).  For regular reads the head-window test of a
     // forward-sense primer equals the tail-window match of its reverse complement on the other
