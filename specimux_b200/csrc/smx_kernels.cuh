@@ -439,28 +439,66 @@ SMX_HD bool sliced_eligible(const Tables &t, const Batch &b, u32 read) {
 // Stage 1 per (read, strand, primer) after the sliced pass: eligible reads decode their column
 // histories from tmix, every other read runs the classic search.  Returns the number of
 // equal-best end locations.
+// `ev` (optional, kFinishMaskWords words): receives the slot's equal-best end mask when it is short enough
+// to stay in registers, `have_ev` says so; the caller then writes the work entries from registers
+// instead of reading the mask back from memory (write_entries).
+constexpr int kFinishMaskWords = 4, kFinishMixWords = 8;
+
 template <typename W>
 SMX_HD int primer_finish_thread(const Tables &t, const Batch &b, u32 read, int strand, int primer,
-                                const u64 *peq, const u64 *peq_fw) {
+                                const u64 *peq, const u64 *peq_fw, u32 *ev = nullptr, bool *have_ev = nullptr) {
+    if (have_ev) *have_ev = false;
     if (!sliced_eligible(t, b, read)) return primer_search_thread<W>(t, b, read, strand, primer, peq, peq_fw);
     const u32 slot = slot_index(t, strand, primer);
     const u64 hit_idx = (u64)slot * b.n_pad + read;
     u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
     const u32 *mix = b.tmix + (u64)slot * t.nw2 * b.n_pad + read;
-    // pass 1: number of improvements (-> best) and the column of the last one (-> first equal-best end)
+    const bool in_regs = t.nw2 <= kFinishMixWords && t.mw <= kFinishMaskWords;
+    // pass 1: number of improvements (-> best) and the column of the last one (-> first equal-best end);
+    // the words stay in registers for pass 2 when there are few enough of them
+    u32 mw_[kFinishMixWords];
     int improvements = 0, first = 0;
-    for (int blk = 0; blk < t.nw2; ++blk) {
-        const u32 im = mix[(u64)blk * b.n_pad] >> 16;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int blk = 0; blk < kFinishMixWords; ++blk) {
+        mw_[blk] = (in_regs && blk < t.nw2) ? mix[(u64)blk * b.n_pad] : 0u;
+        const u32 im = mw_[blk] >> 16;
         improvements += popcount32(im);
         if (im) first = blk * 16 + 31 - count_leading_zeros32(im);
     }
+    if (!in_regs)
+        for (int blk = 0; blk < t.nw2; ++blk) {
+            const u32 im = mix[(u64)blk * b.n_pad] >> 16;
+            improvements += popcount32(im);
+            if (im) first = blk * 16 + 31 - count_leading_zeros32(im);
+        }
     const int best = (int)t.p_len[primer] - improvements;
     b.orient_hit[hit_idx] = 0;                          // eligible reads never need the explicit test
     smx_primer_hit h;
     h.distance = -1; h.n_locations = 0; h.first_start = 0; h.first_end = 0;
     int nloc = 0;
-    if (best <= t.p_k[primer]) {
-        // pass 2: equality bits from the last improvement on are the equal-best ends
+    const bool hit = best <= t.p_k[primer];
+    if (in_regs) {
+        // pass 2 from registers: equality bits from the last improvement on are the equal-best ends
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int mwi = 0; mwi < kFinishMaskWords; ++mwi) {
+            if (mwi >= t.mw) break;
+            u32 v = 0;
+            if (hit) {
+                v = (mw_[2 * mwi] & 0xFFFFu) | (mw_[2 * mwi + 1] << 16);
+                const int lo = mwi * 32;
+                if (lo + 32 <= first) v = 0;
+                else if (lo < first) v &= ~0u << (first - lo);
+            }
+            emask[(u64)mwi * b.n_pad] = v;
+            nloc += popcount32(v);
+            if (ev) ev[mwi] = v;
+        }
+        if (have_ev && ev) *have_ev = true;
+    } else if (hit) {
         for (int mwi = 0; mwi < t.mw; ++mwi) {
             u32 v = mix[(u64)(2 * mwi) * b.n_pad] & 0xFFFFu;
             if (2 * mwi + 1 < t.nw2) v |= mix[(u64)(2 * mwi + 1) * b.n_pad] << 16;
@@ -470,13 +508,15 @@ SMX_HD int primer_finish_thread(const Tables &t, const Batch &b, u32 read, int s
             emask[(u64)mwi * b.n_pad] = v;
             nloc += popcount32(v);
         }
+    } else {
+        for (int mwi = 0; mwi < t.mw; ++mwi) emask[(u64)mwi * b.n_pad] = 0;
+    }
+    if (hit) {
         const Geo g = make_geo((int)b.lengths[read], t.L);
         h.distance = (int16_t)best;
         h.n_locations = (uint16_t)nloc;
         h.first_end = g.woff + first + g.delta;
         h.first_start = h.first_end;                    // filled in by primer_start_thread
-    } else {
-        for (int mwi = 0; mwi < t.mw; ++mwi) emask[(u64)mwi * b.n_pad] = 0;
     }
     b.phit[hit_idx] = h;
     return nloc;
@@ -777,12 +817,13 @@ SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, 
 }
 
 // Work-entry bookkeeping of stage 1: entries [base, base + nloc) of `slot` for one matched read.
-SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u32 base) {
+// `ev`: the end mask in registers (primer_finish_thread), or nullptr to read it from memory.
+SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u32 base, const u32 *ev = nullptr) {
     b.ent_base[(u64)slot * b.n_pad + read] = base;
     const u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + read;
     u32 e = base;
     for (int mwi = 0; mwi < t.mw; ++mwi) {
-        u32 word = emask[(u64)mwi * b.n_pad];
+        u32 word = ev ? ev[mwi] : emask[(u64)mwi * b.n_pad];
         while (word) {
             int p = mwi * 32 + lowest_bit32(word);
             word &= word - 1;
@@ -901,8 +942,10 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     u32 cells = 0;
     int nloc = 0;
+    u32 ev[kFinishMaskWords];
+    bool have_ev = false;
     if (read < b.n_reads) {
-        nloc = primer_finish_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2]);
+        nloc = primer_finish_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2], ev, &have_ev);
         int n = (int)b.lengths[read];
         cells = (u32)(n < c_tables.L ? n : c_tables.L);                      // HW columns of this search
     }
@@ -924,7 +967,8 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
             s_wtot[kFinishBlock / 32] = base;
         }
         __syncthreads();
-        if (nloc) write_entries(c_tables, b, blockIdx.y, read, s_wtot[kFinishBlock / 32] + s_wtot[warp] + (u32)(incl - nloc));
+        if (nloc) write_entries(c_tables, b, blockIdx.y, read, s_wtot[kFinishBlock / 32] + s_wtot[warp] + (u32)(incl - nloc),
+                                have_ev ? ev : nullptr);
     }
     const int m = c_tables.p_len[primer];
     block_work_add(cells, (unsigned long long)m, &b.counters[0], (unsigned long long)((m + 31) >> 5), &b.counters[2], &s_acc);
