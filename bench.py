@@ -64,25 +64,53 @@ def dataset(name, n_reads, seed_shift):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Reads NVML in-process
+    (nvidia_ml_py); spawning `nvidia-smi` every 0.2 s from each of N ranks takes the driver's global lock often
+    enough to stretch the host-side CUDA calls of the e2e loop (measured at N = 8: 7.9 ms per step instead of ~2),
+    so the command-line tool is only the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.samples, self._stop, self._th = index, [], threading.Event(), None
+        self._nvml = self._handle = None
+        self.source = "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml, self._handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if r & bit else "Not Active"
+        return [str(sm), str(mx), "", hex(r), flag(n.nvmlClocksThrottleReasonHwSlowdown),
+                flag(n.nvmlClocksThrottleReasonHwThermalSlowdown), flag(n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                flag(n.nvmlClocksThrottleReasonSwPowerCap)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 8:
-                    self.samples.append(f)
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 8:
+                        self.samples.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -95,7 +123,7 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
         reasons = set()
         for s in self.samples:
@@ -103,7 +131,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": self.source}
 
 
 def dist_env():
@@ -264,7 +292,7 @@ def main():
     # keep the GPU under the same load until nvidia-smi has been polled a few times (its period is
     # ~0.2 s, the timed loops above take milliseconds); these extra runs are not part of any figure
     t_hold = time.perf_counter()
-    while len(clocks.samples) < 3 and time.perf_counter() - t_hold < 3.0:
+    while len(clocks.samples) < 5 and time.perf_counter() - t_hold < 3.0:
         matcher.match(batch, reuse=True)
     clocks.__exit__(None, None, None)
     barrier()
