@@ -158,7 +158,7 @@ struct smx_ctx {
     bool tiny_caps = false;                 // SMX_TEST_TINY_CAPS=1: see lane_upload
     bool overlap_start = true;              // start recovery beside the barcode search (SMX_OVERLAP_START=0 disables)
     bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
-    bool ramp = false;                      // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
+    int ramp = 0;   // 0 even split (default); 1 / 2: small first chunks (SMX_PIPELINE_RAMP), both measured no faster:                     // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
                                             // measured slower on config 2: 1.83 vs 1.76 ms, the extra chunks cost more
                                             // kernel-chain latency than the earlier first copy-out saves)
 };
@@ -661,7 +661,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
     if (const char *env = getenv("SMX_TEST_TINY_CAPS")) c->tiny_caps = atoi(env) != 0;
     if (const char *env = getenv("SMX_OVERLAP_START")) c->overlap_start = atoi(env) != 0;
-    if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env) != 0;
+    if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env);
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
     return SMX_OK;
@@ -904,14 +904,24 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
     // two chunks are a quarter and a half of the nominal size so that the copy-out engine starts
     // earlier.
     std::vector<u32> cuts{0};
-    if (c->ramp && (u64)n > 2ull * chunk) {
+    u32 k_total = (n + chunk - 1) / chunk;                     // chunks of the even split
+    if (c->ramp == 1 && (u64)n > 2ull * chunk) {
         const u32 c0 = ((chunk / 4) + 127u) & ~127u, c1 = ((chunk / 2) + 127u) & ~127u;
         cuts.push_back(c0);
         cuts.push_back(c0 + c1);
+        k_total = 0;
+    } else if (c->ramp == 2 && k_total >= 4) {
+        // same NUMBER of chunks as the even split, but the first two are a third and two thirds of the
+        // average and the others make up for it
+        const u32 avg = n / k_total;
+        const u32 c0 = ((avg / 3) + 127u) & ~127u, c1 = ((2 * avg / 3) + 127u) & ~127u;
+        cuts.push_back(c0);
+        cuts.push_back(c0 + c1);
+        k_total -= 2;
     }
     {
         const u32 rest = n - cuts.back();
-        const u32 k = (rest + chunk - 1) / chunk;
+        const u32 k = k_total ? k_total : (rest + chunk - 1) / chunk;
         const u32 per = (((rest + k - 1) / k) + 127u) & ~127u;
         while (cuts.back() < n) cuts.push_back((u32)std::min<u64>((u64)cuts.back() + per, n));
     }
