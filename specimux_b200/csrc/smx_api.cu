@@ -158,9 +158,10 @@ struct smx_ctx {
     bool tiny_caps = false;                 // SMX_TEST_TINY_CAPS=1: see lane_upload
     bool overlap_start = true;              // start recovery beside the barcode search (SMX_OVERLAP_START=0 disables)
     bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
-    int ramp = 0;   // 0 even split (default); 1 / 2: small first chunks (SMX_PIPELINE_RAMP), both measured no faster:                     // pipelined smx_match_batch: small first chunks (SMX_PIPELINE_RAMP=1 enables;
-                                            // measured slower on config 2: 1.83 vs 1.76 ms, the extra chunks cost more
-                                            // kernel-chain latency than the earlier first copy-out saves)
+    // pipelined smx_match_batch chunking (SMX_PIPELINE_RAMP): 0 = even split (default); 1 = two extra small
+    // chunks first (measured 1.83 vs 1.76 ms on config 2: the extra chunks cost more kernel-chain latency than
+    // the earlier first copy-out saves); 2 = same chunk count, first two chunks smaller (1.70 vs 1.70 ms)
+    int ramp = 0;
 };
 
 // `prio`: CUDA stream priority of the lane (lower number = served first).  Lanes are filled in index
