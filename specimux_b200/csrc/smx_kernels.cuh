@@ -855,7 +855,7 @@ template <int SW> SMX_HD u32 long_carry_in(u32 G, u32 P) {
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------
-// __global__ wrappers.  Tables live in __constant__ memory, Peq masks are staged once per block
+// __global__ wrappers.  Tables travel as __grid_constant__ parameters, Peq masks are staged once per block
 // in shared memory.
 
 // Tables and Batch travel as __grid_constant__ kernel parameters (constant bank, per launch), so
