@@ -159,6 +159,28 @@ typedef struct smx_record {
     uint8_t pad[2];
 } smx_record;               /* 64 bytes */
 
+/*
+ * Compact form of smx_record for output paths that never look at the four location pairs: in the
+ * reference those feed only --color highlighting (alignment.py:59-95) and the trace, while the
+ * per-specimen files need sample / names / trim extents / distance code / orientation
+ * (io_utils.py:233-268).  Half the bytes on the wire: the copy-out of the records is what bounds
+ * smx_match_batch with host buffers.
+ */
+typedef struct smx_record32 {
+    uint32_t read;
+    int32_t sample;
+    int32_t trim_start;
+    int32_t trim_end;
+    int16_t pool;
+    int16_t p1;
+    int16_t p2;
+    int8_t dist[4];
+    uint8_t resolution;
+    uint8_t flags;             /* bit 0: reverse, bit 1: trim_empty                               */
+    uint8_t candidate;
+    uint8_t pad[3];
+} smx_record32;             /* 32 bytes */
+
 /* Optional per-search detail (level-1 results), used by parity tests and trace emission.
  * Slot index: ((strand * n_primers + primer) * n_reads + read); strand 0 = read as given,
  * 1 = its reverse complement.  Coordinates are the values align_seq reports (alignment.py:49). */
@@ -208,6 +230,8 @@ typedef struct smx_results {
                                   end location, in no particular order; at most barcode_loc_cap entries are written */
     uint64_t barcode_loc_cap;
     uint64_t n_barcode_loc_hits; /* out: entries that exist (may exceed the capacity: call again with more)       */
+    smx_record32 *records32;   /* optional: when non-NULL (and `records` NULL) the records are returned in the
+                                  compact form; records_cap then counts smx_record32 entries                     */
 } smx_results;
 
 typedef struct smx_ctx smx_ctx;

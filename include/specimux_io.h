@@ -102,6 +102,9 @@ int smx_writer_open(const char *output_dir, const char *prefix, int is_fastq, co
  * missing qualities as 'I' (Q40; alignment.py:52-56). */
 int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *records, uint64_t n_records);
 
+/* Same for the compact record form (smx_record32: everything the files need, no location pairs). */
+int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *records, uint64_t n_records);
+
 /* Flushes every buffer and releases the writer.  Returns the first error seen, if any. */
 int smx_writer_close(smx_writer *w);
 

@@ -45,7 +45,8 @@ class SmxResults(C.Structure):
     _fields_ = [("rec_offset", u32p), ("records", C.c_void_p), ("records_cap", C.c_uint64),
                 ("n_records", C.c_uint64), ("n_matched", C.c_uint64), ("endmask_bits", C.c_void_p),
                 ("primer_hits", C.c_void_p), ("barcode_hits", C.c_void_p), ("orient_hits", C.c_void_p),
-                ("barcode_loc_hits", C.c_void_p), ("barcode_loc_cap", C.c_uint64), ("n_barcode_loc_hits", C.c_uint64)]
+                ("barcode_loc_hits", C.c_void_p), ("barcode_loc_cap", C.c_uint64), ("n_barcode_loc_hits", C.c_uint64),
+                ("records32", C.c_void_p)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<i4"), ("trim_end", "<i4"),
@@ -56,6 +57,10 @@ RECORD_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<i4
 PRIMER_HIT_DTYPE = np.dtype([("first_start", "<i4"), ("first_end", "<i4"), ("distance", "<i2"),
                              ("n_locations", "<u2")])
 BARCODE_HIT_DTYPE = np.dtype([("end_mask", "<u8"), ("search_start", "<i4"), ("distance", "<i2"), ("barcode", "<u2")])
+RECORD32_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<i4"), ("trim_end", "<i4"),
+                           ("pool", "<i2"), ("p1", "<i2"), ("p2", "<i2"), ("dist", "i1", (4,)), ("resolution", "u1"),
+                           ("flags", "u1"), ("candidate", "u1"), ("pad", "u1", (3,))])
+assert RECORD32_DTYPE.itemsize == 32
 BARCODE_LOC_HIT_DTYPE = np.dtype([("read", "<u4"), ("slot", "<u2"), ("location", "<u2"), ("hit", BARCODE_HIT_DTYPE)])
 assert BARCODE_LOC_HIT_DTYPE.itemsize == 24
 assert RECORD_DTYPE.itemsize == 64 and PRIMER_HIT_DTYPE.itemsize == 12 and BARCODE_HIT_DTYPE.itemsize == 16

@@ -89,6 +89,7 @@ struct Lane {
     DevBuf<unsigned short> ent_pos;
     DevBuf<u32> defer_list;
     DevBuf<smx_record> rec_stage, rec_pool, records;
+    DevBuf<smx_record32> records32;             // compact copy of `records` (only when the caller asks for it)
     DevBuf<unsigned char> big_scratch;
     // control block: 8 counters (4 work, matched, (u32,u32) overflow, (u32,u32) total/pool, hit overflow)
     // followed by the 2 * SMX_MAX_PRIMERS per-slot entry counts -- one memset, one read-back
@@ -112,7 +113,7 @@ struct Lane {
         rec_count.release(); rec_offset.release(); rec_offset_out.release(); ticket.release(); tile_status.release(); word_off.release();
         off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
         ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
-        ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release();
+        ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release(); records32.release();
         big_scratch.release(); counters.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr; h_slot_counts = nullptr;
@@ -542,6 +543,21 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     return SMX_OK;
 }
 
+// Copy-out of a lane's compacted records into the caller's array, full or compact form (asynchronous on `st`,
+// which must already be ordered after the lane's kernels).
+static int lane_copy_records(Lane &ln, smx_results *out, u64 rec_base, cudaStream_t st) {
+    if (!ln.n_records) return SMX_OK;
+    if (out->records) {
+        CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, (size_t)ln.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
+    } else if (out->records32) {
+        CU(ln.records32.ensure((size_t)ln.n_records));
+        k_pack_records32<<<(unsigned)((ln.n_records + 255) / 256), 256, 0, st>>>(ln.records.p, (u32)ln.n_records, ln.records32.p);
+        ++ln.launches;
+        CU(cudaMemcpyAsync(out->records32 + rec_base, ln.records32.p, (size_t)ln.n_records * sizeof(smx_record32), cudaMemcpyDeviceToHost, st));
+    }
+    return SMX_OK;
+}
+
 // The records are already compacted (k_scan_compact); what is left is the sub-batch's record offsets
 // in the caller's whole batch (asynchronous).
 static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
@@ -814,8 +830,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
             resident_bounds(c, i, r0, r1);
             if (out->rec_offset)
                 CU(cudaMemcpyAsync(out->rec_offset + r0, l.offsets_src, (size_t)(r1 - r0) * sizeof(u32), cudaMemcpyDeviceToHost, l.stream));
-            if (out->records && l.n_records)
-                CU(cudaMemcpyAsync(out->records + rec_base, l.records.p, (size_t)l.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, l.stream));
+            { int rc2 = lane_copy_records(l, out, rec_base, l.stream); if (rc2) return rc2; }
             rec_base += l.n_records;
         }
         for (int i = 0; i < c->resident_lanes; ++i) CU(cudaStreamSynchronize(c->lane[i].stream));
@@ -833,8 +848,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     cudaStream_t st = ln.stream;
     if (out->rec_offset)
         CU(cudaMemcpyAsync(out->rec_offset, b.rec_offset, ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    if (out->records && ln.n_records)
-        CU(cudaMemcpyAsync(out->records, b.records, ln.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
+    { int rc2 = lane_copy_records(ln, out, 0, st); if (rc2) return rc2; }
     // level-1 detail is stored padded ([slot][n_pad]) on the device and returned dense ([slot][n])
     if (out->primer_hits)
         CU(cudaMemcpy2DAsync(out->primer_hits, (size_t)n * sizeof(smx_primer_hit), b.phit,
@@ -963,9 +977,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
             if (out->rec_offset)
                 CU(cudaMemcpyAsync(out->rec_offset + r0, ln.offsets_src, (size_t)(r1 - r0) * sizeof(u32),
                                    cudaMemcpyDeviceToHost, ln.out_stream));
-            if (out->records && ln.n_records)
-                CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, ln.n_records * sizeof(smx_record),
-                                   cudaMemcpyDeviceToHost, ln.out_stream));
+            if ((r = lane_copy_records(ln, out, rec_base, ln.out_stream))) return r;
             CU(cudaEventRecord(ln.ev_drained, ln.out_stream));
             ln.drain_pending = true;
             mark(i, 3, ln.out_stream);

@@ -18,6 +18,7 @@
 namespace smx {
 
 static_assert(sizeof(smx_record) == 64, "smx_record layout");
+static_assert(sizeof(smx_record32) == 32, "smx_record32 layout");
 static_assert(sizeof(smx_primer_hit) == 12, "smx_primer_hit layout");
 static_assert(sizeof(smx_barcode_hit) == 16, "smx_barcode_hit layout");
 

@@ -750,6 +750,24 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
     return SMX_IO_OK;
 }
 
+int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *recs, uint64_t n_records) {
+    if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write32: null argument");
+    // widen into the full layout (locations unused by the writer) and take the common path
+    std::vector<smx_record> full((size_t)n_records);
+    for (uint64_t i = 0; i < n_records; ++i) {
+        const smx_record32 &c = recs[i];
+        smx_record &r = full[i];
+        memset(&r, 0, sizeof(r));
+        r.read = c.read; r.sample = c.sample; r.trim_start = c.trim_start; r.trim_end = c.trim_end;
+        r.pool = c.pool; r.p1 = c.p1; r.p2 = c.p2;
+        for (int k = 0; k < 4; ++k) r.dist[k] = c.dist[k];
+        r.resolution = c.resolution;
+        r.reverse = c.flags & 1; r.trim_empty = (c.flags >> 1) & 1;
+        r.candidate = c.candidate;
+    }
+    return smx_writer_write(w, blk, full.data(), n_records);
+}
+
 int smx_writer_close(smx_writer *w) {
     if (!w) return SMX_IO_OK;
     if (!w->threads.empty()) {

@@ -1391,6 +1391,21 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_compact(SMX_KARGS, u32 re
     }
 }
 
+// smx_record -> smx_record32 (drops the four location pairs) ahead of the copy-out.
+__global__ void __launch_bounds__(256) k_pack_records32(const smx_record *in, u32 n, smx_record32 *out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const smx_record r = in[i];
+    smx_record32 o;
+    o.read = r.read; o.sample = r.sample; o.trim_start = r.trim_start; o.trim_end = r.trim_end;
+    o.pool = r.pool; o.p1 = r.p1; o.p2 = r.p2;
+    o.dist[0] = r.dist[0]; o.dist[1] = r.dist[1]; o.dist[2] = r.dist[2]; o.dist[3] = r.dist[3];
+    o.resolution = r.resolution;
+    o.flags = (uint8_t)((r.reverse ? 1 : 0) | (r.trim_empty ? 2 : 0));
+    o.candidate = r.candidate; o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    out[i] = o;
+}
+
 // rec_offset of a sub-batch in the caller's whole batch (its records start at rec_base).
 __global__ void __launch_bounds__(256) k_rebase_offsets(const u32 *in, u32 n, u32 rec_base, u32 *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;

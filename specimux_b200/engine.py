@@ -138,10 +138,12 @@ class Matcher:
             pass
 
     # -- results allocation ---------------------------------------------------------------
-    def _alloc_results(self, n, detail, cap=None, reuse=False):
+    def _alloc_results(self, n, detail, cap=None, reuse=False, compact=False):
         t = self.tables
         cap = int(cap if cap is not None else n + n // 8 + 1024)
         res = _lib.SmxResults()
+        rec_dtype = _lib.RECORD32_DTYPE if compact else _lib.RECORD_DTYPE
+        rec_key = "rec32" if compact else "rec"
         if reuse is not None and reuse is not False:
             # pinned pool reused across calls: the previous call's result arrays are overwritten.
             # reuse=True: one pool per Matcher; reuse=<dict>: a pool owned by the caller (lets several
@@ -149,15 +151,18 @@ class Matcher:
             pool = reuse if isinstance(reuse, dict) else self.__dict__.setdefault("_result_pool", {})
             if pool.get("n", -1) < n + 1:
                 pool["n"], pool["off"] = n + 1, _lib.HostBuffer(n + 1, np.uint32)
-            if pool.get("cap", -1) < cap:
-                pool["cap"], pool["rec"] = cap, _lib.HostBuffer(cap, _lib.RECORD_DTYPE)
+            if pool.get("cap_" + rec_key, -1) < cap:
+                pool["cap_" + rec_key], pool[rec_key] = cap, _lib.HostBuffer(cap, rec_dtype)
             rec_offset = pool["off"].array[:n + 1]
-            records = pool["rec"].array[:cap]
+            records = pool[rec_key].array[:cap]
         else:
             rec_offset = np.empty(n + 1, dtype=np.uint32)
-            records = np.empty(cap, dtype=_lib.RECORD_DTYPE)
+            records = np.empty(cap, dtype=rec_dtype)
         res.rec_offset = _lib.ptr(rec_offset, _lib.u32p)
-        res.records = records.ctypes.data
+        if compact:
+            res.records32 = records.ctypes.data
+        else:
+            res.records = records.ctypes.data
         res.records_cap = cap
         ph = em = bh = oh = None
         if detail:
@@ -185,18 +190,19 @@ class Matcher:
         return out
 
     # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
-    def match(self, batch: PackedBatch, detail: bool = False, reuse=False) -> BatchResult:
+    def match(self, batch: PackedBatch, detail: bool = False, reuse=False, compact: bool = False) -> BatchResult:
         """`reuse=True` returns views into a pinned pool that the next reuse=True call overwrites;
-        `reuse=<dict>` uses (and grows) a caller-owned pool instead.  A context is not re-entrant:
-        calls from several threads are serialised here."""
+        `reuse=<dict>` uses (and grows) a caller-owned pool instead.  `compact=True` returns 32-byte
+        smx_record32 records (no location pairs: what the output-tree writer needs).  A context is not
+        re-entrant: calls from several threads are serialised here."""
         with self._lock:
-            return self._match_locked(batch, detail, reuse)
+            return self._match_locked(batch, detail, reuse, compact)
 
-    def _match_locked(self, batch, detail, reuse):
+    def _match_locked(self, batch, detail, reuse, compact=False):
         cb = batch.c_batch()
         cap = None
         while True:
-            res, rec_offset, records, ph, em, bh = self._alloc_results(batch.n_reads, detail, cap, reuse)
+            res, rec_offset, records, ph, em, bh = self._alloc_results(batch.n_reads, detail, cap, reuse, compact)
             if self._binding is not None:
                 rc = self._binding.hostsim_match_batch(self.tables.tables_ref(), self.tables.params_ref(),
                                                        C.byref(cb), C.byref(res))

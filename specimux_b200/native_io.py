@@ -23,7 +23,7 @@ strp = C.POINTER(C.c_char_p)
 
 EXPORTS = ["smx_io_abi_version", "smx_io_last_error", "smx_reader_open", "smx_reader_close", "smx_block_create",
            "smx_block_destroy", "smx_block_get", "smx_reader_next", "smx_reader_skip", "smx_writer_open",
-           "smx_writer_write", "smx_writer_close", "smx_writer_stats"]
+           "smx_writer_write", "smx_writer_write32", "smx_writer_close", "smx_writer_stats"]
 
 
 class SmxBlockView(C.Structure):
@@ -67,6 +67,7 @@ def load():
         lib.smx_reader_skip.argtypes = [C.c_void_p, C.c_uint64, u64p]
         lib.smx_writer_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(SmxNames), C.POINTER(C.c_void_p)]
         lib.smx_writer_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.smx_writer_write32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.smx_writer_close.argtypes = [C.c_void_p]
         lib.smx_writer_stats.argtypes = [C.c_void_p, u64p, u64p]
         lib.smx_writer_stats.restype = None
@@ -234,9 +235,13 @@ class TreeWriter:
                                          C.byref(self._h)))
 
     def write(self, block: ReadBlock, records: np.ndarray):
-        assert records.dtype == _lib.RECORD_DTYPE
+        """records: smx_record (RECORD_DTYPE) or the compact smx_record32 (RECORD32_DTYPE)."""
         rec = np.ascontiguousarray(records)
-        _check(self._lib.smx_writer_write(self._h, block.handle, rec.ctypes.data, len(rec)))
+        if rec.dtype == _lib.RECORD32_DTYPE:
+            _check(self._lib.smx_writer_write32(self._h, block.handle, rec.ctypes.data, len(rec)))
+        else:
+            assert rec.dtype == _lib.RECORD_DTYPE
+            _check(self._lib.smx_writer_write(self._h, block.handle, rec.ctypes.data, len(rec)))
 
     def stats(self):
         n, b = C.c_uint64(0), C.c_uint64(0)

@@ -299,7 +299,7 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             if job is None:
                 return
             try:
-                job.result = matchers[dev].match(job.batch, reuse=job.pool)
+                job.result = matchers[dev].match(job.batch, reuse=job.pool, compact=True)     # the writer needs no locations
             except BaseException as e:          # surfaced by the writer thread in submission order
                 job.error = e
             job.done.set()

@@ -288,6 +288,19 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     }
     if (out->rec_offset) memcpy(out->rec_offset, rec_offset.data(), (size_t)(n + 1) * sizeof(u32));
     if (out->records && total) memcpy(out->records, records.data(), total * sizeof(smx_record));
+    if (!out->records && out->records32)
+        for (u64 i = 0; i < total; ++i) {           // what k_pack_records32 does
+            const smx_record &r = records[i];
+            smx_record32 o;
+            memset(&o, 0, sizeof(o));
+            o.read = r.read; o.sample = r.sample; o.trim_start = r.trim_start; o.trim_end = r.trim_end;
+            o.pool = r.pool; o.p1 = r.p1; o.p2 = r.p2;
+            for (int k = 0; k < 4; ++k) o.dist[k] = r.dist[k];
+            o.resolution = r.resolution;
+            o.flags = (uint8_t)((r.reverse ? 1 : 0) | (r.trim_empty ? 2 : 0));
+            o.candidate = r.candidate;
+            out->records32[i] = o;
+        }
     // level-1 detail is kept padded ([row][n_pad]) and returned dense ([row][n])
     if (out->primer_hits)
         for (size_t row = 0; row < (size_t)2 * nP; ++row)

@@ -182,6 +182,15 @@ def test_native_writer_tree_equals_python_output_manager(tmp_path, name, run_nam
             n_rec += len(res.records)
         assert wr.stats()[0] == n_rec == len(ops)
     assert _tree(native_dir) == _tree(args.output_dir)
+    # the compact record form (smx_record32, no location pairs) gives the same tree
+    compact_dir = str(tmp_path / "compact")
+    with native_io.FastxReader(fq, True) as rd, native_io.TreeWriter(compact_dir, "pre_", True, matcher.tables) as wr:
+        blk = native_io.ReadBlock()
+        while rd.next_block(97, blk).n_reads:
+            res = matcher.match(PackedBatch.from_block(blk, clip=params.search_len), compact=True)
+            assert res.records.dtype.itemsize == 32
+            wr.write(blk, res.records)
+    assert _tree(compact_dir) == _tree(args.output_dir)
 
 
 def test_native_writer_fasta_input_and_console_form(tmp_path, capfd):
