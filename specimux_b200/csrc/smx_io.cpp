@@ -310,7 +310,8 @@ void smx_block_get(const smx_block *b, smx_block_view *out) {
     out->n_reads = b->n();
     out->bases = b->bases.data();
     out->seq_off = b->seq_off.data();
-    out->quals = b->has_qual ? b->quals.data() : nullptr;
+    static const char kEmpty[1] = {0};
+    out->quals = b->has_qual ? (b->quals.empty() ? kEmpty : b->quals.data()) : nullptr;     // FASTQ with no bases at all: still "has qualities"
     out->titles = b->titles.data();
     out->title_off = b->title_off.data();
     out->id_start = b->id_start.data();

@@ -285,3 +285,57 @@ def test_native_pipeline_num_seqs_and_start(tmp_path):
     for v in _tree(args.output_dir).values():
         ids.update(l.split()[0][1:] for l in v.decode().split("\n")[0::4] if l)
     assert ids <= {r[0] for r in g["reads"][5:15]} and ids
+
+
+def test_fastq_reader_agrees_with_python_parser_on_random_text(tmp_path):
+    """Random files out of well-formed and damaged FASTQ records: both parsers return the same records or both
+    raise ValueError (the native one never crashes, never silently differs)."""
+    rng = np.random.default_rng(123)
+
+    def rnd(n, alphabet):
+        return "".join(rng.choice(list(alphabet), size=n)) if n else ""
+
+    def record():
+        n = int(rng.integers(0, 40))
+        seq, qual = rnd(n, "ACGTNacgu"), rnd(n, "!#5?I~")
+        # ASCII only here: the native reader compares sequence / quality lengths in BYTES, Python in characters, which
+        # differs only when a damaged file makes a non-ASCII title line part of a sequence or quality (documented)
+        title = rng.choice(["r%d" % rng.integers(0, 99), "r x\ty", "", " lead", "a b  c "])
+        form = rng.random()
+        if form < 0.55:
+            lines = ["@" + title, seq, "+", qual]
+        elif form < 0.65 and n > 4:                              # wrapped sequence and quality
+            k = int(rng.integers(1, n))
+            lines = ["@" + title, seq[:k], seq[k:], "+" + title, qual[:k], qual[k:]]
+        elif form < 0.72:
+            lines = ["@" + title, seq + " ", "+", " " + qual, "", "  "]      # padding, blank lines after
+        elif form < 0.80:
+            lines = ["@" + title, seq, "+", qual[:-1] if n else "I"]          # length mismatch
+        elif form < 0.86:
+            lines = [title, seq, "+", qual]                                 # no '@'
+        elif form < 0.92:
+            lines = ["@" + title, seq, qual]                                # no '+' line
+        else:
+            lines = ["@" + title, seq, "+", "@" + qual[1:] if n else ""]      # quality starting with '@'
+        return lines
+
+    agree = raised = 0
+    for trial in range(300):
+        lines = []
+        for _ in range(int(rng.integers(1, 6))):
+            lines += record()
+        eol = "\r\n" if rng.random() < 0.2 else "\n"
+        text = eol.join(lines) + (eol if rng.random() < 0.7 else "")
+        path = str(tmp_path / ("f%d.fastq" % trial))
+        with open(path, "wb") as fh:
+            fh.write(text.encode("latin-1"))
+        try:
+            want = _python_records(path, "fastq")
+        except ValueError:
+            with pytest.raises(ValueError):
+                _native_records(path, True)
+            raised += 1
+            continue
+        assert _native_records(path, True) == want, repr(text)
+        agree += 1
+    assert agree > 60 and raised > 60, (agree, raised)
