@@ -1033,6 +1033,9 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
 
     // ---- forward HW pass over the staged window [g.start, g.wl)
     const int p_begin = g.start, cols = valid ? g.wl - g.start : 0;
+    const u32 *wwin = b.win + (u64)strand * t.wpw * b.n_pad + (valid ? read : 0);     // this read's 4-bit window words
+    u32 wcur = 0;
+    int wcur_idx = -1;
     if (valid && top) for (int w = 0; w < t.mw; ++w) { emask[(u64)w * b.n_pad] = 0; imask[(u64)w * b.n_pad] = 0; }
     u32 Pv = ~0u, Mv = 0u;
     int score = m, best = m + 1;
@@ -1043,7 +1046,11 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
         for (int j = 0; j < maxcols; ++j) {
             const bool active = j < cols;
             const int p = p_begin + j;
-            const int c = active ? staged_sym(t, b, read, strand, p) : kSymOther;
+            int c = kSymOther;
+            if (active) {                                   // one window word per 8 columns, not one load per column
+                if ((p >> 3) != wcur_idx) { wcur_idx = p >> 3; wcur = wwin[(u64)wcur_idx * b.n_pad]; }
+                c = (int)((wcur >> (4 * (p & 7))) & 15u);
+            }
             const u32 sPv = Pv, sMv = Mv;
             const int d = long_step<SW, false>(s_peq[0][c * SW + sub], Pv, Mv, sub, lane);
             if (!active) { Pv = sPv; Mv = sMv; }
@@ -1079,7 +1086,12 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
         int rs = m, last = m - 1;
         for (int j = 0; j < maxr; ++j) {
             const bool active = j < rcols;
-            const int c = active ? staged_sym(t, b, read, strand, first - j) : kSymOther;
+            int c = kSymOther;
+            if (active) {
+                const int p = first - j;
+                if ((p >> 3) != wcur_idx) { wcur_idx = p >> 3; wcur = wwin[(u64)wcur_idx * b.n_pad]; }
+                c = (int)((wcur >> (4 * (p & 7))) & 15u);
+            }
             const u32 sPv = Pv, sMv = Mv;
             const int d = long_step<SW, true>(s_peq[1][c * SW + sub], Pv, Mv, sub, lane);
             if (!active) { Pv = sPv; Mv = sMv; }
