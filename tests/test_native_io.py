@@ -339,3 +339,22 @@ def test_fastq_reader_agrees_with_python_parser_on_random_text(tmp_path):
         assert _native_records(path, True) == want, repr(text)
         agree += 1
     assert agree > 60 and raised > 60, (agree, raised)
+
+
+def test_compact_records_are_the_projection_of_full_records():
+    """smx_record32 == smx_record minus the four location pairs, field by field (kernel simulator here; the CUDA
+    library's k_pack_records32 is compared against the same simulator output in the GPU tier through the CLI trees)."""
+    g = H.load_golden("synth_dense")
+    run = g["runs"]["derep_none"]
+    specimens = H.build_specimens(g["primers"], g["specimens"])
+    params = H.params_from_run(run, specimens)
+    args = H.make_args(run["flags"])
+    matcher = get_matcher(params, specimens, args, H.prefilter_for(args), 0, H.hostsim_binding())
+    batch = PackedBatch([r[1] for r in g["reads"]], clip=params.search_len)
+    full = matcher.match(batch).records
+    lite = matcher.match(batch, compact=True).records
+    assert len(full) == len(lite) > len(g["reads"]) // 2
+    for name in ("read", "sample", "trim_start", "trim_end", "pool", "p1", "p2", "resolution", "candidate"):
+        assert np.array_equal(full[name], lite[name]), name
+    assert np.array_equal(full["dist"], lite["dist"])
+    assert np.array_equal(lite["flags"] & 1, full["reverse"]) and np.array_equal((lite["flags"] >> 1) & 1, full["trim_empty"])
