@@ -40,7 +40,12 @@ def revcomp(s):
 
 WriteOp = namedtuple("WriteOp", "sample_id seq_id distance_code sequence quality_sequence "
                                 "p1_location p2_location b1_location b2_location "
-                                "primer_pool p1_name p2_name resolution_type")
+                                "primer_pool p1_name p2_name resolution_type "
+                                "trim_start trim_end is_rc trim_empty",
+                     defaults=(None, None, None, None))
+# trim_start / trim_end / is_rc / trim_empty are intermediate values of create_write_operation
+# (demultiplex.py:39-43,47,74; match.sequence is seq or rseq, :703,724) exposed so that the record-level
+# parity tests can compare them with smx_record without re-deriving them from the sliced strings.
 
 
 class Primer:
@@ -98,6 +103,12 @@ class Tables:
             if pool not in active:
                 del self.pool_primers[pool]
         self._pairs = {}
+        # lookup indexes (same answers as the reference's linear scans, databases.py:219-245,266-271)
+        self._rows_by_bc = {}
+        self._pool_by_sid = {}
+        for i, row in enumerate(self.specimens):
+            self._rows_by_bc.setdefault((row[2], row[4]), []).append(i)
+            self._pool_by_sid.setdefault(row[0], row[1])
 
     def _resolve(self, name, pool, direction):   # databases.py:197-217
         if name in ("-", "*"):
@@ -123,21 +134,24 @@ class Tables:
                                           if q.direction != primer.direction and q.specimens & primer.specimens]
         return self._pairs[primer.primer]
 
-    def specimen_pool(self, sid):                # databases.py:266-271
-        for row in self.specimens:
-            if row[0] == sid:
-                return row[1]
-        return None
+    def specimen_pool(self, sid):                # databases.py:266-271 (first row with that id)
+        return self._pool_by_sid.get(sid)
 
-    def exact_specimen(self, b1, b2, p1, p2):    # databases.py:232-245 (identity test on primer objects)
-        for sid, _pool, sb1, p1s, sb2, p2s in self.specimens:
-            if any(p1 is x for x in p1s) and any(p2 is x for x in p2s) and sb1 == b1 and sb2 == b2:
+    def exact_specimen(self, b1, b2, p1, p2):    # databases.py:232-245 (identity test on primer objects;
+        for i in self._rows_by_bc.get((b1, b2), ()):     # first row in file order, via the (b1, b2) index)
+            sid, _pool, _sb1, p1s, _sb2, p2s = self.specimens[i]
+            if any(p1 is x for x in p1s) and any(p2 is x for x in p2s):
                 return sid
         return None
 
-    def specimens_for(self, b1_list, b2_list, p1, p2):   # databases.py:219-230
-        return [sid for sid, _pool, sb1, p1s, sb2, p2s in self.specimens
-                if any(p1 is x for x in p1s) and any(p2 is x for x in p2s) and sb1 in b1_list and sb2 in b2_list]
+    def specimens_for(self, b1_list, b2_list, p1, p2):   # databases.py:219-230 (file order)
+        rows = sorted({i for b1 in b1_list for b2 in b2_list for i in self._rows_by_bc.get((b1, b2), ())})
+        out = []
+        for i in rows:
+            sid, _pool, _sb1, p1s, _sb2, p2s = self.specimens[i]
+            if any(p1 is x for x in p1s) and any(p2 is x for x in p2s):
+                out.append(sid)
+        return out
 
 
 class Params:
@@ -541,7 +555,7 @@ def make_write_op(params, sample_id, seq_id, bases, quals, c, res):
         if s >= e:                                                # :47-73 empty-trim fallback
             p1l, p2l, b1l, b2l = locs()
             return WriteOp("unknown", seq_id, c.distance_code(), bases, quals, p1l, p2l, b1l, b2l,
-                           "unknown", "unknown", "unknown", UNKNOWN)
+                           "unknown", "unknown", "unknown", UNKNOWN, 0, len(bases), c.is_rc, True)
         bases = bases[s:e]
         quals = quals[s:e] if quals is not None else None
         c.shift(s)
@@ -549,7 +563,7 @@ def make_write_op(params, sample_id, seq_id, bases, quals, c, res):
     return WriteOp(sample_id, seq_id, c.distance_code(), bases, quals, p1l, p2l, b1l, b2l,
                    c.pool if c.pool else "unknown",
                    c.p1.name if c.p1 is not None else "unknown",
-                   c.p2.name if c.p2 is not None else "unknown", res)
+                   c.p2.name if c.p2 is not None else "unknown", res, s, e, c.is_rc, False)
 
 
 def process_read(tables, params, seq_id, bases, quals):

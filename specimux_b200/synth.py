@@ -343,4 +343,29 @@ def dense_grid(n_reads=2_000_000, seed=5, with_quals=True) -> SynthDataset:
     return _build("dense", primers, rows, struct, n_reads, seed, _normal_insert(640, 60, 50), 0.12, 80, with_quals)
 
 
-CONFIGS = {"ont037": ont037, "multipool": multipool, "long": long_amplicon, "dense": dense_grid}
+def tie_storm(n_reads=40_000, seed=11, with_quals=True) -> SynthDataset:
+    """Stress case of the parity tests (not a BASELINE config): a 96 x 96 grid whose barcodes are 1-2
+    substitutions away from six seed 13-mers, to be searched with a forced k_idx = 3.  Every flank is then
+    within k of a dozen or more barcodes: hit sub-lists overflow, equal-best ties map to many specimens
+    (dereplication groups beyond the thread-local storage, many records per read)."""
+    rng = np.random.default_rng(seed)
+
+    def family(count):
+        out, seen = [], set()
+        seeds = rng.integers(0, 4, size=(6, 13), dtype=np.uint8)
+        while len(out) < count:
+            v = seeds[len(out) % 6].copy()
+            for pos in rng.choice(13, size=int(rng.integers(1, 3)), replace=False):
+                v[pos] = (v[pos] + rng.integers(1, 4)) & 3
+            sv = "".join("ACGT"[c] for c in v)
+            if sv not in seen:
+                seen.add(sv)
+                out.append(sv)
+        return out
+    fb, rb = family(96), family(96)
+    primers = [("ITS1F", ITS1F, "forward", ["ITS"]), ("ITS4", ITS4, "reverse", ["ITS"])]
+    rows, struct = _grid_specimens("TIE", "ITS", fb, rb, "ITS1F", "ITS4", ITS1F, ITS4)
+    return _build("tiestorm", primers, rows, struct, n_reads, seed, _normal_insert(640, 60, 50), 0.05, 80, with_quals)
+
+
+CONFIGS = {"tiestorm": tie_storm, "ont037": ont037, "multipool": multipool, "long": long_amplicon, "dense": dense_grid}

@@ -1,0 +1,17 @@
+"""CPU tier of the full-config parity machinery (tests/fullcfg.py): the same record-for-record comparison
+with the multi-process oracle, at small sizes, through the kernel simulator."""
+import pytest
+
+import fullcfg
+import helpers as H
+
+
+@pytest.mark.parametrize("cfg,n,flags,kw", [
+    ("ont037", 1500, {}, {}),
+    ("multipool", 800, {"dereplicate": "none"}, {"sprinkle": 1500}),
+    ("long", 400, {}, {"search_len": 500}),
+    ("tiestorm", 500, {"trim": "tails"}, {"index_edit_distance": 3, "sprinkle": 3000}),
+])
+def test_records_equal_multiprocess_oracle(cfg, n, flags, kw):
+    fig = fullcfg.compare(cfg, n, flags, binding=H.hostsim_binding(), processes=2, **kw)
+    assert fig["records"] >= n
