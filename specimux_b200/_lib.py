@@ -138,38 +138,33 @@ def ptr(arr, typ):
 
 class HostBuffer:
     """numpy view over pinned host memory (cudaHostAlloc through the library); falls back to ordinary
-    pageable memory when no GPU driver is present (packing still works on a CPU-only box)."""
+    pageable memory when no GPU driver is present (packing still works on a CPU-only box).
+
+    The pinned block belongs to the views: it is released (cudaFreeHost) when the last numpy array that looks
+    into it has gone, not when this object is dropped or `free()`d -- a result handed to another thread stays
+    valid after the pool that produced it has grown a new buffer."""
 
     def __init__(self, count, dtype):
+        import weakref
         dtype = np.dtype(dtype)
         self.nbytes = max(1, int(count) * dtype.itemsize)
-        self._ptr = None
+        self.pinned = False
         try:
-            p = load().smx_host_alloc(self.nbytes)
+            lib = load()
+            p = lib.smx_host_alloc(self.nbytes)
         except Exception:
             p = None
         if p:
-            self._ptr = p
+            self.pinned = True
             raw = (C.c_char * self.nbytes).from_address(p)
+            weakref.finalize(raw, lib.smx_host_free, p)
             self.array = np.frombuffer(raw, dtype=dtype, count=int(count))
         else:
             self.array = np.empty(int(count), dtype=dtype)
 
-    @property
-    def pinned(self):
-        return self._ptr is not None
-
     def free(self):
-        if self._ptr is not None:
-            self.array = None
-            load().smx_host_free(self._ptr)
-            self._ptr = None
-
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
+        """Drops this object's own view (the memory goes when every other view has gone too)."""
+        self.array = None
 
 
 def bind_thread_to_gpu_numa_node(device: int):

@@ -14,6 +14,7 @@
 
 #include "smx_host_tables.hpp"
 #include "smx_kernels.cuh"
+#include "smx_launch.hpp"
 
 using namespace smx;
 
@@ -85,6 +86,7 @@ struct Lane {
     DevBuf<smx_primer_hit> phit;
     DevBuf<unsigned char> orient_hit, read_flags, bh_count;
     DevBuf<smx_barcode_hit> bh_list;
+    DevBuf<BarcodeDigest> bdig;
     DevBuf<u32> ent_base, ent_read, rec_extra, big_list;
     DevBuf<unsigned short> ent_pos;
     DevBuf<u32> defer_list;
@@ -111,7 +113,7 @@ struct Lane {
     void release() {
         packed2.release(); lengths.release(); packed4.release(); win.release(); win2.release(); tmix.release(); endmask.release(); impmask.release();
         rec_count.release(); rec_offset.release(); rec_offset_out.release(); ticket.release(); tile_status.release(); word_off.release();
-        off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release();
+        off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release(); bdig.release();
         ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
         ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release(); records32.release();
         big_scratch.release(); counters.release();
@@ -137,7 +139,10 @@ struct smx_ctx {
     DevBuf<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
     DevBuf<unsigned char> b_len, bw_len, bw_primer;
     DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq, peq_long;
-    DevBuf<unsigned short> bw_list;
+    DevBuf<unsigned short> bw_list, bt_g0, bt_class_tasks;
+    DevBuf<unsigned char> bt_nw;
+    DevBuf<u32> bt_row, bt_eq;
+    u32 bt_class_off[kMaxTaskWords + 1] = {};
     DevBuf<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
     std::vector<unsigned char> prow_code;   // [primer][32] pattern row codes (sliced primer search)
@@ -195,10 +200,11 @@ static cudaError_t ensure_entry_buffers(smx_ctx *c, Lane &ln) {
     if ((e = ln.ent_pos.ensure((size_t)2 * t.n_primers * ln.e_cap)) != cudaSuccess) return e;
     if ((e = ln.bh_count.ensure((size_t)2 * t.n_bwords * ln.e_cap + 1)) != cudaSuccess) return e;
     if ((e = ln.bh_list.ensure((size_t)2 * t.n_bwords * ln.hit_cap * ln.e_cap + 1)) != cudaSuccess) return e;
+    if ((e = ln.bdig.ensure((size_t)2 * t.n_btasks * ln.e_cap + 1)) != cudaSuccess) return e;
     if ((e = ln.rec_pool.ensure(ln.pool_cap)) != cudaSuccess) return e;
     Batch &b = ln.b;
     b.e_cap = ln.e_cap; b.pool_cap = ln.pool_cap;
-    b.ent_read = ln.ent_read.p; b.ent_pos = ln.ent_pos.p; b.bh_count = ln.bh_count.p; b.bh_list = ln.bh_list.p;
+    b.ent_read = ln.ent_read.p; b.ent_pos = ln.ent_pos.p; b.bh_count = ln.bh_count.p; b.bh_list = ln.bh_list.p; b.bdig = ln.bdig.p;
     b.rec_pool = ln.rec_pool.p;
     return cudaSuccess;
 }
@@ -313,7 +319,7 @@ static cudaError_t enqueue_scan_compact(smx_ctx *c, Lane &ln) {
     const unsigned tiles = (n + kScanTile - 1) / kScanTile;
     ln.epoch = ln.epoch % ((1u << 30) - 1u) + 1u;
     const u32 cap = (u32)std::min<size_t>(ln.records.cap, 0xFFFFFFFFu);
-    k_scan_compact<<<tiles, kScanThreads, 0, st>>>(lane_tables(c, ln), b, cap, ln.tile_status.p, ln.ticket.p, ln.tickets_issued, ln.epoch);
+    if ((e = launch_scan_compact(lane_tables(c, ln), b, cap, ln.tile_status.p, ln.ticket.p, ln.tickets_issued, ln.epoch, st)) != cudaSuccess) return e;
     ln.tickets_issued += tiles;
     ++ln.launches;
     if ((e = cudaMemcpyAsync(ln.h_counters, ln.counters.p, kCtlWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
@@ -337,17 +343,12 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     const int nP = t.n_primers;
     cudaStream_t st = ln.stream;
 #define KMARK(i) do { if (timed) CU(cudaEventRecord(ln.kev[i], st)); } while (0)
-    bool start_forked = false;
-    const unsigned blocks = (n + 127) / 128;
+    (void)n;
     if (from <= 0) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
         if (timed) CU(cudaEventRecord(ln.ev[0], st));
         KMARK(0);
-        // shared-memory tile: 128 reads x the words of a clipped read (+1 word of slack per read, +2 per tile)
-        u32 tile_words = 0;
-        if (b.clip) tile_words = (u32)kStageBlock * ((2 * b.clip + 15) / 16 + 1) + 2;
-        if (tile_words * sizeof(u32) > 48u * 1024u) tile_words = 0;           // beyond the default dynamic limit: direct loads
-        k_stage_windows<<<(n + kStageBlock - 1) / kStageBlock, dim3(kStageBlock, 2), tile_words * sizeof(u32), st>>>(t, b, tile_words);
+        CU(launch_stage_windows(t, b, st));
         ++ln.launches;
     }
     if (from <= 1) {   // stage 1
@@ -358,28 +359,12 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
             // forward pass bit-sliced across reads, one launch per primer (pattern length = template)
             // The primers' kernels are independent and each fills only ~2.5 warps per scheduler at
             // 765k reads, so they run concurrently on auxiliary streams (fork / join on events).
-            dim3 sgrid((b.n_pad / 32 + kSlicedBlock - 1) / kSlicedBlock, 2);
             const bool fork = nP > 1;
             if (fork) CU(cudaEventRecord(ln.ev_fork, st));
             for (int p = 0; p < nP; ++p) {
                 cudaStream_t ps = fork ? ln.aux[p % kAuxStreams] : st;
                 if (fork && p < kAuxStreams) CU(cudaStreamWaitEvent(ps, ln.ev_fork, 0));
-                RowOffsets ro;
-                bool degenerate = false;
-                for (int i = 0; i < 32; ++i) {
-                    int code = i < t.p_len[p] ? c->prow_code[(size_t)p * 32 + i] : 0;
-                    degenerate |= code > 3;
-                    ro.off[i] = (unsigned short)(code * kSlicedBlock * sizeof(u32));
-                }
-                switch (t.p_len[p]) {
-#define SMX_M(MM) case MM: k_primer_sliced<MM><<<sgrid, kSlicedBlock, 0, ps>>>(t, b, p, ro, degenerate ? 1 : 0); break;
-                    SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
-                    SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
-                    SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
-                    SMX_M(32)
-#undef SMX_M
-                    default: return fail(SMX_ERR_INTERNAL, "sliced primer search: pattern length %d", (int)t.p_len[p]);
-                }
+                CU(launch_primer_sliced(t, b, p, c->prow_code.data() + (size_t)p * 32, ps));
                 ++ln.launches;
             }
             if (fork)
@@ -389,40 +374,15 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
                 }
         }
         KMARK(2);
-        dim3 grid((n + kFinishBlock - 1) / kFinishBlock, 2 * nP);
-        if (t.use64) k_primer_search<u64><<<grid, kFinishBlock, 0, st>>>(t, b);
-        else k_primer_search<u32><<<grid, kFinishBlock, 0, st>>>(t, b);
+        CU(launch_primer_finish(t, b, true, st));
         for (int p = 0; p < nP; ++p) {
             if (!t.p_sw[p]) continue;
             // long primer: warp-cooperative multi-word search, p_sw lanes per read
-            const int sw = t.p_sw[p];
-            dim3 lgrid((unsigned)(((u64)n * sw + 127) / 128), 2);
-            switch (sw) {
-                case 4: k_primer_long<4><<<lgrid, 128, 0, st>>>(t, b, p); break;
-                case 8: k_primer_long<8><<<lgrid, 128, 0, st>>>(t, b, p); break;
-                case 16: k_primer_long<16><<<lgrid, 128, 0, st>>>(t, b, p); break;
-                default: k_primer_long<32><<<lgrid, 128, 0, st>>>(t, b, p); break;
-            }
+            CU(launch_primer_long(t, b, p, st));
             ++ln.launches;
         }
         KMARK(3);
-        // Start recovery and the barcode search both consume the work entries and are independent of
-        // each other (selection needs both); neither fills the ALU pipe alone (ncu: 68 % / 80 %), so
-        // when this call also enqueues stage 2 the start recovery goes to an auxiliary stream and
-        // runs beside the barcode kernel.  A timed one-lane run keeps them back to back so that the
-        // per-kernel marks stay meaningful.
-        dim3 sgrid((b.e_cap + 127) / 128, 2 * nP);
-        cudaStream_t ss = st;
-        if (!timed && c->overlap_start) {
-            ss = ln.aux[0];
-            CU(cudaEventRecord(ln.ev_fork, st));
-            CU(cudaStreamWaitEvent(ss, ln.ev_fork, 0));
-            start_forked = true;
-        }
-        if (t.use64) k_primer_start<u64><<<sgrid, 128, 0, ss>>>(t, b);
-        else k_primer_start<u32><<<sgrid, 128, 0, ss>>>(t, b);
-        if (start_forked) CU(cudaEventRecord(ln.ev_join[0], ss));
-        ln.launches += 2;
+        ++ln.launches;
     }
     if (from <= 2) {   // stage 2
         if (from == 2) {                                                                                     // re-run
@@ -432,18 +392,8 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         }
         if (timed) CU(cudaEventRecord(ln.ev[2], st));
         KMARK(4);
-        if (t.n_bwords) {
-            dim3 grid((b.e_cap + 127) / 128, 2 * t.n_bwords);
-            switch (t.k_idx) {
-#define SMX_K2(KK) case KK: k_barcode_bitsliced<KK><<<grid, 128, 0, st>>>(t, b); break;
-                SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
-#undef SMX_K2
-                default: return fail(SMX_ERR_INTERNAL, "unsupported k_idx");
-            }
-            ++ln.launches;
-        }
+        if (t.n_btasks) CU(launch_barcode_tasks(t, b, c->bt_class_tasks.p, c->bt_class_off, st, &ln.launches));
     }
-    if (start_forked) CU(cudaStreamWaitEvent(st, ln.ev_join[0], 0));
     // stage 3: slot digests, single-pass selection, scan
     if (from >= 2) {                                                                                           // re-run
         CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
@@ -452,15 +402,9 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     if (timed) CU(cudaEventRecord(ln.ev[3], st));
     KMARK(5);
     // fast path for (nearly) every read, then the general routine over the reads it deferred
-    if (nP <= 8) {
-        k_select_fast<8><<<blocks, 128, 0, st>>>(t, b);
-        KMARK(6);
-        k_select<8><<<blocks, 128, 0, st>>>(t, b);
-    } else {
-        k_select_fast<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
-        KMARK(6);
-        k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
-    }
+    CU(launch_select_fast(t, b, st));
+    KMARK(6);
+    CU(launch_select(t, b, st));
     ln.launches += 2;
     KMARK(7);
     CU(enqueue_scan_compact(c, ln));
@@ -513,7 +457,7 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
             CU(ln.big_scratch.ensure(std::min<size_t>(chunk, n_big) * kBigScratchBytes));
             for (size_t off = 0; off < n_big; off += chunk) {
                 u32 cnt = (u32)std::min<size_t>(chunk, n_big - off);
-                k_select_big<<<(cnt + 31) / 32, 32, 0, st>>>(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p);
+                CU(launch_select_big(t, b, ln.big_list.p + off, cnt, ln.big_scratch.p, st));
                 ++ln.launches;
             }
             CU(reset_scan_counters(ln));
@@ -551,7 +495,7 @@ static int lane_copy_records(Lane &ln, smx_results *out, u64 rec_base, cudaStrea
         CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, (size_t)ln.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
     } else if (out->records32) {
         CU(ln.records32.ensure((size_t)ln.n_records));
-        k_pack_records32<<<(unsigned)((ln.n_records + 255) / 256), 256, 0, st>>>(ln.records.p, (u32)ln.n_records, ln.records32.p);
+        CU(launch_pack_records32(ln.records.p, (u32)ln.n_records, ln.records32.p, st));
         ++ln.launches;
         CU(cudaMemcpyAsync(out->records32 + rec_base, ln.records32.p, (size_t)ln.n_records * sizeof(smx_record32), cudaMemcpyDeviceToHost, st));
     }
@@ -567,7 +511,7 @@ static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
     if (timed) CU(cudaEventRecord(ln.kev[9], st));
     ln.offsets_src = b.rec_offset;
     if (rec_base) {
-        k_rebase_offsets<<<(b.n_reads + 255) / 256, 256, 0, st>>>(b.rec_offset, b.n_reads, rec_base, ln.rec_offset_out.p);
+        CU(launch_rebase_offsets(b.rec_offset, b.n_reads, rec_base, ln.rec_offset_out.p, st));
         ++ln.launches;
         ln.offsets_src = ln.rec_offset_out.p;
     }
@@ -609,6 +553,7 @@ void smx_destroy(smx_ctx *c) {
     c->pb_barcode.release(); c->pair_fwd.release(); c->pair_rev.release(); c->spec_key_off.release();
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release();
     c->shared_packed4.release(); c->l2_scratch.release(); c->peq_long.release();
+    c->bt_g0.release(); c->bt_nw.release(); c->bt_row.release(); c->bt_eq.release(); c->bt_class_tasks.release();
     delete c;
 }
 
@@ -658,6 +603,10 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->spec_pool, ht.spec_pool));
     CUC(upload(c->spec_dense, ht.spec_dense));
     CUC(upload(c->peq_long, ht.peq_long));
+    CUC(upload(c->bt_g0, ht.bt_g0)); CUC(upload(c->bt_nw, ht.bt_nw)); CUC(upload(c->bt_row, ht.bt_row));
+    CUC(upload(c->bt_eq, ht.bt_eq)); CUC(upload(c->bt_class_tasks, ht.bt_class_tasks));
+    for (int i = 0; i <= kMaxTaskWords; ++i) c->bt_class_off[i] = ht.bt_class_off[i];
+    ht.set_task_pointers(c->bt_g0.p, c->bt_nw.p, c->bt_row.p, c->bt_eq.p);
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
     ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,
                     c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
@@ -1115,8 +1064,7 @@ int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint3
     CU(cudaMemcpy(d_seq, seqs, bytes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_off, seq_off, (size_t)(n + 1) * sizeof(u32), cudaMemcpyHostToDevice));
     u64 total = (u64)n * n;
-    k_pairwise_nw<<<(unsigned)((total + 127) / 128), 128>>>(d_seq, d_off, n, d_out);
-    CU(cudaGetLastError());
+    CU(launch_pairwise_nw(d_seq, d_off, n, d_out, 0));
     CU(cudaMemcpy(out, d_out, total * sizeof(i32), cudaMemcpyDeviceToHost));
     cudaFree(d_seq); cudaFree(d_off); cudaFree(d_out);
     return SMX_OK;
@@ -1142,9 +1090,7 @@ int smx_int_alu_peak(int device, double out_tops[3]) {
         float best = 1e30f;
         for (int rep = 0; rep < 5; ++rep) {
             CU(cudaEventRecord(e0));
-            if (mode == 0) k_int_peak<0><<<blocks, threads>>>(d_out, iters, 17u + rep);
-            else if (mode == 1) k_int_peak<1><<<blocks, threads>>>(d_out, iters, 17u + rep);
-            else k_int_peak<2><<<blocks, threads>>>(d_out, iters, 17u + rep);
+            CU(launch_int_peak(mode, blocks, threads, d_out, iters, 17u + rep, 0));
             CU(cudaEventRecord(e1));
             CU(cudaEventSynchronize(e1));
             float ms = 0;

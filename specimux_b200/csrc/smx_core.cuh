@@ -31,6 +31,8 @@ constexpr int kNone = INT32_MIN;    // Python None in coordinates
 constexpr int kMaxPairs = 64;       // candidate slots per read = 2 * pairs
 constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in the first pass
 constexpr int kBigGroups = 4096;
+constexpr int kMaxTaskWords = 4;    // bwords one stage-2 thread evaluates side by side
+constexpr int kMaxTaskK = 4;        // largest k_idx with multi-word stage-2 tasks (beyond: one bword per task)
 // control block of a batch: kCtrWords 64-bit counters followed by the 2 * SMX_MAX_PRIMERS u32 per-slot entry counts
 constexpr int kCtrDeferred = 8;     // (u32) reads left to the general selection kernel
 constexpr int kCtrBig = 9;          // (u32) reads left to the second selection pass (k_select_big)
@@ -180,6 +182,14 @@ struct Tables {
     const u32 *bw_valid;               // [bword] mask of populated bit lanes
     const unsigned short *bw_list;     // [bword][32] position j in the primer's barcode list
     const u32 *beq;
+    // Stage-2 tasks: up to four bwords of one primer and one barcode length.  One thread evaluates a work
+    // entry against all words of its task (flank set-up shared, one vector table load per DP cell).
+    int n_btasks;
+    u32 bt_off[SMX_MAX_PRIMERS + 1];   // primer p owns tasks [bt_off[p], bt_off[p+1])
+    const unsigned short *bt_g0;       // [task] first bword
+    const unsigned char *bt_nw;        // [task] number of bwords (1..4)
+    const u32 *bt_row;                 // [task] word offset of the task's table in bt_eq
+    const u32 *bt_eq;                  // per task [row][16 symbols][S], S = 1, 2 or 4 (bt_nw rounded up to a power of two)
 
     const u32 *pair_fwd, *pair_rev;
     const i32 *pair_pool;
@@ -196,7 +206,7 @@ struct Tables {
 // Per-(slot, read) digest of the barcode hit lists, produced by the summary kernel so that the
 // selection stage does not walk the lists in the common case.
 struct SlotSum {
-    u64 first_mask;            // end mask of the first equal-best barcode
+    u64 first_mask;            // lowest equal-best end column of the first equal-best barcode, as a one-bit mask
     i32 first_ss;              // its barcode_search_start
     unsigned short first_best; // its list position
     unsigned short nhits;      // barcodes within k_idx (saturating)
@@ -205,6 +215,18 @@ struct SlotSum {
     unsigned char pad;
 };
 static_assert(sizeof(SlotSum) == 24, "SlotSum layout");
+
+// Digest of the barcode hits of one (work entry, stage-2 task), written by the barcode kernel so that the
+// selection stage reads 16 bytes per entry instead of walking the hit sub-lists in the common case.
+struct BarcodeDigest {
+    i32 search_start;          // barcode_search_start of this primer end location
+    unsigned short jmin, jmax; // smallest / largest list position among the hits at distance `bd`
+    unsigned short count;      // hits at distance `bd` (saturating)
+    signed char bd;            // smallest distance, -1 = no hit
+    unsigned char first_col;   // lowest equal-best SHW end column of the hit at jmin
+    u32 nhits;                 // hits within k_idx
+};
+static_assert(sizeof(BarcodeDigest) == 16, "BarcodeDigest layout");
 
 // Per-batch device buffers.
 struct Batch {
@@ -236,6 +258,7 @@ struct Batch {
     // Barcode hits of entry e for bword g, gslot = strand * n_bwords + g:
     unsigned char *bh_count; // [gslot * e_cap + e]; may exceed hit_cap (-> re-run with a larger cap)
     smx_barcode_hit *bh_list;    // [(gslot * hit_cap + h) * e_cap + e], ascending barcode position
+    BarcodeDigest *bdig;         // [(strand * n_btasks + task) * e_cap + e]
     u32 *defer_list;         // reads the fast selection kernel left to the general one (count: counters[kCtrDeferred])
     u32 *big_list;           // reads the general selection left to k_select_big (count: counters[kCtrBig])
     // single-pass selection: first record of every read + pool for the (rare) further records
@@ -361,7 +384,7 @@ SMX_HD void spec_all(const Tables &t, u32 b1, u32 b2, int p1, int p2, int &count
 // (demultiplex.py:126-210, 216-598; models.py:72-328).  One thread runs this per read.
 
 struct EndInfo {            // one (strand, primer) slot as seen by a candidate (kept small: it lives in local memory)
-    u64 first_mask;         // SHW end mask of the first equal-best barcode
+    u64 first_mask;         // lowest equal-best SHW end column of the first equal-best barcode (one-bit mask)
     int ps, pe;             // first primer location, reported X coordinates
     int first_ss;           // barcode_search_start of the first equal-best barcode
     int first_best;         // its list position (pinned order), -1 = none
@@ -417,7 +440,7 @@ SMX_HD bool next_hit(const SelectCtx &c, int strand, int primer, int after_j, sm
     return found;
 }
 
-// Digest of the hit lists of one matched slot in ONE pass over the per-(location, bword) sub-lists.
+// Digest of the barcode hits of one matched slot, merged from the per-(location, task) digests of stage 2.
 // A barcode found at several primer end locations keeps its strictly smallest distance, ties the
 // earliest location (demultiplex.py:786-812); the best distance over the merged barcodes is simply
 // the minimum over all hits, the equal-best barcodes are those with some hit at that distance, the
@@ -434,23 +457,21 @@ SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &
     u32 nloc = b.phit[hidx].n_locations;
     if (e0 >= b.e_cap) return;
     if (e0 + nloc > b.e_cap) nloc = b.e_cap - e0;
-    int bd = 1 << 20, nhits = 0, count = 0, jmin = 1 << 20, jmax = -1;
+    int bd = 1 << 20, count = 0, jmin = 1 << 20, jmax = -1;
+    u32 nhits = 0;
     for (u32 l = 0; l < nloc; ++l) {
         const u64 e = (u64)e0 + l;
-        for (u32 g = t.bw_off[primer]; g < t.bw_off[primer + 1]; ++g) {
-            const u64 gslot = (u64)strand * t.n_bwords + g;
-            int cnt = b.bh_count[gslot * b.e_cap + e];
-            if (cnt > t.hit_cap) cnt = t.hit_cap;
-            for (int x = 0; x < cnt; ++x) {
-                const smx_barcode_hit &h = b.bh_list[(gslot * t.hit_cap + x) * b.e_cap + e];
-                const int d = h.distance, j = (int)h.barcode;
-                ++nhits;
-                if (d < bd) { bd = d; count = 0; jmin = 1 << 20; jmax = -1; }
-                if (d == bd) {
-                    ++count;
-                    if (j < jmin) { jmin = j; o.first_best = h.barcode; o.first_mask = h.end_mask; o.first_ss = h.search_start; }
-                    if (j > jmax) jmax = j;
+        for (u32 tk = t.bt_off[primer]; tk < t.bt_off[primer + 1]; ++tk) {
+            const BarcodeDigest d = b.bdig[((u64)strand * t.n_btasks + tk) * b.e_cap + e];
+            if (!d.nhits) continue;
+            nhits += d.nhits;
+            if (d.bd < bd) { bd = d.bd; count = 0; jmin = 1 << 20; jmax = -1; }
+            if (d.bd == bd) {
+                count += d.count;
+                if ((int)d.jmin < jmin) {
+                    jmin = d.jmin; o.first_best = d.jmin; o.first_mask = 1ull << d.first_col; o.first_ss = d.search_start;
                 }
+                if ((int)d.jmax > jmax) jmax = d.jmax;
             }
         }
     }

@@ -69,6 +69,10 @@ struct HostTables {
     std::vector<unsigned char> b_len, bw_len, bw_primer;
     std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     std::vector<unsigned short> bw_list;
+    std::vector<unsigned short> bt_g0, bt_class_tasks;     // stage-2 tasks; task ids grouped by words per task
+    std::vector<unsigned char> bt_nw;
+    std::vector<u32> bt_row, bt_eq;
+    u32 bt_class_off[kMaxTaskWords + 1] = {0, 0, 0, 0, 0}; // tasks of NWQ words: bt_class_tasks[off[NWQ-1] .. off[NWQ])
     std::vector<i32> pair_pool, spec_pool, spec_dense;
     std::vector<u32> peq_long;
     std::vector<unsigned char> prow_code;      // [primer][32] IUPAC code of primer_rc row i (sliced primer search)
@@ -204,6 +208,42 @@ struct HostTables {
         t.bw_off[nP] = (u32)bw_len.size();
         t.n_bwords = (int)bw_len.size();
         t.hit_cap = 4;
+        // stage-2 tasks: consecutive bwords of one primer and one length, up to kMaxTaskWords to a task (one word
+        // when the flank does not fit the 16-column register form, or k is beyond the multi-word instantiations)
+        bt_g0.clear(); bt_nw.clear(); bt_row.clear(); bt_eq.clear(); bt_class_tasks.clear();
+        for (int p = 0; p < nP; ++p) {
+            t.bt_off[p] = (u32)bt_g0.size();
+            u32 g = t.bw_off[p];
+            while (g < t.bw_off[p + 1]) {
+                const int m = bw_len[g];
+                const u32 max_words = (m + t.k_idx <= 16 && t.k_idx <= kMaxTaskK) ? (u32)kMaxTaskWords : 1u;
+                u32 nw = 1;
+                while (nw < max_words && g + nw < t.bw_off[p + 1] && bw_len[g + nw] == m) ++nw;
+                const u32 S = nw == 1 ? 1u : nw == 2 ? 2u : 4u;
+                bt_g0.push_back((unsigned short)g);
+                bt_nw.push_back((unsigned char)nw);
+                while (bt_eq.size() % 4) bt_eq.push_back(0);            // vector loads: 16-byte aligned tables
+                bt_row.push_back((u32)bt_eq.size());
+                const size_t base = bt_eq.size();
+                bt_eq.resize(base + (size_t)m * 16 * S, 0);
+                for (u32 q = 0; q < nw; ++q)
+                    for (int i = 0; i < m; ++i)
+                        for (int c = 0; c < 16; ++c)
+                            bt_eq[base + ((size_t)i * 16 + c) * S + q] = beq[((size_t)bw_row[g + q] + i) * 16 + c];
+                g += nw;
+            }
+        }
+        t.bt_off[nP] = (u32)bt_g0.size();
+        t.n_btasks = (int)bt_g0.size();
+        if (bt_g0.size() > 65535) return err("more than 65535 barcode tasks");
+        for (int w = 1; w <= kMaxTaskWords; ++w) {
+            bt_class_off[w - 1] = (u32)bt_class_tasks.size();
+            for (size_t k = 0; k < bt_nw.size(); ++k) if (bt_nw[k] == w) bt_class_tasks.push_back((unsigned short)k);
+        }
+        bt_class_off[kMaxTaskWords] = (u32)bt_class_tasks.size();
+        if (bt_eq.empty()) bt_eq.push_back(0);
+        if (bt_g0.empty()) { bt_g0.push_back(0); bt_nw.push_back(0); bt_row.push_back(0); }
+        if (bt_class_tasks.empty()) bt_class_tasks.push_back(0);
         if (tb->pb_off[nP] - tb->pb_off[0] > 65535) return err("more than 65535 barcodes for one primer");
 
         u32 run = 0;
@@ -246,12 +286,17 @@ struct HostTables {
                      pair_fwd.data(), pair_rev.data(), pair_pool.data(), spec_key.data(), spec_key_off.data(),
                      spec_row.data(), spec_p1.data(), spec_p2.data(), spec_pool.data());
         set_bword_pointers(bw_len.data(), bw_primer.data(), bw_row.data(), bw_valid.data(), bw_list.data(), beq.data());
+        set_task_pointers(bt_g0.data(), bt_nw.data(), bt_row.data(), bt_eq.data());
         return true;
     }
 
     void set_bword_pointers(const unsigned char *len, const unsigned char *prim, const u32 *row, const u32 *valid,
                             const unsigned short *list, const u32 *eq) {
         t.bw_len = len; t.bw_primer = prim; t.bw_row = row; t.bw_valid = valid; t.bw_list = list; t.beq = eq;
+    }
+
+    void set_task_pointers(const unsigned short *g0, const unsigned char *nw, const u32 *row, const u32 *eq) {
+        t.bt_g0 = g0; t.bt_nw = nw; t.bt_row = row; t.bt_eq = eq;
     }
 
     void set_pointers(const u64 *a, const u64 *b, const u64 *c, const unsigned char *e, const u32 *f,

@@ -1,0 +1,42 @@
+// smx_k_sliced.cu -- stage 1 forward pass, bit-sliced across reads (one instantiation per primer length).
+#include <cuda_runtime.h>
+
+#include "smx_device.cuh"
+#include "smx_launch.hpp"
+
+namespace smx {
+
+// Sliced primer search: one thread per (group of 32 reads, strand) for one primer of length M.
+constexpr int kSlicedBlock = 64;        // small blocks: equal-length tasks, let the block scheduler balance the SMs
+template <int M>
+__global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
+    __shared__ u32 s_planes[(kSlicedCodes + 48) * kSlicedBlock];
+    const u32 group = blockIdx.x * kSlicedBlock + threadIdx.x;
+    if (group >= b.n_pad / 32) return;
+    primer_sliced_thread<M, kSlicedBlock>(c_tables, b, group, (int)blockIdx.y, primer, ro, degenerate != 0,
+                                          s_planes + threadIdx.x, s_planes + kSlicedCodes * kSlicedBlock + threadIdx.x);
+}
+
+
+cudaError_t launch_primer_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st) {
+    dim3 sgrid((b.n_pad / 32 + kSlicedBlock - 1) / kSlicedBlock, 2);
+    RowOffsets ro;
+    bool degenerate = false;
+    for (int i = 0; i < 32; ++i) {
+        int code = i < t.p_len[primer] ? prow_code[i] : 0;
+        degenerate |= code > 3;
+        ro.off[i] = (unsigned short)(code * kSlicedBlock * sizeof(u32));
+    }
+    switch (t.p_len[primer]) {
+#define SMX_M(MM) case MM: k_primer_sliced<MM><<<sgrid, kSlicedBlock, 0, st>>>(t, b, primer, ro, degenerate ? 1 : 0); break;
+        SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
+        SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
+        SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
+        SMX_M(32)
+#undef SMX_M
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace smx

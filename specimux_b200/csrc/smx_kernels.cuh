@@ -385,12 +385,15 @@ SMX_HD void primer_sliced_thread(const Tables &t, const Batch &b, u32 group, int
 #endif
                 for (int i = 0; i < M; ++i) {
                     const u32 Eq = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(sp) + ro.off[i]);
+                    // Pv & Mv = 0 and Ph & Mh = 0 (a delta is +1, 0 or -1), so the two "match or negative delta"
+                    // terms Eq | Mv and Eq | Mh can share ONE three-input term X = Eq | Mv | Mh: wherever X adds a
+                    // bit to one of them, the factor it is combined with is zero.  5 LOP3 per cell instead of 6.
                     const u32 Pv = VP[i], Mv = VM[i];
-                    const u32 Xv = Eq | Mv, Xh = Eq | Mh;
-                    VP[i] = Mh | ~(Xv | Ph);
-                    VM[i] = Ph & Xv;
-                    const u32 nPh = Mv | ~(Xh | Pv);
-                    Mh = Pv & Xh;
+                    const u32 X = Eq | Mv | Mh;
+                    VP[i] = Mh | ~(X | Ph);
+                    VM[i] = Ph & X;
+                    const u32 nPh = Mv | ~(X | Pv);
+                    Mh = Pv & X;
                     Ph = nPh;
                 }
                 // score += Ph - Mh against the running best: the difference saturates at 0 from below
@@ -522,22 +525,65 @@ SMX_HD int primer_finish_thread(const Tables &t, const Batch &b, u32 read, int s
     return nloc;
 }
 
-// Start recovery for the first equal-best end of a matched slot (edlib: reverse SHW pass with
-// k = best, the LAST equal-best reverse end wins = longest alignment).  One thread per work entry;
-// only a read's first entry does the work.
+// Start recovery over the staged 2-bit window (reads without non-ACGT symbols): same recurrence as
+// hw_start_back, but the up to m + best symbols before the end are cut out of the window words ONCE into a
+// 64-bit register (32 symbols, the end on top) and shifted out two bits per column -- the per-column window
+// load of the first form was 30 % of the start-recovery kernel's instructions (profiles/r2_a_*).
+// win2: the strand's 2-bit window words of this read, `stride` words apart.
+template <typename W>
+SMX_HD int hw_start_back_win2(const u64 *peq_rev, int m, int best, int e_pos, int start_pos, const u32 *win2, u64 stride) {
+    W Pv = pattern_mask<W>(m), Mv = 0;
+    int score = m;
+    int cols = e_pos - start_pos + 1;
+    const int lim = m + best;
+    if (cols > lim) cols = lim;
+    int last = m - 1;
+    for (int j0 = 0; j0 < cols; j0 += 32) {
+        // symbols e-31 .. e of the window with e = e_pos - j0, symbol e in the top two bits
+        const int e = e_pos - j0, hi = e >> 4, sh = 30 - 2 * (e & 15);
+        const u32 w0 = win2[(u64)hi * stride];
+        const u32 w1 = hi >= 1 ? win2[(u64)(hi - 1) * stride] : 0u;
+        const u32 w2 = hi >= 2 ? win2[(u64)(hi - 2) * stride] : 0u;
+        u64 X = (((u64)w0 << 32) | w1) << sh;
+        if (sh) X |= (u64)(w2 >> (32 - sh));
+        const int jn = cols - j0 < 32 ? cols - j0 : 32;
+        for (int j = 0; j < jn; ++j) {
+            const int c = (int)(X >> 62);
+            X <<= 2;
+            const W Eq = peq_word<W>(peq_rev[c]);
+            score += myers_step<W, true>(Eq, Pv, Mv);
+            if (score == best) last = j0 + j;
+        }
+    }
+    return last;
+}
+
+// Start recovery for the first equal-best end (staged position `first`) of a matched slot (edlib: reverse SHW
+// pass with k = best, the LAST equal-best reverse end wins = longest alignment).
+template <typename W>
+SMX_HD void primer_start_slot(const Tables &t, const Batch &b, u32 read, int strand, int primer, int first, const u64 *peq_rev) {
+    const int n = (int)b.lengths[read];
+    const Geo g = make_geo(n, t.L);
+    smx_primer_hit &h = b.phit[(u64)slot_index(t, strand, primer) * b.n_pad + read];
+    int back;
+    if (!read_is_flagged(b, read)) {
+        back = hw_start_back_win2<W>(peq_rev, t.p_len[primer], h.distance, first, g.start,
+                                     b.win2 + (u64)strand * t.nw2 * b.n_pad + read, b.n_pad);
+    } else {
+        auto load = [&](int p) { return staged_sym(t, b, read, strand, p); };
+        back = hw_start_back<W>(peq_rev, t.p_len[primer], h.distance, first, g.start, load);
+    }
+    h.first_start = h.first_end - back;
+}
+
+// The same over the compact work-entry lists: one thread per work entry; only a read's first entry does the work.
 template <typename W>
 SMX_HD void primer_start_thread(const Tables &t, const Batch &b, u32 slot, u32 entry, const u64 *peq_rev) {
     const u32 read = b.ent_read[(u64)slot * b.e_cap + entry];
     const u64 hit_idx = (u64)slot * b.n_pad + read;
     if (b.ent_base[hit_idx] != entry) return;              // not the first location of its read
     const int strand = (int)slot / t.n_primers, primer = (int)slot % t.n_primers;
-    const int n = (int)b.lengths[read];
-    const Geo g = make_geo(n, t.L);
-    smx_primer_hit &h = b.phit[hit_idx];
-    const int first = (int)b.ent_pos[(u64)slot * b.e_cap + entry];
-    auto load = [&](int p) { return staged_sym(t, b, read, strand, p); };
-    int back = hw_start_back<W>(peq_rev, t.p_len[primer], h.distance, first, g.start, load);
-    h.first_start = h.first_end - back;
+    primer_start_slot<W>(t, b, read, strand, primer, (int)b.ent_pos[(u64)slot * b.e_cap + entry], peq_rev);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -561,12 +607,14 @@ template <int K> struct BitSliced {
 
     // One cell of the automaton for 32 barcodes.
     static SMX_HD void cell(u32 Eq, u32 Pv, u32 Mv, u32 Ph, u32 Mh, u32 &oPv, u32 &oMv, u32 &oPh, u32 &oMh, u32 &inc) {
-        u32 Xv = Eq | Mv, Xh = Eq | Mh;
-        oPv = Mh | ~(Xv | Ph);
-        oMv = Ph & Xv;
-        oPh = Mv | ~(Xh | Pv);
-        oMh = Pv & Xh;
-        inc = ~(Xv | Mh);                                      // D[i][j] - D[i-1][j-1]
+        // Pv & Mv = 0 and Ph & Mh = 0, so Eq | Mv and Eq | Mh share one term X = Eq | Mv | Mh (see the sliced
+        // primer search): 5 LOP3 per cell, and the diagonal increment is simply ~X.
+        const u32 X = Eq | Mv | Mh;
+        oPv = Mh | ~(X | Ph);
+        oMv = Ph & X;
+        oPh = Mv | ~(X | Pv);
+        oMh = Pv & X;
+        inc = ~X;                                              // D[i][j] - D[i-1][j-1]
     }
 
     // beq_rows: table rows of this bword ([i][16]); rowwin(i): nibble t = 4-bit symbol of flank
@@ -620,62 +668,6 @@ template <int K> struct BitSliced {
         for (int t = 1; t < NT; ++t) { o.rp[t - 1] = HP[t]; o.rm[t - 1] = HM[t]; }
     }
 
-    // Small form (m + K <= 16): the whole flank sits in one 64-bit register F (nibble j-1 = symbol of
-    // column j, kSymOther beyond the flank).  One table address is formed per COLUMN (beq row 0 of
-    // that column's symbol); the rows are fully unrolled, so every cell's Eq is a single load at a
-    // compile-time offset from its column's address -- no per-cell shift / mask / scale arithmetic.
-    static constexpr int kSmallRows = 16 - K > 0 ? 16 - K : 0;
-    static SMX_HD void run_small(const u32 *beq_rows, int m, u64 F, Out &o) {
-        const u32 *col[16];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 16; ++j) col[j] = beq_rows + (u32)((F >> (4 * j)) & 15u);
-        u32 HP[NT], HM[NT];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int t = 0; t < NT; ++t) { HP[t] = ~0u; HM[t] = 0; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int b = 0; b < NB; ++b) o.cnt[b] = (K >> b) & 1 ? ~0u : 0u;
-        o.over = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int i = 1; i <= kSmallRows; ++i) {
-            if (i <= m) {                                       // uniform over the block
-                u32 Pv = ~0u, Mv = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int t = 0; t < NT; ++t) {
-                    const int j = i - K + t;                    // compile-time
-                    if (j < 1 || j > 16) continue;
-                    u32 Ph = t < NT - 1 ? HP[t + 1] : ~0u;
-                    u32 Mh = t < NT - 1 ? HM[t + 1] : 0u;
-                    u32 Eq = col[j - 1][(i - 1) * 16];
-                    u32 nPv, nMv, nPh, nMh, inc;
-                    cell(Eq, Pv, Mv, Ph, Mh, nPv, nMv, nPh, nMh, inc);
-                    if (t == 0) {
-                        u32 x = inc;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                        for (int b = 0; b < NB; ++b) { u32 c = o.cnt[b] & x; o.cnt[b] ^= x; x = c; }
-                        o.over |= x;
-                    }
-                    HP[t] = nPh; HM[t] = nMh;
-                    Pv = nPv; Mv = nMv;
-                }
-            }
-        }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int t = 1; t < NT; ++t) { o.rp[t - 1] = HP[t]; o.rm[t - 1] = HM[t]; }
-    }
 };
 // value <= K on NB bit-planes (K compile-time)
 template <int K, int NB> SMX_HD u32 planes_le(const u32 *v) {
@@ -692,77 +684,112 @@ template <int K, int NB> SMX_HD u32 planes_le(const u32 *v) {
 
 constexpr int kMaxWordHits = 32;
 
-// One work entry (matched slot of a read, one equal-best primer end at staged position p) and one
-// bword.  `beq_rows` points at the bword's [m][16] table (shared memory in the CUDA launch).
-// Accumulates the SURVEY.md 8d work formula into cells / wcols.
-template <int K>
-SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, int p, u64 entry, int strand,
-                                     int primer, u32 g, const u32 *beq_rows,
-                                     unsigned long long &cells, unsigned long long &wcols) {
-    typedef BitSliced<K> BS;
-    const u64 gslot = (u64)strand * t.n_bwords + g;
-    unsigned char &out_count = b.bh_count[gslot * b.e_cap + entry];
-    out_count = 0;
-    const int n = (int)b.lengths[read];
-    const Geo geo = make_geo(n, t.L);
-    const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
-    const int m = t.bw_len[g];
-    const u32 valid = t.bw_valid[g];
-    const int nbits = popcount32(valid);
-    const bool small = m + K <= 16;            // whole flank fits one 64-bit register
-
-    const Flank f = make_flank(geo.woff + p + geo.delta, n);
-    const int fl = n - f.a_align;
-    const int cols = fl < m + K ? fl : m + K;
-    if (cols > 0) {
-        cells += (unsigned long long)nbits * m * cols;
-        wcols += (unsigned long long)nbits * ((m + 31) >> 5) * cols;
-    }
-    const int base = f.a_align - geo.woff;          // staged index of flank column 1
-    u64 F = ~0ull;
-    if (small && cols > 0) {
-        // 16 symbols starting at staged position `base`, symbols >= cols forced to "other"
-        int w0 = base >> 3, sh = 4 * (base & 7);
-        u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
-        u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
-        u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
-        u64 lo = ((u64)a1 << 32) | a0, hi = a2;
-        F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
-        if (cols < 16) F |= ~0ull << (4 * cols);
-    }
-    if (t.prefilter) {
-        // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key
-        // barcode_rc + flank[:m-k] can only be present if those m-k symbols exist and are
-        // all A/C/G/T; for such flanks the filter has no false negatives (SURVEY.md Q5).
-        const int need = m - K;
-        if (n - f.a_pref < need) return;
-        bool acgt = true;
-        if (small && f.a_pref == f.a_align) {
-            u64 chk = need >= 16 ? ~0ull : ((1ull << (4 * need)) - 1);
-            acgt = (F & chk & 0xCCCCCCCCCCCCCCCCull) == 0;
-        } else {
-            for (int x = 0; x < need; ++x)
-                if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { acgt = false; break; }
-        }
-        if (!acgt) return;
-    }
-    if (cols < m - K || cols <= 0) return;           // D[m][j] >= m - j > K for every column
-    typename BS::Out o;
-    if (small) {
-        BS::run_small(beq_rows, m, F, o);
+// Eq words of one (row, symbol) of a task table: S consecutive words, one vector load on the GPU.
+template <int S> SMX_HD void load_eq(const u32 *p, u32 (&eq)[S]) {
+#if defined(__CUDA_ARCH__)
+    if (S == 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        eq[0] = v.x; eq[1 % S] = v.y; eq[2 % S] = v.z; eq[3 % S] = v.w;
+    } else if (S == 2) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        eq[0] = v.x; eq[1 % S] = v.y;
     } else {
-        auto rowwin = [&](int i) -> u64 {
-            u64 W = 0;
-            for (int tt = 0; tt < BS::NT; ++tt) {
-                int j = i - K + tt;
-                u64 c = (j >= 1 && j <= cols) ? (u64)staged_sym(t, b, read, strand, base + j - 1) : 15ull;
-                W |= c << (4 * tt);
-            }
-            return W;
-        };
-        BS::run(beq_rows, m, rowwin, o);
+        eq[0] = *p;
     }
-    // bit-sliced test "some in-range column has D[m][j] <= K"
+#else
+    for (int q = 0; q < S; ++q) eq[q] = p[q];
+#endif
+}
+
+// Small form of the automaton (m + K <= 16) for the NWQ bwords of one task at once.  The whole flank sits in
+// one 64-bit register F (nibble j-1 = symbol of column j, kSymOther beyond the flank).  One table address is
+// formed per COLUMN (row 0 of that column's symbol); the rows are fully unrolled, so every cell's Eq words are
+// one vector load at a compile-time offset from its column's address, shared by the task's words, and the
+// NWQ independent automata interleave in the instruction stream.  Rows beyond m leave the unrolled sequence
+// through one early exit, so the horizontal-delta registers are renamed from row to row without moves.
+template <int K, int NWQ>
+SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, typename BitSliced<K>::Out (&o)[NWQ]) {
+    typedef BitSliced<K> BS;
+    constexpr int NT = BS::NT, NB = BS::NB, S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
+    constexpr int kRows = 16 - K > 0 ? 16 - K : 0;
+    const u32 *col[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 16; ++j) col[j] = tab + (u32)((F >> (4 * j)) & 15u) * S;
+    u32 HP[NWQ][NT], HM[NWQ][NT];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NWQ; ++q) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < NT; ++t) { HP[q][t] = ~0u; HM[q][t] = 0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int bb = 0; bb < NB; ++bb) o[q].cnt[bb] = (K >> bb) & 1 ? ~0u : 0u;
+        o[q].over = 0;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i <= kRows; ++i) {
+        if (i > m) break;                                   // uniform over the block
+        u32 Pv[NWQ], Mv[NWQ];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < NWQ; ++q) { Pv[q] = ~0u; Mv[q] = 0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < NT; ++t) {
+            const int j = i - K + t;                        // compile-time
+            if (j < 1 || j > 16) continue;
+            u32 eq[S];
+            load_eq<S>(col[j - 1] + (i - 1) * 16 * S, eq);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < NWQ; ++q) {
+                const u32 Ph = t < NT - 1 ? HP[q][t + 1] : ~0u;
+                const u32 Mh = t < NT - 1 ? HM[q][t + 1] : 0u;
+                u32 nPv, nMv, nPh, nMh, inc;
+                BS::cell(eq[q], Pv[q], Mv[q], Ph, Mh, nPv, nMv, nPh, nMh, inc);
+                if (t == 0) {
+                    u32 x = inc;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int bb = 0; bb < NB; ++bb) { u32 c = o[q].cnt[bb] & x; o[q].cnt[bb] ^= x; x = c; }
+                    o[q].over |= x;
+                }
+                HP[q][t] = nPh; HM[q][t] = nMh;
+                Pv[q] = nPv; Mv[q] = nMv;
+            }
+        }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NWQ; ++q)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 1; t < NT; ++t) { o[q].rp[t - 1] = HP[q][t]; o[q].rm[t - 1] = HM[q][t]; }
+}
+
+// Read-out of one bword after the automaton: bit-sliced test "some in-range end column has D[m][j] <= K",
+// exact scalar values of the few flagged barcodes (ascending bit = ascending list position), their hit
+// records, and the running digest of the entry.
+struct DigestAcc { int bd, count, jmin, jmax, first_col; u32 nhits; };
+
+template <int K>
+SMX_HD void barcode_readout(const Tables &t, const Batch &b, const typename BitSliced<K>::Out &o, u32 g, u64 gslot, u64 entry,
+                            int m, int cols, int search_start, DigestAcc &acc) {
+    typedef BitSliced<K> BS;
     u32 v[BS::NB];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -787,8 +814,7 @@ SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, 
         for (int q = 0; q < BS::NB; ++q) { u32 br = ~v[q] & x; v[q] ^= x; x = br; }
         if (m - K + tt <= cols) flag |= planes_le<K, BS::NB>(v) & ~ov;
     }
-    flag &= valid;
-    // exact scalar read-out of the few flagged barcodes (ascending bit = ascending list position)
+    flag &= t.bw_valid[g];
     int nh = 0;
     while (flag) {
         int q = lowest_bit32(flag);
@@ -805,15 +831,116 @@ SMX_HD void barcode_bitsliced_thread(const Tables &t, const Batch &b, u32 read, 
             if (val == best) mask |= 1ull << (col - 1);
         }
         if (best > K) continue;
+        const int j = (int)t.bw_list[(u64)g * 32 + q];
         if (nh < t.hit_cap) {
             smx_barcode_hit h;
-            h.barcode = t.bw_list[(u64)g * 32 + q]; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = f.bs;
+            h.barcode = (uint16_t)j; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = search_start;
             b.bh_list[(gslot * t.hit_cap + nh) * b.e_cap + entry] = h;
         }
         ++nh;
+        ++acc.nhits;
+        if (best < acc.bd) { acc.bd = best; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; }
+        if (best == acc.bd) {
+            ++acc.count;
+            if (j < acc.jmin) { acc.jmin = j; acc.first_col = lowest_bit64(mask); }
+            if (j > acc.jmax) acc.jmax = j;
+        }
     }
-    out_count = (unsigned char)nh;
+    b.bh_count[gslot * b.e_cap + entry] = (unsigned char)nh;
     if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
+}
+
+// One work entry (matched slot of a read, one equal-best primer end at staged position p) against the NWQ bwords
+// of stage-2 task `task` (all of one barcode length m).  `tab` points at the task's [m][16][S] table (shared
+// memory in the CUDA launch).  Returns lanes x columns of the SURVEY.md 8d work formula (x m = cells).
+template <int K, int NWQ>
+SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p, u64 entry, int strand, int primer,
+                               u32 task, const u32 *tab) {
+    typedef BitSliced<K> BS;
+    const u32 g0 = t.bt_g0[task];
+    const u64 gslot0 = (u64)strand * t.n_bwords + g0;
+    BarcodeDigest dg;
+    dg.search_start = 0; dg.jmin = 0; dg.jmax = 0; dg.count = 0; dg.bd = -1; dg.first_col = 0; dg.nhits = 0;
+    BarcodeDigest &dg_out = b.bdig[((u64)strand * t.n_btasks + task) * b.e_cap + entry];
+    const int n = (int)b.lengths[read];
+    const Geo geo = make_geo(n, t.L);
+    const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
+    const int m = t.bw_len[g0];
+    int nbits = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NWQ; ++q) nbits += popcount32(t.bw_valid[g0 + q]);
+    const bool small = m + K <= 16;            // whole flank fits one 64-bit register
+
+    const Flank f = make_flank(geo.woff + p + geo.delta, n);
+    dg.search_start = f.bs;
+    const int fl = n - f.a_align;
+    const int cols = fl < m + K ? fl : m + K;
+    const u32 work = cols > 0 ? (u32)(nbits * cols) : 0u;
+    const int base = f.a_align - geo.woff;          // staged index of flank column 1
+    u64 F = ~0ull;
+    if (small && cols > 0) {
+        // 16 symbols starting at staged position `base`, symbols >= cols forced to "other"
+        int w0 = base >> 3, sh = 4 * (base & 7);
+        u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
+        u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
+        u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
+        u64 lo = ((u64)a1 << 32) | a0, hi = a2;
+        F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        if (cols < 16) F |= ~0ull << (4 * cols);
+    }
+    bool skip = cols < m - K || cols <= 0;           // D[m][j] >= m - j > K for every column
+    if (t.prefilter && !skip) {
+        // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key
+        // barcode_rc + flank[:m-k] can only be present if those m-k symbols exist and are
+        // all A/C/G/T; for such flanks the filter has no false negatives (SURVEY.md Q5).
+        const int need = m - K;
+        if (n - f.a_pref < need) skip = true;
+        else if (small && f.a_pref == f.a_align) {
+            u64 chk = need >= 16 ? ~0ull : ((1ull << (4 * need)) - 1);
+            skip = (F & chk & 0xCCCCCCCCCCCCCCCCull) != 0;
+        } else {
+            for (int x = 0; x < need; ++x)
+                if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { skip = true; break; }
+        }
+    }
+    if (skip) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < NWQ; ++q) b.bh_count[(gslot0 + q) * b.e_cap + entry] = 0;
+        dg_out = dg;
+        return work;
+    }
+    typename BS::Out o[NWQ];
+    if (small) {
+        bitsliced_small_rows<K, NWQ>(tab, m, F, o);
+    } else {
+        // long barcodes (m + K > 16): the general band walk, one word at a time (tasks of such lengths hold one word)
+        auto rowwin = [&](int i) -> u64 {
+            u64 W = 0;
+            for (int tt = 0; tt < BS::NT; ++tt) {
+                int j = i - K + tt;
+                u64 c = (j >= 1 && j <= cols) ? (u64)staged_sym(t, b, read, strand, base + j - 1) : 15ull;
+                W |= c << (4 * tt);
+            }
+            return W;
+        };
+        BS::run(tab, m, rowwin, o[0]);
+    }
+    DigestAcc acc;
+    acc.bd = 1 << 20; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; acc.first_col = 0; acc.nhits = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NWQ; ++q) barcode_readout<K>(t, b, o[q], g0 + q, gslot0 + q, entry, m, cols, f.bs, acc);
+    if (acc.nhits) {
+        dg.nhits = acc.nhits; dg.bd = (signed char)acc.bd; dg.count = (unsigned short)(acc.count > 65535 ? 65535 : acc.count);
+        dg.jmin = (unsigned short)acc.jmin; dg.jmax = (unsigned short)acc.jmax; dg.first_col = (unsigned char)acc.first_col;
+    }
+    dg_out = dg;
+    return work;
 }
 
 // Work-entry bookkeeping of stage 1: entries [base, base + nloc) of `slot` for one matched read.
@@ -852,621 +979,5 @@ template <int SW> SMX_HD u32 long_carry_in(u32 G, u32 P) {
     const u32 V = (G << 1) & inner, Pm = P & inner;
     return ((Pm + V) ^ Pm) & inner;
 }
-
-#if defined(__CUDACC__)
-// ---------------------------------------------------------------------------------------------
-// __global__ wrappers.  Tables travel as __grid_constant__ parameters, Peq masks are staged once per block
-// in shared memory.
-
-// Tables and Batch travel as __grid_constant__ kernel parameters (constant bank, per launch), so
-// several contexts / pipeline lanes can be in flight on one device without sharing a symbol.
-#define SMX_KARGS const __grid_constant__ Tables c_tables, const __grid_constant__ Batch b
-
-// One block stages the windows of 128 consecutive reads.  Their 2-bit words are one contiguous range
-// of the packed stream (reads are packed back to back), so the block first copies that range into
-// shared memory with fully coalesced loads and every thread then cuts its read's 2 * nw2 windows
-// out of the copy; the stores are coalesced across the block's reads as before.  The first form --
-// one thread per (read, window word), each loading its two words straight from the stream -- made a
-// warp touch 32 different reads' lines per load and was the top kernel of the long-amplicon config
-// (457 us of 1,279; profiles/r1_v20_bench_long.json).  The tile is dynamic shared memory sized by the
-// host for the batch's clip length (128 reads x the most words a clipped read can have); blocks whose
-// reads span more than that (unclipped long reads) read the stream directly.
-constexpr int kStageBlock = 128;                // reads per block; blockDim = (kStageBlock, 2 strands)
-
-// tile_words: capacity of the dynamic shared-memory tile in words (0 = always read the stream directly)
-__global__ void __launch_bounds__(2 * kStageBlock) k_stage_windows(SMX_KARGS, u32 tile_words) {
-    extern __shared__ u32 s_src[];
-    const Tables &t = c_tables;
-    const u32 r0 = blockIdx.x * kStageBlock;
-    const u32 r1 = r0 + kStageBlock < b.n_reads ? r0 + kStageBlock : b.n_reads;
-    const u64 w0 = b.word_off[r0];
-    const u64 w1 = b.word_off[r1 - 1] + (u64)((stored_len(b, (int)b.lengths[r1 - 1]) + 15) >> 4);
-    const bool tiled = w1 - w0 + 2 <= tile_words;                             // window extraction reads one word past the read
-    if (tiled) {
-        const u32 span = (u32)(w1 - w0) + 2;
-        const u32 *g = b.packed2 + (w0 - b.word_base);
-        for (u32 i = threadIdx.y * kStageBlock + threadIdx.x; i < span; i += 2 * kStageBlock) s_src[i] = g[i];
-    }
-    __syncthreads();
-    const u32 read = r0 + threadIdx.x;
-    if (read >= b.n_reads) return;
-    const u32 *src2 = tiled ? s_src : b.packed2;
-    const u64 origin = tiled ? w0 : b.word_base;
-    const int strand = (int)threadIdx.y;
-    for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, read, strand, w2, src2, origin);
-}
-
-// Sliced primer search: one thread per (group of 32 reads, strand) for one primer of length M.
-constexpr int kSlicedBlock = 64;        // small blocks: equal-length tasks, let the block scheduler balance the SMs
-template <int M>
-__global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
-    __shared__ u32 s_planes[(kSlicedCodes + 48) * kSlicedBlock];
-    const u32 group = blockIdx.x * kSlicedBlock + threadIdx.x;
-    if (group >= b.n_pad / 32) return;
-    primer_sliced_thread<M, kSlicedBlock>(c_tables, b, group, (int)blockIdx.y, primer, ro, degenerate != 0,
-                                          s_planes + threadIdx.x, s_planes + kSlicedCodes * kSlicedBlock + threadIdx.x);
-}
-
-constexpr int kFinishBlock = 256;
-
-// Work counters.  Every thread of a block contributes a small 32-bit count `v` (DP columns, or
-// barcode lanes x columns); the block adds v_total * mul0 and v_total * mul1 to two 64-bit device
-// counters.  One REDUX per warp, one shared atomic per warp, two global atomics per block (the
-// first form -- a shuffle tree per counter and two barriers each -- was 9 % of the barcode
-// kernel's instructions and 14 % of its stall samples: profiles/r1_v14_ncu_full.md).
-__device__ __forceinline__ void block_work_add(u32 v, unsigned long long mul0, unsigned long long *dst0,
-                                               unsigned long long mul1, unsigned long long *dst1, u32 *s_acc /*1, zeroed*/) {
-    const u32 wsum = __reduce_add_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(s_acc, wsum);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long tot = *s_acc;
-        if (tot) { atomicAdd(dst0, tot * mul0); atomicAdd(dst1, tot * mul1); }
-    }
-}
-
-template <typename W>
-__global__ void __launch_bounds__(kFinishBlock) k_primer_search(SMX_KARGS) {
-    // grid: x over reads, y = strand * n_primers + primer
-    __shared__ u64 s_peq[3][16];
-    __shared__ u32 s_wtot[kFinishBlock / 32 + 1];
-    __shared__ u32 s_acc;
-    const int primer = blockIdx.y % c_tables.n_primers, strand = blockIdx.y / c_tables.n_primers;
-    if (c_tables.p_sw[primer]) return;                  // long primer: k_primer_long owns this slot
-    if (threadIdx.x == 64) s_acc = 0;
-    if (threadIdx.x < 48) {
-        const u64 *src = threadIdx.x < 16 ? c_tables.peq_rc : threadIdx.x < 32 ? c_tables.peq_rcrev : c_tables.peq_fw;
-        s_peq[threadIdx.x >> 4][threadIdx.x & 15] = src[primer * 16 + (threadIdx.x & 15)];
-    }
-    __syncthreads();
-    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 cells = 0;
-    int nloc = 0;
-    u32 ev[kFinishMaskWords];
-    bool have_ev = false;
-    if (read < b.n_reads) {
-        nloc = primer_finish_thread<W>(c_tables, b, read, strand, primer, s_peq[0], s_peq[2], ev, &have_ev);
-        int n = (int)b.lengths[read];
-        cells = (u32)(n < c_tables.L ? n : c_tables.L);                      // HW columns of this search
-    }
-    // work entries, one per equal-best end location: block-aggregated allocation (one atomic per
-    // block), a read's entries stay consecutive (the order of reads inside the list is irrelevant)
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        int incl = nloc;
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_wtot[warp] = (u32)incl;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 run = 0;
-            for (int w = 0; w < kFinishBlock / 32; ++w) { u32 v = s_wtot[w]; s_wtot[w] = run; run += v; }
-            u32 base = run ? atomicAdd(&b.slot_count[blockIdx.y], run) : 0u;
-            s_wtot[kFinishBlock / 32] = base;
-        }
-        __syncthreads();
-        if (nloc) write_entries(c_tables, b, blockIdx.y, read, s_wtot[kFinishBlock / 32] + s_wtot[warp] + (u32)(incl - nloc),
-                                have_ev ? ev : nullptr);
-    }
-    const int m = c_tables.p_len[primer];
-    block_work_add(cells, (unsigned long long)m, &b.counters[0], (unsigned long long)((m + 31) >> 5), &b.counters[2], &s_acc);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Long primers (65 .. 1024 nt): warp-cooperative multi-word Myers/Hyyro.  The pattern occupies the
-// top m bits of a 32*SW-bit vector spread over SW consecutive lanes (lane `sub` holds word `sub`;
-// row m is the sign bit of the top lane), so a warp works on 32/SW reads at once.  Per column the
-// only cross-lane traffic is the carry of (Eq & Pv) + Pv -- resolved for all segments at once from
-// two ballots (generate / propagate masks, carry-lookahead by one integer addition) -- and the
-// one-bit shifts of Ph / Mh (__shfl_up).  Same recurrences as myers_step<>, i.e. edlib's
-// calculateBlock over several blocks (alignment.py:42).  One kernel does the forward HW pass, the
-// hit bookkeeping, the reverse pass that recovers the start of the first location, the work
-// entries and, for irregular reads, the explicit orientation test.
-
-// One DP column for every segment of the warp.  Returns the score delta of the last row (only
-// meaningful in a segment's top lane).  Must be called by all 32 lanes.
-template <int SW, bool kShiftInOne>
-__device__ __forceinline__ int long_step(u32 Eq, u32 &Pv, u32 &Mv, int sub, int lane) {
-    const u32 a = Eq & Pv;
-    u32 sum = a + Pv;
-    const u32 G = __ballot_sync(0xffffffffu, sum < a);                 // word generates a carry
-    const u32 P = __ballot_sync(0xffffffffu, sum == 0xFFFFFFFFu);      // word propagates an incoming carry
-    sum += (long_carry_in<SW>(G, P) >> lane) & 1u;
-    const u32 Xh = (sum ^ Pv) | Eq;
-    const u32 Xv = Eq | Mv;
-    u32 Ph = Mv | ~(Xh | Pv);
-    u32 Mh = Pv & Xh;
-    const int d = (int)(Ph >> 31) - (int)(Mh >> 31);
-    u32 Ph_lo = __shfl_up_sync(0xffffffffu, Ph, 1), Mh_lo = __shfl_up_sync(0xffffffffu, Mh, 1);
-    if (sub == 0) { Ph_lo = kShiftInOne ? 0x80000000u : 0u; Mh_lo = 0u; }
-    Ph = __funnelshift_l(Ph_lo, Ph, 1);
-    Mh = __funnelshift_l(Mh_lo, Mh, 1);
-    Pv = Mh | ~(Xv | Ph);
-    Mv = Ph & Xv;
-    return d;
-}
-
-template <int SW>
-__global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
-    // grid: x over (read, word) pairs, y = strand
-    __shared__ u32 s_peq[3][16 * SW];
-    const Tables &t = c_tables;
-    {
-        const u32 *src = t.peq_long + t.p_long[primer];
-        for (int i = threadIdx.x; i < 3 * 16 * SW; i += blockDim.x) s_peq[i / (16 * SW)][i % (16 * SW)] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, sub = lane % SW;
-    const bool top = sub == SW - 1;
-    const int strand = (int)blockIdx.y;
-    const u32 read = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) / SW);
-    const bool valid = read < b.n_reads;
-    const int m = t.p_len[primer], k = t.p_k[primer];
-    const u32 slot = slot_index(t, strand, primer);
-    const int n = valid ? (int)b.lengths[read] : 0;
-    const Geo g = make_geo(n, t.L);
-    const u64 hit_idx = (u64)slot * b.n_pad + (valid ? read : 0);
-    u32 *emask = b.endmask + (u64)slot * t.mw * b.n_pad + (valid ? read : 0);
-    u32 *imask = b.impmask + (u64)slot * t.mw * b.n_pad + (valid ? read : 0);
-
-    // ---- forward HW pass over the staged window [g.start, g.wl)
-    const int p_begin = g.start, cols = valid ? g.wl - g.start : 0;
-    const u32 *wwin = b.win + (u64)strand * t.wpw * b.n_pad + (valid ? read : 0);     // this read's 4-bit window words
-    u32 wcur = 0;
-    int wcur_idx = -1;
-    if (valid && top) for (int w = 0; w < t.mw; ++w) { emask[(u64)w * b.n_pad] = 0; imask[(u64)w * b.n_pad] = 0; }
-    u32 Pv = ~0u, Mv = 0u;
-    int score = m, best = m + 1;
-    {
-        u32 eqw = 0, imw = 0;
-        int cur = p_begin >> 5;
-        const int maxcols = __reduce_max_sync(0xffffffffu, cols);
-        for (int j = 0; j < maxcols; ++j) {
-            const bool active = j < cols;
-            const int p = p_begin + j;
-            int c = kSymOther;
-            if (active) {                                   // one window word per 8 columns, not one load per column
-                if ((p >> 3) != wcur_idx) { wcur_idx = p >> 3; wcur = wwin[(u64)wcur_idx * b.n_pad]; }
-                c = (int)((wcur >> (4 * (p & 7))) & 15u);
-            }
-            const u32 sPv = Pv, sMv = Mv;
-            const int d = long_step<SW, false>(s_peq[0][c * SW + sub], Pv, Mv, sub, lane);
-            if (!active) { Pv = sPv; Mv = sMv; }
-            else if (top) {
-                if ((p >> 5) != cur) { emask[(u64)cur * b.n_pad] = eqw; imask[(u64)cur * b.n_pad] = imw; eqw = imw = 0; cur = p >> 5; }
-                score += d;
-                if (score < best) { best = score; imw |= 1u << (p & 31); }
-                if (score == best) eqw |= 1u << (p & 31);
-            }
-        }
-        if (valid && top && cols > 0) { emask[(u64)cur * b.n_pad] = eqw; imask[(u64)cur * b.n_pad] = imw; }
-    }
-    // ---- hit bookkeeping (top lane), then the segment learns (nloc, first, best)
-    int nloc = 0, first = 0;
-    if (valid && top) {
-        nloc = primer_tail(t, b, read, strand, primer, best);
-        if (nloc) first = b.phit[hit_idx].first_end - g.woff - g.delta;
-    }
-    const int src_lane = lane - sub + SW - 1;
-    nloc = __shfl_sync(0xffffffffu, nloc, src_lane);
-    first = __shfl_sync(0xffffffffu, first, src_lane);
-    best = __shfl_sync(0xffffffffu, best, src_lane);
-    // ---- reverse SHW pass from the first equal-best end: the LAST column with score == best is the
-    //      longest alignment (edlib start recovery)
-    {
-        int rcols = 0;
-        if (nloc) { rcols = first - p_begin + 1; if (rcols > m + best) rcols = m + best; }
-        const int maxr = __reduce_max_sync(0xffffffffu, rcols);
-        // pattern mask: bits at positions >= 32*SW - m of the 32*SW-bit vector
-        const int lo = 32 * SW - m - 32 * sub;                // first pattern bit inside this word
-        Pv = lo <= 0 ? ~0u : (lo >= 32 ? 0u : ~0u << lo);
-        Mv = 0u;
-        int rs = m, last = m - 1;
-        for (int j = 0; j < maxr; ++j) {
-            const bool active = j < rcols;
-            int c = kSymOther;
-            if (active) {
-                const int p = first - j;
-                if ((p >> 3) != wcur_idx) { wcur_idx = p >> 3; wcur = wwin[(u64)wcur_idx * b.n_pad]; }
-                c = (int)((wcur >> (4 * (p & 7))) & 15u);
-            }
-            const u32 sPv = Pv, sMv = Mv;
-            const int d = long_step<SW, true>(s_peq[1][c * SW + sub], Pv, Mv, sub, lane);
-            if (!active) { Pv = sPv; Mv = sMv; }
-            else if (top) { rs += d; if (rs == best) last = j; }
-        }
-        if (valid && top && nloc) b.phit[hit_idx].first_start = b.phit[hit_idx].first_end - last;
-    }
-    // ---- work entries and counters (top lane; this kernel is the rare path, plain atomics)
-    if (valid && top) {
-        if (nloc) write_entries(t, b, slot, read, atomicAdd(&b.slot_count[slot], (u32)nloc));
-        const unsigned long long hw_cols = (unsigned long long)(n < t.L ? n : t.L);
-        atomicAdd(&b.counters[0], hw_cols * (unsigned long long)m);
-        atomicAdd(&b.counters[2], hw_cols * (unsigned long long)((m + 31) >> 5));
-    }
-    // ---- determine_orientation, explicit form (demultiplex.py:602-638), irregular reads only
-    {
-        const bool need = valid && t.preorient && (!g.regular || read_is_flagged(b, read));
-        const int ocols = need ? (n < t.L ? n : t.L) : 0;
-        const int maxo = __reduce_max_sync(0xffffffffu, ocols);
-        Pv = ~0u; Mv = 0u;
-        int sc = m, bst = m + 1;
-        for (int x = 0; x < maxo; ++x) {
-            const bool active = x < ocols;
-            const int c = active ? sym_at(b, read, strand, x, n) : kSymOther;
-            const u32 sPv = Pv, sMv = Mv;
-            const int d = long_step<SW, false>(s_peq[2][c * SW + sub], Pv, Mv, sub, lane);
-            if (!active) { Pv = sPv; Mv = sMv; }
-            else if (top) { sc += d; if (sc < bst) bst = sc; }
-        }
-        if (valid && top) b.orient_hit[hit_idx] = (unsigned char)(need && bst <= k);
-    }
-}
-
-// Start recovery over the compact work-entry lists (full warps instead of the ~50 % matched lanes).
-template <typename W>
-__global__ void __launch_bounds__(128) k_primer_start(SMX_KARGS) {
-    __shared__ u64 s_rev[16];
-    const u32 slot = blockIdx.y;
-    if (c_tables.p_sw[slot % c_tables.n_primers]) return;   // long primer: start recovered by k_primer_long
-    u32 cnt = b.slot_count[slot];
-    if (cnt > b.e_cap) cnt = b.e_cap;
-    if (blockIdx.x * blockDim.x >= cnt) return;
-    if (threadIdx.x < 16) s_rev[threadIdx.x] = c_tables.peq_rcrev[(slot % c_tables.n_primers) * 16 + threadIdx.x];
-    __syncthreads();
-    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < cnt) primer_start_thread<W>(c_tables, b, slot, idx, s_rev);
-}
-
-// One thread per (matched slot entry, bword); the bword's bit-sliced table sits in shared memory.
-template <int K>
-__global__ void __launch_bounds__(128) k_barcode_bitsliced(SMX_KARGS) {
-    __shared__ u32 s_beq[SMX_MAX_PATTERN * 16];
-    const Tables &t = c_tables;
-    const u32 g = blockIdx.y % t.n_bwords;
-    const int strand = blockIdx.y / t.n_bwords;
-    const int primer = t.bw_primer[g];
-    const u32 slot = slot_index(t, strand, primer);
-    u32 cnt = b.slot_count[slot];
-    if (cnt > b.e_cap) cnt = b.e_cap;
-    if (blockIdx.x * blockDim.x >= cnt) return;
-    const int m = t.bw_len[g];
-    __shared__ u32 s_acc;
-    if (threadIdx.x == 0) s_acc = 0;
-    for (int i = threadIdx.x; i < m * 16; i += blockDim.x) s_beq[i] = t.beq[(u64)t.bw_row[g] * 16 + i];
-    __syncthreads();
-    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long cells = 0, wcols = 0;
-    if (idx < cnt) {
-        const u32 read = b.ent_read[(u64)slot * b.e_cap + idx];
-        const int p = b.ent_pos[(u64)slot * b.e_cap + idx];
-        barcode_bitsliced_thread<K>(t, b, read, p, idx, strand, primer, g, s_beq, cells, wcols);
-    }
-    // m is uniform over the block: cells = m * S, word-columns = ceil(m/32) * S with S = sum of lanes x columns
-    const unsigned long long wmul = (unsigned long long)((m + 31) >> 5);
-    (void)cells;
-    block_work_add((u32)(wcols / wmul), (unsigned long long)m, &b.counters[1], wmul, &b.counters[3], &s_acc);
-}
-
-constexpr int kInlineRecords = 4;
-
-// Stage 3a, fast selection: one thread per read, only the common single-candidate path of the
-// selection routine (slot digests computed on the fly, no grouping, small register footprint so
-// the dependent global loads are hidden by occupancy).  Reads that need the general routine
-// (several equal-best candidates, tied barcodes, TAILS trimming) are appended to defer_list.
-template <int MAXP>
-__global__ void __launch_bounds__(128) k_select_fast(SMX_KARGS) {
-    u32 read = blockIdx.x * blockDim.x + threadIdx.x;
-    bool defer = false;
-    if (read < b.n_reads) {
-        EndInfo ends[2 * MAXP];
-        int ts_cand[1], ts_shift[1];
-        smx_record rec;
-        SelectStore st;
-        st.groups = nullptr; st.gcand = nullptr; st.pg = nullptr; st.pcand = nullptr;
-        st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = 1;
-        SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
-        unsigned char flags;
-        u32 cnt = select_read_impl<true>(c, ends, st, &rec, 1, flags);
-        defer = (flags & kFlagDeferred) != 0;
-        if (!defer) {
-            b.rec_count[read] = cnt;
-            b.read_flags[read] = flags & 1;
-            if (cnt) {
-                uint4 *dst = reinterpret_cast<uint4 *>(b.rec_stage + read);
-                const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
-                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-            }
-        }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, defer);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd((unsigned int *)&b.counters[kCtrDeferred], (u32)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (defer) b.defer_list[base + __popc(m & ((1u << lane) - 1))] = read;
-    }
-}
-
-// Stage 3b, general selection over the deferred reads: working storage in thread-local arrays.
-// Records are produced once into a small local buffer; the first goes to rec_stage[read], further
-// ones (rare) to a contiguous block of rec_pool.  Reads whose groups overflow kSmallGroups or that
-// emit more than kInlineRecords records are flagged (bit1) for k_select_big.
-template <int MAXP>
-__global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
-    // The routine is long and branchy: when few reads are deferred they are spread one per 8 lanes
-    // so that a warp serialises 4 divergent reads instead of 32.
-    const u32 n_def = (u32)b.counters[kCtrDeferred];
-    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool spread = (u64)n_def * 8 <= (u64)gridDim.x * blockDim.x;
-    if (spread && (tid & 7)) return;
-    const u32 i = spread ? tid >> 3 : tid;
-    if (i >= n_def) return;
-    const u32 read = b.defer_list[i];
-    EndInfo ends[2 * MAXP];
-    Group groups[kSmallGroups], pg[kSmallGroups];
-    Cand gcand[kSmallGroups], pcand[kSmallGroups];
-    int ts_cand[kSmallGroups], ts_shift[kSmallGroups];
-    smx_record local[kInlineRecords];
-    SelectStore st;
-    st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
-    st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
-    SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
-    unsigned char flags;
-    u32 cnt = select_read(c, ends, st, local, kInlineRecords, flags);
-    if (cnt > kInlineRecords) flags |= 2;
-    b.rec_count[read] = cnt;
-    b.read_flags[read] = flags;
-    if (flags & 2) {                                    // second pass: listed on the device, no host round trip
-        b.big_list[atomicAdd((unsigned int *)&b.counters[kCtrBig], 1u)] = read;
-        return;
-    }
-    if (cnt >= 1) b.rec_stage[read] = local[0];
-    if (cnt >= 2) {
-        u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt - 1);
-        b.rec_extra[read] = base;
-        if (base + cnt - 1 <= b.pool_cap)
-            for (u32 i2 = 1; i2 < cnt; ++i2) b.rec_pool[base + i2 - 1] = local[i2];
-    }
-}
-
-// Second pass over the (rare) reads flagged by the first: same routine, kBigGroups-entry storage
-// in global scratch.  One thread per flagged read, list built on the device by k_select.  The
-// routine runs twice in the thread (count, then write) and the records take the same route as
-// everybody else's -- first record staged per read, the rest in a contiguous pool block -- so that
-// the scan + compaction that follows needs no special case.  Reads that overflow even this pass
-// keep bit 1 and get bit 2 (the library reports them).
-__global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u32 n_list, unsigned char *scratch) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_list) return;
-    u32 read = list[i];
-    EndInfo *ends;
-    SelectStore st = big_store(scratch + (size_t)i * kBigScratchBytes, ends);
-    SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
-    unsigned char flags;
-    const u32 cnt = select_read(c, ends, st, nullptr, 0xFFFFFFFFu, flags);
-    b.rec_count[read] = cnt;
-    if (flags & 2) {
-        b.read_flags[read] = (unsigned char)((flags & 1) | 2 | 4);
-        return;
-    }
-    b.read_flags[read] = (unsigned char)(flags & 1);
-    if (!cnt) return;
-    const u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt);
-    if ((u64)base + cnt > b.pool_cap) return;           // pool overflow: the library grows it and re-runs selection
-    select_read(c, ends, st, b.rec_pool + base, cnt, flags);
-    b.rec_stage[read] = b.rec_pool[base];
-    b.rec_extra[read] = base + 1;
-}
-
-// Stage 3c.  rec_count -> rec_offset (exclusive scan, n + 1 entries), the per-read flag counters, and
-// the read-ordered compaction of the staged records, in ONE pass: a single-pass scan with decoupled
-// look-back over 1024-read tiles (tile ids are taken from a ticket counter, so a tile only ever waits
-// for tiles that already started), then each tile moves its own records (four threads per 64-byte
-// record, 16-byte quarters, coalesced both ways).  Replaces a two-launch scan plus a compaction
-// launch that needed a host round trip in between (profiles/r1_v14_ncu_full.md: 67 us for 3 MB of
-// counts and 49 MB of records).
-//
-// Tile status word: epoch (30 bits) | state (2 bits: 1 = tile aggregate, 2 = inclusive prefix) |
-// value (32 bits).  The epoch changes with every launch, so the status array is never cleared.
-constexpr int kScanTile = 1024, kScanThreads = 256;
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_compact(SMX_KARGS, u32 rec_cap, unsigned long long *tile_status,
-                                                               u32 *ticket, u32 ticket_base, u32 epoch) {
-    __shared__ u32 s_off[kScanTile + 1];
-    __shared__ unsigned char s_big[kScanTile];
-    __shared__ u32 s_warp[kScanThreads / 32];
-    __shared__ u32 s_tile, s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    __syncthreads();
-    const u32 tile = s_tile, n = b.n_reads;
-    const u32 r0 = tile * kScanTile + threadIdx.x * 4;
-    // four consecutive reads per thread
-    u32 c[4] = {0, 0, 0, 0};
-    unsigned f[4] = {0, 0, 0, 0};
-    if (r0 + 3 < n) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(b.rec_count + r0);
-        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
-        const uchar4 g = *reinterpret_cast<const uchar4 *>(b.read_flags + r0);
-        f[0] = g.x; f[1] = g.y; f[2] = g.z; f[3] = g.w;
-    } else {
-        for (int i = 0; i < 4; ++i) if (r0 + i < n) { c[i] = b.rec_count[r0 + i]; f[i] = b.read_flags[r0 + i]; }
-    }
-    const u32 fm = (f[0] & 1) + (f[1] & 1) + (f[2] & 1) + (f[3] & 1);
-    const u32 fo = ((f[0] >> 1) & 1) + ((f[1] >> 1) & 1) + ((f[2] >> 1) & 1) + ((f[3] >> 1) & 1);
-    const u32 fh = ((f[0] >> 2) & 1) + ((f[1] >> 2) & 1) + ((f[2] >> 2) & 1) + ((f[3] >> 2) & 1);
-    const u32 wm = __reduce_add_sync(0xffffffffu, fm), wo = __reduce_add_sync(0xffffffffu, fo), wh = __reduce_add_sync(0xffffffffu, fh);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        if (wm) atomicAdd(&b.counters[4], (unsigned long long)wm);            // reads with a full match
-        if (wo) atomicAdd((unsigned int *)&b.counters[5], wo);                 // reads needing the big pass
-        if (wh) atomicAdd((unsigned int *)&b.counters[5] + 1, wh);             // reads beyond even that
-    }
-    const u32 tsum = c[0] + c[1] + c[2] + c[3];
-    u32 incl = tsum;
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 x = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += x;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        u32 w = lane < kScanThreads / 32 ? s_warp[lane] : 0u, wi = w;
-        for (int o = 1; o < kScanThreads / 32; o <<= 1) {
-            const u32 x = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += x;
-        }
-        if (lane < kScanThreads / 32) s_warp[lane] = wi - w;                   // exclusive prefix of the warp totals
-        const u32 total = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
-        if (lane == 0) {
-            const unsigned long long tag = (unsigned long long)epoch << 34;
-            volatile unsigned long long *st = tile_status;
-            u32 excl = 0;
-            if (tile == 0) {
-                st[0] = tag | (2ull << 32) | total;
-            } else {
-                st[tile] = tag | (1ull << 32) | total;
-                __threadfence();
-                for (u32 j = tile; j-- > 0;) {
-                    unsigned long long v;
-                    do { v = st[j]; } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0);
-                    excl += (u32)v;
-                    if (((v >> 32) & 3ull) == 2ull) break;
-                }
-                st[tile] = tag | (2ull << 32) | (u32)(excl + total);
-            }
-            s_prefix = excl;
-            if ((u64)(tile + 1) * kScanTile >= n) {                            // last tile: grand total
-                b.rec_offset[n] = excl + total;
-                *(u32 *)&b.counters[6] = excl + total;
-            }
-        }
-    }
-    __syncthreads();
-    u32 off = s_prefix + s_warp[warp] + incl - tsum;
-    for (int i = 0; i < 4; ++i) {
-        s_off[threadIdx.x * 4 + i] = off;
-        s_big[threadIdx.x * 4 + i] = (unsigned char)(f[i] & 2);
-        if (r0 + i < n) b.rec_offset[r0 + i] = off;
-        off += c[i];
-    }
-    if (threadIdx.x == kScanThreads - 1) s_off[kScanTile] = off;
-    __syncthreads();
-    // compaction of the tile's records: four quarters in flight per thread (loads first, then stores)
-    const u32 tile_r0 = tile * kScanTile;
-#pragma unroll 1
-    for (u32 base = 0; base < kScanTile * 4; base += 4 * kScanThreads) {
-        uint4 v[4];
-        u32 o[4], cnt[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const u32 idx = base + k * kScanThreads + threadIdx.x, lr = idx >> 2, read = tile_r0 + lr;
-            o[k] = s_off[lr];
-            cnt[k] = read < n ? s_off[lr + 1] - o[k] : 0u;
-            if (cnt[k] && (s_big[lr] || (u64)o[k] + cnt[k] > rec_cap)) cnt[k] = 0;      // k_select_big writes flagged reads
-            if (cnt[k]) v[k] = reinterpret_cast<const uint4 *>(b.rec_stage + read)[idx & 3];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!cnt[k]) continue;
-            const u32 idx = base + k * kScanThreads + threadIdx.x, q = idx & 3, read = tile_r0 + (idx >> 2);
-            uint4 *dst = reinterpret_cast<uint4 *>(b.records + o[k]);
-            dst[q] = v[k];
-            if (cnt[k] > 1) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(b.rec_pool + b.rec_extra[read]);
-                for (u32 i = q; i < 4 * (cnt[k] - 1); i += 4) dst[4 + i] = src[i];
-            }
-        }
-    }
-}
-
-// smx_record -> smx_record32 (drops the four location pairs) ahead of the copy-out.
-__global__ void __launch_bounds__(256) k_pack_records32(const smx_record *in, u32 n, smx_record32 *out) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const smx_record r = in[i];
-    smx_record32 o;
-    o.read = r.read; o.sample = r.sample; o.trim_start = r.trim_start; o.trim_end = r.trim_end;
-    o.pool = r.pool; o.p1 = r.p1; o.p2 = r.p2;
-    o.dist[0] = r.dist[0]; o.dist[1] = r.dist[1]; o.dist[2] = r.dist[2]; o.dist[3] = r.dist[3];
-    o.resolution = r.resolution;
-    o.flags = (uint8_t)((r.reverse ? 1 : 0) | (r.trim_empty ? 2 : 0));
-    o.candidate = r.candidate; o.pad[0] = o.pad[1] = o.pad[2] = 0;
-    out[i] = o;
-}
-
-// rec_offset of a sub-batch in the caller's whole batch (its records start at rec_base).
-__global__ void __launch_bounds__(256) k_rebase_offsets(const u32 *in, u32 n, u32 rec_base, u32 *out) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i] + rec_base;
-}
-
-// Batched global (NW) distances for setup_match_parameters (orchestration.py:549-555):
-// one thread per ordered pair (i, j), Myers with D[0][j] = j, score read at the last column.
-__global__ void k_pairwise_nw(const char *seqs, const u32 *off, u32 n, i32 *out) {
-    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (u64)n * n) return;
-    u32 i = (u32)(idx / n), j = (u32)(idx % n);
-    const char *a = seqs + off[i], *bseq = seqs + off[j];
-    int m = (int)(off[i + 1] - off[i]), len = (int)(off[j + 1] - off[j]);
-    if (m == 0 || len == 0) { out[idx] = m > len ? m : len; return; }
-    // plain equality (edlib default alphabet, no additionalEqualities at orchestration.py:552)
-    u64 Pv = pattern_mask<u64>(m), Mv = 0;
-    int score = m;
-    for (int x = 0; x < len; ++x) {
-        char ch = bseq[x];
-        u64 Eq = 0;
-        for (int r = 0; r < m; ++r) if (a[r] == ch) Eq |= 1ull << (64 - m + r);
-        score += myers_step<u64, true>(Eq, Pv, Mv);
-    }
-    out[idx] = score;
-}
-// Integer-ALU peak microbenchmark: 8 independent chains per thread, fully unrolled.
-// MODE 0: LOP3 only, 1: IADD3 only, 2: alternating.
-template <int MODE>
-__global__ void __launch_bounds__(256) k_int_peak(u32 *out, int iters, u32 seed) {
-    u32 a[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = seed * (threadIdx.x + 1) + j * 0x9E3779B9u + blockIdx.x;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                u32 x = a[j], y = a[(j + 1) & 7], z = a[(j + 3) & 7];
-                bool logic = MODE == 0 || (MODE == 2 && ((j + u) & 1));
-                a[j] = logic ? ((x & y) ^ z) : (x + y + z);
-            }
-        }
-    }
-    u32 r = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r ^= a[j];
-    if (r == 0x12345678u) out[0] = r;       // practically never; keeps the chains alive
-}
-#endif  // __CUDACC__
 
 }  // namespace smx

@@ -1,0 +1,35 @@
+// smx_launch.hpp -- host-callable launchers of the kernels (one translation unit per stage, see Makefile).
+// Every launcher enqueues on `st` and returns the launch error (cudaGetLastError), nothing synchronises.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "smx_core.cuh"
+
+namespace smx {
+
+constexpr int kScanTile = 1024;         // reads per tile of k_scan_compact (sizes the tile status array)
+
+// stage 0 / 1
+cudaError_t launch_stage_windows(const Tables &t, const Batch &b, cudaStream_t st);
+// prow_code: the primer's 32 pattern-row IUPAC codes (HostTables::prow_code + 32 * primer)
+cudaError_t launch_primer_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st);
+// finish of both strands per (read, primer) + work entries + (with_start) start of the first location
+cudaError_t launch_primer_finish(const Tables &t, const Batch &b, bool with_start, cudaStream_t st);
+cudaError_t launch_primer_long(const Tables &t, const Batch &b, int primer, cudaStream_t st);
+// stage 2: one launch per task width present; class_tasks is the DEVICE copy of HostTables::bt_class_tasks,
+// class_off the host offsets.  *launches receives the number of kernels enqueued.
+cudaError_t launch_barcode_tasks(const Tables &t, const Batch &b, const unsigned short *class_tasks,
+                                 const u32 class_off[kMaxTaskWords + 1], cudaStream_t st, int *launches);
+// stage 3
+cudaError_t launch_select_fast(const Tables &t, const Batch &b, cudaStream_t st);
+cudaError_t launch_select(const Tables &t, const Batch &b, cudaStream_t st);
+cudaError_t launch_select_big(const Tables &t, const Batch &b, const u32 *list, u32 n_list, unsigned char *scratch, cudaStream_t st);
+cudaError_t launch_scan_compact(const Tables &t, const Batch &b, u32 rec_cap, unsigned long long *tile_status, u32 *ticket,
+                                u32 ticket_base, u32 epoch, cudaStream_t st);
+cudaError_t launch_pack_records32(const smx_record *in, u32 n, smx_record32 *out, cudaStream_t st);
+cudaError_t launch_rebase_offsets(const u32 *in, u32 n, u32 rec_base, u32 *out, cudaStream_t st);
+// utilities
+cudaError_t launch_pairwise_nw(const char *seqs, const u32 *off, u32 n, i32 *out, cudaStream_t st);
+cudaError_t launch_int_peak(int mode, int blocks, int threads, u32 *out, int iters, u32 seed, cudaStream_t st);
+
+}  // namespace smx

@@ -205,6 +205,10 @@ def _run(args, multi: bool):
     if args.diagnostics and args.output_to_files:
         from .trace import TraceLogger
         trace_logger = TraceLogger(True, args.diagnostics, args.output_dir, "main", stamp)
+        if n_gpus > 1:
+            # the reference writes one trace file per worker process; here one ordered stream is kept instead
+            logging.warning(f"Trace output (-d) runs on one GPU (of {n_gpus}) so that events stay in input order")
+            n_gpus = 1
 
     from concurrent.futures import ThreadPoolExecutor
     from collections import deque
@@ -213,32 +217,41 @@ def _run(args, multi: bool):
     output_manager = OutputManager(args.output_dir, args.output_file_prefix, args.isfastq) if args.output_to_files else None
     if output_manager:
         output_manager.__enter__()
+    # One single-thread executor PER GPU: a device's Matcher (and the pinned result pool its records are views
+    # into) is only ever touched by that device's own thread, which converts a batch's records into
+    # WriteOperations before it starts the next match.  Batches are dealt round-robin and their results consumed
+    # in submission order, so the per-file record order is the input order (= the reference's `-t 1` order) for
+    # any GPU count.
+    executors = [ThreadPoolExecutor(max_workers=1) for _ in range(n_gpus)]
     try:
-        # One feeder thread per GPU (ctypes releases the GIL inside the C call); batches are dealt
-        # round-robin and their results consumed in submission order, so the per-file record order
-        # is the input order (= the reference's `-t 1` order) for any GPU count.
-        with ThreadPoolExecutor(max_workers=n_gpus) as pool:
-            pending = deque()
+        pending = deque()
 
-            def drain(limit):
-                nonlocal total, matched
-                while len(pending) > limit:
-                    ops, n, m = pending.popleft().result()
-                    for op in ops:
-                        output_write_operation(op, output_manager, args, trace_logger)
-                    total += n
-                    matched += m
+        def consume(ops, n, m):
+            nonlocal total, matched
+            for op in ops:
+                output_write_operation(op, output_manager, args, trace_logger)
+            total += n
+            matched += m
 
-            per_call = TRACE_BATCH_READS if trace_logger is not None else GPU_BATCH_READS
-            for i, batch in enumerate(iter_batches(seq_records, per_call, args.num_seqs, all_seqs)):
-                # tracing needs the batch processed in the main thread order; it still runs on the GPU
-                fut = pool.submit(process_sequences, batch, parameters, specimens, args, prefilter,
-                                  trace_logger if n_gpus == 1 else None, offset, i % n_gpus)
-                offset += len(batch)
-                pending.append(fut)
+        def drain(limit):
+            while len(pending) > limit:
+                consume(*pending.popleft().result())
+
+        per_call = TRACE_BATCH_READS if trace_logger is not None else GPU_BATCH_READS
+        for i, batch in enumerate(iter_batches(seq_records, per_call, args.num_seqs, all_seqs)):
+            if trace_logger is not None:
+                # tracing: a batch's search events and its SEQUENCE_OUTPUT events are logged back to back from
+                # this thread, in the order a reference worker logs them (multiprocessing_utils.py:89-99)
+                consume(*process_sequences(batch, parameters, specimens, args, prefilter, trace_logger, offset, 0))
+            else:
+                pending.append(executors[i % n_gpus].submit(process_sequences, batch, parameters, specimens, args,
+                                                            prefilter, None, offset, i % n_gpus))
                 drain(2 * n_gpus)
-            drain(0)
+            offset += len(batch)
+        drain(0)
     finally:
+        for ex in executors:
+            ex.shutdown(wait=True)
         if output_manager:
             output_manager.__exit__(None, None, None)
         if trace_logger:

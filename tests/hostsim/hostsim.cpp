@@ -148,6 +148,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     std::vector<unsigned short> ent_pos;
     std::vector<unsigned char> bh_count;
     std::vector<smx_barcode_hit> bh_list;
+    std::vector<BarcodeDigest> bdig;
     u32 e_cap = 16;        // deliberately tiny: exercises the capacity re-run
     unsigned long long counters[kCtrWords] = {0};
     Batch b;
@@ -217,20 +218,29 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                 const u64 *rev = t.peq_rcrev + (size_t)(slot % nP) * 16;
                 if (t.use64) primer_start_thread<u64>(t, b, slot, e, rev); else primer_start_thread<u32>(t, b, slot, e, rev);
             }
+        bdig.assign((size_t)2 * t.n_btasks * e_cap + 1, BarcodeDigest());
+        b.bdig = bdig.data();
         for (int s = 0; s < 2; ++s)
-            for (int g = 0; g < t.n_bwords; ++g) {
-                const u32 *rows = t.beq + (size_t)t.bw_row[g] * 16;
-                int p = t.bw_primer[g];
+            for (int tk = 0; tk < t.n_btasks; ++tk) {
+                const u32 g0 = t.bt_g0[tk];
+                const u32 *tab = t.bt_eq + t.bt_row[tk];
+                const int p = t.bw_primer[g0], m = t.bw_len[g0], nw = t.bt_nw[tk];
                 u32 slot = (u32)(s * nP + p);
                 for (u32 e = 0; e < slot_count[slot]; ++e) {
                     u32 r = ent_read[(size_t)slot * e_cap + e];
                     int pos = ent_pos[(size_t)slot * e_cap + e];
-                    switch (t.k_idx) {
-#define SMX_K2(KK) case KK: barcode_bitsliced_thread<KK>(t, b, r, pos, e, s, p, (u32)g, rows, counters[1], counters[3]); break;
-                        SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
+                    u32 work = 0;
+                    switch (t.k_idx * 8 + nw) {
+#define SMX_K2(KK, NN) case KK * 8 + NN: work = barcode_task_thread<KK, NN>(t, b, r, pos, e, s, p, (u32)tk, tab); break;
+#define SMX_K2M(KK) SMX_K2(KK, 1) SMX_K2(KK, 2) SMX_K2(KK, 3) SMX_K2(KK, 4)
+                        SMX_K2M(0) SMX_K2M(1) SMX_K2M(2) SMX_K2M(3) SMX_K2M(4)
+                        SMX_K2(5, 1) SMX_K2(6, 1) SMX_K2(7, 1) SMX_K2(8, 1)
+#undef SMX_K2M
 #undef SMX_K2
-                        default: snprintf(g_err, sizeof(g_err), "unsupported k_idx"); return SMX_ERR_ARG;
+                        default: snprintf(g_err, sizeof(g_err), "unsupported k_idx / task width"); return SMX_ERR_ARG;
                     }
+                    counters[1] += (unsigned long long)work * m;
+                    counters[3] += (unsigned long long)work * ((m + 31) >> 5);
                 }
             }
         if (counters[7] == 0) break;

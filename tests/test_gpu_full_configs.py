@@ -51,7 +51,7 @@ def test_non_acgt_sprinkled(cfg, n, flags):
     """1 in 2,000 bases replaced by N / IUPAC / lower case: those reads take the exact 4-bit side stream."""
     fig = fullcfg.compare(cfg, n, flags, sprinkle=2000)
     _report(fig)
-    assert fig["flagged_reads"] > 0.2 * n
+    assert fig["flagged_reads"] > 0.03 * n
 
 
 @pytest.mark.parametrize("derep,tiny", [("best", False), ("none", False), ("best", True)])
