@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SMX_ABI_VERSION 2
+#define SMX_ABI_VERSION 3
 
 #define SMX_MAX_PRIMERS 64      /* canonical primers (distinct sequences)                         */
 #define SMX_MAX_PATTERN 64      /* primer / barcode length handled by the single-thread kernels   */
@@ -116,6 +116,12 @@ typedef struct smx_params {
  *  clip_len : 0 = whole reads are packed.  Otherwise every read longer than 2*clip_len is stored as
  *             its first clip_len bases followed by its last clip_len bases (the only bases the
  *             path ever looks at when clip_len >= search_len); `lengths` keeps the TRUE length.
+ *  stride_words : 0 = reads are packed back to back and word_off gives every read's first word.  Otherwise
+ *             every read owns exactly stride_words words (read r starts at word r * stride_words) and word_off
+ *             is not read (may be NULL): the form the packer produces for clipped batches, where all but the
+ *             rare short reads store 2 * clip_len bases anyway.  Saves the 8-byte offset per read on the wire.
+ *  lengths16: optional 16-bit form of `lengths` (all reads shorter than 65,536 bases); when non-NULL
+ *             `lengths` is not read.
  *  packed4  : optional exact side stream for reads containing any non-ACGT symbol (NULL if none).
  *             For such a read r, off4[r] != UINT64_MAX and packed4 holds the forward strand then the
  *             reverse-complement strand (Biopython ambiguous-DNA complement, U->A), each
@@ -132,6 +138,8 @@ typedef struct smx_batch {
     uint64_t packed4_words;
     const uint64_t *off4;       /* may be NULL when packed4 is NULL */
     uint32_t clip_len;          /* see above; must be 0 or >= search_len */
+    uint32_t stride_words;      /* see above; 0 = use word_off */
+    const uint16_t *lengths16;  /* may be NULL (then `lengths` is used) */
 } smx_batch;
 
 /*
@@ -180,6 +188,25 @@ typedef struct smx_record32 {
     uint8_t candidate;
     uint8_t pad[3];
 } smx_record32;             /* 32 bytes */
+
+/*
+ * Wire form of a record for output paths that write the per-specimen files (io_utils.py:233-268): 16 bytes.
+ * Records come in read order, a read's records consecutive; `flags` bit 5 marks the LAST record of its read,
+ * so neither the read index nor rec_offset travels.  trim_end is sent as its distance from the read end:
+ * both extents lie within search_len + barcode length of an end of the read (models.py:278-319), so 16 bits
+ * hold them (SMX_MAX_SEARCH_LEN = 1024); should one ever not fit, the call fails with SMX_ERR_INTERNAL
+ * (never a silently wrong extent) and the caller asks for smx_record32 records instead.
+ */
+typedef struct smx_record16 {
+    int32_t sample;            /* as smx_record.sample                                            */
+    uint16_t trim_start;       /* slice [trim_start, length - trim_tail) of the oriented read     */
+    uint16_t trim_tail;
+    int16_t pool;              /* -1 = "unknown"                                                  */
+    uint8_t p1, p2;            /* canonical primer index, 0xFF = "unknown"                        */
+    uint8_t dist_p1, dist_p2;  /* primer edit distances, 0xFF = 'X'                               */
+    uint8_t dist_b;            /* barcode distances: b1 in the low nibble, b2 in the high one, 0xF = 'X' */
+    uint8_t flags;             /* bits 0-2 resolution (SMX_RES_*), bit 3 reverse, bit 4 trim_empty, bit 5 last of read */
+} smx_record16;             /* 16 bytes */
 
 /* Optional per-search detail (level-1 results), used by parity tests and trace emission.
  * Slot index: ((strand * n_primers + primer) * n_reads + read); strand 0 = read as given,
@@ -232,6 +259,9 @@ typedef struct smx_results {
     uint64_t n_barcode_loc_hits; /* out: entries that exist (may exceed the capacity: call again with more)       */
     smx_record32 *records32;   /* optional: when non-NULL (and `records` NULL) the records are returned in the
                                   compact form; records_cap then counts smx_record32 entries                     */
+    smx_record16 *records16;   /* optional: when non-NULL (and the two above NULL) the records are returned in the
+                                  16-byte wire form; records_cap counts smx_record16 entries; rec_offset may be
+                                  NULL (the last-of-read flag carries the grouping)                              */
 } smx_results;
 
 typedef struct smx_ctx smx_ctx;
@@ -331,6 +361,18 @@ void smx_pack_bound(const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len
 int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
                    uint32_t *packed2, uint64_t *word_off, uint32_t *lengths,
                    uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged);
+
+/* Fixed-stride form of the packer for clipped batches (clip_len > 0): every read owns
+ * smx_pack_stride(clip_len) words of `packed2` (n_reads * stride + 1 words in all), no word_off.  lengths16
+ * (optional) receives the 16-bit lengths when every read is shorter than 65,536 bases; *lengths_fit16 says so. */
+uint32_t smx_pack_stride(uint32_t clip_len);
+int smx_pack_reads_fixed(const char *bases, const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
+                         uint32_t *packed2, uint32_t *lengths, uint16_t *lengths16, int *lengths_fit16,
+                         uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged);
+
+/* Measured pinned-memory copy bandwidth of `device` (GB/s) for `bytes`-sized transfers: out[0] host-to-device,
+ * out[1] device-to-host, out[2] both directions at once (sum of the two).  The roofline of the host-buffer path. */
+int smx_copy_peak(int device, uint64_t bytes, double out_gbs[3]);
 
 #ifdef __cplusplus
 }

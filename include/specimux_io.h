@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SMX_IO_ABI_VERSION 1
+#define SMX_IO_ABI_VERSION 2
 
 #define SMX_IO_OK 0
 #define SMX_IO_ERR_ARG 1
@@ -104,6 +104,10 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *reco
 
 /* Same for the compact record form (smx_record32: everything the files need, no location pairs). */
 int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *records, uint64_t n_records);
+
+/* Same for the 16-byte wire form (smx_record16): records in read order covering the block's reads from read 0,
+ * read indices recovered from the last-of-read flags, trim_end from the reads' lengths. */
+int smx_writer_write16(smx_writer *w, const smx_block *blk, const smx_record16 *records, uint64_t n_records);
 
 /* Flushes every buffer and releases the writer.  Returns the first error seen, if any. */
 int smx_writer_close(smx_writer *w);

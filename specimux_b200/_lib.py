@@ -15,8 +15,8 @@ SMX_OK, SMX_ERR_ARG, SMX_ERR_CUDA, SMX_ERR_NO_DEVICE, SMX_ERR_CAPACITY, SMX_ERR_
 TRIM_CODES = {"none": 0, "primers": 1, "barcodes": 2, "tails": 3}
 NONE = -(2 ** 31)
 
-u8p, u32p, u64p, i32p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
-                         C.POINTER(C.c_int32))
+u8p, u16p, u32p, u64p, i32p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                               C.POINTER(C.c_int32))
 
 
 class SmxTables(C.Structure):
@@ -38,7 +38,7 @@ class SmxParams(C.Structure):
 class SmxBatch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("packed2", u32p), ("packed2_words", C.c_uint64),
                 ("word_off", u64p), ("lengths", u32p), ("packed4", u32p), ("packed4_words", C.c_uint64),
-                ("off4", u64p), ("clip_len", C.c_uint32)]
+                ("off4", u64p), ("clip_len", C.c_uint32), ("stride_words", C.c_uint32), ("lengths16", u16p)]
 
 
 class SmxResults(C.Structure):
@@ -46,7 +46,7 @@ class SmxResults(C.Structure):
                 ("n_records", C.c_uint64), ("n_matched", C.c_uint64), ("endmask_bits", C.c_void_p),
                 ("primer_hits", C.c_void_p), ("barcode_hits", C.c_void_p), ("orient_hits", C.c_void_p),
                 ("barcode_loc_hits", C.c_void_p), ("barcode_loc_cap", C.c_uint64), ("n_barcode_loc_hits", C.c_uint64),
-                ("records32", C.c_void_p)]
+                ("records32", C.c_void_p), ("records16", C.c_void_p)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<i4"), ("trim_end", "<i4"),
@@ -61,6 +61,10 @@ RECORD32_DTYPE = np.dtype([("read", "<u4"), ("sample", "<i4"), ("trim_start", "<
                            ("pool", "<i2"), ("p1", "<i2"), ("p2", "<i2"), ("dist", "i1", (4,)), ("resolution", "u1"),
                            ("flags", "u1"), ("candidate", "u1"), ("pad", "u1", (3,))])
 assert RECORD32_DTYPE.itemsize == 32
+# smx_record16, the 16-byte wire form: records in read order, flags bit 5 = last record of its read
+RECORD16_DTYPE = np.dtype([("sample", "<i4"), ("trim_start", "<u2"), ("trim_tail", "<u2"), ("pool", "<i2"), ("p1", "u1"),
+                           ("p2", "u1"), ("dist_p1", "u1"), ("dist_p2", "u1"), ("dist_b", "u1"), ("flags", "u1")])
+assert RECORD16_DTYPE.itemsize == 16
 BARCODE_LOC_HIT_DTYPE = np.dtype([("read", "<u4"), ("slot", "<u2"), ("location", "<u2"), ("hit", BARCODE_HIT_DTYPE)])
 assert BARCODE_LOC_HIT_DTYPE.itemsize == 24
 assert RECORD_DTYPE.itemsize == 64 and PRIMER_HIT_DTYPE.itemsize == 12 and BARCODE_HIT_DTYPE.itemsize == 16
@@ -70,7 +74,7 @@ EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create"
            "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
            "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads", "smx_int_alu_peak", "smx_host_alloc",
            "smx_host_free", "smx_flush_l2", "smx_set_pipeline_chunk", "smx_last_chunk_count", "smx_last_deferred", "smx_last_kernel_times", "smx_set_resident_split",
-           "smx_device_pci_bus_id"]
+           "smx_device_pci_bus_id", "smx_pack_stride", "smx_pack_reads_fixed", "smx_copy_peak"]
 
 
 class SmxError(RuntimeError):
@@ -121,7 +125,12 @@ def load():
         lib.smx_last_deferred.restype = C.c_uint64
         lib.smx_set_resident_split.argtypes = [C.c_void_p, C.c_uint32]
         lib.smx_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
-        if lib.smx_abi_version() != 2:
+        lib.smx_pack_stride.argtypes = [C.c_uint32]
+        lib.smx_pack_stride.restype = C.c_uint32
+        lib.smx_pack_reads_fixed.argtypes = [C.c_char_p, u64p, C.c_uint32, C.c_uint32, u32p, u32p, u16p, C.POINTER(C.c_int),
+                                             u32p, u64p, u64p, u32p]
+        lib.smx_copy_peak.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_double)]
+        if lib.smx_abi_version() != 3:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib
     return _lib

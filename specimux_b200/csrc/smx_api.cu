@@ -92,6 +92,9 @@ struct Lane {
     DevBuf<u32> defer_list;
     DevBuf<smx_record> rec_stage, rec_pool, records;
     DevBuf<smx_record32> records32;             // compact copy of `records` (only when the caller asks for it)
+    DevBuf<smx_record16> records16;             // 16-byte wire form of `records` (only when the caller asks for it)
+    DevBuf<unsigned short> lengths16;           // 16-bit lengths as uploaded (expanded into `lengths` on the device)
+    DevBuf<u32> bad16;                          // records whose extents did not fit smx_record16 (cumulative, must stay 0)
     DevBuf<unsigned char> big_scratch;
     // control block: 8 counters (4 work, matched, (u32,u32) overflow, (u32,u32) total/pool, hit overflow)
     // followed by the 2 * SMX_MAX_PRIMERS per-slot entry counts -- one memset, one read-back
@@ -115,7 +118,7 @@ struct Lane {
         rec_count.release(); rec_offset.release(); rec_offset_out.release(); ticket.release(); tile_status.release(); word_off.release();
         off4.release(); phit.release(); orient_hit.release(); read_flags.release(); bh_count.release(); bh_list.release(); bdig.release();
         ent_base.release(); ent_read.release(); rec_extra.release(); big_list.release();
-        ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release(); records32.release();
+        ent_pos.release(); defer_list.release(); rec_stage.release(); rec_pool.release(); records.release(); records32.release(); records16.release(); lengths16.release(); bad16.release();
         big_scratch.release(); counters.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr; h_slot_counts = nullptr;
@@ -189,6 +192,8 @@ static cudaError_t lane_init(Lane &ln, int prio = 0) {
     if ((e = cudaHostAlloc((void **)&ln.h_counters, kCtlWords * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return e;
     ln.h_slot_counts = (u32 *)(ln.h_counters + kCtrWords);
     if ((e = ln.counters.ensure(kCtlWords)) != cudaSuccess) return e;
+    if ((e = ln.bad16.ensure(1)) != cudaSuccess) return e;
+    if ((e = cudaMemset(ln.bad16.p, 0, sizeof(u32))) != cudaSuccess) return e;
     memset(&ln.b, 0, sizeof(ln.b));
     return cudaSuccess;
 }
@@ -223,8 +228,10 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     const Tables &t = c->t;
     const u32 n = r1 - r0, n_pad = (n + 127u) & ~127u;
     const int nP = t.n_primers;
-    const u64 w0 = in->word_off[r0];
-    const u64 w1 = (r1 < in->n_reads) ? std::min<u64>(in->word_off[r1] + 1, in->packed2_words) : in->packed2_words;
+    const u64 stride = in->stride_words;
+    const u64 w0 = stride ? (u64)r0 * stride : in->word_off[r0];
+    const u64 w1 = stride ? std::min<u64>((u64)r1 * stride + 1, in->packed2_words)
+                          : ((r1 < in->n_reads) ? std::min<u64>(in->word_off[r1] + 1, in->packed2_words) : in->packed2_words);
     if (w1 < w0) return fail(SMX_ERR_ARG, "smx_batch: word_off is not ascending");
     {
         int prio = 0;
@@ -236,7 +243,9 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
         }
         CU(lane_init(ln, prio));
     }
-    CU(ln.packed2.ensure(w1 - w0 + 2)); CU(ln.word_off.ensure(n)); CU(ln.lengths.ensure(n));
+    ln.launches = 0;
+    CU(ln.packed2.ensure(w1 - w0 + 2)); if (!stride) CU(ln.word_off.ensure(n)); CU(ln.lengths.ensure(n));
+    if (in->lengths16) CU(ln.lengths16.ensure(n));
     const bool flagged = in->packed4 && in->off4 && in->packed4_words;
     if (flagged) { CU(ln.off4.ensure(n)); if (!shared4) CU(ln.packed4.ensure(in->packed4_words)); }
     CU(ln.win.ensure((size_t)2 * t.wpw * n_pad));
@@ -282,16 +291,22 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
         CU(ln.records.ensure((size_t)n_pad + ln.pool_cap + 1));
     }
     CU(cudaMemcpyAsync(ln.packed2.p, in->packed2 + w0, (w1 - w0) * sizeof(u32), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ln.word_off.p, in->word_off + r0, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ln.lengths.p, in->lengths + r0, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, st));
+    if (!stride) CU(cudaMemcpyAsync(ln.word_off.p, in->word_off + r0, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, st));
+    if (in->lengths16) {
+        CU(cudaMemcpyAsync(ln.lengths16.p, in->lengths16 + r0, (size_t)n * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
+        CU(launch_expand_lengths(ln.lengths16.p, n, ln.lengths.p, st));
+        ++ln.launches;
+    } else {
+        CU(cudaMemcpyAsync(ln.lengths.p, in->lengths + r0, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, st));
+    }
     if (flagged) {
         if (!shared4)
             CU(cudaMemcpyAsync(ln.packed4.p, in->packed4, in->packed4_words * sizeof(u32), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ln.off4.p, in->off4 + r0, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, st));
     }
     Batch &b = ln.b;
-    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len; b.word_base = w0; b.read_base = r0;
-    b.packed2 = ln.packed2.p; b.word_off = ln.word_off.p; b.lengths = ln.lengths.p;
+    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len; b.stride = (u32)stride; b.word_base = w0; b.read_base = r0;
+    b.packed2 = ln.packed2.p; b.word_off = stride ? nullptr : ln.word_off.p; b.lengths = ln.lengths.p;
     b.packed4 = flagged ? (shared4 ? shared4 : ln.packed4.p) : nullptr; b.off4 = flagged ? ln.off4.p : nullptr;
     b.win = ln.win.p; b.win2 = ln.win2.p; b.tmix = ln.tmix.p; b.phit = ln.phit.p; b.endmask = ln.endmask.p; b.impmask = ln.impmask.p; b.orient_hit = ln.orient_hit.p;
     b.slot_count = (u32 *)(ln.counters.p + kCtrWords); b.ent_base = ln.ent_base.p; b.defer_list = ln.defer_list.p; b.big_list = ln.big_list.p;
@@ -299,7 +314,6 @@ static int lane_upload(smx_ctx *c, Lane &ln, const smx_batch *in, u32 r0, u32 r1
     b.rec_count = ln.rec_count.p; b.rec_offset = ln.rec_offset.p;
     b.records = ln.records.p; b.read_flags = ln.read_flags.p; b.counters = ln.counters.p;
     ln.have_batch = true; ln.have_results = false;
-    ln.launches = 0;
     return SMX_OK;
 }
 
@@ -498,6 +512,11 @@ static int lane_copy_records(Lane &ln, smx_results *out, u64 rec_base, cudaStrea
         CU(launch_pack_records32(ln.records.p, (u32)ln.n_records, ln.records32.p, st));
         ++ln.launches;
         CU(cudaMemcpyAsync(out->records32 + rec_base, ln.records32.p, (size_t)ln.n_records * sizeof(smx_record32), cudaMemcpyDeviceToHost, st));
+    } else if (out->records16) {
+        CU(ln.records16.ensure((size_t)ln.n_records));
+        CU(launch_pack_records16(ln.records.p, (u32)ln.n_records, ln.b.lengths, ln.b.read_base, ln.records16.p, ln.bad16.p, st));
+        ++ln.launches;
+        CU(cudaMemcpyAsync(out->records16 + rec_base, ln.records16.p, (size_t)ln.n_records * sizeof(smx_record16), cudaMemcpyDeviceToHost, st));
     }
     return SMX_OK;
 }
@@ -518,6 +537,22 @@ static int lane_compact(smx_ctx *c, Lane &ln, u32 rec_base, bool timed) {
     if (timed) CU(cudaEventRecord(ln.ev[4], st));
     CU(cudaGetLastError());
     ln.have_results = true;
+    return SMX_OK;
+}
+
+// smx_record16 carries 16-bit extents: fail loudly if a record of the last call did not fit (never observed:
+// both extents lie within search_len + barcode length of a read end).
+static int check_record16_fit(smx_ctx *c) {
+    u32 bad = 0;
+    for (auto &ln : c->lane) {
+        if (!ln.stream || !ln.bad16.p) continue;
+        u32 v = 0;
+        CU(cudaMemcpy(&v, ln.bad16.p, sizeof(u32), cudaMemcpyDeviceToHost));
+        if (v) CU(cudaMemset(ln.bad16.p, 0, sizeof(u32)));
+        bad += v;
+    }
+    if (bad) return fail(SMX_ERR_INTERNAL, "%u record(s) do not fit smx_record16 (trim extent or id beyond its field); "
+                                           "ask for smx_record32 records", bad);
     return SMX_OK;
 }
 
@@ -643,7 +678,10 @@ uint64_t smx_result_bound(const smx_ctx *c, uint32_t n_reads) {
 static int check_batch(const smx_ctx *c, const smx_batch *in, const char *who) {
     if (!c || !in) return fail(SMX_ERR_ARG, "%s: null argument", who);
     if (in->n_reads == 0) return fail(SMX_ERR_ARG, "%s: empty batch", who);
-    if (!in->packed2 || !in->word_off || !in->lengths) return fail(SMX_ERR_ARG, "%s: null batch array", who);
+    if (!in->packed2 || (!in->word_off && !in->stride_words) || (!in->lengths && !in->lengths16))
+        return fail(SMX_ERR_ARG, "%s: null batch array", who);
+    if (in->stride_words && (u64)in->n_reads * in->stride_words > in->packed2_words)
+        return fail(SMX_ERR_ARG, "%s: packed2 holds fewer than n_reads * stride_words words", who);
     if (in->clip_len && (int)in->clip_len < c->t.L)
         return fail(SMX_ERR_ARG, "%s: clip_len %u is below search_len %d", who, in->clip_len, c->t.L);
     if ((in->packed4 == nullptr) != (in->off4 == nullptr) && in->packed4_words)
@@ -784,6 +822,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
         }
         for (int i = 0; i < c->resident_lanes; ++i) CU(cudaStreamSynchronize(c->lane[i].stream));
         if (out->rec_offset) out->rec_offset[c->resident_n] = (u32)total;
+        if (out->records16 && !out->records && !out->records32) return check_record16_fit(c);
         return SMX_OK;
     }
     const Batch &b = ln.b;
@@ -855,6 +894,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
             }
         out->n_barcode_loc_hits = n_loc_hits;
     }
+    if (out->records16 && !out->records && !out->records32) return check_record16_fit(c);
     return SMX_OK;
 }
 
@@ -974,6 +1014,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         return fail(SMX_ERR_CAPACITY, "smx_match_batch: %llu records, capacity %llu",
                     (unsigned long long)rec_base, (unsigned long long)out->records_cap);
     if (out->rec_offset) out->rec_offset[n] = (u32)rec_base;
+    if (out->records16 && !out->records && !out->records32) return check_record16_fit(c);
     return SMX_OK;
 }
 
@@ -1057,17 +1098,21 @@ int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint3
     }
     CU(cudaSetDevice(device));
     char *d_seq = nullptr; u32 *d_off = nullptr; i32 *d_out = nullptr;
-    size_t bytes = seq_off[n];
-    CU(cudaMalloc((void **)&d_seq, bytes ? bytes : 1));
-    CU(cudaMalloc((void **)&d_off, (size_t)(n + 1) * sizeof(u32)));
-    CU(cudaMalloc((void **)&d_out, (size_t)n * n * sizeof(i32)));
-    CU(cudaMemcpy(d_seq, seqs, bytes, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_off, seq_off, (size_t)(n + 1) * sizeof(u32), cudaMemcpyHostToDevice));
-    u64 total = (u64)n * n;
-    CU(launch_pairwise_nw(d_seq, d_off, n, d_out, 0));
-    CU(cudaMemcpy(out, d_out, total * sizeof(i32), cudaMemcpyDeviceToHost));
+    const size_t bytes = seq_off[n];
+    const u64 total = (u64)n * n;
+    auto run = [&]() -> int {
+        CU(cudaMalloc((void **)&d_seq, bytes ? bytes : 1));
+        CU(cudaMalloc((void **)&d_off, (size_t)(n + 1) * sizeof(u32)));
+        CU(cudaMalloc((void **)&d_out, (size_t)total * sizeof(i32)));
+        CU(cudaMemcpy(d_seq, seqs, bytes, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_off, seq_off, (size_t)(n + 1) * sizeof(u32), cudaMemcpyHostToDevice));
+        CU(launch_pairwise_nw(d_seq, d_off, n, d_out, 0));
+        CU(cudaMemcpy(out, d_out, total * sizeof(i32), cudaMemcpyDeviceToHost));
+        return SMX_OK;
+    };
+    const int rc = run();                                   // the device buffers go on every path
     cudaFree(d_seq); cudaFree(d_off); cudaFree(d_out);
-    return SMX_OK;
+    return rc;
 }
 
 int smx_int_alu_peak(int device, double out_tops[3]) {
@@ -1195,6 +1240,111 @@ int smx_pack_reads(const char *bases, const uint64_t *seq_off, uint32_t n_reads,
     if (packed4_words) *packed4_words = w4;
     if (n_flagged) *n_flagged = flagged;
     return SMX_OK;
+}
+
+uint32_t smx_pack_stride(uint32_t clip_len) { return (2 * clip_len + 15) / 16; }
+
+int smx_pack_reads_fixed(const char *bases, const uint64_t *seq_off, uint32_t n_reads, uint32_t clip_len,
+                         uint32_t *packed2, uint32_t *lengths, uint16_t *lengths16, int *lengths_fit16,
+                         uint32_t *packed4, uint64_t *off4, uint64_t *packed4_words, uint32_t *n_flagged) {
+    if (!bases || !seq_off || !packed2 || (!lengths && !lengths16)) return fail(SMX_ERR_ARG, "smx_pack_reads_fixed: null argument");
+    if (!clip_len) return fail(SMX_ERR_ARG, "smx_pack_reads_fixed: needs clip_len > 0 (unclipped reads have no common stride)");
+    const uint32_t stride = smx_pack_stride(clip_len);
+    uint64_t w4 = 0;
+    uint32_t flagged = 0;
+    bool fit16 = true;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const unsigned char *s = (const unsigned char *)bases + seq_off[r];
+        const uint64_t len = seq_off[r + 1] - seq_off[r];
+        if (len > 0x7FFFFFFFull) return fail(SMX_ERR_ARG, "smx_pack_reads_fixed: read %u too long", r);
+        const bool clipped = len > 2ull * clip_len;
+        const uint64_t slen = clipped ? 2ull * clip_len : len;
+        const uint64_t skip = len - slen;
+        auto src = [&](uint64_t i) { return (clipped && i >= clip_len) ? i + skip : i; };
+        if (lengths) lengths[r] = (uint32_t)len;
+        if (len > 0xFFFFull) fit16 = false;
+        else if (lengths16) lengths16[r] = (uint16_t)len;
+        bool exotic = false;
+        uint32_t *dst = packed2 + (uint64_t)r * stride;
+        const uint64_t nw = (slen + 15) / 16;
+        for (uint64_t w = 0; w < stride; ++w) {
+            uint32_t v = 0;
+            if (w < nw) {
+                const uint64_t lim = std::min<uint64_t>(16, slen - w * 16);
+                for (uint64_t i = 0; i < lim; ++i) {
+                    int c = read_code(s[src(w * 16 + i)]);
+                    if (c > 3) { exotic = true; c = 0; }
+                    v |= (uint32_t)c << (2 * i);
+                }
+            }
+            dst[w] = v;
+        }
+        if (off4) off4[r] = ~0ull;
+        if (exotic) {
+            if (!packed4 || !off4) return fail(SMX_ERR_ARG, "smx_pack_reads_fixed: read %u needs the packed4 stream", r);
+            off4[r] = w4;
+            const uint64_t n4 = (slen + 7) / 8;
+            for (uint64_t w = 0; w < 2 * n4; ++w) packed4[w4 + w] = 0;
+            for (uint64_t i = 0; i < slen; ++i) {
+                unsigned char ch = s[src(i)];
+                packed4[w4 + i / 8] |= (uint32_t)read_code(ch) << (4 * (i % 8));
+                uint64_t x = slen - 1 - i;
+                packed4[w4 + n4 + x / 8] |= (uint32_t)read_code_rc(ch) << (4 * (x % 8));
+            }
+            w4 += 2 * n4;
+            ++flagged;
+        }
+    }
+    packed2[(uint64_t)n_reads * stride] = 0;             // the slack word window extraction may read
+    if (packed4_words) *packed4_words = w4;
+    if (n_flagged) *n_flagged = flagged;
+    if (lengths_fit16) *lengths_fit16 = fit16 ? 1 : 0;
+    return SMX_OK;
+}
+
+int smx_copy_peak(int device, uint64_t bytes, double out_gbs[3]) {
+    if (!out_gbs || !bytes) return fail(SMX_ERR_ARG, "smx_copy_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SMX_ERR_NO_DEVICE, "smx_copy_peak: no CUDA device");
+    }
+    CU(cudaSetDevice(device));
+    void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    int rc = SMX_OK;
+    auto run = [&]() -> int {
+        CU(cudaHostAlloc(&h_in, bytes, cudaHostAllocDefault)); CU(cudaHostAlloc(&h_out, bytes, cudaHostAllocDefault));
+        memset(h_in, 0x5a, bytes); memset(h_out, 0, bytes);
+        CU(cudaMalloc(&d_in, bytes)); CU(cudaMalloc(&d_out, bytes));
+        CU(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+        for (int mode = 0; mode < 3; ++mode) {
+            float best = 1e30f;
+            for (int rep = 0; rep < 6; ++rep) {
+                CU(cudaEventRecord(e0, s0));
+                CU(cudaStreamWaitEvent(s1, e0, 0));
+                if (mode != 1) CU(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s0));
+                if (mode != 0) CU(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s1));
+                CU(cudaEventRecord(e2, s1));
+                CU(cudaStreamWaitEvent(s0, e2, 0));
+                CU(cudaEventRecord(e1, s0));
+                CU(cudaEventSynchronize(e1));
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep > 0 && ms < best) best = ms;
+            }
+            out_gbs[mode] = (mode == 2 ? 2.0 : 1.0) * (double)bytes / (best * 1e-3) / 1e9;
+        }
+        return SMX_OK;
+    };
+    rc = run();
+    if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2);
+    if (s0) cudaStreamDestroy(s0); if (s1) cudaStreamDestroy(s1);
+    if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out);
+    if (h_in) cudaFreeHost(h_in); if (h_out) cudaFreeHost(h_out);
+    return rc;
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@ namespace smx {
 
 static_assert(sizeof(smx_record) == 64, "smx_record layout");
 static_assert(sizeof(smx_record32) == 32, "smx_record32 layout");
+static_assert(sizeof(smx_record16) == 16, "smx_record16 layout");
 static_assert(sizeof(smx_primer_hit) == 12, "smx_primer_hit layout");
 static_assert(sizeof(smx_barcode_hit) == 16, "smx_barcode_hit layout");
 
@@ -46,6 +47,33 @@ SMX_HD int sym_complement(int c) {
     // A<->T C<->G R<->Y S W K<->M B<->V D<->H N other
     const u64 table = 0xFE'A'B'C'D'8'9'7'6'4'5'0'1'2'3ull;   // nibble i = complement of code i
     return (int)((table >> (4 * c)) & 15);
+}
+
+// ---------------------------------------------------------------------------------------------
+// smx_record -> the compact wire forms.
+
+SMX_HD void pack_record32(const smx_record &r, smx_record32 &o) {
+    o.read = r.read; o.sample = r.sample; o.trim_start = r.trim_start; o.trim_end = r.trim_end;
+    o.pool = r.pool; o.p1 = r.p1; o.p2 = r.p2;
+    o.dist[0] = r.dist[0]; o.dist[1] = r.dist[1]; o.dist[2] = r.dist[2]; o.dist[3] = r.dist[3];
+    o.resolution = r.resolution;
+    o.flags = (uint8_t)((r.reverse ? 1 : 0) | (r.trim_empty ? 2 : 0));
+    o.candidate = r.candidate; o.pad[0] = o.pad[1] = o.pad[2] = 0;
+}
+
+// n: true length of the record's read; last: last record of its read.  Returns false when an extent does not
+// fit 16 bits (see smx_record16).
+SMX_HD bool pack_record16(const smx_record &r, int n, bool last, smx_record16 &o) {
+    const int tail = n - r.trim_end;
+    o.sample = r.sample;
+    o.trim_start = (uint16_t)r.trim_start; o.trim_tail = (uint16_t)tail;
+    o.pool = r.pool;
+    o.p1 = (uint8_t)(r.p1 < 0 ? 0xFF : r.p1); o.p2 = (uint8_t)(r.p2 < 0 ? 0xFF : r.p2);
+    o.dist_p1 = (uint8_t)(r.dist[0] < 0 ? 0xFF : r.dist[0]); o.dist_p2 = (uint8_t)(r.dist[3] < 0 ? 0xFF : r.dist[3]);
+    o.dist_b = (uint8_t)((r.dist[1] < 0 ? 0xF : r.dist[1]) | ((r.dist[2] < 0 ? 0xF : r.dist[2]) << 4));
+    o.flags = (uint8_t)(r.resolution | (r.reverse ? 8 : 0) | (r.trim_empty ? 16 : 0) | (last ? 32 : 0));
+    return r.trim_start >= 0 && r.trim_start <= 0xFFFF && tail >= 0 && tail <= 0xFFFF && r.p1 < 0xFF && r.p2 < 0xFF &&
+           r.dist[1] < 0xF && r.dist[2] < 0xF;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,6 +265,7 @@ struct Batch {
     const u32 *packed4;
     const u64 *off4;         // nullptr when no read is flagged
     u32 clip;                // 0, or reads longer than 2*clip are stored as head clip + tail clip bases
+    u32 stride;              // 0, or every read owns `stride` words of packed2 (word_off unused)
     u64 word_base;           // word_off values are absolute stream offsets; packed2[0] is stream word word_base
     u32 read_base;           // index of this (sub-)batch's read 0 in the caller's batch (smx_record.read)
     u32 *win;                // staged 4-bit windows [(strand*wpw + w) * n_pad + read]
@@ -283,6 +312,11 @@ SMX_HD void counter_add(unsigned long long *p, unsigned long long v) {
 #endif
 }
 
+// First word of read r inside this (sub-)batch's packed2 buffer.
+SMX_HD u64 read_word0(const Batch &b, u32 r) {
+    return b.stride ? (u64)r * b.stride : b.word_off[r] - b.word_base;
+}
+
 SMX_HD bool read_is_flagged(const Batch &b, u32 r) {
     return b.off4 != nullptr && b.off4[r] != ~0ull;
 }
@@ -306,7 +340,7 @@ SMX_HD int sym_at(const Batch &b, u32 r, int strand, int x, int n) {
         return (int)((w >> (4 * (xs & 7))) & 15);
     }
     int i = stored_pos(b, strand ? n - 1 - x : x, n);
-    u32 w = b.packed2[b.word_off[r] - b.word_base + (u64)(i >> 4)];
+    u32 w = b.packed2[read_word0(b, r) + (u64)(i >> 4)];
     int c = (int)((w >> (2 * (i & 15))) & 3);
     return strand ? 3 - c : c;
 }

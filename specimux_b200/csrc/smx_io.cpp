@@ -769,6 +769,32 @@ int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *
     return smx_writer_write(w, blk, full.data(), n_records);
 }
 
+int smx_writer_write16(smx_writer *w, const smx_block *blk, const smx_record16 *recs, uint64_t n_records) {
+    if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write16: null argument");
+    // widen into the full layout: the read index comes from the last-of-read flags (records are in read order),
+    // trim_end from the read's length
+    std::vector<smx_record> full((size_t)n_records);
+    uint32_t read = 0;
+    const uint32_t n_reads = blk->n();
+    for (uint64_t i = 0; i < n_records; ++i) {
+        const smx_record16 &c = recs[i];
+        if (read >= n_reads) return fail(SMX_IO_ERR_ARG, "smx_writer_write16: records run past the block's %u reads", n_reads);
+        smx_record &r = full[i];
+        memset(&r, 0, sizeof(r));
+        const int64_t len = (int64_t)(blk->seq_off[read + 1] - blk->seq_off[read]);
+        r.read = read; r.sample = c.sample; r.trim_start = c.trim_start; r.trim_end = (int32_t)(len - c.trim_tail);
+        r.pool = c.pool; r.p1 = c.p1 == 0xFF ? -1 : c.p1; r.p2 = c.p2 == 0xFF ? -1 : c.p2;
+        r.dist[0] = c.dist_p1 == 0xFF ? -1 : (int8_t)c.dist_p1;
+        r.dist[1] = (c.dist_b & 0xF) == 0xF ? -1 : (int8_t)(c.dist_b & 0xF);
+        r.dist[2] = (c.dist_b >> 4) == 0xF ? -1 : (int8_t)(c.dist_b >> 4);
+        r.dist[3] = c.dist_p2 == 0xFF ? -1 : (int8_t)c.dist_p2;
+        r.resolution = c.flags & 7;
+        r.reverse = (c.flags >> 3) & 1; r.trim_empty = (c.flags >> 4) & 1;
+        if (c.flags & 32) ++read;
+    }
+    return smx_writer_write(w, blk, full.data(), n_records);
+}
+
 int smx_writer_close(smx_writer *w) {
     if (!w) return SMX_IO_OK;
     if (!w->threads.empty()) {

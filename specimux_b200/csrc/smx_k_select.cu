@@ -251,15 +251,28 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_compact(SMX_KARGS, u32 re
 __global__ void __launch_bounds__(256) k_pack_records32(const smx_record *in, u32 n, smx_record32 *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const smx_record r = in[i];
     smx_record32 o;
-    o.read = r.read; o.sample = r.sample; o.trim_start = r.trim_start; o.trim_end = r.trim_end;
-    o.pool = r.pool; o.p1 = r.p1; o.p2 = r.p2;
-    o.dist[0] = r.dist[0]; o.dist[1] = r.dist[1]; o.dist[2] = r.dist[2]; o.dist[3] = r.dist[3];
-    o.resolution = r.resolution;
-    o.flags = (uint8_t)((r.reverse ? 1 : 0) | (r.trim_empty ? 2 : 0));
-    o.candidate = r.candidate; o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    pack_record32(in[i], o);
     out[i] = o;
+}
+
+// smx_record -> smx_record16 (the 16-byte wire form).  read_base: index of the (sub-)batch's first read in the
+// caller's batch (smx_record.read is batch-wide); bad: counts records whose extents do not fit.
+__global__ void __launch_bounds__(256) k_pack_records16(const smx_record *in, u32 n, const u32 *lengths, u32 read_base,
+                                                        smx_record16 *out, u32 *bad) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const smx_record r = in[i];
+    const bool last = i + 1 >= n || in[i + 1].read != r.read;
+    smx_record16 o;
+    if (!pack_record16(r, (int)lengths[r.read - read_base], last, o)) atomicAdd(bad, 1u);
+    out[i] = o;
+}
+
+// 16-bit lengths of the wire form -> the 32-bit array every kernel reads.
+__global__ void __launch_bounds__(256) k_expand_lengths(const unsigned short *in, u32 n, u32 *out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
 // rec_offset of a sub-batch in the caller's whole batch (its records start at rec_base).
@@ -340,6 +353,17 @@ cudaError_t launch_scan_compact(const Tables &t, const Batch &b, u32 rec_cap, un
 
 cudaError_t launch_pack_records32(const smx_record *in, u32 n, smx_record32 *out, cudaStream_t st) {
     k_pack_records32<<<(n + 255) / 256, 256, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_records16(const smx_record *in, u32 n, const u32 *lengths, u32 read_base, smx_record16 *out, u32 *bad,
+                                  cudaStream_t st) {
+    k_pack_records16<<<(n + 255) / 256, 256, 0, st>>>(in, n, lengths, read_base, out, bad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_lengths(const unsigned short *in, u32 n, u32 *out, cudaStream_t st) {
+    k_expand_lengths<<<(n + 255) / 256, 256, 0, st>>>(in, n, out);
     return cudaGetLastError();
 }
 

@@ -24,19 +24,19 @@ __global__ void __launch_bounds__(2 * kStageBlock) k_stage_windows(SMX_KARGS, u3
     const Tables &t = c_tables;
     const u32 r0 = blockIdx.x * kStageBlock;
     const u32 r1 = r0 + kStageBlock < b.n_reads ? r0 + kStageBlock : b.n_reads;
-    const u64 w0 = b.word_off[r0];
-    const u64 w1 = b.word_off[r1 - 1] + (u64)((stored_len(b, (int)b.lengths[r1 - 1]) + 15) >> 4);
+    const u64 w0 = read_word0(b, r0);
+    const u64 w1 = read_word0(b, r1 - 1) + (u64)((stored_len(b, (int)b.lengths[r1 - 1]) + 15) >> 4);
     const bool tiled = w1 - w0 + 2 <= tile_words;                             // window extraction reads one word past the read
     if (tiled) {
         const u32 span = (u32)(w1 - w0) + 2;
-        const u32 *g = b.packed2 + (w0 - b.word_base);
+        const u32 *g = b.packed2 + w0;
         for (u32 i = threadIdx.y * kStageBlock + threadIdx.x; i < span; i += 2 * kStageBlock) s_src[i] = g[i];
     }
     __syncthreads();
     const u32 read = r0 + threadIdx.x;
     if (read >= b.n_reads) return;
     const u32 *src2 = tiled ? s_src : b.packed2;
-    const u64 origin = tiled ? w0 : b.word_base;
+    const u64 origin = tiled ? w0 : 0;
     const int strand = (int)threadIdx.y;
     for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, read, strand, w2, src2, origin);
 }

@@ -44,8 +44,9 @@ SMX_HD u32 revcomp16(u32 v) {
 // One thread stages 16 symbols of one strand: the 2-bit word win2[w2] (input of the sliced primer
 // search) and the two 4-bit words win[2*w2], win[2*w2+1] (barcode stage, start recovery, classic
 // primer search).  Positions past the staged length hold kSymOther in `win`.
-// `src2` / `src2_origin`: where the read's 2-bit words are read from -- src2[word_off[read] - src2_origin + i];
-// the packed stream itself (b.packed2, b.word_base) or a block's shared-memory copy of its reads' words.
+// `src2` / `src2_origin`: where the read's 2-bit words are read from -- src2[read_word0(read) - src2_origin + i];
+// the packed buffer itself (b.packed2, origin 0) or a block's shared-memory copy of its reads' words (origin =
+// first word of the block's first read).
 SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int strand, int w2, const u32 *src2, u64 src2_origin) {
     const int n = (int)b.lengths[read];
     const Geo g = make_geo(n, t.L);
@@ -61,7 +62,7 @@ SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int str
             const int x0 = g.woff + 16 * w2;                  // strand coordinate of symbol 0
             const int first = strand ? (n - 1 - x0) - 15 : stored_pos(b, x0, n);   // stored index of the lowest base needed
             const int lo = first < 0 ? 0 : first;
-            const u32 *src = src2 + (b.word_off[read] - src2_origin) + (u64)(lo >> 4);
+            const u32 *src = src2 + (read_word0(b, read) - src2_origin) + (u64)(lo >> 4);
             const u64 pair = (u64)src[0] | ((u64)src[1] << 32);
             v = (u32)(pair >> (2 * (lo & 15)));
             if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below

@@ -27,6 +27,9 @@ cudaError_t launch_select_big(const Tables &t, const Batch &b, const u32 *list, 
 cudaError_t launch_scan_compact(const Tables &t, const Batch &b, u32 rec_cap, unsigned long long *tile_status, u32 *ticket,
                                 u32 ticket_base, u32 epoch, cudaStream_t st);
 cudaError_t launch_pack_records32(const smx_record *in, u32 n, smx_record32 *out, cudaStream_t st);
+cudaError_t launch_pack_records16(const smx_record *in, u32 n, const u32 *lengths, u32 read_base, smx_record16 *out, u32 *bad,
+                                  cudaStream_t st);
+cudaError_t launch_expand_lengths(const unsigned short *in, u32 n, u32 *out, cudaStream_t st);
 cudaError_t launch_rebase_offsets(const u32 *in, u32 n, u32 rec_base, u32 *out, cudaStream_t st);
 // utilities
 cudaError_t launch_pairwise_nw(const char *seqs, const u32 *off, u32 n, i32 *out, cudaStream_t st);

@@ -50,7 +50,8 @@ class PackedBatch:
         return hb.array[:count]
 
     def _init_from_blob(self, blob, seq_off, clip):
-        """blob: bytes, or the address of the concatenated bases."""
+        """blob: bytes, or the address of the concatenated bases.  Clipped batches (clip > 0) are packed at a fixed
+        stride (no per-read offsets on the wire) with 16-bit lengths when every read is shorter than 65,536."""
         lib = _lib.load()
         n = len(seq_off) - 1
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
@@ -58,20 +59,34 @@ class PackedBatch:
         lib.smx_pack_bound(_lib.ptr(seq_off, _lib.u64p), n, clip, C.byref(w2), C.byref(w4))
         self.n_reads = n
         self.clip = int(clip)
-        self.packed2 = self._buffer(0, int(w2.value), np.uint32)
-        self.word_off = self._buffer(1, max(n, 1), np.uint64)
+        self.stride = int(lib.smx_pack_stride(clip)) if clip else 0
         self.lengths = self._buffer(2, max(n, 1), np.uint32)
         self.off4 = self._buffer(3, max(n, 1), np.uint64)
         packed4 = np.zeros(int(w4.value), dtype=np.uint32)
         used4, flagged = C.c_uint64(0), C.c_uint32(0)
         src = blob if isinstance(blob, (bytes, bytearray)) else C.cast(C.c_void_p(int(blob)), C.c_char_p)
-        _lib.check(lib.smx_pack_reads(src, _lib.ptr(seq_off, _lib.u64p), n, clip, _lib.ptr(self.packed2, _lib.u32p),
-                                      _lib.ptr(self.word_off, _lib.u64p), _lib.ptr(self.lengths, _lib.u32p),
-                                      _lib.ptr(packed4, _lib.u32p), _lib.ptr(self.off4, _lib.u64p),
-                                      C.byref(used4), C.byref(flagged)))
+        if self.stride:
+            self.packed2 = self._buffer(0, n * self.stride + 1, np.uint32)
+            self.word_off = None
+            l16 = self._buffer(4, max(n, 1), np.uint16)
+            fit = C.c_int(0)
+            _lib.check(lib.smx_pack_reads_fixed(src, _lib.ptr(seq_off, _lib.u64p), n, clip, _lib.ptr(self.packed2, _lib.u32p),
+                                                _lib.ptr(self.lengths, _lib.u32p), _lib.ptr(l16, _lib.u16p), C.byref(fit),
+                                                _lib.ptr(packed4, _lib.u32p), _lib.ptr(self.off4, _lib.u64p),
+                                                C.byref(used4), C.byref(flagged)))
+            self.lengths16 = l16 if fit.value else None
+        else:
+            self.packed2 = self._buffer(0, int(w2.value), np.uint32)
+            self.word_off = self._buffer(1, max(n, 1), np.uint64)
+            self.lengths16 = None
+            _lib.check(lib.smx_pack_reads(src, _lib.ptr(seq_off, _lib.u64p), n, clip, _lib.ptr(self.packed2, _lib.u32p),
+                                          _lib.ptr(self.word_off, _lib.u64p), _lib.ptr(self.lengths, _lib.u32p),
+                                          _lib.ptr(packed4, _lib.u32p), _lib.ptr(self.off4, _lib.u64p),
+                                          C.byref(used4), C.byref(flagged)))
         self.n_flagged = int(flagged.value)
         self.packed4 = packed4[:int(used4.value)].copy() if self.n_flagged else None
-        self.h2d_bytes = (self.packed2.nbytes + self.word_off.nbytes + self.lengths.nbytes +
+        self.h2d_bytes = (self.packed2.nbytes + (self.word_off.nbytes if self.word_off is not None else 0) +
+                          (self.lengths16.nbytes if self.lengths16 is not None else self.lengths.nbytes) +
                           (self.packed4.nbytes + self.off4.nbytes if self.n_flagged else 0))
 
     def c_batch(self) -> "_lib.SmxBatch":
@@ -80,8 +95,10 @@ class PackedBatch:
         b.clip_len = self.clip
         b.packed2 = _lib.ptr(self.packed2, _lib.u32p)
         b.packed2_words = len(self.packed2)
-        b.word_off = _lib.ptr(self.word_off, _lib.u64p)
+        b.stride_words = self.stride
+        b.word_off = _lib.ptr(self.word_off, _lib.u64p) if self.word_off is not None else None
         b.lengths = _lib.ptr(self.lengths, _lib.u32p)
+        b.lengths16 = _lib.ptr(self.lengths16, _lib.u16p) if self.lengths16 is not None else None
         if self.n_flagged:
             b.packed4 = _lib.ptr(self.packed4, _lib.u32p)
             b.packed4_words = len(self.packed4)
@@ -142,8 +159,9 @@ class Matcher:
         t = self.tables
         cap = int(cap if cap is not None else n + n // 8 + 1024)
         res = _lib.SmxResults()
-        rec_dtype = _lib.RECORD32_DTYPE if compact else _lib.RECORD_DTYPE
-        rec_key = "rec32" if compact else "rec"
+        wire = compact == "wire"
+        rec_dtype = _lib.RECORD16_DTYPE if wire else _lib.RECORD32_DTYPE if compact else _lib.RECORD_DTYPE
+        rec_key = "rec16" if wire else "rec32" if compact else "rec"
         if reuse is not None and reuse is not False:
             # pinned pool reused across calls: the previous call's result arrays are overwritten.
             # reuse=True: one pool per Matcher; reuse=<dict>: a pool owned by the caller (lets several
@@ -158,11 +176,16 @@ class Matcher:
         else:
             rec_offset = np.empty(n + 1, dtype=np.uint32)
             records = np.empty(cap, dtype=rec_dtype)
-        res.rec_offset = _lib.ptr(rec_offset, _lib.u32p)
-        if compact:
-            res.records32 = records.ctypes.data
+        if wire:
+            rec_offset = None                       # the last-of-read flags carry the grouping
+            res.rec_offset = None
+            res.records16 = records.ctypes.data
         else:
-            res.records = records.ctypes.data
+            res.rec_offset = _lib.ptr(rec_offset, _lib.u32p)
+            if compact:
+                res.records32 = records.ctypes.data
+            else:
+                res.records = records.ctypes.data
         res.records_cap = cap
         ph = em = bh = oh = None
         if detail:
@@ -193,7 +216,8 @@ class Matcher:
     def match(self, batch: PackedBatch, detail: bool = False, reuse=False, compact: bool = False) -> BatchResult:
         """`reuse=True` returns views into a pinned pool that the next reuse=True call overwrites;
         `reuse=<dict>` uses (and grows) a caller-owned pool instead.  `compact=True` returns 32-byte
-        smx_record32 records (no location pairs: what the output-tree writer needs).  A context is not
+        smx_record32 records (no location pairs); `compact="wire"` the 16-byte smx_record16 records in read
+        order (what the output-tree writer needs; no rec_offset).  A context is not
         re-entrant: calls from several threads are serialised here."""
         with self._lock:
             return self._match_locked(batch, detail, reuse, compact)

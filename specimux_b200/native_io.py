@@ -23,7 +23,7 @@ strp = C.POINTER(C.c_char_p)
 
 EXPORTS = ["smx_io_abi_version", "smx_io_last_error", "smx_reader_open", "smx_reader_close", "smx_block_create",
            "smx_block_destroy", "smx_block_get", "smx_reader_next", "smx_reader_skip", "smx_writer_open",
-           "smx_writer_write", "smx_writer_write32", "smx_writer_close", "smx_writer_stats"]
+           "smx_writer_write", "smx_writer_write32", "smx_writer_write16", "smx_writer_close", "smx_writer_stats"]
 
 
 class SmxBlockView(C.Structure):
@@ -68,10 +68,11 @@ def load():
         lib.smx_writer_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(SmxNames), C.POINTER(C.c_void_p)]
         lib.smx_writer_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.smx_writer_write32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.smx_writer_write16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.smx_writer_close.argtypes = [C.c_void_p]
         lib.smx_writer_stats.argtypes = [C.c_void_p, u64p, u64p]
         lib.smx_writer_stats.restype = None
-        if lib.smx_io_abi_version() != 1:
+        if lib.smx_io_abi_version() != 2:
             raise ImportError("libspecimux_io.so ABI version mismatch")
         _io = lib
     return _io
@@ -235,9 +236,11 @@ class TreeWriter:
                                          C.byref(self._h)))
 
     def write(self, block: ReadBlock, records: np.ndarray):
-        """records: smx_record (RECORD_DTYPE) or the compact smx_record32 (RECORD32_DTYPE)."""
+        """records: smx_record (RECORD_DTYPE), the compact smx_record32 or the 16-byte wire form smx_record16."""
         rec = np.ascontiguousarray(records)
-        if rec.dtype == _lib.RECORD32_DTYPE:
+        if rec.dtype == _lib.RECORD16_DTYPE:
+            _check(self._lib.smx_writer_write16(self._h, block.handle, rec.ctypes.data, len(rec)))
+        elif rec.dtype == _lib.RECORD32_DTYPE:
             _check(self._lib.smx_writer_write32(self._h, block.handle, rec.ctypes.data, len(rec)))
         else:
             assert rec.dtype == _lib.RECORD_DTYPE

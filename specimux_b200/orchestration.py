@@ -312,7 +312,7 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             if job is None:
                 return
             try:
-                job.result = matchers[dev].match(job.batch, reuse=job.pool, compact=True)     # the writer needs no locations
+                job.result = matchers[dev].match(job.batch, reuse=job.pool, compact="wire")   # 16-byte records: all the files need
             except BaseException as e:          # surfaced by the writer thread in submission order
                 job.error = e
             job.done.set()

@@ -153,8 +153,12 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     unsigned long long counters[kCtrWords] = {0};
     Batch b;
     memset(&b, 0, sizeof(b));
-    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len;
-    b.packed2 = in->packed2; b.word_off = in->word_off; b.lengths = in->lengths;
+    b.n_reads = n; b.n_pad = n_pad; b.clip = in->clip_len; b.stride = in->stride_words;
+    std::vector<u32> lengths32;
+    if (in->lengths16) {                // 16-bit lengths of the wire form: what k_expand_lengths does
+        lengths32.assign(in->lengths16, in->lengths16 + n);
+    }
+    b.packed2 = in->packed2; b.word_off = in->word_off; b.lengths = in->lengths16 ? lengths32.data() : in->lengths;
     bool flagged = in->packed4 && in->off4 && in->packed4_words;
     b.packed4 = flagged ? in->packed4 : nullptr; b.off4 = flagged ? in->off4 : nullptr;
     b.win = win.data(); b.win2 = win2.data(); b.tmix = tmix.data(); b.phit = phit.data(); b.endmask = endmask.data(); b.impmask = impmask.data(); b.orient_hit = orient_hit.data();
@@ -164,7 +168,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
 
     for (u32 r = 0; r < n; ++r)
         for (int s = 0; s < 2; ++s)
-            for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, r, s, w2, b.packed2, b.word_base);
+            for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, r, s, w2, b.packed2, 0);
     if (t.sliced)       // forward pass bit-sliced across reads: one "thread" per (group of 32 reads, strand, primer)
         for (int p = 0; p < nP; ++p) {
             RowOffsets ro;
@@ -299,17 +303,14 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
     if (out->rec_offset) memcpy(out->rec_offset, rec_offset.data(), (size_t)(n + 1) * sizeof(u32));
     if (out->records && total) memcpy(out->records, records.data(), total * sizeof(smx_record));
     if (!out->records && out->records32)
-        for (u64 i = 0; i < total; ++i) {           // what k_pack_records32 does
-            const smx_record &r = records[i];
-            smx_record32 o;
-            memset(&o, 0, sizeof(o));
-            o.read = r.read; o.sample = r.sample; o.trim_start = r.trim_start; o.trim_end = r.trim_end;
-            o.pool = r.pool; o.p1 = r.p1; o.p2 = r.p2;
-            for (int k = 0; k < 4; ++k) o.dist[k] = r.dist[k];
-            o.resolution = r.resolution;
-            o.flags = (uint8_t)((r.reverse ? 1 : 0) | (r.trim_empty ? 2 : 0));
-            o.candidate = r.candidate;
-            out->records32[i] = o;
+        for (u64 i = 0; i < total; ++i) pack_record32(records[i], out->records32[i]);      // what k_pack_records32 does
+    if (!out->records && !out->records32 && out->records16)
+        for (u64 i = 0; i < total; ++i) {           // what k_pack_records16 does
+            const bool last = i + 1 >= total || records[i + 1].read != records[i].read;
+            if (!pack_record16(records[i], (int)b.lengths[records[i].read], last, out->records16[i])) {
+                snprintf(g_err, sizeof(g_err), "record does not fit smx_record16");
+                return SMX_ERR_INTERNAL;
+            }
         }
     // level-1 detail is kept padded ([row][n_pad]) and returned dense ([row][n])
     if (out->primer_hits)

@@ -24,12 +24,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libspecimux_b200.so does not export %s" % name
     assert set(_lib.EXPORTS) == declared
-    assert lib.smx_abi_version() == 2
+    assert lib.smx_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.SmxParams) == 36
-    assert _lib.RECORD_DTYPE.itemsize == 64
+    assert _lib.RECORD_DTYPE.itemsize == 64 and _lib.RECORD32_DTYPE.itemsize == 32 and _lib.RECORD16_DTYPE.itemsize == 16
+    assert ctypes.sizeof(_lib.SmxBatch) == 80 and ctypes.sizeof(_lib.SmxResults) == 112
 
 
 @pytest.mark.skipif(_lib.load().smx_device_count() > 0, reason="box has a GPU")
@@ -79,8 +80,11 @@ def test_packer_roundtrip(clip):
         stored = list(range(n)) if not clip or n <= 2 * clip else list(range(clip)) + list(range(n - clip, n))
         flagged = b.n_flagged and b.off4[r] != np.uint64(2 ** 64 - 1)
         assert bool(flagged) == any(c not in "ACGT" for c in (s[i] for i in stored))
+        if clip:        # clipped batches are packed at a fixed stride, 16-bit lengths beside the 32-bit ones
+            assert b.word_off is None and b.stride == (2 * clip + 15) // 16 and b.lengths16[r] == n
+        first_word = r * b.stride if b.stride else int(b.word_off[r])
         for si, i in enumerate(stored):
-            w = b.packed2[int(b.word_off[r]) + si // 16]
+            w = b.packed2[first_word + si // 16]
             c2 = (int(w) >> (2 * (si % 16))) & 3
             assert c2 == (code[s[i]] if s[i] in "ACGT" else 0)
         if flagged:

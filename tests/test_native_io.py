@@ -60,7 +60,7 @@ def test_library_exports_every_declared_symbol():
     assert declared and set(native_io.EXPORTS) == declared
     for name in declared:
         assert hasattr(lib, name), "libspecimux_io.so does not export %s" % name
-    assert lib.smx_io_abi_version() == 1
+    assert lib.smx_io_abi_version() == 2
 
 
 @pytest.mark.parametrize("name", sorted(FASTQ_CASES))
@@ -191,6 +191,15 @@ def test_native_writer_tree_equals_python_output_manager(tmp_path, name, run_nam
             assert res.records.dtype.itemsize == 32
             wr.write(blk, res.records)
     assert _tree(compact_dir) == _tree(args.output_dir)
+    # ... and so does the 16-byte wire form (smx_record16: no read index, no offsets, 16-bit trim extents)
+    wire_dir = str(tmp_path / "wire")
+    with native_io.FastxReader(fq, True) as rd, native_io.TreeWriter(wire_dir, "pre_", True, matcher.tables) as wr:
+        blk = native_io.ReadBlock()
+        while rd.next_block(97, blk).n_reads:
+            res = matcher.match(PackedBatch.from_block(blk, clip=params.search_len), compact="wire")
+            assert res.records.dtype.itemsize == 16 and res.rec_offset is None
+            wr.write(blk, res.records)
+    assert _tree(wire_dir) == _tree(args.output_dir)
 
 
 def test_native_writer_fasta_input_and_console_form(tmp_path, capfd):
@@ -358,3 +367,21 @@ def test_compact_records_are_the_projection_of_full_records():
         assert np.array_equal(full[name], lite[name]), name
     assert np.array_equal(full["dist"], lite["dist"])
     assert np.array_equal(lite["flags"] & 1, full["reverse"]) and np.array_equal((lite["flags"] >> 1) & 1, full["trim_empty"])
+    # the 16-byte wire form: read index from the last-of-read flags, trim_end from the read length
+    wire = matcher.match(batch, compact="wire").records
+    assert len(wire) == len(full)
+    last = (wire["flags"] >> 5) & 1
+    read = np.concatenate([[0], np.cumsum(last)[:-1]]).astype(np.int64)
+    assert np.array_equal(read, full["read"])
+    lens = np.array([len(r[1]) for r in g["reads"]])[read]
+    assert np.array_equal(wire["sample"], full["sample"]) and np.array_equal(wire["trim_start"], full["trim_start"])
+    assert np.array_equal(lens - wire["trim_tail"], full["trim_end"]) and np.array_equal(wire["pool"], full["pool"])
+    for a, b in (("p1", "p1"), ("p2", "p2")):
+        assert np.array_equal(np.where(wire[a] == 255, -1, wire[a].astype(int)), full[b])
+    d = full["dist"].astype(int)
+    assert np.array_equal(np.where(wire["dist_p1"] == 255, -1, wire["dist_p1"].astype(int)), d[:, 0])
+    assert np.array_equal(np.where(wire["dist_p2"] == 255, -1, wire["dist_p2"].astype(int)), d[:, 3])
+    b1, b2 = wire["dist_b"] & 15, wire["dist_b"] >> 4
+    assert np.array_equal(np.where(b1 == 15, -1, b1.astype(int)), d[:, 1]) and np.array_equal(np.where(b2 == 15, -1, b2.astype(int)), d[:, 2])
+    assert np.array_equal(wire["flags"] & 7, full["resolution"]) and np.array_equal((wire["flags"] >> 3) & 1, full["reverse"])
+    assert np.array_equal((wire["flags"] >> 4) & 1, full["trim_empty"])
