@@ -260,6 +260,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def file_to_tree(args, ds, n_reads, n_gpus):
+    """BASELINE.json's whole-box metric: the workload as a FASTQ file on local disk -> finished output tree through
+    this package's own CLI (`python -m specimux.cli ... -F -t <n_gpus>`), timed by the CLI's 'Elapsed time' clock
+    exactly as the reference arm is; the second of two runs is reported (the first warms the page cache)."""
+    d, files = _workload_files(args.config, ds, n_reads)
+    out = os.path.join(d, "out_b200")
+    runs = [_run_cli([ROOT], files, out, ["-t", str(n_gpus)], 900) for _ in range(2)]
+    n_done, el, wall = runs[-1]
+    size = os.path.getsize(files[2])
+    import shutil
+    shutil.rmtree(out, ignore_errors=True)
+    return {"value": n_done / el, "unit": "reads/s", "n_gpus": n_gpus, "reads": n_done, "elapsed_s": el, "process_wall_s": wall,
+            "fastq_bytes": size, "fastq_gbs": size / el / 1e9,
+            "api": "python -m specimux.cli primers.fasta specimens.txt reads.fastq -F -O <dir> -t %d (native reader / packer, "
+                   "smx_match_batch per 65,536-read batch, native tree writer)" % n_gpus}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -271,6 +288,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="reads per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=12000, help="reads of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-to-tree", action="store_true", help="skip the FASTQ file -> output tree leg")
     ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of the resident run (1 = one lane)")
     ap.add_argument("--chunk", type=int, default=-1, help="reads per pipeline chunk of smx_match_batch (-1 = library default)")
     args = ap.parse_args()
@@ -319,9 +337,12 @@ def main():
     log("rank %d: packed %d reads (%.1f MB) in %.1fs" % (rank, n_reads, batch.h2d_bytes / 1e6, time.time() - t0))
 
     import ctypes
+    import hashlib
     peaks = (ctypes.c_double * 3)()
     _lib.check(lib.smx_int_alu_peak(local, peaks))
     int_peak = max(peaks)
+    copy_peak = (ctypes.c_double * 3)()
+    _lib.check(lib.smx_copy_peak(local, 32 << 20, copy_peak))
 
     def barrier():
         if dist is not None:
@@ -346,6 +367,7 @@ def main():
     launches = matcher.last_launch_count()
     deferred = matcher.last_deferred()
     cells, wcols = matcher.last_work()
+    useful = matcher.last_useful_cells()
     res = matcher.download()
     ms = float(np.mean(step_ms))
     # (b) attribution pass: the same batch on ONE lane, kernels back to back, CUDA events around each
@@ -370,39 +392,49 @@ def main():
     ms_serial = float(np.mean(serial_ms))
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
+    # headline form: fixed-stride 2-bit reads + 16-bit lengths in, 16-byte smx_record16 records out (everything the
+    # per-specimen files need); the full 64-byte records (with the four location pairs) are timed beside it
     if args.chunk >= 0:
         matcher.set_pipeline_chunk(args.chunk)
-    for _ in range(min(args.warmup, 2)):
-        r = matcher.match(batch, reuse=True)
-    barrier()
-    t_e2e = time.perf_counter()
-    for _ in range(args.steps):
-        r = matcher.match(batch, reuse=True)
-    e2e_ms = (time.perf_counter() - t_e2e) * 1000.0 / args.steps
-    # the same call returning compact records (smx_record32: no location pairs -- what the output-tree writer of
-    # the CLI consumes); an extra figure, `e2e` above stays the full-record one
-    for _ in range(min(args.warmup, 2)):
-        rc_ = matcher.match(batch, reuse=True, compact=True)
-    barrier()
-    t_c = time.perf_counter()
-    for _ in range(args.steps):
-        rc_ = matcher.match(batch, reuse=True, compact=True)
-    e2e_compact_ms = (time.perf_counter() - t_c) * 1000.0 / args.steps
-    d2h_compact = rc_.records.nbytes + rc_.rec_offset.nbytes
-    # keep the GPU under the same load until nvidia-smi has been polled a few times (its period is
-    # ~0.2 s, the timed loops above take milliseconds); these extra runs are not part of any figure
+
+    def time_e2e(**kw):
+        for _ in range(min(args.warmup, 2)):
+            r_ = matcher.match(batch, reuse=True, **kw)
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(args.steps):
+            r_ = matcher.match(batch, reuse=True, **kw)
+        dt = (time.perf_counter() - t0_) * 1000.0 / args.steps
+        return dt, r_.records.nbytes + (r_.rec_offset.nbytes if r_.rec_offset is not None else 0), r_
+
+    e2e_ms, d2h, r_wire = time_e2e(compact="wire")
+    matcher_chunks = matcher.last_chunk_count()
+    e2e_full_ms, d2h_full, r_full = time_e2e()
+    if len(r_wire.records) != len(r_full.records) or not np.array_equal(r_wire.records["sample"], r_full.records["sample"]):
+        raise SystemExit("bench.py: wire-form and full records disagree")
+    # keep the GPU under the same load until the clock sampler has a few samples (the timed loops above take
+    # milliseconds); these extra runs are not part of any figure
     t_hold = time.perf_counter()
     while len(clocks.samples) < 5 and time.perf_counter() - t_hold < 3.0:
-        matcher.match(batch, reuse=True)
+        matcher.match(batch, reuse=True, compact="wire")
     clocks.__exit__(None, None, None)
     barrier()
-    d2h = r.records.nbytes + r.rec_offset.nbytes
 
     if dist is not None:
         import torch
-        t = torch.tensor([ms, e2e_ms, wall_ms, e2e_compact_ms], dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, wall_ms, e2e_full_ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, wall_ms, e2e_compact_ms = [float(x) for x in t.tolist()]
+        ms, e2e_ms, wall_ms, e2e_full_ms = [float(x) for x in t.tolist()]
+
+    matcher.close()
+    # ---- whole box: FASTQ file on local disk -> output tree through the CLI, all N GPUs (rank 0 runs it) ----
+    f2t = None
+    if rank == 0 and not args.no_file_to_tree:
+        try:
+            f2t = file_to_tree(args, ds, n_reads, world)
+        except Exception as e:                      # reported, never fatal for the kernel figures
+            f2t = {"error": str(e)[-500:]}
+    barrier()
 
     if rank == 0:
         total_reads = n_reads * world
@@ -411,23 +443,35 @@ def main():
         gcups = (cells[0] + cells[1]) / (ms / 1000.0) / 1e9
         # per-kernel durations (CUDA events on the launching stream, mean over the timed steps)
         kt = {k: float(np.mean([d[k] for d in kernel_ms])) for k in kernel_ms[0]}
-        # the two DP kernels: stage 1 forward pass (primer HW, bit-sliced across reads) and stage 2
-        # (barcode SHW, bit-sliced across barcodes); the dominant one by time carries the roofline
-        k_ops = {"primer_sliced": 15.0 * wcols[0], "barcode_bitsliced": 15.0 * wcols[1]}
-        dom_name = max(k_ops, key=lambda k: kt[k])
+        # The two DP kernels: stage 1 forward pass (primer HW, bit-sliced across reads) and stage 2 (barcode SHW,
+        # bit-sliced across barcodes).  Useful work = bit-sliced DP cells actually evaluated (counted on the device)
+        # x 5 three-input logic ops, the cost of one cell of either automaton for its 32 problems; the rate is set
+        # against the integer-ALU peak measured in this run.  The dominant kernel by time carries the roofline.
+        k_useful = {"primer_sliced": 5.0 * useful[0], "barcode_tasks": 5.0 * useful[1]}
+        k_model = {"primer_sliced": 15.0 * wcols[0], "barcode_tasks": 15.0 * wcols[1]}
+        dom_name = max(k_useful, key=lambda k: kt[k])
         dp = {}
-        for k, ops in k_ops.items():
+        for k, ops in k_useful.items():
             a_tops = ops / (kt[k] / 1000.0) / 1e12 if kt[k] > 0 else 0.0
-            dp[k] = {"ms": kt[k], "achieved": a_tops, "frac": a_tops / int_peak if int_peak else None}
+            dp[k] = {"ms": kt[k], "achieved": a_tops, "frac": a_tops / int_peak if int_peak else None,
+                     "survey_8d_model_tops": k_model[k] / (kt[k] / 1000.0) / 1e12 if kt[k] > 0 else 0.0}
         achieved = dp[dom_name]["achieved"]
+        # ncu figures (executed ALU-pipe utilisation, DRAM bytes) only when the committed capture is of THIS build
+        with open(_lib.LIB_PATH, "rb") as fh:
+            build_id = hashlib.sha1(fh.read()).hexdigest()[:16]
         ncu_static = {}
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_latest.json")) as fh:
                 ncu_static = json.load(fh)
         except OSError:
             pass
-        ncu_dom = ncu_static.get("kernels", {}).get(dom_name, {})
+        same_build = ncu_static.get("build_id") == build_id
+        ncu_dom = ncu_static.get("kernels", {}).get(dom_name, {}) if same_build else {}
         hbm_bytes = batch.h2d_bytes + res.records.nbytes
+        # e2e against its own roofline: the slower of the two copy directions at the measured pinned-copy peak, or
+        # the kernels (device-resident step time), whichever is larger
+        floor_copy = max(batch.h2d_bytes / (copy_peak[0] * 1e9), d2h / (copy_peak[1] * 1e9)) * 1000.0
+        floor_ms = max(floor_copy, ms)
         line = {
             "metric": "reads/sec demuxed (whole box)", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -447,29 +491,41 @@ def main():
                               "ms_per_step is the same work as %d concurrent sub-batches" % args.split,
             "roofline": {"bound": "int_alu", "kernel": dom_name, "achieved": achieved, "peak": int_peak,
                          "unit": "Tops/s", "frac": achieved / int_peak if int_peak else None,
-                         "whole_step_frac": (alg_ops / (ms / 1000.0) / 1e12) / int_peak if int_peak else None,
+                         "whole_step_frac": (5.0 * (useful[0] + useful[1]) / (ms / 1000.0) / 1e12) / int_peak if int_peak else None,
+                         "useful_ops": "bit-sliced DP cells evaluated (counted on the device: smx_last_useful_cells) x 5 "
+                                       "three-input logic ops per cell of 32 problems",
                          "peak_source": "measured in this run by smx_int_alu_peak (LOP3 %.2f / IADD3 %.2f / mix %.2f Tops/s); "
                                         "MEASURED_PEAKS.json has no integer figure" % (peaks[0], peaks[1], peaks[2]),
-                         "algorithmic_ops": "15 int ops x 32-bit word-columns (SURVEY.md 8d), counted on the device",
                          "dp_kernels": dp,
-                         "note": "both DP kernels are bit-sliced (32 barcodes / 32 reads per machine word, 6 LOP3 per "
-                                 "cell), so they execute far fewer than 15 integer ops per algorithmic word-column "
-                                 "and the algorithmic fraction exceeds 1; alu_pipe_pct_ncu is the EXECUTED ALU-pipe "
-                                 "utilisation of the same kernel from the committed ncu capture",
+                         "survey_8d_model": {"ops": "15 int ops x 32-bit word-columns of the one-pattern-per-word model "
+                                                    "(SURVEY.md 8d), counted on the device",
+                                             "whole_step_tops": alg_ops / (ms / 1000.0) / 1e12,
+                                             "note": "kept for continuity; it exceeds the peak because the kernels hold 32 "
+                                                     "problems per word and evaluate only the band"},
                          "alu_pipe_pct_ncu": ncu_dom.get("alu_pipe_pct"),
+                         "whole_step_alu_pipe_pct_ncu": ncu_static.get("whole_step_alu_pipe_pct") if same_build else None,
                          "traffic": ncu_dom.get("dram_bytes"),
-                         "ncu_capture": ncu_static.get("capture"),
+                         "ncu_capture": ncu_static.get("capture") if same_build else
+                                        "none for this build (%s); see profiles/ for the captures of committed builds" % build_id,
+                         "build_id": build_id,
                          "hbm_sanity_gbs": hbm_bytes / (ms / 1000.0) / 1e9},
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": "reads/s",
                     "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "chunks": matcher.last_chunk_count(),
-                    "api": "smx_match_batch (pinned host buffers, reads clipped to head/tail search_len bases; "
-                           "H2D + kernels + D2H, chunks pipelined over three streams)"},
-            "e2e_compact_records": {"value": total_reads / (e2e_compact_ms / 1000.0), "unit": "reads/s",
-                                    "ms_per_step": e2e_compact_ms, "h2d_bytes_per_step": int(batch.h2d_bytes),
-                                    "d2h_bytes_per_step": int(d2h_compact),
-                                    "note": "same call, 32-byte smx_record32 records (no location pairs: all the per-specimen "
-                                            "files need); extra figure, not the headline"},
+                    "ms_per_step": e2e_ms, "chunks": matcher_chunks,
+                    "api": "smx_match_batch (pinned host buffers: fixed-stride 2-bit reads clipped to head/tail search_len "
+                           "bases + 16-bit lengths in, 16-byte smx_record16 records out; H2D + kernels + D2H, chunks "
+                           "pipelined over three streams)",
+                    "roofline": {"h2d_peak_gbs": copy_peak[0], "d2h_peak_gbs": copy_peak[1], "both_peak_gbs": copy_peak[2],
+                                 "copy_floor_ms": floor_copy, "kernel_floor_ms": ms, "frac": floor_ms / e2e_ms,
+                                 "achieved_gbs": (batch.h2d_bytes + d2h) / (e2e_ms / 1000.0) / 1e9,
+                                 "note": "floor = max(slower copy direction at the measured pinned-copy peak, device-resident "
+                                         "step time); frac = floor / measured"}},
+            "e2e_full_records": {"value": total_reads / (e2e_full_ms / 1000.0), "unit": "reads/s",
+                                 "ms_per_step": e2e_full_ms, "h2d_bytes_per_step": int(batch.h2d_bytes),
+                                 "d2h_bytes_per_step": int(d2h_full),
+                                 "note": "same call returning the 64-byte smx_record records (with the four location pairs "
+                                         "the reference keeps for --color / traces) and rec_offset; extra figure"},
+            "file_to_tree": f2t,
             "gpu_launches": int(launches * args.steps),
             "host_numa_node": numa[0] if numa else None,
             "clocks": clocks.summary(),
@@ -478,14 +534,15 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             from oracle import cpu_bench
-            sample = min(args.cpu_sample, n_reads)
+            cores = cpu_bench.host_cores()
+            sample = min(max(args.cpu_sample, 1500 * cores), n_reads)
             reads = ds.reads(0, sample)
-            cb = cpu_bench.run(ds.primers, ds.specimens, reads, ds.search_len, processes=1)
-            line["cpu_baseline"] = {"value": cb["reads_per_s"], "unit": "reads/s", "cores": 1, "kind": "port",
-                                    "sample": "first %d reads of the workload, %.1f s on one host core "
-                                              "(oracle port of specimux process_sequences)" % (sample, cb["seconds"])}
+            cb = cpu_bench.run(ds.primers, ds.specimens, reads, ds.search_len, processes=cores)
+            line["cpu_baseline"] = {"value": cb["reads_per_s"], "unit": "reads/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d reads of the workload, %.1f s on %d host cores (oracle port of "
+                                              "specimux process_sequences over the C edlib restatement; the unmodified "
+                                              "reference CLI is the --impl reference arm)" % (sample, cb["seconds"], cores)}
         print(json.dumps(line, default=float), flush=True)
-    matcher.close()
     if dist is not None:
         dist.destroy_process_group()
 

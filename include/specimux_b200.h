@@ -335,6 +335,12 @@ int smx_last_launch_count(const smx_ctx *ctx);
  * cells[0] = HW cells, cells[1] = SHW cells, wordcols[0..1] the same in 32-bit word-columns. */
 int smx_last_work(const smx_ctx *ctx, uint64_t cells[2], uint64_t wordcols[2]);
 
+/* Bit-sliced DP cells the last smx_run_resident actually evaluated, counted on the device: cells[0] = stage 1
+ * (pattern rows x window columns per group of 32 reads, strand and primer), cells[1] = stage 2 (band cells x
+ * 32-barcode words per work entry).  One cell of either automaton costs 5 three-input logic ops for its 32
+ * problems, so 5 x cells / kernel time is the useful-op rate set against the measured integer peak. */
+int smx_last_useful_cells(const smx_ctx *ctx, uint64_t cells[2]);
+
 /* Batched global (NW) edit distances between all pairs of `n` strings, on the GPU.
  * Replaces the O(B^2) edlib.align(task="distance") loop of orchestration.py:549-555.
  * out[i*n + j] = distance(seq_i, seq_j). */

@@ -1,18 +1,21 @@
 #!/usr/bin/env python3
 """raw.csv (ncu -i X.ncu-rep --page raw --csv) -> profiles/ncu_latest.json: per stage kernel of ONE step, the
 figures bench.py quotes beside its live timings (executed ALU-pipe utilisation, DRAM bytes per launch).
-usage: make_ncu_latest.py raw.csv "capture description" > profiles/ncu_latest.json"""
+The json carries the sha1 prefix of the library the capture was taken from (`build_id`); bench.py quotes these figures
+only when it is running that very build.
+usage: make_ncu_latest.py raw.csv "capture description" [path/to/libspecimux_b200.so] > profiles/ncu_latest.json"""
 import csv
+import hashlib
 import json
+import os
 import sys
 
-NAMES = [("k_stage_windows", "stage_windows"), ("k_primer_sliced", "primer_sliced"), ("k_primer_search", "primer_finish"),
-         ("k_primer_start", "primer_start"), ("k_barcode_bitsliced", "barcode_bitsliced"), ("k_select_fast", "select_fast"),
-         ("k_select<", "select_general"), ("k_scan_compact", "scan_compact"), ("k_rebase_offsets", "rebase_offsets"), ("k_scan", "scan"),
-         ("k_compact_records", "compact_records")]
+NAMES = [("k_stage_windows", "stage_windows"), ("k_primer_sliced", "primer_sliced"), ("k_primer_finish", "primer_finish_start"),
+         ("k_primer_long", "primer_long"), ("k_barcode_task", "barcode_tasks"), ("k_select_fast", "select_fast"),
+         ("k_select<", "select_general"), ("k_scan_compact", "scan_compact"), ("k_rebase_offsets", "rebase_offsets")]
 
 
-def main(path, capture):
+def main(path, capture, lib_path=None):
     rows = list(csv.reader(open(path)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     names, units = rows[hdr], rows[hdr + 1]
@@ -39,12 +42,21 @@ def main(path, capture):
         d["warp_inst"] += val("smsp__inst_executed.sum")
         d["_alu"].append(val("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"))
         d["_issue"].append(val("smsp__issue_active.avg.pct_of_peak_sustained_active"))
+    t_all = a_all = 0.0
     for d in out.values():
         d["alu_pipe_pct"] = sum(d.pop("_alu")) / d["launches"]
         d["issue_active_pct"] = sum(d.pop("_issue")) / d["launches"]
-    json.dump({"capture": capture, "kernels": out}, sys.stdout, indent=1)
+        t_all += d["duration_us"]
+        a_all += d["duration_us"] * d["alu_pipe_pct"]
+    lib_path = lib_path or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "specimux_b200",
+                                        "libspecimux_b200.so")
+    with open(lib_path, "rb") as fh:
+        build_id = hashlib.sha1(fh.read()).hexdigest()[:16]
+    json.dump({"capture": capture, "build_id": build_id, "step_us": t_all,
+               "whole_step_alu_pipe_pct": a_all / t_all if t_all else None,
+               "whole_step_dram_bytes": sum(d["dram_bytes"] for d in out.values()), "kernels": out}, sys.stdout, indent=1)
     print()
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "")
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "", sys.argv[3] if len(sys.argv) > 3 else None)

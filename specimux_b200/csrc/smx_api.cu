@@ -109,7 +109,7 @@ struct Lane {
     u32 *h_slot_counts = nullptr;               // = (u32 *)(h_counters + 8)
     bool have_batch = false, have_results = false;
     u64 n_records = 0, n_matched = 0;
-    unsigned long long work[4] = {0, 0, 0, 0};
+    unsigned long long work[4] = {0, 0, 0, 0}, useful[2] = {0, 0};
     int launches = 0;
     u32 n_deferred = 0;
 
@@ -403,6 +403,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
             CU(cudaMemsetAsync(ln.counters.p + 1, 0, sizeof(unsigned long long), st));
             CU(cudaMemsetAsync(ln.counters.p + 3, 0, sizeof(unsigned long long), st));
             CU(cudaMemsetAsync(ln.counters.p + 7, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(ln.counters.p + kCtrUseful2, 0, sizeof(unsigned long long), st));
         }
         if (timed) CU(cudaEventRecord(ln.ev[2], st));
         KMARK(4);
@@ -498,6 +499,7 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     ln.n_matched = ln.h_counters[4];
     ln.n_deferred = (u32)ln.h_counters[kCtrDeferred];
     for (int i = 0; i < 4; ++i) ln.work[i] = ln.h_counters[i];
+    ln.useful[0] = ln.h_counters[kCtrUseful1]; ln.useful[1] = ln.h_counters[kCtrUseful2];
     return SMX_OK;
 }
 
@@ -1083,6 +1085,13 @@ int smx_last_work(const smx_ctx *c, uint64_t cells[2], uint64_t wordcols[2]) {
         cells[0] += ln.work[0]; cells[1] += ln.work[1];
         wordcols[0] += ln.work[2]; wordcols[1] += ln.work[3];
     }
+    return SMX_OK;
+}
+
+int smx_last_useful_cells(const smx_ctx *c, uint64_t cells[2]) {
+    if (!c || !c->lane[0].have_results) return fail(SMX_ERR_ARG, "smx_last_useful_cells: no results");
+    cells[0] = cells[1] = 0;
+    for (int i = 0; i < std::max(1, c->resident_lanes); ++i) { cells[0] += c->lane[i].useful[0]; cells[1] += c->lane[i].useful[1]; }
     return SMX_OK;
 }
 

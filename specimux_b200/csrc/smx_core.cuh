@@ -37,7 +37,9 @@ constexpr int kMaxTaskK = 4;        // largest k_idx with multi-word stage-2 tas
 // control block of a batch: kCtrWords 64-bit counters followed by the 2 * SMX_MAX_PRIMERS u32 per-slot entry counts
 constexpr int kCtrDeferred = 8;     // (u32) reads left to the general selection kernel
 constexpr int kCtrBig = 9;          // (u32) reads left to the second selection pass (k_select_big)
-constexpr int kCtrWords = 10;    // ... in the second pass over reads that overflowed the first
+constexpr int kCtrUseful1 = 10;     // stage 1: bit-sliced DP cells (pattern rows x columns per 32 reads) actually evaluated
+constexpr int kCtrUseful2 = 11;     // stage 2: bit-sliced DP cells (band cells x bwords per work entry) actually evaluated
+constexpr int kCtrWords = 12;
 
 // ---------------------------------------------------------------------------------------------
 // Symbols.  4-bit read codes: A0 C1 G2 T3 R4 Y5 S6 W7 K8 M9 B10 D11 H12 V13 N14 other15.
@@ -555,6 +557,18 @@ SMX_HD int cand_score(const EndInfo &a, const EndInfo &b) {   // demultiplex.py:
     if (p1 && p2) return 2;
     if (p1 || p2) return 1;
     return 0;
+}
+
+// Band cells the stage-2 automaton evaluates for an m-row pattern (columns j = i-K .. i+K inside 1 .. 16, or the
+// whole band for the general form).
+SMX_HD int band_cells(int m, int K, bool small) {
+    int n = 0;
+    for (int i = 1; i <= m; ++i) {
+        int lo = i - K < 1 ? 1 : i - K, hi = i + K;
+        if (small && hi > 16) hi = 16;
+        n += hi - lo + 1;
+    }
+    return n;
 }
 
 // Emits records for one read.  `emit` = nullptr counts only.  Returns the number of records.

@@ -12,6 +12,11 @@ template <int M>
 __global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
     __shared__ u32 s_planes[(kSlicedCodes + 48) * kSlicedBlock];
     const u32 group = blockIdx.x * kSlicedBlock + threadIdx.x;
+    if (threadIdx.x == 0) {             // evaluated bit-sliced cells: M rows x L columns per thread of the block
+        const u32 groups = b.n_pad / 32, first = blockIdx.x * kSlicedBlock;
+        const u32 act = groups > first ? (groups - first < (u32)kSlicedBlock ? groups - first : (u32)kSlicedBlock) : 0u;
+        if (act) atomicAdd(&b.counters[kCtrUseful1], (unsigned long long)act * M * c_tables.L);
+    }
     if (group >= b.n_pad / 32) return;
     primer_sliced_thread<M, kSlicedBlock>(c_tables, b, group, (int)blockIdx.y, primer, ro, degenerate != 0,
                                           s_planes + threadIdx.x, s_planes + kSlicedCodes * kSlicedBlock + threadIdx.x);

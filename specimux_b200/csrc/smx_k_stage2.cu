@@ -38,8 +38,19 @@ __global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned 
         const int p = b.ent_pos[(u64)slot * b.e_cap + idx];
         work = barcode_task_thread<K, NWQ>(t, b, read, p, idx, strand, primer, task, s_tab);
     }
-    // m is uniform over the block: cells = m * W, word-columns = ceil(m/32) * W with W = sum of lanes x columns
-    block_work_add(work, (unsigned long long)m, &b.counters[1], (unsigned long long)((m + 31) >> 5), &b.counters[3], &s_acc);
+    // m is uniform over the block: cells = m * W, word-columns = ceil(m/32) * W with W = sum of lanes x columns (low 20
+    // bits of `work`); the bits above count the bwords whose automaton ran (x band cells = evaluated bit-sliced cells)
+    const u32 wsum = __reduce_add_sync(0xffffffffu, work);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_acc, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long tot = s_acc & 0xFFFFFu, ran = s_acc >> 20;
+        if (tot) {
+            atomicAdd(&b.counters[1], tot * (unsigned long long)m);
+            atomicAdd(&b.counters[3], tot * (unsigned long long)((m + 31) >> 5));
+        }
+        if (ran) atomicAdd(&b.counters[kCtrUseful2], ran * (unsigned long long)band_cells(m, K, m + K <= 16));
+    }
 }
 
 template <int K>

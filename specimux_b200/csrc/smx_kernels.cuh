@@ -702,6 +702,64 @@ template <int S> SMX_HD void load_eq(const u32 *p, u32 (&eq)[S]) {
 #endif
 }
 
+// Bit-sliced full adder / majority on planes.
+SMX_HD u32 maj3(u32 a, u32 b, u32 c) { return (a & b) | (a & c) | (b & c); }
+
+// Result of the small form for one bword: D[m][m-K] as five bit-planes (values <= 16 there), and the horizontal
+// deltas of row m to its right.
+template <int K> struct SmallOut {
+    static constexpr int NT = 2 * K + 1;
+    u32 v0[5];
+    u32 rp[NT > 1 ? NT - 1 : 1], rm[NT > 1 ? NT - 1 : 1];
+};
+
+// Carry-save count of one-bit planes: value = sum s[l] << l + sum p[l] << l.  Two planes of one weight meet in a
+// full adder (2 LOP3) whose carry moves up a level, so n planes cost ~2n LOP3 instead of the 8n of rippling
+// every plane through a 4-bit counter (the per-row diagonal increments were 5 % of the barcode kernel's
+// instructions, profiles/r2_c_*).  `r` = planes added so far (a compile-time value in the unrolled row loop).
+struct CsaCount {
+    u32 s[5], p[4];
+    SMX_HD void init() {
+        for (int l = 0; l < 5; ++l) s[l] = 0;
+        for (int l = 0; l < 4; ++l) p[l] = 0;
+    }
+    SMX_HD void add(u32 x, int r) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 4; ++l) {
+            if (((r >> l) & 1) == 0) { p[l] = x; return; }
+            const u32 c = maj3(s[l], p[l], x);
+            s[l] = s[l] ^ p[l] ^ x;
+            p[l] = 0;
+            x = c;
+        }
+        s[4] ^= x;                                  // at most 16 planes: no carry out of the top level
+    }
+    // s + p + constant k -> five planes
+    SMX_HD void finish(int k, u32 (&v)[5]) const {
+        u32 c = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 5; ++l) {               // s + p
+            const u32 pl = l < 4 ? p[l] : 0u;
+            v[l] = s[l] ^ pl ^ c;
+            c = maj3(s[l], pl, c);
+        }
+        c = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 5; ++l) {               // + k (constant planes fold away)
+            const u32 kl = (k >> l) & 1 ? ~0u : 0u;
+            const u32 a = v[l];
+            v[l] = a ^ kl ^ c;
+            c = maj3(a, kl, c);
+        }
+    }
+};
+
 // Small form of the automaton (m + K <= 16) for the NWQ bwords of one task at once.  The whole flank sits in
 // one 64-bit register F (nibble j-1 = symbol of column j, kSymOther beyond the flank).  One table address is
 // formed per COLUMN (row 0 of that column's symbol); the rows are fully unrolled, so every cell's Eq words are
@@ -709,9 +767,9 @@ template <int S> SMX_HD void load_eq(const u32 *p, u32 (&eq)[S]) {
 // NWQ independent automata interleave in the instruction stream.  Rows beyond m leave the unrolled sequence
 // through one early exit, so the horizontal-delta registers are renamed from row to row without moves.
 template <int K, int NWQ>
-SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, typename BitSliced<K>::Out (&o)[NWQ]) {
+SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[NWQ]) {
     typedef BitSliced<K> BS;
-    constexpr int NT = BS::NT, NB = BS::NB, S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
+    constexpr int NT = BS::NT, S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
     constexpr int kRows = 16 - K > 0 ? 16 - K : 0;
     const u32 *col[16];
 #if defined(__CUDA_ARCH__)
@@ -719,6 +777,7 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, typename BitSlice
 #endif
     for (int j = 0; j < 16; ++j) col[j] = tab + (u32)((F >> (4 * j)) & 15u) * S;
     u32 HP[NWQ][NT], HM[NWQ][NT];
+    CsaCount cnt[NWQ];                                      // D[i][i-K] - K along the band's lower diagonal
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -727,11 +786,7 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, typename BitSlice
 #pragma unroll
 #endif
         for (int t = 0; t < NT; ++t) { HP[q][t] = ~0u; HM[q][t] = 0; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int bb = 0; bb < NB; ++bb) o[q].cnt[bb] = (K >> bb) & 1 ? ~0u : 0u;
-        o[q].over = 0;
+        cnt[q].init();
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -759,14 +814,7 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, typename BitSlice
                 const u32 Mh = t < NT - 1 ? HM[q][t + 1] : 0u;
                 u32 nPv, nMv, nPh, nMh, inc;
                 BS::cell(eq[q], Pv[q], Mv[q], Ph, Mh, nPv, nMv, nPh, nMh, inc);
-                if (t == 0) {
-                    u32 x = inc;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (int bb = 0; bb < NB; ++bb) { u32 c = o[q].cnt[bb] & x; o[q].cnt[bb] ^= x; x = c; }
-                    o[q].over |= x;
-                }
+                if (t == 0) cnt[q].add(inc, i - K - 1);     // lower diagonal: D[i][i-K] = D[i-1][i-1-K] + inc
                 HP[q][t] = nPh; HM[q][t] = nMh;
                 Pv[q] = nPv; Mv[q] = nMv;
             }
@@ -775,18 +823,100 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, typename BitSlice
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int q = 0; q < NWQ; ++q)
+    for (int q = 0; q < NWQ; ++q) {
+        cnt[q].finish(K, o[q].v0);                          // anchor D[K][0] = K
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int t = 1; t < NT; ++t) { o[q].rp[t - 1] = HP[q][t]; o[q].rm[t - 1] = HM[q][t]; }
+    }
 }
 
-// Read-out of one bword after the automaton: bit-sliced test "some in-range end column has D[m][j] <= K",
-// exact scalar values of the few flagged barcodes (ascending bit = ascending list position), their hit
-// records, and the running digest of the entry.
+// The scalar part of the read-out: exact values of the flagged barcodes of one bword (ascending bit = ascending
+// list position), their hit records and the running digest of the entry.  v0: NV bit-planes of D[m][m-K].
 struct DigestAcc { int bd, count, jmin, jmax, first_col; u32 nhits; };
 
+template <int K, int NV>
+SMX_HD void barcode_emit_hits(const Tables &t, const Batch &b, u32 flag, const u32 *v0, const u32 *rp, const u32 *rm,
+                              u32 g, u64 gslot, u64 entry, int m, int cols, int search_start, DigestAcc &acc) {
+    constexpr int NT = 2 * K + 1;
+    int nh = 0;
+    while (flag) {
+        int q = lowest_bit32(flag);
+        flag &= flag - 1;
+        int val = 0;
+        for (int bb = 0; bb < NV; ++bb) val |= (int)((v0[bb] >> q) & 1) << bb;
+        int best = 1 << 20;
+        u64 mask = 0;
+        for (int tt = 0; tt < NT; ++tt) {
+            if (tt > 0) val += (int)((rp[tt - 1] >> q) & 1) - (int)((rm[tt - 1] >> q) & 1);
+            int col = m - K + tt;
+            if (col > cols) break;
+            if (val < best) { best = val; mask = 0; }
+            if (val == best) mask |= 1ull << (col - 1);
+        }
+        if (best > K) continue;
+        const int j = (int)t.bw_list[(u64)g * 32 + q];
+        if (nh < t.hit_cap) {
+            smx_barcode_hit h;
+            h.barcode = (uint16_t)j; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = search_start;
+            b.bh_list[(gslot * t.hit_cap + nh) * b.e_cap + entry] = h;
+        }
+        ++nh;
+        ++acc.nhits;
+        if (best < acc.bd) { acc.bd = best; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; }
+        if (best == acc.bd) {
+            ++acc.count;
+            if (j < acc.jmin) { acc.jmin = j; acc.first_col = lowest_bit64(mask); }
+            if (j > acc.jmax) acc.jmax = j;
+        }
+    }
+    b.bh_count[gslot * b.e_cap + entry] = (unsigned char)nh;
+    if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
+}
+
+// Read-out of the small form: "some in-range end column has D[m][j] <= K" as a threshold test on the biased value
+// u = D + (15 - K): u fits five planes (D[m][m-K] <= m <= 16 - K, at most 2K columns further right) and D <= K
+// exactly when bit 4 of u is clear.  Walking one column to the right adds the +-1 horizontal delta in ONE ripple:
+// the +1 enters as the carry-in, the -1 as an all-ones addend (2 LOP3 per plane).
+template <int K>
+SMX_HD void barcode_readout_small(const Tables &t, const Batch &b, const SmallOut<K> &o, u32 g, u64 gslot, u64 entry,
+                                  int m, int cols, int search_start, DigestAcc &acc) {
+    constexpr int NT = 2 * K + 1;
+    u32 u[5];
+    {
+        u32 c = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 5; ++l) {
+            const u32 kl = ((15 - K) >> l) & 1 ? ~0u : 0u;
+            u[l] = o.v0[l] ^ kl ^ c;
+            c = maj3(o.v0[l], kl, c);
+        }
+    }
+    u32 flag = (m - K <= cols) ? ~u[4] : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int tt = 1; tt < NT; ++tt) {
+        u32 c = o.rp[tt - 1];
+        const u32 neg = o.rm[tt - 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 5; ++l) {
+            const u32 a = u[l];
+            u[l] = a ^ neg ^ c;
+            c = maj3(a, neg, c);
+        }
+        if (m - K + tt <= cols) flag |= ~u[4];
+    }
+    flag &= t.bw_valid[g];
+    barcode_emit_hits<K, 5>(t, b, flag, o.v0, o.rp, o.rm, g, gslot, entry, m, cols, search_start, acc);
+}
+
+// Read-out of the general form (BitSliced<K>::run: long barcodes): counter planes with a saturation flag.
 template <int K>
 SMX_HD void barcode_readout(const Tables &t, const Batch &b, const typename BitSliced<K>::Out &o, u32 g, u64 gslot, u64 entry,
                             int m, int cols, int search_start, DigestAcc &acc) {
@@ -816,44 +946,13 @@ SMX_HD void barcode_readout(const Tables &t, const Batch &b, const typename BitS
         if (m - K + tt <= cols) flag |= planes_le<K, BS::NB>(v) & ~ov;
     }
     flag &= t.bw_valid[g];
-    int nh = 0;
-    while (flag) {
-        int q = lowest_bit32(flag);
-        flag &= flag - 1;
-        int val = 0;
-        for (int bb = 0; bb < BS::NB; ++bb) val |= (int)((o.cnt[bb] >> q) & 1) << bb;
-        int best = 1 << 20;
-        u64 mask = 0;
-        for (int tt = 0; tt < BS::NT; ++tt) {
-            if (tt > 0) val += (int)((o.rp[tt - 1] >> q) & 1) - (int)((o.rm[tt - 1] >> q) & 1);
-            int col = m - K + tt;
-            if (col > cols) break;
-            if (val < best) { best = val; mask = 0; }
-            if (val == best) mask |= 1ull << (col - 1);
-        }
-        if (best > K) continue;
-        const int j = (int)t.bw_list[(u64)g * 32 + q];
-        if (nh < t.hit_cap) {
-            smx_barcode_hit h;
-            h.barcode = (uint16_t)j; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = search_start;
-            b.bh_list[(gslot * t.hit_cap + nh) * b.e_cap + entry] = h;
-        }
-        ++nh;
-        ++acc.nhits;
-        if (best < acc.bd) { acc.bd = best; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; }
-        if (best == acc.bd) {
-            ++acc.count;
-            if (j < acc.jmin) { acc.jmin = j; acc.first_col = lowest_bit64(mask); }
-            if (j > acc.jmax) acc.jmax = j;
-        }
-    }
-    b.bh_count[gslot * b.e_cap + entry] = (unsigned char)nh;
-    if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
+    barcode_emit_hits<K, BS::NB>(t, b, flag, o.cnt, o.rp, o.rm, g, gslot, entry, m, cols, search_start, acc);
 }
 
 // One work entry (matched slot of a read, one equal-best primer end at staged position p) against the NWQ bwords
 // of stage-2 task `task` (all of one barcode length m).  `tab` points at the task's [m][16][S] table (shared
-// memory in the CUDA launch).  Returns lanes x columns of the SURVEY.md 8d work formula (x m = cells).
+// memory in the CUDA launch).  Returns lanes x columns of the SURVEY.md 8d work formula (x m = cells) in the low
+// 20 bits and, from bit 20 up, the number of bwords whose automaton actually ran (0 or NWQ).
 template <int K, int NWQ>
 SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p, u64 entry, int strand, int primer,
                                u32 task, const u32 *tab) {
@@ -914,11 +1013,18 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
         dg_out = dg;
         return work;
     }
-    typename BS::Out o[NWQ];
+    DigestAcc acc;
+    acc.bd = 1 << 20; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; acc.first_col = 0; acc.nhits = 0;
     if (small) {
+        SmallOut<K> o[NWQ];
         bitsliced_small_rows<K, NWQ>(tab, m, F, o);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < NWQ; ++q) barcode_readout_small<K>(t, b, o[q], g0 + q, gslot0 + q, entry, m, cols, f.bs, acc);
     } else {
-        // long barcodes (m + K > 16): the general band walk, one word at a time (tasks of such lengths hold one word)
+        // long barcodes (m + K > 16): the general band walk (tasks of such lengths hold one word)
+        typename BS::Out o;
         auto rowwin = [&](int i) -> u64 {
             u64 W = 0;
             for (int tt = 0; tt < BS::NT; ++tt) {
@@ -928,20 +1034,15 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
             }
             return W;
         };
-        BS::run(tab, m, rowwin, o[0]);
+        BS::run(tab, m, rowwin, o);
+        barcode_readout<K>(t, b, o, g0, gslot0, entry, m, cols, f.bs, acc);
     }
-    DigestAcc acc;
-    acc.bd = 1 << 20; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; acc.first_col = 0; acc.nhits = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int q = 0; q < NWQ; ++q) barcode_readout<K>(t, b, o[q], g0 + q, gslot0 + q, entry, m, cols, f.bs, acc);
     if (acc.nhits) {
         dg.nhits = acc.nhits; dg.bd = (signed char)acc.bd; dg.count = (unsigned short)(acc.count > 65535 ? 65535 : acc.count);
         dg.jmin = (unsigned short)acc.jmin; dg.jmax = (unsigned short)acc.jmax; dg.first_col = (unsigned char)acc.first_col;
     }
     dg_out = dg;
-    return work;
+    return work | ((u32)NWQ << 20);
 }
 
 // Work-entry bookkeeping of stage 1: entries [base, base + nloc) of `slot` for one matched read.

@@ -277,7 +277,8 @@ class Matcher:
     def last_chunk_count(self) -> int:
         return int(self._lib.smx_last_chunk_count(self._ctx))
 
-    KERNEL_NAMES = ("stage_windows", "primer_sliced", "primer_finish", "primer_start", "barcode_bitsliced",
+    # slot 3 (once the separate start-recovery kernel) is the gap between stage 1 and stage 2: ~0
+    KERNEL_NAMES = ("stage_windows", "primer_sliced", "primer_finish_start", "stage_gap", "barcode_tasks",
                     "select_fast", "select_general", "scan_compact", "rebase_offsets")
 
     def last_kernel_times(self):
@@ -300,6 +301,12 @@ class Matcher:
 
     def last_launch_count(self) -> int:
         return int(self._lib.smx_last_launch_count(self._ctx))
+
+    def last_useful_cells(self):
+        """(stage 1, stage 2) bit-sliced DP cells evaluated by the last run_resident (5 LOP3 per cell)."""
+        cells = (C.c_uint64 * 2)()
+        _lib.check(self._lib.smx_last_useful_cells(self._ctx, cells))
+        return int(cells[0]), int(cells[1])
 
     def last_work(self):
         cells = (C.c_uint64 * 2)()

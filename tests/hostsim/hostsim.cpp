@@ -243,8 +243,8 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
 #undef SMX_K2
                         default: snprintf(g_err, sizeof(g_err), "unsupported k_idx / task width"); return SMX_ERR_ARG;
                     }
-                    counters[1] += (unsigned long long)work * m;
-                    counters[3] += (unsigned long long)work * ((m + 31) >> 5);
+                    counters[1] += (unsigned long long)(work & 0xFFFFFu) * m;
+                    counters[3] += (unsigned long long)(work & 0xFFFFFu) * ((m + 31) >> 5);
                 }
             }
         if (counters[7] == 0) break;
