@@ -55,6 +55,11 @@ const char *smx_io_last_error(void);
 /* Opens a FASTQ (is_fastq = 1) or FASTA (0) file, gzip-compressed when the name ends in .gz/.gzip
  * (reference: io_utils.py:429-450).  Format detection stays with the caller (io_utils.py:380-427). */
 int smx_reader_open(const char *path, int is_fastq, smx_reader **out);
+/* Reader over the records of a PLAIN four-line FASTQ file that START inside [byte_start, byte_end): both ends are
+ * moved forward to the next record boundary (first line beginning '@' whose second-next line begins '+'), so
+ * readers over consecutive ranges see every record exactly once -- the parallel form of the reader
+ * (the reference reads serially through Bio.SeqIO, io_utils.py:429-450).  Compressed files: SMX_IO_ERR_ARG. */
+int smx_reader_open_range(const char *path, int is_fastq, uint64_t byte_start, uint64_t byte_end, smx_reader **out);
 void smx_reader_close(smx_reader *r);
 
 smx_block *smx_block_create(void);

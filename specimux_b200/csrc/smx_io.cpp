@@ -102,6 +102,9 @@ struct smx_reader {
     // FASTA: the title of the record whose sequence lines are being collected
     bool fasta_open = false;
     std::string fasta_title;
+    // byte-range readers (smx_reader_open_range): the file position the next read() starts at and the position the
+    // range ends at (the reader sees end-of-file there); stop_off == UINT64_MAX for whole-file readers
+    uint64_t read_off = 0, stop_off = UINT64_MAX;
 
     // Fills the buffer; returns false on a read error.
     bool refill() {
@@ -109,7 +112,12 @@ struct smx_reader {
         if (end == buf.size()) buf.resize(buf.size() * 2);
         long got;
         if (gz) got = gzread(gz, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
-        else got = (long)read(fd, buf.data() + end, buf.size() - end);
+        else {
+            size_t want = buf.size() - end;
+            if (stop_off != UINT64_MAX) want = (size_t)std::min<uint64_t>(want, stop_off > read_off ? stop_off - read_off : 0);
+            got = want ? (long)read(fd, buf.data() + end, want) : 0;
+            if (got > 0) read_off += (uint64_t)got;
+        }
         if (got < 0) return false;
         if (got == 0) eof = true;
         end += (size_t)got;
@@ -287,6 +295,58 @@ int smx_reader_open(const char *path, int is_fastq, smx_reader **out) {
 #endif
     }
     *out = r;
+    return SMX_IO_OK;
+}
+
+// First FASTQ record boundary at or after byte `off` of a plain four-line FASTQ file: the first line start p with
+// line(p) beginning '@' and line(p + 2) beginning '+'.  Exact for four-line records: a quality line that happens to
+// begin with '@' is followed two lines later by a sequence line, which never begins with '+'.  Returns the file
+// size when no record starts after `off`, -1 on a read error.
+static int64_t fastq_sync(int fd, uint64_t off, uint64_t file_size) {
+    if (off == 0) return 0;
+    if (off >= file_size) return (int64_t)file_size;
+    size_t window = 1u << 20;
+    std::vector<char> w;
+    for (;;) {
+        const uint64_t from = off - 1;                      // the byte before `off` tells whether `off` starts a line
+        const size_t len = (size_t)std::min<uint64_t>(window, file_size - from);
+        w.resize(len);
+        size_t got = 0;
+        while (got < len) {
+            ssize_t k = pread(fd, w.data() + got, len - got, (off_t)(from + got));
+            if (k < 0) return -1;
+            if (k == 0) break;
+            got += (size_t)k;
+        }
+        const bool whole = from + got >= file_size;
+        // line starts inside the window
+        std::vector<size_t> starts;
+        for (size_t i = 0; i + 1 <= got; ++i)
+            if (w[i] == '\n' && i + 1 < got) starts.push_back(i + 1);
+        for (size_t k = 0; k + 2 < starts.size(); ++k)
+            if (w[starts[k]] == '@' && w[starts[k + 2]] == '+') return (int64_t)(from + starts[k]);
+        if (whole) return (int64_t)file_size;
+        window *= 4;
+    }
+}
+
+int smx_reader_open_range(const char *path, int is_fastq, uint64_t byte_start, uint64_t byte_end, smx_reader **out) {
+    if (!path || !out) return fail(SMX_IO_ERR_ARG, "smx_reader_open_range: null argument");
+    if (!is_fastq) return fail(SMX_IO_ERR_ARG, "smx_reader_open_range: byte ranges need a FASTQ file");
+    std::string p(path);
+    if (ends_with(p, ".gz") || ends_with(p, ".gzip")) return fail(SMX_IO_ERR_ARG, "smx_reader_open_range: compressed files are read serially");
+    int rc = smx_reader_open(path, is_fastq, out);
+    if (rc) return rc;
+    smx_reader *r = *out;
+    struct stat st;
+    if (fstat(r->fd, &st) != 0) { smx_reader_close(r); *out = nullptr; return fail(SMX_IO_ERR_IO, "cannot stat %s", path); }
+    const uint64_t size = (uint64_t)st.st_size;
+    const int64_t a = fastq_sync(r->fd, std::min(byte_start, size), size);
+    const int64_t b = byte_end >= size ? (int64_t)size : fastq_sync(r->fd, byte_end, size);
+    if (a < 0 || b < 0) { smx_reader_close(r); *out = nullptr; return fail(SMX_IO_ERR_IO, "read error on %s", path); }
+    if (lseek(r->fd, (off_t)a, SEEK_SET) < 0) { smx_reader_close(r); *out = nullptr; return fail(SMX_IO_ERR_IO, "cannot seek %s", path); }
+    r->read_off = (uint64_t)a;
+    r->stop_off = (uint64_t)std::max(a, b);
     return SMX_IO_OK;
 }
 

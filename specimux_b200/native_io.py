@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libspecimux_io.so")
 u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 strp = C.POINTER(C.c_char_p)
 
-EXPORTS = ["smx_io_abi_version", "smx_io_last_error", "smx_reader_open", "smx_reader_close", "smx_block_create",
+EXPORTS = ["smx_io_abi_version", "smx_io_last_error", "smx_reader_open", "smx_reader_open_range", "smx_reader_close", "smx_block_create",
            "smx_block_destroy", "smx_block_get", "smx_reader_next", "smx_reader_skip", "smx_writer_open",
            "smx_writer_write", "smx_writer_write32", "smx_writer_write16", "smx_writer_close", "smx_writer_stats"]
 
@@ -56,6 +56,7 @@ def load():
         lib = C.CDLL(LIB_PATH)
         lib.smx_io_last_error.restype = C.c_char_p
         lib.smx_reader_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.smx_reader_open_range.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
         lib.smx_reader_close.argtypes = [C.c_void_p]
         lib.smx_reader_close.restype = None
         lib.smx_block_create.restype = C.c_void_p
@@ -162,10 +163,16 @@ class ReadBlock:
 class FastxReader:
     """Native FASTQ / FASTA reader (plain or gzip)."""
 
-    def __init__(self, path: str, is_fastq: bool):
+    def __init__(self, path: str, is_fastq: bool, byte_range=None):
+        """byte_range=(start, end): only the records that start inside that range of a plain four-line FASTQ file
+        (both ends moved forward to a record boundary; consecutive ranges see every record exactly once)."""
         self._lib = load()
         self._h = C.c_void_p(None)
-        _check(self._lib.smx_reader_open(os.fsencode(path), 1 if is_fastq else 0, C.byref(self._h)))
+        if byte_range is None:
+            _check(self._lib.smx_reader_open(os.fsencode(path), 1 if is_fastq else 0, C.byref(self._h)))
+        else:
+            _check(self._lib.smx_reader_open_range(os.fsencode(path), 1 if is_fastq else 0, int(byte_range[0]),
+                                                   int(byte_range[1]), C.byref(self._h)))
         self.is_fastq = is_fastq
 
     def close(self):

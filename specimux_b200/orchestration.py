@@ -269,13 +269,53 @@ def _native_eligible(args) -> bool:
     return not args.diagnostics and os.environ.get("SMX_NATIVE_IO", "1") != "0"
 
 
+def _reader_chunk_bytes() -> int:
+    """Bytes of the FASTQ file one parser thread takes at a time = one GPU batch (SMX_READER_CHUNK_BYTES)."""
+    return max(1 << 16, int(os.environ.get("SMX_READER_CHUNK_BYTES", str(96 << 20))))
+
+
+def _reader_threads(n_gpus: int) -> int:
+    """Parser + packer threads of the parallel reader (SMX_READER_THREADS overrides): the host cores left beside one
+    feeder thread per GPU, the writer's pool and this thread, at most 12."""
+    env = os.environ.get("SMX_READER_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return max(1, min(12, cores // 2 - 1))
+
+
+def _parallel_read_ok(args, path: str, is_fastq: bool) -> bool:
+    """The byte-range reader needs a plain (not gzip) FASTQ file in the usual four-line layout, read from its first
+    record to its end; the head of the file is checked for the layout."""
+    if not is_fastq or path.endswith((".gz", ".gzip")) or args.num_seqs >= 0 or getattr(args, "start_seq", 1) > 1:
+        return False
+    if os.environ.get("SMX_PARALLEL_READER", "1") == "0":
+        return False
+    try:
+        if os.path.getsize(path) < 2 * _reader_chunk_bytes():
+            return False
+        with open(path, "rb") as fh:
+            lines = fh.read(1 << 20).split(b"\n")[:-1]
+    except OSError:
+        return False
+    if len(lines) < 8:
+        return False
+    for i in range(0, len(lines) - len(lines) % 4, 4):
+        if not (lines[i].startswith(b"@") and lines[i + 2].startswith(b"+") and len(lines[i + 1]) == len(lines[i + 3])):
+            return False
+    return True
+
+
 def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=None):
     """FASTQ/FASTA file -> output tree with no per-read Python objects: native reader -> 2-bit packer
-    -> smx_match_batch on `n_gpus` GPUs -> native writer.  Three kinds of threads run concurrently
-    (every stage is a GIL-free C call): this thread reads + packs, one feeder thread per GPU matches,
-    one writer thread formats and appends in submission order, so per-file record order is the input
-    order (= the reference's `-t 1` order) for any GPU count.
-    Returns (total reads, matched reads)."""
+    -> smx_match_batch on `n_gpus` GPUs -> native writer.  Every stage is a GIL-free C call, run by its own threads:
+    K parser threads read and pack (each a byte range of the file at a time, re-synchronised on FASTQ record
+    boundaries; one serial reader for gzip / FASTA / -n), one feeder thread per GPU matches, one writer thread formats
+    and appends in input order, so per-file record order is the input order (= the reference's `-t 1` order) for any
+    thread or GPU count.  Returns (total reads, matched reads)."""
     import queue
     import threading
     from .demultiplex import get_matcher
@@ -286,24 +326,30 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
     fmt = detect_file_format(args.sequence_file)
     args.isfastq = fmt == "fastq"
     matchers = [get_matcher(parameters, specimens, args, prefilter, dev, _binding) for dev in range(n_gpus)]
-    reader = FastxReader(args.sequence_file, args.isfastq)
     writer = TreeWriter(args.output_dir if args.output_to_files else None, args.output_file_prefix, args.isfastq,
                         matchers[0].tables)
+    parallel = _parallel_read_ok(args, args.sequence_file, args.isfastq)
+    chunk_bytes = _reader_chunk_bytes()
+    n_parsers = _reader_threads(n_gpus) if parallel else 1
 
     class Job:
         def __init__(self):
             self.block, self.batch, self.pool = ReadBlock(), None, {}
             self.result = self.error = None
             self.done = threading.Event()
+            self.index = -1
 
-    n_jobs = 2 * n_gpus + 2
+    n_jobs = n_parsers + 2 * n_gpus + 2
     free = queue.Queue()
     for _ in range(n_jobs):
         free.put(Job())
     gpu_q = [queue.Queue() for _ in range(n_gpus)]
-    write_q = queue.Queue()
     errors = []
     counts = [0, 0]
+    # jobs reach the writer in input order: `slots[i]` is job i once its parser has claimed it
+    order_lock = threading.Condition()
+    slots = {}
+    state = {"next_index": 0, "n_chunks": None}
 
     def gpu_worker(dev):
         _lib.bind_thread_to_gpu_numa_node(dev)
@@ -312,21 +358,26 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             if job is None:
                 return
             try:
-                job.result = matchers[dev].match(job.batch, reuse=job.pool, compact="wire")   # 16-byte records: all the files need
-            except BaseException as e:          # surfaced by the writer thread in submission order
+                if job.block.n_reads:
+                    job.result = matchers[dev].match(job.batch, reuse=job.pool, compact="wire")   # 16-byte records: all the files need
+            except BaseException as e:          # surfaced by the writer thread in input order
                 job.error = e
             job.done.set()
 
     def write_worker():
+        i = 0
         while True:
-            job = write_q.get()
-            if job is None:
-                return
+            with order_lock:
+                while i not in slots and not (state["n_chunks"] is not None and i >= state["n_chunks"]):
+                    order_lock.wait()
+                if i not in slots:
+                    return
+                job = slots.pop(i)
             job.done.wait()
             try:
                 if job.error is not None:
                     raise job.error
-                if not errors:
+                if not errors and job.block.n_reads:
                     writer.write(job.block, job.result.records)
                     counts[0] += job.block.n_reads
                     counts[1] += job.result.n_matched
@@ -335,38 +386,90 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             job.result = job.error = None
             job.done.clear()
             free.put(job)
+            i += 1
+
+    def submit(job, index):
+        job.index = index
+        with order_lock:
+            slots[index] = job
+            order_lock.notify_all()
+        gpu_q[index % n_gpus].put(job)
+
+    def parse_worker(n_chunks):
+        # a job slot is taken BEFORE the chunk index, so the lowest outstanding chunk always owns a slot
+        while not errors:
+            job = free.get()
+            with order_lock:
+                index = state["next_index"]
+                if index < n_chunks:
+                    state["next_index"] += 1
+            if index >= n_chunks:
+                free.put(job)
+                return
+            try:
+                lo = index * chunk_bytes
+                with FastxReader(args.sequence_file, True, byte_range=(lo, lo + chunk_bytes)) as rd:
+                    rd.next_block(0x7FFFFFFF, job.block)
+                if job.block.n_reads:
+                    job.batch = PackedBatch.from_block(job.block, clip=parameters.search_len, reuse=job.batch)
+            except BaseException as e:
+                job.error = e
+            submit(job, index)
+        with order_lock:                        # stopped by an error: no index beyond the claimed ones will come
+            state["n_chunks"] = min(state["n_chunks"], state["next_index"])
+            order_lock.notify_all()
 
     threads = [threading.Thread(target=gpu_worker, args=(d,), daemon=True) for d in range(n_gpus)]
     threads.append(threading.Thread(target=write_worker, daemon=True))
     for t in threads:
         t.start()
     try:
-        if getattr(args, "start_seq", 1) > 1:
-            reader.skip(args.start_seq - 1)
-        remaining = args.num_seqs if args.num_seqs >= 0 else None
-        i = 0
-        while not errors and (remaining is None or remaining > 0):
-            job = free.get()
-            want = GPU_BATCH_READS if remaining is None else min(GPU_BATCH_READS, remaining)
-            reader.next_block(want, job.block)
-            if job.block.n_reads == 0:
-                free.put(job)
-                break
-            if remaining is not None:
-                remaining -= job.block.n_reads
-            job.batch = PackedBatch.from_block(job.block, clip=parameters.search_len, reuse=job.batch)
-            write_q.put(job)                     # submission order = output order
-            gpu_q[i % n_gpus].put(job)
-            i += 1
+        if parallel:
+            n_chunks = -(-os.path.getsize(args.sequence_file) // chunk_bytes)
+            with order_lock:
+                state["n_chunks"] = n_chunks
+            logging.info(f"Parallel reader: {n_parsers} parser threads over {n_chunks} byte ranges of "
+                         f"{chunk_bytes >> 10} KiB")
+            parsers = [threading.Thread(target=parse_worker, args=(n_chunks,), daemon=True) for _ in range(n_parsers)]
+            for t in parsers:
+                t.start()
+            for t in parsers:
+                t.join()
+        else:
+            submitted = 0
+            reader = FastxReader(args.sequence_file, args.isfastq)
+            try:
+                if getattr(args, "start_seq", 1) > 1:
+                    reader.skip(args.start_seq - 1)
+                remaining = args.num_seqs if args.num_seqs >= 0 else None
+                while not errors and (remaining is None or remaining > 0):
+                    job = free.get()
+                    want = GPU_BATCH_READS if remaining is None else min(GPU_BATCH_READS, remaining)
+                    reader.next_block(want, job.block)
+                    if job.block.n_reads == 0:
+                        free.put(job)
+                        break
+                    if remaining is not None:
+                        remaining -= job.block.n_reads
+                    job.batch = PackedBatch.from_block(job.block, clip=parameters.search_len, reuse=job.batch)
+                    submit(job, submitted)
+                    submitted += 1
+            finally:
+                reader.close()
+                with order_lock:
+                    state["n_chunks"] = submitted
+                    order_lock.notify_all()
     except BaseException as e:
         errors.append(e)
+        with order_lock:
+            if state["n_chunks"] is None:
+                state["n_chunks"] = 0
+            order_lock.notify_all()
     finally:
         for q in gpu_q:
             q.put(None)
-        write_q.put(None)
         for t in threads:
             t.join()
-        reader.close()
         try:
             writer.close()
         except BaseException as e:

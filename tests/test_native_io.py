@@ -276,6 +276,65 @@ def test_native_pipeline_reproduces_reference_expected_output(tmp_path, gz):
         assert produced[k] == expected[k], k
 
 
+@pytest.mark.parametrize("chunk,threads", [(1 << 16, 3), (70_001, 5), (1 << 18, 2)])
+def test_parallel_reader_gives_the_serial_tree(tmp_path, monkeypatch, chunk, threads):
+    """K parser threads over byte ranges of the FASTQ file (re-synchronised on record boundaries, quality lines that
+    begin with '@' included) produce the same tree, in the same per-file record order, as the serial reader."""
+    import argparse
+    from specimux_b200 import orchestration, synth
+    ds = synth.ont037(n_reads=700, seed=11)
+    fq = str(tmp_path / "reads.fastq")
+    with open(fq, "w") as fh:
+        for i, (rid, seq, qual) in enumerate(ds.reads()):
+            if i % 3 == 0:
+                qual = "@" + qual[1:]            # a quality line starting with '@' must not be taken for a title
+            if i % 5 == 0:
+                qual = "+" + qual[1:]
+            fh.write("@%s extra=%d\n%s\n+\n%s\n" % (rid, i, seq, qual))
+    specimens = H.build_specimens(ds.primers, ds.specimens)
+    from oracle import pipeline as orc
+    oparams = orc.setup_params(orc.Tables(ds.primers, ds.specimens))
+    from specimux_b200.models import MatchParameters
+    params = MatchParameters(dict(oparams.max_dist_primers), oparams.max_dist_index, 80, True)
+    trees = {}
+    for mode in ("serial", "parallel"):
+        args = argparse.Namespace(**vars(H.make_args({})))
+        args.sequence_file, args.output_dir, args.output_file_prefix = fq, str(tmp_path / mode), ""
+        args.num_seqs, args.start_seq, args.output_to_files = -1, 1, True
+        monkeypatch.setenv("SMX_PARALLEL_READER", "0" if mode == "serial" else "1")
+        monkeypatch.setenv("SMX_READER_CHUNK_BYTES", str(chunk))
+        monkeypatch.setenv("SMX_READER_THREADS", str(threads))
+        assert orchestration._parallel_read_ok(args, fq, True) == (mode == "parallel")
+        total, matched = orchestration._run_native(args, specimens, params, 1, H.prefilter_for(args),
+                                                   _binding=H.hostsim_binding())
+        assert total == 700
+        trees[mode] = (_tree(args.output_dir), matched)
+    assert trees["serial"][1] == trees["parallel"][1]
+    assert trees["serial"][0] == trees["parallel"][0]
+    assert len(trees["serial"][0]) > 50
+
+
+def test_range_readers_partition_the_file(tmp_path):
+    """Consecutive byte ranges see every record exactly once, whatever the cut points."""
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(400):
+        n = int(rng.integers(1, 300))
+        seq = "".join(rng.choice(list("ACGT"), size=n))
+        qual = "".join(rng.choice(list("@+!IJK#5"), size=n))
+        recs.append(("r%d" % i, seq, qual))
+    fq = str(tmp_path / "x.fastq")
+    _write_fastq(fq, recs)
+    size = os.path.getsize(fq)
+    for step in (97, 1000, 4096, size // 3 + 1, size + 10):
+        got = []
+        for lo in range(0, size, step):
+            with native_io.FastxReader(fq, True, byte_range=(lo, lo + step)) as rd:
+                blk = rd.next_block(1 << 30)
+                got.extend(blk.read(i)[0] for i in range(blk.n_reads))
+        assert got == [r[0] for r in recs], step
+
+
 def test_native_pipeline_num_seqs_and_start(tmp_path):
     import argparse
     from specimux_b200 import orchestration
