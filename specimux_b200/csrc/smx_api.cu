@@ -145,7 +145,7 @@ struct smx_ctx {
     DevBuf<unsigned short> bw_list, bt_g0, bt_class_tasks;
     DevBuf<unsigned char> bt_nw;
     DevBuf<u32> bt_row, bt_eq;
-    u32 bt_class_off[kMaxTaskWords + 1] = {};
+    std::vector<BtClass> bt_classes;
     DevBuf<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
     std::vector<unsigned char> prow_code;   // [primer][32] pattern row codes (sliced primer search)
@@ -407,7 +407,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         }
         if (timed) CU(cudaEventRecord(ln.ev[2], st));
         KMARK(4);
-        if (t.n_btasks) CU(launch_barcode_tasks(t, b, c->bt_class_tasks.p, c->bt_class_off, st, &ln.launches));
+        if (t.n_btasks) CU(launch_barcode_tasks(t, b, c->bt_class_tasks.p, c->bt_classes.data(), (int)c->bt_classes.size(), st, &ln.launches));
     }
     // stage 3: slot digests, single-pass selection, scan
     if (from >= 2) {                                                                                           // re-run
@@ -642,7 +642,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->peq_long, ht.peq_long));
     CUC(upload(c->bt_g0, ht.bt_g0)); CUC(upload(c->bt_nw, ht.bt_nw)); CUC(upload(c->bt_row, ht.bt_row));
     CUC(upload(c->bt_eq, ht.bt_eq)); CUC(upload(c->bt_class_tasks, ht.bt_class_tasks));
-    for (int i = 0; i <= kMaxTaskWords; ++i) c->bt_class_off[i] = ht.bt_class_off[i];
+    c->bt_classes = ht.bt_classes;
     ht.set_task_pointers(c->bt_g0.p, c->bt_nw.p, c->bt_row.p, c->bt_eq.p);
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
     ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,

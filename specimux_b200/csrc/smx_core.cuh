@@ -246,6 +246,9 @@ struct SlotSum {
 };
 static_assert(sizeof(SlotSum) == 24, "SlotSum layout");
 
+// Stage-2 tasks of one (words per task, barcode length): bt_class_tasks[off .. off + count), one kernel launch.
+struct BtClass { int nw, m; u32 off, count; };
+
 // Digest of the barcode hits of one (work entry, stage-2 task), written by the barcode kernel so that the
 // selection stage reads 16 bytes per entry instead of walking the hit sub-lists in the common case.
 struct BarcodeDigest {

@@ -69,10 +69,10 @@ struct HostTables {
     std::vector<unsigned char> b_len, bw_len, bw_primer;
     std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     std::vector<unsigned short> bw_list;
-    std::vector<unsigned short> bt_g0, bt_class_tasks;     // stage-2 tasks; task ids grouped by words per task
+    std::vector<unsigned short> bt_g0, bt_class_tasks;     // stage-2 tasks; task ids grouped by (words per task, barcode length)
     std::vector<unsigned char> bt_nw;
     std::vector<u32> bt_row, bt_eq;
-    u32 bt_class_off[kMaxTaskWords + 1] = {0, 0, 0, 0, 0}; // tasks of NWQ words: bt_class_tasks[off[NWQ-1] .. off[NWQ])
+    std::vector<BtClass> bt_classes;                       // one kernel launch each
     std::vector<i32> pair_pool, spec_pool, spec_dense;
     std::vector<u32> peq_long;
     std::vector<unsigned char> prow_code;      // [primer][32] IUPAC code of primer_rc row i (sliced primer search)
@@ -236,11 +236,15 @@ struct HostTables {
         t.bt_off[nP] = (u32)bt_g0.size();
         t.n_btasks = (int)bt_g0.size();
         if (bt_g0.size() > 65535) return err("more than 65535 barcode tasks");
-        for (int w = 1; w <= kMaxTaskWords; ++w) {
-            bt_class_off[w - 1] = (u32)bt_class_tasks.size();
-            for (size_t k = 0; k < bt_nw.size(); ++k) if (bt_nw[k] == w) bt_class_tasks.push_back((unsigned short)k);
-        }
-        bt_class_off[kMaxTaskWords] = (u32)bt_class_tasks.size();
+        bt_classes.clear();
+        for (int w = 1; w <= kMaxTaskWords; ++w)
+            for (int m = 1; m <= SMX_MAX_PATTERN; ++m) {
+                BtClass c;
+                c.nw = w; c.m = m; c.off = (u32)bt_class_tasks.size(); c.count = 0;
+                for (size_t k = 0; k < bt_nw.size(); ++k)
+                    if (bt_nw[k] == w && bw_len[bt_g0[k]] == m) { bt_class_tasks.push_back((unsigned short)k); ++c.count; }
+                if (c.count) bt_classes.push_back(c);
+            }
         if (bt_eq.empty()) bt_eq.push_back(0);
         if (bt_g0.empty()) { bt_g0.push_back(0); bt_nw.push_back(0); bt_row.push_back(0); }
         if (bt_class_tasks.empty()) bt_class_tasks.push_back(0);

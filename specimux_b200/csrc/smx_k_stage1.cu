@@ -267,6 +267,24 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
     }
 }
 
+cudaError_t launch_barcode_tasks(const Tables &t, const Batch &b, const unsigned short *class_tasks,
+                                 const BtClass *classes, int n_classes, cudaStream_t st, int *launches) {
+    for (int i = 0; i < n_classes; ++i) {
+        const BtClass &c = classes[i];
+        const unsigned short *list = class_tasks + c.off;
+        cudaError_t e;
+        switch (t.k_idx) {
+#define SMX_K2(KK) case KK: e = launch_barcode_class_k##KK(t, b, list, (int)c.count, c.nw, c.m, st); break;
+            SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
+#undef SMX_K2
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_stage_windows(const Tables &t, const Batch &b, cudaStream_t st) {
     // shared-memory tile: 128 reads x the words of a clipped read (+1 word of slack per read, +2 per tile)
     u32 tile_words = 0;

@@ -1,15 +1,23 @@
 // smx_k_stage2.cu -- stage 2: barcode SHW search, bit-sliced across barcodes (smx_kernels.cuh: barcode_task_thread).
+// Compiled once per barcode threshold: -DSMX_STAGE2_K=<k_idx> (Makefile), so the instantiations of the nine
+// thresholds build side by side.
 #include <cuda_runtime.h>
 
 #include "smx_device.cuh"
 #include "smx_launch.hpp"
 
+#ifndef SMX_STAGE2_K
+#error "compile with -DSMX_STAGE2_K=<0..8>"
+#endif
+
 namespace smx {
 
 // One thread per work entry of a matched slot; the thread evaluates the entry against the NWQ bwords of one
 // stage-2 task.  blockIdx.y = strand * n_list + (index into task_list); the task's interleaved table sits in
-// shared memory.
-template <int K, int NWQ>
+// shared memory.  MF > 0: the barcode length is a template argument (the unrolled row sequence then has no early
+// exit: registers are renamed from row to row without moves and the carry-save counter's bookkeeping folds
+// away -- 2,944 instead of 3,960 instructions for K = 3, three words, 13 rows); MF = 0: any length.
+template <int K, int NWQ, int MF>
 __global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned short *task_list, int n_list) {
     constexpr int S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
     constexpr int kRows = NWQ == 1 ? SMX_MAX_PATTERN : 16;      // multi-word tasks only exist for m + K <= 16
@@ -24,7 +32,7 @@ __global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned 
     u32 cnt = b.slot_count[slot];
     if (cnt > b.e_cap) cnt = b.e_cap;
     if (blockIdx.x * blockDim.x >= cnt) return;
-    const int m = t.bw_len[g0];
+    const int m = MF ? MF : (int)t.bw_len[g0];
     if (threadIdx.x == 0) s_acc = 0;
     {
         const u32 *src = t.bt_eq + t.bt_row[task];
@@ -36,7 +44,7 @@ __global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned 
     if (idx < cnt) {
         const u32 read = b.ent_read[(u64)slot * b.e_cap + idx];
         const int p = b.ent_pos[(u64)slot * b.e_cap + idx];
-        work = barcode_task_thread<K, NWQ>(t, b, read, p, idx, strand, primer, task, s_tab);
+        work = barcode_task_thread<K, NWQ, MF>(t, b, read, p, idx, strand, primer, task, s_tab);
     }
     // m is uniform over the block: cells = m * W, word-columns = ceil(m/32) * W with W = sum of lanes x columns (low 20
     // bits of `work`); the bits above count the bwords whose automaton ran (x band cells = evaluated bit-sliced cells)
@@ -53,32 +61,41 @@ __global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned 
     }
 }
 
-template <int K>
-static cudaError_t launch_k(const Tables &t, const Batch &b, const unsigned short *class_tasks,
-                            const u32 class_off[kMaxTaskWords + 1], cudaStream_t st, int *launches) {
-    for (int w = 1; w <= kMaxTaskWords; ++w) {
-        const int n_list = (int)(class_off[w] - class_off[w - 1]);
-        if (!n_list) continue;
-        const unsigned short *list = class_tasks + class_off[w - 1];
-        dim3 grid((b.e_cap + 127) / 128, 2 * n_list);
-        if (w == 1) k_barcode_task<K, 1><<<grid, 128, 0, st>>>(t, b, list, n_list);
-        else if (K > kMaxTaskK) return cudaErrorInvalidValue;          // the host never builds such tasks
-        else if (w == 2) k_barcode_task<(K > kMaxTaskK ? 0 : K), 2><<<grid, 128, 0, st>>>(t, b, list, n_list);
-        else if (w == 3) k_barcode_task<(K > kMaxTaskK ? 0 : K), 3><<<grid, 128, 0, st>>>(t, b, list, n_list);
-        else k_barcode_task<(K > kMaxTaskK ? 0 : K), 4><<<grid, 128, 0, st>>>(t, b, list, n_list);
-        if (launches) ++*launches;
+// barcode lengths with their own instantiation (the lengths barcode sets are built in; every other length runs the
+// any-length form)
+template <int K, int M> struct FixedLen { static constexpr int value = (K >= 1 && K <= kMaxTaskK && M > K && M + K <= 16) ? M : 0; };
+
+template <int K, int NWQ>
+static cudaError_t launch_class(const Tables &t, const Batch &b, const unsigned short *list, int n_list, int m, cudaStream_t st) {
+    dim3 grid((b.e_cap + 127) / 128, 2 * n_list);
+    switch (m) {
+#define SMX_MF(MM)                                                                                         \
+        case MM:                                                                                           \
+            if (FixedLen<K, MM>::value) {                                                                  \
+                k_barcode_task<K, NWQ, FixedLen<K, MM>::value><<<grid, 128, 0, st>>>(t, b, list, n_list);  \
+                return cudaGetLastError();                                                                 \
+            }                                                                                              \
+            break;
+        SMX_MF(8) SMX_MF(10) SMX_MF(12) SMX_MF(13)
+#undef SMX_MF
+        default: break;
     }
+    k_barcode_task<K, NWQ, 0><<<grid, 128, 0, st>>>(t, b, list, n_list);
     return cudaGetLastError();
 }
 
-cudaError_t launch_barcode_tasks(const Tables &t, const Batch &b, const unsigned short *class_tasks,
-                                 const u32 class_off[kMaxTaskWords + 1], cudaStream_t st, int *launches) {
-    switch (t.k_idx) {
-#define SMX_K2(KK) case KK: return launch_k<KK>(t, b, class_tasks, class_off, st, launches);
-        SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
-#undef SMX_K2
-        default: return cudaErrorInvalidValue;
-    }
+#define SMX_CAT_(a, b) a##b
+#define SMX_CAT(a, b) SMX_CAT_(a, b)
+
+cudaError_t SMX_CAT(launch_barcode_class_k, SMX_STAGE2_K)(const Tables &t, const Batch &b, const unsigned short *list,
+                                                          int n_list, int nw, int m, cudaStream_t st) {
+    constexpr int K = SMX_STAGE2_K;
+    if (nw == 1) return launch_class<K, 1>(t, b, list, n_list, m, st);
+    if (K > kMaxTaskK) return cudaErrorInvalidValue;            // the host never builds multi-word tasks there
+    constexpr int KM = K > kMaxTaskK ? 0 : K;
+    if (nw == 2) return launch_class<KM, 2>(t, b, list, n_list, m, st);
+    if (nw == 3) return launch_class<KM, 3>(t, b, list, n_list, m, st);
+    return launch_class<KM, 4>(t, b, list, n_list, m, st);
 }
 
 }  // namespace smx

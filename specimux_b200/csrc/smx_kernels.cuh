@@ -766,7 +766,7 @@ struct CsaCount {
 // one vector load at a compile-time offset from its column's address, shared by the task's words, and the
 // NWQ independent automata interleave in the instruction stream.  Rows beyond m leave the unrolled sequence
 // through one early exit, so the horizontal-delta registers are renamed from row to row without moves.
-template <int K, int NWQ>
+template <int K, int NWQ, int MF = 0>
 SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[NWQ]) {
     typedef BitSliced<K> BS;
     constexpr int NT = BS::NT, S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
@@ -791,8 +791,8 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 1; i <= kRows; ++i) {
-        if (i > m) break;                                   // uniform over the block
+    for (int i = 1; i <= (MF ? MF : kRows); ++i) {
+        if (!MF && i > m) break;                            // uniform over the block; MF: the length is a template argument
         u32 Pv[NWQ], Mv[NWQ];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -832,56 +832,74 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[
     }
 }
 
-// The scalar part of the read-out: exact values of the flagged barcodes of one bword (ascending bit = ascending
-// list position), their hit records and the running digest of the entry.  v0: NV bit-planes of D[m][m-K].
+// The scalar part of the read-out: exact values of ONE flagged barcode (bit q of a bword): smallest D[m][j] over
+// the in-range end columns and the mask of the columns attaining it; v0: NV bit-planes of D[m][m-K].
 struct DigestAcc { int bd, count, jmin, jmax, first_col; u32 nhits; };
+
+template <int K, int NV>
+SMX_HD int barcode_lane_value(const u32 *v0, const u32 *rp, const u32 *rm, int q, int m, int cols, u64 &mask) {
+    constexpr int NT = 2 * K + 1;
+    int val = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int bb = 0; bb < NV; ++bb) val |= (int)((v0[bb] >> q) & 1) << bb;
+    int best = 1 << 20;
+    mask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int tt = 0; tt < NT; ++tt) {
+        if (tt > 0) val += (int)((rp[tt - 1] >> q) & 1) - (int)((rm[tt - 1] >> q) & 1);
+        const int col = m - K + tt;
+        if (col <= cols) {
+            if (val < best) { best = val; mask = 0; }
+            if (val == best) mask |= 1ull << (col - 1);
+        }
+    }
+    return best;
+}
+
+// Hit record + digest update for one barcode hit (list position j) of (gslot, entry); nh = hits of this bword so far.
+SMX_HD void barcode_add_hit(const Tables &t, const Batch &b, u64 gslot, u64 entry, int nh, int j, int best, u64 mask,
+                            int search_start, DigestAcc &acc) {
+    if (nh < t.hit_cap) {
+        smx_barcode_hit h;
+        h.barcode = (uint16_t)j; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = search_start;
+        b.bh_list[(gslot * t.hit_cap + nh) * b.e_cap + entry] = h;
+    }
+    ++acc.nhits;
+    if (best < acc.bd) { acc.bd = best; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; }
+    if (best == acc.bd) {
+        ++acc.count;
+        if (j < acc.jmin) { acc.jmin = j; acc.first_col = lowest_bit64(mask); }
+        if (j > acc.jmax) acc.jmax = j;
+    }
+}
 
 template <int K, int NV>
 SMX_HD void barcode_emit_hits(const Tables &t, const Batch &b, u32 flag, const u32 *v0, const u32 *rp, const u32 *rm,
                               u32 g, u64 gslot, u64 entry, int m, int cols, int search_start, DigestAcc &acc) {
-    constexpr int NT = 2 * K + 1;
     int nh = 0;
     while (flag) {
         int q = lowest_bit32(flag);
         flag &= flag - 1;
-        int val = 0;
-        for (int bb = 0; bb < NV; ++bb) val |= (int)((v0[bb] >> q) & 1) << bb;
-        int best = 1 << 20;
-        u64 mask = 0;
-        for (int tt = 0; tt < NT; ++tt) {
-            if (tt > 0) val += (int)((rp[tt - 1] >> q) & 1) - (int)((rm[tt - 1] >> q) & 1);
-            int col = m - K + tt;
-            if (col > cols) break;
-            if (val < best) { best = val; mask = 0; }
-            if (val == best) mask |= 1ull << (col - 1);
-        }
+        u64 mask;
+        const int best = barcode_lane_value<K, NV>(v0, rp, rm, q, m, cols, mask);
         if (best > K) continue;
-        const int j = (int)t.bw_list[(u64)g * 32 + q];
-        if (nh < t.hit_cap) {
-            smx_barcode_hit h;
-            h.barcode = (uint16_t)j; h.distance = (int16_t)best; h.end_mask = mask; h.search_start = search_start;
-            b.bh_list[(gslot * t.hit_cap + nh) * b.e_cap + entry] = h;
-        }
+        barcode_add_hit(t, b, gslot, entry, nh, (int)t.bw_list[(u64)g * 32 + q], best, mask, search_start, acc);
         ++nh;
-        ++acc.nhits;
-        if (best < acc.bd) { acc.bd = best; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; }
-        if (best == acc.bd) {
-            ++acc.count;
-            if (j < acc.jmin) { acc.jmin = j; acc.first_col = lowest_bit64(mask); }
-            if (j > acc.jmax) acc.jmax = j;
-        }
     }
     b.bh_count[gslot * b.e_cap + entry] = (unsigned char)nh;
     if (nh > t.hit_cap) counter_add(&b.counters[7], 1);      // the library re-runs with a larger cap
 }
 
-// Read-out of the small form: "some in-range end column has D[m][j] <= K" as a threshold test on the biased value
+// Flag planes of the small form: "some in-range end column has D[m][j] <= K" as a threshold test on the biased value
 // u = D + (15 - K): u fits five planes (D[m][m-K] <= m <= 16 - K, at most 2K columns further right) and D <= K
 // exactly when bit 4 of u is clear.  Walking one column to the right adds the +-1 horizontal delta in ONE ripple:
 // the +1 enters as the carry-in, the -1 as an all-ones addend (2 LOP3 per plane).
 template <int K>
-SMX_HD void barcode_readout_small(const Tables &t, const Batch &b, const SmallOut<K> &o, u32 g, u64 gslot, u64 entry,
-                                  int m, int cols, int search_start, DigestAcc &acc) {
+SMX_HD u32 barcode_flags_small(const SmallOut<K> &o, int m, int cols) {
     constexpr int NT = 2 * K + 1;
     u32 u[5];
     {
@@ -912,8 +930,7 @@ SMX_HD void barcode_readout_small(const Tables &t, const Batch &b, const SmallOu
         }
         if (m - K + tt <= cols) flag |= ~u[4];
     }
-    flag &= t.bw_valid[g];
-    barcode_emit_hits<K, 5>(t, b, flag, o.v0, o.rp, o.rm, g, gslot, entry, m, cols, search_start, acc);
+    return flag;
 }
 
 // Read-out of the general form (BitSliced<K>::run: long barcodes): counter planes with a saturation flag.
@@ -953,7 +970,7 @@ SMX_HD void barcode_readout(const Tables &t, const Batch &b, const typename BitS
 // of stage-2 task `task` (all of one barcode length m).  `tab` points at the task's [m][16][S] table (shared
 // memory in the CUDA launch).  Returns lanes x columns of the SURVEY.md 8d work formula (x m = cells) in the low
 // 20 bits and, from bit 20 up, the number of bwords whose automaton actually ran (0 or NWQ).
-template <int K, int NWQ>
+template <int K, int NWQ, int MF = 0>
 SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p, u64 entry, int strand, int primer,
                                u32 task, const u32 *tab) {
     typedef BitSliced<K> BS;
@@ -965,7 +982,7 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
     const int n = (int)b.lengths[read];
     const Geo geo = make_geo(n, t.L);
     const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
-    const int m = t.bw_len[g0];
+    const int m = MF ? MF : (int)t.bw_len[g0];
     int nbits = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -1017,11 +1034,61 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
     acc.bd = 1 << 20; acc.count = 0; acc.jmin = 1 << 20; acc.jmax = -1; acc.first_col = 0; acc.nhits = 0;
     if (small) {
         SmallOut<K> o[NWQ];
-        bitsliced_small_rows<K, NWQ>(tab, m, F, o);
+        bitsliced_small_rows<K, NWQ, MF>(tab, m, F, o);
+        u32 flag[NWQ];
+        int nh[NWQ];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int q = 0; q < NWQ; ++q) barcode_readout_small<K>(t, b, o[q], g0 + q, gslot0 + q, entry, m, cols, f.bs, acc);
+        for (int q = 0; q < NWQ; ++q) { flag[q] = barcode_flags_small<K>(o[q], m, cols) & t.bw_valid[g0 + q]; nh[q] = 0; }
+        // ONE scalar loop over the flagged barcodes of all the task's words (ascending word, then bit = ascending list
+        // position): a work entry usually has a single hit, in whichever word its barcode lives, so a warp runs about
+        // one iteration instead of one per word (the per-word loops were 20 % of the kernel, profiles/r2_d_*).
+        for (;;) {
+            int w = -1;
+            u32 fw = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = NWQ - 1; q >= 0; --q) if (flag[q]) { w = q; fw = flag[q]; }
+            if (w < 0) break;
+            const int bit = lowest_bit32(fw);
+            u32 v0[5], rp[BS::NT > 1 ? BS::NT - 1 : 1], rm[BS::NT > 1 ? BS::NT - 1 : 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < NWQ; ++q) {                 // the chosen word's planes (register selects)
+                if (q == w || q == 0) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int l = 0; l < 5; ++l) v0[l] = o[q].v0[l];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int l = 0; l < BS::NT - 1; ++l) { rp[l] = o[q].rp[l]; rm[l] = o[q].rm[l]; }
+                }
+                if (q == w) flag[q] &= flag[q] - 1;
+            }
+            u64 mask;
+            const int best = barcode_lane_value<K, 5>(v0, rp, rm, bit, m, cols, mask);
+            if (best > K) continue;
+            int nhw = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < NWQ; ++q) if (q == w) nhw = nh[q]++;
+            barcode_add_hit(t, b, gslot0 + w, entry, nhw, (int)t.bw_list[(u64)(g0 + w) * 32 + bit], best, mask, f.bs, acc);
+        }
+        bool over_cap = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < NWQ; ++q) {
+            b.bh_count[(gslot0 + q) * b.e_cap + entry] = (unsigned char)nh[q];
+            over_cap |= nh[q] > t.hit_cap;
+        }
+        if (over_cap) counter_add(&b.counters[7], 1);        // the library re-runs with a larger cap
     } else {
         // long barcodes (m + K > 16): the general band walk (tasks of such lengths hold one word)
         typename BS::Out o;

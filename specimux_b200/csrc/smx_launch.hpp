@@ -16,10 +16,15 @@ cudaError_t launch_primer_sliced(const Tables &t, const Batch &b, int primer, co
 // finish of both strands per (read, primer) + work entries + (with_start) start of the first location
 cudaError_t launch_primer_finish(const Tables &t, const Batch &b, bool with_start, cudaStream_t st);
 cudaError_t launch_primer_long(const Tables &t, const Batch &b, int primer, cudaStream_t st);
-// stage 2: one launch per task width present; class_tasks is the DEVICE copy of HostTables::bt_class_tasks,
-// class_off the host offsets.  *launches receives the number of kernels enqueued.
+// stage 2: one launch per (task width, barcode length) class; class_tasks is the DEVICE copy of
+// HostTables::bt_class_tasks.  *launches receives the number of kernels enqueued.
 cudaError_t launch_barcode_tasks(const Tables &t, const Batch &b, const unsigned short *class_tasks,
-                                 const u32 class_off[kMaxTaskWords + 1], cudaStream_t st, int *launches);
+                                 const BtClass *classes, int n_classes, cudaStream_t st, int *launches);
+// one translation unit per barcode threshold (smx_k_stage2.cu, -DSMX_STAGE2_K=k)
+#define SMX_DECL_K2(KK) cudaError_t launch_barcode_class_k##KK(const Tables &t, const Batch &b, const unsigned short *list, \
+                                                                int n_list, int nw, int m, cudaStream_t st);
+SMX_DECL_K2(0) SMX_DECL_K2(1) SMX_DECL_K2(2) SMX_DECL_K2(3) SMX_DECL_K2(4) SMX_DECL_K2(5) SMX_DECL_K2(6) SMX_DECL_K2(7) SMX_DECL_K2(8)
+#undef SMX_DECL_K2
 // stage 3
 cudaError_t launch_select_fast(const Tables &t, const Batch &b, cudaStream_t st);
 cudaError_t launch_select(const Tables &t, const Batch &b, cudaStream_t st);

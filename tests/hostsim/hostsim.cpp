@@ -235,7 +235,10 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                     int pos = ent_pos[(size_t)slot * e_cap + e];
                     u32 work = 0;
                     switch (t.k_idx * 8 + nw) {
-#define SMX_K2(KK, NN) case KK * 8 + NN: work = barcode_task_thread<KK, NN>(t, b, r, pos, e, s, p, (u32)tk, tab); break;
+// 13-nt barcodes take the fixed-length instantiation, as the CUDA launcher does (smx_k_stage2.cu)
+#define SMX_K2(KK, NN) case KK * 8 + NN: work = (m == 13 && KK >= 1 && KK <= 3) \
+        ? barcode_task_thread<KK, NN, (KK >= 1 && KK <= 3) ? 13 : 0>(t, b, r, pos, e, s, p, (u32)tk, tab) \
+        : barcode_task_thread<KK, NN>(t, b, r, pos, e, s, p, (u32)tk, tab); break;
 #define SMX_K2M(KK) SMX_K2(KK, 1) SMX_K2(KK, 2) SMX_K2(KK, 3) SMX_K2(KK, 4)
                         SMX_K2M(0) SMX_K2M(1) SMX_K2M(2) SMX_K2M(3) SMX_K2M(4)
                         SMX_K2(5, 1) SMX_K2(6, 1) SMX_K2(7, 1) SMX_K2(8, 1)
