@@ -346,6 +346,15 @@ int smx_last_useful_cells(const smx_ctx *ctx, uint64_t cells[2]);
  * out[i*n + j] = distance(seq_i, seq_j). */
 int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint32_t n, int32_t *out);
 
+/* All-pairs infix (HW) edit distances of `n_patterns` byte strings in `n_texts` byte strings on the GPU, plain byte
+ * equality: out[i * n_texts + j] = min over substrings s of text j of the edit distance (pattern i, s), or -1 when
+ * that exceeds pat_k[i] (pat_k[i] < 0: unbounded).  Patterns up to 4096 bytes.  Replaces the
+ * edlib.align(full_seq, partial_seq, mode="HW", task="path", k=max_distance) loop of specimine
+ * (specimine.py:226-248), which reads only editDistance from the result.  Empty pattern: 0; empty text: the
+ * pattern's length whatever k (edlib's empty-sequence rule). */
+int smx_hw_distances(int device, const char *patterns, const uint64_t *pat_off, const int32_t *pat_k, uint32_t n_patterns,
+                     const char *texts, const uint64_t *txt_off, uint32_t n_texts, int32_t *out);
+
 /* Integer-ALU roofline denominator: measured throughput (10^12 ops/s) of independent 32-bit
  * LOP3 (logic) and IADD3 (add) chains over the whole chip, the two instruction classes of the
  * Myers column step.  out[0] = LOP3-only, out[1] = IADD3-only, out[2] = 1:1 mix. */

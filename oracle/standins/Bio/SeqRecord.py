@@ -32,6 +32,15 @@ class SeqRecord:
         if fmt == "fasta":
             return ">%s\n%s\n" % (self.description, str(self.seq))
         if fmt == "fastq":
+            # Bio.SeqIO.QualityIO.FastqPhredWriter.write_record: the description when it already starts with the id,
+            # else "<id> <description>"
+            clean = lambda s: s.replace("\n", " ").replace("\r", " ")
+            ident = clean(self.id) if self.id else ""
+            desc = clean(self.description or "")
+            if desc and desc.split(None, 1)[0] == ident:
+                title = desc
+            else:
+                title = "%s %s" % (ident, desc) if desc else ident
             q = "".join(chr(x + 33) for x in self.letter_annotations["phred_quality"])
-            return "@%s\n%s\n+\n%s\n" % (self.description, str(self.seq), q)
+            return "@%s\n%s\n+\n%s\n" % (title, str(self.seq), q)
         raise ValueError(fmt)

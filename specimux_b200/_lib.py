@@ -74,7 +74,7 @@ EXPORTS = ["smx_abi_version", "smx_last_error", "smx_device_count", "smx_create"
            "smx_download_results", "smx_last_timing", "smx_last_launch_count", "smx_last_work",
            "smx_pairwise_nw", "smx_pack_bound", "smx_pack_reads", "smx_int_alu_peak", "smx_host_alloc",
            "smx_host_free", "smx_flush_l2", "smx_set_pipeline_chunk", "smx_last_chunk_count", "smx_last_deferred", "smx_last_kernel_times", "smx_set_resident_split",
-           "smx_device_pci_bus_id", "smx_pack_stride", "smx_pack_reads_fixed", "smx_copy_peak", "smx_last_useful_cells"]
+           "smx_device_pci_bus_id", "smx_pack_stride", "smx_pack_reads_fixed", "smx_copy_peak", "smx_last_useful_cells", "smx_hw_distances"]
 
 
 class SmxError(RuntimeError):
@@ -131,6 +131,7 @@ def load():
                                              u32p, u64p, u64p, u32p]
         lib.smx_copy_peak.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_double)]
         lib.smx_last_useful_cells.argtypes = [C.c_void_p, u64p]
+        lib.smx_hw_distances.argtypes = [C.c_int, C.c_char_p, u64p, i32p, C.c_uint32, C.c_char_p, u64p, C.c_uint32, i32p]
         if lib.smx_abi_version() != 3:
             raise ImportError("libspecimux_b200.so ABI version mismatch")
         _lib = lib

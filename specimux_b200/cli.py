@@ -39,6 +39,10 @@ def parse_args(argv):
     p.add_argument("--sample-topq", type=int, default=0, metavar="N", help="(accepted for compatibility; not implemented)")
     p.add_argument("-v", "--version", action="version", version=version())
     args = p.parse_args(argv[1:])
+    if args.color:
+        print("specimux_b200: --color highlighting is not implemented; records are written without colour", file=sys.stderr)
+    if args.sample_topq:
+        print("specimux_b200: --sample-topq is not implemented and is ignored", file=sys.stderr)
     if "," in args.num_seqs:
         try:
             start, num = args.num_seqs.split(",")
@@ -85,6 +89,12 @@ def main(argv=None):
     except Exception as e:          # the reference logs worker failures and exits 1 (orchestration.py:222-224)
         logging.error(f"Unexpected error: {e}")
         sys.exit(1)
+
+
+def specimine_main():
+    """Entry point of the `specimine` command (reference cli.py:113-116)."""
+    from . import specimine
+    specimine.main()
 
 
 if __name__ == "__main__":

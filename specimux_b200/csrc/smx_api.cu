@@ -503,23 +503,33 @@ static int lane_resolve(smx_ctx *c, Lane &ln, bool timed) {
     return SMX_OK;
 }
 
-// Copy-out of a lane's compacted records into the caller's array, full or compact form (asynchronous on `st`,
-// which must already be ordered after the lane's kernels).
-static int lane_copy_records(Lane &ln, smx_results *out, u64 rec_base, cudaStream_t st) {
-    if (!ln.n_records) return SMX_OK;
-    if (out->records) {
-        CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, (size_t)ln.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
-    } else if (out->records32) {
+// Compact forms of the lane's compacted records (smx_record32 / smx_record16), produced on the lane's OWN stream: the
+// kernels read the lane's batch buffers (lengths), which the lane's next upload overwrites.
+static int lane_pack_records(Lane &ln, const smx_results *out) {
+    if (!ln.n_records || out->records) return SMX_OK;
+    cudaStream_t st = ln.stream;
+    if (out->records32) {
         CU(ln.records32.ensure((size_t)ln.n_records));
         CU(launch_pack_records32(ln.records.p, (u32)ln.n_records, ln.records32.p, st));
         ++ln.launches;
-        CU(cudaMemcpyAsync(out->records32 + rec_base, ln.records32.p, (size_t)ln.n_records * sizeof(smx_record32), cudaMemcpyDeviceToHost, st));
     } else if (out->records16) {
         CU(ln.records16.ensure((size_t)ln.n_records));
         CU(launch_pack_records16(ln.records.p, (u32)ln.n_records, ln.b.lengths, ln.b.read_base, ln.records16.p, ln.bad16.p, st));
         ++ln.launches;
-        CU(cudaMemcpyAsync(out->records16 + rec_base, ln.records16.p, (size_t)ln.n_records * sizeof(smx_record16), cudaMemcpyDeviceToHost, st));
     }
+    return SMX_OK;
+}
+
+// Copy-out of a lane's records into the caller's array, full or compact form (asynchronous on `st`, which must
+// already be ordered after the lane's kernels and lane_pack_records).
+static int lane_copy_records(Lane &ln, smx_results *out, u64 rec_base, cudaStream_t st) {
+    if (!ln.n_records) return SMX_OK;
+    if (out->records)
+        CU(cudaMemcpyAsync(out->records + rec_base, ln.records.p, (size_t)ln.n_records * sizeof(smx_record), cudaMemcpyDeviceToHost, st));
+    else if (out->records32)
+        CU(cudaMemcpyAsync(out->records32 + rec_base, ln.records32.p, (size_t)ln.n_records * sizeof(smx_record32), cudaMemcpyDeviceToHost, st));
+    else if (out->records16)
+        CU(cudaMemcpyAsync(out->records16 + rec_base, ln.records16.p, (size_t)ln.n_records * sizeof(smx_record16), cudaMemcpyDeviceToHost, st));
     return SMX_OK;
 }
 
@@ -819,7 +829,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
             resident_bounds(c, i, r0, r1);
             if (out->rec_offset)
                 CU(cudaMemcpyAsync(out->rec_offset + r0, l.offsets_src, (size_t)(r1 - r0) * sizeof(u32), cudaMemcpyDeviceToHost, l.stream));
-            { int rc2 = lane_copy_records(l, out, rec_base, l.stream); if (rc2) return rc2; }
+            { int rc2 = lane_pack_records(l, out); if (!rc2) rc2 = lane_copy_records(l, out, rec_base, l.stream); if (rc2) return rc2; }
             rec_base += l.n_records;
         }
         for (int i = 0; i < c->resident_lanes; ++i) CU(cudaStreamSynchronize(c->lane[i].stream));
@@ -838,7 +848,7 @@ int smx_download_results(smx_ctx *c, smx_results *out) {
     cudaStream_t st = ln.stream;
     if (out->rec_offset)
         CU(cudaMemcpyAsync(out->rec_offset, b.rec_offset, ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    { int rc2 = lane_copy_records(ln, out, 0, st); if (rc2) return rc2; }
+    { int rc2 = lane_pack_records(ln, out); if (!rc2) rc2 = lane_copy_records(ln, out, 0, st); if (rc2) return rc2; }
     // level-1 detail is stored padded ([slot][n_pad]) on the device and returned dense ([slot][n])
     if (out->primer_hits)
         CU(cudaMemcpy2DAsync(out->primer_hits, (size_t)n * sizeof(smx_primer_hit), b.phit,
@@ -962,6 +972,7 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         if (rec_base + ln.n_records > out->records_cap || rec_base + ln.n_records > 0xFFFFFFFFull) overflow = true;
         if (!overflow) {
             if ((r = lane_compact(c, ln, (u32)rec_base, false))) return r;
+            if ((r = lane_pack_records(ln, out))) return r;
             // the copy-out runs on its own stream so the lane's next H2D + kernels need not wait for it
             CU(cudaEventRecord(ln.ev_ready, ln.stream));
             CU(cudaStreamWaitEvent(ln.out_stream, ln.ev_ready, 0));
@@ -1122,6 +1133,74 @@ int smx_pairwise_nw(int device, const char *seqs, const uint32_t *seq_off, uint3
     const int rc = run();                                   // the device buffers go on every path
     cudaFree(d_seq); cudaFree(d_off); cudaFree(d_out);
     return rc;
+}
+
+int smx_hw_distances(int device, const char *patterns, const uint64_t *pat_off, const int32_t *pat_k, uint32_t n_patterns,
+                     const char *texts, const uint64_t *txt_off, uint32_t n_texts, int32_t *out) {
+    if (!patterns || !pat_off || !pat_k || !texts || !txt_off || !out) return fail(SMX_ERR_ARG, "smx_hw_distances: null argument");
+    if (!n_patterns || !n_texts) return SMX_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SMX_ERR_NO_DEVICE, "smx_hw_distances: no CUDA device; this library has no CPU path");
+    }
+    // classes by pattern length: lanes per problem and words per lane of the multi-word column vector
+    struct Cls { int sw, w; std::vector<u32> list; };
+    std::vector<Cls> classes;
+    std::vector<u32> empty_pat;
+    for (u32 i = 0; i < n_patterns; ++i) {
+        const u64 m = pat_off[i + 1] - pat_off[i];
+        if (m == 0) { empty_pat.push_back(i); continue; }
+        if (m > 4096) return fail(SMX_ERR_ARG, "smx_hw_distances: pattern %u is %llu long (limit 4096)", i, (unsigned long long)m);
+        const int words = (int)((m + 31) / 32);
+        int sw = 4, w = 1;
+        if (words <= 32) { while (sw < words) sw *= 2; }
+        else { sw = 32; w = words <= 64 ? 2 : 4; }
+        size_t c = 0;
+        for (; c < classes.size(); ++c) if (classes[c].sw == sw && classes[c].w == w) break;
+        if (c == classes.size()) { Cls n; n.sw = sw; n.w = w; classes.push_back(n); }
+        classes[c].list.push_back(i);
+    }
+    CU(cudaSetDevice(device));
+    unsigned char *d_pat = nullptr, *d_txt = nullptr;
+    u64 *d_po = nullptr, *d_to = nullptr;
+    i32 *d_k = nullptr, *d_out = nullptr;
+    u32 *d_list = nullptr, *d_bad = nullptr;
+    const size_t pb = pat_off[n_patterns], tb = txt_off[n_texts];
+    const size_t total = (size_t)n_patterns * n_texts;
+    auto run = [&]() -> int {
+        CU(cudaMalloc((void **)&d_pat, pb ? pb : 1)); CU(cudaMalloc((void **)&d_txt, tb ? tb : 1));
+        CU(cudaMalloc((void **)&d_po, (size_t)(n_patterns + 1) * sizeof(u64))); CU(cudaMalloc((void **)&d_to, (size_t)(n_texts + 1) * sizeof(u64)));
+        CU(cudaMalloc((void **)&d_k, (size_t)n_patterns * sizeof(i32))); CU(cudaMalloc((void **)&d_out, total * sizeof(i32)));
+        CU(cudaMalloc((void **)&d_list, (size_t)n_patterns * sizeof(u32))); CU(cudaMalloc((void **)&d_bad, sizeof(u32)));
+        CU(cudaMemcpy(d_pat, patterns, pb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_txt, texts, tb, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_po, pat_off, (size_t)(n_patterns + 1) * sizeof(u64), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_to, txt_off, (size_t)(n_texts + 1) * sizeof(u64), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_k, pat_k, (size_t)n_patterns * sizeof(i32), cudaMemcpyHostToDevice));
+        CU(cudaMemset(d_bad, 0, sizeof(u32)));
+        size_t off = 0;
+        for (const Cls &c : classes) {
+            CU(cudaMemcpy(d_list + off, c.list.data(), c.list.size() * sizeof(u32), cudaMemcpyHostToDevice));
+            CU(launch_hw_distance(c.sw, c.w, d_pat, d_po, d_k, d_list + off, (u32)c.list.size(), d_txt, d_to, n_texts, d_out, d_bad, 0));
+            off += c.list.size();
+        }
+        CU(cudaDeviceSynchronize());
+        u32 bad = 0;
+        CU(cudaMemcpy(&bad, d_bad, sizeof(u32), cudaMemcpyDeviceToHost));
+        if (bad) return fail(SMX_ERR_ARG, "smx_hw_distances: %u pattern(s) hold more than 64 distinct byte values", bad);
+        CU(cudaMemcpy(out, d_out, total * sizeof(i32), cudaMemcpyDeviceToHost));
+        return SMX_OK;
+    };
+    const int rc = run();
+    cudaFree(d_pat); cudaFree(d_txt); cudaFree(d_po); cudaFree(d_to); cudaFree(d_k); cudaFree(d_out); cudaFree(d_list); cudaFree(d_bad);
+    if (rc) return rc;
+    // an empty pattern has distance 0 everywhere; an empty text leaves the whole pattern unmatched (edlib: editDistance =
+    // pattern length whatever k is -- SURVEY.md Q4)
+    for (u32 i : empty_pat) for (u32 j = 0; j < n_texts; ++j) out[(size_t)i * n_texts + j] = 0;
+    for (u32 j = 0; j < n_texts; ++j)
+        if (txt_off[j + 1] == txt_off[j])
+            for (u32 i = 0; i < n_patterns; ++i) out[(size_t)i * n_texts + j] = (int32_t)(pat_off[i + 1] - pat_off[i]);
+    return SMX_OK;
 }
 
 int smx_int_alu_peak(int device, double out_tops[3]) {

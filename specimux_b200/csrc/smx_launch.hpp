@@ -36,6 +36,10 @@ cudaError_t launch_pack_records16(const smx_record *in, u32 n, const u32 *length
                                   cudaStream_t st);
 cudaError_t launch_expand_lengths(const unsigned short *in, u32 n, u32 *out, cudaStream_t st);
 cudaError_t launch_rebase_offsets(const u32 *in, u32 n, u32 rec_base, u32 *out, cudaStream_t st);
+// specimine: HW distances of the patterns listed in pat_list (all of one (lanes, words per lane) class) in every text
+cudaError_t launch_hw_distance(int sw, int w, const unsigned char *pat, const u64 *pat_off, const i32 *pat_k, const u32 *pat_list,
+                               u32 n_list, const unsigned char *txt, const u64 *txt_off, u32 n_txt, i32 *out, u32 *bad,
+                               cudaStream_t st);
 // utilities
 cudaError_t launch_pairwise_nw(const char *seqs, const u32 *off, u32 n, i32 *out, cudaStream_t st);
 cudaError_t launch_int_peak(int mode, int blocks, int threads, u32 *out, int iters, u32 seed, cudaStream_t st);

@@ -346,6 +346,8 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
     gpu_q = [queue.Queue() for _ in range(n_gpus)]
     errors = []
     counts = [0, 0]
+    busy = {"parse": 0.0, "pack": 0.0, "match": 0.0, "write": 0.0}     # summed over threads (SMX_IO_TRACE=1 logs them)
+    clock = timeit.default_timer
     # jobs reach the writer in input order: `slots[i]` is job i once its parser has claimed it
     order_lock = threading.Condition()
     slots = {}
@@ -357,11 +359,13 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             job = gpu_q[dev].get()
             if job is None:
                 return
+            t0 = clock()
             try:
                 if job.block.n_reads:
                     job.result = matchers[dev].match(job.batch, reuse=job.pool, compact="wire")   # 16-byte records: all the files need
             except BaseException as e:          # surfaced by the writer thread in input order
                 job.error = e
+            busy["match"] += clock() - t0
             job.done.set()
 
     def write_worker():
@@ -378,7 +382,9 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
                 if job.error is not None:
                     raise job.error
                 if not errors and job.block.n_reads:
+                    t0 = clock()
                     writer.write(job.block, job.result.records)
+                    busy["write"] += clock() - t0
                     counts[0] += job.block.n_reads
                     counts[1] += job.result.n_matched
             except BaseException as e:
@@ -408,10 +414,14 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
                 return
             try:
                 lo = index * chunk_bytes
+                t0 = clock()
                 with FastxReader(args.sequence_file, True, byte_range=(lo, lo + chunk_bytes)) as rd:
                     rd.next_block(0x7FFFFFFF, job.block)
+                t1 = clock()
                 if job.block.n_reads:
                     job.batch = PackedBatch.from_block(job.block, clip=parameters.search_len, reuse=job.batch)
+                busy["parse"] += t1 - t0
+                busy["pack"] += clock() - t1
             except BaseException as e:
                 job.error = e
             submit(job, index)
@@ -445,13 +455,17 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
                 while not errors and (remaining is None or remaining > 0):
                     job = free.get()
                     want = GPU_BATCH_READS if remaining is None else min(GPU_BATCH_READS, remaining)
+                    t0 = clock()
                     reader.next_block(want, job.block)
+                    t1 = clock()
+                    busy["parse"] += t1 - t0
                     if job.block.n_reads == 0:
                         free.put(job)
                         break
                     if remaining is not None:
                         remaining -= job.block.n_reads
                     job.batch = PackedBatch.from_block(job.block, clip=parameters.search_len, reuse=job.batch)
+                    busy["pack"] += clock() - t1
                     submit(job, submitted)
                     submitted += 1
             finally:
@@ -470,10 +484,15 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             q.put(None)
         for t in threads:
             t.join()
+        t0 = clock()
         try:
             writer.close()
         except BaseException as e:
             errors.append(e)
+        busy["write"] += clock() - t0
+    if os.environ.get("SMX_IO_TRACE"):
+        logging.info("I/O pipeline busy seconds (summed over threads): " + ", ".join("%s %.3f" % kv for kv in busy.items()) +
+                     "; %d parser thread(s), %d GPU(s)" % (n_parsers, n_gpus))
     if errors:
         raise errors[0]
     return counts[0], counts[1]
