@@ -77,6 +77,7 @@ struct Lane {
     cudaEvent_t ev_ready = nullptr, ev_drained = nullptr;   // records compacted / records copied out
     cudaStream_t aux[kAuxStreams] = {};     // the per-primer sliced searches run side by side
     cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
+    cudaEvent_t ev_dp_done = nullptr;       // stage 1 + 2 (the ALU-bound kernels) of the lane's current chunk are through
     bool drain_pending = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[kKernelMarks] = {};    // per-kernel boundaries of a timed (resident) run
@@ -127,6 +128,7 @@ struct Lane {
         if (ev_ready) { cudaEventDestroy(ev_ready); ev_ready = nullptr; }
         if (ev_counters) { cudaEventDestroy(ev_counters); ev_counters = nullptr; }
         if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+        if (ev_dp_done) { cudaEventDestroy(ev_dp_done); ev_dp_done = nullptr; }
         for (auto &e : ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &a : aux) if (a) { cudaStreamDestroy(a); a = nullptr; }
         if (ev_drained) { cudaEventDestroy(ev_drained); ev_drained = nullptr; }
@@ -171,6 +173,11 @@ struct smx_ctx {
     // chunks first (measured 1.83 vs 1.76 ms on config 2: the extra chunks cost more kernel-chain latency than
     // the earlier first copy-out saves); 2 = same chunk count, first two chunks smaller (1.70 vs 1.70 ms)
     int ramp = 0;
+    // pipelined smx_match_batch: a chunk's kernels start when the previous chunk's ALU-bound stages (1 + 2) are
+    // through, so chunks take the SMs one after the other -- each finishes (and starts its copy-out, and frees its
+    // lane) early -- while a chunk's latency-bound tail still overlaps the next chunk's head.  Without the chain
+    // the in-flight chunks share the SMs evenly and all finish late (SMX_PIPELINE_CHAIN=0 restores that).
+    bool chain = true;
 };
 
 // `prio`: CUDA stream priority of the lane (lower number = served first).  Lanes are filled in index
@@ -183,6 +190,7 @@ static cudaError_t lane_init(Lane &ln, int prio = 0) {
     if ((e = cudaStreamCreateWithFlags(&ln.out_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ln.ev_dp_done, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto &a : ln.aux) if ((e = cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, prio)) != cudaSuccess) return e;
     for (auto &j : ln.ev_join) if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&ln.ev_drained, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -409,6 +417,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         KMARK(4);
         if (t.n_btasks) CU(launch_barcode_tasks(t, b, c->bt_class_tasks.p, c->bt_classes.data(), (int)c->bt_classes.size(), st, &ln.launches));
     }
+    CU(cudaEventRecord(ln.ev_dp_done, st));
     // stage 3: slot digests, single-pass selection, scan
     if (from >= 2) {                                                                                           // re-run
         CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
@@ -675,6 +684,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_TEST_TINY_CAPS")) c->tiny_caps = atoi(env) != 0;
     if (const char *env = getenv("SMX_OVERLAP_START")) c->overlap_start = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env);
+    if (const char *env = getenv("SMX_PIPELINE_CHAIN")) c->chain = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;
     *out = c;
     return SMX_OK;
@@ -999,6 +1009,10 @@ static int match_batch_pipelined(smx_ctx *c, const smx_batch *in, smx_results *o
         if (r0 >= r1) { ln.have_batch = false; continue; }
         mark(issued, 0, ln.stream);
         if ((rc = lane_upload(c, ln, in, r0, r1, shared4))) break;
+        if (c->chain && issued > 0) {
+            Lane &prev = c->lane[(issued - 1) % c->n_lanes];
+            if (prev.ev_dp_done && prev.stream) CU(cudaStreamWaitEvent(ln.stream, prev.ev_dp_done, 0));
+        }
         mark(issued, 1, ln.stream);
         if ((rc = lane_enqueue(c, ln, 0, false))) break;
         mark(issued, 2, ln.stream);

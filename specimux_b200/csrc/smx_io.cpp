@@ -381,6 +381,13 @@ void smx_block_get(const smx_block *b, smx_block_view *out) {
 int smx_reader_next(smx_reader *r, uint32_t max_reads, smx_block *blk) {
     if (!r || !blk) return fail(SMX_IO_ERR_ARG, "smx_reader_next: null argument");
     blk->clear(r->fastq);
+    if (r->stop_off != UINT64_MAX && r->stop_off > r->read_off) {
+        // byte-range reader: the whole range lands in this block -- size the buffers once (bases and qualities are
+        // each a little under half of a four-line FASTQ file) instead of growing them by doubling
+        const size_t span = (size_t)(r->stop_off - r->read_off);
+        if (blk->bases.capacity() < span / 2) blk->bases.reserve(span / 2 + 4096);
+        if (r->fastq && blk->quals.capacity() < span / 2) blk->quals.reserve(span / 2 + 4096);
+    }
     for (uint32_t i = 0; i < max_reads; ++i) {
         int rc = r->fastq ? next_fastq(*r, blk) : next_fasta(*r, blk);
         if (rc < 0) {
@@ -503,7 +510,9 @@ struct Plan {
     Target *primary, *pool_level;
 };
 
-struct Task { uint32_t rec; Target *dst; };
+// One record for one worker: formatted once into `dst`; `copy` (the pool-level duplicate of a full match, owned by
+// the same worker) receives the same bytes.
+struct Task { uint32_t rec; Target *dst; Target *copy; };
 
 struct smx_writer {
     bool to_files = true, fastq = true;
@@ -563,12 +572,14 @@ struct smx_writer {
         f.buf.clear();
     }
 
-    Target *target(uint64_t key, const std::string &path) {
+    // owner_key: files with the same key belong to the same worker (a specimen's primer-pair file and its
+    // pool-level duplicate: the record is formatted once and copied)
+    Target *target(uint64_t key, const std::string &path, uint64_t owner_key) {
         auto it = files.find(key);
         if (it != files.end()) return it->second;
         Target *t = new Target();
         t->file.path = path;
-        t->owner = (int)(all_files.size() % (size_t)n_threads);
+        t->owner = (int)((owner_key * 0x9E3779B97F4A7C15ull >> 33) % (uint64_t)n_threads);
         all_files.push_back(t);
         files.emplace(key, t);
         return t;
@@ -657,7 +668,14 @@ void smx_writer::run_tasks(int t) {
         const size_t before = buf.size();
         const Plan &pl = (*cur_plans)[k.rec];
         format(buf, *cur_blk, cur_recs[k.rec], pl);
-        if (k.dst == pl.primary) bytes += buf.size() - before;      // payload counted once per record
+        const size_t len = buf.size() - before;
+        bytes += len;                                               // payload counted once per record
+        if (k.copy) {
+            Bytes &dup = k.copy->file.buf;
+            memcpy(dup.grow(len), buf.data() + before, len);
+            dup.n += len;
+            if (dup.size() >= flush_bytes()) flush(k.copy->file);
+        }
         if (buf.size() >= flush_bytes()) flush(k.dst->file);
     }
     thread_bytes[t] = bytes;
@@ -770,16 +788,15 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
         static const char *kTop[3] = {"full", "partial", "unknown"};
         auto it = w->files.find(key);
         pl.primary = it != w->files.end() ? it->second
-                   : w->target(key, w->dir + "/" + kTop[top] + "/" + *pl.pool + "/" + *pl.p1 + "-" + *pl.p2 + "/" + w->prefix + *sample_file + w->ext);
-        w->tasks[(size_t)pl.primary->owner].push_back(Task{(uint32_t)i, pl.primary});
+                   : w->target(key, w->dir + "/" + kTop[top] + "/" + *pl.pool + "/" + *pl.p1 + "-" + *pl.p2 + "/" + w->prefix + *sample_file + w->ext, skey);
         if (!rec.trim_empty && (rec.resolution == SMX_RES_FULL_MATCH || rec.resolution == SMX_RES_DEREPLICATED_FULL)) {
-            // pool-level duplicate of full matches (io_utils.py:259-268)
+            // pool-level duplicate of full matches (io_utils.py:259-268): same worker, the formatted bytes are copied
             const uint64_t pkey = (3ull << 62) | (pool_i << 52) | skey;
             auto pit = w->files.find(pkey);
             pl.pool_level = pit != w->files.end() ? pit->second
-                          : w->target(pkey, w->dir + "/full/" + *pl.pool + "/" + w->prefix + *sample_file + w->ext);
-            w->tasks[(size_t)pl.pool_level->owner].push_back(Task{(uint32_t)i, pl.pool_level});
+                          : w->target(pkey, w->dir + "/full/" + *pl.pool + "/" + w->prefix + *sample_file + w->ext, skey);
         }
+        w->tasks[(size_t)pl.primary->owner].push_back(Task{(uint32_t)i, pl.primary, pl.pool_level});
     }
     w->n_records += n_records;
     // ---- formatting

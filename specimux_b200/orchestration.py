@@ -270,13 +270,16 @@ def _native_eligible(args) -> bool:
 
 
 def _reader_chunk_bytes() -> int:
-    """Bytes of the FASTQ file one parser thread takes at a time = one GPU batch (SMX_READER_CHUNK_BYTES)."""
-    return max(1 << 16, int(os.environ.get("SMX_READER_CHUNK_BYTES", str(96 << 20))))
+    """Bytes of the FASTQ file one parser thread takes at a time = one GPU batch (SMX_READER_CHUNK_BYTES).  Small
+    enough that the ring of job slots (blocks + pinned buffers) is re-used many times over a file: a slot's first
+    use pays the page faults of its buffers, and those serialise on the process's memory map."""
+    return max(1 << 16, int(os.environ.get("SMX_READER_CHUNK_BYTES", str(24 << 20))))
 
 
 def _reader_threads(n_gpus: int) -> int:
     """Parser + packer threads of the parallel reader (SMX_READER_THREADS overrides): the host cores left beside one
-    feeder thread per GPU, the writer's pool and this thread, at most 12."""
+    feeder thread per GPU, the writer's pool and this thread: a quarter of the cores, at most 8 (more parser threads
+    only contend for the memory map and the writer's cores: measured on the 16-vCPU box, profiles/r2_*file_to_tree*)."""
     env = os.environ.get("SMX_READER_THREADS")
     if env:
         return max(1, int(env))
@@ -284,7 +287,7 @@ def _reader_threads(n_gpus: int) -> int:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    return max(1, min(12, cores // 2 - 1))
+    return max(1, min(8, cores // 4))
 
 
 def _parallel_read_ok(args, path: str, is_fastq: bool) -> bool:

@@ -25,9 +25,10 @@ params = MatchParameters(k_primers, k_idx, ds.search_len, True)
 tables = MatchTables(specimens, params)
 blob = np.frombuffer(b"ACGT", dtype=np.uint8)[ds.codes].tobytes()
 batch = PackedBatch.from_blob(blob, ds.offsets.astype(np.uint64), clip=ds.search_len)
-for lanes in (2, 3, 4, 6):
+for chain, lanes in ((1, 3), (1, 4), (1, 6), (0, 3)):
     os.environ["SMX_PIPELINE_LANES"] = str(lanes)
-    for chunk in (65536, 98304, 131072, 196608, 262144, 393216, 0):
+    os.environ["SMX_PIPELINE_CHAIN"] = str(chain)
+    for chunk in (49152, 65536, 98304, 131072, 196608, 262144):
         with Matcher(tables) as m:
             m.set_pipeline_chunk(chunk)
             for _ in range(3):
@@ -36,9 +37,10 @@ for lanes in (2, 3, 4, 6):
             for _ in range(10):
                 m.match(batch, reuse=True, compact="wire")
             ms = (time.perf_counter() - t0) * 100.0
-            print("lanes %d chunk %6d: %.3f ms  %.0f M reads/s  (%d chunks)" % (lanes, chunk, ms, n / ms / 1e3, m.last_chunk_count()), flush=True)
+            print("chain %d lanes %d chunk %6d: %.3f ms  %.0f M reads/s  (%d chunks)" % (chain, lanes, chunk, ms, n / ms / 1e3, m.last_chunk_count()), flush=True)
 if os.environ.get("SMX_PROBE_TRACE"):
-    os.environ["SMX_PIPELINE_LANES"] = "3"
+    os.environ["SMX_PIPELINE_LANES"] = "4"
+    os.environ["SMX_PIPELINE_CHAIN"] = "1"
     os.environ["SMX_PIPELINE_TRACE"] = "1"
     with Matcher(tables) as m:
         for _ in range(3):
