@@ -294,9 +294,9 @@ uint64_t smx_result_bound(const smx_ctx *ctx, uint32_t n_reads);
  * Replaces process_sequences' matching and selection (demultiplex.py:108-212,216-598,602-820). */
 int smx_match_batch(smx_ctx *ctx, const smx_batch *batch, smx_results *out);
 
-/* smx_match_batch cuts batches of at least 2 * reads_per_chunk reads into chunks that rotate over
+/* smx_match_batch cuts batches of more than 1.5 * reads_per_chunk reads into chunks that rotate over
  * three streams, overlapping one chunk's H2D, another's kernels and a third's D2H; the results are
- * identical to the one-shot form.  Default 131072 (env SMX_PIPELINE_CHUNK); 0 disables.  The
+ * identical to the one-shot form.  Default 262144 (env SMX_PIPELINE_CHUNK); 0 disables.  The
  * reference's unit of work is a 1000-read batch per worker process (orchestration.py:165,199). */
 int smx_set_pipeline_chunk(smx_ctx *ctx, uint32_t reads_per_chunk);
 int smx_last_chunk_count(const smx_ctx *ctx);   /* chunks used by the last smx_match_batch */

@@ -142,7 +142,8 @@ struct smx_ctx {
     Tables t;
     // table storage
     DevBuf<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
-    DevBuf<unsigned char> b_len, bw_len, bw_primer;
+    DevBuf<unsigned char> b_len, bw_len, bw_primer, b_codes;
+    DevBuf<u32> b_code_off, bw_iupac;
     DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq, peq_long;
     DevBuf<unsigned short> bw_list, bt_g0, bt_class_tasks;
     DevBuf<unsigned char> bt_nw;
@@ -162,7 +163,8 @@ struct smx_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane_done[kMaxLanes] = {};
     DevBuf<u32> shared_packed4;            // pipelined mode: the (small) exact side stream, uploaded once
     DevBuf<unsigned char> l2_scratch;
-    u32 chunk_reads = 128 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK)
+    u32 chunk_reads = 256 * 1024;          // pipelined smx_match_batch: reads per chunk (SMX_PIPELINE_CHUNK); measured best
+                                           // for the 16-byte wire records: 1.21 ms at 256k vs 1.29 ms at 128k (config 2)
     float total_ms = 0, stage_ms[4] = {0, 0, 0, 0}, kernel_ms[kKernelTimes] = {};
     int last_chunks = 0;
     bool trace = false;
@@ -173,11 +175,12 @@ struct smx_ctx {
     // chunks first (measured 1.83 vs 1.76 ms on config 2: the extra chunks cost more kernel-chain latency than
     // the earlier first copy-out saves); 2 = same chunk count, first two chunks smaller (1.70 vs 1.70 ms)
     int ramp = 0;
-    // pipelined smx_match_batch: a chunk's kernels start when the previous chunk's ALU-bound stages (1 + 2) are
-    // through, so chunks take the SMs one after the other -- each finishes (and starts its copy-out, and frees its
-    // lane) early -- while a chunk's latency-bound tail still overlaps the next chunk's head.  Without the chain
-    // the in-flight chunks share the SMs evenly and all finish late (SMX_PIPELINE_CHAIN=0 restores that).
-    bool chain = true;
+    // pipelined smx_match_batch, SMX_PIPELINE_CHAIN=1: a chunk's kernels start only when the previous chunk's
+    // ALU-bound stages (1 + 2) are through, so that chunks take the SMs one after the other and finish staggered.
+    // Measured (profiles/r2_g_e2e_probe.txt): no gain -- one 128k..256k-read chunk does not fill the GPU (its ten
+    // dependent launches take ~0.3 ms alone against 0.11 ms of pure throughput), so sharing the SMs among the
+    // in-flight chunks is what keeps them busy: 1.21 ms unchained vs 1.23..1.37 ms chained on config 2.  Off.
+    bool chain = false;
 };
 
 // `prio`: CUDA stream priority of the lane (lower number = served first).  Lanes are filled in index
@@ -610,6 +613,7 @@ void smx_destroy(smx_ctx *c) {
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release();
     c->shared_packed4.release(); c->l2_scratch.release(); c->peq_long.release();
     c->bt_g0.release(); c->bt_nw.release(); c->bt_row.release(); c->bt_eq.release(); c->bt_class_tasks.release();
+    c->b_codes.release(); c->b_code_off.release(); c->bw_iupac.release();
     delete c;
 }
 
@@ -618,8 +622,8 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     *out = nullptr;
     HostTables ht;
     if (!ht.build(tb, pr)) return fail(SMX_ERR_ARG, "smx_create: %s", ht.error.c_str());
-    if (ht.t.k_idx > 8)
-        return fail(SMX_ERR_ARG, "smx_create: barcode distance threshold %d exceeds the supported 8", ht.t.k_idx);
+    if (ht.t.k_idx > kMaxBarcodeK)
+        return fail(SMX_ERR_ARG, "smx_create: barcode distance threshold %d exceeds the supported %d", ht.t.k_idx, kMaxBarcodeK);
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) {
@@ -663,6 +667,8 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->bt_eq, ht.bt_eq)); CUC(upload(c->bt_class_tasks, ht.bt_class_tasks));
     c->bt_classes = ht.bt_classes;
     ht.set_task_pointers(c->bt_g0.p, c->bt_nw.p, c->bt_row.p, c->bt_eq.p);
+    CUC(upload(c->b_codes, ht.b_codes)); CUC(upload(c->b_code_off, ht.b_code_off)); CUC(upload(c->bw_iupac, ht.bw_iupac));
+    ht.set_code_pointers(c->b_codes.p, c->b_code_off.p, c->bw_iupac.p);
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);
     ht.set_pointers(c->peq_rc.p, c->peq_rcrev.p, c->peq_fw.p, c->b_len.p, c->pb_barcode.p,
                     c->pair_fwd.p, c->pair_rev.p, c->pair_pool.p, c->spec_key.p, c->spec_key_off.p,
@@ -1051,7 +1057,7 @@ int smx_match_batch(smx_ctx *c, const smx_batch *in, smx_results *out) {
     if (rc) return rc;
     const bool detail = out->primer_hits || out->endmask_bits || out->barcode_hits || out->orient_hits;
     out->n_barcode_loc_hits = 0;
-    if (!detail && c->chunk_reads && in->n_reads >= 2 * (u64)c->chunk_reads) {
+    if (!detail && c->chunk_reads && in->n_reads > (u64)c->chunk_reads + c->chunk_reads / 2) {
         CU(cudaSetDevice(c->device));
         return match_batch_pipelined(c, in, out);
     }

@@ -33,6 +33,7 @@ constexpr int kMaxPairs = 64;       // candidate slots per read = 2 * pairs
 constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in the first pass
 constexpr int kBigGroups = 4096;
 constexpr int kMaxTaskWords = 4;    // bwords one stage-2 thread evaluates side by side
+constexpr int kMaxBarcodeK = 12;     // largest barcode threshold k_idx (the reference derives ceil(min distance / 2))
 constexpr int kMaxTaskK = 4;        // largest k_idx with multi-word stage-2 tasks (beyond: one bword per task)
 // control block of a batch: kCtrWords 64-bit counters followed by the 2 * SMX_MAX_PRIMERS u32 per-slot entry counts
 constexpr int kCtrDeferred = 8;     // (u32) reads left to the general selection kernel
@@ -199,6 +200,10 @@ struct Tables {
     const u64 *peq_fw;       // [primer][16]   forward-sense primer (explicit orientation test)
     const u32 *peq_long;     // long primers: [rc | rcrev | fw][16 symbols][p_sw words], pattern top-aligned in 32*p_sw bits
     const unsigned char *b_len;    // [list entry]
+    const unsigned char *b_codes;  // barcode_rc symbols (4-bit codes, one per byte) of every list entry, concatenated
+    const u32 *b_code_off;         // [list entry] offset into b_codes
+    const u32 *bw_iupac;           // [bword] bit lanes whose barcode holds an IUPAC code (exact Bloom emulation, see
+                                   // bloom_literal_yes)
     const u32 *pb_barcode;   // [list entry] global barcode id
 
     // Bit-sliced barcode match table: barcodes of one primer and one length are grouped 32 to a

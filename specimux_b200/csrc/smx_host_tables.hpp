@@ -66,7 +66,8 @@ inline bool build_peq(const char *s, int m, bool reversed, u64 *out /*16*/) {
 struct HostTables {
     Tables t;
     std::vector<u64> peq_rc, peq_rcrev, peq_fw, spec_key, spec_p1, spec_p2;
-    std::vector<unsigned char> b_len, bw_len, bw_primer;
+    std::vector<unsigned char> b_len, bw_len, bw_primer, b_codes;
+    std::vector<u32> b_code_off, bw_iupac;
     std::vector<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq;
     std::vector<unsigned short> bw_list;
     std::vector<unsigned short> bt_g0, bt_class_tasks;     // stage-2 tasks; task ids grouped by (words per task, barcode length)
@@ -165,16 +166,18 @@ struct HostTables {
                 if (t.k_idx >= m) return err("barcode distance threshold %d must be below barcode length %d", t.k_idx, m);
                 for (int i = 0; i < m; ++i) if (code_of(s[i]) < 0) return err("barcode has a non-IUPAC character");
                 b_str[e].assign(s, s + m);
-                if (t.prefilter)
-                    for (int i = 0; i < m; ++i)
-                        if (code_of(s[i]) > 3)
-                            return err("Bloom-prefilter emulation needs A/C/G/T-only barcodes; pass prefilter=0 "
-                                       "(--disable-prefilter)");
                 b_len[e] = (unsigned char)m;
             }
         }
+        b_codes.clear(); b_code_off.assign(n_list + 1, 0);
+        for (u32 e = 0; e < n_list; ++e) {
+            b_code_off[e] = (u32)b_codes.size();
+            for (char ch : b_str[e]) b_codes.push_back((unsigned char)code_of(ch));
+        }
+        b_code_off[n_list] = (u32)b_codes.size();
+        if (b_codes.empty()) b_codes.push_back(0);
         // bit-sliced barcode words: per primer, barcodes grouped by length, 32 to a word
-        bw_len.clear(); bw_primer.clear(); bw_row.clear(); bw_valid.clear(); bw_list.clear(); beq.clear();
+        bw_len.clear(); bw_primer.clear(); bw_row.clear(); bw_valid.clear(); bw_list.clear(); beq.clear(); bw_iupac.clear();
         for (int p = 0; p < nP; ++p) {
             t.bw_off[p] = (u32)bw_len.size();
             std::vector<int> lens;
@@ -190,6 +193,7 @@ struct HostTables {
                     bw_primer.push_back((unsigned char)p);
                     bw_row.push_back((u32)(beq.size() / 16));
                     bw_valid.push_back(cnt == 32 ? ~0u : ((1u << cnt) - 1));
+                    bw_iupac.push_back(0);
                     size_t row0 = beq.size();
                     beq.resize(row0 + (size_t)m * 16, 0);
                     for (size_t q = 0; q < 32; ++q) {
@@ -198,6 +202,7 @@ struct HostTables {
                         bw_list.push_back((unsigned short)(e - tb->pb_off[p]));
                         for (int i = 0; i < m; ++i) {
                             int pc = code_of(b_str[e][i]);
+                            if (pc > 3) bw_iupac.back() |= 1u << q;
                             for (int c = 0; c < 16; ++c)
                                 if (sym_equal(pc, c)) beq[row0 + (size_t)i * 16 + c] |= 1u << q;
                         }
@@ -291,12 +296,17 @@ struct HostTables {
                      spec_row.data(), spec_p1.data(), spec_p2.data(), spec_pool.data());
         set_bword_pointers(bw_len.data(), bw_primer.data(), bw_row.data(), bw_valid.data(), bw_list.data(), beq.data());
         set_task_pointers(bt_g0.data(), bt_nw.data(), bt_row.data(), bt_eq.data());
+        set_code_pointers(b_codes.data(), b_code_off.data(), bw_iupac.data());
         return true;
     }
 
     void set_bword_pointers(const unsigned char *len, const unsigned char *prim, const u32 *row, const u32 *valid,
                             const unsigned short *list, const u32 *eq) {
         t.bw_len = len; t.bw_primer = prim; t.bw_row = row; t.bw_valid = valid; t.bw_list = list; t.beq = eq;
+    }
+
+    void set_code_pointers(const unsigned char *codes, const u32 *off, const u32 *iupac) {
+        t.b_codes = codes; t.b_code_off = off; t.bw_iupac = iupac;
     }
 
     void set_task_pointers(const unsigned short *g0, const unsigned char *nw, const u32 *row, const u32 *eq) {

@@ -7,7 +7,7 @@
 #include "smx_launch.hpp"
 
 #ifndef SMX_STAGE2_K
-#error "compile with -DSMX_STAGE2_K=<0..8>"
+#error "compile with -DSMX_STAGE2_K=<0..12>"
 #endif
 
 namespace smx {

@@ -602,7 +602,7 @@ SMX_HD void primer_start_thread(const Tables &t, const Batch &b, u32 slot, u32 e
 
 template <int K> struct BitSliced {
     static constexpr int NT = 2 * K + 1;                       // band width
-    static constexpr int NB = K <= 1 ? 3 : (K <= 4 ? 4 : 5);   // counter bits: values up to 3K+1 matter
+    static constexpr int NB = K <= 1 ? 3 : (K <= 4 ? 4 : (K <= 10 ? 5 : 6));   // counter bits: values up to 3K+1 matter
 
     struct Out { u32 rp[NT > 1 ? NT - 1 : 1], rm[NT > 1 ? NT - 1 : 1], cnt[NB], over; };
 
@@ -618,10 +618,9 @@ template <int K> struct BitSliced {
         inc = ~X;                                              // D[i][j] - D[i-1][j-1]
     }
 
-    // beq_rows: table rows of this bword ([i][16]); rowwin(i): nibble t = 4-bit symbol of flank
-    // column i-K+t (1-based columns), kSymOther beyond the flank.
-    template <typename RowWin>
-    static SMX_HD void run(const u32 *beq_rows, int m, RowWin rowwin, Out &o) {
+    // beq_rows: table rows of this bword ([i][16]); fsym[j - 1]: 4-bit symbol of flank column j (1-based),
+    // kSymOther beyond the flank (m + K entries).
+    static SMX_HD void run(const u32 *beq_rows, int m, const unsigned char *fsym, Out &o) {
         u32 HP[NT], HM[NT];                                    // horizontal deltas of the previous row
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -634,7 +633,6 @@ template <int K> struct BitSliced {
         o.over = 0;
         for (int i = 1; i <= m; ++i) {
             const u32 *row = beq_rows + (i - 1) * 16;
-            const u64 W = rowwin(i);
             u32 Pv = ~0u, Mv = 0;                              // column 0 / below the band: +1
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -644,7 +642,7 @@ template <int K> struct BitSliced {
                 if (j < 1) continue;                           // uniform over the warp
                 u32 Ph = t < NT - 1 ? HP[t + 1] : ~0u;          // above the band: +1
                 u32 Mh = t < NT - 1 ? HM[t + 1] : 0u;
-                u32 Eq = row[(u32)(W >> (4 * t)) & 15u];
+                u32 Eq = row[j <= m + K ? fsym[j - 1] : (unsigned char)kSymOther];
                 u32 nPv, nMv, nPh, nMh, inc;
                 cell(Eq, Pv, Mv, Ph, Mh, nPv, nMv, nPh, nMh, inc);
                 if (t == 0) {                                   // lower diagonal: anchor += inc
@@ -832,6 +830,38 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[
     }
 }
 
+// BloomPrefilter.match for a barcode that holds IUPAC codes, with an exact set (bloom_filter.py:70-101, 176-186): the
+// filter's keys are barcode + variant[:m-k] over all variants within k edits of the barcode STRING whose substituted
+// / inserted characters come from "ACGT"; unedited positions keep the barcode's own character.  So the key
+// barcode + flank[:m-k] is present iff the flank prefix is within k such edits of some prefix of the barcode, a
+// flank symbol matching a barcode position only when it is the same character (a read's N equals the barcode's N,
+// its A does not) and a flank symbol that is not A/C/G/T never being created by an edit.  For A/C/G/T-only barcodes
+// this reduces to "the prefix is A/C/G/T" (no false negatives) and is tested on the whole word instead.
+// bc: the barcode_rc symbols (4-bit codes); sym(x): symbol x of the flank the prefilter looks at.
+template <typename Sym>
+SMX_HD bool bloom_literal_yes(const unsigned char *bc, int m, int K, Sym sym) {
+    const int need = m - K;
+    if (need <= 0) return true;
+    int prev[SMX_MAX_PATTERN + 1], cur[SMX_MAX_PATTERN + 1];
+    const int kInf = 1 << 20;
+    for (int j = 0; j <= m; ++j) prev[j] = j;
+    for (int i = 0; i < need; ++i) {
+        const int ch = sym(i);
+        const bool creatable = ch <= 3;
+        cur[0] = creatable ? prev[0] + 1 : kInf;
+        for (int j = 1; j <= m; ++j) {
+            int best = (ch == (int)bc[j - 1] && ch != kSymOther) ? prev[j - 1] : (creatable ? prev[j - 1] + 1 : kInf);
+            if (creatable && prev[j] + 1 < best) best = prev[j] + 1;
+            if (cur[j - 1] + 1 < best) best = cur[j - 1] + 1;
+            cur[j] = best < kInf ? best : kInf;
+        }
+        for (int j = 0; j <= m; ++j) prev[j] = cur[j];
+    }
+    int best = prev[0];
+    for (int j = 1; j <= m; ++j) if (prev[j] < best) best = prev[j];
+    return best <= K;
+}
+
 // The scalar part of the read-out: exact values of ONE flagged barcode (bit q of a bword): smallest D[m][j] over
 // the in-range end columns and the mask of the columns attaining it; v0: NV bit-planes of D[m][m-K].
 struct DigestAcc { int bd, count, jmin, jmax, first_col; u32 nhits; };
@@ -877,16 +907,16 @@ SMX_HD void barcode_add_hit(const Tables &t, const Batch &b, u64 gslot, u64 entr
     }
 }
 
-template <int K, int NV>
+template <int K, int NV, typename LaneOk>
 SMX_HD void barcode_emit_hits(const Tables &t, const Batch &b, u32 flag, const u32 *v0, const u32 *rp, const u32 *rm,
-                              u32 g, u64 gslot, u64 entry, int m, int cols, int search_start, DigestAcc &acc) {
+                              u32 g, u64 gslot, u64 entry, int m, int cols, int search_start, DigestAcc &acc, LaneOk lane_ok) {
     int nh = 0;
     while (flag) {
         int q = lowest_bit32(flag);
         flag &= flag - 1;
         u64 mask;
         const int best = barcode_lane_value<K, NV>(v0, rp, rm, q, m, cols, mask);
-        if (best > K) continue;
+        if (best > K || !lane_ok(g, q)) continue;
         barcode_add_hit(t, b, gslot, entry, nh, (int)t.bw_list[(u64)g * 32 + q], best, mask, search_start, acc);
         ++nh;
     }
@@ -934,9 +964,9 @@ SMX_HD u32 barcode_flags_small(const SmallOut<K> &o, int m, int cols) {
 }
 
 // Read-out of the general form (BitSliced<K>::run: long barcodes): counter planes with a saturation flag.
-template <int K>
+template <int K, typename LaneOk>
 SMX_HD void barcode_readout(const Tables &t, const Batch &b, const typename BitSliced<K>::Out &o, u32 g, u64 gslot, u64 entry,
-                            int m, int cols, int search_start, DigestAcc &acc) {
+                            int m, int cols, int search_start, DigestAcc &acc, LaneOk lane_ok) {
     typedef BitSliced<K> BS;
     u32 v[BS::NB];
 #if defined(__CUDA_ARCH__)
@@ -963,7 +993,7 @@ SMX_HD void barcode_readout(const Tables &t, const Batch &b, const typename BitS
         if (m - K + tt <= cols) flag |= planes_le<K, BS::NB>(v) & ~ov;
     }
     flag &= t.bw_valid[g];
-    barcode_emit_hits<K, BS::NB>(t, b, flag, o.cnt, o.rp, o.rm, g, gslot, entry, m, cols, search_start, acc);
+    barcode_emit_hits<K, BS::NB>(t, b, flag, o.cnt, o.rp, o.rm, g, gslot, entry, m, cols, search_start, acc, lane_ok);
 }
 
 // One work entry (matched slot of a read, one equal-best primer end at staged position p) against the NWQ bwords
@@ -1008,20 +1038,36 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
         if (cols < 16) F |= ~0ull << (4 * cols);
     }
     bool skip = cols < m - K || cols <= 0;           // D[m][j] >= m - j > K for every column
+    bool flank_exotic = false;                       // the prefilter's flank prefix holds a symbol other than A/C/G/T
+    u32 iupac_any = 0;                               // some barcode of the task holds an IUPAC code
     if (t.prefilter && !skip) {
-        // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key
-        // barcode_rc + flank[:m-k] can only be present if those m-k symbols exist and are
-        // all A/C/G/T; for such flanks the filter has no false negatives.
+        // BloomPrefilter.match (bloom_filter.py:176-186) with an exact set: the key barcode_rc + flank[:m-k] can only
+        // be present if those m-k symbols exist; for an A/C/G/T-only barcode they must also all be A/C/G/T, and for
+        // such flanks the filter has no false negatives.  Barcodes with IUPAC codes get the exact
+        // per-barcode test (bloom_literal_yes) on the few lanes that survive the search.
         const int need = m - K;
         if (n - f.a_pref < need) skip = true;
         else if (small && f.a_pref == f.a_align) {
             u64 chk = need >= 16 ? ~0ull : ((1ull << (4 * need)) - 1);
-            skip = (F & chk & 0xCCCCCCCCCCCCCCCCull) != 0;
+            flank_exotic = (F & chk & 0xCCCCCCCCCCCCCCCCull) != 0;
         } else {
             for (int x = 0; x < need; ++x)
-                if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { skip = true; break; }
+                if (staged_sym(t, b, read, strand, f.a_pref - geo.woff + x) > 3) { flank_exotic = true; break; }
         }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < NWQ; ++q) iupac_any |= t.bw_iupac[g0 + q];
+        if (flank_exotic && !iupac_any) skip = true;
     }
+    // a flagged barcode (bit `bit` of bword g) passes the prefilter emulation
+    auto lane_ok = [&](u32 g, int bit) -> bool {
+        if (!t.prefilter) return true;
+        if (!((t.bw_iupac[g] >> bit) & 1u)) return !flank_exotic;
+        const u32 e = t.pb_off[primer] + t.bw_list[(u64)g * 32 + bit];
+        return bloom_literal_yes(t.b_codes + t.b_code_off[e], m, K,
+                                 [&](int x) { return staged_sym(t, b, read, strand, f.a_pref - geo.woff + x); });
+    };
     if (skip) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -1072,7 +1118,7 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
             }
             u64 mask;
             const int best = barcode_lane_value<K, 5>(v0, rp, rm, bit, m, cols, mask);
-            if (best > K) continue;
+            if (best > K || ((flank_exotic || iupac_any) && !lane_ok(g0 + w, bit))) continue;
             int nhw = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -1092,17 +1138,11 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
     } else {
         // long barcodes (m + K > 16): the general band walk (tasks of such lengths hold one word)
         typename BS::Out o;
-        auto rowwin = [&](int i) -> u64 {
-            u64 W = 0;
-            for (int tt = 0; tt < BS::NT; ++tt) {
-                int j = i - K + tt;
-                u64 c = (j >= 1 && j <= cols) ? (u64)staged_sym(t, b, read, strand, base + j - 1) : 15ull;
-                W |= c << (4 * tt);
-            }
-            return W;
-        };
-        BS::run(tab, m, rowwin, o);
-        barcode_readout<K>(t, b, o, g0, gslot0, entry, m, cols, f.bs, acc);
+        unsigned char fsym[SMX_MAX_PATTERN];                    // m + K <= SMX_MAX_PATTERN flank symbols
+        for (int j = 1; j <= m + K; ++j)
+            fsym[j - 1] = (unsigned char)(j <= cols ? staged_sym(t, b, read, strand, base + j - 1) : kSymOther);
+        BS::run(tab, m, fsym, o);
+        barcode_readout<K>(t, b, o, g0, gslot0, entry, m, cols, f.bs, acc, lane_ok);
     }
     if (acc.nhits) {
         dg.nhits = acc.nhits; dg.bd = (signed char)acc.bd; dg.count = (unsigned short)(acc.count > 65535 ? 65535 : acc.count);

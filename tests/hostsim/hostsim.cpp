@@ -241,7 +241,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         : barcode_task_thread<KK, NN>(t, b, r, pos, e, s, p, (u32)tk, tab); break;
 #define SMX_K2M(KK) SMX_K2(KK, 1) SMX_K2(KK, 2) SMX_K2(KK, 3) SMX_K2(KK, 4)
                         SMX_K2M(0) SMX_K2M(1) SMX_K2M(2) SMX_K2M(3) SMX_K2M(4)
-                        SMX_K2(5, 1) SMX_K2(6, 1) SMX_K2(7, 1) SMX_K2(8, 1)
+                        SMX_K2(5, 1) SMX_K2(6, 1) SMX_K2(7, 1) SMX_K2(8, 1) SMX_K2(9, 1) SMX_K2(10, 1) SMX_K2(11, 1) SMX_K2(12, 1)
 #undef SMX_K2M
 #undef SMX_K2
                         default: snprintf(g_err, sizeof(g_err), "unsupported k_idx / task width"); return SMX_ERR_ARG;

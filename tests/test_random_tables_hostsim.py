@@ -127,6 +127,88 @@ def make_case(seed, long_primers=False):
     return primers, specimens, reads, k_idx, flags
 
 
+def make_iupac_barcode_case(seed):
+    """Barcodes that hold IUPAC codes, searched with the Bloom prefilter ON (the default flags): the reference builds
+    the filter's variants from the barcode STRING (bloom_filter.py:70-101), so an N in a barcode only passes the
+    filter where the read has a literal N or an edit is spent on it, while edlib itself matches it for free.
+    Uniform barcode length (the reference takes the filter's key length from one barcode)."""
+    rng = random.Random(7000 + seed)
+    primers = [("F0", rand_seq(rng, 20), "forward", ["P0"]), ("R0", rand_seq(rng, 22), "reverse", ["P0"])]
+    if rng.random() < 0.5:
+        primers.append(("F1", rand_seq(rng, 18), "forward", ["P0"]))
+    blen = rng.choice([11, 13, 13])
+
+    def barcode():
+        s = list(rand_seq(rng, blen))
+        if rng.random() < 0.6:
+            for _ in range(rng.randint(1, 2)):
+                i = rng.randrange(blen)
+                s[i] = rng.choice([c for c, v in IUPAC.items() if s[i] in v or s[i] == c])
+        return "".join(s)
+    b1s = sorted({barcode() for _ in range(rng.randint(3, 20))})
+    b2s = sorted({barcode() for _ in range(rng.randint(3, 40))})
+    specimens, seen = [], set()
+    for i in range(rng.randint(5, 60)):
+        p1 = rng.choice([p[0] for p in primers if p[2] == "forward"])
+        b1, b2 = rng.choice(b1s), rng.choice(b2s)
+        if (b1, b2, p1) in seen:
+            continue
+        seen.add((b1, b2, p1))
+        specimens.append(("S%03d" % i, "P0", b1, p1, b2, "R0"))
+    by_name = {p[0]: p for p in primers}
+    reads = []
+    for r in range(70):
+        sp = rng.choice(specimens)
+
+        def concrete(bc):           # what a read carries where the barcode has a code: a base of the set, or a literal N
+            return "".join((("N" if rng.random() < 0.3 else rng.choice(IUPAC[c])) if c in IUPAC else c) for c in bc)
+        s = (rand_seq(rng, rng.randint(0, 20)) + concrete(sp[2]) + by_name[sp[3]][1] + rand_seq(rng, rng.randint(30, 200)) +
+             reverse_complement(by_name[sp[5]][1]) + reverse_complement(concrete(sp[4])) + rand_seq(rng, rng.randint(0, 20)))
+        s = mutate(rng, s, rng.choice([0.0, 0.03, 0.08]))
+        if rng.random() < 0.5:
+            s = reverse_complement(s)
+        reads.append(("q%04d" % r, s, "I" * len(s)))
+    flags = dict(search_len=80, trim=rng.choice(["barcodes", "tails"]), dereplicate=rng.choice(["best", "none"]),
+                 disable_preorient=False, disable_prefilter=False)
+    return primers, specimens, reads, rng.choice([1, 2, 3]), flags
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_iupac_barcodes_with_prefilter(seed):
+    run_case(*make_iupac_barcode_case(seed), tag="iupac barcode seed %d" % seed)
+
+
+def make_large_k_case(seed):
+    """Long barcodes searched with thresholds beyond 8 (the reference derives k = ceil(min pairwise distance / 2),
+    orchestration.py:583-600): the general band walk of stage 2 with up to 25 diagonals."""
+    rng = random.Random(9000 + seed)
+    primers = [("F0", rand_seq(rng, 21), "forward", ["P0"]), ("R0", rand_seq(rng, 19), "reverse", ["P0"])]
+    blen = rng.choice([24, 28, 30])
+    b1s = sorted({rand_seq(rng, blen) for _ in range(rng.randint(2, 12))})
+    b2s = sorted({rand_seq(rng, blen) for _ in range(rng.randint(2, 40))})
+    specimens = [("S%03d" % i, "P0", rng.choice(b1s), "F0", rng.choice(b2s), "R0") for i in range(25)]
+    specimens = list({(s[2], s[4]): s for s in specimens}.values())
+    reads = []
+    for r in range(50):
+        sp = rng.choice(specimens)
+        s = (rand_seq(rng, rng.randint(0, 20)) + sp[2] + primers[0][1] + rand_seq(rng, rng.randint(30, 200)) +
+             reverse_complement(primers[1][1]) + reverse_complement(sp[4]) + rand_seq(rng, rng.randint(0, 20)))
+        s = mutate(rng, s, rng.choice([0.05, 0.15, 0.3]))
+        if rng.random() < 0.5:
+            s = reverse_complement(s)
+        if rng.random() < 0.1:
+            s = s[:40] + "N" + s[41:]
+        reads.append(("k%04d" % r, s, "I" * len(s)))
+    flags = dict(search_len=rng.choice([80, 120]), trim=rng.choice(["barcodes", "tails"]), dereplicate=rng.choice(["best", "none"]),
+                 disable_preorient=False, disable_prefilter=rng.random() < 0.5)
+    return primers, specimens, reads, rng.choice([9, 10, 11, 12]), flags
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_barcode_threshold_beyond_eight(seed):
+    run_case(*make_large_k_case(seed), tag="large k seed %d" % seed)
+
+
 def test_long_primer_carry_lookahead():
     """The kernel's one-addition carry-lookahead over the words of every segment of a warp
     (long_carry_in<SW>) against a rippled carry chain, 2M random generate/propagate masks per width."""
