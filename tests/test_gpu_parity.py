@@ -246,6 +246,20 @@ def test_cuda_long_primers_match_live_oracle(seed):
     run_case(*make_case(seed, long_primers=True), tag="long seed %d" % seed, binding="cuda")
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_cuda_iupac_barcodes_with_prefilter(seed):
+    """Barcodes holding IUPAC codes with the Bloom prefilter on (exact per-barcode emulation), through the CUDA library."""
+    from test_random_tables_hostsim import make_iupac_barcode_case, run_case
+    run_case(*make_iupac_barcode_case(seed), tag="iupac barcode seed %d" % seed, binding="cuda")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_cuda_barcode_threshold_beyond_eight(seed):
+    """Barcode thresholds 9..12 on 24-30 nt barcodes (general band walk), through the CUDA library."""
+    from test_random_tables_hostsim import make_large_k_case, run_case
+    run_case(*make_large_k_case(seed), tag="large k seed %d" % seed, binding="cuda")
+
+
 @pytest.mark.parametrize("cfg,n", [("ont037", 300_000), ("dense", 150_000), ("multipool", 140_000)])
 def test_resident_sub_batches_equal_one_lane(cfg, n):
     """upload / run_resident / download with the batch cut into concurrent sub-batches (2, 3, 5 lanes)
