@@ -23,7 +23,8 @@ extern "C" {
 
 #define SMX_ABI_VERSION 3
 
-#define SMX_MAX_PRIMERS 64      /* canonical primers (distinct sequences)                         */
+#define SMX_MAX_PRIMERS 254     /* canonical primers (distinct sequences); 0xFF = "unknown" in smx_record16 */
+#define SMX_MAX_PAIRS 4096      /* primer pairs (candidate enumeration order)                     */
 #define SMX_MAX_PATTERN 64      /* primer / barcode length handled by the single-thread kernels   */
 #define SMX_MAX_LONG_PATTERN 1024 /* primer length handled by the warp-cooperative multi-word kernel */
 #define SMX_MAX_SEARCH_LEN 1024 /* --search-len                                                   */
@@ -87,7 +88,8 @@ typedef struct smx_tables {
     const int32_t *pair_pool;      /* get_pool_from_primers(fwd, rev), demultiplex.py:640-665; -1 = none */
 
     /* specimen rows in file order (databases.py:167).  p1_mask / p2_mask: bit c set iff canonical
-     * primer c is (by identity) one of the row's resolved primers (databases.py:224-225,241; Q7).  */
+     * primer c is (by identity) one of the row's resolved primers (databases.py:224-225,241; Q7);
+     * ceil(n_primers / 64) words per row, row r at [r * words, (r + 1) * words), bit c in word c / 64. */
     uint32_t n_specimens;
     const uint32_t *spec_b1;
     const uint32_t *spec_b2;

@@ -29,7 +29,7 @@ typedef int32_t i32;
 
 constexpr int kSymOther = 15;       // read symbol that matches nothing (lower case, unknown bytes)
 constexpr int kNone = INT32_MIN;    // Python None in coordinates
-constexpr int kMaxPairs = 64;       // candidate slots per read = 2 * pairs
+constexpr int kMaxPairs = SMX_MAX_PAIRS;   // candidate slots per read = 2 * pairs
 constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in the first pass
 constexpr int kBigGroups = 4096;
 constexpr int kMaxTaskWords = 4;    // bwords one stage-2 thread evaluates side by side
@@ -234,7 +234,8 @@ struct Tables {
     const u64 *spec_key;     // sorted unique (b1 << 32 | b2)
     const u32 *spec_key_off; // n_keys+1 -> rows of that key in file order
     const u32 *spec_row;     // row indices
-    const u64 *spec_p1_mask, *spec_p2_mask;   // by row
+    const u64 *spec_p1_mask, *spec_p2_mask;   // by row, pmask_words words each (bit c of word c / 64 = canonical primer c)
+    int pmask_words;
     const i32 *spec_pool;    // by row
 };
 
@@ -399,13 +400,19 @@ SMX_HD int spec_find_key(const Tables &t, u32 b1, u32 b2) {
     return -1;
 }
 
+// Row `row` lists canonical primers p1 / p2 among its resolved primers (identity test, databases.py:224-225,241).
+SMX_HD bool spec_row_has(const Tables &t, u32 row, int p1, int p2) {
+    const u64 w1 = t.spec_p1_mask[(u64)row * t.pmask_words + (p1 >> 6)], w2 = t.spec_p2_mask[(u64)row * t.pmask_words + (p2 >> 6)];
+    return ((w1 >> (p1 & 63)) & 1) && ((w2 >> (p2 & 63)) & 1);
+}
+
 // First specimen row (file order) with exactly (b1, b2, p1, p2); -1 if none.  specimen_for_exact_match.
 SMX_HD int spec_exact(const Tables &t, u32 b1, u32 b2, int p1, int p2) {
     int k = spec_find_key(t, b1, b2);
     if (k < 0) return -1;
     for (u32 i = t.spec_key_off[k]; i < t.spec_key_off[k + 1]; ++i) {
         u32 row = t.spec_row[i];
-        if (((t.spec_p1_mask[row] >> p1) & 1) && ((t.spec_p2_mask[row] >> p2) & 1)) return (int)row;
+        if (spec_row_has(t, row, p1, p2)) return (int)row;
     }
     return -1;
 }
@@ -416,7 +423,7 @@ SMX_HD void spec_all(const Tables &t, u32 b1, u32 b2, int p1, int p2, int &count
     if (k < 0) return;
     for (u32 i = t.spec_key_off[k]; i < t.spec_key_off[k + 1]; ++i) {
         u32 row = t.spec_row[i];
-        if (((t.spec_p1_mask[row] >> p1) & 1) && ((t.spec_p2_mask[row] >> p2) & 1)) {
+        if (spec_row_has(t, row, p1, p2)) {
             ++count;
             if (min_row < 0 || (int)row < min_row) min_row = (int)row;
         }

@@ -253,7 +253,8 @@ struct HostTables {
         if (bt_eq.empty()) bt_eq.push_back(0);
         if (bt_g0.empty()) { bt_g0.push_back(0); bt_nw.push_back(0); bt_row.push_back(0); }
         if (bt_class_tasks.empty()) bt_class_tasks.push_back(0);
-        if (tb->pb_off[nP] - tb->pb_off[0] > 65535) return err("more than 65535 barcodes for one primer");
+        for (int p = 0; p < nP; ++p)
+            if (tb->pb_off[p + 1] - tb->pb_off[p] > 65535) return err("primer %d has more than 65535 barcodes", p);
 
         u32 run = 0;
         for (int s = 0; s < 2; ++s)
@@ -286,8 +287,10 @@ struct HostTables {
                 spec_dense[(size_t)(spec_key[i] >> 32) * tb->n_b2 + (u32)spec_key[i]] = (i32)i;
         }
         t.spec_dense = spec_dense.empty() ? nullptr : spec_dense.data();
-        spec_p1.assign(tb->spec_p1_mask, tb->spec_p1_mask + tb->n_specimens);
-        spec_p2.assign(tb->spec_p2_mask, tb->spec_p2_mask + tb->n_specimens);
+        t.pmask_words = (nP + 63) / 64;
+        spec_p1.assign(tb->spec_p1_mask, tb->spec_p1_mask + (size_t)tb->n_specimens * t.pmask_words);
+        spec_p2.assign(tb->spec_p2_mask, tb->spec_p2_mask + (size_t)tb->n_specimens * t.pmask_words);
+        if (spec_p1.empty()) { spec_p1.push_back(0); spec_p2.push_back(0); }
         spec_pool.assign(tb->spec_pool, tb->spec_pool + tb->n_specimens);
         for (u32 i = 0; i < tb->n_specimens; ++i)
             if (tb->spec_pool[i] < -1 || tb->spec_pool[i] > 32767) return err("specimen pool id out of range");

@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256) k_int_peak(u32 *out, int iters, u32 seed)
 cudaError_t launch_select_fast(const Tables &t, const Batch &b, cudaStream_t st) {
     const unsigned blocks = (b.n_reads + 127) / 128;
     if (t.n_primers <= 8) k_select_fast<8><<<blocks, 128, 0, st>>>(t, b);
+    else if (t.n_primers <= 64) k_select_fast<64><<<blocks, 128, 0, st>>>(t, b);
     else k_select_fast<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
     return cudaGetLastError();
 }
@@ -335,6 +336,7 @@ cudaError_t launch_select_fast(const Tables &t, const Batch &b, cudaStream_t st)
 cudaError_t launch_select(const Tables &t, const Batch &b, cudaStream_t st) {
     const unsigned blocks = (b.n_reads + 127) / 128;
     if (t.n_primers <= 8) k_select<8><<<blocks, 128, 0, st>>>(t, b);
+    else if (t.n_primers <= 64) k_select<64><<<blocks, 128, 0, st>>>(t, b);
     else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
     return cudaGetLastError();
 }

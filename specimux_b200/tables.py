@@ -82,13 +82,15 @@ class MatchTables:
         self.specimen_ids = [r[0] for r in rows]
         self.specimen_pools = [r[1] for r in rows]
 
+        mask_words = (len(primers) + 63) // 64
+
         def mask(plist):
-            m = 0
+            words = [0] * mask_words
             for p in plist:
                 i = index.get(id(p))
                 if i is not None:
-                    m |= 1 << i
-            return m
+                    words[i >> 6] |= 1 << (i & 63)
+            return words
 
         # keep every array alive for the lifetime of the object (ctypes only borrows pointers)
         k = self._keep = {}
@@ -106,8 +108,8 @@ class MatchTables:
         k["pair_pool"] = np.array([p[2] for p in pairs] or [0], dtype=np.int32)
         k["spec_b1"] = np.array([b1_id[r[2].upper()] if r[2].upper() in b1_id else b1_id[r[2]] for r in rows], dtype=np.uint32)
         k["spec_b2"] = np.array([b2_id[r[4].upper()] if r[4].upper() in b2_id else b2_id[r[4]] for r in rows], dtype=np.uint32)
-        k["spec_p1"] = np.array([mask(r[3]) for r in rows], dtype=np.uint64)
-        k["spec_p2"] = np.array([mask(r[5]) for r in rows], dtype=np.uint64)
+        k["spec_p1"] = np.array([mask(r[3]) for r in rows] or [[0] * mask_words], dtype=np.uint64).reshape(-1)
+        k["spec_p2"] = np.array([mask(r[5]) for r in rows] or [[0] * mask_words], dtype=np.uint64).reshape(-1)
         k["spec_pool"] = np.array([pid(r[1]) for r in rows], dtype=np.int32)
 
         t = _lib.SmxTables()

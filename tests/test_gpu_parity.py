@@ -260,6 +260,13 @@ def test_cuda_barcode_threshold_beyond_eight(seed):
     run_case(*make_large_k_case(seed), tag="large k seed %d" % seed, binding="cuda")
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_cuda_two_hundred_primers_three_hundred_pairs(seed):
+    """200 canonical primers, 300 pairs, an N barcode with the prefilter on, through the CUDA library."""
+    from test_random_tables_hostsim import make_many_primers_case, run_case
+    run_case(*make_many_primers_case(seed), tag="many primers seed %d" % seed, binding="cuda")
+
+
 @pytest.mark.parametrize("cfg,n", [("ont037", 300_000), ("dense", 150_000), ("multipool", 140_000)])
 def test_resident_sub_batches_equal_one_lane(cfg, n):
     """upload / run_resident / download with the batch cut into concurrent sub-batches (2, 3, 5 lanes)

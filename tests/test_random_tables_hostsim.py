@@ -209,6 +209,52 @@ def test_barcode_threshold_beyond_eight(seed):
     run_case(*make_large_k_case(seed), tag="large k seed %d" % seed)
 
 
+def make_many_primers_case(seed, n_fwd=100, n_rev=100, n_pairs=300):
+    """200 canonical primers in 300 primer pairs (the reference is unbounded, databases.py:247-264): multi-word
+    primer-identity masks, the 254-primer selection instantiation, one sliced launch per primer; one barcode holds N."""
+    rng = random.Random(11000 + seed)
+    pools = ["PA", "PB", "PC"]
+    seqs = set()
+    while len(seqs) < n_fwd + n_rev:
+        seqs.add(rand_seq(rng, rng.randint(18, 24)))
+    seqs = sorted(seqs, key=lambda _: rng.random())
+    primers = []
+    for i, sq in enumerate(seqs):
+        pool = pools[i % 3]
+        primers.append(("F%03d" % i if i < n_fwd else "R%03d" % i, sq, "forward" if i < n_fwd else "reverse", [pool]))
+    b1s = [rand_seq(rng, 13) for _ in range(12)]
+    b2s = [rand_seq(rng, 13) for _ in range(24)]
+    b1s[3] = b1s[3][:5] + "N" + b1s[3][6:]
+    specimens, seen = [], set()
+    while len(seen) < n_pairs:
+        pool = rng.choice(pools)
+        f = rng.choice([p for p in primers if p[2] == "forward" and p[3] == [pool]])
+        r = rng.choice([p for p in primers if p[2] == "reverse" and p[3] == [pool]])
+        if (f[0], r[0]) in seen:
+            continue
+        seen.add((f[0], r[0]))
+        specimens.append(("S%04d" % len(specimens), pool, rng.choice(b1s), f[0], rng.choice(b2s), r[0]))
+    by_name = {p[0]: p for p in primers}
+    reads = []
+    for r in range(60):
+        sp = rng.choice(specimens)
+        b1 = sp[2].replace("N", rng.choice("ACGTN"))
+        s = (rand_seq(rng, rng.randint(0, 20)) + b1 + by_name[sp[3]][1] + rand_seq(rng, rng.randint(30, 150)) +
+             reverse_complement(by_name[sp[5]][1]) + reverse_complement(sp[4]) + rand_seq(rng, rng.randint(0, 20)))
+        s = mutate(rng, s, rng.choice([0.0, 0.04, 0.08]))
+        if rng.random() < 0.5:
+            s = reverse_complement(s)
+        reads.append(("m%04d" % r, s, "I" * len(s)))
+    flags = dict(search_len=80, trim="barcodes", dereplicate=rng.choice(["best", "none"]), disable_preorient=rng.random() < 0.5,
+                 disable_prefilter=False)
+    return primers, specimens, reads, 3, flags
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_two_hundred_primers_three_hundred_pairs(seed):
+    run_case(*make_many_primers_case(seed), tag="many primers seed %d" % seed)
+
+
 def test_long_primer_carry_lookahead():
     """The kernel's one-addition carry-lookahead over the words of every segment of a warp
     (long_carry_in<SW>) against a rippled carry chain, 2M random generate/propagate masks per width."""
