@@ -169,7 +169,7 @@ struct smx_ctx {
     int last_chunks = 0;
     bool trace = false;
     bool tiny_caps = false;                 // SMX_TEST_TINY_CAPS=1: see lane_upload
-    bool overlap_start = true;              // start recovery beside the barcode search (SMX_OVERLAP_START=0 disables)
+    bool start_sliced = true;               // bit-sliced start recovery kernel (SMX_START_SLICED=0: single-word form only)
     bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
     // pipelined smx_match_batch chunking (SMX_PIPELINE_RAMP): 0 = even split (default); 1 = two extra small
     // chunks first (measured 1.83 vs 1.76 ms on config 2: the extra chunks cost more kernel-chain latency than
@@ -368,6 +368,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
     const int nP = t.n_primers;
     cudaStream_t st = ln.stream;
 #define KMARK(i) do { if (timed) CU(cudaEventRecord(ln.kev[i], st)); } while (0)
+    bool start_forked = false;
     (void)n;
     if (from <= 0) {
         CU(cudaMemsetAsync(ln.counters.p, 0, kCtlWords * sizeof(unsigned long long), st));     // the only memset of a fresh run
@@ -399,7 +400,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
                 }
         }
         KMARK(2);
-        CU(launch_primer_finish(t, b, true, st));
+        CU(launch_primer_finish(t, b, c->start_sliced ? 1 : 2, st));
         for (int p = 0; p < nP; ++p) {
             if (!t.p_sw[p]) continue;
             // long primer: warp-cooperative multi-word search, p_sw lanes per read
@@ -408,6 +409,25 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         }
         KMARK(3);
         ++ln.launches;
+        // start of the first location, bit-sliced across work entries: independent of the barcode search (selection
+        // needs both), so outside timed one-lane runs it goes to an auxiliary stream beside stage 2
+        if (c->start_sliced) {
+            cudaStream_t ss = st;
+            bool any = false;
+            for (int p = 0; p < nP; ++p) any |= start_sliced_ok(t, p);
+            if (any && !timed) {
+                ss = ln.aux[0];
+                CU(cudaEventRecord(ln.ev_fork, st));
+                CU(cudaStreamWaitEvent(ss, ln.ev_fork, 0));
+                start_forked = true;
+            }
+            for (int p = 0; p < nP; ++p) {
+                if (!start_sliced_ok(t, p)) continue;
+                CU(launch_primer_start_sliced(t, b, p, c->prow_code.data() + (size_t)p * 32, ss));
+                ++ln.launches;
+            }
+            if (start_forked) CU(cudaEventRecord(ln.ev_join[0], ss));
+        }
     }
     if (from <= 2) {   // stage 2
         if (from == 2) {                                                                                     // re-run
@@ -421,6 +441,7 @@ static int lane_enqueue(smx_ctx *c, Lane &ln, int from, bool timed) {
         if (t.n_btasks) CU(launch_barcode_tasks(t, b, c->bt_class_tasks.p, c->bt_classes.data(), (int)c->bt_classes.size(), st, &ln.launches));
     }
     CU(cudaEventRecord(ln.ev_dp_done, st));
+    if (start_forked) CU(cudaStreamWaitEvent(st, ln.ev_join[0], 0));
     // stage 3: slot digests, single-pass selection, scan
     if (from >= 2) {                                                                                           // re-run
         CU(cudaMemsetAsync(ln.counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
@@ -688,7 +709,7 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     if (const char *env = getenv("SMX_PRIMER_SLICED")) if (atoi(env) == 0) c->t.sliced = 0;     // A/B switch: classic stage 1
     if (const char *env = getenv("SMX_PIPELINE_PRIORITIES")) c->lane_priorities = atoi(env) != 0;
     if (const char *env = getenv("SMX_TEST_TINY_CAPS")) c->tiny_caps = atoi(env) != 0;
-    if (const char *env = getenv("SMX_OVERLAP_START")) c->overlap_start = atoi(env) != 0;
+    if (const char *env = getenv("SMX_START_SLICED")) c->start_sliced = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_RAMP")) c->ramp = atoi(env);
     if (const char *env = getenv("SMX_PIPELINE_CHAIN")) c->chain = atoi(env) != 0;
     if (const char *env = getenv("SMX_PIPELINE_TRACE")) c->trace = atoi(env) != 0;

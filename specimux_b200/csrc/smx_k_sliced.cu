@@ -23,6 +23,41 @@ __global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int p
 }
 
 
+// Start recovery, bit-sliced across work entries: one thread per (32 consecutive entries of a slot) for one primer.
+template <int M>
+__global__ void __launch_bounds__(kSlicedBlock) k_primer_start_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
+    __shared__ u32 s_planes[(kSlicedCodes + kStartPlanes) * kSlicedBlock];
+    const u32 slot = blockIdx.y * c_tables.n_primers + primer;
+    u32 cnt = b.slot_count[slot];
+    if (cnt > b.e_cap) cnt = b.e_cap;
+    const u32 e0 = (blockIdx.x * kSlicedBlock + threadIdx.x) * 32u;
+    if (e0 >= cnt) return;
+    primer_start_sliced_thread<M, kSlicedBlock>(c_tables, b, slot, e0, cnt, ro, degenerate != 0, s_planes + threadIdx.x,
+                                                s_planes + kSlicedCodes * kSlicedBlock + threadIdx.x);
+}
+
+cudaError_t launch_primer_start_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st) {
+    const int m = t.p_len[primer];
+    dim3 sgrid((b.e_cap / 32 + kSlicedBlock) / kSlicedBlock, 2);
+    RowOffsets ro;
+    bool degenerate = false;
+    for (int i = 0; i < 32; ++i) {                      // rows of the REVERSED primer_rc
+        int code = i < m ? prow_code[m - 1 - i] : 0;
+        degenerate |= code > 3;
+        ro.off[i] = (unsigned short)(code * kSlicedBlock * sizeof(u32));
+    }
+    switch (m) {
+#define SMX_M(MM) case MM: k_primer_start_sliced<MM><<<sgrid, kSlicedBlock, 0, st>>>(t, b, primer, ro, degenerate ? 1 : 0); break;
+        SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
+        SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
+        SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
+        SMX_M(32)
+#undef SMX_M
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_primer_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st) {
     dim3 sgrid((b.n_pad / 32 + kSlicedBlock - 1) / kSlicedBlock, 2);
     RowOffsets ro;

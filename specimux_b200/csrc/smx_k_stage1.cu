@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(kFinishBlock) k_primer_finish(SMX_KARGS, int w
         if (nloc[s])
             write_entries(t, b, (u32)(s * t.n_primers + primer), read,
                           s_wtot[s][kFinishBlock / 32] + s_wtot[s][warp] + (u32)(incl[s] - nloc[s]), have_ev[s] ? ev[s] : nullptr);
-    if (with_start && (nloc[0] | nloc[1])) {
+    // start of the first location, single-word form: every matched slot when with_start == 2, else only what the
+    // sliced start kernel leaves out (reads on the 4-bit side stream; primers with m + k > 32)
+    if (with_start && (nloc[0] | nloc[1]) &&
+        (with_start == 2 || !start_sliced_ok(t, primer) || read_is_flagged(b, read))) {
         const Geo g = make_geo((int)b.lengths[read], t.L);
         const int s1 = nloc[0] ? 0 : 1;                 // the strand that matched (per lane: the warp stays converged)
         {
@@ -295,10 +298,10 @@ cudaError_t launch_stage_windows(const Tables &t, const Batch &b, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_primer_finish(const Tables &t, const Batch &b, bool with_start, cudaStream_t st) {
+cudaError_t launch_primer_finish(const Tables &t, const Batch &b, int with_start, cudaStream_t st) {
     dim3 grid((b.n_reads + kFinishBlock - 1) / kFinishBlock, t.n_primers);
-    if (t.use64) k_primer_finish<u64><<<grid, kFinishBlock, 0, st>>>(t, b, with_start ? 1 : 0);
-    else k_primer_finish<u32><<<grid, kFinishBlock, 0, st>>>(t, b, with_start ? 1 : 0);
+    if (t.use64) k_primer_finish<u64><<<grid, kFinishBlock, 0, st>>>(t, b, with_start);
+    else k_primer_finish<u32><<<grid, kFinishBlock, 0, st>>>(t, b, with_start);
     return cudaGetLastError();
 }
 

@@ -285,6 +285,9 @@ SMX_HD int primer_search_thread(const Tables &t, const Batch &b, u32 read, int s
 // transpose turns them into a per-read word of interleaved (equal, improved) bits.  The running
 // best itself is never materialised: best = m - (number of improvements).
 
+// Bit-sliced full adder carry / majority on planes.
+SMX_HD u32 maj3(u32 a, u32 b, u32 c) { return (a & b) | (a & c) | (b & c); }
+
 // In-register 32x32 bit-matrix transpose: afterwards bit r of a[c] is the former bit c of a[r].
 SMX_HD void transpose32(u32 (&a)[32]) {
 #if defined(__CUDA_ARCH__)
@@ -588,6 +591,167 @@ SMX_HD void primer_start_thread(const Tables &t, const Batch &b, u32 slot, u32 e
 }
 
 // ---------------------------------------------------------------------------------------------
+// Start recovery, sliced form: the reverse SHW pass of 32 work entries at once (bit r of every word = entry
+// e0 + r of one slot), the same bit-sliced cell as the forward search.  Per entry the up to 32 window symbols that
+// end at its first equal-best end are cut out in REVERSE order (symbol first - j in column j), the 32 entries'
+// words are transposed into code-bit planes, the m x (m + k) cells are evaluated (5 LOP3 per cell for 32 entries),
+// the score of the last row is tracked on six bit-planes and compared with the entries' best distances, and one
+// more transpose turns the per-column "score == best" planes into a word per entry whose top set bit is the
+// number of columns walked back (edlib: the LAST equal-best reverse end = the longest alignment).  ~250 thread
+// instructions per entry against ~1,070 for the single-word form (profiles/r2_c_*), which stays in charge of
+// reads on the 4-bit side stream and of primers with m + k > 32.
+
+SMX_HD bool start_sliced_ok(const Tables &t, int primer) {
+    return t.sliced && !t.p_sw[primer] && (int)t.p_len[primer] + (int)t.p_k[primer] <= 32;
+}
+
+// 16 consecutive 2-bit symbols starting at staged position p0 (may be negative: symbols before the window read 0)
+SMX_HD u32 win2_extract16(const u32 *win2, u64 stride, int nw2, int p0) {
+    const int idx = p0 >> 4, sh = 2 * (p0 & 15);              // arithmetic shift: floor for negative p0
+    const u32 lo = (idx >= 0 && idx < nw2) ? win2[(u64)idx * stride] : 0u;
+    const u32 hi = (idx + 1 >= 0 && idx + 1 < nw2) ? win2[(u64)(idx + 1) * stride] : 0u;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+
+// the 16 two-bit groups of a word in reverse order
+SMX_HD u32 reverse_pairs16(u32 v) {
+    v = bit_reverse32(v);
+    return ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);
+}
+
+constexpr int kStartPlanes = 104;       // per-thread plane buffer of primer_start_sliced_thread (words)
+
+// sp: kSlicedCodes code planes, sa: kStartPlanes words (element stride STRIDE).  ro: byte offsets of the Eq plane
+// of every row of the REVERSED primer_rc.  e0: first of the thread's 32 entries of `slot`; n_entries: entries of
+// the slot.
+template <int M, int STRIDE>
+SMX_HD void primer_start_sliced_thread(const Tables &t, const Batch &b, u32 slot, u32 e0, u32 n_entries,
+                                       const RowOffsets &ro, bool degenerate, u32 *sp, u32 *sa) {
+    const int strand = (int)slot / t.n_primers, primer = (int)slot % t.n_primers;
+    const int ncols = (int)t.p_len[primer] + (int)t.p_k[primer];       // <= 32 (start_sliced_ok)
+    u32 *XH = sa, *XL = sa + 32 * STRIDE, *ACT = sa + 64 * STRIDE, *BP = sa + 96 * STRIDE;
+    u32 a[32];
+    // ---- per entry: reversed window words, active-column mask, best distance
+    u32 bestw[32];
+    for (int r = 0; r < 32; ++r) {
+        const u32 e = e0 + (u32)r;
+        u32 xh = 0, xl = 0, act = 0, best = 63;
+        if (e < n_entries) {
+            const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
+            const u64 hit_idx = (u64)slot * b.n_pad + read;
+            if (b.ent_base[hit_idx] == e && !read_is_flagged(b, read)) {     // first location of its read, 2-bit window
+                const smx_primer_hit h = b.phit[hit_idx];
+                const Geo g = make_geo((int)b.lengths[read], t.L);
+                const int first = h.first_end - g.woff - g.delta;
+                int cols = first - g.start + 1;
+                const int lim = M + (int)h.distance;
+                if (cols > lim) cols = lim;
+                const u32 *w2 = b.win2 + (u64)strand * t.nw2 * b.n_pad + read;
+                xh = reverse_pairs16(win2_extract16(w2, b.n_pad, t.nw2, first - 15));
+                xl = reverse_pairs16(win2_extract16(w2, b.n_pad, t.nw2, first - 31));
+                act = cols >= 32 ? ~0u : ((1u << cols) - 1u);
+                best = (u32)h.distance;
+            }
+        }
+        XH[r * STRIDE] = xh; XL[r * STRIDE] = xl; ACT[r * STRIDE] = act;
+        bestw[r] = best;
+    }
+    // ---- entries x bits -> bit planes x entries (four transposes; the best distances need six planes)
+    for (int which = 0; which < 3; ++which) {
+        u32 *buf = which == 0 ? XH : which == 1 ? XL : ACT;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 32; ++r) a[r] = buf[r * STRIDE];
+        transpose32(a);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 32; ++r) buf[r * STRIDE] = a[r];
+    }
+    {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 32; ++r) a[r] = bestw[r];
+        transpose32(a);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 6; ++l) BP[l * STRIDE] = a[l];
+    }
+    // ---- the reverse SHW pass (D[0][j] = j, D[i][0] = i), score of row m on six planes
+    u32 VP[M], VM[M];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < M; ++i) { VP[i] = ~0u; VM[i] = 0u; }
+    u32 sc[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int l = 0; l < 6; ++l) sc[l] = (M >> l) & 1 ? ~0u : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int c = 0; c < ncols; ++c) {
+        const u32 *X = c < 16 ? XH : XL;
+        const u32 b0 = X[(2 * (c & 15)) * STRIDE], b1 = X[(2 * (c & 15) + 1) * STRIDE];
+        sp[0 * STRIDE] = ~(b0 | b1);            // A
+        sp[1 * STRIDE] = b0 & ~b1;              // C
+        sp[2 * STRIDE] = b1 & ~b0;              // G
+        sp[3 * STRIDE] = b0 & b1;               // T
+        if (degenerate) {                       // IUPAC base sets (constants.py:13-20)
+            sp[4 * STRIDE] = ~b0; sp[5 * STRIDE] = b0; sp[6 * STRIDE] = b0 ^ b1; sp[7 * STRIDE] = ~(b0 ^ b1);
+            sp[8 * STRIDE] = b1; sp[9 * STRIDE] = ~b1; sp[10 * STRIDE] = b0 | b1; sp[11 * STRIDE] = ~(b0 & ~b1);
+            sp[12 * STRIDE] = ~(b1 & ~b0); sp[13 * STRIDE] = ~(b0 & b1); sp[14 * STRIDE] = ~0u;
+        }
+        u32 Ph = ~0u, Mh = 0u;                  // row 0: D[0][j] = j (SHW)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < M; ++i) {
+            const u32 Eq = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(sp) + ro.off[i]);
+            const u32 Pv = VP[i], Mv = VM[i];
+            const u32 X3 = Eq | Mv | Mh;
+            VP[i] = Mh | ~(X3 | Ph);
+            VM[i] = Ph & X3;
+            const u32 nPh = Mv | ~(X3 | Pv);
+            Mh = Pv & X3;
+            Ph = nPh;
+        }
+        // score += Ph - Mh in one ripple (+1 as the carry-in, -1 as an all-ones addend); equal to the entry's best?
+        u32 carry = Ph, diff = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int l = 0; l < 6; ++l) {
+            const u32 v = sc[l];
+            sc[l] = v ^ Mh ^ carry;
+            carry = maj3(v, Mh, carry);
+            diff |= sc[l] ^ BP[l * STRIDE];
+        }
+        // the consumed input planes of column c make room for its result (slot c <= 2c)
+        const u32 eq = ~diff & ACT[c * STRIDE];
+        if (c < 16) XH[c * STRIDE] = eq; else XL[(c - 16) * STRIDE] = eq;
+    }
+    // ---- per-column planes -> a word per entry: the top set bit is the last column whose score equals the best
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 32; ++c) a[c] = c < ncols ? (c < 16 ? XH[c * STRIDE] : XL[(c - 16) * STRIDE]) : 0u;
+    transpose32(a);
+    for (int r = 0; r < 32; ++r) {
+        if (bestw[r] == 63) continue;
+        const u32 e = e0 + (u32)r;
+        const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
+        smx_primer_hit &h = b.phit[(u64)slot * b.n_pad + read];
+        const int last = a[r] ? 31 - count_leading_zeros32(a[r]) : M - 1;
+        h.first_start = h.first_end - last;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage 2.  match_one_end's barcode loop (demultiplex.py:781-815): for one matched (read, strand,
 // primer) slot and one bword (<= 32 barcodes of one length), the SHW distance of every barcode at
 // every equal-best primer end; strictly-smallest distance over the ends wins (first end on ties).
@@ -699,9 +863,6 @@ template <int S> SMX_HD void load_eq(const u32 *p, u32 (&eq)[S]) {
     for (int q = 0; q < S; ++q) eq[q] = p[q];
 #endif
 }
-
-// Bit-sliced full adder / majority on planes.
-SMX_HD u32 maj3(u32 a, u32 b, u32 c) { return (a & b) | (a & c) | (b & c); }
 
 // Result of the small form for one bword: D[m][m-K] as five bit-planes (values <= 16 there), and the horizontal
 // deltas of row m to its right.

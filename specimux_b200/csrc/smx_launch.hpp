@@ -13,8 +13,11 @@ constexpr int kScanTile = 1024;         // reads per tile of k_scan_compact (siz
 cudaError_t launch_stage_windows(const Tables &t, const Batch &b, cudaStream_t st);
 // prow_code: the primer's 32 pattern-row IUPAC codes (HostTables::prow_code + 32 * primer)
 cudaError_t launch_primer_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st);
-// finish of both strands per (read, primer) + work entries + (with_start) start of the first location
-cudaError_t launch_primer_finish(const Tables &t, const Batch &b, bool with_start, cudaStream_t st);
+// finish of both strands per (read, primer) + work entries + start of the first location in the single-word form:
+// with_start 0 = none, 1 = only what launch_primer_start_sliced leaves out, 2 = every matched slot
+cudaError_t launch_primer_finish(const Tables &t, const Batch &b, int with_start, cudaStream_t st);
+// start of the first location, bit-sliced across 32 work entries (primers with start_sliced_ok); prow_code as above
+cudaError_t launch_primer_start_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st);
 cudaError_t launch_primer_long(const Tables &t, const Batch &b, int primer, cudaStream_t st);
 // stage 2: one launch per (task width, barcode length) class; class_tasks is the DEVICE copy of
 // HostTables::bt_class_tasks.  *launches receives the number of kernels enqueued.

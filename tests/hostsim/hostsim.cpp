@@ -216,12 +216,38 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         u32 max_entries = 0;
         for (u32 v : slot_count) max_entries = std::max(max_entries, v);
         if (max_entries > e_cap) { e_cap = max_entries; continue; }
-        for (u32 slot = 0; slot < (u32)(2 * nP); ++slot)
+        for (u32 slot = 0; slot < (u32)(2 * nP); ++slot) {
+            const int p = (int)(slot % nP);
+            if (t.p_sw[p]) continue;                 // long primer: start already recovered
+            const u64 *rev = t.peq_rcrev + (size_t)p * 16;
+            const bool sliced_start = start_sliced_ok(t, p);
+            // what k_primer_finish keeps of the single-word form: every slot of a primer without the sliced start,
+            // otherwise only the reads on the 4-bit side stream
             for (u32 e = 0; e < slot_count[slot]; ++e) {
-                if (t.p_sw[slot % nP]) break;        // long primer: start already recovered
-                const u64 *rev = t.peq_rcrev + (size_t)(slot % nP) * 16;
+                if (sliced_start && !read_is_flagged(b, ent_read[(size_t)slot * e_cap + e])) continue;
                 if (t.use64) primer_start_thread<u64>(t, b, slot, e, rev); else primer_start_thread<u32>(t, b, slot, e, rev);
             }
+            if (!sliced_start) continue;
+            RowOffsets ro;
+            bool degenerate = false;
+            const int m = t.p_len[p];
+            for (int i = 0; i < 32; ++i) {
+                int code = i < m ? ht.prow_code[(size_t)p * 32 + (m - 1 - i)] : 0;
+                degenerate |= code > 3;
+                ro.off[i] = (unsigned short)(code * sizeof(u32));
+            }
+            u32 scratch[kSlicedCodes], planes[kStartPlanes];
+            for (u32 e0 = 0; e0 < slot_count[slot]; e0 += 32)
+                switch (m) {
+#define SMX_M(MM) case MM: primer_start_sliced_thread<MM, 1>(t, b, slot, e0, slot_count[slot], ro, degenerate, scratch, planes); break;
+                    SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
+                    SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
+                    SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
+                    SMX_M(32)
+#undef SMX_M
+                    default: snprintf(g_err, sizeof(g_err), "sliced start: primer length"); return SMX_ERR_INTERNAL;
+                }
+        }
         bdig.assign((size_t)2 * t.n_btasks * e_cap + 1, BarcodeDigest());
         b.bdig = bdig.data();
         for (int s = 0; s < 2; ++s)
