@@ -147,7 +147,8 @@ struct smx_ctx {
     DevBuf<u32> pb_barcode, pair_fwd, pair_rev, spec_key_off, spec_row, bw_row, bw_valid, beq, peq_long;
     DevBuf<unsigned short> bw_list, bt_g0, bt_class_tasks;
     DevBuf<unsigned char> bt_nw;
-    DevBuf<u32> bt_row, bt_eq;
+    DevBuf<u32> bt_row, bt_eq, bt_quad;
+    DevBuf<i32> bt_quad_row;
     std::vector<BtClass> bt_classes;
     DevBuf<i32> pair_pool, spec_pool, spec_dense;
     int max_nb = 0;
@@ -634,7 +635,7 @@ void smx_destroy(smx_ctx *c) {
     c->spec_row.release(); c->pair_pool.release(); c->spec_pool.release(); c->spec_dense.release();
     c->shared_packed4.release(); c->l2_scratch.release(); c->peq_long.release();
     c->bt_g0.release(); c->bt_nw.release(); c->bt_row.release(); c->bt_eq.release(); c->bt_class_tasks.release();
-    c->b_codes.release(); c->b_code_off.release(); c->bw_iupac.release();
+    c->b_codes.release(); c->b_code_off.release(); c->bw_iupac.release(); c->bt_quad.release(); c->bt_quad_row.release();
     delete c;
 }
 
@@ -688,6 +689,8 @@ int smx_create(int device, const smx_tables *tb, const smx_params *pr, smx_ctx *
     CUC(upload(c->bt_eq, ht.bt_eq)); CUC(upload(c->bt_class_tasks, ht.bt_class_tasks));
     c->bt_classes = ht.bt_classes;
     ht.set_task_pointers(c->bt_g0.p, c->bt_nw.p, c->bt_row.p, c->bt_eq.p);
+    CUC(upload(c->bt_quad, ht.bt_quad)); CUC(upload(c->bt_quad_row, ht.bt_quad_row));
+    ht.set_quad_pointers(c->bt_quad_row.p, c->bt_quad.p);
     CUC(upload(c->b_codes, ht.b_codes)); CUC(upload(c->b_code_off, ht.b_code_off)); CUC(upload(c->bw_iupac, ht.bw_iupac));
     ht.set_code_pointers(c->b_codes.p, c->b_code_off.p, c->bw_iupac.p);
     ht.set_bword_pointers(c->bw_len.p, c->bw_primer.p, c->bw_row.p, c->bw_valid.p, c->bw_list.p, c->beq.p);

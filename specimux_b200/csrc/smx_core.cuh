@@ -34,6 +34,7 @@ constexpr int kSmallGroups = 16;    // dereplication groups tracked per read in 
 constexpr int kBigGroups = 4096;
 constexpr int kMaxTaskWords = 4;    // bwords one stage-2 thread evaluates side by side
 constexpr int kMaxBarcodeK = 12;     // largest barcode threshold k_idx (the reference derives ceil(min distance / 2))
+constexpr int kQuadSyms = 5, kQuadRow = 625;   // four-entry narrow-word tables: symbols per entry, entries per row (5^4)
 constexpr int kMaxTaskK = 4;        // largest k_idx with multi-word stage-2 tasks (beyond: one bword per task)
 // control block of a batch: kCtrWords 64-bit counters followed by the 2 * SMX_MAX_PRIMERS u32 per-slot entry counts
 constexpr int kCtrDeferred = 8;     // (u32) reads left to the general selection kernel
@@ -225,6 +226,8 @@ struct Tables {
     const unsigned char *bt_nw;        // [task] number of bwords (1..4)
     const u32 *bt_row;                 // [task] word offset of the task's table in bt_eq
     const u32 *bt_eq;                  // per task [row][16 symbols][S], S = 1, 2 or 4 (bt_nw rounded up to a power of two)
+    const i32 *bt_quad_row;            // [task] word offset of the task's four-entry table in bt_quad ([row][625]), -1 = none
+    const u32 *bt_quad;
 
     const u32 *pair_fwd, *pair_rev;
     const i32 *pair_pool;
@@ -253,7 +256,8 @@ struct SlotSum {
 static_assert(sizeof(SlotSum) == 24, "SlotSum layout");
 
 // Stage-2 tasks of one (words per task, barcode length): bt_class_tasks[off .. off + count), one kernel launch.
-struct BtClass { int nw, m; u32 off, count; };
+// quad: narrow single-word tasks (<= 8 barcodes) evaluated four work entries to a word (barcode_quad_thread).
+struct BtClass { int nw, m, quad; u32 off, count; };
 
 // Digest of the barcode hits of one (work entry, stage-2 task), written by the barcode kernel so that the
 // selection stage reads 16 bytes per entry instead of walking the hit sub-lists in the common case.

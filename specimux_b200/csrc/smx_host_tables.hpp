@@ -72,7 +72,8 @@ struct HostTables {
     std::vector<unsigned short> bw_list;
     std::vector<unsigned short> bt_g0, bt_class_tasks;     // stage-2 tasks; task ids grouped by (words per task, barcode length)
     std::vector<unsigned char> bt_nw;
-    std::vector<u32> bt_row, bt_eq;
+    std::vector<u32> bt_row, bt_eq, bt_quad;
+    std::vector<i32> bt_quad_row;
     std::vector<BtClass> bt_classes;                       // one kernel launch each
     std::vector<i32> pair_pool, spec_pool, spec_dense;
     std::vector<u32> peq_long;
@@ -215,7 +216,7 @@ struct HostTables {
         t.hit_cap = 4;
         // stage-2 tasks: consecutive bwords of one primer and one length, up to kMaxTaskWords to a task (one word
         // when the flank does not fit the 16-column register form, or k is beyond the multi-word instantiations)
-        bt_g0.clear(); bt_nw.clear(); bt_row.clear(); bt_eq.clear(); bt_class_tasks.clear();
+        bt_g0.clear(); bt_nw.clear(); bt_row.clear(); bt_eq.clear(); bt_class_tasks.clear(); bt_quad.clear(); bt_quad_row.clear();
         for (int p = 0; p < nP; ++p) {
             t.bt_off[p] = (u32)bt_g0.size();
             u32 g = t.bw_off[p];
@@ -235,6 +236,25 @@ struct HostTables {
                     for (int i = 0; i < m; ++i)
                         for (int c = 0; c < 16; ++c)
                             bt_eq[base + ((size_t)i * 16 + c) * S + q] = beq[((size_t)bw_row[g + q] + i) * 16 + c];
+                // narrow word (<= 8 barcodes, register form): the four-entries-to-a-word table, indexed per row by the
+                // four entries' symbols (0..3 = A/C/G/T, 4 = beyond the flank: matches nothing), entry q in byte lane q
+                bt_quad_row.push_back(-1);
+                if (nw == 1 && m + t.k_idx <= 16 && t.k_idx <= kMaxTaskK && (bw_valid[g] & ~0xFFu) == 0) {
+                    bt_quad_row.back() = (i32)bt_quad.size();
+                    const size_t qb = bt_quad.size();
+                    bt_quad.resize(qb + (size_t)m * kQuadRow, 0);
+                    for (int i = 0; i < m; ++i)
+                        for (int idx = 0; idx < kQuadRow; ++idx) {
+                            u32 w = 0;
+                            int rest = idx;
+                            for (int q = 0; q < 4; ++q) {
+                                const int sym = rest % kQuadSyms;
+                                rest /= kQuadSyms;
+                                if (sym < 4) w |= (beq[((size_t)bw_row[g] + i) * 16 + sym] & 0xFFu) << (8 * q);
+                            }
+                            bt_quad[qb + (size_t)i * kQuadRow + idx] = w;
+                        }
+                }
                 g += nw;
             }
         }
@@ -244,14 +264,20 @@ struct HostTables {
         bt_classes.clear();
         for (int w = 1; w <= kMaxTaskWords; ++w)
             for (int m = 1; m <= SMX_MAX_PATTERN; ++m) {
-                BtClass c;
-                c.nw = w; c.m = m; c.off = (u32)bt_class_tasks.size(); c.count = 0;
-                for (size_t k = 0; k < bt_nw.size(); ++k)
-                    if (bt_nw[k] == w && bw_len[bt_g0[k]] == m) { bt_class_tasks.push_back((unsigned short)k); ++c.count; }
-                if (c.count) bt_classes.push_back(c);
+                for (int quad = 0; quad < 2; ++quad) {
+                    BtClass c;
+                    c.nw = w; c.m = m; c.quad = quad; c.off = (u32)bt_class_tasks.size(); c.count = 0;
+                    for (size_t k = 0; k < bt_nw.size(); ++k)
+                        if (bt_nw[k] == w && bw_len[bt_g0[k]] == m && (bt_quad_row[k] >= 0) == (quad != 0)) {
+                            bt_class_tasks.push_back((unsigned short)k);
+                            ++c.count;
+                        }
+                    if (c.count) bt_classes.push_back(c);
+                }
             }
         if (bt_eq.empty()) bt_eq.push_back(0);
-        if (bt_g0.empty()) { bt_g0.push_back(0); bt_nw.push_back(0); bt_row.push_back(0); }
+        if (bt_g0.empty()) { bt_g0.push_back(0); bt_nw.push_back(0); bt_row.push_back(0); bt_quad_row.push_back(-1); }
+        if (bt_quad.empty()) bt_quad.push_back(0);
         if (bt_class_tasks.empty()) bt_class_tasks.push_back(0);
         for (int p = 0; p < nP; ++p)
             if (tb->pb_off[p + 1] - tb->pb_off[p] > 65535) return err("primer %d has more than 65535 barcodes", p);
@@ -299,6 +325,7 @@ struct HostTables {
                      spec_row.data(), spec_p1.data(), spec_p2.data(), spec_pool.data());
         set_bword_pointers(bw_len.data(), bw_primer.data(), bw_row.data(), bw_valid.data(), bw_list.data(), beq.data());
         set_task_pointers(bt_g0.data(), bt_nw.data(), bt_row.data(), bt_eq.data());
+        set_quad_pointers(bt_quad_row.data(), bt_quad.data());
         set_code_pointers(b_codes.data(), b_code_off.data(), bw_iupac.data());
         return true;
     }
@@ -307,6 +334,8 @@ struct HostTables {
                             const unsigned short *list, const u32 *eq) {
         t.bw_len = len; t.bw_primer = prim; t.bw_row = row; t.bw_valid = valid; t.bw_list = list; t.beq = eq;
     }
+
+    void set_quad_pointers(const i32 *row, const u32 *quad) { t.bt_quad_row = row; t.bt_quad = quad; }
 
     void set_code_pointers(const unsigned char *codes, const u32 *off, const u32 *iupac) {
         t.b_codes = codes; t.b_code_off = off; t.bw_iupac = iupac;

@@ -23,17 +23,41 @@ __global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int p
 }
 
 
-// Start recovery, bit-sliced across work entries: one thread per (32 consecutive entries of a slot) for one primer.
+// Start recovery, bit-sliced across work entries: one thread owns 32 consecutive entries of a slot, a block of 64
+// threads 2,048.  The entries' window words are gathered by the WHOLE block, one entry per thread and step (the
+// first form let every thread gather its own 32 entries one after the other: 258 us at 10 % ALU, a chain of
+// dependent loads per entry -- profiles/r2_i_ncu_full.md), the reverse passes run bit-sliced, and the starts go
+// back out the same cooperative way.
 template <int M>
 __global__ void __launch_bounds__(kSlicedBlock) k_primer_start_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
     __shared__ u32 s_planes[(kSlicedCodes + kStartPlanes) * kSlicedBlock];
-    const u32 slot = blockIdx.y * c_tables.n_primers + primer;
+    const Tables &t = c_tables;
+    const u32 slot = blockIdx.y * t.n_primers + primer;
     u32 cnt = b.slot_count[slot];
     if (cnt > b.e_cap) cnt = b.e_cap;
-    const u32 e0 = (blockIdx.x * kSlicedBlock + threadIdx.x) * 32u;
-    if (e0 >= cnt) return;
-    primer_start_sliced_thread<M, kSlicedBlock>(c_tables, b, slot, e0, cnt, ro, degenerate != 0, s_planes + threadIdx.x,
-                                                s_planes + kSlicedCodes * kSlicedBlock + threadIdx.x);
+    const u32 block_e0 = blockIdx.x * kSlicedBlock * 32u;
+    if (block_e0 >= cnt) return;
+    u32 *sa = s_planes + kSlicedCodes * kSlicedBlock;              // [plane word][owner thread]
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+        const u32 idx = (u32)it * kSlicedBlock + threadIdx.x;      // entry block_e0 + idx: owner idx / 32, its word idx % 32
+        u32 xh, xl, act, best;
+        start_gather_entry(t, b, slot, block_e0 + idx, cnt, M, xh, xl, act, best);
+        u32 *dst = sa + (idx & 31u) * kSlicedBlock + (idx >> 5);
+        dst[0] = xh; dst[32 * kSlicedBlock] = xl; dst[64 * kSlicedBlock] = act; dst[96 * kSlicedBlock] = best;
+    }
+    __syncthreads();
+    if (block_e0 + threadIdx.x * 32u < cnt)
+        primer_start_sliced_thread<M, kSlicedBlock>((int)t.p_len[primer] + (int)t.p_k[primer], ro, degenerate != 0,
+                                                    s_planes + threadIdx.x, sa + threadIdx.x);
+    __syncthreads();
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+        const u32 idx = (u32)it * kSlicedBlock + threadIdx.x;
+        if (block_e0 + (idx & ~31u) >= cnt) continue;              // its owner did not run
+        const u32 last = sa[(idx & 31u) * kSlicedBlock + (idx >> 5)];
+        if (last != 0xFFFFFFFFu) start_store_entry(t, b, slot, block_e0 + idx, (int)last);
+    }
 }
 
 cudaError_t launch_primer_start_sliced(const Tables &t, const Batch &b, int primer, const unsigned char *prow_code, cudaStream_t st) {

@@ -277,7 +277,7 @@ cudaError_t launch_barcode_tasks(const Tables &t, const Batch &b, const unsigned
         const unsigned short *list = class_tasks + c.off;
         cudaError_t e;
         switch (t.k_idx) {
-#define SMX_K2(KK) case KK: e = launch_barcode_class_k##KK(t, b, list, (int)c.count, c.nw, c.m, st); break;
+#define SMX_K2(KK) case KK: e = launch_barcode_class_k##KK(t, b, list, (int)c.count, c.nw, c.m, c.quad, st); break;
             SMX_K2(0) SMX_K2(1) SMX_K2(2) SMX_K2(3) SMX_K2(4) SMX_K2(5) SMX_K2(6) SMX_K2(7) SMX_K2(8)
             SMX_K2(9) SMX_K2(10) SMX_K2(11) SMX_K2(12)
 #undef SMX_K2

@@ -61,6 +61,47 @@ __global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned 
     }
 }
 
+// Narrow single-word tasks, four work entries to a thread (barcode_quad_thread): blockIdx.x walks the entries in
+// groups of 4 * blockDim.x; the 625-entry-per-row table and the task's ordinary table (for the entries that fall back
+// to the one-entry routine) sit in shared memory.
+template <int K, int MF>
+__global__ void __launch_bounds__(128) k_barcode_quad(SMX_KARGS, const unsigned short *task_list, int n_list) {
+    __shared__ u32 s_tab4[16 * kQuadRow];
+    __shared__ u32 s_tab1[16 * 16];
+    __shared__ u32 s_acc;
+    const Tables &t = c_tables;
+    const u32 task = task_list[blockIdx.y % n_list];
+    const int strand = blockIdx.y / n_list;
+    const u32 g0 = t.bt_g0[task];
+    const int primer = t.bw_primer[g0];
+    const u32 slot = slot_index(t, strand, primer);
+    u32 cnt = b.slot_count[slot];
+    if (cnt > b.e_cap) cnt = b.e_cap;
+    if (blockIdx.x * blockDim.x * 4u >= cnt) return;
+    const int m = MF ? MF : (int)t.bw_len[g0];
+    if (threadIdx.x == 0) s_acc = 0;
+    {
+        const u32 *src4 = t.bt_quad + t.bt_quad_row[task], *src1 = t.bt_eq + t.bt_row[task];
+        for (int i = threadIdx.x; i < m * kQuadRow; i += blockDim.x) s_tab4[i] = src4[i];
+        for (int i = threadIdx.x; i < m * 16; i += blockDim.x) s_tab1[i] = src1[i];
+    }
+    __syncthreads();
+    const u32 e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    u32 work = 0;
+    if (e0 < cnt) work = barcode_quad_thread<K, MF>(t, b, slot, e0, cnt, strand, primer, task, s_tab4, s_tab1);
+    const u32 wsum = __reduce_add_sync(0xffffffffu, work);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_acc, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long tot = s_acc & 0xFFFFFu, ran = s_acc >> 20;
+        if (tot) {
+            atomicAdd(&b.counters[1], tot * (unsigned long long)m);
+            atomicAdd(&b.counters[3], tot * (unsigned long long)((m + 31) >> 5));
+        }
+        if (ran) atomicAdd(&b.counters[kCtrUseful2], ran * (unsigned long long)band_cells(m, K, true));
+    }
+}
+
 // barcode lengths with their own instantiation (the lengths barcode sets are built in; every other length runs the
 // any-length form)
 template <int K, int M> struct FixedLen { static constexpr int value = (K >= 1 && K <= kMaxTaskK && M > K && M + K <= 16) ? M : 0; };
@@ -87,9 +128,29 @@ static cudaError_t launch_class(const Tables &t, const Batch &b, const unsigned 
 #define SMX_CAT_(a, b) a##b
 #define SMX_CAT(a, b) SMX_CAT_(a, b)
 
+template <int K>
+static cudaError_t launch_quad(const Tables &t, const Batch &b, const unsigned short *list, int n_list, int m, cudaStream_t st) {
+    dim3 grid((b.e_cap / 4 + 128) / 128, 2 * n_list);
+    switch (m) {
+#define SMX_MF(MM)                                                                                         \
+        case MM:                                                                                           \
+            if (FixedLen<K, MM>::value) {                                                                  \
+                k_barcode_quad<K, FixedLen<K, MM>::value><<<grid, 128, 0, st>>>(t, b, list, n_list);       \
+                return cudaGetLastError();                                                                 \
+            }                                                                                              \
+            break;
+        SMX_MF(8) SMX_MF(10) SMX_MF(12) SMX_MF(13)
+#undef SMX_MF
+        default: break;
+    }
+    k_barcode_quad<K, 0><<<grid, 128, 0, st>>>(t, b, list, n_list);
+    return cudaGetLastError();
+}
+
 cudaError_t SMX_CAT(launch_barcode_class_k, SMX_STAGE2_K)(const Tables &t, const Batch &b, const unsigned short *list,
-                                                          int n_list, int nw, int m, cudaStream_t st) {
+                                                          int n_list, int nw, int m, int quad, cudaStream_t st) {
     constexpr int K = SMX_STAGE2_K;
+    if (quad) return launch_quad<K>(t, b, list, n_list, m, st);
     if (nw == 1) return launch_class<K, 1>(t, b, list, n_list, m, st);
     if (K > kMaxTaskK) return cudaErrorInvalidValue;            // the host never builds multi-word tasks there
     constexpr int KM = K > kMaxTaskK ? 0 : K;

@@ -41,6 +41,13 @@ SMX_HD u32 revcomp16(u32 v) {
     return ~v;
 }
 
+// Reads whose primer search runs bit-sliced (regular full-length A/C/G/T window).  Only the OTHER reads get the 4-bit
+// staged windows (`win`): sliced reads are served from the 2-bit words everywhere (stage 1, start recovery, the
+// barcode flank), which cuts the staging kernel's stores from 120 to 40 bytes per read.
+SMX_HD bool sliced_eligible(const Tables &t, const Batch &b, u32 read) {
+    return t.sliced && !read_is_flagged(b, read) && (int)b.lengths[read] >= t.L;
+}
+
 // One thread stages 16 symbols of one strand: the 2-bit word win2[w2] (input of the sliced primer
 // search) and the two 4-bit words win[2*w2], win[2*w2+1] (barcode stage, start recovery, classic
 // primer search).  Positions past the staged length hold kSymOther in `win`.
@@ -69,6 +76,7 @@ SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int str
             if (strand) v = revcomp16(v);
         }
         b.win2[((u64)strand * t.nw2 + w2) * b.n_pad + read] = v;
+        if (t.sliced && n >= t.L) return;                     // sliced read: no 4-bit window (staged_sym reads win2)
         const int vlo = valid > 8 ? 8 : valid, vhi = valid > 8 ? valid - 8 : 0;
         u32 out = spread2to4(v);
         if (vlo < 8) out |= ~0u << (4 * vlo);
@@ -94,6 +102,10 @@ SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int str
 }
 
 SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int p) {
+    if (sliced_eligible(t, b, read)) {
+        const u32 w2 = b.win2[((u64)strand * t.nw2 + (p >> 4)) * b.n_pad + read];
+        return (int)((w2 >> (2 * (p & 15))) & 3);
+    }
     u32 w = b.win[((u64)strand * t.wpw + (p >> 3)) * b.n_pad + read];
     return (int)((w >> (4 * (p & 7))) & 15);
 }
@@ -439,10 +451,6 @@ SMX_HD void primer_sliced_thread(const Tables &t, const Batch &b, u32 group, int
     }
 }
 
-SMX_HD bool sliced_eligible(const Tables &t, const Batch &b, u32 read) {
-    return t.sliced && !read_is_flagged(b, read) && (int)b.lengths[read] >= t.L;
-}
-
 // Stage 1 per (read, strand, primer) after the sliced pass: eligible reads decode their column
 // histories from tmix, every other read runs the classic search.  Returns the number of
 // equal-best end locations.
@@ -619,66 +627,66 @@ SMX_HD u32 reverse_pairs16(u32 v) {
     return ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);
 }
 
-constexpr int kStartPlanes = 104;       // per-thread plane buffer of primer_start_sliced_thread (words)
+constexpr int kStartPlanes = 128;       // per-thread plane buffer of the sliced start recovery (words): XH, XL, ACT, BEST
 
-// sp: kSlicedCodes code planes, sa: kStartPlanes words (element stride STRIDE).  ro: byte offsets of the Eq plane
-// of every row of the REVERSED primer_rc.  e0: first of the thread's 32 entries of `slot`; n_entries: entries of
-// the slot.
+// Gather of ONE work entry for the sliced start recovery: the reversed window words (symbol first - j in column j,
+// 16 columns per word), the active-column mask and the best distance (63 = the entry takes no part: not the first
+// location of its read, beyond the list, or a read on the 4-bit side stream).
+SMX_HD void start_gather_entry(const Tables &t, const Batch &b, u32 slot, u32 e, u32 n_entries, int m,
+                               u32 &xh, u32 &xl, u32 &act, u32 &best) {
+    xh = 0; xl = 0; act = 0; best = 63;
+    if (e >= n_entries) return;
+    const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
+    const u64 hit_idx = (u64)slot * b.n_pad + read;
+    if (b.ent_base[hit_idx] != e || read_is_flagged(b, read)) return;
+    const int strand = (int)slot / t.n_primers;
+    const smx_primer_hit h = b.phit[hit_idx];
+    const Geo g = make_geo((int)b.lengths[read], t.L);
+    const int first = h.first_end - g.woff - g.delta;
+    int cols = first - g.start + 1;
+    const int lim = m + (int)h.distance;
+    if (cols > lim) cols = lim;
+    const u32 *w2 = b.win2 + (u64)strand * t.nw2 * b.n_pad + read;
+    xh = reverse_pairs16(win2_extract16(w2, b.n_pad, t.nw2, first - 15));
+    xl = reverse_pairs16(win2_extract16(w2, b.n_pad, t.nw2, first - 31));
+    act = cols >= 32 ? ~0u : ((1u << cols) - 1u);
+    best = (u32)h.distance;
+}
+
+// `last` = number of columns walked back from the first equal-best end (edlib: the LAST reverse end at the best score)
+SMX_HD void start_store_entry(const Tables &t, const Batch &b, u32 slot, u32 e, int last) {
+    const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
+    smx_primer_hit &h = b.phit[(u64)slot * b.n_pad + read];
+    h.first_start = h.first_end - last;
+}
+
+// The bit-sliced reverse SHW pass over the 32 gathered entries of one thread.  sp: kSlicedCodes code planes; sa:
+// kStartPlanes words (element stride STRIDE) holding the gathered XH[32], XL[32], ACT[32], BEST[32] words; on return
+// XH[r] = columns walked back for entry r, or 0xFFFFFFFF when the entry takes no part.  ro: byte offsets of the Eq
+// plane of every row of the REVERSED primer_rc.
 template <int M, int STRIDE>
-SMX_HD void primer_start_sliced_thread(const Tables &t, const Batch &b, u32 slot, u32 e0, u32 n_entries,
-                                       const RowOffsets &ro, bool degenerate, u32 *sp, u32 *sa) {
-    const int strand = (int)slot / t.n_primers, primer = (int)slot % t.n_primers;
-    const int ncols = (int)t.p_len[primer] + (int)t.p_k[primer];       // <= 32 (start_sliced_ok)
+SMX_HD void primer_start_sliced_thread(int ncols, const RowOffsets &ro, bool degenerate, u32 *sp, u32 *sa) {
     u32 *XH = sa, *XL = sa + 32 * STRIDE, *ACT = sa + 64 * STRIDE, *BP = sa + 96 * STRIDE;
     u32 a[32];
-    // ---- per entry: reversed window words, active-column mask, best distance
-    u32 bestw[32];
-    for (int r = 0; r < 32; ++r) {
-        const u32 e = e0 + (u32)r;
-        u32 xh = 0, xl = 0, act = 0, best = 63;
-        if (e < n_entries) {
-            const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
-            const u64 hit_idx = (u64)slot * b.n_pad + read;
-            if (b.ent_base[hit_idx] == e && !read_is_flagged(b, read)) {     // first location of its read, 2-bit window
-                const smx_primer_hit h = b.phit[hit_idx];
-                const Geo g = make_geo((int)b.lengths[read], t.L);
-                const int first = h.first_end - g.woff - g.delta;
-                int cols = first - g.start + 1;
-                const int lim = M + (int)h.distance;
-                if (cols > lim) cols = lim;
-                const u32 *w2 = b.win2 + (u64)strand * t.nw2 * b.n_pad + read;
-                xh = reverse_pairs16(win2_extract16(w2, b.n_pad, t.nw2, first - 15));
-                xl = reverse_pairs16(win2_extract16(w2, b.n_pad, t.nw2, first - 31));
-                act = cols >= 32 ? ~0u : ((1u << cols) - 1u);
-                best = (u32)h.distance;
-            }
-        }
-        XH[r * STRIDE] = xh; XL[r * STRIDE] = xl; ACT[r * STRIDE] = act;
-        bestw[r] = best;
-    }
-    // ---- entries x bits -> bit planes x entries (four transposes; the best distances need six planes)
-    for (int which = 0; which < 3; ++which) {
-        u32 *buf = which == 0 ? XH : which == 1 ? XL : ACT;
+    u32 part = 0;                       // entries that take part (best != 63)
+    // ---- entries x bits -> bit planes x entries
+    for (int which = 0; which < 4; ++which) {
+        u32 *buf = which == 0 ? XH : which == 1 ? XL : which == 2 ? ACT : BP;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int r = 0; r < 32; ++r) a[r] = buf[r * STRIDE];
+        if (which == 3) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < 32; ++r) part |= (a[r] != 63u ? 1u : 0u) << r;
+        }
         transpose32(a);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int r = 0; r < 32; ++r) buf[r * STRIDE] = a[r];
-    }
-    {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int r = 0; r < 32; ++r) a[r] = bestw[r];
-        transpose32(a);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int l = 0; l < 6; ++l) BP[l * STRIDE] = a[l];
     }
     // ---- the reverse SHW pass (D[0][j] = j, D[i][0] = i), score of row m on six planes
     u32 VP[M], VM[M];
@@ -741,14 +749,11 @@ SMX_HD void primer_start_sliced_thread(const Tables &t, const Batch &b, u32 slot
 #endif
     for (int c = 0; c < 32; ++c) a[c] = c < ncols ? (c < 16 ? XH[c * STRIDE] : XL[(c - 16) * STRIDE]) : 0u;
     transpose32(a);
-    for (int r = 0; r < 32; ++r) {
-        if (bestw[r] == 63) continue;
-        const u32 e = e0 + (u32)r;
-        const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
-        smx_primer_hit &h = b.phit[(u64)slot * b.n_pad + read];
-        const int last = a[r] ? 31 - count_leading_zeros32(a[r]) : M - 1;
-        h.first_start = h.first_end - last;
-    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 32; ++r)
+        XH[r * STRIDE] = ((part >> r) & 1u) ? (a[r] ? (u32)(31 - count_leading_zeros32(a[r])) : (u32)(M - 1)) : 0xFFFFFFFFu;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -925,16 +930,12 @@ struct CsaCount {
 // one vector load at a compile-time offset from its column's address, shared by the task's words, and the
 // NWQ independent automata interleave in the instruction stream.  Rows beyond m leave the unrolled sequence
 // through one early exit, so the horizontal-delta registers are renamed from row to row without moves.
-template <int K, int NWQ, int MF = 0>
-SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[NWQ]) {
+// col[j]: address of row 0 of flank column j + 1 in the task table; ROWSTRIDE: words from one row to the next.
+template <int K, int NWQ, int MF, int ROWSTRIDE>
+SMX_HD void bitsliced_small_rows_cols(const u32 *const (&col)[16], int m, SmallOut<K> (&o)[NWQ]) {
     typedef BitSliced<K> BS;
     constexpr int NT = BS::NT, S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
     constexpr int kRows = 16 - K > 0 ? 16 - K : 0;
-    const u32 *col[16];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 16; ++j) col[j] = tab + (u32)((F >> (4 * j)) & 15u) * S;
     u32 HP[NWQ][NT], HM[NWQ][NT];
     CsaCount cnt[NWQ];                                      // D[i][i-K] - K along the band's lower diagonal
 #if defined(__CUDA_ARCH__)
@@ -964,7 +965,7 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[
             const int j = i - K + t;                        // compile-time
             if (j < 1 || j > 16) continue;
             u32 eq[S];
-            load_eq<S>(col[j - 1] + (i - 1) * 16 * S, eq);
+            load_eq<S>(col[j - 1] + (i - 1) * ROWSTRIDE, eq);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -989,6 +990,17 @@ SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[
 #endif
         for (int t = 1; t < NT; ++t) { o[q].rp[t - 1] = HP[q][t]; o[q].rm[t - 1] = HM[q][t]; }
     }
+}
+
+template <int K, int NWQ, int MF = 0>
+SMX_HD void bitsliced_small_rows(const u32 *tab, int m, u64 F, SmallOut<K> (&o)[NWQ]) {
+    constexpr int S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
+    const u32 *col[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 16; ++j) col[j] = tab + (u32)((F >> (4 * j)) & 15u) * S;
+    bitsliced_small_rows_cols<K, NWQ, MF, 16 * S>(col, m, o);
 }
 
 // BloomPrefilter.match for a barcode that holds IUPAC codes, with an exact set (bloom_filter.py:70-101, 176-186): the
@@ -1172,7 +1184,6 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
     BarcodeDigest &dg_out = b.bdig[((u64)strand * t.n_btasks + task) * b.e_cap + entry];
     const int n = (int)b.lengths[read];
     const Geo geo = make_geo(n, t.L);
-    const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
     const int m = MF ? MF : (int)t.bw_len[g0];
     int nbits = 0;
 #if defined(__CUDA_ARCH__)
@@ -1190,12 +1201,23 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
     u64 F = ~0ull;
     if (small && cols > 0) {
         // 16 symbols starting at staged position `base`, symbols >= cols forced to "other"
-        int w0 = base >> 3, sh = 4 * (base & 7);
-        u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
-        u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
-        u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
-        u64 lo = ((u64)a1 << 32) | a0, hi = a2;
-        F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        if (sliced_eligible(t, b, read)) {
+            // from the 2-bit window words: 16 symbols = 32 bits, spread into nibbles
+            const u32 *w2p = b.win2 + (u64)strand * t.nw2 * b.n_pad + read;
+            const int w0 = base >> 4, sh = 2 * (base & 15);
+            const u32 a0 = w0 < t.nw2 ? w2p[(u64)w0 * b.n_pad] : 0u;
+            const u32 a1 = w0 + 1 < t.nw2 ? w2p[(u64)(w0 + 1) * b.n_pad] : 0u;
+            const u32 v = sh ? (a0 >> sh) | (a1 << (32 - sh)) : a0;
+            F = (u64)spread2to4(v) | ((u64)spread2to4(v >> 16) << 32);
+        } else {
+            const u32 *win = b.win + (u64)strand * t.wpw * b.n_pad + read;
+            int w0 = base >> 3, sh = 4 * (base & 7);
+            u32 a0 = w0 < t.wpw ? win[(u64)w0 * b.n_pad] : ~0u;
+            u32 a1 = w0 + 1 < t.wpw ? win[(u64)(w0 + 1) * b.n_pad] : ~0u;
+            u32 a2 = w0 + 2 < t.wpw ? win[(u64)(w0 + 2) * b.n_pad] : ~0u;
+            u64 lo = ((u64)a1 << 32) | a0, hi = a2;
+            F = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        }
         if (cols < 16) F |= ~0ull << (4 * cols);
     }
     bool skip = cols < m - K || cols <= 0;           // D[m][j] >= m - j > K for every column
@@ -1311,6 +1333,120 @@ SMX_HD u32 barcode_task_thread(const Tables &t, const Batch &b, u32 read, int p,
     }
     dg_out = dg;
     return work | ((u32)NWQ << 20);
+}
+
+// Narrow bwords (at most 8 barcodes: config 2's forward primer): FOUR work entries share one machine word, entry q in
+// byte lane q.  The Eq word of a cell is one load from a table indexed by the four entries' symbols of that column
+// (five symbols each: A/C/G/T or "beyond the flank" -> 625 combinations per row), so the automaton costs the same
+// 5 LOP3 + 1 LDS per cell as a full word while serving four entries: the one-entry-per-thread form spent a third of
+// stage 2 (66 of 199 us, profiles/r2_h_ncu_full.md) on a word with a quarter of its lanes in use.
+// Entries the quad form cannot take (reads on the 4-bit side stream, the Python-slice corner where the prefilter's
+// flank differs from the aligned one) run the one-entry routine from the same thread.
+
+template <int K, int MF>
+SMX_HD u32 barcode_quad_thread(const Tables &t, const Batch &b, u32 slot, u32 e0, u32 n_entries, int strand, int primer,
+                               u32 task, const u32 *tab4, const u32 *tab1) {
+    typedef BitSliced<K> BS;
+    const u32 g0 = t.bt_g0[task];
+    const u64 gslot0 = (u64)strand * t.n_bwords + g0;
+    const int m = MF ? MF : (int)t.bw_len[g0];
+    const u32 valid8 = t.bw_valid[g0] & 0xFFu, iupac8 = t.bw_iupac[g0] & 0xFFu;
+    const int nbits = popcount32(valid8);
+    u32 work = 0, ran = 0;
+    u32 F2[4];                      // 16 flank symbols, 2 bits each
+    int cols[4], bs[4], apref[4], woff[4];
+    u32 rd[4];
+    bool act[4];
+    u32 lanes = 0;                  // byte lanes of the entries whose automaton runs
+    for (int q = 0; q < 4; ++q) {
+        act[q] = false; F2[q] = 0; cols[q] = 0; bs[q] = 0; apref[q] = 0; woff[q] = 0; rd[q] = 0;
+        const u32 e = e0 + (u32)q;
+        if (e >= n_entries) continue;
+        const u32 read = b.ent_read[(u64)slot * b.e_cap + e];
+        const int p = b.ent_pos[(u64)slot * b.e_cap + e];
+        const int n = (int)b.lengths[read];
+        const Geo geo = make_geo(n, t.L);
+        const Flank f = make_flank(geo.woff + p + geo.delta, n);
+        if (!sliced_eligible(t, b, read) || f.a_pref != f.a_align) {
+            const u32 w1 = barcode_task_thread<K, 1, MF>(t, b, read, p, e, strand, primer, task, tab1);
+            work += w1 & 0xFFFFFu; ran += w1 >> 20;
+            continue;
+        }
+        const int fl = n - f.a_align;
+        const int c = fl < m + K ? fl : m + K;
+        if (c > 0) work += (u32)(nbits * c);
+        BarcodeDigest dg;
+        dg.search_start = f.bs; dg.jmin = 0; dg.jmax = 0; dg.count = 0; dg.bd = -1; dg.first_col = 0; dg.nhits = 0;
+        b.bdig[((u64)strand * t.n_btasks + task) * b.e_cap + e] = dg;          // overwritten below when hits turn up
+        b.bh_count[gslot0 * b.e_cap + e] = 0;
+        if (c < m - K || c <= 0 || (t.prefilter && n - f.a_pref < m - K)) continue;     // no barcode can match
+        const int base = f.a_align - geo.woff;
+        const u32 *w2p = b.win2 + (u64)strand * t.nw2 * b.n_pad + read;
+        const int w0 = base >> 4, sh = 2 * (base & 15);
+        const u32 a0 = w0 < t.nw2 ? w2p[(u64)w0 * b.n_pad] : 0u;
+        const u32 a1 = w0 + 1 < t.nw2 ? w2p[(u64)(w0 + 1) * b.n_pad] : 0u;
+        F2[q] = sh ? (a0 >> sh) | (a1 << (32 - sh)) : a0;
+        cols[q] = c; bs[q] = f.bs; apref[q] = f.a_pref; woff[q] = geo.woff; rd[q] = read;
+        act[q] = true;
+        lanes |= valid8 << (8 * q);
+        ++ran;
+    }
+    if (!lanes) return work | (ran << 20);
+    // table address of every column: the four entries' symbols (4 = beyond the entry's flank, or no entry)
+    const u32 *col[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 16; ++j) {
+        u32 idx = 0, mul = 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q) {
+            const u32 sym = (act[q] && j < cols[q]) ? (F2[q] >> (2 * j)) & 3u : 4u;
+            idx += sym * mul;
+            mul *= kQuadSyms;
+        }
+        col[j] = tab4 + idx;
+    }
+    SmallOut<K> o[1];
+    bitsliced_small_rows_cols<K, 1, MF, kQuadRow>(col, m, o);
+    // flags over all end columns (an entry's own column limit is applied by the exact scalar read-out)
+    u32 flag = barcode_flags_small<K>(o[0], m, 16) & lanes;
+    DigestAcc acc[4];
+    int nh[4];
+    for (int q = 0; q < 4; ++q) { acc[q].bd = 1 << 20; acc[q].count = 0; acc[q].jmin = 1 << 20; acc[q].jmax = -1; acc[q].first_col = 0; acc[q].nhits = 0; nh[q] = 0; }
+    while (flag) {
+        const int bit = lowest_bit32(flag);
+        flag &= flag - 1;
+        const int q = bit >> 3, lane = bit & 7;
+        u64 mask;
+        const int best = barcode_lane_value<K, 5>(o[0].v0, o[0].rp, o[0].rm, bit, m, cols[q], mask);
+        if (best > K) continue;
+        if (t.prefilter && ((iupac8 >> lane) & 1u)) {           // exact per-barcode Bloom emulation (see bloom_literal_yes)
+            const u32 le = t.pb_off[primer] + t.bw_list[(u64)g0 * 32 + lane];
+            const u32 read = rd[q];
+            const int off = apref[q] - woff[q];
+            if (!bloom_literal_yes(t.b_codes + t.b_code_off[le], m, K, [&](int x) { return staged_sym(t, b, read, strand, off + x); }))
+                continue;
+        }
+        barcode_add_hit(t, b, gslot0, (u64)e0 + q, nh[q], (int)t.bw_list[(u64)g0 * 32 + lane], best, mask, bs[q], acc[q]);
+        ++nh[q];
+    }
+    bool over_cap = false;
+    for (int q = 0; q < 4; ++q) {
+        if (!act[q] || !nh[q]) continue;
+        const u64 e = (u64)e0 + q;
+        b.bh_count[gslot0 * b.e_cap + e] = (unsigned char)nh[q];
+        over_cap |= nh[q] > t.hit_cap;
+        BarcodeDigest dg;
+        dg.search_start = bs[q]; dg.nhits = acc[q].nhits; dg.bd = (signed char)acc[q].bd;
+        dg.count = (unsigned short)(acc[q].count > 65535 ? 65535 : acc[q].count);
+        dg.jmin = (unsigned short)acc[q].jmin; dg.jmax = (unsigned short)acc[q].jmax; dg.first_col = (unsigned char)acc[q].first_col;
+        b.bdig[((u64)strand * t.n_btasks + task) * b.e_cap + e] = dg;
+    }
+    if (over_cap) counter_add(&b.counters[7], 1);
+    return work | (ran << 20);
 }
 
 // Work-entry bookkeeping of stage 1: entries [base, base + nloc) of `slot` for one matched read.

@@ -25,7 +25,7 @@ cudaError_t launch_barcode_tasks(const Tables &t, const Batch &b, const unsigned
                                  const BtClass *classes, int n_classes, cudaStream_t st, int *launches);
 // one translation unit per barcode threshold (smx_k_stage2.cu, -DSMX_STAGE2_K=k)
 #define SMX_DECL_K2(KK) cudaError_t launch_barcode_class_k##KK(const Tables &t, const Batch &b, const unsigned short *list, \
-                                                                int n_list, int nw, int m, cudaStream_t st);
+                                                                int n_list, int nw, int m, int quad, cudaStream_t st);
 SMX_DECL_K2(0) SMX_DECL_K2(1) SMX_DECL_K2(2) SMX_DECL_K2(3) SMX_DECL_K2(4) SMX_DECL_K2(5) SMX_DECL_K2(6) SMX_DECL_K2(7) SMX_DECL_K2(8)
 SMX_DECL_K2(9) SMX_DECL_K2(10) SMX_DECL_K2(11) SMX_DECL_K2(12)
 #undef SMX_DECL_K2

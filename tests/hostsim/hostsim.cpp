@@ -237,9 +237,12 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                 ro.off[i] = (unsigned short)(code * sizeof(u32));
             }
             u32 scratch[kSlicedCodes], planes[kStartPlanes];
-            for (u32 e0 = 0; e0 < slot_count[slot]; e0 += 32)
+            for (u32 e0 = 0; e0 < slot_count[slot]; e0 += 32) {
+                for (u32 r = 0; r < 32; ++r)
+                    start_gather_entry(t, b, slot, e0 + r, slot_count[slot], m, planes[r], planes[32 + r], planes[64 + r], planes[96 + r]);
+                const int ncols = m + (int)t.p_k[p];
                 switch (m) {
-#define SMX_M(MM) case MM: primer_start_sliced_thread<MM, 1>(t, b, slot, e0, slot_count[slot], ro, degenerate, scratch, planes); break;
+#define SMX_M(MM) case MM: primer_start_sliced_thread<MM, 1>(ncols, ro, degenerate, scratch, planes); break;
                     SMX_M(1) SMX_M(2) SMX_M(3) SMX_M(4) SMX_M(5) SMX_M(6) SMX_M(7) SMX_M(8) SMX_M(9) SMX_M(10) SMX_M(11)
                     SMX_M(12) SMX_M(13) SMX_M(14) SMX_M(15) SMX_M(16) SMX_M(17) SMX_M(18) SMX_M(19) SMX_M(20) SMX_M(21)
                     SMX_M(22) SMX_M(23) SMX_M(24) SMX_M(25) SMX_M(26) SMX_M(27) SMX_M(28) SMX_M(29) SMX_M(30) SMX_M(31)
@@ -247,6 +250,9 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
 #undef SMX_M
                     default: snprintf(g_err, sizeof(g_err), "sliced start: primer length"); return SMX_ERR_INTERNAL;
                 }
+                for (u32 r = 0; r < 32; ++r)
+                    if (planes[r] != 0xFFFFFFFFu) start_store_entry(t, b, slot, e0 + r, (int)planes[r]);
+            }
         }
         bdig.assign((size_t)2 * t.n_btasks * e_cap + 1, BarcodeDigest());
         b.bdig = bdig.data();
@@ -256,6 +262,23 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
                 const u32 *tab = t.bt_eq + t.bt_row[tk];
                 const int p = t.bw_primer[g0], m = t.bw_len[g0], nw = t.bt_nw[tk];
                 u32 slot = (u32)(s * nP + p);
+                if (t.bt_quad_row[tk] >= 0 && t.k_idx <= kMaxTaskK) {          // narrow word: four entries to a "thread"
+                    const u32 *tab4 = t.bt_quad + t.bt_quad_row[tk];
+                    for (u32 e0 = 0; e0 < slot_count[slot]; e0 += 4) {
+                        u32 work = 0;
+                        switch (t.k_idx) {
+#define SMX_Q(KK) case KK: work = (m == 13 && KK >= 1 && KK <= 3) \
+        ? barcode_quad_thread<KK, (KK >= 1 && KK <= 3) ? 13 : 0>(t, b, slot, e0, slot_count[slot], s, p, (u32)tk, tab4, tab) \
+        : barcode_quad_thread<KK, 0>(t, b, slot, e0, slot_count[slot], s, p, (u32)tk, tab4, tab); break;
+                            SMX_Q(0) SMX_Q(1) SMX_Q(2) SMX_Q(3) SMX_Q(4)
+#undef SMX_Q
+                            default: break;
+                        }
+                        counters[1] += (unsigned long long)(work & 0xFFFFFu) * m;
+                        counters[3] += (unsigned long long)(work & 0xFFFFFu) * ((m + 31) >> 5);
+                    }
+                    continue;
+                }
                 for (u32 e = 0; e < slot_count[slot]; ++e) {
                     u32 r = ent_read[(size_t)slot * e_cap + e];
                     int pos = ent_pos[(size_t)slot * e_cap + e];
