@@ -170,7 +170,9 @@ struct smx_ctx {
     int last_chunks = 0;
     bool trace = false;
     bool tiny_caps = false;                 // SMX_TEST_TINY_CAPS=1: see lane_upload
-    bool start_sliced = true;               // bit-sliced start recovery kernel (SMX_START_SLICED=0: single-word form only)
+    bool start_sliced = false;              // bit-sliced start recovery kernel (SMX_START_SLICED=1): 4x fewer instructions than the
+                                            // single-word form fused into the finish kernel, but latency-bound on its gather and
+                                            // slower on the box (215 vs 58 us, profiles/r2_k_ab.md), so it is off by default
     bool lane_priorities = false;           // SMX_PIPELINE_PRIORITIES=1: earlier lanes get higher stream priority
     // pipelined smx_match_batch chunking (SMX_PIPELINE_RAMP): 0 = even split (default); 1 = two extra small
     // chunks first (measured 1.83 vs 1.76 ms on config 2: the extra chunks cost more kernel-chain latency than

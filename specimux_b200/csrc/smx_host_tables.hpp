@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -239,7 +240,7 @@ struct HostTables {
                 // narrow word (<= 8 barcodes, register form): the four-entries-to-a-word table, indexed per row by the
                 // four entries' symbols (0..3 = A/C/G/T, 4 = beyond the flank: matches nothing), entry q in byte lane q
                 bt_quad_row.push_back(-1);
-                if (nw == 1 && m + t.k_idx <= 16 && t.k_idx <= kMaxTaskK && (bw_valid[g] & ~0xFFu) == 0) {
+                if (quad_enabled() && nw == 1 && m + t.k_idx <= 16 && t.k_idx <= kMaxTaskK && (bw_valid[g] & ~0xFFu) == 0) {
                     bt_quad_row.back() = (i32)bt_quad.size();
                     const size_t qb = bt_quad.size();
                     bt_quad.resize(qb + (size_t)m * kQuadRow, 0);
@@ -335,6 +336,9 @@ struct HostTables {
         t.bw_len = len; t.bw_primer = prim; t.bw_row = row; t.bw_valid = valid; t.bw_list = list; t.beq = eq;
     }
 
+    // A/B switch (SMX_BARCODE_QUAD=1: narrow words of <= 8 barcodes take four work entries to a thread).  Off by
+    // default: measured slower than the one-entry-per-thread task on config 2 (224 vs 197 us, profiles/r2_k_ab.md)
+    static bool quad_enabled() { const char *e = getenv("SMX_BARCODE_QUAD"); return e && atoi(e) != 0; }
     void set_quad_pointers(const i32 *row, const u32 *quad) { t.bt_quad_row = row; t.bt_quad = quad; }
 
     void set_code_pointers(const unsigned char *codes, const u32 *off, const u32 *iupac) {

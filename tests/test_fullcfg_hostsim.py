@@ -15,3 +15,10 @@ import helpers as H
 def test_records_equal_multiprocess_oracle(cfg, n, flags, kw):
     fig = fullcfg.compare(cfg, n, flags, binding=H.hostsim_binding(), processes=2, **kw)
     assert fig["records"] >= n
+
+
+def test_quad_barcode_form_equals_oracle_on_the_simulator(monkeypatch):
+    """SMX_BARCODE_QUAD=1: narrow barcode words take four work entries to a thread (off by default)."""
+    monkeypatch.setenv("SMX_BARCODE_QUAD", "1")
+    fig = fullcfg.compare("ont037", 1200, {"trim": "primers"}, binding=H.hostsim_binding(), processes=2, sprinkle=4000)
+    assert fig["records"] >= 1200

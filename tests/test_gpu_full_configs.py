@@ -67,3 +67,15 @@ def test_tie_storm_rare_device_paths(derep, tiny, monkeypatch):
     _report(fig)
     if derep == "best":
         assert fig["multi_record_reads"] > 0.05 * fig["reads"]
+
+
+@pytest.mark.parametrize("cfg,n,flags", [("ont037", 60_000, {"trim": "primers"}), ("multipool", 40_000, {"trim": "tails"})])
+def test_switched_off_kernel_forms_still_match_oracle(cfg, n, flags, monkeypatch):
+    """The bit-sliced start recovery (k_primer_start_sliced) and the four-entries-to-a-word barcode task (k_barcode_quad)
+    are off by default (slower on the box, profiles/r2_k_ab.md); they stay in the library behind their switches and
+    have to stay exact."""
+    monkeypatch.setenv("SMX_START_SLICED", "1")
+    monkeypatch.setenv("SMX_BARCODE_QUAD", "1")
+    fig = fullcfg.compare(cfg, n, flags, sprinkle=5000)
+    _report(fig)
+    assert fig["matched"] > 0.8 * fig["reads"]
