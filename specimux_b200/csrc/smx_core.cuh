@@ -452,11 +452,19 @@ struct EndInfo {            // one (strand, primer) slot as seen by a candidate 
 };
 static_assert(sizeof(EndInfo) == 40, "EndInfo layout");
 
+// Gathered equal-best barcode list of one end (see gather_best).
+constexpr int kBestCache = 12;
+struct BestList {
+    short n;                               // -1: not gathered yet, -2: more than kBestCache (walk the lists instead)
+    unsigned short j[kBestCache];
+};
+
 struct SelectCtx {
     const Tables *t;
     const Batch *b;
     u32 read;
     int n;
+    BestList *best = nullptr;              // optional [2 * n_primers] cache, entries start at n = -1 (general selection)
 };
 
 SMX_HD u32 slot_index(const Tables &t, int strand, int primer) { return (u32)(strand * t.n_primers + primer); }
@@ -502,14 +510,14 @@ SMX_HD bool next_hit(const SelectCtx &c, int strand, int primer, int after_j, sm
 // first of them (pinned order) is the smallest list position, and its location is the earliest one
 // carrying that hit.  nhits counts hits (only zero / non-zero is ever used); nbest is exact for a
 // single location and saturates at 2 otherwise (only 0 / 1 / more is ever used).
-SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &o) {
+SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &o, u32 e0, u32 nloc,
+                           const BarcodeDigest *d0 = nullptr) {
+    // e0 / nloc: the slot's first work entry and its number of equal-best primer ends (loaded by the caller, so that a
+    // caller with several slots can have all of those loads in flight at once); d0: the digest of (entry e0, the
+    // primer's first task) if the caller fetched it ahead as well.
     o.first_mask = 0; o.first_ss = 0; o.first_best = 0; o.nhits = 0; o.nbest = 0; o.bd = -1; o.pad = 0;
     const Tables &t = *c.t;
     const Batch &b = *c.b;
-    const u32 slot = (u32)(strand * t.n_primers + primer);
-    const u64 hidx = (u64)slot * b.n_pad + c.read;
-    const u32 e0 = b.ent_base[hidx];
-    u32 nloc = b.phit[hidx].n_locations;
     if (e0 >= b.e_cap) return;
     if (e0 + nloc > b.e_cap) nloc = b.e_cap - e0;
     int bd = 1 << 20, count = 0, jmin = 1 << 20, jmax = -1;
@@ -517,7 +525,8 @@ SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &
     for (u32 l = 0; l < nloc; ++l) {
         const u64 e = (u64)e0 + l;
         for (u32 tk = t.bt_off[primer]; tk < t.bt_off[primer + 1]; ++tk) {
-            const BarcodeDigest d = b.bdig[((u64)strand * t.n_btasks + tk) * b.e_cap + e];
+            const BarcodeDigest d = (d0 && l == 0 && tk == t.bt_off[primer])
+                                        ? *d0 : b.bdig[((u64)strand * t.n_btasks + tk) * b.e_cap + e];
             if (!d.nhits) continue;
             nhits += d.nhits;
             if (d.bd < bd) { bd = d.bd; count = 0; jmin = 1 << 20; jmax = -1; }
@@ -537,19 +546,60 @@ SMX_HD void summarize_slot(const SelectCtx &c, int strand, int primer, SlotSum &
     o.nbest = (unsigned short)(nbest > 65535 ? 65535 : nbest);
 }
 
-SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
-    const Tables &t = *c.t;
-    const u64 idx = (u64)slot_index(t, strand, primer) * c.b->n_pad + c.read;
-    const smx_primer_hit &ph = c.b->phit[idx];
+// EndInfo of one slot from its (already loaded) primer hit, first work entry and, optionally, first digest.
+SMX_HD void fill_end(const SelectCtx &c, int strand, int primer, const smx_primer_hit &ph, u32 e0, const BarcodeDigest *d0,
+                     EndInfo &e) {
     e.strand = (unsigned char)strand; e.primer = (unsigned char)primer;
     e.matched = ph.distance >= 0;
     e.pd = ph.distance; e.ps = ph.first_start; e.pe = ph.first_end;
     e.nhits = 0; e.bd = -1; e.nbest = 0; e.first_best = -1; e.first_ss = 0; e.first_mask = 0;
     if (!e.matched) return;
     SlotSum ss;
-    summarize_slot(c, strand, primer, ss);
+    summarize_slot(c, strand, primer, ss, e0, ph.n_locations, d0);
     e.nhits = ss.nhits; e.bd = ss.bd; e.nbest = ss.nbest;
     e.first_best = ss.nhits ? (int)ss.first_best : -1; e.first_ss = ss.first_ss; e.first_mask = ss.first_mask;
+}
+
+SMX_HD void load_end(const SelectCtx &c, int strand, int primer, EndInfo &e) {
+    const Tables &t = *c.t;
+    const u64 idx = (u64)slot_index(t, strand, primer) * c.b->n_pad + c.read;
+    const smx_primer_hit ph = c.b->phit[idx];
+    fill_end(c, strand, primer, ph, ph.distance >= 0 ? c.b->ent_base[idx] : 0u, nullptr, e);
+}
+
+// All 2 * NP slots of a read when the number of primers is a compile-time constant: the primer hits and first work
+// entries of every slot are loaded first (2 * NP independent pairs of loads in flight), then the first digest of every
+// matched slot, and only then is anything consumed.  The one-slot-at-a-time form above is a chain of three dependent
+// loads per slot, one slot after the other: 12 round trips to L2 / HBM per read for two primers, and k_select_fast
+// spent most of its time waiting on them (profiles/r2_j: long-scoreboard 14 stalls per issue).
+template <int NP>
+SMX_HD void load_ends_ahead(const SelectCtx &c, EndInfo *ends) {
+    constexpr int NS = 2 * NP;
+    const Tables &t = *c.t;
+    const Batch &b = *c.b;
+    smx_primer_hit ph[NS];
+    u32 e0[NS];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < NS; ++i) {
+        ph[i] = b.phit[(u64)i * b.n_pad + c.read];
+        e0[i] = b.ent_base[(u64)i * b.n_pad + c.read];       // only meaningful where the slot matched
+    }
+    BarcodeDigest d0[NS];
+    bool have[NS];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < NS; ++i) {
+        const int strand = i / NP, primer = i % NP;
+        have[i] = ph[i].distance >= 0 && e0[i] < b.e_cap && t.bt_off[primer] < t.bt_off[primer + 1];
+        if (have[i]) d0[i] = b.bdig[((u64)strand * t.n_btasks + t.bt_off[primer]) * b.e_cap + e0[i]];
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < NS; ++i) fill_end(c, i / NP, i % NP, ph[i], e0[i], have[i] ? &d0[i] : nullptr, ends[i]);
 }
 
 // Equal-best barcodes of an end in pinned order (models.py:116-126 best_b1 / best_b2): the list
@@ -561,6 +611,55 @@ SMX_HD int next_best(const SelectCtx &c, const EndInfo &e, int after_j) {
         if (h.distance == e.bd) return after_j;
     }
     return -1;
+}
+
+// The equal-best barcodes of an end, gathered ONCE: every hit at the end's best distance e.bd, over all of its
+// sub-lists, sorted by list position without duplicates -- the sequence next_best() walks (a barcode's merged distance
+// is the minimum over its hits and e.bd the minimum over all of them, so the barcode is equal-best exactly when one of
+// its hits is at e.bd).  next_best() re-walks every sub-list per call and the general selection calls it in nested
+// loops (dereplication keys, in_none, resolve): for a deferred read that was a chain of hundreds of dependent loads.
+SMX_HD void gather_best(const SelectCtx &c, const EndInfo &e, BestList &bl) {
+    const Tables &t = *c.t;
+    const Batch &b = *c.b;
+    bl.n = 0;
+    if (!e.matched || e.nhits == 0) return;
+    const u32 slot = (u32)(e.strand * t.n_primers + e.primer);
+    const u64 hidx = (u64)slot * b.n_pad + c.read;
+    const u32 e0 = b.ent_base[hidx];
+    u32 nloc = b.phit[hidx].n_locations;
+    if (e0 >= b.e_cap) return;
+    if (e0 + nloc > b.e_cap) nloc = b.e_cap - e0;
+    for (u32 l = 0; l < nloc; ++l) {
+        const u64 en = (u64)e0 + l;
+        for (u32 g = t.bw_off[e.primer]; g < t.bw_off[e.primer + 1]; ++g) {
+            const u64 gslot = (u64)e.strand * t.n_bwords + g;
+            int cnt = b.bh_count[gslot * b.e_cap + en];
+            if (cnt > t.hit_cap) cnt = t.hit_cap;
+            for (int x = 0; x < cnt; ++x) {
+                const smx_barcode_hit &h = b.bh_list[(gslot * t.hit_cap + x) * b.e_cap + en];
+                if (h.distance != e.bd) continue;
+                const unsigned short j = h.barcode;
+                int pos = 0;
+                while (pos < bl.n && bl.j[pos] < j) ++pos;
+                if (pos < bl.n && bl.j[pos] == j) continue;
+                if (bl.n == kBestCache) { bl.n = -2; return; }
+                for (int q = bl.n; q > pos; --q) bl.j[q] = bl.j[q - 1];
+                bl.j[pos] = j;
+                ++bl.n;
+            }
+        }
+    }
+}
+
+// k-th equal-best barcode of end e (list position), -1 past the last: from the gathered list when the context carries
+// a cache (indexed like the EndInfo cache), else by walking on from prev_j.
+SMX_HD int best_at(const SelectCtx &c, const EndInfo &e, int k, int prev_j) {
+    if (c.best) {
+        BestList &bl = c.best[(int)e.strand * c.t->n_primers + (int)e.primer];
+        if (bl.n == -1) gather_best(c, e, bl);
+        if (bl.n >= 0) return k < bl.n ? (int)bl.j[k] : -1;
+    }
+    return next_best(c, e, prev_j);
 }
 
 struct Cand {               // CandidateMatch (models.py:72-95) by reference to its two ends
@@ -732,8 +831,8 @@ SMX_HD void resolve(const SelectCtx &c, const EndInfo &e1, const EndInfo &e2, in
     bool b1 = e1.matched && e1.nhits > 0, b2 = e2.matched && e2.nhits > 0;
     if (e1.matched && e2.matched && b1 && b2) {
         int count = 0, min_row = -1;
-        for (int j1 = next_best(c, e1, -1); j1 >= 0; j1 = next_best(c, e1, j1))
-            for (int j2 = next_best(c, e2, -1); j2 >= 0; j2 = next_best(c, e2, j2))
+        for (int q1 = 0, j1 = best_at(c, e1, 0, -1); j1 >= 0; ++q1, j1 = best_at(c, e1, q1, j1))
+            for (int q2 = 0, j2 = best_at(c, e2, 0, -1); j2 >= 0; ++q2, j2 = best_at(c, e2, q2, j2))
                 spec_all(t, t.pb_barcode[t.pb_off[e1.primer] + j1], t.pb_barcode[t.pb_off[e2.primer] + j2],
                          e1.primer, e2.primer, count, min_row);
         if (count > 1) { sample = min_row; resolution = SMX_RES_MULTIPLE_SPECIMENS; pool = t.spec_pool[min_row]; }
@@ -800,7 +899,9 @@ constexpr unsigned char kFlagDeferred = 8;   // fast-only pass: the read needs t
 // Whole per-read selection.  ends: cache of 2*n_primers EndInfo (index strand*n_primers+primer).
 // kFastOnly = true compiles only the common single-candidate path (no grouping, no list walks,
 // no TAILS fold): reads that need more come back with flags = kFlagDeferred and no record.
-template <bool kFastOnly>
+// NP > 0: the number of primers as a compile-time constant (the caller checked t.n_primers == NP): the slots' loads
+// are then issued ahead (load_ends_ahead); NP = 0: any number, one slot at a time.
+template <bool kFastOnly, int NP = 0>
 SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, u32 out_cap,
                             unsigned char &flags) {
     const Tables &t = *c.t;
@@ -816,8 +917,12 @@ SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore
 
     Geo g = make_geo(n, t.L);
     bool irregular = !g.regular || read_is_flagged(b, c.read);
-    for (int s = 0; s < 2; ++s)
-        for (int p = 0; p < t.n_primers; ++p) load_end(c, s, p, ends[s * t.n_primers + p]);
+    if constexpr (NP > 0) {
+        load_ends_ahead<NP>(c, ends);
+    } else {
+        for (int s = 0; s < 2; ++s)
+            for (int p = 0; p < t.n_primers; ++p) load_end(c, s, p, ends[s * t.n_primers + p]);
+    }
 
     // determine_orientation (demultiplex.py:602-638).  For regular reads the head-window test of a
     // forward-sense primer equals the tail-window match of its reverse complement on the other
@@ -932,8 +1037,8 @@ SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore
         bool full = a.matched && z.matched && a.nhits > 0 && z.nhits > 0;
         bool found = false;
         if (full) {
-            for (int j1 = next_best(c, a, -1); j1 >= 0; j1 = next_best(c, a, j1))
-                for (int j2 = next_best(c, z, -1); j2 >= 0; j2 = next_best(c, z, j2)) {
+            for (int q1 = 0, j1 = best_at(c, a, 0, -1); j1 >= 0; ++q1, j1 = best_at(c, a, q1, j1))
+                for (int q2 = 0, j2 = best_at(c, z, 0, -1); j2 >= 0; ++q2, j2 = best_at(c, z, q2, j2)) {
                     int row = spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + j1],
                                          t.pb_barcode[t.pb_off[z.primer] + j2], a.primer, z.primer);
                     if (row < 0) continue;
@@ -974,8 +1079,8 @@ SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore
             const EndInfo &z = ends[cd.e2];
             bool full = a.matched && z.matched && a.nhits > 0 && z.nhits > 0;
             if (!full) return true;
-            for (int j1 = next_best(c, a, -1); j1 >= 0; j1 = next_best(c, a, j1))
-                for (int j2 = next_best(c, z, -1); j2 >= 0; j2 = next_best(c, z, j2))
+            for (int q1 = 0, j1 = best_at(c, a, 0, -1); j1 >= 0; ++q1, j1 = best_at(c, a, q1, j1))
+                for (int q2 = 0, j2 = best_at(c, z, 0, -1); j2 >= 0; ++q2, j2 = best_at(c, z, q2, j2))
                     if (spec_exact(t, t.pb_barcode[t.pb_off[a.primer] + j1], t.pb_barcode[t.pb_off[z.primer] + j2],
                                    a.primer, z.primer) >= 0)
                         return false;
@@ -995,7 +1100,7 @@ SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore
             int pcnt = (a.matched ? 1 : 0) + (z.matched ? 1 : 0);
             int pdist = (a.matched ? a.pd : 0) + (z.matched ? z.pd : 0);
             int fidx = (a.matched ? t.p_fidx[a.primer] : 0) + (z.matched ? t.p_fidx[z.primer] : 0);
-            for (int jb = next_best(c, be, -1); jb >= 0; jb = next_best(c, be, jb)) {
+            for (int qb = 0, jb = best_at(c, be, 0, -1); jb >= 0; ++qb, jb = best_at(c, be, qb, jb)) {
                 int key = (hb1 ? 0 : (1 << 30)) | (int)t.pb_barcode[t.pb_off[be.primer] + jb];
                 int q = -1;
                 for (int x = 0; x < npg; ++x) if (pg[x].key == key) { q = x; break; }
@@ -1056,9 +1161,10 @@ SMX_HD u32 select_read_impl(const SelectCtx &c, EndInfo *ends, const SelectStore
     return em.count;
 }
 
+template <int NP = 0>
 SMX_HD u32 select_read(const SelectCtx &c, EndInfo *ends, const SelectStore &st, smx_record *out, u32 out_cap,
                        unsigned char &flags) {
-    return select_read_impl<false>(c, ends, st, out, out_cap, flags);
+    return select_read_impl<false, NP>(c, ends, st, out, out_cap, flags);
 }
 
 // Bytes of global scratch one read needs in the second pass.

@@ -14,6 +14,9 @@ constexpr int kInlineRecords = 4;
 // (several equal-best candidates, tied barcodes, TAILS trimming) are appended to defer_list.
 template <int MAXP>
 __global__ void __launch_bounds__(128) k_select_fast(SMX_KARGS) {
+    // (loading all slots ahead -- select_read_impl<true, NP> -- was measured SLOWER here: 93 vs 80 us, 62 vs 38
+    // registers; the kernel lives on occupancy, profiles/r2_l_ab.md)
+    constexpr int NP = 0;
     u32 read = blockIdx.x * blockDim.x + threadIdx.x;
     bool defer = false;
     if (read < b.n_reads) {
@@ -25,7 +28,7 @@ __global__ void __launch_bounds__(128) k_select_fast(SMX_KARGS) {
         st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = 1;
         SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
         unsigned char flags;
-        u32 cnt = select_read_impl<true>(c, ends, st, &rec, 1, flags);
+        u32 cnt = select_read_impl<true, NP>(c, ends, st, &rec, 1, flags);
         defer = (flags & kFlagDeferred) != 0;
         if (!defer) {
             b.rec_count[read] = cnt;
@@ -54,38 +57,47 @@ __global__ void __launch_bounds__(128) k_select_fast(SMX_KARGS) {
 template <int MAXP>
 __global__ void __launch_bounds__(128) k_select(SMX_KARGS) {
     // The routine is long and branchy: when few reads are deferred they are spread one per 8 lanes
-    // so that a warp serialises 4 divergent reads instead of 32.
+    // so that a warp serialises 4 divergent reads instead of 32.  The grid is a fixed few blocks per SM walking the
+    // list in strides (a grid over all reads spent a fifth of the kernel's instructions on threads that only looked
+    // at the count and left, profiles/r2_j).
+    constexpr int NP = MAXP <= 4 ? MAXP : 0;
     const u32 n_def = (u32)b.counters[kCtrDeferred];
-    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool spread = (u64)n_def * 8 <= (u64)gridDim.x * blockDim.x;
-    if (spread && (tid & 7)) return;
-    const u32 i = spread ? tid >> 3 : tid;
-    if (i >= n_def) return;
-    const u32 read = b.defer_list[i];
-    EndInfo ends[2 * MAXP];
-    Group groups[kSmallGroups], pg[kSmallGroups];
-    Cand gcand[kSmallGroups], pcand[kSmallGroups];
-    int ts_cand[kSmallGroups], ts_shift[kSmallGroups];
-    smx_record local[kInlineRecords];
-    SelectStore st;
-    st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
-    st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
-    SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
-    unsigned char flags;
-    u32 cnt = select_read(c, ends, st, local, kInlineRecords, flags);
-    if (cnt > kInlineRecords) flags |= 2;
-    b.rec_count[read] = cnt;
-    b.read_flags[read] = flags;
-    if (flags & 2) {                                    // second pass: listed on the device, no host round trip
-        b.big_list[atomicAdd((unsigned int *)&b.counters[kCtrBig], 1u)] = read;
-        return;
-    }
-    if (cnt >= 1) b.rec_stage[read] = local[0];
-    if (cnt >= 2) {
-        u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt - 1);
-        b.rec_extra[read] = base;
-        if (base + cnt - 1 <= b.pool_cap)
-            for (u32 i2 = 1; i2 < cnt; ++i2) b.rec_pool[base + i2 - 1] = local[i2];
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
+    // lanes per read: a whole warp when the list is short enough (divergent reads of one warp run one after the other,
+    // and a read is ~3 k dependent instructions: four to a warp was a 12 k-instruction chain, 50 us), else 8, else 1
+    const u32 shift = (u64)n_def * 32 <= (u64)total ? 5u : (u64)n_def * 8 <= (u64)total ? 3u : 0u;
+    if (tid & ((1u << shift) - 1u)) return;
+    const u32 first = tid >> shift, step = total >> shift;
+    for (u32 i = first; i < n_def; i += step) {
+        const u32 read = b.defer_list[i];
+        EndInfo ends[2 * MAXP];
+        Group groups[kSmallGroups], pg[kSmallGroups];
+        Cand gcand[kSmallGroups], pcand[kSmallGroups];
+        int ts_cand[kSmallGroups], ts_shift[kSmallGroups];
+        BestList best[2 * MAXP];
+        smx_record local[kInlineRecords];
+        SelectStore st;
+        st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
+        st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
+        SelectCtx c; c.t = &c_tables; c.b = &b; c.read = read; c.n = (int)b.lengths[read];
+        for (int q = 0; q < 2 * c_tables.n_primers; ++q) best[q].n = -1;
+        c.best = best;
+        unsigned char flags;
+        u32 cnt = select_read<NP>(c, ends, st, local, kInlineRecords, flags);
+        if (cnt > kInlineRecords) flags |= 2;
+        b.rec_count[read] = cnt;
+        b.read_flags[read] = flags;
+        if (flags & 2) {                                    // second pass: listed on the device, no host round trip
+            b.big_list[atomicAdd((unsigned int *)&b.counters[kCtrBig], 1u)] = read;
+            continue;
+        }
+        if (cnt >= 1) b.rec_stage[read] = local[0];
+        if (cnt >= 2) {
+            u32 base = atomicAdd((unsigned int *)&b.counters[6] + 1, cnt - 1);
+            b.rec_extra[read] = base;
+            if (base + cnt - 1 <= b.pool_cap)
+                for (u32 i2 = 1; i2 < cnt; ++i2) b.rec_pool[base + i2 - 1] = local[i2];
+        }
     }
 }
 
@@ -325,6 +337,19 @@ __global__ void __launch_bounds__(256) k_int_peak(u32 *out, int iters, u32 seed)
     if (r == 0x12345678u) out[0] = r;       // practically never; keeps the chains alive
 }
 
+// SMs of the current device (cached per device ordinal).
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 cudaError_t launch_select_fast(const Tables &t, const Batch &b, cudaStream_t st) {
     const unsigned blocks = (b.n_reads + 127) / 128;
     if (t.n_primers <= 8) k_select_fast<8><<<blocks, 128, 0, st>>>(t, b);
@@ -334,8 +359,12 @@ cudaError_t launch_select_fast(const Tables &t, const Batch &b, cudaStream_t st)
 }
 
 cudaError_t launch_select(const Tables &t, const Batch &b, cudaStream_t st) {
-    const unsigned blocks = (b.n_reads + 127) / 128;
-    if (t.n_primers <= 8) k_select<8><<<blocks, 128, 0, st>>>(t, b);
+    // a fixed grid (a few blocks per SM) strides over the deferred list, whose length only the device knows
+    unsigned blocks = (b.n_reads + 127) / 128;
+    const unsigned cap = 6u * (unsigned)sm_count();
+    if (blocks > cap) blocks = cap;
+    if (t.n_primers == 2) k_select<2><<<blocks, 128, 0, st>>>(t, b);
+    else if (t.n_primers <= 8) k_select<8><<<blocks, 128, 0, st>>>(t, b);
     else if (t.n_primers <= 64) k_select<64><<<blocks, 128, 0, st>>>(t, b);
     else k_select<SMX_MAX_PRIMERS><<<blocks, 128, 0, st>>>(t, b);
     return cudaGetLastError();

@@ -313,18 +313,29 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
         SelectStore st;
         st.groups = groups; st.gcand = gcand; st.pg = pg; st.pcand = pcand;
         st.ts_cand = ts_cand; st.ts_shift = ts_shift; st.cap = kSmallGroups;
+        // the kernels' dispatch: a compile-time primer count (slots loaded ahead) for 1..4 primers; the general pass
+        // carries the equal-best list cache, the second pass on the big scratch walks the lists
+        const int np = t.n_primers;
         {   // the fast-only pass first, exactly as k_select_fast does; deferred reads take the general routine
             SelectStore fst = st;
             fst.cap = 1;
             smx_record one;
-            u32 fc = select_read_impl<true>(c, ends, fst, dst ? &one : nullptr, 1, f);
+            u32 fc = np == 1 ? select_read_impl<true, 1>(c, ends, fst, dst ? &one : nullptr, 1, f)
+                   : np == 2 ? select_read_impl<true, 2>(c, ends, fst, dst ? &one : nullptr, 1, f)
+                   : np == 3 ? select_read_impl<true, 3>(c, ends, fst, dst ? &one : nullptr, 1, f)
+                   : np == 4 ? select_read_impl<true, 4>(c, ends, fst, dst ? &one : nullptr, 1, f)
+                             : select_read_impl<true>(c, ends, fst, dst ? &one : nullptr, 1, f);
             if (!(f & kFlagDeferred)) {
                 if (dst && fc) dst[0] = one;
                 f &= 1;
                 return fc;
             }
         }
-        u32 cnt = select_read(c, ends, st, dst, 0xFFFFFFFFu, f);
+        std::vector<BestList> best(2 * (size_t)np);
+        for (auto &bl : best) bl.n = -1;
+        c.best = best.data();
+        u32 cnt = np == 2 ? select_read<2>(c, ends, st, dst, 0xFFFFFFFFu, f) : select_read(c, ends, st, dst, 0xFFFFFFFFu, f);
+        c.best = nullptr;
         if (f & 2) {            // second pass on the big scratch, as k_select_big does
             EndInfo *bends;
             SelectStore bst = big_store(big.data(), bends);
