@@ -457,8 +457,7 @@ def main():
                      "survey_8d_model_tops": k_model[k] / (kt[k] / 1000.0) / 1e12 if kt[k] > 0 else 0.0}
         achieved = dp[dom_name]["achieved"]
         # ncu figures (executed ALU-pipe utilisation, DRAM bytes) only when the committed capture is of THIS build
-        with open(_lib.LIB_PATH, "rb") as fh:
-            build_id = hashlib.sha1(fh.read()).hexdigest()[:16]
+        build_id = _lib.source_id()          # identity of the library's sources (a rebuild of the same code keeps it)
         ncu_static = {}
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_latest.json")) as fh:

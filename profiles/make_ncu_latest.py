@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """raw.csv (ncu -i X.ncu-rep --page raw --csv) -> profiles/ncu_latest.json: per stage kernel of ONE step, the
 figures bench.py quotes beside its live timings (executed ALU-pipe utilisation, DRAM bytes per launch).
-The json carries the sha1 prefix of the library the capture was taken from (`build_id`); bench.py quotes these figures
-only when it is running that very build.
+The json carries the sha1 prefix of the library SOURCES the capture was taken from (`build_id`, _lib.source_id()); bench.py quotes these figures
+only when it is running a library built from those very sources.
 usage: make_ncu_latest.py raw.csv "capture description" [path/to/libspecimux_b200.so] > profiles/ncu_latest.json"""
 import csv
 import hashlib
@@ -48,10 +48,9 @@ def main(path, capture, lib_path=None):
         d["issue_active_pct"] = sum(d.pop("_issue")) / d["launches"]
         t_all += d["duration_us"]
         a_all += d["duration_us"] * d["alu_pipe_pct"]
-    lib_path = lib_path or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "specimux_b200",
-                                        "libspecimux_b200.so")
-    with open(lib_path, "rb") as fh:
-        build_id = hashlib.sha1(fh.read()).hexdigest()[:16]
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from specimux_b200 import _lib
+    build_id = _lib.source_id()             # sources of the library the capture ran (bench.py compares the same id)
     json.dump({"capture": capture, "build_id": build_id, "step_us": t_all,
                "whole_step_alu_pipe_pct": a_all / t_all if t_all else None,
                "whole_step_dram_bytes": sum(d["dram_bytes"] for d in out.values()), "kernels": out}, sys.stdout, indent=1)

@@ -147,6 +147,24 @@ def ptr(arr, typ):
     return arr.ctypes.data_as(typ)
 
 
+def source_id() -> str:
+    """sha1 prefix over the sources libspecimux_b200.so is built from (csrc/*.cu|cuh|hpp, the Makefile, include/*.h): the
+    identity a committed ncu capture is stamped with, so that bench.py quotes its figures only for the same code --
+    independent of where and when the library was compiled."""
+    import glob
+    import hashlib
+    here = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(here, "csrc", "*.cu")) + glob.glob(os.path.join(here, "csrc", "*.cuh")) +
+                   glob.glob(os.path.join(here, "csrc", "*.hpp")) + [os.path.join(here, "csrc", "Makefile")] +
+                   glob.glob(os.path.join(here, "..", "include", "*.h")))
+    h = hashlib.sha1()
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 class HostBuffer:
     """numpy view over pinned host memory (cudaHostAlloc through the library); falls back to ordinary
     pageable memory when no GPU driver is present (packing still works on a CPU-only box).

@@ -42,12 +42,17 @@ int fail(int code, const char *fmt, ...) {
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    // The first allocation is exact; a buffer that has to GROW takes a quarter more than asked: cudaFree / cudaMalloc
+    // synchronise the device, and a stream of batches of slightly different sizes (the file pipeline's byte-range
+    // chunks) would otherwise reallocate every buffer of a lane each time a new largest batch comes by.
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        size_t want = n;
+        if (p) { cudaFree(p); want = n + n / 4; }
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess && want != n) { (void)cudaGetLastError(); want = n; e = cudaMalloc((void **)&p, want * sizeof(T)); }
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(32) k_select_big(SMX_KARGS, const u32 *list, u
 // value (32 bits).  The epoch changes with every launch, so the status array is never cleared.
 constexpr int kScanThreads = 256;
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_compact(SMX_KARGS, u32 rec_cap, unsigned long long *tile_status,
+__global__ void __launch_bounds__(kScanThreads, 6) k_scan_compact(SMX_KARGS, u32 rec_cap, unsigned long long *tile_status,
                                                                u32 *ticket, u32 ticket_base, u32 epoch) {
     __shared__ u32 s_off[kScanTile + 1];
     __shared__ unsigned char s_big[kScanTile];

@@ -4,6 +4,7 @@
 missing library raises ImportError, a missing GPU raises SmxError(SMX_ERR_NO_DEVICE).
 """
 import ctypes as C
+import os
 import threading
 from typing import List, Optional, Sequence
 
@@ -37,6 +38,20 @@ class PackedBatch:
         `reuse`: a PackedBatch whose pinned buffers are recycled when they are large enough."""
         self = reuse if reuse is not None else cls.__new__(cls)
         self._init_from_blob(block.bases_ptr or b"", block.seq_off(), clip)
+        return self
+
+    @classmethod
+    def reserve(cls, n_reads: int, clip: int):
+        """An empty batch whose pinned buffers already hold `n_reads` clipped reads: a pipeline that re-packs into
+        it (from_block(..., reuse=...)) then never allocates or frees pinned memory while the GPU is busy --
+        cudaHostAlloc / cudaFreeHost synchronise with every device of the process."""
+        self = cls.__new__(cls)
+        if clip:
+            stride = int(_lib.load().smx_pack_stride(clip))
+            self._buffer(0, n_reads * stride + 1, np.uint32)
+            for slot, dt in ((2, np.uint32), (3, np.uint64), (4, np.uint16)):
+                self._buffer(slot, max(n_reads, 1), dt)
+        self.n_reads = 0
         return self
 
     def _buffer(self, slot, count, dtype):
@@ -123,10 +138,15 @@ class BatchResult:
 
 
 class Matcher:
-    """One device context.  `binding` lets the unit tests drive the same code through the CPU
-    kernel simulator (tests/hostsim); the product never passes it."""
+    """One device context.  `binding` lets the unit tests drive the same host code through the CPU
+    kernel simulator (tests/hostsim); the product never passes it, and it is refused unless the test suite
+    has opened the seam (SMX_TEST_SEAM=1, set by tests/conftest.py): there is no CPU execution route
+    through the product API."""
 
     def __init__(self, tables, device: int = 0, binding=None):
+        if binding is not None and os.environ.get("SMX_TEST_SEAM") != "1":
+            raise RuntimeError("specimux_b200: the simulator binding is a test seam (SMX_TEST_SEAM=1); "
+                               "the matching runs on the GPU only")
         self.tables = tables
         self._binding = binding
         self._ctx = C.c_void_p(None)
@@ -167,10 +187,14 @@ class Matcher:
             # reuse=True: one pool per Matcher; reuse=<dict>: a pool owned by the caller (lets several
             # results stay alive, e.g. while a writer thread still formats an earlier batch)
             pool = reuse if isinstance(reuse, dict) else self.__dict__.setdefault("_result_pool", {})
+            # grown geometrically: every growth is a cudaHostAlloc + (later) cudaFreeHost, and both synchronise with
+            # the devices -- batches of slightly different sizes must not reallocate each time
             if pool.get("n", -1) < n + 1:
-                pool["n"], pool["off"] = n + 1, _lib.HostBuffer(n + 1, np.uint32)
+                grown = n + 1 if "n" not in pool else n + n // 4 + 1024
+                pool["n"], pool["off"] = grown, _lib.HostBuffer(grown, np.uint32)
             if pool.get("cap_" + rec_key, -1) < cap:
-                pool["cap_" + rec_key], pool[rec_key] = cap, _lib.HostBuffer(cap, rec_dtype)
+                grown = cap if ("cap_" + rec_key) not in pool else cap + cap // 4 + 1024
+                pool["cap_" + rec_key], pool[rec_key] = grown, _lib.HostBuffer(grown, rec_dtype)
             rec_offset = pool["off"].array[:n + 1]
             records = pool[rec_key].array[:cap]
         else:
@@ -211,6 +235,10 @@ class Matcher:
         if lh is not None:
             out.barcode_loc_hits = lh[:min(int(res.n_barcode_loc_hits), len(lh))]
         return out
+
+    def reserve_results(self, pool: dict, n: int, compact=False):
+        """Sizes a caller-owned pinned result pool for batches of up to `n` reads ahead of the first match."""
+        self._alloc_results(int(n), False, None, pool, compact)
 
     # -- whole path with host buffers (H2D + kernels + D2H) ---------------------------------
     def match(self, batch: PackedBatch, detail: bool = False, reuse=False, compact: bool = False) -> BatchResult:

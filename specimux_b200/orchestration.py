@@ -184,6 +184,7 @@ def _run(args, multi: bool):
     if _native_eligible(args):
         create_output_files(args, specimens)
         start = timeit.default_timer()
+        n_gpus = _gpus_worth_starting(args, n_gpus)
         logging.info(f"Will run on {n_gpus} GPU(s), {GPU_BATCH_READS} reads per batch, native reader/writer")
         total, matched = _run_native(args, specimens, parameters, n_gpus, prefilter)
         if total > 0:
@@ -269,6 +270,26 @@ def _native_eligible(args) -> bool:
     return not args.diagnostics and os.environ.get("SMX_NATIVE_IO", "1") != "0"
 
 
+def _gpus_worth_starting(args, n_gpus: int) -> int:
+    """GPUs the file pipeline starts for this input.  One B200 matches ~25x faster than the host side reads, packs and
+    writes (SMX_IO_TRACE=1: 0.04 s of GPU work in a 0.47 s run of 765 k reads), while every further device context
+    costs ~0.5 s of start-up inside the timed run (measured: -t 2 took 1.6 s where -t 1 took 0.47 s,
+    profiles/r2_o_file_to_tree.md).  A further GPU is therefore started per SMX_BYTES_PER_GPU bytes of input
+    (default 8 GiB; gzip input counts four-fold), never more than asked for with -t."""
+    per_gpu = max(1, int(os.environ.get("SMX_BYTES_PER_GPU", str(8 << 30))))
+    try:
+        size = os.path.getsize(args.sequence_file)
+    except OSError:
+        return n_gpus
+    if args.sequence_file.endswith((".gz", ".gzip")):
+        size *= 4
+    want = max(1, -(-size // per_gpu))
+    if want < n_gpus:
+        logging.info(f"Input of {size >> 20} MiB: starting {want} of {n_gpus} GPU(s) "
+                     f"(one more per {per_gpu >> 20} MiB, SMX_BYTES_PER_GPU)")
+    return min(n_gpus, want)
+
+
 def _reader_chunk_bytes() -> int:
     """Bytes of the FASTQ file one parser thread takes at a time = one GPU batch (SMX_READER_CHUNK_BYTES).  Small
     enough that the ring of job slots (blocks + pinned buffers) is re-used many times over a file: a slot's first
@@ -290,26 +311,28 @@ def _reader_threads(n_gpus: int) -> int:
     return max(1, min(8, cores // 4))
 
 
-def _parallel_read_ok(args, path: str, is_fastq: bool) -> bool:
+def _parallel_read_ok(args, path: str, is_fastq: bool) -> float:
     """The byte-range reader needs a plain (not gzip) FASTQ file in the usual four-line layout, read from its first
-    record to its end; the head of the file is checked for the layout."""
+    record to its end; the head of the file is checked for the layout.  Returns the mean bytes per record of the
+    head (the pipeline sizes its pinned buffers from it), 0.0 when the file does not qualify."""
     if not is_fastq or path.endswith((".gz", ".gzip")) or args.num_seqs >= 0 or getattr(args, "start_seq", 1) > 1:
-        return False
+        return 0.0
     if os.environ.get("SMX_PARALLEL_READER", "1") == "0":
-        return False
+        return 0.0
     try:
         if os.path.getsize(path) < 2 * _reader_chunk_bytes():
-            return False
+            return 0.0
         with open(path, "rb") as fh:
             lines = fh.read(1 << 20).split(b"\n")[:-1]
     except OSError:
-        return False
+        return 0.0
     if len(lines) < 8:
-        return False
-    for i in range(0, len(lines) - len(lines) % 4, 4):
+        return 0.0
+    n4 = len(lines) - len(lines) % 4
+    for i in range(0, n4, 4):
         if not (lines[i].startswith(b"@") and lines[i + 2].startswith(b"+") and len(lines[i + 1]) == len(lines[i + 3])):
-            return False
-    return True
+            return 0.0
+    return (sum(len(x) for x in lines[:n4]) + n4) / (n4 // 4)
 
 
 def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=None):
@@ -328,10 +351,18 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
 
     fmt = detect_file_format(args.sequence_file)
     args.isfastq = fmt == "fastq"
-    matchers = [get_matcher(parameters, specimens, args, prefilter, dev, _binding) for dev in range(n_gpus)]
+    if n_gpus > 1:
+        # device contexts come up side by side (each is ~0.5 s of driver work)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=n_gpus) as ex:
+            matchers = list(ex.map(lambda dev: get_matcher(parameters, specimens, args, prefilter, dev, _binding),
+                                   range(n_gpus)))
+    else:
+        matchers = [get_matcher(parameters, specimens, args, prefilter, 0, _binding)]
     writer = TreeWriter(args.output_dir if args.output_to_files else None, args.output_file_prefix, args.isfastq,
                         matchers[0].tables)
-    parallel = _parallel_read_ok(args, args.sequence_file, args.isfastq)
+    record_bytes = _parallel_read_ok(args, args.sequence_file, args.isfastq)
+    parallel = record_bytes > 0
     chunk_bytes = _reader_chunk_bytes()
     n_parsers = _reader_threads(n_gpus) if parallel else 1
 
@@ -346,6 +377,16 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
     free = queue.Queue()
     for _ in range(n_jobs):
         free.put(Job())
+    # Every job slot's pinned buffers (packed reads in, records out) are sized ONCE, before any GPU work: pinned
+    # allocation and release synchronise with every device of the process, and a slot that grew its buffers in
+    # the middle of a run stalled all feeder threads (with two GPUs: 0.9 s one run, 2.6 s the next).
+    reads_hint = int(chunk_bytes / record_bytes * 1.25) + 1024 if parallel else GPU_BATCH_READS
+    if _binding is None:
+        for _ in range(n_jobs):
+            job = free.get()
+            job.batch = PackedBatch.reserve(reads_hint, parameters.search_len)
+            matchers[0].reserve_results(job.pool, reads_hint, compact="wire")
+            free.put(job)
     gpu_q = [queue.Queue() for _ in range(n_gpus)]
     errors = []
     counts = [0, 0]

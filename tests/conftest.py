@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("SMX_TEST_SEAM", "1")      # opens the simulator seam of specimux_b200.engine.Matcher (tests only)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

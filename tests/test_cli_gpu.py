@@ -143,7 +143,9 @@ def test_two_gpus_give_the_same_tree_as_one(tmp_path):
     for route in ("1", "0"):
         for t in ("1", "2"):
             out = str(tmp_path / ("out_%s_%s" % (route, t)))
-            env = dict(os.environ, SMX_NATIVE_IO=route, SMX_GPU_BATCH_READS="4096")
+            # SMX_BYTES_PER_GPU=1: start every GPU asked for (the default policy starts one per 8 GiB of input)
+            env = dict(os.environ, SMX_NATIVE_IO=route, SMX_GPU_BATCH_READS="4096", SMX_BYTES_PER_GPU="1",
+                       SMX_READER_CHUNK_BYTES=str(1 << 20))
             r = subprocess.run([sys.executable, "-m", "specimux_b200.cli", p, s, q, "-F", "-O", out, "-t", t],
                                capture_output=True, text=True, cwd=H.ROOT, timeout=900, env=env)
             assert r.returncode == 0, r.stderr

@@ -139,3 +139,12 @@ def test_parsers(tmp_path):
     recs = list(parse(str(fq), "fastq"))
     assert [(r.id, r.description, r.seq, r.qual) for r in recs] == [("id1", "id1 extra words", "ACGT", "IIII"),
                                                                     ("id2", "id2", "ACGT", "IIII")]
+
+
+def test_simulator_seam_is_closed_outside_the_test_suite(monkeypatch):
+    """The `binding` argument is a test seam: without SMX_TEST_SEAM=1 the product API refuses it (no CPU execution
+    route through process_sequences / Matcher)."""
+    from specimux_b200.engine import Matcher
+    monkeypatch.delenv("SMX_TEST_SEAM", raising=False)
+    with pytest.raises(RuntimeError, match="test seam"):
+        Matcher(None, binding=object())

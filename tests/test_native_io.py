@@ -304,7 +304,7 @@ def test_parallel_reader_gives_the_serial_tree(tmp_path, monkeypatch, chunk, thr
         monkeypatch.setenv("SMX_PARALLEL_READER", "0" if mode == "serial" else "1")
         monkeypatch.setenv("SMX_READER_CHUNK_BYTES", str(chunk))
         monkeypatch.setenv("SMX_READER_THREADS", str(threads))
-        assert orchestration._parallel_read_ok(args, fq, True) == (mode == "parallel")
+        assert bool(orchestration._parallel_read_ok(args, fq, True)) == (mode == "parallel")
         total, matched = orchestration._run_native(args, specimens, params, 1, H.prefilter_for(args),
                                                    _binding=H.hostsim_binding())
         assert total == 700

@@ -6,7 +6,7 @@ OUT=gpurun_out; mkdir -p $OUT
 i=0
 for envs in "$@"; do
   echo "== $envs"
-  env $envs timeout 300 python bench.py --no-cpu-baseline --no-file-to-tree > $OUT/ab_${TAG}_$i.json 2> $OUT/ab_${TAG}_$i.err; echo "rc=$?"
+  env $envs timeout 300 python bench.py --no-cpu-baseline --no-file-to-tree $BENCH_ARGS > $OUT/ab_${TAG}_$i.json 2> $OUT/ab_${TAG}_$i.err; echo "rc=$?"
   python - <<PY
 import json
 d=json.loads(open("$OUT/ab_${TAG}_$i.json").read().strip().splitlines()[-1])

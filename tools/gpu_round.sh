@@ -3,7 +3,7 @@
 # usage (from the repo root, on the GPU box): bash tools/gpu_round.sh TAG [skip-tests]
 TAG=${1:-dev}
 # 9 kernels per resident step on one lane (stage, sliced x 2 primers, finish, start, barcode, 2 x select, scan_compact); skip = split pass (warm-up + step) + attribution warm-up
-SKIP=${SKIP:-33}
+SKIP=${SKIP:-27}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L
