@@ -263,15 +263,17 @@ def run_reference(args):
 def file_to_tree(args, ds, n_reads, n_gpus):
     """BASELINE.json's whole-box metric: the workload as a FASTQ file on local disk -> finished output tree through
     this package's own CLI (`python -m specimux.cli ... -F -t <n_gpus>`), timed by the CLI's 'Elapsed time' clock
-    exactly as the reference arm is; the second of two runs is reported (the first warms the page cache)."""
+    exactly as the reference arm is; one warm-up run (page cache), then the median of three runs is reported (a run is
+    ~0.5 s on a shared 16-vCPU VM: single runs scatter by +-0.2 s; all three are listed)."""
     d, files = _workload_files(args.config, ds, n_reads)
     out = os.path.join(d, "out_b200")
-    runs = [_run_cli([ROOT], files, out, ["-t", str(n_gpus)], 900) for _ in range(2)]
-    n_done, el, wall = runs[-1]
+    runs = [_run_cli([ROOT], files, out, ["-t", str(n_gpus)], 900) for _ in range(4)][1:]
+    n_done, el, wall = sorted(runs, key=lambda r: r[1])[1]
     size = os.path.getsize(files[2])
     import shutil
     shutil.rmtree(out, ignore_errors=True)
     return {"value": n_done / el, "unit": "reads/s", "n_gpus": n_gpus, "reads": n_done, "elapsed_s": el, "process_wall_s": wall,
+            "elapsed_s_runs": [r[1] for r in runs],
             "fastq_bytes": size, "fastq_gbs": size / el / 1e9,
             "api": "python -m specimux.cli primers.fasta specimens.txt reads.fastq -F -O <dir> -t %d (native reader / packer, "
                    "smx_match_batch per 65,536-read batch, native tree writer)" % n_gpus}

@@ -114,6 +114,17 @@ int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *
  * read indices recovered from the last-of-read flags, trim_end from the reads' lengths. */
 int smx_writer_write16(smx_writer *w, const smx_block *blk, const smx_record16 *records, uint64_t n_records);
 
+/* Deferred form of smx_writer_write16 for a pipeline: returns as soon as the records are planned and handed to the
+ * writer's worker threads, so the caller's next block is planned while this one is still being formatted and
+ * appended.  `blk` must stay valid and unchanged until the NEXT smx_writer_write* / smx_writer_wait /
+ * smx_writer_close call on this writer has returned (each of them first waits for the deferred call); `records` may
+ * be reused at once.  Replaces the per-batch hand-over of the reference's single writer loop
+ * (io_utils.py:452-471 output_write_operation called batch by batch from orchestration.py:181-203). */
+int smx_writer_write16_deferred(smx_writer *w, const smx_block *blk, const smx_record16 *records, uint64_t n_records);
+
+/* Waits for a deferred call to finish.  Returns the first error seen so far, if any. */
+int smx_writer_wait(smx_writer *w);
+
 /* Flushes every buffer and releases the writer.  Returns the first error seen, if any. */
 int smx_writer_close(smx_writer *w);
 

@@ -529,7 +529,14 @@ struct smx_writer {
     // worker pool (file output only): thread t formats the tasks of the files it owns
     int n_threads = 1;
     std::vector<std::thread> threads;
-    std::vector<std::vector<Task>> tasks;             // per thread, in record order
+    // Two sets of planning storage: while the workers format call i from one set, the calling thread plans call i + 1
+    // into the other (smx_writer_write*_deferred).
+    std::vector<std::vector<Task>> task_sets[2];      // per thread, in record order
+    std::vector<Plan> plan_sets[2];
+    std::vector<smx_record> full_sets[2];             // widened records of the 16 / 32-byte forms
+    int next_set = 0;
+    bool in_flight = false;                           // a dispatched call the workers may still be formatting
+    const std::vector<std::vector<Task>> *cur_tasks = nullptr;
     std::vector<uint64_t> thread_bytes;
     std::mutex mu;
     std::condition_variable cv_go, cv_done;
@@ -586,6 +593,8 @@ struct smx_writer {
     }
 
     void format(Bytes &c, const smx_block &blk, const smx_record &rec, const Plan &pl);
+    int write_planned(const smx_block *blk, const smx_record *recs, uint64_t n_records, int set, bool deferred);
+    void wait_in_flight();
     void run_tasks(int t);
     void worker(int t);
     ~smx_writer() { for (Target *t : all_files) delete t; }
@@ -663,7 +672,7 @@ void smx_writer::format(Bytes &c, const smx_block &blk, const smx_record &rec, c
 
 void smx_writer::run_tasks(int t) {
     uint64_t bytes = 0;
-    for (const Task &k : tasks[t]) {
+    for (const Task &k : (*cur_tasks)[(size_t)t]) {
         Bytes &buf = k.dst->file.buf;
         const size_t before = buf.size();
         const Plan &pl = (*cur_plans)[k.rec];
@@ -733,7 +742,7 @@ int smx_writer_open(const char *output_dir, const char *prefix, int is_fastq, co
         }
         w->n_threads = std::min(n, 64);
     }
-    w->tasks.resize((size_t)w->n_threads);
+    for (auto &ts : w->task_sets) ts.resize((size_t)w->n_threads);
     w->thread_bytes.assign((size_t)w->n_threads, 0);
     if (w->n_threads > 1)
         for (int t = 0; t < w->n_threads; ++t) w->threads.emplace_back(&smx_writer::worker, w, t);
@@ -741,12 +750,29 @@ int smx_writer_open(const char *output_dir, const char *prefix, int is_fastq, co
     return SMX_IO_OK;
 }
 
-int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs, uint64_t n_records) {
-    if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write: null argument");
-    if (n_records > 0xFFFFFFFFull) return fail(SMX_IO_ERR_ARG, "smx_writer_write: too many records in one call");
+}  // extern "C"
+
+// Waits for the workers of the last dispatched call (deferred form) and books their byte counts.
+void smx_writer::wait_in_flight() {
+    if (!in_flight) return;
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    for (uint64_t v : thread_bytes) n_bytes += v;
+    cur_blk = nullptr; cur_recs = nullptr; cur_plans = nullptr; cur_tasks = nullptr;
+    in_flight = false;
+}
+
+// Plans `recs` into planning set `set` (this thread; the workers may still be formatting the previous call from the
+// other set), waits for that previous call, hands the new one to the workers and -- unless `deferred` -- waits for it.
+int smx_writer::write_planned(const smx_block *blk, const smx_record *recs, uint64_t n_records, int set, bool deferred) {
+    smx_writer *w = this;
     const uint32_t n_reads = blk->n();
-    std::vector<Plan> plans((size_t)n_records);
-    for (auto &t : w->tasks) t.clear();
+    std::vector<Plan> &plans = plan_sets[set];
+    plans.assign((size_t)n_records, Plan());
+    std::vector<std::vector<Task>> &tasks = task_sets[set];
+    for (auto &t : tasks) t.clear();
     // ---- planning pass (this thread): names, slice bounds, destination files
     for (uint64_t i = 0; i < n_records; ++i) {
         const smx_record &rec = recs[i];
@@ -796,8 +822,9 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
             pl.pool_level = pit != w->files.end() ? pit->second
                           : w->target(pkey, w->dir + "/full/" + *pl.pool + "/" + w->prefix + *sample_file + w->ext, skey);
         }
-        w->tasks[(size_t)pl.primary->owner].push_back(Task{(uint32_t)i, pl.primary, pl.pool_level});
+        tasks[(size_t)pl.primary->owner].push_back(Task{(uint32_t)i, pl.primary, pl.pool_level});
     }
+    wait_in_flight();                                   // the previous call's block and records are free from here on
     w->n_records += n_records;
     // ---- formatting
     if (!w->to_files) {
@@ -808,7 +835,7 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
             if (w->console.size() >= flush_bytes()) { fwrite(w->console.data(), 1, w->console.size(), stdout); w->console.clear(); }
         }
     } else {
-        w->cur_blk = blk; w->cur_recs = recs; w->cur_plans = &plans;
+        w->cur_blk = blk; w->cur_recs = recs; w->cur_plans = &plans; w->cur_tasks = &tasks;
         if (w->n_threads > 1) {
             {
                 std::lock_guard<std::mutex> lk(w->mu);
@@ -816,22 +843,44 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
                 ++w->generation;
             }
             w->cv_go.notify_all();
-            std::unique_lock<std::mutex> lk(w->mu);
-            w->cv_done.wait(lk, [&] { return w->pending == 0; });
+            w->in_flight = true;
+            if (!deferred) wait_in_flight();
         } else {
             try { w->run_tasks(0); } catch (const std::exception &e) { w->note_error(SMX_IO_ERR_IO, e.what()); }
+            for (uint64_t v : w->thread_bytes) w->n_bytes += v;
+            w->cur_blk = nullptr; w->cur_recs = nullptr; w->cur_plans = nullptr; w->cur_tasks = nullptr;
         }
-        for (uint64_t v : w->thread_bytes) w->n_bytes += v;
-        w->cur_blk = nullptr; w->cur_recs = nullptr; w->cur_plans = nullptr;
     }
     if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());
     return SMX_IO_OK;
 }
 
+extern "C" {
+
+int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs, uint64_t n_records) {
+    if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write: null argument");
+    if (n_records > 0xFFFFFFFFull) return fail(SMX_IO_ERR_ARG, "smx_writer_write: too many records in one call");
+    const int set = w->next_set;
+    w->next_set ^= 1;
+    return w->write_planned(blk, recs, n_records, set, false);
+}
+
+int smx_writer_wait(smx_writer *w) {
+    if (!w) return SMX_IO_OK;
+    w->wait_in_flight();
+    if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());
+    return SMX_IO_OK;
+}
+
+
 int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *recs, uint64_t n_records) {
     if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write32: null argument");
+    if (n_records > 0xFFFFFFFFull) return fail(SMX_IO_ERR_ARG, "smx_writer_write32: too many records in one call");
     // widen into the full layout (locations unused by the writer) and take the common path
-    std::vector<smx_record> full((size_t)n_records);
+    const int set = w->next_set;
+    w->next_set ^= 1;
+    std::vector<smx_record> &full = w->full_sets[set];
+    full.resize((size_t)n_records);
     for (uint64_t i = 0; i < n_records; ++i) {
         const smx_record32 &c = recs[i];
         smx_record &r = full[i];
@@ -843,14 +892,18 @@ int smx_writer_write32(smx_writer *w, const smx_block *blk, const smx_record32 *
         r.reverse = c.flags & 1; r.trim_empty = (c.flags >> 1) & 1;
         r.candidate = c.candidate;
     }
-    return smx_writer_write(w, blk, full.data(), n_records);
+    return w->write_planned(blk, full.data(), n_records, set, false);
 }
 
-int smx_writer_write16(smx_writer *w, const smx_block *blk, const smx_record16 *recs, uint64_t n_records) {
+static int write16_common(smx_writer *w, const smx_block *blk, const smx_record16 *recs, uint64_t n_records, bool deferred) {
     if (!w || !blk || (!recs && n_records)) return fail(SMX_IO_ERR_ARG, "smx_writer_write16: null argument");
+    if (n_records > 0xFFFFFFFFull) return fail(SMX_IO_ERR_ARG, "smx_writer_write16: too many records in one call");
     // widen into the full layout: the read index comes from the last-of-read flags (records are in read order),
     // trim_end from the read's length
-    std::vector<smx_record> full((size_t)n_records);
+    const int set = w->next_set;
+    w->next_set ^= 1;
+    std::vector<smx_record> &full = w->full_sets[set];
+    full.resize((size_t)n_records);
     uint32_t read = 0;
     const uint32_t n_reads = blk->n();
     for (uint64_t i = 0; i < n_records; ++i) {
@@ -869,11 +922,20 @@ int smx_writer_write16(smx_writer *w, const smx_block *blk, const smx_record16 *
         r.reverse = (c.flags >> 3) & 1; r.trim_empty = (c.flags >> 4) & 1;
         if (c.flags & 32) ++read;
     }
-    return smx_writer_write(w, blk, full.data(), n_records);
+    return w->write_planned(blk, full.data(), n_records, set, deferred);
+}
+
+int smx_writer_write16(smx_writer *w, const smx_block *blk, const smx_record16 *recs, uint64_t n_records) {
+    return write16_common(w, blk, recs, n_records, false);
+}
+
+int smx_writer_write16_deferred(smx_writer *w, const smx_block *blk, const smx_record16 *recs, uint64_t n_records) {
+    return write16_common(w, blk, recs, n_records, true);
 }
 
 int smx_writer_close(smx_writer *w) {
     if (!w) return SMX_IO_OK;
+    w->wait_in_flight();
     if (!w->threads.empty()) {
         { std::lock_guard<std::mutex> lk(w->mu); w->stop = true; }
         w->cv_go.notify_all();

@@ -23,7 +23,8 @@ strp = C.POINTER(C.c_char_p)
 
 EXPORTS = ["smx_io_abi_version", "smx_io_last_error", "smx_reader_open", "smx_reader_open_range", "smx_reader_close", "smx_block_create",
            "smx_block_destroy", "smx_block_get", "smx_reader_next", "smx_reader_skip", "smx_writer_open",
-           "smx_writer_write", "smx_writer_write32", "smx_writer_write16", "smx_writer_close", "smx_writer_stats"]
+           "smx_writer_write", "smx_writer_write32", "smx_writer_write16", "smx_writer_write16_deferred", "smx_writer_wait",
+           "smx_writer_close", "smx_writer_stats"]
 
 
 class SmxBlockView(C.Structure):
@@ -70,6 +71,8 @@ def load():
         lib.smx_writer_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.smx_writer_write32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.smx_writer_write16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.smx_writer_write16_deferred.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.smx_writer_wait.argtypes = [C.c_void_p]
         lib.smx_writer_close.argtypes = [C.c_void_p]
         lib.smx_writer_stats.argtypes = [C.c_void_p, u64p, u64p]
         lib.smx_writer_stats.restype = None
@@ -252,6 +255,16 @@ class TreeWriter:
         else:
             assert rec.dtype == _lib.RECORD_DTYPE
             _check(self._lib.smx_writer_write(self._h, block.handle, rec.ctypes.data, len(rec)))
+
+    def write_deferred(self, block: ReadBlock, records: np.ndarray):
+        """smx_record16 records only: returns once the records are planned and with the worker threads; `block` must stay
+        untouched until the next write / write_deferred / wait / close call on this writer has returned."""
+        rec = np.ascontiguousarray(records)
+        assert rec.dtype == _lib.RECORD16_DTYPE
+        _check(self._lib.smx_writer_write16_deferred(self._h, block.handle, rec.ctypes.data, len(rec)))
+
+    def wait(self):
+        _check(self._lib.smx_writer_wait(self._h))
 
     def stats(self):
         n, b = C.c_uint64(0), C.c_uint64(0)

@@ -413,30 +413,56 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             job.done.set()
 
     def write_worker():
+        # The hand-over to the writer is deferred: writer.write_deferred() returns once job i is planned and with the
+        # writer's worker threads, and job i's block stays untouched until the NEXT writer call has returned -- so job
+        # i goes back to the free list only after job i + 1 has been handed over (or after the final wait).
         i = 0
-        while True:
-            with order_lock:
-                while i not in slots and not (state["n_chunks"] is not None and i >= state["n_chunks"]):
-                    order_lock.wait()
-                if i not in slots:
-                    return
-                job = slots.pop(i)
-            job.done.wait()
-            try:
-                if job.error is not None:
-                    raise job.error
-                if not errors and job.block.n_reads:
-                    t0 = clock()
-                    writer.write(job.block, job.result.records)
-                    busy["write"] += clock() - t0
-                    counts[0] += job.block.n_reads
-                    counts[1] += job.result.n_matched
-            except BaseException as e:
-                errors.append(e)
-            job.result = job.error = None
-            job.done.clear()
-            free.put(job)
-            i += 1
+        held = None
+        try:
+            while True:
+                with order_lock:
+                    while i not in slots and not (state["n_chunks"] is not None and i >= state["n_chunks"]):
+                        order_lock.wait()
+                    if i not in slots:
+                        return
+                    job = slots.pop(i)
+                job.done.wait()
+                wrote = False
+                try:
+                    if job.error is not None:
+                        raise job.error
+                    if not errors and job.block.n_reads:
+                        t0 = clock()
+                        if job.result.records.dtype == _lib.RECORD16_DTYPE and args.output_to_files:
+                            writer.write_deferred(job.block, job.result.records)
+                            wrote = True
+                        else:
+                            writer.write(job.block, job.result.records)
+                        busy["write"] += clock() - t0
+                        counts[0] += job.block.n_reads
+                        counts[1] += job.result.n_matched
+                except BaseException as e:
+                    errors.append(e)
+                if held is not None:                   # the call above waited for the held job's formatting
+                    release(held)
+                    held = None
+                if wrote:
+                    held = job
+                else:
+                    release(job)
+                i += 1
+        finally:
+            if held is not None:
+                try:
+                    writer.wait()
+                except BaseException as e:
+                    errors.append(e)
+                release(held)
+
+    def release(job):
+        job.result = job.error = None
+        job.done.clear()
+        free.put(job)
 
     def submit(job, index):
         job.index = index

@@ -2,9 +2,9 @@
 # BASELINE.json configs 3-5 at one GPU (per-GPU share of the named read counts) + config 2 at N=2 when two GPUs are visible.
 OUT=gpurun_out
 TAG=${1:-v15}
-python bench.py --config dense --reads 2000000 --cpu-sample 4000 > $OUT/bench_${TAG}_dense.json 2> $OUT/bench_${TAG}_dense.err; tail -c 600 $OUT/bench_${TAG}_dense.err
-python bench.py --config multipool --reads 625000 --cpu-sample 4000 > $OUT/bench_${TAG}_multipool.json 2> $OUT/bench_${TAG}_multipool.err
-python bench.py --config long --reads 1000000 --cpu-sample 2000 > $OUT/bench_${TAG}_long.json 2> $OUT/bench_${TAG}_long.err
+python bench.py --config dense --reads 2000000 --cpu-sample 4000 --no-file-to-tree > $OUT/bench_${TAG}_dense.json 2> $OUT/bench_${TAG}_dense.err; tail -c 600 $OUT/bench_${TAG}_dense.err
+python bench.py --config multipool --reads 625000 --cpu-sample 4000 --no-file-to-tree > $OUT/bench_${TAG}_multipool.json 2> $OUT/bench_${TAG}_multipool.err
+python bench.py --config long --reads 1000000 --cpu-sample 2000 --no-file-to-tree > $OUT/bench_${TAG}_long.json 2> $OUT/bench_${TAG}_long.err
 for c in dense multipool long; do python - <<PY
 import json
 try:
