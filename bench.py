@@ -190,6 +190,14 @@ def _run_cli(pythonpath, files, out_dir, extra, timeout):
 REF_COPY = os.path.join(ROOT, "baseline", "_ref")
 
 
+def bench_config(workload, reads_per_gpu, search_len, k_index):
+    """The `config` object of the JSON line, identical in the two arms for one workload."""
+    return {"workload": workload, "description": WORKLOADS[workload]["desc"], "reads_per_gpu": int(reads_per_gpu),
+            "search_len": int(search_len), "k_index": int(k_index), "dereplicate": "best", "trim": "barcodes",
+            "l2": "GPU arm: L2 flushed (512 MB memset) before every timed step, inputs resident in HBM for `value` and in "
+                  "pinned host memory for `e2e`; CPU arm: a FASTQ file in the page cache"}
+
+
 def run_reference(args):
     """Reference arm: the UNMODIFIED reference CLI (baseline/_ref, a git-ignored copy of /root/reference made by
     baseline/make_ref.py) run as `python -m specimux.cli ... -F -t <all host cores>` over the stand-ins for its
@@ -205,8 +213,9 @@ def run_reference(args):
     n_runs = args.warmup + args.steps
     budget_s = 150.0                       # the whole arm should end within a few minutes
     ds_small = dataset(args.config, 64, 0)
-    config = {"workload": args.config, "description": wl["desc"], "reads_per_gpu": wl["reads"], "search_len": ds_small.search_len,
-              "dereplicate": "best", "trim": "barcodes"}
+    from oracle import pipeline as orc
+    k_index = orc.setup_params(orc.Tables(ds_small.primers, ds_small.specimens), search_len=ds_small.search_len).max_dist_index
+    config = bench_config(args.config, args.reads or wl["reads"], ds_small.search_len, k_index)
     if have_ref:
         pythonpath = [os.path.join(ROOT, "oracle", "standins"), os.path.join(REF_COPY, "src"), ROOT]
         flags = ["-t", str(cores), "--disable-prefilter"]
@@ -477,11 +486,10 @@ def main():
             "metric": "reads/sec demuxed (whole box)", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.config, "description": wl["desc"], "reads_per_gpu": n_reads,
-                       "search_len": ds.search_len, "k_index": k_idx, "dereplicate": "best", "trim": "barcodes",
-                       "resident_sub_batches": args.split,
-                       "l2": "L2 flushed (512 MB memset) before every timed step; %.0f MB packed reads resident"
-                             % (batch.h2d_bytes / 1e6)},
+            # the same object in both arms (run_reference builds it through the same helper)
+            "config": bench_config(args.config, n_reads, ds.search_len, k_idx),
+            "l2_note": "%.0f MB packed reads resident, L2 flushed by a 512 MB memset before every timed step"
+                       % (batch.h2d_bytes / 1e6),
             "gcups": gcups, "cells_per_read": (cells[0] + cells[1]) / n_reads,
             "stage_ms": {"stage_windows": st[0], "primer_search": st[1], "barcode_search": st[2], "select": st[3]},
             "wall_ms_per_step": wall_ms,
