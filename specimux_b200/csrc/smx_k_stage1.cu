@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(2 * kStageBlock) k_stage_windows(SMX_KARGS, u3
     const u32 *src2 = tiled ? s_src : b.packed2;
     const u64 origin = tiled ? w0 : 0;
     const int strand = (int)threadIdx.y;
-    for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, read, strand, w2, src2, origin);
+    stage_windows_thread(t, b, read, strand, src2, origin);
 }
 
 constexpr int kFinishBlock = 256;

@@ -54,14 +54,32 @@ SMX_HD bool sliced_eligible(const Tables &t, const Batch &b, u32 read) {
 // `src2` / `src2_origin`: where the read's 2-bit words are read from -- src2[read_word0(read) - src2_origin + i];
 // the packed buffer itself (b.packed2, origin 0) or a block's shared-memory copy of its reads' words (origin =
 // first word of the block's first read).
-SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int strand, int w2, const u32 *src2, u64 src2_origin) {
-    const int n = (int)b.lengths[read];
-    const Geo g = make_geo(n, t.L);
+// What every 16-symbol word of one (read, strand) shares: length, window geometry, where the read's 2-bit words start.
+struct StageCtx {
+    int n;
+    Geo g;
+    bool flagged, want4;            // want4: the read also gets 4-bit windows (it is off the sliced path)
+    const u32 *src;                 // the read's first 2-bit word inside src2
+};
+
+SMX_HD StageCtx stage_ctx(const Tables &t, const Batch &b, u32 read, const u32 *src2, u64 src2_origin) {
+    StageCtx c;
+    c.n = (int)b.lengths[read];
+    c.g = make_geo(c.n, t.L);
+    c.flagged = read_is_flagged(b, read);
+    c.want4 = c.flagged || !(t.sliced && c.n >= t.L);
+    c.src = src2 + (read_word0(b, read) - src2_origin);
+    return c;
+}
+
+SMX_HD void stage_window_word(const Tables &t, const Batch &b, const StageCtx &c, u32 read, int strand, int w2) {
+    const int n = c.n;
+    const Geo &g = c.g;
     u32 *wlo = b.win + ((u64)strand * t.wpw + 2 * w2) * b.n_pad + read;
     const bool has_hi = 2 * w2 + 1 < t.wpw;
     int valid = g.wl - 16 * w2;
     valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
-    if (!read_is_flagged(b, read)) {
+    if (!c.flagged) {
         // fast path: the staged symbols are one contiguous run of the 2-bit stream (the tail of the
         // read for strand 0, its head read backwards and complemented for strand 1)
         u32 v = 0;
@@ -69,14 +87,14 @@ SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int str
             const int x0 = g.woff + 16 * w2;                  // strand coordinate of symbol 0
             const int first = strand ? (n - 1 - x0) - 15 : stored_pos(b, x0, n);   // stored index of the lowest base needed
             const int lo = first < 0 ? 0 : first;
-            const u32 *src = src2 + (read_word0(b, read) - src2_origin) + (u64)(lo >> 4);
+            const u32 *src = c.src + (lo >> 4);
             const u64 pair = (u64)src[0] | ((u64)src[1] << 32);
             v = (u32)(pair >> (2 * (lo & 15)));
             if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below
             if (strand) v = revcomp16(v);
         }
         b.win2[((u64)strand * t.nw2 + w2) * b.n_pad + read] = v;
-        if (t.sliced && n >= t.L) return;                     // sliced read: no 4-bit window (staged_sym reads win2)
+        if (!c.want4) return;                                 // sliced read: no 4-bit window (staged_sym reads win2)
         const int vlo = valid > 8 ? 8 : valid, vhi = valid > 8 ? valid - 8 : 0;
         u32 out = spread2to4(v);
         if (vlo < 8) out |= ~0u << (4 * vlo);
@@ -93,12 +111,20 @@ SMX_HD void stage_window_pair(const Tables &t, const Batch &b, u32 read, int str
         u32 out = 0;
         for (int i = 0; i < 8; ++i) {
             int p = w2 * 16 + h * 8 + i;
-            int c = kSymOther;
-            if (p < g.wl) c = sym_at(b, read, strand, g.woff + p, n);
-            out |= (u32)c << (4 * i);
+            int c4 = kSymOther;
+            if (p < g.wl) c4 = sym_at(b, read, strand, g.woff + p, n);
+            out |= (u32)c4 << (4 * i);
         }
         wlo[(u64)h * b.n_pad] = out;
     }
+}
+
+// All window words of one (read, strand): the per-read part (length, geometry, flags, stream position) is worked out
+// once -- computing it per 16-symbol word was three quarters of the staging kernel's instructions
+// (profiles/r2_m ncu source view: 147 instructions per word, ~25 of them the word's own).
+SMX_HD void stage_windows_thread(const Tables &t, const Batch &b, u32 read, int strand, const u32 *src2, u64 src2_origin) {
+    const StageCtx c = stage_ctx(t, b, read, src2, src2_origin);
+    for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_word(t, b, c, read, strand, w2);
 }
 
 SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int p) {

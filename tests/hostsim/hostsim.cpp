@@ -168,7 +168,7 @@ extern "C" int hostsim_match_batch(const smx_tables *tb, const smx_params *pr, c
 
     for (u32 r = 0; r < n; ++r)
         for (int s = 0; s < 2; ++s)
-            for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_pair(t, b, r, s, w2, b.packed2, 0);
+            stage_windows_thread(t, b, r, s, b.packed2, 0);
     if (t.sliced)       // forward pass bit-sliced across reads: one "thread" per (group of 32 reads, strand, primer)
         for (int p = 0; p < nP; ++p) {
             RowOffsets ro;
