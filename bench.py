@@ -156,7 +156,16 @@ def _write_fastq(path, ds, n):
 
 def _workload_files(config, ds, n):
     """primers.fasta / specimens.txt / reads.fastq of the first n reads under /tmp (shared by the two arms)."""
-    d = "/tmp/smx_bench_files_%s_%d" % (config, n)
+    # tmpfs when the box has one with room (both arms, input and output tree): on the GPU boxes /tmp sits on a virtual
+    # ext4 disk whose journal / write-back adds up to +-2 s to a 0.5 s run (profiles/r2_o_file_to_tree.md)
+    base = "/tmp"
+    try:
+        import shutil
+        if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (16 << 30):
+            base = "/dev/shm"
+    except OSError:
+        pass
+    d = "%s/smx_bench_files_%s_%d" % (base, config, n)
     os.makedirs(d, exist_ok=True)
     files = [os.path.join(d, f) for f in ("primers.fasta", "specimens.txt", "reads.fastq")]
     if not all(os.path.exists(f) for f in files):
@@ -240,7 +249,7 @@ def run_reference(args):
                 walls.append(wall)
         kind = "reference"
         what = ("unmodified reference CLI (baseline/_ref: specimux 0.7.0 `python -m specimux.cli -F -t %d --disable-prefilter`, "
-                "FASTQ file of the first %d reads -> output tree) over stand-ins for edlib (C restatement), Bio and "
+                "FASTQ file of the first %d reads -> output tree, both on tmpfs when /dev/shm has room) over stand-ins for edlib (C restatement), Bio and "
                 "pybloomfilter; timed by the CLI's own 'Elapsed time' clock; the prefilter is off because its stand-in is a "
                 "Python set whose build takes minutes (result-neutral on A/C/G/T reads, 18 %% faster when cached)" % (cores, sample))
     else:
@@ -284,8 +293,9 @@ def file_to_tree(args, ds, n_reads, n_gpus):
     return {"value": n_done / el, "unit": "reads/s", "n_gpus": n_gpus, "reads": n_done, "elapsed_s": el, "process_wall_s": wall,
             "elapsed_s_runs": [r[1] for r in runs],
             "fastq_bytes": size, "fastq_gbs": size / el / 1e9,
-            "api": "python -m specimux.cli primers.fasta specimens.txt reads.fastq -F -O <dir> -t %d (native reader / packer, "
-                   "smx_match_batch per 65,536-read batch, native tree writer)" % n_gpus}
+            "medium": "tmpfs (/dev/shm)" if d.startswith("/dev/shm") else "local disk (/tmp), page cache",
+            "api": "python -m specimux.cli primers.fasta specimens.txt reads.fastq -F -O <dir> -t %d (native parallel reader / "
+                   "packer, smx_match_batch per byte-range chunk, native tree writer)" % n_gpus}
 
 
 def main():

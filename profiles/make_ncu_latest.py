@@ -21,12 +21,19 @@ def main(path, capture, lib_path=None):
     names, units = rows[hdr], rows[hdr + 1]
     col = {n: i for i, n in enumerate(names)}
     out = {}
+    seen_stage = False
     for r in rows[hdr + 2:]:
         if len(r) != len(names):
             continue
         kname = r[col["Kernel Name"]]
         key = next((k for pat, k in NAMES if pat in kname), None)
         if key is None:
+            continue
+        if key == "stage_windows":          # ONE step: from the first window staging to just before the next one
+            if seen_stage:
+                break
+            seen_stage = True
+        if not seen_stage:
             continue
 
         def val(metric, scale_unit=True):

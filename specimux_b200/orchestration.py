@@ -351,6 +351,7 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
 
     fmt = detect_file_format(args.sequence_file)
     args.isfastq = fmt == "fastq"
+    t_setup0 = timeit.default_timer()
     if n_gpus > 1:
         # device contexts come up side by side (each is ~0.5 s of driver work)
         from concurrent.futures import ThreadPoolExecutor
@@ -387,6 +388,7 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
             job.batch = PackedBatch.reserve(reads_hint, parameters.search_len)
             matchers[0].reserve_results(job.pool, reads_hint, compact="wire")
             free.put(job)
+    setup_s = timeit.default_timer() - t_setup0
     gpu_q = [queue.Queue() for _ in range(n_gpus)]
     errors = []
     counts = [0, 0]
@@ -562,7 +564,7 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
         busy["write"] += clock() - t0
     if os.environ.get("SMX_IO_TRACE"):
         logging.info("I/O pipeline busy seconds (summed over threads): " + ", ".join("%s %.3f" % kv for kv in busy.items()) +
-                     "; %d parser thread(s), %d GPU(s)" % (n_parsers, n_gpus))
+                     "; %d parser thread(s), %d GPU(s); set-up (device context(s), pinned buffers, writer) %.3f s before the first read" % (n_parsers, n_gpus, setup_s))
     if errors:
         raise errors[0]
     return counts[0], counts[1]

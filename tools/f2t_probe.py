@@ -8,7 +8,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench  # noqa: E402
+import bench  # noqa: E402  (bench._workload_files puts the files on tmpfs when there is room)
 
 # arguments: GPU counts, and VAR=value settings tried one after the other on top of the environment ("-" = none)
 gpus = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1]
