@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspecimux_b200.so")
+# SMX_LIB_PATH: an alternative build of the same library (A/B of compile-time knobs, tools/ab_round.sh)
+LIB_PATH = os.environ.get("SMX_LIB_PATH") or os.path.join(_HERE, "libspecimux_b200.so")
 
 SMX_OK, SMX_ERR_ARG, SMX_ERR_CUDA, SMX_ERR_NO_DEVICE, SMX_ERR_CAPACITY, SMX_ERR_INTERNAL = range(6)
 TRIM_CODES = {"none": 0, "primers": 1, "barcodes": 2, "tails": 3}

@@ -1,4 +1,5 @@
 // smx_k_select.cu -- stage 3 (selection, scan + compaction, record packing) and the small utility kernels.
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "smx_device.cuh"
@@ -12,8 +13,10 @@ constexpr int kInlineRecords = 4;
 // selection routine (slot digests computed on the fly, no grouping, small register footprint so
 // the dependent global loads are hidden by occupancy).  Reads that need the general routine
 // (several equal-best candidates, tied barcodes, TAILS trimming) are appended to defer_list.
+// 16 resident blocks asked for = at most 32 registers: the kernel lives on warps in flight (measured on config 2:
+// 52 registers 89 us, 38 registers 79 us, 32 registers 76 us; profiles/r2_u_ab.md).
 template <int MAXP>
-__global__ void __launch_bounds__(128) k_select_fast(SMX_KARGS) {
+__global__ void __launch_bounds__(128, 16) k_select_fast(SMX_KARGS) {
     // (loading all slots ahead -- select_read_impl<true, NP> -- was measured SLOWER here: 93 vs 80 us, 62 vs 38
     // registers; the kernel lives on occupancy, profiles/r2_l_ab.md)
     constexpr int NP = 0;

@@ -1,5 +1,6 @@
 // smx_k_stage1.cu -- stage 0 / 1 kernels other than the sliced forward pass: window staging, primer finish /
 // classic search, long primers, start recovery.  Per-thread logic lives in smx_kernels.cuh.
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "smx_device.cuh"
@@ -19,7 +20,11 @@ namespace smx {
 constexpr int kStageBlock = 128;                // reads per block; blockDim = (kStageBlock, 2 strands)
 
 // tile_words: capacity of the dynamic shared-memory tile in words (0 = always read the stream directly)
-__global__ void __launch_bounds__(2 * kStageBlock) k_stage_windows(SMX_KARGS, u32 tile_words) {
+// 8 resident blocks = 32 registers (was 40 / 6 blocks): 47 -> 42 us on config 2 (profiles/r2_u_ab.md)
+#ifndef SMX_STAGE_MINB
+#define SMX_STAGE_MINB 8
+#endif
+__global__ void __launch_bounds__(2 * kStageBlock, SMX_STAGE_MINB) k_stage_windows(SMX_KARGS, u32 tile_words) {
     extern __shared__ u32 s_src[];
     const Tables &t = c_tables;
     const u32 r0 = blockIdx.x * kStageBlock;
@@ -50,8 +55,10 @@ constexpr int kFinishBlock = 256;
 // strands keeps the warp full through the start-recovery pass (a thread per (read, strand, primer) leaves half
 // the lanes idle there, which is why the first form ran it as a separate kernel over the compact entry lists:
 // 84 us, 30 % of its instructions per-column window loads -- profiles/r2_a_ncu_head.md).
+// Six resident blocks asked for = at most 40 registers (measured on config 2: 56 registers 136 us, 48 registers 127 us,
+// 40 registers 124 us, 32 registers with spills 126 us; profiles/r2_u_ab.md).
 template <typename W>
-__global__ void __launch_bounds__(kFinishBlock) k_primer_finish(SMX_KARGS, int with_start) {
+__global__ void __launch_bounds__(kFinishBlock, 6) k_primer_finish(SMX_KARGS, int with_start) {
     // grid: x over reads, y = primer
     __shared__ u64 s_peq[3][16];
     __shared__ u32 s_wtot[2][kFinishBlock / 32 + 1];

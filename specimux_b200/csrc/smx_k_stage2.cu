@@ -17,8 +17,18 @@ namespace smx {
 // shared memory.  MF > 0: the barcode length is a template argument (the unrolled row sequence then has no early
 // exit: registers are renamed from row to row without moves and the carry-save counter's bookkeeping folds
 // away -- 2,944 instead of 3,960 instructions for K = 3, three words, 13 rows); MF = 0: any length.
+// Resident blocks per SM the register allocation aims for (knobs of the build for A/B runs: -DSMX_BT_MINB1 one-word
+// tasks, -DSMX_BT_MINB3 multi-word tasks).  Measured on config 2 (profiles/r2_u_ab.md): one-word task 91 registers
+// (5 blocks) -> 64 registers (8 blocks, a few spills): stage 2 200 -> 194 us; three-word task: 128 registers (4 blocks)
+// kept, 96 registers with 140 B of spills was no faster.
+#ifndef SMX_BT_MINB1
+#define SMX_BT_MINB1 8
+#endif
+#ifndef SMX_BT_MINB3
+#define SMX_BT_MINB3 4
+#endif
 template <int K, int NWQ, int MF>
-__global__ void __launch_bounds__(128) k_barcode_task(SMX_KARGS, const unsigned short *task_list, int n_list) {
+__global__ void __launch_bounds__(128, NWQ == 1 ? SMX_BT_MINB1 : SMX_BT_MINB3) k_barcode_task(SMX_KARGS, const unsigned short *task_list, int n_list) {
     constexpr int S = NWQ == 1 ? 1 : NWQ == 2 ? 2 : 4;
     constexpr int kRows = NWQ == 1 ? SMX_MAX_PATTERN : 16;      // multi-word tasks only exist for m + K <= 16
     __shared__ __align__(16) u32 s_tab[kRows * 16 * S];

@@ -72,11 +72,10 @@ SMX_HD StageCtx stage_ctx(const Tables &t, const Batch &b, u32 read, const u32 *
     return c;
 }
 
-SMX_HD void stage_window_word(const Tables &t, const Batch &b, const StageCtx &c, u32 read, int strand, int w2) {
+// w2p: the (strand, w2) word of this read in win2 (the caller steps it by n_pad per word: no 64-bit multiply per word).
+SMX_HD void stage_window_word(const Tables &t, const Batch &b, const StageCtx &c, u32 read, int strand, int w2, u32 *w2p) {
     const int n = c.n;
     const Geo &g = c.g;
-    u32 *wlo = b.win + ((u64)strand * t.wpw + 2 * w2) * b.n_pad + read;
-    const bool has_hi = 2 * w2 + 1 < t.wpw;
     int valid = g.wl - 16 * w2;
     valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
     if (!c.flagged) {
@@ -93,8 +92,10 @@ SMX_HD void stage_window_word(const Tables &t, const Batch &b, const StageCtx &c
             if (first < 0) v <<= 2 * (-first);                // bases before the read start: masked below
             if (strand) v = revcomp16(v);
         }
-        b.win2[((u64)strand * t.nw2 + w2) * b.n_pad + read] = v;
+        *w2p = v;
         if (!c.want4) return;                                 // sliced read: no 4-bit window (staged_sym reads win2)
+        u32 *wlo = b.win + ((u64)strand * t.wpw + 2 * w2) * b.n_pad + read;
+        const bool has_hi = 2 * w2 + 1 < t.wpw;
         const int vlo = valid > 8 ? 8 : valid, vhi = valid > 8 ? valid - 8 : 0;
         u32 out = spread2to4(v);
         if (vlo < 8) out |= ~0u << (4 * vlo);
@@ -106,7 +107,9 @@ SMX_HD void stage_window_word(const Tables &t, const Batch &b, const StageCtx &c
         }
         return;
     }
-    b.win2[((u64)strand * t.nw2 + w2) * b.n_pad + read] = 0;      // flagged reads take the classic search
+    u32 *wlo = b.win + ((u64)strand * t.wpw + 2 * w2) * b.n_pad + read;
+    const bool has_hi = 2 * w2 + 1 < t.wpw;
+    *w2p = 0;                                                     // flagged reads take the classic search
     for (int h = 0; h < (has_hi ? 2 : 1); ++h) {
         u32 out = 0;
         for (int i = 0; i < 8; ++i) {
@@ -124,7 +127,8 @@ SMX_HD void stage_window_word(const Tables &t, const Batch &b, const StageCtx &c
 // (profiles/r2_m ncu source view: 147 instructions per word, ~25 of them the word's own).
 SMX_HD void stage_windows_thread(const Tables &t, const Batch &b, u32 read, int strand, const u32 *src2, u64 src2_origin) {
     const StageCtx c = stage_ctx(t, b, read, src2, src2_origin);
-    for (int w2 = 0; w2 < t.nw2; ++w2) stage_window_word(t, b, c, read, strand, w2);
+    u32 *w2p = b.win2 + (u64)strand * t.nw2 * b.n_pad + read;
+    for (int w2 = 0; w2 < t.nw2; ++w2, w2p += b.n_pad) stage_window_word(t, b, c, read, strand, w2, w2p);
 }
 
 SMX_HD int staged_sym(const Tables &t, const Batch &b, u32 read, int strand, int p) {
