@@ -7,7 +7,10 @@
 namespace smx {
 
 // Sliced primer search: one thread per (group of 32 reads, strand) for one primer of length M.
-constexpr int kSlicedBlock = 64;        // small blocks: equal-length tasks, let the block scheduler balance the SMs
+#ifndef SMX_SLICED_BLOCK
+#define SMX_SLICED_BLOCK 64
+#endif
+constexpr int kSlicedBlock = SMX_SLICED_BLOCK;        // small blocks: equal-length tasks, let the block scheduler balance the SMs
 template <int M>
 __global__ void __launch_bounds__(kSlicedBlock) k_primer_sliced(SMX_KARGS, int primer, const __grid_constant__ RowOffsets ro, int degenerate) {
     __shared__ u32 s_planes[(kSlicedCodes + 48) * kSlicedBlock];

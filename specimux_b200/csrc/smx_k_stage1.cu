@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(2 * kStageBlock, SMX_STAGE_MINB) k_stage_windo
     stage_windows_thread(t, b, read, strand, src2, origin);
 }
 
-constexpr int kFinishBlock = 256;
+#ifndef SMX_FINISH_BLOCK
+#define SMX_FINISH_BLOCK 256
+#endif
+constexpr int kFinishBlock = SMX_FINISH_BLOCK;
 
 // Stage 1 finish: one thread per (read, primer) closes BOTH strands' searches -- eligible reads decode the column
 // histories of the sliced pass, the others run the classic single-word search -- allocates the work entries
@@ -58,7 +61,7 @@ constexpr int kFinishBlock = 256;
 // Six resident blocks asked for = at most 40 registers (measured on config 2: 56 registers 136 us, 48 registers 127 us,
 // 40 registers 124 us, 32 registers with spills 126 us; profiles/r2_u_ab.md).
 template <typename W>
-__global__ void __launch_bounds__(kFinishBlock, 6) k_primer_finish(SMX_KARGS, int with_start) {
+__global__ void __launch_bounds__(kFinishBlock, 1536 / kFinishBlock) k_primer_finish(SMX_KARGS, int with_start) {
     // grid: x over reads, y = primer
     __shared__ u64 s_peq[3][16];
     __shared__ u32 s_wtot[2][kFinishBlock / 32 + 1];
