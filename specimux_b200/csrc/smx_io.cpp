@@ -438,6 +438,67 @@ struct Complement {
 };
 const Complement kComplement;
 
+// dst[j] = tab[src_last[-j]] (reverse complement) / dst[j] = src_last[-j] (reverse copy), n bytes; src_last points at
+// the LAST byte of the source run.  Half the reads of a mixed-orientation run are written reversed, byte by byte in
+// the first form of the writer; on x86-64 with SSSE3 sixteen bytes go at a time: the reversal is one byte shuffle, the
+// complement two 16-entry table look-ups on the low five bits of a letter (A..Z / a..z keep their case bits; bytes
+// outside 0x40..0x7F pass through), the same mapping as kComplement.
+void reverse_complement_scalar(char *dst, const unsigned char *src_last, size_t n) {
+    const unsigned char *tab = kComplement.t;
+    for (size_t j = 0; j < n; ++j) dst[j] = (char)tab[src_last[-(long long)j]];
+}
+void reverse_copy_scalar(char *dst, const char *src_last, size_t n) {
+    for (size_t j = 0; j < n; ++j) dst[j] = src_last[-(long long)j];
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("ssse3"))) void reverse_complement_ssse3(char *dst, const unsigned char *src_last, size_t n) {
+    // index = byte & 0x1F: 0 '@', 1..26 'A'..'Z', 27..31 '[' .. '_'
+    //                          @   A   B   C   D   E   F   G   H   I   J   K   L   M   N   O
+    const __m128i lo = _mm_setr_epi8(0, 20, 22, 7, 8, 5, 6, 3, 4, 9, 10, 13, 12, 11, 14, 15);
+    //                          P   Q   R   S   T   U   V   W   X   Y   Z   [   \   ]   ^   _
+    const __m128i hi = _mm_setr_epi8(16, 17, 25, 19, 1, 1, 2, 23, 24, 18, 26, 27, 28, 29, 30, 31);
+    const __m128i rev = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m128i m1f = _mm_set1_epi8(0x1F), m0f = _mm_set1_epi8(0x0F), me0 = _mm_set1_epi8((char)0xE0),
+                  mc0 = _mm_set1_epi8((char)0xC0), v40 = _mm_set1_epi8(0x40), v10 = _mm_set1_epi8(0x10);
+    size_t j = 0;
+    for (; j + 16 <= n; j += 16) {
+        __m128i v = _mm_loadu_si128((const __m128i *)(src_last - j - 15));
+        v = _mm_shuffle_epi8(v, rev);
+        const __m128i idx = _mm_and_si128(v, m1f);
+        const __m128i from_lo = _mm_shuffle_epi8(lo, _mm_and_si128(idx, m0f));
+        const __m128i from_hi = _mm_shuffle_epi8(hi, _mm_and_si128(idx, m0f));
+        const __m128i is_hi = _mm_cmpeq_epi8(_mm_and_si128(idx, v10), v10);
+        const __m128i mapped = _mm_or_si128(_mm_and_si128(is_hi, from_hi), _mm_andnot_si128(is_hi, from_lo));
+        const __m128i letter = _mm_cmpeq_epi8(_mm_and_si128(v, mc0), v40);          // 0x40..0x7F
+        const __m128i out = _mm_or_si128(_mm_and_si128(letter, _mm_or_si128(mapped, _mm_and_si128(v, me0))),
+                                         _mm_andnot_si128(letter, v));
+        _mm_storeu_si128((__m128i *)(dst + j), out);
+    }
+    reverse_complement_scalar(dst + j, src_last - j, n - j);
+}
+__attribute__((target("ssse3"))) void reverse_copy_ssse3(char *dst, const char *src_last, size_t n) {
+    const __m128i rev = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    size_t j = 0;
+    for (; j + 16 <= n; j += 16)
+        _mm_storeu_si128((__m128i *)(dst + j), _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(src_last - j - 15)), rev));
+    reverse_copy_scalar(dst + j, src_last - j, n - j);
+}
+const bool kHaveSsse3 = __builtin_cpu_supports("ssse3") && !getenv("SMX_IO_NO_SIMD");     // (switch for A/B runs)
+#else
+const bool kHaveSsse3 = false;
+void reverse_complement_ssse3(char *dst, const unsigned char *src_last, size_t n) { reverse_complement_scalar(dst, src_last, n); }
+void reverse_copy_ssse3(char *dst, const char *src_last, size_t n) { reverse_copy_scalar(dst, src_last, n); }
+#endif
+
+inline void reverse_complement_into(char *dst, const unsigned char *src_last, size_t n) {
+    if (kHaveSsse3) reverse_complement_ssse3(dst, src_last, n); else reverse_complement_scalar(dst, src_last, n);
+}
+inline void reverse_copy_into(char *dst, const char *src_last, size_t n) {
+    if (kHaveSsse3) reverse_copy_ssse3(dst, src_last, n); else reverse_copy_scalar(dst, src_last, n);
+}
+
 // Growable byte buffer without value-initialisation (std::vector<char>::resize zero-fills what the
 // formatter overwrites straight away; realloc can also remap large blocks instead of copying them).
 struct Bytes {
@@ -649,9 +710,7 @@ void smx_writer::format(Bytes &c, const smx_block &blk, const smx_record &rec, c
     char *dst = c.grow(2 * n_out + 4);
     if (rec.reverse) {
         // oriented read = reverse complement; its slice [a, b) = original (len-b .. len-a] reversed
-        const unsigned char *src = (const unsigned char *)seq + (len - (long long)a) - 1;
-        const unsigned char *tab = kComplement.t;
-        for (size_t j = 0; j < n_out; ++j) dst[j] = (char)tab[src[-(long long)j]];
+        reverse_complement_into(dst, (const unsigned char *)seq + (len - (long long)a) - 1, n_out);
     } else if (n_out) {
         memcpy(dst, seq + a, n_out);
     }
@@ -661,8 +720,7 @@ void smx_writer::format(Bytes &c, const smx_block &blk, const smx_record &rec, c
         *dst++ = '+'; *dst++ = '\n';
         if (!qual) memset(dst, 'I', n_out);          // get_quality_seq: [40] * len (alignment.py:52-56)
         else if (rec.reverse) {
-            const char *src = qual + (len - (long long)a) - 1;
-            for (size_t j = 0; j < n_out; ++j) dst[j] = src[-(long long)j];
+            reverse_copy_into(dst, qual + (len - (long long)a) - 1, n_out);
         } else if (n_out) memcpy(dst, qual + a, n_out);
         dst += n_out;
         *dst++ = '\n';
