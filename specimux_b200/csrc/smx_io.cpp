@@ -612,6 +612,11 @@ struct smx_writer {
         std::lock_guard<std::mutex> g(err_mu);
         if (first_error == SMX_IO_OK) { first_error = code; first_error_msg = msg; }
     }
+    // first error seen so far (workers of a deferred call may still be reporting: read under the lock)
+    int error_status() {
+        std::lock_guard<std::mutex> g(err_mu);
+        return first_error == SMX_IO_OK ? SMX_IO_OK : fail(first_error, "%s", first_error_msg.c_str());
+    }
 
     void flush(OutFile &f) {
         if (f.buf.empty()) return;
@@ -909,8 +914,7 @@ int smx_writer::write_planned(const smx_block *blk, const smx_record *recs, uint
             w->cur_blk = nullptr; w->cur_recs = nullptr; w->cur_plans = nullptr; w->cur_tasks = nullptr;
         }
     }
-    if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());
-    return SMX_IO_OK;
+    return w->error_status();
 }
 
 extern "C" {
@@ -926,8 +930,7 @@ int smx_writer_write(smx_writer *w, const smx_block *blk, const smx_record *recs
 int smx_writer_wait(smx_writer *w) {
     if (!w) return SMX_IO_OK;
     w->wait_in_flight();
-    if (w->first_error != SMX_IO_OK) return fail(w->first_error, "%s", w->first_error_msg.c_str());
-    return SMX_IO_OK;
+    return w->error_status();
 }
 
 
