@@ -124,9 +124,13 @@ struct HostTables {
             if (m > 32) t.use64 = 1;
             t.p_sw[p] = 0; t.p_long[p] = -1;
             if (m > SMX_MAX_PATTERN) {
-                // warp-cooperative multi-word search: lanes per problem = power of two >= ceil(m/32), at least 4
-                int sw = 4;
-                while (32 * sw < m) sw *= 2;
+                // warp-cooperative multi-word search: lanes per problem = the narrowest segment width >= ceil(m/32)
+                // that gives a different number of reads per warp (3 -> 10 reads, 4 -> 8, 5 -> 6, 6 -> 5, 8 -> 4,
+                // 10 -> 3, 16 -> 2, 32 -> 1)
+                const int words = (m + 31) / 32;
+                static const int kWidths[] = {3, 4, 5, 6, 8, 10, 16, 32};
+                int sw = 32;
+                for (int w : kWidths) if (w >= words) { sw = w; break; }
                 t.p_sw[p] = (unsigned char)sw; t.p_long[p] = (int)peq_long.size();
                 size_t base = peq_long.size();
                 peq_long.resize(base + (size_t)3 * 16 * sw, 0);

@@ -173,11 +173,13 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
         for (int i = threadIdx.x; i < 3 * 16 * SW; i += blockDim.x) s_peq[i / (16 * SW)][i % (16 * SW)] = src[i];
     }
     __syncthreads();
+    constexpr int kReads = LongSeg<SW>::kReads;          // reads (whole segments) per warp; lanes beyond them idle
     const int lane = threadIdx.x & 31, sub = lane % SW;
     const bool top = sub == SW - 1;
     const int strand = (int)blockIdx.y;
-    const u32 read = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) / SW);
-    const bool valid = read < b.n_reads;
+    const u32 warp_global = (u32)(((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const u32 read = warp_global * (u32)kReads + (u32)(lane / SW);
+    const bool valid = lane < kReads * SW && read < b.n_reads;
     const int m = t.p_len[primer], k = t.p_k[primer];
     const u32 slot = slot_index(t, strand, primer);
     const int n = valid ? (int)b.lengths[read] : 0;
@@ -190,33 +192,48 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
     const int p_begin = g.start, cols = valid ? g.wl - g.start : 0;
     const u32 *wwin = b.win + (u64)strand * t.wpw * b.n_pad + (valid ? read : 0);     // this read's 4-bit window words
     u32 wcur = 0;
-    int wcur_idx = -1;
     if (valid && top) for (int w = 0; w < t.mw; ++w) { emask[(u64)w * b.n_pad] = 0; imask[(u64)w * b.n_pad] = 0; }
     u32 Pv = ~0u, Mv = 0u;
     int score = m, best = m + 1;
     {
+        // The warp walks the window positions p in step (the same p in every lane; a read whose window starts later or
+        // ends earlier -- short reads -- sits those columns out), eight columns = one 4-bit window word at a time, so
+        // the word load, the history-word stores and the column's bit are uniform across the warp and every lane runs
+        // the same straight-line code per column: the running best / equal / improved bits are plain selects that
+        // only mean something in a segment's top lane.  The first form branched per column for the word load, for the
+        // top lane's bookkeeping and for idle columns: ~100 executed instructions per lane and column in the worst
+        // path (profiles/r1_v30_long_primer_ncu.md: 72 on average).
+        const int p_end = p_begin + cols;
+        const int p_lo = __reduce_min_sync(0xffffffffu, cols > 0 ? p_begin : 0x7fffffff);
+        const int p_hi = __reduce_max_sync(0xffffffffu, cols > 0 ? p_end : 0);
         u32 eqw = 0, imw = 0;
-        int cur = p_begin >> 5;
-        const int maxcols = __reduce_max_sync(0xffffffffu, cols);
-        for (int j = 0; j < maxcols; ++j) {
-            const bool active = j < cols;
-            const int p = p_begin + j;
-            int c = kSymOther;
-            if (active) {                                   // one window word per 8 columns, not one load per column
-                if ((p >> 3) != wcur_idx) { wcur_idx = p >> 3; wcur = wwin[(u64)wcur_idx * b.n_pad]; }
-                c = (int)((wcur >> (4 * (p & 7))) & 15u);
+        for (int p0 = p_lo & ~7; p0 < p_hi; p0 += 8) {
+            const bool touches = p0 + 8 > p_begin && p0 < p_end;
+            const u32 w = touches ? wwin[(u64)(p0 >> 3) * b.n_pad] : 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int p = p0 + q;
+                const bool active = p >= p_begin && p < p_end;
+                const int c = active ? (int)((w >> (4 * q)) & 15u) : kSymOther;
+                const u32 sPv = Pv, sMv = Mv;
+                const int d = long_step<SW, false>(s_peq[0][c * SW + sub], Pv, Mv, sub, lane);
+                Pv = active ? Pv : sPv;
+                Mv = active ? Mv : sMv;
+                const int ns = score + d;
+                const bool improved = active && ns < best;
+                score = active ? ns : score;
+                best = improved ? ns : best;
+                const u32 bit = 1u << (p & 31);
+                imw |= improved ? bit : 0u;
+                eqw |= (active && score == best) ? bit : 0u;
             }
-            const u32 sPv = Pv, sMv = Mv;
-            const int d = long_step<SW, false>(s_peq[0][c * SW + sub], Pv, Mv, sub, lane);
-            if (!active) { Pv = sPv; Mv = sMv; }
-            else if (top) {
-                if ((p >> 5) != cur) { emask[(u64)cur * b.n_pad] = eqw; imask[(u64)cur * b.n_pad] = imw; eqw = imw = 0; cur = p >> 5; }
-                score += d;
-                if (score < best) { best = score; imw |= 1u << (p & 31); }
-                if (score == best) eqw |= 1u << (p & 31);
+            if ((p0 & 31) == 24 || p0 + 8 >= p_hi) {        // uniform: the 32-column history words are complete
+                if (top && valid && p0 + 8 > p_begin && (p0 & ~31) < p_end) {
+                    emask[(u64)(p0 >> 5) * b.n_pad] = eqw; imask[(u64)(p0 >> 5) * b.n_pad] = imw;
+                }
+                eqw = imw = 0;
             }
         }
-        if (valid && top && cols > 0) { emask[(u64)cur * b.n_pad] = eqw; imask[(u64)cur * b.n_pad] = imw; }
     }
     // ---- hit bookkeeping (top lane), then the segment learns (nloc, first, best)
     int nloc = 0, first = 0;
@@ -241,16 +258,15 @@ __global__ void __launch_bounds__(128) k_primer_long(SMX_KARGS, int primer) {
         int rs = m, last = m - 1;
         for (int j = 0; j < maxr; ++j) {
             const bool active = j < rcols;
-            int c = kSymOther;
-            if (active) {
-                const int p = first - j;
-                if ((p >> 3) != wcur_idx) { wcur_idx = p >> 3; wcur = wwin[(u64)wcur_idx * b.n_pad]; }
-                c = (int)((wcur >> (4 * (p & 7))) & 15u);
-            }
+            const int p = first - j;
+            if (active && (j == 0 || (p & 7) == 7)) wcur = wwin[(u64)(p >> 3) * b.n_pad];      // walking down: a new word at its top symbol
+            const int c = active ? (int)((wcur >> (4 * (p & 7))) & 15u) : kSymOther;
             const u32 sPv = Pv, sMv = Mv;
             const int d = long_step<SW, true>(s_peq[1][c * SW + sub], Pv, Mv, sub, lane);
-            if (!active) { Pv = sPv; Mv = sMv; }
-            else if (top) { rs += d; if (rs == best) last = j; }
+            Pv = active ? Pv : sPv;
+            Mv = active ? Mv : sMv;
+            rs = active ? rs + d : rs;
+            last = (active && rs == best) ? j : last;
         }
         if (valid && top && nloc) b.phit[hit_idx].first_start = b.phit[hit_idx].first_end - last;
     }
@@ -317,12 +333,18 @@ cudaError_t launch_primer_finish(const Tables &t, const Batch &b, int with_start
 
 cudaError_t launch_primer_long(const Tables &t, const Batch &b, int primer, cudaStream_t st) {
     const int sw = t.p_sw[primer];
-    dim3 lgrid((unsigned)(((u64)b.n_reads * sw + 127) / 128), 2);
+    const unsigned reads_per_block = 4u * (unsigned)(32 / sw);         // 128 threads = 4 warps of 32 / sw reads each
+    dim3 lgrid((b.n_reads + reads_per_block - 1) / reads_per_block, 2);
     switch (sw) {
+        case 3: k_primer_long<3><<<lgrid, 128, 0, st>>>(t, b, primer); break;
         case 4: k_primer_long<4><<<lgrid, 128, 0, st>>>(t, b, primer); break;
+        case 5: k_primer_long<5><<<lgrid, 128, 0, st>>>(t, b, primer); break;
+        case 6: k_primer_long<6><<<lgrid, 128, 0, st>>>(t, b, primer); break;
         case 8: k_primer_long<8><<<lgrid, 128, 0, st>>>(t, b, primer); break;
+        case 10: k_primer_long<10><<<lgrid, 128, 0, st>>>(t, b, primer); break;
         case 16: k_primer_long<16><<<lgrid, 128, 0, st>>>(t, b, primer); break;
-        default: k_primer_long<32><<<lgrid, 128, 0, st>>>(t, b, primer); break;
+        case 32: k_primer_long<32><<<lgrid, 128, 0, st>>>(t, b, primer); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

@@ -1505,9 +1505,18 @@ SMX_HD void write_entries(const Tables &t, const Batch &b, u32 slot, u32 read, u
 // l set iff a carry enters word l.  One integer addition ripples all segments: the generate bits
 // are injected one position up, the propagate bits let the machine carry run through, and word 0
 // of every segment (never a carry target) is masked out so nothing crosses a segment boundary.
+// Segments need not be a power of two wide: a warp holds 32 / SW whole segments (lanes beyond the last whole segment
+// idle) -- a 150-nt primer is five words, six reads to a warp instead of the four of an eight-lane segment.
 template <int SW> struct LongSeg {
-    static_assert(SW == 4 || SW == 8 || SW == 16 || SW == 32, "segment width");
-    static constexpr u32 kStart = SW == 32 ? 0x00000001u : SW == 16 ? 0x00010001u : SW == 8 ? 0x01010101u : 0x11111111u;
+    static_assert(SW >= 2 && SW <= 32, "segment width");
+    static constexpr int kReads = 32 / SW;                 // whole segments (reads) per warp
+    static constexpr u32 start_mask() {                    // word 0 of every segment, and every idle lane
+        u32 m = 0;
+        for (int l = 0; l < 32; ++l)
+            if (l >= kReads * SW || l % SW == 0) m |= 1u << l;
+        return m;
+    }
+    static constexpr u32 kStart = start_mask();
 };
 
 template <int SW> SMX_HD u32 long_carry_in(u32 G, u32 P) {

@@ -130,7 +130,8 @@ template <int SW> static int check_long_carry(unsigned long long trials) {
 }
 
 extern "C" int hostsim_check_long_carry(unsigned long long trials) {
-    return check_long_carry<4>(trials) | check_long_carry<8>(trials) | check_long_carry<16>(trials) | check_long_carry<32>(trials);
+    return check_long_carry<3>(trials) | check_long_carry<4>(trials) | check_long_carry<5>(trials) | check_long_carry<6>(trials) |
+           check_long_carry<8>(trials) | check_long_carry<10>(trials) | check_long_carry<16>(trials) | check_long_carry<32>(trials);
 }
 
 extern "C" const char *hostsim_last_error(void) { return g_err; }

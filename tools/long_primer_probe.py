@@ -7,6 +7,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("SMX_TEST_SEAM", "1")      # the probe cross-checks 3,000 reads against the kernel simulator
+
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -41,11 +43,11 @@ def main(n_reads=200_000):
         res = m.download()
         cells, wcols = m.last_work()
         print("k (primer thresholds):", k_primers.values(), "k_idx", k_idx)
-        print("matched %d of %d reads; stage-1 kernels (k_primer_search<u64> for ITS4 + k_primer_long<8> for the 150-mer): %.1f us"
-              % (res.n_matched, n_reads, 1000 * kt["primer_finish"]))
+        print("matched %d of %d reads; stage-1 kernels (k_primer_search<u64> for ITS4 + k_primer_long<5> for the 150-mer): %.1f us"
+              % (res.n_matched, n_reads, 1000 * kt.get("primer_finish_start", kt.get("primer_finish", 0.0))))
         print("kernel_ms", {k: round(v, 4) for k, v in kt.items()})
         hw_cells_long = 2 * 150 * 256 * n_reads
-        print("HW cells of the long primer: %.3g -> %.0f GCUPS on that kernel pair" % (hw_cells_long, hw_cells_long / (kt["primer_finish"] * 1e-3) / 1e9))
+        print("HW cells of the long primer: %.3g -> %.0f GCUPS on that kernel pair" % (hw_cells_long, hw_cells_long / (kt.get("primer_finish_start", kt.get("primer_finish", 0.0)) * 1e-3) / 1e9))
         n_sim = 3000
         sub = PackedBatch.from_blob(blob[:int(offs[n_sim])], offs[:n_sim + 1], clip=ds.search_len)
         gpu = m.match(sub)
