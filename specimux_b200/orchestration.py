@@ -399,8 +399,26 @@ def _run_native(args, specimens, parameters, n_gpus: int, prefilter, _binding=No
     slots = {}
     state = {"next_index": 0, "n_chunks": None}
 
+    keep_alive = []
+
     def gpu_worker(dev):
         _lib.bind_thread_to_gpu_numa_node(dev)
+        if _binding is None and os.environ.get("SMX_GPU_WARMUP", "1") != "0":
+            # While the parser threads work on their first chunks this thread has nothing to do: it runs one batch of
+            # `reads_hint` dummy reads so that the device's one-time work -- streams, the lanes' ~100 device buffers at
+            # their final size, pinned staging, lazy loading of every kernel on the path -- is done when the first real
+            # batch arrives instead of inside it (that first call took 0.03 .. 1.0 s, profiles/r2_o_file_to_tree.md).
+            t0 = clock()
+            try:
+                n_w, l_w = reads_hint, 2 * int(parameters.search_len) + 40
+                dummy = PackedBatch.from_blob(b"A" * (n_w * l_w), np.arange(n_w + 1, dtype=np.uint64) * l_w,
+                                              clip=parameters.search_len)
+                pool = {}
+                matchers[dev].match(dummy, reuse=pool, compact="wire")
+                keep_alive.append((dummy, pool))       # released after the run: freeing pinned memory synchronises the device
+            except BaseException:
+                pass                                   # a real batch will surface whatever is wrong
+            busy["warmup"] = busy.get("warmup", 0.0) + clock() - t0
         while True:
             job = gpu_q[dev].get()
             if job is None:
