@@ -148,3 +148,30 @@ def test_simulator_seam_is_closed_outside_the_test_suite(monkeypatch):
     monkeypatch.delenv("SMX_TEST_SEAM", raising=False)
     with pytest.raises(RuntimeError, match="test seam"):
         Matcher(None, binding=object())
+
+
+def test_file_pipeline_starts_one_gpu_per_share_of_input(tmp_path, monkeypatch):
+    """orchestration._gpus_worth_starting: a further GPU per SMX_BYTES_PER_GPU bytes of input, never more than asked
+    for, gzip input counted four-fold, unknown sizes left alone."""
+    import argparse
+    from specimux_b200 import orchestration
+    f = tmp_path / "reads.fastq"
+    f.write_bytes(b"x" * 3000)
+    args = argparse.Namespace(sequence_file=str(f))
+    monkeypatch.setenv("SMX_BYTES_PER_GPU", "1000")
+    assert orchestration._gpus_worth_starting(args, 8) == 3
+    assert orchestration._gpus_worth_starting(args, 2) == 2
+    monkeypatch.setenv("SMX_BYTES_PER_GPU", str(8 << 30))
+    assert orchestration._gpus_worth_starting(args, 8) == 1
+    gz = tmp_path / "reads.fastq.gz"
+    gz.write_bytes(b"x" * 1000)
+    monkeypatch.setenv("SMX_BYTES_PER_GPU", "1000")
+    assert orchestration._gpus_worth_starting(argparse.Namespace(sequence_file=str(gz)), 8) == 4
+    assert orchestration._gpus_worth_starting(argparse.Namespace(sequence_file=str(tmp_path / "missing")), 5) == 5
+
+
+def test_both_bench_arms_build_the_same_config_object():
+    import bench
+    a = bench.bench_config("ont037", 765_000, 80, 3)
+    b = bench.bench_config("ont037", 765000, 80, 3)
+    assert a == b and set(a) == {"workload", "description", "reads_per_gpu", "search_len", "k_index", "dereplicate", "trim", "l2"}
